@@ -1,0 +1,192 @@
+/*
+ * mate_b200.h -- C ABI of the B200-native batched MultiAgentTracking simulator.
+ *
+ * The reference (XuehaiPan/mate) is pure Python and has NO native/FFI layer; its boundary
+ * for the step path is the Python class ``mate.environment.MultiAgentTracking``
+ * (mate/environment.py:288) reached through ``mate.make`` (mate/__init__.py:24-43).  This
+ * header is the C-ABI a binding for that class calls instead of the per-entity Python
+ * loops.  Each entry point cites the reference method it replaces.  The Python binding
+ * (ctypes) that mirrors the reference class on top of it is ``mate_b200/environment.py``;
+ * INTEGRATION.md shows the stub a reference maintainer would add.
+ *
+ * Conventions
+ *   - plain C types only; no torch / CUDA types in signatures (streams are passed as
+ *     ``void*`` holding a ``cudaStream_t``; NULL = legacy default stream);
+ *   - every function returns 0 on success or a negative MateStatus; the message is
+ *     available from mate_b200_last_error() (thread-local);
+ *   - "dev" pointers are device pointers owned by the caller (e.g. PyTorch tensors) on the
+ *     device the handle was created for; "host" pointers are ordinary host memory;
+ *   - batched I/O is row-major [B, N, D] float32 in the reference's feature order
+ *     (mate/environment.py:908-983, mate/constants.py:267-300);
+ *   - a handle is not re-entrant; different handles are independent (one per GPU);
+ *   - step/reset/observe enqueue work on the given stream and never synchronise the host.
+ */
+#ifndef MATE_B200_H_
+#define MATE_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MATE_B200_ABI_VERSION 1
+#define MATE_NUM_WAREHOUSES 4   /* mate/constants.py:70-75 */
+#define MATE_MAX_CAMERAS 32
+#define MATE_MAX_TARGETS 32
+#define MATE_MAX_OBSTACLES 64
+
+typedef enum MateStatus {
+    MATE_OK = 0,
+    MATE_EINVAL = -1,   /* bad argument / unsupported configuration */
+    MATE_ECUDA = -2,    /* CUDA runtime error (message has the cudaError string) */
+    MATE_ENOMEM = -3,   /* allocation failure */
+    MATE_ESTATE = -4    /* handle in the wrong state for this call */
+} MateStatus;
+
+/* Validated configuration, flattened from the YAML/dict the reference's read_config()
+ * produces (mate/environment.py:113-269).  Per-entity parameters are common to all
+ * entities of a kind, exactly as in the reference's config schema. */
+typedef struct MateConfig {
+    int32_t num_cameras;                /* Nc >= 0 */
+    int32_t num_targets;                /* Nt >= 1 */
+    int32_t num_obstacles;              /* No >= 0 */
+    int32_t max_episode_steps;          /* environment.py:199-203 */
+    int32_t num_cargoes_per_target;     /* environment.py:223-229 (>= 4) */
+    int32_t num_high_capacity_targets;  /* int(Nt * high_capacity_target_split), environment.py:1527-1535 */
+    int32_t targets_start_with_cargoes; /* bool */
+    int32_t shuffle_entities;           /* bool */
+    int32_t reward_sparse;              /* reward_type == 'sparse' */
+    int32_t reserved0;
+    double bounty_factor;
+    double camera_radius;
+    double camera_min_viewing_angle;
+    double camera_max_sight_range;
+    double camera_rotation_step;
+    double camera_zooming_step;
+    double target_step_size;
+    double target_sight_range;
+    double obstacle_transmittance;
+    double obstacle_radius_low;   /* radius_random_range (low == high for a fixed radius) */
+    double obstacle_radius_high;
+    /* host arrays [N][4] = (x_low, x_high, y_low, y_high); a fixed location has low == high */
+    const double* camera_location_ranges;
+    const double* target_location_ranges;
+    const double* obstacle_location_ranges;
+} MateConfig;
+
+/* Host-side view of the simulator state for get/set (checkpoint, parity harness).
+ * These are the quantities SURVEY.md section 8a lists as carried between steps; the
+ * reference has state() (environment.py:894-906) but no set_state.  All arrays are
+ * host pointers, batched row-major; any pointer may be NULL to skip that field. */
+typedef struct MateStateView {
+    double* cam_xy;          /* [B, Nc, 2]  Camera.location                      */
+    double* cam_phi;         /* [B, Nc]     Camera.orientation, degrees [-180,180) */
+    double* cam_theta;       /* [B, Nc]     Camera.viewing_angle, degrees         */
+    double* tgt_xy;          /* [B, Nt, 2]  Target.location                       */
+    double* obs_xyr;         /* [B, No, 3]  Obstacle.location, radius             */
+    int32_t* tgt_capacity;   /* [B, Nt]     1 or 2 (step_size = cfg step / capacity) */
+    int32_t* tgt_goal;       /* [B, Nt]     target_goals, -1 = no cargo           */
+    int32_t* tgt_weight;     /* [B, Nt]     target_goal_bits[t, goal] (cargo weight) */
+    int32_t* tgt_bounty;     /* [B, Nt]     bounties                              */
+    int32_t* tgt_empty_bits; /* [B, Nt]     bit w = Target.empty_bits[w]          */
+    int32_t* remaining;      /* [B, 4, 4]   remaining_cargoes                     */
+    int32_t* awaiting;       /* [B, 4]      awaiting_cargo_counts                 */
+    int32_t* num_delivered;  /* [B]         num_delivered_cargoes                 */
+    int32_t* episode_step;   /* [B]                                               */
+    int32_t* episode_id;     /* [B]         counter-based RNG episode counter     */
+    double* episode_reward;  /* [B, 2]      target_team_episode_reward, delayed_* */
+} MateStateView;
+
+/* Optional per-step auxiliary outputs (all dev pointers; NULL = not wanted).
+ * These are the reference's public per-step attributes / info-dict entries
+ * (environment.py:634-661) as tensors. */
+typedef struct MateStepAux {
+    uint8_t* mask_ct;        /* [B, Nc, Nt] camera_target_view_mask   */
+    uint8_t* mask_cc;        /* [B, Nc, Nc] camera_camera_view_mask   */
+    uint8_t* mask_co;        /* [B, Nc, No] camera_obstacle_view_mask */
+    uint8_t* mask_tc;        /* [B, Nt, Nc] target_camera_view_mask   */
+    uint8_t* mask_to;        /* [B, Nt, No] target_obstacle_view_mask */
+    uint8_t* mask_tt;        /* [B, Nt, Nt] target_target_view_mask   */
+    float* coverage;         /* [B, 3] coverage_rate, real_coverage_rate, mean_transport_rate */
+    int32_t* num_delivered;  /* [B]                                                          */
+    uint8_t* target_dones;   /* [B, Nt] environment.py:1320-1322                             */
+    uint8_t* is_colliding;   /* [B, Nt] Target.is_colliding, entities.py:668                 */
+    float* warehouse_dist;   /* [B, Nt, 4] target_warehouse_distances                        */
+    int32_t* episode_step;   /* [B] episode_step after this step (before auto-reset)         */
+} MateStepAux;
+
+/* Parity mode: recorded outcomes of the reference's two stochastic step-path draws
+ * (dev pointers).  NULL members / NULL struct => the counter-based Philox stream is used. */
+typedef struct MateReplay {
+    const uint8_t* transmit;   /* [B, Nc, Nt] outcome of binomial(1, transmittance), entities.py:503 */
+    const int8_t* goal_choice; /* [B, Nt] outcome of np_random.choice(...), environment.py:1303; -1 = none */
+} MateReplay;
+
+typedef struct MateSim MateSim;
+
+/* Flags for mate_b200_step. */
+#define MATE_STEP_AUTO_RESET 1u /* reset finished episodes inside the call; returned obs are the new episode's */
+
+const char* mate_b200_last_error(void);
+int mate_b200_abi_version(void);
+
+/* MultiAgentTracking.__init__ (environment.py:330-562): allocate the struct-of-arrays
+ * state for num_envs environments on CUDA device `device`.  env_index_base is the global
+ * index of local env 0 (multi-GPU sharding: RNG streams are keyed on the global index so
+ * results do not depend on the number of GPUs). */
+int mate_b200_create(const MateConfig* cfg, int32_t num_envs, int32_t device,
+                     int64_t env_index_base, MateSim** out);
+int mate_b200_destroy(MateSim* sim);
+
+/* Observation row widths: Dc, Dt (constants.py:267-300). */
+int mate_b200_obs_dims(const MateSim* sim, int32_t* cam_dim, int32_t* tgt_dim);
+
+/* MultiAgentTracking.reset (environment.py:679-834) for the envs with env_mask[b] != 0
+ * (dev, NULL = all); Philox streams keyed on (seed, global env index, episode id).
+ * Writes the first joint observation of the reset envs (other rows are rewritten with
+ * their current observation). */
+int mate_b200_reset(MateSim* sim, const uint8_t* env_mask, uint64_t seed,
+                    float* cam_obs, float* tgt_obs, void* stream);
+
+/* MultiAgentTracking.step (environment.py:590-676) for all envs: _simulate,
+ * _update_view, _assign_goals, joint_observation, reward/done.
+ *   cam_act [B,Nc,2], tgt_act [B,Nt,2] float32 dev (finite);
+ *   cam_obs [B,Nc,Dc], tgt_obs [B,Nt,Dt] float32 dev;
+ *   rewards [B,2] float32 dev = (camera_team_reward, target_team_reward);
+ *   done [B] uint8 dev. */
+int mate_b200_step(MateSim* sim, const float* cam_act, const float* tgt_act,
+                   float* cam_obs, float* tgt_obs, float* rewards, uint8_t* done,
+                   const MateStepAux* aux, const MateReplay* replay, uint32_t flags,
+                   void* stream);
+
+/* joint_observation() of the current state without stepping (_update_view +
+ * joint_observation, environment.py:1356-1388, 908-983); used after set_state. */
+int mate_b200_observe(MateSim* sim, float* cam_obs, float* tgt_obs,
+                      const MateStepAux* aux, const MateReplay* replay, void* stream);
+
+/* Same as mate_b200_step but with HOST buffers (pinned or pageable): actions are copied
+ * host->device, results device->host, chunked over internal streams so that copies
+ * overlap the kernel.  Returns after the results are in the host buffers. */
+int mate_b200_step_host(MateSim* sim, const float* cam_act, const float* tgt_act,
+                        float* cam_obs, float* tgt_obs, float* rewards, uint8_t* done,
+                        uint32_t flags);
+
+/* State checkpoint / injection (host arrays; synchronises the device). */
+int mate_b200_get_state(MateSim* sim, MateStateView* view);
+int mate_b200_set_state(MateSim* sim, const MateStateView* view);
+
+/* Episode statistics accumulated on device since the last call with reset_after != 0:
+ * out[0]=episodes finished, [1]=sum return (target team), [2]=sum length,
+ * [3]=sum delivered cargoes, [4]=sum of per-episode mean coverage, [5]=env-steps,
+ * [6..15] reserved (0).  `out16` is a dev pointer to 16 floats; the optional multi-GPU
+ * all-reduce of this vector is done by the caller (torch.distributed / NCCL). */
+int mate_b200_episode_stats(MateSim* sim, float* out16, int32_t reset_after, void* stream);
+
+/* Number of kernels this handle has launched since creation (bench bookkeeping). */
+int64_t mate_b200_launch_count(const MateSim* sim);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MATE_B200_H_ */
