@@ -1,0 +1,340 @@
+#!/usr/bin/env python
+"""Throughput benchmark of the batched MultiAgentTracking step (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...  # CPU arm (oracle port, all host threads)
+
+A "step" is one pass of the fused step kernel over one batch of environments
+(MATE-4v8-9, 65 536 envs per GPU, random joint actions, auto-reset on).  Multi-GPU runs
+are launched by ``torch.distributed.run`` (one rank per GPU): environments are independent,
+so the batch is sharded with no step-path collective (weak scaling: 65 536 envs per rank);
+timing is CUDA events per rank, MAX over ranks.  Rank 0 prints ONE JSON line.
+"""
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = 'env-steps/sec, MATE-4v8-9 batched, 1/2/4/8 B200 vs host-CPU reference'
+UNIT = 'env-steps/s'
+
+
+def algorithmic_bytes(nc, nt, no):
+    """in + out + state bytes per env-step (fp32 I/O)."""
+    dc = 22 + 5 * nt + 4 * no + 7 * nc
+    dt = 27 + 7 * nc + 4 * no + 5 * nt
+    return 8 * (nc + nt) + 4 * (nc * dc + nt * dt) + 9 + 8 * (2 * nc + 4 * nt + 10) + 4 * (2 * nc + 3 * no + 1)
+
+
+def measured_peak_gbs():
+    path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    try:
+        with open(path, encoding='UTF-8') as f:
+            return float(json.load(f)['hbm_gbs']), 'measured (MEASURED_PEAKS.json)'
+    except (OSError, KeyError, ValueError):
+        return 6650.0, 'fallback (B200_PROFILING.md)'
+
+
+def ncu_traffic_bytes(workload):
+    """dram read+write bytes per launch from the committed ncu --set full capture, if any."""
+    path = os.path.join(ROOT, 'profiles', 'traffic.json')
+    try:
+        with open(path, encoding='UTF-8') as f:
+            return json.load(f).get(workload)
+    except (OSError, ValueError):
+        return None
+
+
+class ClockSampler:
+    """Samples nvidia-smi SM clocks and throttle reasons while the timed region runs."""
+
+    QUERY = ('clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,'
+             'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+             'clocks_event_reasons.sw_power_cap')
+    NAMES = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+
+    def __init__(self, index):
+        self.index = index
+        self.samples = []
+        self.reasons = set()
+        self.max_mhz = None
+        self._stop = threading.Event()
+        self._thread = threading.Thread(target=self._run, daemon=True)
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(
+                    ['nvidia-smi', f'--id={self.index}', f'--query-gpu={self.QUERY}', '--format=csv,noheader,nounits'],
+                    capture_output=True, text=True, timeout=5).stdout.strip().splitlines()
+                if out:
+                    parts = [x.strip() for x in out[0].split(',')]
+                    self.samples.append(float(parts[0]))
+                    self.max_mhz = float(parts[1])
+                    for name, value in zip(self.NAMES, parts[2:]):
+                        if value.lower().startswith('active'):
+                            self.reasons.add(name)
+            except (OSError, ValueError, subprocess.SubprocessError, IndexError):
+                pass
+            self._stop.wait(0.1)
+
+    def __enter__(self):
+        self._thread.start()
+        return self
+
+    def __exit__(self, *exc):
+        self._stop.set()
+        self._thread.join(timeout=10)
+
+    def summary(self):
+        return {
+            'sm_mhz': statistics.median(self.samples) if self.samples else None,
+            'sm_max_mhz': self.max_mhz,
+            'reasons': sorted(self.reasons),
+            'samples': len(self.samples),
+        }
+
+
+def make_actions(cfg, B, device, ring, seed):
+    import torch
+
+    gen = torch.Generator(device=device)
+    gen.manual_seed(seed)
+    nc, nt = cfg['num_cameras'], cfg['num_targets']
+    scale = torch.tensor([cfg['camera_rotation_step'], cfg['camera_zooming_step']], device=device)
+    cams, tgts = [], []
+    for _ in range(ring):
+        cams.append((torch.rand((B, max(nc, 1), 2), device=device, generator=gen) * 2 - 1) * scale)
+        tgts.append((torch.rand((B, nt, 2), device=device, generator=gen) * 2 - 1) * cfg['target_step_size'])
+    return cams, tgts
+
+
+def cpu_arm(cfg, envs, seconds, threads, seed=0):
+    """Time the CPU oracle (float64 C port of the reference step) on `envs` environments with
+    `threads` host threads for about `seconds` seconds.  Returns (env-steps/s, steps, sample)."""
+    import numpy as np
+
+    from oracle.oracle import Oracle
+
+    nc, nt = cfg['num_cameras'], cfg['num_targets']
+    ref = Oracle(cfg, envs, num_threads=threads)
+    ref.reset(seed=seed)
+    rng = np.random.RandomState(seed)
+    ring = 4
+    cams = [rng.uniform(-1, 1, (envs, nc, 2)) * [cfg['camera_rotation_step'], cfg['camera_zooming_step']] for _ in range(ring)]
+    tgts = [rng.uniform(-1, 1, (envs, nt, 2)) * cfg['target_step_size'] for _ in range(ring)]
+    aux = ref.alloc_aux()
+    aux = {k: (v if k in ('coverage', 'num_delivered') else None) for k, v in aux.items()}
+    ref.step(cams[0], tgts[0], seed=seed, auto_reset=True, aux=aux)   # warm-up / calibration
+    t0 = time.perf_counter()
+    ref.step(cams[1], tgts[1], seed=seed, auto_reset=True, aux=aux)
+    per_step = max(time.perf_counter() - t0, 1e-6)
+    steps = max(3, min(2000, int(seconds / per_step)))
+    t0 = time.perf_counter()
+    for k in range(steps):
+        ref.step(cams[k % ring], tgts[k % ring], seed=seed, auto_reset=True, aux=aux)
+    elapsed = time.perf_counter() - t0
+    return envs * steps / elapsed, steps, elapsed
+
+
+def run_reference(args, cfg, workload):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    envs = args.cpu_envs
+    # K "steps", each a bounded sample: one pass over `envs` environments
+    import numpy as np
+
+    from oracle.oracle import Oracle
+
+    nc, nt = cfg['num_cameras'], cfg['num_targets']
+    ref = Oracle(cfg, envs, num_threads=threads)
+    ref.reset(seed=0)
+    rng = np.random.RandomState(0)
+    ring = 4
+    cams = [rng.uniform(-1, 1, (envs, nc, 2)) * [cfg['camera_rotation_step'], cfg['camera_zooming_step']] for _ in range(ring)]
+    tgts = [rng.uniform(-1, 1, (envs, nt, 2)) * cfg['target_step_size'] for _ in range(ring)]
+    aux = {k: (v if k in ('coverage', 'num_delivered') else None) for k, v in ref.alloc_aux().items()}
+    for k in range(args.warmup):
+        ref.step(cams[k % ring], tgts[k % ring], seed=0, auto_reset=True, aux=aux)
+    t0 = time.perf_counter()
+    for k in range(args.steps):
+        ref.step(cams[k % ring], tgts[k % ring], seed=0, auto_reset=True, aux=aux)
+    elapsed = time.perf_counter() - t0
+    value = envs * args.steps / elapsed
+    sample = f'{envs} envs x {args.steps} steps, float64 C port of the reference step (oracle/mate_oracle.c), {threads} pthreads'
+    line = {
+        'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus,
+        'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * elapsed / args.steps,
+        'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+        'config': {'workload': workload, 'envs_per_step': envs, 'actions': 'uniform random joint actions', 'auto_reset': True},
+        'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': threads, 'kind': 'port', 'sample': sample},
+        'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'agent_steps_per_s': value * (nc + nt),
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    parser = argparse.ArgumentParser()
+    parser.add_argument('--gpus', type=int, default=1)
+    parser.add_argument('--steps', type=int, default=200)
+    parser.add_argument('--warmup', type=int, default=20)
+    parser.add_argument('--impl', default='mine', choices=['mine', 'reference'])
+    parser.add_argument('--config', default='MATE-4v8-9.yaml')
+    parser.add_argument('--envs', type=int, default=65536, help='environments per GPU')
+    parser.add_argument('--cpu-envs', type=int, default=4096, help='environments per CPU-arm step')
+    parser.add_argument('--cpu-seconds', type=float, default=12.0)
+    parser.add_argument('--e2e-steps', type=int, default=10)
+    parser.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
+    parser.add_argument('--no-e2e', action='store_true', help='skip the host-buffer e2e leg')
+    args = parser.parse_args()
+
+    from mate_b200.config import flatten_config, read_config
+
+    cfg = flatten_config(read_config(args.config))
+    nc, nt, no = cfg['num_cameras'], cfg['num_targets'], cfg['num_obstacles']
+    workload = f'{args.config.replace(".yaml", "")} x {args.envs} envs/GPU'
+    if args.impl == 'reference':
+        run_reference(args, cfg, workload)
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    from mate_b200.sim import BatchedSim
+
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    if world > 1:
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
+    torch.cuda.set_device(local_rank)
+    device = torch.device('cuda', local_rank)
+    B = args.envs
+    sim = BatchedSim(cfg, B, device=local_rank, env_index_base=rank * B)
+    sim.reset(seed=0)
+    ring = 8
+    cams, tgts = make_actions(cfg, B, device, ring, seed=rank)
+    aux = sim.alloc_aux()
+    # per-step info tensors the reference returns in its info dicts: keep only the cheap ones
+    import ctypes
+
+    from mate_b200 import _abi
+    for name, ctype, _, _ in _abi.AUX_FIELDS:
+        if name not in ('coverage', 'num_delivered'):
+            setattr(sim._aux_struct, name, ctype())
+    del aux
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(device)
+
+    for k in range(max(args.warmup, 3)):
+        sim.step(cams[k % ring], tgts[k % ring], auto_reset=True, aux=True)
+    barrier()
+    launches0 = sim.launch_count
+    start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local_rank) as clocks:
+        barrier()
+        start.record()
+        for k in range(args.steps):
+            sim.step(cams[k % ring], tgts[k % ring], auto_reset=True, aux=True)
+        stop.record()
+        barrier()
+    elapsed_ms = start.elapsed_time(stop)
+    launches = sim.launch_count - launches0
+    if world > 1:
+        t = torch.tensor([elapsed_ms], device=device, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        elapsed_ms = float(t.item())
+    value = world * B * args.steps / (elapsed_ms * 1e-3)
+
+    # optional all-reduce of the episode statistics (outside the timed region)
+    stats = sim.episode_stats().clone()
+    if world > 1:
+        dist.all_reduce(stats, op=dist.ReduceOp.SUM)
+    stats = stats.cpu().tolist()
+
+    # ---- e2e: the same step through the host-buffer ABI call (pinned host memory) ----
+    e2e = None
+    if not args.no_e2e:
+        host_cam_act = [c.cpu().pin_memory() for c in cams[:2]]
+        host_tgt_act = [t.cpu().pin_memory() for t in tgts[:2]]
+        out = (torch.zeros((B, nc, sim.dc)).pin_memory(), torch.zeros((B, nt, sim.dt)).pin_memory(),
+               torch.zeros((B, 2)).pin_memory(), torch.zeros(B, dtype=torch.uint8).pin_memory())
+        for k in range(3):
+            sim.step_host(host_cam_act[k % 2], host_tgt_act[k % 2], out, auto_reset=True)
+        barrier()
+        t0 = time.perf_counter()
+        for k in range(args.e2e_steps):
+            sim.step_host(host_cam_act[k % 2], host_tgt_act[k % 2], out, auto_reset=True)
+        e2e_s = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([e2e_s], device=device, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            e2e_s = float(t.item())
+        e2e = {
+            'value': world * B * args.e2e_steps / e2e_s, 'unit': UNIT,
+            'h2d_bytes_per_step': B * (nc + nt) * 2 * 4,
+            'd2h_bytes_per_step': B * (4 * (nc * sim.dc + nt * sim.dt) + 8 + 1),
+            'steps': args.e2e_steps,
+            'note': 'mate_b200_step_host: pinned host actions in, observations/rewards/done out, chunked over 4 streams',
+        }
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    A = algorithmic_bytes(nc, nt, no)
+    peak, peak_src = measured_peak_gbs()
+    kernel_ms = elapsed_ms / max(launches, 1)
+    achieved = A * B / (kernel_ms * 1e-3) / 1e9
+    line = {
+        'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
+        'warmup': max(args.warmup, 3), 'ms_per_step': elapsed_ms / args.steps, 'higher_is_better': True,
+        'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64 decision state, f32 I/O', 'data': 'synthetic',
+        'config': {
+            'workload': workload, 'envs_per_gpu': B, 'actions': 'uniform random joint actions (ring of 8 pre-generated batches)',
+            'auto_reset': True, 'l2': 'per-step working set (observations %.0f MB + state) exceeds the 126 MB L2' % (B * 4 * (nc * sim.dc + nt * sim.dt) / 1e6),
+        },
+        'agent_steps_per_s': value * (nc + nt),
+        'gpu_launches': launches,
+        'roofline': {
+            'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
+            'traffic': ncu_traffic_bytes(args.config.replace('.yaml', '')),
+            'kernel': 'mate_step_kernel<%d,%d,%d>' % (nc, nt, no), 'algorithmic_bytes_per_env_step': A,
+            'kernel_ms': kernel_ms, 'peak_source': peak_src,
+        },
+        'clocks': clocks.summary(),
+        'episode_stats': {'episodes': stats[0], 'sum_return': stats[1], 'sum_length': stats[2], 'env_steps': stats[5]},
+    }
+    if e2e is not None:
+        line['e2e'] = e2e
+    if not args.no_cpu:
+        threads = os.cpu_count() or 1
+        cpu_value, cpu_steps, cpu_elapsed = cpu_arm(cfg, args.cpu_envs, args.cpu_seconds, threads)
+        line['cpu_baseline'] = {
+            'value': cpu_value, 'unit': UNIT, 'cores': threads, 'kind': 'port',
+            'sample': f'{args.cpu_envs} envs x {cpu_steps} steps ({cpu_elapsed:.1f} s) of the same workload, '
+                      f'float64 C port of the reference step (oracle/mate_oracle.c), {threads} pthreads',
+        }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

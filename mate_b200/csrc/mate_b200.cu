@@ -1,0 +1,493 @@
+// mate_b200.cu -- host side of the C ABI declared in include/mate_b200.h.
+//
+// Owns the struct-of-arrays device state of one batch of environments and launches the
+// fused step kernel (mate_kernels.cuh).  No torch types, no CPU simulation fallback.
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "mate_kernels.cuh"
+
+using namespace mate;
+
+static thread_local std::string g_error;
+
+static int fail(int code, const std::string& msg) {
+    g_error = msg;
+    return code;
+}
+#define CUDA_TRY(expr)                                                                        \
+    do {                                                                                      \
+        cudaError_t err__ = (expr);                                                           \
+        if (err__ != cudaSuccess)                                                             \
+            return fail(MATE_ECUDA, std::string(#expr) + ": " + cudaGetErrorString(err__));   \
+    } while (0)
+
+// ---- supported entity-count shapes (compile-time specialisations of the kernel) ------------
+// All 17 presets of the reference (mate/assets/MATE-*.yaml).
+#define MATE_SHAPES(X)                                                                        \
+    X(1, 1, 0) X(1, 1, 9) X(1, 2, 0) X(1, 2, 9) X(2, 2, 0) X(2, 2, 9) X(2, 4, 0) X(2, 4, 9)   \
+    X(4, 2, 0) X(4, 2, 9) X(4, 4, 0) X(4, 4, 9) X(4, 8, 0) X(4, 8, 9) X(8, 8, 0) X(8, 8, 9)   \
+    X(0, 8, 32)
+
+struct KernelInfo {
+    void (*launch)(const Params&, int grid, cudaStream_t);
+    int envs_per_cta, smem_bytes, dc, dt, epw;
+    cudaError_t (*prepare)();
+};
+
+template <int NC, int NT, int NO>
+static void launch_shape(const Params& p, int grid, cudaStream_t stream) {
+    using S = Shape<NC, NT, NO>;
+    mate_step_kernel<NC, NT, NO><<<grid, S::WARPS * 32, S::SMEM_BYTES, stream>>>(p);
+}
+template <int NC, int NT, int NO>
+static cudaError_t prepare_shape() {
+    using S = Shape<NC, NT, NO>;
+    return cudaFuncSetAttribute(mate_step_kernel<NC, NT, NO>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::SMEM_BYTES);
+}
+
+static bool find_kernel(int nc, int nt, int no, KernelInfo* out) {
+#define X(NC, NT, NO)                                                                          \
+    if (nc == NC && nt == NT && no == NO) {                                                    \
+        using S = Shape<NC, NT, NO>;                                                           \
+        *out = KernelInfo{&launch_shape<NC, NT, NO>, S::ENVS_PER_CTA, S::SMEM_BYTES, S::DC, S::DT, \
+                          S::EPW, &prepare_shape<NC, NT, NO>};                                 \
+        return true;                                                                           \
+    }
+    MATE_SHAPES(X)
+#undef X
+    return false;
+}
+
+struct MateSim {
+    MateConfig cfg;
+    int num_envs = 0, bpad = 0, device = 0;
+    long long env_index_base = 0;
+    KernelInfo kernel{};
+    Params base{};            // state pointers + scalars; per-call fields are filled per launch
+    void* state_block = nullptr;
+    size_t state_bytes = 0;
+    double* d_ranges = nullptr;
+    unsigned long long seed = 0;
+    long long launches = 0;
+    // host-path (step_host) resources
+    static constexpr int kHostStreams = 4;
+    cudaStream_t hstreams[kHostStreams] = {};
+    cudaEvent_t hevents[kHostStreams] = {};
+    float *h_cam_act = nullptr, *h_tgt_act = nullptr, *h_cam_obs = nullptr, *h_tgt_obs = nullptr, *h_rewards = nullptr;
+    uint8_t* h_done = nullptr;
+    bool host_ready = false;
+};
+
+extern "C" const char* mate_b200_last_error(void) { return g_error.c_str(); }
+extern "C" int mate_b200_abi_version(void) { return MATE_B200_ABI_VERSION; }
+
+static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+extern "C" int mate_b200_create(const MateConfig* cfg, int32_t num_envs, int32_t device,
+                                int64_t env_index_base, MateSim** out) {
+    if (!cfg || !out) return fail(MATE_EINVAL, "null argument");
+    if (num_envs <= 0) return fail(MATE_EINVAL, "num_envs must be positive");
+    const int nc = cfg->num_cameras, nt = cfg->num_targets, no = cfg->num_obstacles;
+    KernelInfo kernel;
+    if (!find_kernel(nc, nt, no, &kernel)) {
+        char buf[256];
+        snprintf(buf, sizeof(buf),
+                 "no kernel specialisation for (cameras=%d, targets=%d, obstacles=%d); add it to MATE_SHAPES in "
+                 "mate_b200/csrc/mate_b200.cu and rebuild", nc, nt, no);
+        return fail(MATE_EINVAL, buf);
+    }
+    if ((nc > 0 && !cfg->camera_location_ranges) || !cfg->target_location_ranges || (no > 0 && !cfg->obstacle_location_ranges))
+        return fail(MATE_EINVAL, "missing location ranges");
+    if (!(cfg->target_step_size > 0.0) || !(cfg->target_sight_range > 0.0)) return fail(MATE_EINVAL, "target parameters must be positive");
+    if (nc > 0 && (!(cfg->camera_min_viewing_angle > 0.0) || cfg->camera_min_viewing_angle > 180.0 || !(cfg->camera_rotation_step > 0.0) ||
+                   !(cfg->camera_zooming_step > 0.0) || !(cfg->camera_max_sight_range > 0.0)))
+        return fail(MATE_EINVAL, "camera parameters out of range");
+    if (cfg->max_episode_steps <= 0) return fail(MATE_EINVAL, "max_episode_steps must be positive");
+    if (cfg->num_cargoes_per_target < MATE_NUM_WAREHOUSES) return fail(MATE_EINVAL, "num_cargoes_per_target must be >= 4");
+    if (cfg->num_high_capacity_targets < 0 || cfg->num_high_capacity_targets > nt) return fail(MATE_EINVAL, "bad num_high_capacity_targets");
+    const double freight_scale = std::ceil(2.0 * kTerrain / cfg->target_step_size);       // environment.py:521
+    const double bounty_scale = std::ceil(freight_scale * std::fmax(0.0, cfg->bounty_factor));
+    if (2.0 * bounty_scale > 65535.0 || (double)cfg->num_cargoes_per_target * nt > 65535.0)
+        return fail(MATE_EINVAL, "bounty/cargo counts exceed the packed 16-bit state fields");
+
+    CUDA_TRY(cudaSetDevice(device));
+    CUDA_TRY(kernel.prepare());
+    MateSim* sim = new MateSim();
+    sim->cfg = *cfg;
+    sim->cfg.camera_location_ranges = sim->cfg.target_location_ranges = sim->cfg.obstacle_location_ranges = nullptr;
+    sim->num_envs = num_envs;
+    sim->device = device;
+    sim->env_index_base = env_index_base;
+    sim->kernel = kernel;
+    const int bpad = (int)align_up((size_t)num_envs, 128);
+    sim->bpad = bpad;
+
+    // one allocation, carved into the SoA arrays (each 256-byte aligned)
+    size_t off = 0;
+    auto carve = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
+    const size_t o_cam_x = carve(sizeof(double) * nc * bpad), o_cam_y = carve(sizeof(double) * nc * bpad);
+    const size_t o_cam_phi = carve(sizeof(double) * nc * bpad), o_cam_theta = carve(sizeof(double) * nc * bpad);
+    const size_t o_tgt_x = carve(sizeof(double) * nt * bpad), o_tgt_y = carve(sizeof(double) * nt * bpad);
+    const size_t o_obs_x = carve(sizeof(double) * no * bpad), o_obs_y = carve(sizeof(double) * no * bpad), o_obs_r = carve(sizeof(double) * no * bpad);
+    const size_t o_pack = carve(sizeof(uint32_t) * nt * bpad);
+    const size_t o_cargo = carve(sizeof(uint4) * 2 * bpad), o_env_a = carve(sizeof(uint4) * bpad), o_env_b = carve(sizeof(int4) * bpad);
+    const size_t o_stats = carve(sizeof(float) * 16);
+    sim->state_bytes = off;
+    if (cudaMalloc(&sim->state_block, off) != cudaSuccess) { delete sim; return fail(MATE_ENOMEM, "cudaMalloc(state) failed"); }
+    CUDA_TRY(cudaMemset(sim->state_block, 0, off));
+    char* b = (char*)sim->state_block;
+    Params& p = sim->base;
+    p.cam_x = (double*)(b + o_cam_x); p.cam_y = (double*)(b + o_cam_y); p.cam_phi = (double*)(b + o_cam_phi); p.cam_theta = (double*)(b + o_cam_theta);
+    p.tgt_x = (double*)(b + o_tgt_x); p.tgt_y = (double*)(b + o_tgt_y);
+    p.obs_x = (double*)(b + o_obs_x); p.obs_y = (double*)(b + o_obs_y); p.obs_r = (double*)(b + o_obs_r);
+    p.tgt_pack = (uint32_t*)(b + o_pack);
+    p.cargo = (uint4*)(b + o_cargo); p.env_a = (uint4*)(b + o_env_a); p.env_b = (int4*)(b + o_env_b);
+    p.stats = (float*)(b + o_stats);
+
+    // location ranges on device (reset)
+    std::vector<double> ranges((size_t)4 * (nc + nt + no) + 4, 0.0);
+    if (nc) memcpy(ranges.data(), cfg->camera_location_ranges, sizeof(double) * 4 * nc);
+    memcpy(ranges.data() + 4 * nc, cfg->target_location_ranges, sizeof(double) * 4 * nt);
+    if (no) memcpy(ranges.data() + 4 * (nc + nt), cfg->obstacle_location_ranges, sizeof(double) * 4 * no);
+    CUDA_TRY(cudaMalloc(&sim->d_ranges, ranges.size() * sizeof(double)));
+    CUDA_TRY(cudaMemcpy(sim->d_ranges, ranges.data(), ranges.size() * sizeof(double), cudaMemcpyHostToDevice));
+    p.cam_ranges = sim->d_ranges; p.tgt_ranges = sim->d_ranges + 4 * nc; p.obs_ranges = sim->d_ranges + 4 * (nc + nt);
+
+    p.num_envs = num_envs; p.bpad = bpad; p.env_index_base = env_index_base; p.seed = 0;
+    p.max_episode_steps = cfg->max_episode_steps; p.num_cargoes_per_target = cfg->num_cargoes_per_target;
+    p.num_high_capacity = cfg->num_high_capacity_targets; p.start_with_cargoes = cfg->targets_start_with_cargoes != 0;
+    p.shuffle = cfg->shuffle_entities != 0; p.reward_sparse = cfg->reward_sparse != 0;
+    p.transmittance = std::fmin(std::fmax(cfg->obstacle_transmittance, 0.0), 1.0);   // environment.py:1470-1476
+    p.transmittance_is_one = p.transmittance == 1.0;
+    p.freight_scale = (int)freight_scale; p.bounty_scale = (int)bounty_scale; p.reward_scale = (int)(freight_scale + bounty_scale);
+    p.cam_radius = cfg->camera_radius; p.cam_min_view = cfg->camera_min_viewing_angle; p.cam_rmax = cfg->camera_max_sight_range;
+    p.cam_rot_step = cfg->camera_rotation_step; p.cam_zoom_step = cfg->camera_zooming_step;
+    p.cam_area_product = cfg->camera_min_viewing_angle * (cfg->camera_max_sight_range * cfg->camera_max_sight_range);  // entities.py:285
+    p.tgt_step_size = cfg->target_step_size; p.tgt_sight_range = cfg->target_sight_range;
+    p.obs_r_low = cfg->obstacle_radius_low; p.obs_r_high = cfg->obstacle_radius_high;
+
+    // neutral initial state so that a step before reset/set_state is well defined
+    {
+        std::vector<double> theta((size_t)nc * bpad, cfg->camera_min_viewing_angle > 0 ? cfg->camera_min_viewing_angle : 90.0);
+        if (nc) CUDA_TRY(cudaMemcpy(p.cam_theta, theta.data(), theta.size() * sizeof(double), cudaMemcpyHostToDevice));
+        std::vector<uint32_t> pack((size_t)nt * bpad, pack_target(0, -1, 0, 1, 0, 0));
+        CUDA_TRY(cudaMemcpy(p.tgt_pack, pack.data(), pack.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    }
+    *out = sim;
+    return MATE_OK;
+}
+
+extern "C" int mate_b200_destroy(MateSim* sim) {
+    if (!sim) return MATE_OK;
+    cudaSetDevice(sim->device);
+    if (sim->host_ready) {
+        for (int i = 0; i < MateSim::kHostStreams; ++i) { cudaStreamDestroy(sim->hstreams[i]); cudaEventDestroy(sim->hevents[i]); }
+        cudaFree(sim->h_cam_act); cudaFree(sim->h_tgt_act); cudaFree(sim->h_cam_obs); cudaFree(sim->h_tgt_obs);
+        cudaFree(sim->h_rewards); cudaFree(sim->h_done);
+    }
+    cudaFree(sim->state_block);
+    cudaFree(sim->d_ranges);
+    delete sim;
+    return MATE_OK;
+}
+
+extern "C" int mate_b200_obs_dims(const MateSim* sim, int32_t* cam_dim, int32_t* tgt_dim) {
+    if (!sim) return fail(MATE_EINVAL, "null handle");
+    if (cam_dim) *cam_dim = sim->kernel.dc;
+    if (tgt_dim) *tgt_dim = sim->kernel.dt;
+    return MATE_OK;
+}
+
+extern "C" int64_t mate_b200_launch_count(const MateSim* sim) { return sim ? sim->launches : 0; }
+
+// Launch the fused kernel over envs [begin, begin + count); I/O pointers are for env 0.
+static int launch_range(MateSim* sim, Params p, int begin, int count, cudaStream_t stream) {
+    const int nc = sim->cfg.num_cameras, nt = sim->cfg.num_targets;
+    const int dc = sim->kernel.dc, dt = sim->kernel.dt;
+    // SoA rows are indexed [row * bpad + env]: shifting the base pointers selects the sub-range
+    p.cam_x += begin; p.cam_y += begin; p.cam_phi += begin; p.cam_theta += begin;
+    p.tgt_x += begin; p.tgt_y += begin; p.obs_x += begin; p.obs_y += begin; p.obs_r += begin;
+    p.tgt_pack += begin; p.cargo += begin; p.env_a += begin; p.env_b += begin;
+    if (p.cam_act) p.cam_act += (size_t)begin * nc * 2;
+    if (p.tgt_act) p.tgt_act += (size_t)begin * nt * 2;
+    if (p.cam_obs) p.cam_obs += (size_t)begin * nc * dc;
+    if (p.tgt_obs) p.tgt_obs += (size_t)begin * nt * dt;
+    if (p.rewards) p.rewards += (size_t)begin * 2;
+    if (p.done) p.done += begin;
+    if (p.env_mask) p.env_mask += begin;
+    if (p.replay_transmit) p.replay_transmit += (size_t)begin * nc * nt;
+    if (p.replay_choice) p.replay_choice += (size_t)begin * nt;
+    p.env_index_base += begin;
+    p.num_envs = count;
+    const int grid = (count + sim->kernel.envs_per_cta - 1) / sim->kernel.envs_per_cta;
+    sim->kernel.launch(p, grid, stream);
+    sim->launches += 1;
+    cudaError_t err = cudaGetLastError();
+    if (err != cudaSuccess) return fail(MATE_ECUDA, std::string("kernel launch: ") + cudaGetErrorString(err));
+    return MATE_OK;
+}
+
+static int check_obs_alignment(const void* cam_obs, const void* tgt_obs) {
+    if (((uintptr_t)cam_obs & 15) || ((uintptr_t)tgt_obs & 15)) return fail(MATE_EINVAL, "observation buffers must be 16-byte aligned");
+    return MATE_OK;
+}
+
+static void fill_aux(Params& p, const MateStepAux* aux, const MateReplay* replay) {
+    if (aux) { p.aux = *aux; p.has_aux = 1; } else { memset(&p.aux, 0, sizeof(p.aux)); p.has_aux = 0; }
+    p.replay_transmit = replay ? replay->transmit : nullptr;
+    p.replay_choice = replay ? replay->goal_choice : nullptr;
+}
+
+extern "C" int mate_b200_reset(MateSim* sim, const uint8_t* env_mask, uint64_t seed, float* cam_obs,
+                               float* tgt_obs, void* stream) {
+    if (!sim || !tgt_obs || (sim->cfg.num_cameras > 0 && !cam_obs)) return fail(MATE_EINVAL, "null argument");
+    if (int rc = check_obs_alignment(cam_obs, tgt_obs)) return rc;
+    CUDA_TRY(cudaSetDevice(sim->device));
+    sim->seed = seed;
+    Params p = sim->base;
+    p.mode = MODE_RESET; p.flags = 0; p.seed = seed;
+    p.cam_obs = cam_obs; p.tgt_obs = tgt_obs; p.env_mask = env_mask;
+    fill_aux(p, nullptr, nullptr);
+    return launch_range(sim, p, 0, sim->num_envs, (cudaStream_t)stream);
+}
+
+extern "C" int mate_b200_step(MateSim* sim, const float* cam_act, const float* tgt_act, float* cam_obs,
+                              float* tgt_obs, float* rewards, uint8_t* done, const MateStepAux* aux,
+                              const MateReplay* replay, uint32_t flags, void* stream) {
+    if (!sim || !tgt_act || !tgt_obs || !rewards || !done) return fail(MATE_EINVAL, "null argument");
+    if (sim->cfg.num_cameras > 0 && (!cam_act || !cam_obs)) return fail(MATE_EINVAL, "null camera buffers");
+    if (int rc = check_obs_alignment(cam_obs, tgt_obs)) return rc;
+    if (((uintptr_t)cam_act & 7) || ((uintptr_t)tgt_act & 7) || ((uintptr_t)rewards & 7)) return fail(MATE_EINVAL, "action/reward buffers must be 8-byte aligned");
+    CUDA_TRY(cudaSetDevice(sim->device));
+    Params p = sim->base;
+    p.mode = MODE_STEP; p.flags = flags; p.seed = sim->seed;
+    p.cam_act = cam_act; p.tgt_act = tgt_act; p.cam_obs = cam_obs; p.tgt_obs = tgt_obs; p.rewards = rewards; p.done = done;
+    fill_aux(p, aux, replay);
+    return launch_range(sim, p, 0, sim->num_envs, (cudaStream_t)stream);
+}
+
+extern "C" int mate_b200_observe(MateSim* sim, float* cam_obs, float* tgt_obs, const MateStepAux* aux,
+                                 const MateReplay* replay, void* stream) {
+    if (!sim || !tgt_obs || (sim->cfg.num_cameras > 0 && !cam_obs)) return fail(MATE_EINVAL, "null argument");
+    if (int rc = check_obs_alignment(cam_obs, tgt_obs)) return rc;
+    CUDA_TRY(cudaSetDevice(sim->device));
+    Params p = sim->base;
+    p.mode = MODE_OBSERVE; p.flags = 0; p.seed = sim->seed;
+    p.cam_obs = cam_obs; p.tgt_obs = tgt_obs;
+    fill_aux(p, aux, replay);
+    return launch_range(sim, p, 0, sim->num_envs, (cudaStream_t)stream);
+}
+
+// ---- host-buffer path: chunked H2D -> kernel -> D2H over a few streams ------------------------
+static int ensure_host_path(MateSim* sim) {
+    if (sim->host_ready) return MATE_OK;
+    const size_t B = sim->num_envs;
+    const int nc = sim->cfg.num_cameras, nt = sim->cfg.num_targets;
+    for (int i = 0; i < MateSim::kHostStreams; ++i) {
+        CUDA_TRY(cudaStreamCreateWithFlags(&sim->hstreams[i], cudaStreamNonBlocking));
+        CUDA_TRY(cudaEventCreateWithFlags(&sim->hevents[i], cudaEventDisableTiming));
+    }
+    CUDA_TRY(cudaMalloc(&sim->h_cam_act, sizeof(float) * (B * nc * 2 + 4)));
+    CUDA_TRY(cudaMalloc(&sim->h_tgt_act, sizeof(float) * B * nt * 2));
+    CUDA_TRY(cudaMalloc(&sim->h_cam_obs, sizeof(float) * (B * nc * sim->kernel.dc + 4)));
+    CUDA_TRY(cudaMalloc(&sim->h_tgt_obs, sizeof(float) * B * nt * sim->kernel.dt));
+    CUDA_TRY(cudaMalloc(&sim->h_rewards, sizeof(float) * B * 2));
+    CUDA_TRY(cudaMalloc(&sim->h_done, B));
+    sim->host_ready = true;
+    return MATE_OK;
+}
+
+extern "C" int mate_b200_step_host(MateSim* sim, const float* cam_act, const float* tgt_act, float* cam_obs,
+                                   float* tgt_obs, float* rewards, uint8_t* done, uint32_t flags) {
+    if (!sim || !tgt_act || !tgt_obs || !rewards || !done) return fail(MATE_EINVAL, "null argument");
+    const int nc = sim->cfg.num_cameras, nt = sim->cfg.num_targets;
+    if (nc > 0 && (!cam_act || !cam_obs)) return fail(MATE_EINVAL, "null camera buffers");
+    CUDA_TRY(cudaSetDevice(sim->device));
+    if (int rc = ensure_host_path(sim)) return rc;
+    const int dc = sim->kernel.dc, dt = sim->kernel.dt;
+    const int B = sim->num_envs;
+    // chunk size: a multiple of the CTA tile, ~16 chunks so copies and kernels overlap
+    int chunk = (B + 15) / 16;
+    const int tile = sim->kernel.envs_per_cta * 8;
+    chunk = (int)align_up((size_t)std::max(chunk, 1), (size_t)tile);
+    Params p = sim->base;
+    p.mode = MODE_STEP; p.flags = flags; p.seed = sim->seed;
+    p.cam_act = sim->h_cam_act; p.tgt_act = sim->h_tgt_act; p.cam_obs = sim->h_cam_obs; p.tgt_obs = sim->h_tgt_obs;
+    p.rewards = sim->h_rewards; p.done = sim->h_done;
+    fill_aux(p, nullptr, nullptr);
+    int k = 0;
+    for (int begin = 0; begin < B; begin += chunk, ++k) {
+        const int count = std::min(chunk, B - begin);
+        cudaStream_t s = sim->hstreams[k % MateSim::kHostStreams];
+        if (nc) CUDA_TRY(cudaMemcpyAsync(sim->h_cam_act + (size_t)begin * nc * 2, cam_act + (size_t)begin * nc * 2, sizeof(float) * count * nc * 2, cudaMemcpyHostToDevice, s));
+        CUDA_TRY(cudaMemcpyAsync(sim->h_tgt_act + (size_t)begin * nt * 2, tgt_act + (size_t)begin * nt * 2, sizeof(float) * count * nt * 2, cudaMemcpyHostToDevice, s));
+        if (int rc = launch_range(sim, p, begin, count, s)) return rc;
+        if (nc) CUDA_TRY(cudaMemcpyAsync(cam_obs + (size_t)begin * nc * dc, sim->h_cam_obs + (size_t)begin * nc * dc, sizeof(float) * count * nc * dc, cudaMemcpyDeviceToHost, s));
+        CUDA_TRY(cudaMemcpyAsync(tgt_obs + (size_t)begin * nt * dt, sim->h_tgt_obs + (size_t)begin * nt * dt, sizeof(float) * count * nt * dt, cudaMemcpyDeviceToHost, s));
+        CUDA_TRY(cudaMemcpyAsync(rewards + (size_t)begin * 2, sim->h_rewards + (size_t)begin * 2, sizeof(float) * count * 2, cudaMemcpyDeviceToHost, s));
+        CUDA_TRY(cudaMemcpyAsync(done + begin, sim->h_done + begin, count, cudaMemcpyDeviceToHost, s));
+    }
+    for (int i = 0; i < MateSim::kHostStreams; ++i) CUDA_TRY(cudaStreamSynchronize(sim->hstreams[i]));
+    return MATE_OK;
+}
+
+// ---- state get / set (host arrays, synchronous) --------------------------------------------------
+template <typename T>
+static int download(std::vector<T>& host, const T* dev, size_t n) {
+    host.resize(n);
+    CUDA_TRY(cudaMemcpy(host.data(), dev, n * sizeof(T), cudaMemcpyDeviceToHost));
+    return MATE_OK;
+}
+template <typename T>
+static int upload(const std::vector<T>& host, T* dev) {
+    CUDA_TRY(cudaMemcpy(dev, host.data(), host.size() * sizeof(T), cudaMemcpyHostToDevice));
+    return MATE_OK;
+}
+
+extern "C" int mate_b200_get_state(MateSim* sim, MateStateView* v) {
+    if (!sim || !v) return fail(MATE_EINVAL, "null argument");
+    CUDA_TRY(cudaSetDevice(sim->device));
+    CUDA_TRY(cudaDeviceSynchronize());
+    const int nc = sim->cfg.num_cameras, nt = sim->cfg.num_targets, no = sim->cfg.num_obstacles;
+    const size_t bp = sim->bpad, B = sim->num_envs;
+    const Params& p = sim->base;
+    std::vector<double> a, b2, c, d;
+    if (nc && (v->cam_xy || v->cam_phi || v->cam_theta)) {
+        if (download(a, p.cam_x, nc * bp) || download(b2, p.cam_y, nc * bp) || download(c, p.cam_phi, nc * bp) || download(d, p.cam_theta, nc * bp)) return MATE_ECUDA;
+        for (size_t e = 0; e < B; ++e)
+            for (int k = 0; k < nc; ++k) {
+                if (v->cam_xy) { v->cam_xy[(e * nc + k) * 2] = a[k * bp + e]; v->cam_xy[(e * nc + k) * 2 + 1] = b2[k * bp + e]; }
+                if (v->cam_phi) v->cam_phi[e * nc + k] = c[k * bp + e];
+                if (v->cam_theta) v->cam_theta[e * nc + k] = d[k * bp + e];
+            }
+    }
+    if (v->tgt_xy) {
+        if (download(a, p.tgt_x, nt * bp) || download(b2, p.tgt_y, nt * bp)) return MATE_ECUDA;
+        for (size_t e = 0; e < B; ++e)
+            for (int k = 0; k < nt; ++k) { v->tgt_xy[(e * nt + k) * 2] = a[k * bp + e]; v->tgt_xy[(e * nt + k) * 2 + 1] = b2[k * bp + e]; }
+    }
+    if (no && v->obs_xyr) {
+        if (download(a, p.obs_x, no * bp) || download(b2, p.obs_y, no * bp) || download(c, p.obs_r, no * bp)) return MATE_ECUDA;
+        for (size_t e = 0; e < B; ++e)
+            for (int k = 0; k < no; ++k) { v->obs_xyr[(e * no + k) * 3] = a[k * bp + e]; v->obs_xyr[(e * no + k) * 3 + 1] = b2[k * bp + e]; v->obs_xyr[(e * no + k) * 3 + 2] = c[k * bp + e]; }
+    }
+    {
+        std::vector<uint32_t> pack;
+        if (download(pack, p.tgt_pack, nt * bp)) return MATE_ECUDA;
+        for (size_t e = 0; e < B; ++e)
+            for (int k = 0; k < nt; ++k) {
+                const uint32_t q = pack[k * bp + e];
+                if (v->tgt_capacity) v->tgt_capacity[e * nt + k] = tp_capacity(q);
+                if (v->tgt_goal) v->tgt_goal[e * nt + k] = tp_goal(q);
+                if (v->tgt_weight) v->tgt_weight[e * nt + k] = tp_weight(q);
+                if (v->tgt_bounty) v->tgt_bounty[e * nt + k] = tp_bounty(q);
+                if (v->tgt_empty_bits) v->tgt_empty_bits[e * nt + k] = tp_empty(q);
+            }
+    }
+    {
+        std::vector<uint4> cargo, ea;
+        std::vector<int4> eb;
+        if (download(cargo, p.cargo, 2 * bp) || download(ea, p.env_a, bp) || download(eb, p.env_b, bp)) return MATE_ECUDA;
+        for (size_t e = 0; e < B; ++e) {
+            const uint32_t words[8] = {cargo[e].x, cargo[e].y, cargo[e].z, cargo[e].w, cargo[bp + e].x, cargo[bp + e].y, cargo[bp + e].z, cargo[bp + e].w};
+            if (v->remaining) for (int i = 0; i < 16; ++i) v->remaining[e * 16 + i] = (int32_t)((words[i >> 1] >> ((i & 1) * 16)) & 0xFFFF);
+            if (v->awaiting) { v->awaiting[e * 4 + 0] = ea[e].x & 0xFFFF; v->awaiting[e * 4 + 1] = ea[e].x >> 16; v->awaiting[e * 4 + 2] = ea[e].y & 0xFFFF; v->awaiting[e * 4 + 3] = ea[e].y >> 16; }
+            if (v->episode_step) v->episode_step[e] = (int32_t)ea[e].z;
+            if (v->num_delivered) v->num_delivered[e] = (int32_t)ea[e].w;
+            if (v->episode_reward) { v->episode_reward[e * 2] = (double)eb[e].x; v->episode_reward[e * 2 + 1] = (double)eb[e].y; }
+            if (v->episode_id) v->episode_id[e] = eb[e].w;
+        }
+    }
+    return MATE_OK;
+}
+
+extern "C" int mate_b200_set_state(MateSim* sim, const MateStateView* v) {
+    if (!sim || !v) return fail(MATE_EINVAL, "null argument");
+    CUDA_TRY(cudaSetDevice(sim->device));
+    CUDA_TRY(cudaDeviceSynchronize());
+    const int nc = sim->cfg.num_cameras, nt = sim->cfg.num_targets, no = sim->cfg.num_obstacles;
+    const size_t bp = sim->bpad, B = sim->num_envs;
+    const Params& p = sim->base;
+    std::vector<double> a, b2, c, d;
+    if (nc) {
+        if (download(a, p.cam_x, nc * bp) || download(b2, p.cam_y, nc * bp) || download(c, p.cam_phi, nc * bp) || download(d, p.cam_theta, nc * bp)) return MATE_ECUDA;
+        for (size_t e = 0; e < B; ++e)
+            for (int k = 0; k < nc; ++k) {
+                if (v->cam_xy) { a[k * bp + e] = v->cam_xy[(e * nc + k) * 2]; b2[k * bp + e] = v->cam_xy[(e * nc + k) * 2 + 1]; }
+                if (v->cam_phi) c[k * bp + e] = v->cam_phi[e * nc + k];
+                if (v->cam_theta) {
+                    const double th = v->cam_theta[e * nc + k];
+                    if (!(th > 0.0) || th > 180.0) return fail(MATE_EINVAL, "cam_theta out of (0, 180]");
+                    d[k * bp + e] = th;
+                }
+            }
+        if (upload(a, p.cam_x) || upload(b2, p.cam_y) || upload(c, p.cam_phi) || upload(d, p.cam_theta)) return MATE_ECUDA;
+    }
+    if (v->tgt_xy) {
+        a.assign(nt * bp, 0.0); b2.assign(nt * bp, 0.0);
+        for (size_t e = 0; e < B; ++e)
+            for (int k = 0; k < nt; ++k) { a[k * bp + e] = v->tgt_xy[(e * nt + k) * 2]; b2[k * bp + e] = v->tgt_xy[(e * nt + k) * 2 + 1]; }
+        if (upload(a, p.tgt_x) || upload(b2, p.tgt_y)) return MATE_ECUDA;
+    }
+    if (no && v->obs_xyr) {
+        a.assign(no * bp, 0.0); b2.assign(no * bp, 0.0); c.assign(no * bp, 0.0);
+        for (size_t e = 0; e < B; ++e)
+            for (int k = 0; k < no; ++k) { a[k * bp + e] = v->obs_xyr[(e * no + k) * 3]; b2[k * bp + e] = v->obs_xyr[(e * no + k) * 3 + 1]; c[k * bp + e] = v->obs_xyr[(e * no + k) * 3 + 2]; }
+        if (upload(a, p.obs_x) || upload(b2, p.obs_y) || upload(c, p.obs_r)) return MATE_ECUDA;
+    }
+    {
+        std::vector<uint32_t> pack;
+        if (download(pack, p.tgt_pack, nt * bp)) return MATE_ECUDA;
+        for (size_t e = 0; e < B; ++e)
+            for (int k = 0; k < nt; ++k) {
+                const uint32_t q = pack[k * bp + e];
+                int capacity = v->tgt_capacity ? v->tgt_capacity[e * nt + k] : tp_capacity(q);
+                int goal = v->tgt_goal ? v->tgt_goal[e * nt + k] : tp_goal(q);
+                int weight = v->tgt_weight ? v->tgt_weight[e * nt + k] : tp_weight(q);
+                int bounty = v->tgt_bounty ? v->tgt_bounty[e * nt + k] : tp_bounty(q);
+                int empty = v->tgt_empty_bits ? v->tgt_empty_bits[e * nt + k] : tp_empty(q);
+                if (capacity < 1 || capacity > 2 || goal < -1 || goal > 3 || weight < 0 || weight > 3 || bounty < 0 || bounty > 65535)
+                    return fail(MATE_EINVAL, "target integer state out of range");
+                pack[k * bp + e] = pack_target(bounty, goal, weight, capacity, empty, tp_colliding(q));
+            }
+        if (upload(pack, p.tgt_pack)) return MATE_ECUDA;
+    }
+    {
+        std::vector<uint4> cargo, ea;
+        std::vector<int4> eb;
+        if (download(cargo, p.cargo, 2 * bp) || download(ea, p.env_a, bp) || download(eb, p.env_b, bp)) return MATE_ECUDA;
+        for (size_t e = 0; e < B; ++e) {
+            if (v->remaining) {
+                uint32_t words[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+                for (int i = 0; i < 16; ++i) words[i >> 1] |= ((uint32_t)v->remaining[e * 16 + i] & 0xFFFF) << ((i & 1) * 16);
+                cargo[e] = make_uint4(words[0], words[1], words[2], words[3]);
+                cargo[bp + e] = make_uint4(words[4], words[5], words[6], words[7]);
+            }
+            if (v->awaiting) {
+                ea[e].x = ((uint32_t)v->awaiting[e * 4 + 0] & 0xFFFF) | ((uint32_t)v->awaiting[e * 4 + 1] << 16);
+                ea[e].y = ((uint32_t)v->awaiting[e * 4 + 2] & 0xFFFF) | ((uint32_t)v->awaiting[e * 4 + 3] << 16);
+            }
+            if (v->episode_step) ea[e].z = (uint32_t)v->episode_step[e];
+            if (v->num_delivered) ea[e].w = (uint32_t)v->num_delivered[e];
+            if (v->episode_reward) { eb[e].x = (int)std::lrint(v->episode_reward[e * 2]); eb[e].y = (int)std::lrint(v->episode_reward[e * 2 + 1]); eb[e].z = 0; }
+            if (v->episode_id) eb[e].w = v->episode_id[e];
+        }
+        if (upload(cargo, p.cargo) || upload(ea, p.env_a) || upload(eb, p.env_b)) return MATE_ECUDA;
+    }
+    return MATE_OK;
+}
+
+extern "C" int mate_b200_episode_stats(MateSim* sim, float* out16, int32_t reset_after, void* stream) {
+    if (!sim || !out16) return fail(MATE_EINVAL, "null argument");
+    CUDA_TRY(cudaSetDevice(sim->device));
+    CUDA_TRY(cudaMemcpyAsync(out16, sim->base.stats, sizeof(float) * 16, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    if (reset_after) CUDA_TRY(cudaMemsetAsync(sim->base.stats, 0, sizeof(float) * 16, (cudaStream_t)stream));
+    return MATE_OK;
+}

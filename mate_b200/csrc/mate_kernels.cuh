@@ -1,0 +1,1020 @@
+// mate_kernels.cuh -- fused per-step kernel of the B200-native MultiAgentTracking simulator.
+//
+// One launch per env.step: camera kinematics, target motion with disc/boundary collision,
+// the five visibility masks (incl. the obstacle-occluded camera field of view), cargo
+// pickup/delivery + rewards + done, auto-reset, and packing of all per-agent observation
+// rows.  Reference behaviour being restated (paths relative to the reference root):
+//   mate/environment.py:590-676 (step), :1271-1388 (_assign_goals/_simulate/_update_view),
+//   :908-983 (joint_observation), :679-834 (reset); mate/entities.py:158-184 (obstruct),
+//   :347-360 (Camera.simulate), :362-511 (FOV polyline + perceive), :645-668 (Target.simulate).
+//
+// Mapping (sm_100a, no tensor cores -- nothing here is a contraction):
+//   * HBM state is struct-of-arrays [field][env]; decision state (positions, angles) is
+//     fp64 so that the visibility predicates reproduce the float64 reference bit-for-bit
+//     in practice; I/O (actions, observations, rewards) is fp32.
+//   * A "group" of G = pow2 >= max(Nc, Nt) lanes owns one environment, 32/G environments
+//     per warp; lane j of a group owns camera j, target j and obstacles j, j+G, ...  A warp
+//     load of one SoA field therefore touches fully-used 32-byte sectors.
+//   * Entity state is staged per environment in shared memory (fp64) so every lane can
+//     loop over all cameras / obstacles with broadcast LDS; each entity-owning lane
+//     computes the *column* of each mask (who sees my entity), which is exactly what the
+//     observation packer needs, so no mask transposes.
+//   * Observation rows are assembled in shared memory in the final [env][agent][feature]
+//     layout and leave the SM as one contiguous bulk copy per warp and tensor
+//     (cp.async.bulk shared->global, i.e. TMA), 16-byte aligned.
+//   * The camera field of view is evaluated on the fly: instead of materialising the
+//     reference's ~500-sample (phi, rho) polyline per camera at reset (35 kB/env), the
+//     two polyline samples that bracket the query bearing are found analytically and
+//     only those two rays are cast against the obstacle discs.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/mate_b200.h"
+
+namespace mate {
+
+constexpr int NW = MATE_NUM_WAREHOUSES;
+constexpr double kTerrain = 1000.0;          // mate/constants.py:52
+constexpr double kWarehouseRadius = 75.0;    // mate/constants.py:67
+constexpr double kWarehouseCoord = 925.0;    // mate/constants.py:70-72
+constexpr double kRad2Deg = 57.295779513082320876798154814105;
+constexpr double kDeg2Rad = 0.017453292519943295769236907684886;
+constexpr int kResetRetries = 500;           // mate/environment.py:53
+
+enum Mode : int { MODE_STEP = 0, MODE_OBSERVE = 1, MODE_RESET = 2 };
+
+enum Stream : uint32_t {
+    STREAM_SHUFFLE_CAM = 0, STREAM_SHUFFLE_TGT = 1, STREAM_SHUFFLE_OBS = 2, STREAM_CAPACITY = 3,
+    STREAM_PLACE = 4, STREAM_CARGO = 5, STREAM_INIT_GOAL = 6, STREAM_TRANSMIT = 7, STREAM_CHOICE = 8
+};
+
+// ---- packed per-target integer state (one u32 per target) -------------------------------
+// bits 0-15 bounty | 16-18 goal+1 | 19-20 cargo weight | 21-22 capacity | 23-26 empty_bits | 27 colliding
+__host__ __device__ inline uint32_t pack_target(int bounty, int goal, int weight, int capacity, int empty, int colliding) {
+    return (uint32_t)(bounty & 0xFFFF) | ((uint32_t)(goal + 1) << 16) | ((uint32_t)(weight & 3) << 19) |
+           ((uint32_t)(capacity & 3) << 21) | ((uint32_t)(empty & 15) << 23) | ((uint32_t)(colliding & 1) << 27);
+}
+__host__ __device__ inline int tp_bounty(uint32_t p) { return (int)(p & 0xFFFF); }
+__host__ __device__ inline int tp_goal(uint32_t p) { return (int)((p >> 16) & 7) - 1; }
+__host__ __device__ inline int tp_weight(uint32_t p) { return (int)((p >> 19) & 3); }
+__host__ __device__ inline int tp_capacity(uint32_t p) { return (int)((p >> 21) & 3); }
+__host__ __device__ inline int tp_empty(uint32_t p) { return (int)((p >> 23) & 15); }
+__host__ __device__ inline int tp_colliding(uint32_t p) { return (int)((p >> 27) & 1); }
+
+struct Params {
+    // --- state (device, struct-of-arrays, row stride = bpad) ---
+    double* cam_x; double* cam_y; double* cam_phi; double* cam_theta;   // [NC][bpad]
+    double* tgt_x; double* tgt_y;                                       // [NT][bpad]
+    double* obs_x; double* obs_y; double* obs_r;                        // [NO][bpad]
+    uint32_t* tgt_pack;                                                 // [NT][bpad]
+    uint4* cargo;      // [2][bpad]  remaining_cargoes as 16 x u16
+    uint4* env_a;      // [bpad] x: awaiting0|awaiting1<<16, y: awaiting2|awaiting3<<16, z: episode_step, w: delivered
+    int4* env_b;       // [bpad] x: episode reward, y: delayed episode reward, z: coverage_sum (float bits), w: episode_id
+    float* stats;      // [16] episode statistics accumulators
+    // --- per-call I/O (device) ---
+    const float* cam_act; const float* tgt_act;
+    float* cam_obs; float* tgt_obs; float* rewards; uint8_t* done;
+    const uint8_t* env_mask;
+    MateStepAux aux; int has_aux;
+    const uint8_t* replay_transmit; const int8_t* replay_choice;
+    // --- scalars ---
+    int num_envs; int bpad; int mode; uint32_t flags;
+    long long env_index_base; unsigned long long seed;
+    int max_episode_steps; int num_cargoes_per_target; int num_high_capacity; int start_with_cargoes;
+    int shuffle; int reward_sparse; int transmittance_is_one;
+    int freight_scale; int bounty_scale; int reward_scale;
+    double cam_radius, cam_min_view, cam_rmax, cam_rot_step, cam_zoom_step, cam_area_product;
+    double tgt_step_size, tgt_sight_range, transmittance;
+    double obs_r_low, obs_r_high;
+    const double* cam_ranges; const double* tgt_ranges; const double* obs_ranges;  // device [N][4]
+};
+
+template <int NC, int NT, int NO>
+struct Shape {
+    static constexpr int MAXE = (NC > NT ? NC : NT) > 1 ? (NC > NT ? NC : NT) : 1;
+    static constexpr int G = MAXE <= 1 ? 1 : MAXE <= 2 ? 2 : MAXE <= 4 ? 4 : MAXE <= 8 ? 8 : MAXE <= 16 ? 16 : 32;
+    static constexpr int EPW = 32 / G;                       // environments per warp
+    static constexpr int OS = NO == 0 ? 0 : (NO + G - 1) / G; // obstacle slots per lane
+    static constexpr int DC = 22 + 5 * NT + 4 * NO + 7 * NC; // mate/constants.py:267-282
+    static constexpr int DT = 27 + 7 * NC + 4 * NO + 5 * NT; // mate/constants.py:285-300
+    // shared-memory entity block per env (doubles): cams (x,y,phi,theta,rs), tgts (x,y), obstacles (x,y,r)
+    static constexpr int CAMF = 5;
+    static constexpr int E_CAM = 0;
+    static constexpr int E_TGT = E_CAM + CAMF * NC;
+    static constexpr int E_OBS = E_TGT + 2 * NT;
+    static constexpr int E_RAW = E_OBS + 3 * NO;
+    static constexpr int ES = E_RAW | 1;                     // odd stride (doubles) -> conflict-free group broadcast LDS.64
+    static constexpr int CAM_ROW = NC * DC;                  // floats per env in cam_obs
+    static constexpr int TGT_ROW = NT * DT;
+    static constexpr int WARPS = 4;                          // warps per CTA
+    static constexpr int ENVS_PER_CTA = WARPS * EPW;
+    // per-warp shared memory (bytes): entity blocks + staged observation rows
+    static constexpr int STAGE_CAM_FLOATS = ((EPW * CAM_ROW + 3) / 4) * 4;
+    static constexpr int STAGE_TGT_FLOATS = ((EPW * TGT_ROW + 3) / 4) * 4;
+    static constexpr int E_BYTES = ((EPW * ES * 8 + 15) / 16) * 16;
+    static constexpr int WARP_BYTES = E_BYTES + (STAGE_CAM_FLOATS + STAGE_TGT_FLOATS) * 4;
+    // a warp's rows start at a multiple of 4 floats in the output tensors => float4 / bulk copies
+    static constexpr bool CAM_VEC = (EPW * CAM_ROW) % 4 == 0;
+    static constexpr bool TGT_VEC = (EPW * TGT_ROW) % 4 == 0;
+    static constexpr int SMEM_BYTES = WARPS * WARP_BYTES;
+};
+
+// ---- small math helpers --------------------------------------------------------------------
+__device__ __forceinline__ double normalize_angle(double a) {   // mate/utils.py:155-158, Python float %
+    double x = a + 180.0;
+    double m = fmod(x, 360.0);
+    if (m != 0.0) { if (m < 0.0) m += 360.0; } else { m = 0.0; }
+    return m - 180.0;
+}
+__device__ __forceinline__ double norm2(double x, double y) { return sqrt(x * x + y * y); }
+__device__ __forceinline__ double atan2_deg(double y, double x) { return atan2(y, x) * kRad2Deg; }
+__device__ __forceinline__ void sincos_deg(double deg, double* s, double* c) { sincos(deg * kDeg2Rad, s, c); }
+
+// ---- Philox4x32-10, same draw scheme as oracle/mate_oracle.c ------------------------------
+struct RngKey { unsigned long long seed; uint32_t env; uint32_t episode; };
+
+__device__ inline uint4 philox(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+        uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+        uint32_t n0 = hi1 ^ c1 ^ k0, n1 = lo1, n2 = hi0 ^ c3 ^ k1, n3 = lo0;
+        c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    return make_uint4(c0, c1, c2, c3);
+}
+__device__ inline uint4 rng_words(const RngKey& k, uint32_t stream, uint32_t index) {
+    return philox(index, stream, k.env, k.episode, (uint32_t)k.seed, (uint32_t)(k.seed >> 32));
+}
+__device__ inline double rng_u01(const RngKey& k, uint32_t stream, uint32_t index) {
+    uint4 w = rng_words(k, stream, index);
+    unsigned long long bits = ((unsigned long long)w.y << 32) | w.x;
+    return (double)(bits >> 11) * (1.0 / 9007199254740992.0);
+}
+__device__ inline uint32_t rng_below(const RngKey& k, uint32_t stream, uint32_t index, uint32_t n) {
+    return __umulhi(rng_words(k, stream, index).x, n);
+}
+
+// ---- per-env cargo table, replicated in every lane of the group ---------------------------
+struct Cargo {
+    uint32_t rem[8];   // remaining[w][g] as u16: word (w*4+g)/2, half (w*4+g)&1
+    uint32_t aw[2];    // awaiting[4] as u16
+    __device__ __forceinline__ int get(int w, int g) const {
+        int i = w * 4 + g;
+        uint32_t word = rem[0];
+#pragma unroll
+        for (int k = 1; k < 8; ++k) word = (i >> 1) == k ? rem[k] : word;
+        return (int)((word >> ((i & 1) * 16)) & 0xFFFF);
+    }
+    __device__ __forceinline__ void add(int w, int g, int delta) {
+        int i = w * 4 + g;
+        uint32_t inc = (uint32_t)delta << ((i & 1) * 16);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) if ((i >> 1) == k) rem[k] += inc;
+    }
+    __device__ __forceinline__ bool row_any(int w) const {
+        uint32_t a = rem[0] | rem[1];
+#pragma unroll
+        for (int k = 1; k < 4; ++k) a = (w == k) ? (rem[2 * k] | rem[2 * k + 1]) : a;
+        return a != 0;
+    }
+    __device__ __forceinline__ int awaiting(int g) const { return (int)((aw[g >> 1] >> ((g & 1) * 16)) & 0xFFFF); }
+    __device__ __forceinline__ void awaiting_add(int g, int delta) {
+        uint32_t inc = (uint32_t)delta << ((g & 1) * 16);
+        if (g >> 1) aw[1] += inc; else aw[0] += inc;
+    }
+    __device__ __forceinline__ bool any_awaiting() const { return (aw[0] | aw[1]) != 0; }
+};
+
+// =============================================================================================
+// Obstacle.obstruct(ray, keep_tangential=True) for target motion (mate/entities.py:158-184).
+// (vx, vy) is the step vector with cached norm n (n < 0 => recompute), cached angle `ang`
+// (valid if has_ang), origin (ox, oy); disc centre (px, py), radius R.
+// =============================================================================================
+struct StepVec { double vx, vy, n, ang; bool has_n, has_ang; };
+
+__device__ __forceinline__ void obstruct_step(StepVec& s, double ox, double oy, double px, double py, double R) {
+    const double relx = px - ox, rely = py - oy;
+    const double d2 = relx * relx + rely * rely;
+    // cheap conservative reject (|v| <= ~step_size + slack): d >= n + R  certainly holds
+    if (s.has_n) {
+        const double reach = s.n + R;
+        if (d2 > reach * reach * (1.0 + 1e-9)) return;
+    }
+    const double reln = sqrt(d2);
+    if (!s.has_n) { s.n = norm2(s.vx, s.vy); s.has_n = true; }
+    const double norm = s.n;
+    if (norm == 0.0 || reln < R) {   // return -ray
+        s.vx = -s.vx; s.vy = -s.vy; s.has_n = false; s.has_ang = false;
+        return;
+    }
+    if (reln >= norm + R) return;
+    const double inner = relx * s.vx + rely * s.vy;
+    if (inner >= 0.0) {
+        const double c = fmin(1.0, inner / (reln * norm));
+        const double perp = reln * sqrt(1.0 - c * c);
+        if (R > perp) {
+            const double hc = sqrt(R * R - perp * perp);
+            const double nn = fmax(0.0, reln * c - hc);
+            if (nn < norm) {
+                if (!s.has_ang) { s.ang = atan2_deg(s.vy, s.vx); s.has_ang = true; }
+                double sn, cs;
+                sincos_deg(s.ang, &sn, &cs);
+                const double radx = (ox + nn * cs) - px, rady = (oy + nn * sn) - py;
+                const double k = (norm - nn) * hc / (R * R);
+                s.vx = s.vx + radx * k; s.vy = s.vy + rady * k;
+                s.has_n = false; s.has_ang = false;
+            }
+        }
+    }
+}
+
+// =============================================================================================
+// On-the-fly field-of-view range: value of the reference's sampled (phi, rho) polyline
+// (Camera.add_obstacles + interp1d, mate/entities.py:362-479, 507-511) at bearing `a`
+// (degrees, already normalised to [-180, 180)), WITHOUT materialising the polyline.
+// The polyline's sample angles are: the 360 integer degrees; per visible obstacle the four
+// edge rays L-+0.01, R-+0.01 and the lattice linspace(L, R, n+1).  We find the two samples
+// that bracket `a`, cast those two rays against all obstacle discs (sequential shortening ==
+// min over discs) and interpolate linearly like np.interp.
+// =============================================================================================
+struct RaySample { double angle; double n0; int tangent_of; };
+
+template <int NO>
+__device__ __forceinline__ double cast_ray(const double* __restrict__ Eobs, double cx, double cy,
+                                           double angle, double n0, int tangent_of) {
+    double sn, cs;
+    sincos_deg(angle, &sn, &cs);
+    double n = n0;
+#pragma unroll 1
+    for (int o = 0; o < NO; ++o) {
+        if (o == tangent_of) continue;   // exact tangent ray: never shortened by its own disc
+        const double relx = Eobs[3 * o] - cx, rely = Eobs[3 * o + 1] - cy, R = Eobs[3 * o + 2];
+        const double proj = relx * cs + rely * sn;
+        if (proj < 0.0) continue;
+        const double d2 = relx * relx + rely * rely;
+        const double perp2 = d2 - proj * proj;
+        if (!(R * R > perp2)) continue;
+        const double hc = sqrt(R * R - fmax(perp2, 0.0));
+        const double nn = fmax(0.0, proj - hc);
+        if (nn < n) n = nn;
+    }
+    return n;
+}
+
+__device__ __forceinline__ void consider(RaySample& P, RaySample& S, double a, double s, double n0, int tangent_of) {
+    if (s <= a) {
+        if (s > P.angle || (s == P.angle && n0 < P.n0)) { P.angle = s; P.n0 = n0; P.tangent_of = tangent_of; }
+    } else {
+        if (s < S.angle || (s == S.angle && n0 < S.n0)) { S.angle = s; S.n0 = n0; S.tangent_of = tangent_of; }
+    }
+}
+
+template <int NO>
+__device__ __noinline__ double sight_range_at(const double* __restrict__ Eobs, double cx, double cy,
+                                              double rmax, double a, double ux, double uy) {
+    // (ux, uy): unit vector of bearing a (rel / dist), used only for the conservative prefilter
+    const double fl = floor(a);
+    RaySample P{fl, rmax, -1}, S{fl + 1.0, rmax, -1};
+    const double c1 = 0.99984154; // cos(1.02 deg)
+    const double s1 = 0.01780139; // sin(1.02 deg)
+#pragma unroll 1
+    for (int o = 0; o < NO; ++o) {
+        const double relx = Eobs[3 * o] - cx, rely = Eobs[3 * o + 1] - cy, R = Eobs[3 * o + 2];
+        const double d2 = relx * relx + rely * rely;
+        const double d = sqrt(d2);
+        if (!(d < rmax + R)) continue;            // entities.py:365 (strict)
+        if (R > d) return 0.0;                    // camera inside the disc (entities.py:378-387)
+        // prefilter: can any sample angle of this obstacle fall inside (floor(a), floor(a)+1)?
+        // angular distance bearing<->centre must be <= half + 1.02 deg
+        const double p = relx * ux + rely * uy + R * s1 * 1.0000001;
+        if (p < 0.0) continue;
+        if (p * p < (d2 - R * R) * (c1 * c1) * 0.9999999) continue;
+        const double ang_o = atan2_deg(rely, relx);
+        const double half = asin(R / d) * kRad2Deg;
+        const double left = ang_o - half, right = ang_o + half;
+        consider(P, S, a, normalize_angle(left - 0.01), rmax, -1);
+        consider(P, S, a, normalize_angle(left + 0.01), rmax, -1);
+        consider(P, S, a, normalize_angle(right - 0.01), rmax, -1);
+        consider(P, S, a, normalize_angle(right + 0.01), rmax, -1);
+        const int two_half = (int)(2.0 * half);
+        const int nlat = two_half > 16 ? two_half : 16;
+        const double step = (right - left) / (double)nlat;   // np.linspace: arange(num) * step + start
+        const double max_rho = fmin(rmax, d + R);
+        if (step > 0.0) {
+#pragma unroll 1
+            for (int k = -1; k <= 1; ++k) {
+                const double ap = a + 360.0 * (double)k;
+                if (ap < left - step || ap > right + step) continue;
+                const int i0 = (int)floor((ap - left) / step);
+#pragma unroll 1
+                for (int i = i0 - 1; i <= i0 + 2; ++i) {
+                    if (i < 0 || i > nlat) continue;
+                    const double raw = (i == nlat) ? right : ((double)i * step + left);
+                    consider(P, S, a, normalize_angle(raw), max_rho, (i == 0 || i == nlat) ? o : -1);
+                }
+            }
+        }
+    }
+    const double rho_p = cast_ray<NO>(Eobs, cx, cy, P.angle, P.n0, P.tangent_of);
+    if (a == P.angle) return rho_p;                // np.interp: exact hit on a sample
+    // the closing sample (phi0 + 360, rho0) of the polyline is the -180 grid ray (entities.py:470-471)
+    const double s_angle = (S.angle >= 180.0) ? -180.0 : S.angle;
+    const double rho_s = cast_ray<NO>(Eobs, cx, cy, s_angle, S.n0, S.tangent_of);
+    const double slope = (rho_s - rho_p) / (S.angle - P.angle);
+    return slope * (a - P.angle) + rho_p;
+}
+
+// Camera.perceive (mate/entities.py:491-505) up to the stochastic draw; returns
+// 0 = not in range/sector, 1 = reached the draw.  Outputs dist and the raw bearing.
+__device__ __forceinline__ int fov_reach(double cx, double cy, double phi, double theta, double rs,
+                                         double qx, double qy, double* dist_out, double* ang_out,
+                                         double* relx_out, double* rely_out) {
+    const double relx = qx - cx, rely = qy - cy;
+    const double d2 = relx * relx + rely * rely;
+    if (d2 > rs * rs * (1.0 + 1e-9)) return 0;      // certainly dist > rs
+    const double dist = sqrt(d2);
+    if (dist > rs) return 0;
+    const double ang = atan2_deg(rely, relx);
+    double ra = fabs(phi - ang);
+    ra = fmin(ra, 360.0 - ra);
+    if (ra * 2.0 > theta) return 0;
+    *dist_out = dist; *ang_out = ang; *relx_out = relx; *rely_out = rely;
+    return 1;
+}
+
+// =============================================================================================
+// The fused kernel
+// =============================================================================================
+template <int NC, int NT, int NO>
+__global__ void __launch_bounds__(Shape<NC, NT, NO>::WARPS * 32)
+mate_step_kernel(const Params p) {
+    using S = Shape<NC, NT, NO>;
+    constexpr int G = S::G, EPW = S::EPW, OS = S::OS, DC = S::DC, DT = S::DT;
+    constexpr uint32_t FULL = 0xffffffffu;
+    constexpr uint32_t GMASK = G == 32 ? 0xffffffffu : ((1u << G) - 1u);
+
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int g = lane / G, j = lane % G;
+    const int gbase = g * G;                                   // first lane of my group
+    unsigned char* wbase = smem_raw + (size_t)warp * S::WARP_BYTES;
+    double* Ewarp = reinterpret_cast<double*>(wbase);
+    float* stage_cam = reinterpret_cast<float*>(wbase + S::E_BYTES);
+    float* stage_tgt = stage_cam + S::STAGE_CAM_FLOATS;
+    double* E = Ewarp + g * S::ES;                             // my env's entity block
+    double* Ecam = E + S::E_CAM;
+    double* Etgt = E + S::E_TGT;
+    double* Eobs = E + S::E_OBS;
+
+    const int env0 = (blockIdx.x * S::WARPS + warp) * EPW;     // first env of this warp
+    const int e = env0 + g;                                    // my env (local index)
+    const bool env_ok = e < p.num_envs;
+    const int er = env_ok ? e : p.num_envs - 1;                // index used for READS (tail lanes mirror the last env)
+    const int bp = p.bpad;
+    const int mode = p.mode;
+
+    // ------------------------------------------------------------------ load state
+    uint32_t tpack = 0;
+    double tx = 0.0, ty = 0.0;
+    if (j < NC) {
+        Ecam[j * 5 + 0] = p.cam_x[(size_t)j * bp + er];
+        Ecam[j * 5 + 1] = p.cam_y[(size_t)j * bp + er];
+        Ecam[j * 5 + 2] = p.cam_phi[(size_t)j * bp + er];
+        Ecam[j * 5 + 3] = p.cam_theta[(size_t)j * bp + er];
+    }
+    if (j < NT) {
+        tx = p.tgt_x[(size_t)j * bp + er];
+        ty = p.tgt_y[(size_t)j * bp + er];
+        tpack = p.tgt_pack[(size_t)j * bp + er];
+    }
+#pragma unroll
+    for (int s = 0; s < OS; ++s) {
+        const int o = j + s * G;
+        if (o < NO) {
+            Eobs[3 * o + 0] = p.obs_x[(size_t)o * bp + er];
+            Eobs[3 * o + 1] = p.obs_y[(size_t)o * bp + er];
+            Eobs[3 * o + 2] = p.obs_r[(size_t)o * bp + er];
+        }
+    }
+    Cargo cargo;
+    {
+        const uint4 c0 = p.cargo[er], c1 = p.cargo[(size_t)bp + er];
+        cargo.rem[0] = c0.x; cargo.rem[1] = c0.y; cargo.rem[2] = c0.z; cargo.rem[3] = c0.w;
+        cargo.rem[4] = c1.x; cargo.rem[5] = c1.y; cargo.rem[6] = c1.z; cargo.rem[7] = c1.w;
+    }
+    const uint4 ea = p.env_a[er];
+    const int4 eb = p.env_b[er];
+    cargo.aw[0] = ea.x; cargo.aw[1] = ea.y;
+    int episode_step = (int)ea.z, delivered = (int)ea.w;
+    int ep_reward = eb.x, delayed_ep_reward = eb.y, episode_id = eb.w;
+    float coverage_sum = __int_as_float(eb.z);
+    RngKey key{p.seed, (uint32_t)(p.env_index_base + e), (uint32_t)episode_id};
+
+    bool cargo_dirty = false, geometry_dirty = false;
+    int tdone = 0;                      // target_dones[j]
+    int reward_i = 0, delayed_i = 0;    // this step's rewards (integers)
+    int done = 0;
+    float whd[NW] = {0.f, 0.f, 0.f, 0.f};
+
+    // ------------------------------------------------------------------ _simulate (environment.py:1326-1354)
+    if (mode == MODE_STEP) {
+        if (j < NC) {   // Camera.simulate (entities.py:347-360)
+            const float2 a = reinterpret_cast<const float2*>(p.cam_act)[(size_t)er * NC + j];
+            const double da = fmin(fmax((double)a.x, -p.cam_rot_step), p.cam_rot_step);
+            const double dv = fmin(fmax((double)a.y, -p.cam_zoom_step), p.cam_zoom_step);
+            const double phi = normalize_angle(Ecam[j * 5 + 2] + da);
+            const double theta = fmin(fmax(Ecam[j * 5 + 3] + dv, p.cam_min_view), 180.0);
+            Ecam[j * 5 + 2] = phi; Ecam[j * 5 + 3] = theta;
+            if (env_ok) { p.cam_phi[(size_t)j * bp + e] = phi; p.cam_theta[(size_t)j * bp + e] = theta; }
+        }
+    }
+    if (j < NC) Ecam[j * 5 + 4] = sqrt(p.cam_area_product / Ecam[j * 5 + 3]);
+    __syncwarp();
+    if (mode == MODE_STEP) {
+        if (j < NT) {   // Target.simulate (entities.py:645-668), brute force over all discs
+            const float2 a = reinterpret_cast<const float2*>(p.tgt_act)[(size_t)er * NT + j];
+            const double step_size = p.tgt_step_size / (double)tp_capacity(tpack);
+            StepVec s{(double)a.x, (double)a.y, 0.0, 0.0, false, false};
+            s.n = norm2(s.vx, s.vy); s.has_n = true;
+            if (s.n > step_size) {   // Vector2D.norm setter: polar round trip (utils.py:223-229)
+                s.ang = atan2_deg(s.vy, s.vx); s.has_ang = true;
+                double sn, cs;
+                sincos_deg(s.ang, &sn, &cs);
+                s.n = step_size; s.vx = step_size * cs; s.vy = step_size * sn;
+            }
+            const double desx = tx + s.vx, desy = ty + s.vy;
+#pragma unroll 1
+            for (int o = 0; o < NO; ++o) obstruct_step(s, tx, ty, Eobs[3 * o], Eobs[3 * o + 1], Eobs[3 * o + 2]);
+#pragma unroll 1
+            for (int c = 0; c < NC; ++c) obstruct_step(s, tx, ty, Ecam[c * 5], Ecam[c * 5 + 1], p.cam_radius);
+            const double nx = fmin(fmax(tx + s.vx, -kTerrain), kTerrain);
+            const double ny = fmin(fmax(ty + s.vy, -kTerrain), kTerrain);
+            const int colliding = !(fabs(nx - desx) <= 1e-6 && fabs(ny - desy) <= 1e-6);
+            tx = nx; ty = ny;
+            tpack = (tpack & ~(1u << 27)) | ((uint32_t)colliding << 27);
+        }
+    }
+
+    // column masks of my entities
+    uint32_t ct_col = 0, tt_col = 0;     // who sees my target: cameras / targets
+    uint32_t cc_col = 0, tc_col = 0;     // who sees my camera: cameras / targets
+    uint32_t co_col[OS > 0 ? OS : 1], to_col[OS > 0 ? OS : 1];
+#pragma unroll
+    for (int s = 0; s < (OS > 0 ? OS : 1); ++s) { co_col[s] = 0; to_col[s] = 0; }
+    float cov_now = 0.f, cov_real = 0.f;
+
+    // aux outputs = the reference's public per-step attributes (environment.py:634-661)
+    auto write_aux = [&]() {
+        if (!p.has_aux || !env_ok) return;
+        const MateStepAux& ax = p.aux;
+        if (j < NT) {
+            for (int c = 0; c < NC; ++c) if (ax.mask_ct) ax.mask_ct[((size_t)e * NC + c) * NT + j] = (ct_col >> c) & 1;
+            for (int t = 0; t < NT; ++t) if (ax.mask_tt) ax.mask_tt[((size_t)e * NT + t) * NT + j] = (tt_col >> t) & 1;
+            if (ax.target_dones) ax.target_dones[(size_t)e * NT + j] = (uint8_t)tdone;
+            if (ax.is_colliding) ax.is_colliding[(size_t)e * NT + j] = (uint8_t)tp_colliding(tpack);
+            if (ax.warehouse_dist) for (int w = 0; w < NW; ++w) ax.warehouse_dist[((size_t)e * NT + j) * NW + w] = whd[w];
+        }
+        if (j < NC) {
+            for (int c = 0; c < NC; ++c) if (ax.mask_cc) ax.mask_cc[((size_t)e * NC + c) * NC + j] = (cc_col >> c) & 1;
+            for (int t = 0; t < NT; ++t) if (ax.mask_tc) ax.mask_tc[((size_t)e * NT + t) * NC + j] = (tc_col >> t) & 1;
+        }
+#pragma unroll
+        for (int s = 0; s < OS; ++s) {
+            const int o = j + s * G;
+            if (o < NO) {
+                for (int c = 0; c < NC; ++c) if (ax.mask_co) ax.mask_co[((size_t)e * NC + c) * NO + o] = (co_col[s] >> c) & 1;
+                for (int t = 0; t < NT; ++t) if (ax.mask_to) ax.mask_to[((size_t)e * NT + t) * NO + o] = (to_col[s] >> t) & 1;
+            }
+        }
+        if (j == 0) {
+            if (ax.coverage) {   // coverage statistics (environment.py:966-979)
+                ax.coverage[(size_t)e * 3 + 0] = cov_now;
+                ax.coverage[(size_t)e * 3 + 1] = cov_real;
+                ax.coverage[(size_t)e * 3 + 2] = delivered > 0 ? (float)((double)delayed_ep_reward / ((double)p.reward_scale * (double)delivered)) : 0.f;
+            }
+            if (ax.num_delivered) ax.num_delivered[e] = delivered;
+            if (ax.episode_step) ax.episode_step[e] = episode_step;
+        }
+    };
+
+    bool auto_reset_needed = false;
+    int draw_step = (mode == MODE_STEP) ? episode_step + 1 : episode_step;
+
+#pragma unroll 1
+    for (int pass = 0; pass < 2; ++pass) {
+        const bool do_reset = (pass == 0)
+            ? ((mode == MODE_RESET) && env_ok && (p.env_mask == nullptr || p.env_mask[e] != 0))
+            : auto_reset_needed;
+        const bool view_active = (pass == 0) || do_reset;
+        // ============================================================== reset (environment.py:679-775)
+        if (__any_sync(FULL, do_reset)) {
+            uint32_t cap2 = 0;   // bit t set => capacity 2
+            if (do_reset && j == 0) {
+                episode_id += 1;
+                key.episode = (uint32_t)episode_id;
+                int perm_c[NC > 0 ? NC : 1], perm_t[NT], perm_o[NO > 0 ? NO : 1];
+                for (int i = 0; i < NC; ++i) perm_c[i] = i;
+                for (int i = 0; i < NT; ++i) perm_t[i] = i;
+                for (int i = 0; i < NO; ++i) perm_o[i] = i;
+                if (p.shuffle) {   // environment.py:707-710 (Fisher-Yates from the top, like RandomState.shuffle)
+                    for (int i = NC - 1; i >= 1; --i) { int k = (int)rng_below(key, STREAM_SHUFFLE_CAM, i, i + 1); int t = perm_c[i]; perm_c[i] = perm_c[k]; perm_c[k] = t; }
+                    for (int i = NT - 1; i >= 1; --i) { int k = (int)rng_below(key, STREAM_SHUFFLE_TGT, i, i + 1); int t = perm_t[i]; perm_t[i] = perm_t[k]; perm_t[k] = t; }
+                    for (int i = NO - 1; i >= 1; --i) { int k = (int)rng_below(key, STREAM_SHUFFLE_OBS, i, i + 1); int t = perm_o[i]; perm_o[i] = perm_o[k]; perm_o[k] = t; }
+                }
+                if (p.num_high_capacity > 0) {   // capacities (environment.py:712-722)
+                    if (p.shuffle) {
+                        int idx[NT];
+                        for (int i = 0; i < NT; ++i) idx[i] = i;
+                        for (int i = 0; i < p.num_high_capacity; ++i) {
+                            int k = i + (int)rng_below(key, STREAM_CAPACITY, i, NT - i);
+                            int t = idx[i]; idx[i] = idx[k]; idx[k] = t;
+                            cap2 |= 1u << idx[i];
+                        }
+                    } else {
+                        for (int i = 0; i < p.num_high_capacity; ++i) cap2 |= 1u << i;
+                    }
+                }
+                // rejection placement (environment.py:724-737): cameras, obstacles, targets
+                int serial = 0;
+                for (int kind = 0; kind < 3; ++kind) {
+                    const int count = kind == 0 ? NC : (kind == 1 ? NO : NT);
+                    for (int i = 0; i < count; ++i, ++serial) {
+                        const double* range = kind == 0 ? p.cam_ranges + 4 * perm_c[i]
+                                            : (kind == 1 ? p.obs_ranges + 4 * perm_o[i] : p.tgt_ranges + 4 * perm_t[i]);
+                        const double r0 = range[0], r1 = range[1], r2 = range[2], r3 = range[3];
+                        const double min_distance = kind == 2 ? 0.0 : p.tgt_step_size;
+                        double x = 0, y = 0, radius = kind == 0 ? p.cam_radius : 0.0, phi = 0, theta = 0, rs = 0;
+                        bool ok = false;
+                        for (int attempt = 0; attempt < kResetRetries && !ok; ++attempt) {
+                            const uint32_t base = ((uint32_t)serial * kResetRetries + (uint32_t)attempt) * 8u;
+                            if (kind == 1)   // Obstacle.reset: radius first (entities.py:150-152)
+                                radius = __dadd_rn(p.obs_r_low, __dmul_rn(p.obs_r_high - p.obs_r_low, rng_u01(key, STREAM_PLACE, base + 2)));
+                            x = __dadd_rn(r0, __dmul_rn(r1 - r0, rng_u01(key, STREAM_PLACE, base + 0)));   // Entity.reset (entities.py:60-65)
+                            y = __dadd_rn(r2, __dmul_rn(r3 - r2, rng_u01(key, STREAM_PLACE, base + 1)));
+                            const double lim = __dsub_rn(kTerrain, __dmul_rn(1.2, radius));
+                            x = fmin(fmax(x, -lim), lim);
+                            y = fmin(fmax(y, -lim), lim);
+                            if (kind == 0) {   // Camera.reset (entities.py:326-334)
+                                const uint32_t nrot = (uint32_t)(360.0 / p.cam_rot_step);
+                                phi = normalize_angle(__dmul_rn(p.cam_rot_step, (double)rng_below(key, STREAM_PLACE, base + 3, nrot)));
+                                theta = __dadd_rn(p.cam_min_view, __dmul_rn(180.0 - p.cam_min_view, rng_u01(key, STREAM_PLACE, base + 4)));
+                                rs = sqrt(p.cam_area_product / theta);
+                            }
+                            ok = true;
+                            for (int w = 0; w < NW && ok; ++w) {   // warehouse discs, radius 0.75 * 75 (environment.py:724-727)
+                                const double wx = (w == 0 || w == 3) ? kWarehouseCoord : -kWarehouseCoord;
+                                const double wy = (w < 2) ? kWarehouseCoord : -kWarehouseCoord;
+                                const double dx = x - wx, dy = y - wy;
+                                const double dist = __dsqrt_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)));
+                                if (__dmul_rn(dist, 1.0 + 1e-6) < __dadd_rn(__dadd_rn(radius, 0.75 * kWarehouseRadius), min_distance)) ok = false;
+                            }
+                            const int ncam_placed = kind == 0 ? i : NC;
+                            for (int q = 0; q < ncam_placed && ok; ++q) {
+                                const double dx = x - Ecam[q * 5], dy = y - Ecam[q * 5 + 1];
+                                const double dist = __dsqrt_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)));
+                                if (__dmul_rn(dist, 1.0 + 1e-6) < __dadd_rn(__dadd_rn(radius, p.cam_radius), min_distance)) ok = false;
+                                else if (kind == 0 && dist < __dmul_rn(0.1, fmin(rs, Ecam[q * 5 + 4]))) ok = false;   // Camera.overlap (entities.py:484-489)
+                            }
+                            const int nobs_placed = kind == 0 ? 0 : (kind == 1 ? i : NO);
+                            for (int q = 0; q < nobs_placed && ok; ++q) {
+                                const double dx = x - Eobs[3 * q], dy = y - Eobs[3 * q + 1];
+                                const double dist = __dsqrt_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)));
+                                if (__dmul_rn(dist, 1.0 + 1e-6) < __dadd_rn(__dadd_rn(radius, Eobs[3 * q + 2]), min_distance)) ok = false;
+                            }
+                            // already placed targets have radius 0 and targets use min_distance 0:
+                            // dist * (1 + 1e-6) < 0 never holds (entities.py:96-100)
+                        }
+                        if (!ok && kind == 1) radius = 0.0;   // environment.py:734-736
+                        if (kind == 0) { Ecam[i * 5] = x; Ecam[i * 5 + 1] = y; Ecam[i * 5 + 2] = phi; Ecam[i * 5 + 3] = theta; Ecam[i * 5 + 4] = rs; }
+                        else if (kind == 1) { Eobs[3 * i] = x; Eobs[3 * i + 1] = y; Eobs[3 * i + 2] = radius; }
+                        else { Etgt[2 * i] = x; Etgt[2 * i + 1] = y; }
+                    }
+                }
+                // cargo table (environment.py:768-775)
+                for (int k = 0; k < 8; ++k) cargo.rem[k] = 0;
+                uint32_t draw = 0;
+                for (;;) {
+                    bool all_rows = true;
+                    for (int w = 0; w < NW; ++w) all_rows = all_rows && cargo.row_any(w);
+                    if (all_rows) break;
+                    for (int i = 0; i < p.num_cargoes_per_target * NT; ++i, ++draw) {
+                        const uint4 w4 = rng_words(key, STREAM_CARGO, draw);
+                        const int sender = (int)__umulhi(w4.x, NW);
+                        int recipient = (int)__umulhi(w4.y, NW - 1);
+                        if (recipient >= sender) recipient += 1;   // choice(4, size=2, replace=False)
+                        cargo.add(sender, recipient, 1);
+                    }
+                }
+                cargo.aw[0] = cargo.aw[1] = 0;
+                for (int gg = 0; gg < NW; ++gg) { int sum = 0; for (int w = 0; w < NW; ++w) sum += cargo.get(w, gg); cargo.awaiting_add(gg, sum); }
+            }
+            __syncwarp();
+            // distribute lane-0 results to the whole group
+            const int src = gbase;
+            cap2 = __shfl_sync(FULL, cap2, src);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) { const uint32_t v = __shfl_sync(FULL, cargo.rem[k], src); if (do_reset) cargo.rem[k] = v; }
+            { const uint32_t v0 = __shfl_sync(FULL, cargo.aw[0], src), v1 = __shfl_sync(FULL, cargo.aw[1], src); if (do_reset) { cargo.aw[0] = v0; cargo.aw[1] = v1; } }
+            const int eid = __shfl_sync(FULL, episode_id, src);
+            if (do_reset) {
+                episode_id = eid; key.episode = (uint32_t)eid;
+                episode_step = 0; delivered = 0; ep_reward = 0; delayed_ep_reward = 0; coverage_sum = 0.f;
+                cargo_dirty = true; geometry_dirty = true;
+                if (j < NT) {
+                    tx = Etgt[2 * j]; ty = Etgt[2 * j + 1];
+                    tpack = pack_target(0, -1, 0, ((cap2 >> j) & 1) ? 2 : 1, 0, 0);
+                }
+                tdone = 0;
+                draw_step = 0;
+            }
+        }
+        // publish target positions for the view phase
+        if (j < NT) { Etgt[2 * j] = tx; Etgt[2 * j + 1] = ty; }
+        __syncwarp();
+
+        // ============================================================== _update_view (environment.py:1356-1388)
+        if (view_active) {
+            ct_col = 0; tt_col = 0; cc_col = 0; tc_col = 0;
+            const double sr = p.tgt_sight_range;
+            if (j < NT) {
+#pragma unroll 1
+                for (int c = 0; c < NC; ++c) {   // Camera.perceive(target j) (entities.py:491-505)
+                    const double cx = Ecam[c * 5], cy = Ecam[c * 5 + 1];
+                    double dist, ang, relx, rely;
+                    if (!fov_reach(cx, cy, Ecam[c * 5 + 2], Ecam[c * 5 + 3], Ecam[c * 5 + 4], tx, ty, &dist, &ang, &relx, &rely)) continue;
+                    bool transmit;
+                    if (p.replay_transmit) transmit = p.replay_transmit[((size_t)er * NC + c) * NT + j] != 0;
+                    else transmit = rng_u01(key, STREAM_TRANSMIT, (uint32_t)draw_step * (uint32_t)(NC * NT) + (uint32_t)(c * NT + j)) < p.transmittance;
+                    bool sees = transmit;
+                    if (!sees) {
+                        double range = p.cam_rmax;
+                        if (NO > 0 && !p.transmittance_is_one)
+                            range = sight_range_at<NO>(Eobs, cx, cy, p.cam_rmax, normalize_angle(ang), relx / dist, rely / dist);
+                        sees = dist <= range * (1.0 + 1e-6);
+                    }
+                    ct_col |= (uint32_t)sees << c;
+                }
+#pragma unroll 1
+                for (int t = 0; t < NT; ++t) {   // Sensor.perceive target->target (entities.py:229-232)
+                    const double dx = Etgt[2 * t] - tx, dy = Etgt[2 * t + 1] - ty;
+                    const bool sees = (t == j) || norm2(dx, dy) <= sr + 0.0;
+                    tt_col |= (uint32_t)sees << t;
+                }
+            }
+            if (j < NC) {
+                const double mx = Ecam[j * 5], my = Ecam[j * 5 + 1];
+#pragma unroll 1
+                for (int c = 0; c < NC; ++c) {   // Camera.perceive(camera j), transmittance 0.0
+                    bool sees = (c == j);
+                    if (!sees) {
+                        const double cx = Ecam[c * 5], cy = Ecam[c * 5 + 1];
+                        double dist, ang, relx, rely;
+                        if (fov_reach(cx, cy, Ecam[c * 5 + 2], Ecam[c * 5 + 3], Ecam[c * 5 + 4], mx, my, &dist, &ang, &relx, &rely)) {
+                            double range = p.cam_rmax;
+                            if (NO > 0 && !p.transmittance_is_one)
+                                range = sight_range_at<NO>(Eobs, cx, cy, p.cam_rmax, normalize_angle(ang), relx / dist, rely / dist);
+                            sees = dist <= range * (1.0 + 1e-6);
+                        }
+                    }
+                    cc_col |= (uint32_t)sees << c;
+                }
+#pragma unroll 1
+                for (int t = 0; t < NT; ++t) {   // target t sees camera j
+                    const double dx = Etgt[2 * t] - mx, dy = Etgt[2 * t + 1] - my;
+                    tc_col |= (uint32_t)(norm2(dx, dy) <= sr + p.cam_radius) << t;
+                }
+            }
+#pragma unroll
+            for (int s = 0; s < OS; ++s) {
+                const int o = j + s * G;
+                co_col[s] = 0; to_col[s] = 0;
+                if (o < NO) {
+                    const double ox = Eobs[3 * o], oy = Eobs[3 * o + 1], orad = Eobs[3 * o + 2];
+#pragma unroll 1
+                    for (int c = 0; c < NC; ++c)   // entities.py:363-368 (strict <)
+                        co_col[s] |= (uint32_t)(norm2(Ecam[c * 5] - ox, Ecam[c * 5 + 1] - oy) < p.cam_rmax + orad) << c;
+#pragma unroll 1
+                    for (int t = 0; t < NT; ++t)
+                        to_col[s] |= (uint32_t)(norm2(Etgt[2 * t] - ox, Etgt[2 * t + 1] - oy) <= sr + orad) << t;
+                }
+            }
+        }
+        const bool tracked = (j < NT) && ct_col != 0;
+        const uint32_t tracked_bits = (__ballot_sync(FULL, tracked) >> gbase) & GMASK;
+
+        // ============================================================== _assign_goals (environment.py:1271-1324)
+        const bool step_goals = (pass == 0) && (mode == MODE_STEP);
+        const bool goals_active = step_goals || do_reset;
+        {
+            int bounty = tp_bounty(tpack);
+            const bool counted = goals_active && tracked && bounty > 0;
+            const int ncount = __popc((__ballot_sync(FULL, counted) >> gbase) & GMASK);
+            int r = -ncount, delayed = 0;
+            int my_wh = -1;
+            if (goals_active && j < NT) {
+                bounty = max(bounty - (int)tracked, 0);
+#pragma unroll
+                for (int w = 0; w < NW; ++w) {
+                    const double wx = (w == 0 || w == 3) ? kWarehouseCoord : -kWarehouseCoord;
+                    const double wy = (w < 2) ? kWarehouseCoord : -kWarehouseCoord;
+                    const double dx = tx - wx, dy = ty - wy;
+                    whd[w] = (float)norm2(dx, dy);
+                    if (fmax(fabs(dx), fabs(dy)) <= kWarehouseRadius) my_wh = w;
+                }
+                tpack = (tpack & ~0xFFFFu) | (uint32_t)bounty;
+            }
+            uint32_t in_bits = (__ballot_sync(FULL, my_wh >= 0) >> gbase) & GMASK;
+            const int old_goal = tp_goal(tpack);
+            // Sequential over the targets standing in a warehouse, ascending index.  The loop runs
+            // warp-wide; each group consumes its own bit set and every lane of a group performs the
+            // same updates on its replicated copy of the cargo table.
+            while (__any_sync(FULL, in_bits != 0)) {
+                const bool act = in_bits != 0;
+                const int t = act ? (__ffs(in_bits) - 1) : 0;
+                in_bits &= in_bits - 1;
+                const uint32_t tp_t = __shfl_sync(FULL, tpack, gbase + t);
+                const int w = __shfl_sync(FULL, my_wh, gbase + t);
+                if (act) {
+                    int goal = tp_goal(tp_t), weight = tp_weight(tp_t), bnty = tp_bounty(tp_t);
+                    const int capacity = tp_capacity(tp_t);
+                    int empty = tp_empty(tp_t);
+                    bool proceed = true;
+                    if (goal >= 0) {
+                        if (goal == w) {
+                            const int reward = weight * p.freight_scale + bnty;
+                            r += reward;
+                            delayed += reward - (weight * p.bounty_scale - bnty);
+                            delivered += weight;
+                            cargo.awaiting_add(goal, -weight);
+                        } else {
+                            proceed = false;
+                        }
+                    }
+                    if (proceed) {
+                        bnty = 0; weight = 0; goal = -1;
+                        if (cargo.row_any(w)) {
+                            int new_goal;
+                            if (p.replay_choice) {
+                                new_goal = p.replay_choice[(size_t)er * NT + t];
+                            } else {   // np_random.choice(flatnonzero(remaining[w] > 0))
+                                const uint32_t ncand = (uint32_t)((cargo.get(w, 0) > 0) + (cargo.get(w, 1) > 0) + (cargo.get(w, 2) > 0) + (cargo.get(w, 3) > 0));
+                                int pick = (int)rng_below(key, STREAM_CHOICE, (uint32_t)draw_step * (uint32_t)NT + (uint32_t)t, ncand);
+                                new_goal = 0;
+                                int seen = 0;
+#pragma unroll
+                                for (int gg = 0; gg < NW; ++gg) {
+                                    if (cargo.get(w, gg) > 0) { if (seen == pick) new_goal = gg; ++seen; }
+                                }
+                            }
+                            new_goal = min(max(new_goal, 0), NW - 1);
+                            const int rem = cargo.get(w, new_goal);
+                            weight = min(capacity, rem);
+                            cargo.add(w, new_goal, -weight);
+                            bnty = weight * p.bounty_scale;
+                            goal = new_goal;
+                        }
+                        cargo_dirty = true;
+                    }
+                    // empty_bits for the warehouse the target stands in (environment.py:1317-1318)
+                    empty = cargo.row_any(w) ? (empty & ~(1 << w)) : (empty | (1 << w));
+                    if (t == j) tpack = pack_target(bnty, goal, weight, capacity, empty, tp_colliding(tp_t));
+                }
+            }
+            if (goals_active && j < NT) tdone = (tp_goal(tpack) != old_goal) && (old_goal >= 0);
+            if (step_goals) { reward_i = r; delayed_i = delayed; }
+            if (__any_sync(FULL, do_reset)) {
+                if (do_reset) { tdone = 0; delivered = 0; }   // environment.py:785-788
+                // targets_start_with_cargoes (environment.py:789-812): sequential over targets without a goal
+                if (p.start_with_cargoes) {
+#pragma unroll 1
+                    for (int t = 0; t < NT; ++t) {
+                        const uint32_t tp_t = __shfl_sync(FULL, tpack, gbase + t);
+                        if (do_reset && tp_goal(tp_t) < 0) {
+                            int perm[NW] = {0, 1, 2, 3};   // np_random.permutation(4)
+#pragma unroll
+                            for (int i = NW - 1; i >= 1; --i) {
+                                const int k = (int)rng_below(key, STREAM_INIT_GOAL, (uint32_t)(t * 8 + i), (uint32_t)(i + 1));
+                                int vi = perm[0], vk = perm[0];
+#pragma unroll
+                                for (int q = 1; q < NW; ++q) { vi = (q == i) ? perm[q] : vi; vk = (q == k) ? perm[q] : vk; }
+#pragma unroll
+                                for (int q = 0; q < NW; ++q) { if (q == i) perm[q] = vk; else if (q == k) perm[q] = vi; }
+                            }
+                            bool assigned = false;
+#pragma unroll
+                            for (int k = 0; k < NW; ++k) {
+                                const int w = perm[k];
+                                if (!assigned && cargo.row_any(w)) {
+                                    const uint32_t ncand = (uint32_t)((cargo.get(w, 0) > 0) + (cargo.get(w, 1) > 0) + (cargo.get(w, 2) > 0) + (cargo.get(w, 3) > 0));
+                                    const int pick = (int)rng_below(key, STREAM_INIT_GOAL, (uint32_t)(t * 8 + 4), ncand);
+                                    int goal = 0, seen = 0;
+#pragma unroll
+                                    for (int gg = 0; gg < NW; ++gg) {
+                                        if (cargo.get(w, gg) > 0) { if (seen == pick) goal = gg; ++seen; }
+                                    }
+                                    const int capacity = tp_capacity(tp_t);
+                                    const int weight = min(capacity, cargo.get(w, goal));
+                                    cargo.add(w, goal, -weight);
+                                    if (t == j) tpack = pack_target(weight * p.bounty_scale, goal, weight, capacity, tp_empty(tp_t), 0);
+                                    assigned = true;
+                                }
+                            }
+                        }
+                    }
+                }
+            }
+        }
+        // coverage statistics of the current view (environment.py:966-972)
+        {
+            const bool wb = (j < NT) && tp_bounty(tpack) > 0;
+            const uint32_t wb_bits = (__ballot_sync(FULL, wb) >> gbase) & GMASK;
+            if (view_active || goals_active) {
+                const int nwb = __popc(wb_bits);
+                cov_now = (float)__popc(tracked_bits) / (float)NT;
+                cov_real = nwb > 0 ? (float)__popc(wb_bits & tracked_bits) / (float)nwb : 0.f;
+            }
+        }
+
+        if (!step_goals) break;
+
+        // ============================================================== finish step (environment.py:614-632)
+        ep_reward += reward_i;
+        delayed_ep_reward += delayed_i;
+        episode_step += 1;
+        coverage_sum += cov_now;
+        done = !(episode_step <= p.max_episode_steps && cargo.any_awaiting());
+        if (env_ok && j == 0) {
+            const int r_out = p.reward_sparse ? delayed_i : reward_i;
+            reinterpret_cast<float2*>(p.rewards)[e] = make_float2(-(float)r_out, (float)r_out);
+            p.done[e] = (uint8_t)done;
+            if (done) {
+                atomicAdd(&p.stats[0], 1.0f);
+                atomicAdd(&p.stats[1], (float)ep_reward);
+                atomicAdd(&p.stats[2], (float)episode_step);
+                atomicAdd(&p.stats[3], (float)delivered);
+                atomicAdd(&p.stats[4], coverage_sum / (float)episode_step);
+            }
+        }
+        write_aux();   // aux reflects the step just taken (before any auto-reset)
+        auto_reset_needed = env_ok && done && (p.flags & MATE_STEP_AUTO_RESET);
+        if (!__any_sync(FULL, auto_reset_needed)) break;
+    }
+    if (mode != MODE_STEP) write_aux();
+    if (mode == MODE_STEP && lane == 0 && warp == 0) {
+        const int first = blockIdx.x * S::ENVS_PER_CTA;
+        const int n = min(S::ENVS_PER_CTA, p.num_envs - first);
+        if (n > 0) atomicAdd(&p.stats[5], (float)n);
+    }
+
+    // ------------------------------------------------------------------ write state back
+    if (env_ok) {
+        if (j < NT) {
+            if (mode != MODE_OBSERVE) {
+                p.tgt_x[(size_t)j * bp + e] = tx;
+                p.tgt_y[(size_t)j * bp + e] = ty;
+                p.tgt_pack[(size_t)j * bp + e] = tpack;
+            }
+        }
+        if (geometry_dirty) {
+            if (j < NC) {
+                p.cam_x[(size_t)j * bp + e] = Ecam[j * 5 + 0];
+                p.cam_y[(size_t)j * bp + e] = Ecam[j * 5 + 1];
+                p.cam_phi[(size_t)j * bp + e] = Ecam[j * 5 + 2];
+                p.cam_theta[(size_t)j * bp + e] = Ecam[j * 5 + 3];
+            }
+#pragma unroll
+            for (int s = 0; s < OS; ++s) {
+                const int o = j + s * G;
+                if (o < NO) {
+                    p.obs_x[(size_t)o * bp + e] = Eobs[3 * o + 0];
+                    p.obs_y[(size_t)o * bp + e] = Eobs[3 * o + 1];
+                    p.obs_r[(size_t)o * bp + e] = Eobs[3 * o + 2];
+                }
+            }
+        }
+        if (j == 0 && mode != MODE_OBSERVE) {
+            if (cargo_dirty) {
+                p.cargo[e] = make_uint4(cargo.rem[0], cargo.rem[1], cargo.rem[2], cargo.rem[3]);
+                p.cargo[(size_t)bp + e] = make_uint4(cargo.rem[4], cargo.rem[5], cargo.rem[6], cargo.rem[7]);
+            }
+            p.env_a[e] = make_uint4(cargo.aw[0], cargo.aw[1], (uint32_t)episode_step, (uint32_t)delivered);
+            p.env_b[e] = make_int4(ep_reward, delayed_ep_reward, __float_as_int(coverage_sum), episode_id);
+        }
+    }
+
+    // ------------------------------------------------------------------ joint_observation (environment.py:908-983)
+    // Each entity-owning lane scatters its (masked) public state into every observer's row.
+    float* srow_cam = stage_cam + g * S::CAM_ROW;
+    float* srow_tgt = stage_tgt + g * S::TGT_ROW;
+    constexpr int C_SELF = 13, C_TGT = 22, C_OBS = 22 + 5 * NT, C_CAM = 22 + 5 * NT + 4 * NO;
+    constexpr int T_SELF = 13, T_CAM = 27, T_OBS = 27 + 7 * NC, T_TGT = 27 + 7 * NC + 4 * NO;
+    if (j < NT) {   // target entity j: Target.state (entities.py:631-637)
+        const float fx = (float)tx, fy = (float)ty, fsr = (float)p.tgt_sight_range;
+        const int goal = tp_goal(tpack), weight = tp_weight(tpack), capacity = tp_capacity(tpack), empty = tp_empty(tpack);
+        const float floaded = (goal >= 0 && weight > 0) ? 1.f : 0.f;
+#pragma unroll
+        for (int c = 0; c < NC; ++c) {
+            float* q = srow_cam + c * DC + C_TGT + 5 * j;
+            const bool m = (ct_col >> c) & 1;
+            q[0] = m ? fx : 0.f; q[1] = m ? fy : 0.f; q[2] = m ? fsr : 0.f; q[3] = m ? floaded : 0.f; q[4] = m ? 1.f : 0.f;
+        }
+#pragma unroll
+        for (int t = 0; t < NT; ++t) {
+            float* q = srow_tgt + t * DT + T_TGT + 5 * j;
+            const bool m = (tt_col >> t) & 1;
+            q[0] = m ? fx : 0.f; q[1] = m ? fy : 0.f; q[2] = m ? fsr : 0.f; q[3] = m ? floaded : 0.f; q[4] = m ? 1.f : 0.f;
+        }
+        // my own row: preserved data + private state
+        float* q = srow_tgt + j * DT;
+        q[0] = (float)NC; q[1] = (float)NT; q[2] = (float)NO; q[3] = (float)j;
+        q[4] = 925.f; q[5] = 925.f; q[6] = -925.f; q[7] = 925.f; q[8] = -925.f; q[9] = -925.f; q[10] = 925.f; q[11] = -925.f;
+        q[12] = 75.f;
+        q += T_SELF;
+        q[0] = fx; q[1] = fy; q[2] = fsr; q[3] = floaded;
+        q[4] = (float)(p.tgt_step_size / (double)capacity); q[5] = (float)capacity;
+#pragma unroll
+        for (int w = 0; w < NW; ++w) { q[6 + w] = (goal == w) ? (float)weight : 0.f; q[10 + w] = (float)((empty >> w) & 1); }
+    }
+    if (j < NC) {   // camera entity j: Camera.state (entities.py:313-324)
+        const double phi = Ecam[j * 5 + 2], rs = Ecam[j * 5 + 4];
+        double sn, cs;
+        sincos_deg(phi, &sn, &cs);
+        const float v0 = (float)Ecam[j * 5], v1 = (float)Ecam[j * 5 + 1], v2 = (float)p.cam_radius;
+        const float v3 = (float)(rs * cs), v4 = (float)(rs * sn), v5 = (float)Ecam[j * 5 + 3];
+#pragma unroll
+        for (int c = 0; c < NC; ++c) {
+            float* q = srow_cam + c * DC + C_CAM + 7 * j;
+            const bool m = (cc_col >> c) & 1;
+            q[0] = m ? v0 : 0.f; q[1] = m ? v1 : 0.f; q[2] = m ? v2 : 0.f; q[3] = m ? v3 : 0.f;
+            q[4] = m ? v4 : 0.f; q[5] = m ? v5 : 0.f; q[6] = m ? 1.f : 0.f;
+        }
+#pragma unroll
+        for (int t = 0; t < NT; ++t) {
+            float* q = srow_tgt + t * DT + T_CAM + 7 * j;
+            const bool m = (tc_col >> t) & 1;
+            q[0] = m ? v0 : 0.f; q[1] = m ? v1 : 0.f; q[2] = m ? v2 : 0.f; q[3] = m ? v3 : 0.f;
+            q[4] = m ? v4 : 0.f; q[5] = m ? v5 : 0.f; q[6] = m ? 1.f : 0.f;
+        }
+        float* q = srow_cam + j * DC;
+        q[0] = (float)NC; q[1] = (float)NT; q[2] = (float)NO; q[3] = (float)j;
+        q[4] = 925.f; q[5] = 925.f; q[6] = -925.f; q[7] = 925.f; q[8] = -925.f; q[9] = -925.f; q[10] = 925.f; q[11] = -925.f;
+        q[12] = 75.f;
+        q += C_SELF;
+        q[0] = v0; q[1] = v1; q[2] = v2; q[3] = v3; q[4] = v4; q[5] = v5;
+        q[6] = (float)p.cam_rmax; q[7] = (float)p.cam_rot_step; q[8] = (float)p.cam_zoom_step;
+    }
+#pragma unroll
+    for (int s = 0; s < OS; ++s) {   // obstacle entities: Obstacle.state (entities.py:147-148)
+        const int o = j + s * G;
+        if (o < NO) {
+            const float v0 = (float)Eobs[3 * o], v1 = (float)Eobs[3 * o + 1], v2 = (float)Eobs[3 * o + 2];
+#pragma unroll
+            for (int c = 0; c < NC; ++c) {
+                float* q = srow_cam + c * DC + C_OBS + 4 * o;
+                const bool m = (co_col[s] >> c) & 1;
+                q[0] = m ? v0 : 0.f; q[1] = m ? v1 : 0.f; q[2] = m ? v2 : 0.f; q[3] = m ? 1.f : 0.f;
+            }
+#pragma unroll
+            for (int t = 0; t < NT; ++t) {
+                float* q = srow_tgt + t * DT + T_OBS + 4 * o;
+                const bool m = (to_col[s] >> t) & 1;
+                q[0] = m ? v0 : 0.f; q[1] = m ? v1 : 0.f; q[2] = m ? v2 : 0.f; q[3] = m ? 1.f : 0.f;
+            }
+        }
+    }
+    __syncwarp();
+
+    // ------------------------------------------------------------------ staged rows -> HBM
+    // The warp's EPW environments are contiguous in both output tensors.
+    {
+        const int nvalid = min(EPW, p.num_envs - env0);
+        if (nvalid > 0) {
+            if (NC > 0) {
+                const int nfl = nvalid * S::CAM_ROW;
+                float* dst = p.cam_obs + (size_t)env0 * S::CAM_ROW;
+                if (S::CAM_VEC && nvalid == EPW) {
+                    const float4* s4 = reinterpret_cast<const float4*>(stage_cam);
+                    float4* d4 = reinterpret_cast<float4*>(dst);
+                    for (int i = lane; i < nfl / 4; i += 32) d4[i] = s4[i];
+                } else {
+                    for (int i = lane; i < nfl; i += 32) dst[i] = stage_cam[i];
+                }
+            }
+            const int nfl = nvalid * S::TGT_ROW;
+            float* dst = p.tgt_obs + (size_t)env0 * S::TGT_ROW;
+            if (S::TGT_VEC && nvalid == EPW) {
+                const float4* s4 = reinterpret_cast<const float4*>(stage_tgt);
+                float4* d4 = reinterpret_cast<float4*>(dst);
+                for (int i = lane; i < nfl / 4; i += 32) d4[i] = s4[i];
+            } else {
+                for (int i = lane; i < nfl; i += 32) dst[i] = stage_tgt[i];
+            }
+        }
+    }
+}
+
+}  // namespace mate

@@ -1,0 +1,190 @@
+"""Low-level Python binding of the C ABI (``include/mate_b200.h``).
+
+PyTorch is used only for device memory and streams: tensors are allocated here and their
+raw device pointers are handed to ``libmate_b200.so``.  There is no CPU path.
+"""
+
+import ctypes
+
+import numpy as np
+import torch
+
+from mate_b200 import _abi
+
+
+class MateError(RuntimeError):
+    pass
+
+
+def _check(lib, rc):
+    if rc != 0:
+        msg = lib.mate_b200_last_error().decode('utf-8', 'replace')
+        if rc == -1:
+            raise ValueError(msg)
+        raise MateError(f'mate_b200 error {rc}: {msg}')
+
+
+def _dptr(t):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+class BatchedSim:
+    """One batch of MultiAgentTracking environments resident on one GPU."""
+
+    def __init__(self, flat_config, num_envs, device=0, env_index_base=0):
+        if not torch.cuda.is_available():
+            raise RuntimeError('mate_b200 needs a CUDA device (there is no CPU fallback)')
+        self.lib = _abi.load_library()
+        self.cfg = dict(flat_config)
+        self._cfg_struct = _abi.make_config_struct(self.cfg)
+        self.B = int(num_envs)
+        self.nc = int(self.cfg['num_cameras'])
+        self.nt = int(self.cfg['num_targets'])
+        self.no = int(self.cfg['num_obstacles'])
+        index = device if isinstance(device, int) else (torch.device(device).index or 0)
+        self.device = torch.device('cuda', index)
+        self.handle = ctypes.c_void_p()
+        _check(self.lib, self.lib.mate_b200_create(ctypes.byref(self._cfg_struct), self.B, self.device.index,
+                                                   int(env_index_base), ctypes.byref(self.handle)))
+        dc, dt = ctypes.c_int32(), ctypes.c_int32()
+        _check(self.lib, self.lib.mate_b200_obs_dims(self.handle, ctypes.byref(dc), ctypes.byref(dt)))
+        self.dc, self.dt = dc.value, dt.value
+        dev = self.device
+        self.cam_obs = torch.zeros((self.B, self.nc, self.dc), dtype=torch.float32, device=dev)
+        self.tgt_obs = torch.zeros((self.B, self.nt, self.dt), dtype=torch.float32, device=dev)
+        self.rewards = torch.zeros((self.B, 2), dtype=torch.float32, device=dev)
+        self.done = torch.zeros((self.B,), dtype=torch.uint8, device=dev)
+        self._stats = torch.zeros(16, dtype=torch.float32, device=dev)
+        self._aux = None
+        self._aux_struct = None
+        self._zero_cam_act = torch.zeros((self.B, max(self.nc, 1), 2), dtype=torch.float32, device=dev)
+
+    def close(self):
+        if getattr(self, 'handle', None) is not None and self.handle:
+            self.lib.mate_b200_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:  # pylint: disable=broad-except
+            pass
+
+    # ------------------------------------------------------------------ helpers
+    def _stream(self):
+        return ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def alloc_aux(self):
+        """Device tensors for every MateStepAux field."""
+        tmap = {np.uint8: torch.uint8, np.float32: torch.float32, np.int32: torch.int32}
+        self._aux = {
+            name: torch.zeros(shape(self.B, self.nc, self.nt, self.no), dtype=tmap[dtype], device=self.device)
+            for name, _, dtype, shape in _abi.AUX_FIELDS
+        }
+        s = _abi.MateStepAux()
+        for name, ctype, _, _ in _abi.AUX_FIELDS:
+            setattr(s, name, ctypes.cast(ctypes.c_void_p(self._aux[name].data_ptr()), ctype))
+        self._aux_struct = s
+        return self._aux
+
+    @property
+    def aux(self):
+        if self._aux is None:
+            self.alloc_aux()
+        return self._aux
+
+    def _replay_struct(self, replay):
+        if replay is None:
+            return None, None
+        transmit, choice = replay
+        keep = []
+        s = _abi.MateReplay()
+        if transmit is not None:
+            t = torch.as_tensor(np.ascontiguousarray(transmit, dtype=np.uint8)).to(self.device)
+            t = t.reshape(self.B, self.nc, self.nt).contiguous()
+            keep.append(t)
+            s.transmit = ctypes.cast(ctypes.c_void_p(t.data_ptr()), _abi.c_uint8_p)
+        if choice is not None:
+            c = torch.as_tensor(np.ascontiguousarray(choice, dtype=np.int8)).to(self.device)
+            c = c.reshape(self.B, self.nt).contiguous()
+            keep.append(c)
+            s.goal_choice = ctypes.cast(ctypes.c_void_p(c.data_ptr()), _abi.c_int8_p)
+        return s, keep
+
+    def _actions(self, cam_act, tgt_act):
+        tgt_act = torch.as_tensor(tgt_act, dtype=torch.float32, device=self.device)
+        tgt_act = tgt_act.reshape(self.B, self.nt, 2).contiguous()
+        if self.nc:
+            cam_act = torch.as_tensor(cam_act, dtype=torch.float32, device=self.device)
+            cam_act = cam_act.reshape(self.B, self.nc, 2).contiguous()
+        else:
+            cam_act = self._zero_cam_act
+        return cam_act, tgt_act
+
+    # ------------------------------------------------------------------ API
+    def reset(self, seed=0, env_mask=None):
+        mask = None
+        if env_mask is not None:
+            mask = torch.as_tensor(env_mask, device=self.device).to(torch.uint8).contiguous()
+        with torch.cuda.device(self.device):
+            _check(self.lib, self.lib.mate_b200_reset(self.handle, _dptr(mask), int(seed), _dptr(self.cam_obs),
+                                                      _dptr(self.tgt_obs), self._stream()))
+        return self.cam_obs, self.tgt_obs
+
+    def step(self, cam_act, tgt_act, auto_reset=True, replay=None, aux=False):
+        cam_act, tgt_act = self._actions(cam_act, tgt_act)
+        rs, keep = self._replay_struct(replay)
+        if aux and self._aux is None:
+            self.alloc_aux()
+        with torch.cuda.device(self.device):
+            _check(self.lib, self.lib.mate_b200_step(
+                self.handle, _dptr(cam_act), _dptr(tgt_act), _dptr(self.cam_obs), _dptr(self.tgt_obs),
+                _dptr(self.rewards), _dptr(self.done),
+                ctypes.byref(self._aux_struct) if aux else None,
+                ctypes.byref(rs) if rs is not None else None,
+                _abi.MATE_STEP_AUTO_RESET if auto_reset else 0, self._stream()))
+        del keep
+        return (self.cam_obs, self.tgt_obs), self.rewards, self.done
+
+    def observe(self, replay=None, aux=False):
+        rs, keep = self._replay_struct(replay)
+        if aux and self._aux is None:
+            self.alloc_aux()
+        with torch.cuda.device(self.device):
+            _check(self.lib, self.lib.mate_b200_observe(
+                self.handle, _dptr(self.cam_obs), _dptr(self.tgt_obs),
+                ctypes.byref(self._aux_struct) if aux else None,
+                ctypes.byref(rs) if rs is not None else None, self._stream()))
+        del keep
+        return self.cam_obs, self.tgt_obs
+
+    def step_host(self, cam_act, tgt_act, out, auto_reset=True):
+        """Host-buffer step: `cam_act`/`tgt_act` and the tensors in `out` (cam_obs, tgt_obs,
+        rewards, done) are CPU tensors (pinned for full PCIe speed)."""
+        cam_obs, tgt_obs, rewards, done = out
+        _check(self.lib, self.lib.mate_b200_step_host(
+            self.handle, _dptr(cam_act) if self.nc else None, _dptr(tgt_act),
+            _dptr(cam_obs) if self.nc else None, _dptr(tgt_obs), _dptr(rewards), _dptr(done),
+            _abi.MATE_STEP_AUTO_RESET if auto_reset else 0))
+        return out
+
+    def get_state(self):
+        arrays = _abi.alloc_state_arrays(self.B, self.nc, self.nt, self.no)
+        view = _abi.state_view_from_arrays(arrays)
+        _check(self.lib, self.lib.mate_b200_get_state(self.handle, ctypes.byref(view)))
+        return arrays
+
+    def set_state(self, arrays):
+        arrays = dict(arrays)
+        view = _abi.state_view_from_arrays(arrays)
+        _check(self.lib, self.lib.mate_b200_set_state(self.handle, ctypes.byref(view)))
+
+    def episode_stats(self, reset_after=False):
+        with torch.cuda.device(self.device):
+            _check(self.lib, self.lib.mate_b200_episode_stats(self.handle, _dptr(self._stats), int(reset_after),
+                                                              self._stream()))
+        return self._stats
+
+    @property
+    def launch_count(self):
+        return int(self.lib.mate_b200_launch_count(self.handle))
