@@ -91,20 +91,45 @@ struct Params {
     const double* cam_ranges; const double* tgt_ranges; const double* obs_ranges;  // device [N][4]
 };
 
+// Static, load-balanced assignment of obstacles to the lanes of a group: every lane already
+// owns camera j and/or target j; obstacles go greedily to the lane with the least packing work.
+template <int NC, int NT, int NO, int G>
+struct ObstacleMap {
+    int owner[NO > 0 ? NO : 1] = {};
+    int slot[NO > 0 ? NO : 1] = {};
+    int count[G] = {};
+    int max_count = 0;
+    constexpr ObstacleMap() {
+        int load[G] = {};
+        for (int j = 0; j < G; ++j)
+            load[j] = (j < NT ? 5 * (NC + NT) + 27 : 0) + (j < NC ? 7 * (NC + NT) + 22 : 0);
+        for (int o = 0; o < NO; ++o) {
+            int best = G - 1;
+            for (int j = G - 1; j >= 0; --j) if (load[j] < load[best]) best = j;
+            owner[o] = best; slot[o] = count[best]; count[best] += 1; load[best] += 4 * (NC + NT);
+        }
+        for (int j = 0; j < G; ++j) if (count[j] > max_count) max_count = count[j];
+    }
+};
+
 template <int NC, int NT, int NO>
 struct Shape {
+    static constexpr int NO_ = NO;
     static constexpr int MAXE = (NC > NT ? NC : NT) > 1 ? (NC > NT ? NC : NT) : 1;
     static constexpr int G = MAXE <= 1 ? 1 : MAXE <= 2 ? 2 : MAXE <= 4 ? 4 : MAXE <= 8 ? 8 : MAXE <= 16 ? 16 : 32;
     static constexpr int EPW = 32 / G;                       // environments per warp
-    static constexpr int OS = NO == 0 ? 0 : (NO + G - 1) / G; // obstacle slots per lane
+    static constexpr ObstacleMap<NC, NT, NO, G> MAP{};
+    static constexpr int OS = MAP.max_count;                 // obstacle slots per lane
     static constexpr int DC = 22 + 5 * NT + 4 * NO + 7 * NC; // mate/constants.py:267-282
     static constexpr int DT = 27 + 7 * NC + 4 * NO + 5 * NT; // mate/constants.py:285-300
-    // shared-memory entity block per env (doubles): cams (x,y,phi,theta,rs), tgts (x,y), obstacles (x,y,r)
-    static constexpr int CAMF = 5;
+    // shared-memory entity block per env (doubles): cams (x, y, phi, theta, rs, rs^2, cos phi, sin phi,
+    // cos^2(theta/2)), tgts (x, y), obstacles (x, y, r)
+    static constexpr int CAMF = 9;
     static constexpr int E_CAM = 0;
     static constexpr int E_TGT = E_CAM + CAMF * NC;
     static constexpr int E_OBS = E_TGT + 2 * NT;
-    static constexpr int E_RAW = E_OBS + 3 * NO;
+    static constexpr int E_SCR = E_OBS + 3 * NO;             // 16 x u32 scratch (reset results)
+    static constexpr int E_RAW = E_SCR + 8;
     static constexpr int ES = E_RAW | 1;                     // odd stride (doubles) -> conflict-free group broadcast LDS.64
     static constexpr int CAM_ROW = NC * DC;                  // floats per env in cam_obs
     static constexpr int TGT_ROW = NT * DT;
@@ -122,11 +147,30 @@ struct Shape {
 };
 
 // ---- small math helpers --------------------------------------------------------------------
-__device__ __forceinline__ double normalize_angle(double a) {   // mate/utils.py:155-158, Python float %
+// mate/utils.py:155-158: (a + 180) % 360 - 180 with Python's float modulo.  Every angle the
+// kernel normalises lies in (-540, 540), where fmod reduces to one exact add/subtract, so this
+// produces the same bits as the reference expression.
+__device__ __forceinline__ double normalize_angle(double a) {
     double x = a + 180.0;
-    double m = fmod(x, 360.0);
-    if (m != 0.0) { if (m < 0.0) m += 360.0; } else { m = 0.0; }
-    return m - 180.0;
+    if (x < 0.0) x += 360.0;
+    else if (x >= 360.0) x -= 360.0;
+    return x - 180.0;
+}
+// sqrt(d2) <= t, decided on squares; the exact square root is only taken inside a 1e-12 band
+__device__ __noinline__ bool dist_cmp_exact(double d2, double t, bool strict) {
+    const double d = sqrt(d2);
+    return strict ? d < t : d <= t;
+}
+// t2lo = t^2 (1 - 1e-12), t2hi = t^2 (1 + 1e-12)
+__device__ __forceinline__ bool dist_le(double d2, double t, double t2lo, double t2hi) {
+    if (d2 < t2lo) return true;
+    if (d2 > t2hi) return false;
+    return dist_cmp_exact(d2, t, false);
+}
+__device__ __forceinline__ bool dist_lt(double d2, double t, double t2lo, double t2hi) {
+    if (d2 < t2lo) return true;
+    if (d2 > t2hi) return false;
+    return dist_cmp_exact(d2, t, true);
 }
 __device__ __forceinline__ double norm2(double x, double y) { return sqrt(x * x + y * y); }
 __device__ __forceinline__ double atan2_deg(double y, double x) { return atan2(y, x) * kRad2Deg; }
@@ -135,7 +179,7 @@ __device__ __forceinline__ void sincos_deg(double deg, double* s, double* c) { s
 // ---- Philox4x32-10, same draw scheme as oracle/mate_oracle.c ------------------------------
 struct RngKey { unsigned long long seed; uint32_t env; uint32_t episode; };
 
-__device__ inline uint4 philox(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1) {
+__device__ __noinline__ uint4 philox(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1) {
 #pragma unroll
     for (int r = 0; r < 10; ++r) {
         uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
@@ -194,24 +238,18 @@ struct Cargo {
 // (vx, vy) is the step vector with cached norm n (n < 0 => recompute), cached angle `ang`
 // (valid if has_ang), origin (ox, oy); disc centre (px, py), radius R.
 // =============================================================================================
-struct StepVec { double vx, vy, n, ang; bool has_n, has_ang; };
+struct StepVec { double vx, vy, n, ang, bound; bool has_n, has_ang; };   // bound >= |v| for the cheap reject
 
-__device__ __forceinline__ void obstruct_step(StepVec& s, double ox, double oy, double px, double py, double R) {
+__device__ __noinline__ StepVec obstruct_exact(StepVec s, double ox, double oy, double px, double py, double R) {
     const double relx = px - ox, rely = py - oy;
-    const double d2 = relx * relx + rely * rely;
-    // cheap conservative reject (|v| <= ~step_size + slack): d >= n + R  certainly holds
-    if (s.has_n) {
-        const double reach = s.n + R;
-        if (d2 > reach * reach * (1.0 + 1e-9)) return;
-    }
-    const double reln = sqrt(d2);
+    const double reln = norm2(relx, rely);
     if (!s.has_n) { s.n = norm2(s.vx, s.vy); s.has_n = true; }
     const double norm = s.n;
     if (norm == 0.0 || reln < R) {   // return -ray
         s.vx = -s.vx; s.vy = -s.vy; s.has_n = false; s.has_ang = false;
-        return;
+        return s;
     }
-    if (reln >= norm + R) return;
+    if (reln >= norm + R) return s;
     const double inner = relx * s.vx + rely * s.vy;
     if (inner >= 0.0) {
         const double c = fmin(1.0, inner / (reln * norm));
@@ -227,9 +265,19 @@ __device__ __forceinline__ void obstruct_step(StepVec& s, double ox, double oy, 
                 const double k = (norm - nn) * hc / (R * R);
                 s.vx = s.vx + radx * k; s.vy = s.vy + rady * k;
                 s.has_n = false; s.has_ang = false;
+                s.bound = fabs(s.vx) + fabs(s.vy);
             }
         }
     }
+    return s;
+}
+
+// cheap conservative reject: with |v| <= bound, `relative.norm >= norm + radius` certainly holds
+__device__ __forceinline__ void obstruct_step(StepVec& s, double ox, double oy, double px, double py, double R) {
+    const double relx = px - ox, rely = py - oy;
+    const double reach = s.bound + R;
+    if (relx * relx + rely * rely > reach * reach * (1.0 + 1e-9)) return;
+    s = obstruct_exact(s, ox, oy, px, py, R);
 }
 
 // =============================================================================================
@@ -328,22 +376,263 @@ __device__ __noinline__ double sight_range_at(const double* __restrict__ Eobs, d
     return slope * (a - P.angle) + rho_p;
 }
 
-// Camera.perceive (mate/entities.py:491-505) up to the stochastic draw; returns
-// 0 = not in range/sector, 1 = reached the draw.  Outputs dist and the raw bearing.
-__device__ __forceinline__ int fov_reach(double cx, double cy, double phi, double theta, double rs,
-                                         double qx, double qy, double* dist_out, double* ang_out,
-                                         double* relx_out, double* rely_out) {
+// Camera.perceive (mate/entities.py:491-505) up to the stochastic draw, exact arithmetic of
+// the reference: returns 0 = not in range/sector, 1 = reached the draw.
+__device__ __noinline__ int fov_reach_exact(double cx, double cy, double phi, double theta, double rs,
+                                            double qx, double qy) {
     const double relx = qx - cx, rely = qy - cy;
-    const double d2 = relx * relx + rely * rely;
-    if (d2 > rs * rs * (1.0 + 1e-9)) return 0;      // certainly dist > rs
-    const double dist = sqrt(d2);
+    const double dist = norm2(relx, rely);
     if (dist > rs) return 0;
     const double ang = atan2_deg(rely, relx);
     double ra = fabs(phi - ang);
     ra = fmin(ra, 360.0 - ra);
     if (ra * 2.0 > theta) return 0;
-    *dist_out = dist; *ang_out = ang; *relx_out = relx; *rely_out = rely;
     return 1;
+}
+
+// The same two tests decided on squares / dot products (no sqrt, no atan2); only when a test
+// falls inside a 1e-9 relative band around its boundary is the exact expression evaluated.
+// C = camera block {x, y, phi, theta, rs, rs^2, cos phi, sin phi, cos^2(theta/2)}.
+__device__ __forceinline__ int fov_reach(const double* __restrict__ C, double qx, double qy) {
+    const double relx = qx - C[0], rely = qy - C[1];
+    const double d2 = relx * relx + rely * rely;
+    const double rs2 = C[5];
+    if (d2 > rs2 * (1.0 + 1e-9)) return 0;
+    const double dot = relx * C[6] + rely * C[7];
+    const double sq = dot >= 0.0 ? dot * dot : -(dot * dot);
+    const double diff = sq - d2 * C[8];          // >= 0  <=>  angle(rel, heading) <= theta / 2
+    const double band = 1e-9 * d2;
+    if (diff < -band) return 0;
+    if (diff > band && d2 < rs2 * (1.0 - 1e-9)) return 1;
+    return fov_reach_exact(C[0], C[1], C[2], C[3], C[4], qx, qy);
+}
+
+// Conservative occlusion classification of the query point q = cam + rel (|rel|^2 = d2) against
+// all obstacle discs, WITHOUT evaluating the sampled polyline:
+//   1 = certainly visible  (no disc comes within R + w of the segment cam->q, where w covers
+//       the +-1.02 degree fan in which the two bracketing polyline samples lie),
+//   0 = certainly occluded (q lies >= 1.02 degrees inside some disc's silhouette and beyond
+//       its tangent length, so both bracketing samples are shortened below |rel|),
+//   2 = near a silhouette edge or a disc surface: evaluate the polyline exactly.
+template <int NO>
+__device__ __forceinline__ int occlusion_fast(const double* __restrict__ Eobs, double cx, double cy,
+                                              double relx, double rely, double d2, double dist, double rmax) {
+    const double w = 0.018 * dist + 1e-3;
+    const double c1sq = 0.99984154 * 0.99984154 * (1.0 + 1e-9);   // cos^2(1.02 deg)
+    const double s1 = 0.01780139;                                   // sin(1.02 deg)
+    const double s1d = s1 * dist * (1.0 + 1e-9);
+    bool all_clear = true;
+#pragma unroll 1
+    for (int o = 0; o < NO; ++o) {
+        const double ox = Eobs[3 * o] - cx, oy = Eobs[3 * o + 1] - cy, R = Eobs[3 * o + 2];
+        const double do2 = ox * ox + oy * oy;
+        const double reach = rmax + R;
+        if (do2 > reach * reach * (1.0 + 1e-9)) continue;     // not in the camera's obstacle set (entities.py:365)
+        const double t = ox * relx + oy * rely;                // projection * |rel|
+        const double Rw = R + w;
+        double seg;                                            // squared distance centre<->segment, times d2
+        if (t <= 0.0) seg = do2 * d2;
+        else if (t >= d2) { const double ex = ox - relx, ey = oy - rely; seg = (ex * ex + ey * ey) * d2; }
+        else seg = do2 * d2 - t * t;
+        if (seg > Rw * Rw * d2 * (1.0 + 1e-9)) continue;       // clear of this disc
+        all_clear = false;
+        const double tl2 = do2 - R * R;                        // squared tangent length
+        const double pm = t - R * s1d;                         // (proj - R sin(1.02)) * |rel|
+        if (tl2 > 0.0 && pm > 0.0 && R * R > s1 * s1 * do2 * (1.0 + 1e-6) && pm * pm > tl2 * c1sq * d2 &&
+            d2 * (1.0 - 4e-6) > tl2 && do2 < reach * reach * (1.0 - 1e-9))
+            return 0;
+    }
+    return all_clear ? 1 : 2;
+}
+
+// Camera.perceive after the draw (entities.py:505): dist <= sight_range_at(angle) * (1 + 1e-6)
+template <int NO>
+__device__ __noinline__ bool occlusion_exact(const double* __restrict__ Eobs, double cx, double cy,
+                                             double relx, double rely, double dist, double rmax) {
+    const double ang = atan2_deg(rely, relx);
+    const double range = sight_range_at<NO>(Eobs, cx, cy, rmax, normalize_angle(ang), relx / dist, rely / dist);
+    return dist <= range * (1.0 + 1e-6);
+}
+
+// =============================================================================================
+// Rare paths, kept out of line so that the hot path stays inside the instruction cache
+// =============================================================================================
+
+// C = {x, y, phi, theta, rs, rs^2, cos phi, sin phi, cos^2(theta/2)}
+__device__ __noinline__ void camera_derive(double* C, double area_product) {
+    const double rs = sqrt(area_product / C[3]);      // entities.py:334,360
+    C[4] = rs; C[5] = rs * rs;
+    double sn, cs;
+    sincospi(C[2] * (1.0 / 180.0), &sn, &cs);
+    C[6] = cs; C[7] = sn;
+    const double ch = cospi(C[3] * (1.0 / 360.0));
+    C[8] = ch * ch;
+}
+
+struct ResetCfg {
+    double cam_radius, cam_min_view, cam_rot_step, cam_area_product, tgt_step_size, obs_r_low, obs_r_high;
+    const double* cam_ranges; const double* tgt_ranges; const double* obs_ranges;
+    int shuffle, num_high_capacity, num_cargoes_per_target;
+};
+
+// MultiAgentTracking.reset (mate/environment.py:679-775) for one environment, executed by ONE
+// lane: entity shuffle, capacities, rejection placement (cameras, obstacles, targets) and the
+// cargo table, on the counter-based Philox streams.  Results go to the shared-memory entity
+// block and to the 16-word scratch: [0..7] remaining cargoes (u16 pairs), [8..9] awaiting
+// (u16 pairs), [10] capacity-2 bit set.
+template <int NC, int NT, int NO, int CF>
+__device__ __noinline__ void env_reset(ResetCfg cfg, RngKey key, double* Ecam, double* Etgt, double* Eobs,
+                                       uint32_t* scr) {
+    int perm_c[NC > 0 ? NC : 1], perm_t[NT], perm_o[NO > 0 ? NO : 1];
+    for (int i = 0; i < NC; ++i) perm_c[i] = i;
+    for (int i = 0; i < NT; ++i) perm_t[i] = i;
+    for (int i = 0; i < NO; ++i) perm_o[i] = i;
+    if (cfg.shuffle) {   // environment.py:707-710 (Fisher-Yates from the top, like RandomState.shuffle)
+        for (int i = NC - 1; i >= 1; --i) { int k = (int)rng_below(key, STREAM_SHUFFLE_CAM, i, i + 1); int t = perm_c[i]; perm_c[i] = perm_c[k]; perm_c[k] = t; }
+        for (int i = NT - 1; i >= 1; --i) { int k = (int)rng_below(key, STREAM_SHUFFLE_TGT, i, i + 1); int t = perm_t[i]; perm_t[i] = perm_t[k]; perm_t[k] = t; }
+        for (int i = NO - 1; i >= 1; --i) { int k = (int)rng_below(key, STREAM_SHUFFLE_OBS, i, i + 1); int t = perm_o[i]; perm_o[i] = perm_o[k]; perm_o[k] = t; }
+    }
+    uint32_t cap2 = 0;   // bit t set => capacity 2 (environment.py:712-722)
+    if (cfg.num_high_capacity > 0) {
+        if (cfg.shuffle) {
+            int idx[NT];
+            for (int i = 0; i < NT; ++i) idx[i] = i;
+            for (int i = 0; i < cfg.num_high_capacity; ++i) {
+                int k = i + (int)rng_below(key, STREAM_CAPACITY, i, NT - i);
+                int t = idx[i]; idx[i] = idx[k]; idx[k] = t;
+                cap2 |= 1u << idx[i];
+            }
+        } else {
+            for (int i = 0; i < cfg.num_high_capacity; ++i) cap2 |= 1u << i;
+        }
+    }
+    // rejection placement (environment.py:724-737): cameras, obstacles, targets
+    int serial = 0;
+    for (int kind = 0; kind < 3; ++kind) {
+        const int count = kind == 0 ? NC : (kind == 1 ? NO : NT);
+        for (int i = 0; i < count; ++i, ++serial) {
+            const double* range = kind == 0 ? cfg.cam_ranges + 4 * perm_c[i]
+                                : (kind == 1 ? cfg.obs_ranges + 4 * perm_o[i] : cfg.tgt_ranges + 4 * perm_t[i]);
+            const double r0 = range[0], r1 = range[1], r2 = range[2], r3 = range[3];
+            const double min_distance = kind == 2 ? 0.0 : cfg.tgt_step_size;
+            double x = 0, y = 0, radius = kind == 0 ? cfg.cam_radius : 0.0, phi = 0, theta = 0, rs = 0;
+            bool ok = false;
+            for (int attempt = 0; attempt < kResetRetries && !ok; ++attempt) {
+                const uint32_t base = ((uint32_t)serial * kResetRetries + (uint32_t)attempt) * 8u;
+                if (kind == 1)   // Obstacle.reset: radius first (entities.py:150-152)
+                    radius = __dadd_rn(cfg.obs_r_low, __dmul_rn(cfg.obs_r_high - cfg.obs_r_low, rng_u01(key, STREAM_PLACE, base + 2)));
+                x = __dadd_rn(r0, __dmul_rn(r1 - r0, rng_u01(key, STREAM_PLACE, base + 0)));   // Entity.reset (entities.py:60-65)
+                y = __dadd_rn(r2, __dmul_rn(r3 - r2, rng_u01(key, STREAM_PLACE, base + 1)));
+                const double lim = __dsub_rn(kTerrain, __dmul_rn(1.2, radius));
+                x = fmin(fmax(x, -lim), lim);
+                y = fmin(fmax(y, -lim), lim);
+                if (kind == 0) {   // Camera.reset (entities.py:326-334)
+                    const uint32_t nrot = (uint32_t)(360.0 / cfg.cam_rot_step);
+                    phi = normalize_angle(__dmul_rn(cfg.cam_rot_step, (double)rng_below(key, STREAM_PLACE, base + 3, nrot)));
+                    theta = __dadd_rn(cfg.cam_min_view, __dmul_rn(180.0 - cfg.cam_min_view, rng_u01(key, STREAM_PLACE, base + 4)));
+                    rs = sqrt(cfg.cam_area_product / theta);
+                }
+                ok = true;
+                for (int w = 0; w < NW && ok; ++w) {   // warehouse discs, radius 0.75 * 75 (environment.py:724-727)
+                    const double wx = (w == 0 || w == 3) ? kWarehouseCoord : -kWarehouseCoord;
+                    const double wy = (w < 2) ? kWarehouseCoord : -kWarehouseCoord;
+                    const double dx = x - wx, dy = y - wy;
+                    const double dist = __dsqrt_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)));
+                    if (__dmul_rn(dist, 1.0 + 1e-6) < __dadd_rn(__dadd_rn(radius, 0.75 * kWarehouseRadius), min_distance)) ok = false;
+                }
+                const int ncam_placed = kind == 0 ? i : NC;
+                for (int q = 0; q < ncam_placed && ok; ++q) {
+                    const double dx = x - Ecam[q * CF], dy = y - Ecam[q * CF + 1];
+                    const double dist = __dsqrt_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)));
+                    if (__dmul_rn(dist, 1.0 + 1e-6) < __dadd_rn(__dadd_rn(radius, cfg.cam_radius), min_distance)) ok = false;
+                    else if (kind == 0 && dist < __dmul_rn(0.1, fmin(rs, Ecam[q * CF + 4]))) ok = false;   // Camera.overlap (entities.py:484-489)
+                }
+                const int nobs_placed = kind == 0 ? 0 : (kind == 1 ? i : NO);
+                for (int q = 0; q < nobs_placed && ok; ++q) {
+                    const double dx = x - Eobs[3 * q], dy = y - Eobs[3 * q + 1];
+                    const double dist = __dsqrt_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)));
+                    if (__dmul_rn(dist, 1.0 + 1e-6) < __dadd_rn(__dadd_rn(radius, Eobs[3 * q + 2]), min_distance)) ok = false;
+                }
+                // already placed targets have radius 0 and targets use min_distance 0:
+                // dist * (1 + 1e-6) < 0 never holds (entities.py:96-100)
+            }
+            if (!ok && kind == 1) radius = 0.0;   // environment.py:734-736
+            if (kind == 0) { Ecam[i * CF] = x; Ecam[i * CF + 1] = y; Ecam[i * CF + 2] = phi; Ecam[i * CF + 3] = theta; Ecam[i * CF + 4] = rs; }
+            else if (kind == 1) { Eobs[3 * i] = x; Eobs[3 * i + 1] = y; Eobs[3 * i + 2] = radius; }
+            else { Etgt[2 * i] = x; Etgt[2 * i + 1] = y; }
+        }
+    }
+    // cargo table (environment.py:768-775)
+    Cargo cargo;
+    for (int k = 0; k < 8; ++k) cargo.rem[k] = 0;
+    uint32_t draw = 0;
+    for (;;) {
+        bool all_rows = true;
+        for (int w = 0; w < NW; ++w) all_rows = all_rows && cargo.row_any(w);
+        if (all_rows) break;
+        for (int i = 0; i < cfg.num_cargoes_per_target * NT; ++i, ++draw) {
+            const uint4 w4 = rng_words(key, STREAM_CARGO, draw);
+            const int sender = (int)__umulhi(w4.x, NW);
+            int recipient = (int)__umulhi(w4.y, NW - 1);
+            if (recipient >= sender) recipient += 1;   // choice(4, size=2, replace=False)
+            cargo.add(sender, recipient, 1);
+        }
+    }
+    cargo.aw[0] = cargo.aw[1] = 0;
+    for (int gg = 0; gg < NW; ++gg) { int sum = 0; for (int w = 0; w < NW; ++w) sum += cargo.get(w, gg); cargo.awaiting_add(gg, sum); }
+    for (int k = 0; k < 8; ++k) scr[k] = cargo.rem[k];
+    scr[8] = cargo.aw[0]; scr[9] = cargo.aw[1]; scr[10] = cap2;
+}
+
+// aux outputs = the reference's public per-step attributes (environment.py:634-661)
+template <int OSN>
+struct AuxArgs {
+    uint32_t ct_col, tt_col, cc_col, tc_col, co_col[OSN], to_col[OSN];
+    int my_obs[OSN];
+    float whd[NW];
+    float cov_now, cov_real, transport;
+    int tdone, colliding, delivered, episode_step, e, j;
+};
+
+template <int NC, int NT, int NO, int OSN>
+__device__ __noinline__ void write_aux(MateStepAux ax, AuxArgs<OSN> a) {
+    const int e = a.e, j = a.j;
+    if (j < NT) {
+        if (ax.mask_ct) for (int c = 0; c < NC; ++c) ax.mask_ct[((size_t)e * NC + c) * NT + j] = (a.ct_col >> c) & 1;
+        if (ax.mask_tt) for (int t = 0; t < NT; ++t) ax.mask_tt[((size_t)e * NT + t) * NT + j] = (a.tt_col >> t) & 1;
+        if (ax.target_dones) ax.target_dones[(size_t)e * NT + j] = (uint8_t)a.tdone;
+        if (ax.is_colliding) ax.is_colliding[(size_t)e * NT + j] = (uint8_t)a.colliding;
+        if (ax.warehouse_dist) for (int w = 0; w < NW; ++w) ax.warehouse_dist[((size_t)e * NT + j) * NW + w] = a.whd[w];
+    }
+    if (j < NC) {
+        if (ax.mask_cc) for (int c = 0; c < NC; ++c) ax.mask_cc[((size_t)e * NC + c) * NC + j] = (a.cc_col >> c) & 1;
+        if (ax.mask_tc) for (int t = 0; t < NT; ++t) ax.mask_tc[((size_t)e * NT + t) * NC + j] = (a.tc_col >> t) & 1;
+    }
+    for (int s = 0; s < OSN; ++s) {
+        const int o = a.my_obs[s];
+        if (o >= 0 && NO > 0) {
+            if (ax.mask_co) for (int c = 0; c < NC; ++c) ax.mask_co[((size_t)e * NC + c) * NO + o] = (a.co_col[s] >> c) & 1;
+            if (ax.mask_to) for (int t = 0; t < NT; ++t) ax.mask_to[((size_t)e * NT + t) * NO + o] = (a.to_col[s] >> t) & 1;
+        }
+    }
+    if (j == 0) {
+        if (ax.coverage) {   // coverage statistics (environment.py:966-979)
+            ax.coverage[(size_t)e * 3 + 0] = a.cov_now;
+            ax.coverage[(size_t)e * 3 + 1] = a.cov_real;
+            ax.coverage[(size_t)e * 3 + 2] = a.transport;
+        }
+        if (ax.num_delivered) ax.num_delivered[e] = a.delivered;
+        if (ax.episode_step) ax.episode_step[e] = a.episode_step;
+    }
+}
+
+template <class S, int O>
+__device__ __forceinline__ void assign_obstacles(int j, int* my_obs) {
+    if constexpr (O < S::NO_) {
+        constexpr int owner = S::MAP.owner[O], slot = S::MAP.slot[O];
+        if (j == owner) my_obs[slot] = O;
+        assign_obstacles<S, O + 1>(j, my_obs);
+    }
 }
 
 // =============================================================================================
@@ -353,7 +642,8 @@ template <int NC, int NT, int NO>
 __global__ void __launch_bounds__(Shape<NC, NT, NO>::WARPS * 32)
 mate_step_kernel(const Params p) {
     using S = Shape<NC, NT, NO>;
-    constexpr int G = S::G, EPW = S::EPW, OS = S::OS, DC = S::DC, DT = S::DT;
+    constexpr int G = S::G, EPW = S::EPW, OS = S::OS, DC = S::DC, DT = S::DT, CF = S::CAMF;
+    constexpr int OSN = OS > 0 ? OS : 1;
     constexpr uint32_t FULL = 0xffffffffu;
     constexpr uint32_t GMASK = G == 32 ? 0xffffffffu : ((1u << G) - 1u);
 
@@ -369,6 +659,7 @@ mate_step_kernel(const Params p) {
     double* Ecam = E + S::E_CAM;
     double* Etgt = E + S::E_TGT;
     double* Eobs = E + S::E_OBS;
+    uint32_t* scr = reinterpret_cast<uint32_t*>(E + S::E_SCR);
 
     const int env0 = (blockIdx.x * S::WARPS + warp) * EPW;     // first env of this warp
     const int e = env0 + g;                                    // my env (local index)
@@ -377,14 +668,20 @@ mate_step_kernel(const Params p) {
     const int bp = p.bpad;
     const int mode = p.mode;
 
+    // obstacles owned by this lane (static, load-balanced map)
+    int my_obs[OSN];
+#pragma unroll
+    for (int s = 0; s < OSN; ++s) my_obs[s] = -1;
+    assign_obstacles<S, 0>(j, my_obs);
+
     // ------------------------------------------------------------------ load state
     uint32_t tpack = 0;
     double tx = 0.0, ty = 0.0;
     if (j < NC) {
-        Ecam[j * 5 + 0] = p.cam_x[(size_t)j * bp + er];
-        Ecam[j * 5 + 1] = p.cam_y[(size_t)j * bp + er];
-        Ecam[j * 5 + 2] = p.cam_phi[(size_t)j * bp + er];
-        Ecam[j * 5 + 3] = p.cam_theta[(size_t)j * bp + er];
+        Ecam[j * CF + 0] = p.cam_x[(size_t)j * bp + er];
+        Ecam[j * CF + 1] = p.cam_y[(size_t)j * bp + er];
+        Ecam[j * CF + 2] = p.cam_phi[(size_t)j * bp + er];
+        Ecam[j * CF + 3] = p.cam_theta[(size_t)j * bp + er];
     }
     if (j < NT) {
         tx = p.tgt_x[(size_t)j * bp + er];
@@ -393,8 +690,8 @@ mate_step_kernel(const Params p) {
     }
 #pragma unroll
     for (int s = 0; s < OS; ++s) {
-        const int o = j + s * G;
-        if (o < NO) {
+        const int o = my_obs[s];
+        if (o >= 0) {
             Eobs[3 * o + 0] = p.obs_x[(size_t)o * bp + er];
             Eobs[3 * o + 1] = p.obs_y[(size_t)o * bp + er];
             Eobs[3 * o + 2] = p.obs_r[(size_t)o * bp + er];
@@ -408,6 +705,17 @@ mate_step_kernel(const Params p) {
     }
     const uint4 ea = p.env_a[er];
     const int4 eb = p.env_b[er];
+
+    // zero the staged observation rows while the loads are in flight: masked-out entries of
+    // an observation are all-zero, so the packer below only writes what is visible
+    {
+        float4* z = reinterpret_cast<float4*>(stage_cam);
+        constexpr int NZ = (S::STAGE_CAM_FLOATS + S::STAGE_TGT_FLOATS) / 4;
+        const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 4
+        for (int i = lane; i < NZ; i += 32) z[i] = zero;
+    }
+
     cargo.aw[0] = ea.x; cargo.aw[1] = ea.y;
     int episode_step = (int)ea.z, delivered = (int)ea.w;
     int ep_reward = eb.x, delayed_ep_reward = eb.y, episode_id = eb.w;
@@ -421,88 +729,78 @@ mate_step_kernel(const Params p) {
     float whd[NW] = {0.f, 0.f, 0.f, 0.f};
 
     // ------------------------------------------------------------------ _simulate (environment.py:1326-1354)
-    if (mode == MODE_STEP) {
-        if (j < NC) {   // Camera.simulate (entities.py:347-360)
+    if (j < NC) {
+        double* C = Ecam + j * CF;
+        if (mode == MODE_STEP) {   // Camera.simulate (entities.py:347-360)
             const float2 a = reinterpret_cast<const float2*>(p.cam_act)[(size_t)er * NC + j];
             const double da = fmin(fmax((double)a.x, -p.cam_rot_step), p.cam_rot_step);
             const double dv = fmin(fmax((double)a.y, -p.cam_zoom_step), p.cam_zoom_step);
-            const double phi = normalize_angle(Ecam[j * 5 + 2] + da);
-            const double theta = fmin(fmax(Ecam[j * 5 + 3] + dv, p.cam_min_view), 180.0);
-            Ecam[j * 5 + 2] = phi; Ecam[j * 5 + 3] = theta;
+            const double phi = normalize_angle(C[2] + da);
+            const double theta = fmin(fmax(C[3] + dv, p.cam_min_view), 180.0);
+            C[2] = phi; C[3] = theta;
             if (env_ok) { p.cam_phi[(size_t)j * bp + e] = phi; p.cam_theta[(size_t)j * bp + e] = theta; }
         }
+        camera_derive(C, p.cam_area_product);
     }
-    if (j < NC) Ecam[j * 5 + 4] = sqrt(p.cam_area_product / Ecam[j * 5 + 3]);
     __syncwarp();
-    if (mode == MODE_STEP) {
-        if (j < NT) {   // Target.simulate (entities.py:645-668), brute force over all discs
-            const float2 a = reinterpret_cast<const float2*>(p.tgt_act)[(size_t)er * NT + j];
-            const double step_size = p.tgt_step_size / (double)tp_capacity(tpack);
-            StepVec s{(double)a.x, (double)a.y, 0.0, 0.0, false, false};
-            s.n = norm2(s.vx, s.vy); s.has_n = true;
-            if (s.n > step_size) {   // Vector2D.norm setter: polar round trip (utils.py:223-229)
-                s.ang = atan2_deg(s.vy, s.vx); s.has_ang = true;
-                double sn, cs;
-                sincos_deg(s.ang, &sn, &cs);
-                s.n = step_size; s.vx = step_size * cs; s.vy = step_size * sn;
+    if (mode == MODE_STEP && j < NT) {   // Target.simulate (entities.py:645-668), brute force over all discs
+        const float2 a = reinterpret_cast<const float2*>(p.tgt_act)[(size_t)er * NT + j];
+        const double step_size = p.tgt_step_size / (double)tp_capacity(tpack);
+        StepVec s{(double)a.x, (double)a.y, 0.0, 0.0, step_size, false, false};
+        const double n2 = s.vx * s.vx + s.vy * s.vy;
+        if (n2 > step_size * step_size * (1.0 - 1e-12)) {
+            s.n = sqrt(n2); s.has_n = true;
+            if (s.n > step_size) {
+                // Vector2D.norm setter (utils.py:223-229): the reference re-derives the vector from
+                // (step_size, atan2(v)); v * (step_size / |v|) is the same vector to 1 ulp
+                const double k = step_size / s.n;
+                s.vx *= k; s.vy *= k; s.n = step_size;
             }
-            const double desx = tx + s.vx, desy = ty + s.vy;
-#pragma unroll 1
-            for (int o = 0; o < NO; ++o) obstruct_step(s, tx, ty, Eobs[3 * o], Eobs[3 * o + 1], Eobs[3 * o + 2]);
-#pragma unroll 1
-            for (int c = 0; c < NC; ++c) obstruct_step(s, tx, ty, Ecam[c * 5], Ecam[c * 5 + 1], p.cam_radius);
-            const double nx = fmin(fmax(tx + s.vx, -kTerrain), kTerrain);
-            const double ny = fmin(fmax(ty + s.vy, -kTerrain), kTerrain);
-            const int colliding = !(fabs(nx - desx) <= 1e-6 && fabs(ny - desy) <= 1e-6);
-            tx = nx; ty = ny;
-            tpack = (tpack & ~(1u << 27)) | ((uint32_t)colliding << 27);
+            s.bound = s.n * (1.0 + 1e-12);
         }
+        const double desx = tx + s.vx, desy = ty + s.vy;
+#pragma unroll 1
+        for (int o = 0; o < NO; ++o) obstruct_step(s, tx, ty, Eobs[3 * o], Eobs[3 * o + 1], Eobs[3 * o + 2]);
+#pragma unroll 1
+        for (int c = 0; c < NC; ++c) obstruct_step(s, tx, ty, Ecam[c * CF], Ecam[c * CF + 1], p.cam_radius);
+        const double nx = fmin(fmax(tx + s.vx, -kTerrain), kTerrain);
+        const double ny = fmin(fmax(ty + s.vy, -kTerrain), kTerrain);
+        const int colliding = !(fabs(nx - desx) <= 1e-6 && fabs(ny - desy) <= 1e-6);
+        tx = nx; ty = ny;
+        tpack = (tpack & ~(1u << 27)) | ((uint32_t)colliding << 27);
     }
 
     // column masks of my entities
     uint32_t ct_col = 0, tt_col = 0;     // who sees my target: cameras / targets
     uint32_t cc_col = 0, tc_col = 0;     // who sees my camera: cameras / targets
-    uint32_t co_col[OS > 0 ? OS : 1], to_col[OS > 0 ? OS : 1];
+    uint32_t co_col[OSN], to_col[OSN];
 #pragma unroll
-    for (int s = 0; s < (OS > 0 ? OS : 1); ++s) { co_col[s] = 0; to_col[s] = 0; }
+    for (int s = 0; s < OSN; ++s) { co_col[s] = 0; to_col[s] = 0; }
     float cov_now = 0.f, cov_real = 0.f;
 
-    // aux outputs = the reference's public per-step attributes (environment.py:634-661)
-    auto write_aux = [&]() {
+    auto emit_aux = [&]() {
         if (!p.has_aux || !env_ok) return;
-        const MateStepAux& ax = p.aux;
-        if (j < NT) {
-            for (int c = 0; c < NC; ++c) if (ax.mask_ct) ax.mask_ct[((size_t)e * NC + c) * NT + j] = (ct_col >> c) & 1;
-            for (int t = 0; t < NT; ++t) if (ax.mask_tt) ax.mask_tt[((size_t)e * NT + t) * NT + j] = (tt_col >> t) & 1;
-            if (ax.target_dones) ax.target_dones[(size_t)e * NT + j] = (uint8_t)tdone;
-            if (ax.is_colliding) ax.is_colliding[(size_t)e * NT + j] = (uint8_t)tp_colliding(tpack);
-            if (ax.warehouse_dist) for (int w = 0; w < NW; ++w) ax.warehouse_dist[((size_t)e * NT + j) * NW + w] = whd[w];
-        }
-        if (j < NC) {
-            for (int c = 0; c < NC; ++c) if (ax.mask_cc) ax.mask_cc[((size_t)e * NC + c) * NC + j] = (cc_col >> c) & 1;
-            for (int t = 0; t < NT; ++t) if (ax.mask_tc) ax.mask_tc[((size_t)e * NT + t) * NC + j] = (tc_col >> t) & 1;
-        }
+        AuxArgs<OSN> a;
+        a.ct_col = ct_col; a.tt_col = tt_col; a.cc_col = cc_col; a.tc_col = tc_col;
 #pragma unroll
-        for (int s = 0; s < OS; ++s) {
-            const int o = j + s * G;
-            if (o < NO) {
-                for (int c = 0; c < NC; ++c) if (ax.mask_co) ax.mask_co[((size_t)e * NC + c) * NO + o] = (co_col[s] >> c) & 1;
-                for (int t = 0; t < NT; ++t) if (ax.mask_to) ax.mask_to[((size_t)e * NT + t) * NO + o] = (to_col[s] >> t) & 1;
-            }
-        }
-        if (j == 0) {
-            if (ax.coverage) {   // coverage statistics (environment.py:966-979)
-                ax.coverage[(size_t)e * 3 + 0] = cov_now;
-                ax.coverage[(size_t)e * 3 + 1] = cov_real;
-                ax.coverage[(size_t)e * 3 + 2] = delivered > 0 ? (float)((double)delayed_ep_reward / ((double)p.reward_scale * (double)delivered)) : 0.f;
-            }
-            if (ax.num_delivered) ax.num_delivered[e] = delivered;
-            if (ax.episode_step) ax.episode_step[e] = episode_step;
-        }
+        for (int s = 0; s < OSN; ++s) { a.co_col[s] = co_col[s]; a.to_col[s] = to_col[s]; a.my_obs[s] = my_obs[s]; }
+#pragma unroll
+        for (int w = 0; w < NW; ++w) a.whd[w] = whd[w];
+        a.cov_now = cov_now; a.cov_real = cov_real;
+        a.transport = delivered > 0 ? (float)((double)delayed_ep_reward / ((double)p.reward_scale * (double)delivered)) : 0.f;
+        a.tdone = tdone; a.colliding = tp_colliding(tpack); a.delivered = delivered; a.episode_step = episode_step;
+        a.e = e; a.j = j;
+        write_aux<NC, NT, NO, OSN>(p.aux, a);
     };
 
     bool auto_reset_needed = false;
     int draw_step = (mode == MODE_STEP) ? episode_step + 1 : episode_step;
+
+    // squared thresholds of the omnidirectional sensing tests
+    const double sr = p.tgt_sight_range;
+    const double sr_lo = sr * sr * (1.0 - 1e-12), sr_hi = sr * sr * (1.0 + 1e-12);
+    const double src = sr + p.cam_radius;
+    const double src_lo = src * src * (1.0 - 1e-12), src_hi = src * src * (1.0 + 1e-12);
 
 #pragma unroll 1
     for (int pass = 0; pass < 2; ++pass) {
@@ -512,116 +810,25 @@ mate_step_kernel(const Params p) {
         const bool view_active = (pass == 0) || do_reset;
         // ============================================================== reset (environment.py:679-775)
         if (__any_sync(FULL, do_reset)) {
-            uint32_t cap2 = 0;   // bit t set => capacity 2
             if (do_reset && j == 0) {
-                episode_id += 1;
-                key.episode = (uint32_t)episode_id;
-                int perm_c[NC > 0 ? NC : 1], perm_t[NT], perm_o[NO > 0 ? NO : 1];
-                for (int i = 0; i < NC; ++i) perm_c[i] = i;
-                for (int i = 0; i < NT; ++i) perm_t[i] = i;
-                for (int i = 0; i < NO; ++i) perm_o[i] = i;
-                if (p.shuffle) {   // environment.py:707-710 (Fisher-Yates from the top, like RandomState.shuffle)
-                    for (int i = NC - 1; i >= 1; --i) { int k = (int)rng_below(key, STREAM_SHUFFLE_CAM, i, i + 1); int t = perm_c[i]; perm_c[i] = perm_c[k]; perm_c[k] = t; }
-                    for (int i = NT - 1; i >= 1; --i) { int k = (int)rng_below(key, STREAM_SHUFFLE_TGT, i, i + 1); int t = perm_t[i]; perm_t[i] = perm_t[k]; perm_t[k] = t; }
-                    for (int i = NO - 1; i >= 1; --i) { int k = (int)rng_below(key, STREAM_SHUFFLE_OBS, i, i + 1); int t = perm_o[i]; perm_o[i] = perm_o[k]; perm_o[k] = t; }
-                }
-                if (p.num_high_capacity > 0) {   // capacities (environment.py:712-722)
-                    if (p.shuffle) {
-                        int idx[NT];
-                        for (int i = 0; i < NT; ++i) idx[i] = i;
-                        for (int i = 0; i < p.num_high_capacity; ++i) {
-                            int k = i + (int)rng_below(key, STREAM_CAPACITY, i, NT - i);
-                            int t = idx[i]; idx[i] = idx[k]; idx[k] = t;
-                            cap2 |= 1u << idx[i];
-                        }
-                    } else {
-                        for (int i = 0; i < p.num_high_capacity; ++i) cap2 |= 1u << i;
-                    }
-                }
-                // rejection placement (environment.py:724-737): cameras, obstacles, targets
-                int serial = 0;
-                for (int kind = 0; kind < 3; ++kind) {
-                    const int count = kind == 0 ? NC : (kind == 1 ? NO : NT);
-                    for (int i = 0; i < count; ++i, ++serial) {
-                        const double* range = kind == 0 ? p.cam_ranges + 4 * perm_c[i]
-                                            : (kind == 1 ? p.obs_ranges + 4 * perm_o[i] : p.tgt_ranges + 4 * perm_t[i]);
-                        const double r0 = range[0], r1 = range[1], r2 = range[2], r3 = range[3];
-                        const double min_distance = kind == 2 ? 0.0 : p.tgt_step_size;
-                        double x = 0, y = 0, radius = kind == 0 ? p.cam_radius : 0.0, phi = 0, theta = 0, rs = 0;
-                        bool ok = false;
-                        for (int attempt = 0; attempt < kResetRetries && !ok; ++attempt) {
-                            const uint32_t base = ((uint32_t)serial * kResetRetries + (uint32_t)attempt) * 8u;
-                            if (kind == 1)   // Obstacle.reset: radius first (entities.py:150-152)
-                                radius = __dadd_rn(p.obs_r_low, __dmul_rn(p.obs_r_high - p.obs_r_low, rng_u01(key, STREAM_PLACE, base + 2)));
-                            x = __dadd_rn(r0, __dmul_rn(r1 - r0, rng_u01(key, STREAM_PLACE, base + 0)));   // Entity.reset (entities.py:60-65)
-                            y = __dadd_rn(r2, __dmul_rn(r3 - r2, rng_u01(key, STREAM_PLACE, base + 1)));
-                            const double lim = __dsub_rn(kTerrain, __dmul_rn(1.2, radius));
-                            x = fmin(fmax(x, -lim), lim);
-                            y = fmin(fmax(y, -lim), lim);
-                            if (kind == 0) {   // Camera.reset (entities.py:326-334)
-                                const uint32_t nrot = (uint32_t)(360.0 / p.cam_rot_step);
-                                phi = normalize_angle(__dmul_rn(p.cam_rot_step, (double)rng_below(key, STREAM_PLACE, base + 3, nrot)));
-                                theta = __dadd_rn(p.cam_min_view, __dmul_rn(180.0 - p.cam_min_view, rng_u01(key, STREAM_PLACE, base + 4)));
-                                rs = sqrt(p.cam_area_product / theta);
-                            }
-                            ok = true;
-                            for (int w = 0; w < NW && ok; ++w) {   // warehouse discs, radius 0.75 * 75 (environment.py:724-727)
-                                const double wx = (w == 0 || w == 3) ? kWarehouseCoord : -kWarehouseCoord;
-                                const double wy = (w < 2) ? kWarehouseCoord : -kWarehouseCoord;
-                                const double dx = x - wx, dy = y - wy;
-                                const double dist = __dsqrt_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)));
-                                if (__dmul_rn(dist, 1.0 + 1e-6) < __dadd_rn(__dadd_rn(radius, 0.75 * kWarehouseRadius), min_distance)) ok = false;
-                            }
-                            const int ncam_placed = kind == 0 ? i : NC;
-                            for (int q = 0; q < ncam_placed && ok; ++q) {
-                                const double dx = x - Ecam[q * 5], dy = y - Ecam[q * 5 + 1];
-                                const double dist = __dsqrt_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)));
-                                if (__dmul_rn(dist, 1.0 + 1e-6) < __dadd_rn(__dadd_rn(radius, p.cam_radius), min_distance)) ok = false;
-                                else if (kind == 0 && dist < __dmul_rn(0.1, fmin(rs, Ecam[q * 5 + 4]))) ok = false;   // Camera.overlap (entities.py:484-489)
-                            }
-                            const int nobs_placed = kind == 0 ? 0 : (kind == 1 ? i : NO);
-                            for (int q = 0; q < nobs_placed && ok; ++q) {
-                                const double dx = x - Eobs[3 * q], dy = y - Eobs[3 * q + 1];
-                                const double dist = __dsqrt_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)));
-                                if (__dmul_rn(dist, 1.0 + 1e-6) < __dadd_rn(__dadd_rn(radius, Eobs[3 * q + 2]), min_distance)) ok = false;
-                            }
-                            // already placed targets have radius 0 and targets use min_distance 0:
-                            // dist * (1 + 1e-6) < 0 never holds (entities.py:96-100)
-                        }
-                        if (!ok && kind == 1) radius = 0.0;   // environment.py:734-736
-                        if (kind == 0) { Ecam[i * 5] = x; Ecam[i * 5 + 1] = y; Ecam[i * 5 + 2] = phi; Ecam[i * 5 + 3] = theta; Ecam[i * 5 + 4] = rs; }
-                        else if (kind == 1) { Eobs[3 * i] = x; Eobs[3 * i + 1] = y; Eobs[3 * i + 2] = radius; }
-                        else { Etgt[2 * i] = x; Etgt[2 * i + 1] = y; }
-                    }
-                }
-                // cargo table (environment.py:768-775)
-                for (int k = 0; k < 8; ++k) cargo.rem[k] = 0;
-                uint32_t draw = 0;
-                for (;;) {
-                    bool all_rows = true;
-                    for (int w = 0; w < NW; ++w) all_rows = all_rows && cargo.row_any(w);
-                    if (all_rows) break;
-                    for (int i = 0; i < p.num_cargoes_per_target * NT; ++i, ++draw) {
-                        const uint4 w4 = rng_words(key, STREAM_CARGO, draw);
-                        const int sender = (int)__umulhi(w4.x, NW);
-                        int recipient = (int)__umulhi(w4.y, NW - 1);
-                        if (recipient >= sender) recipient += 1;   // choice(4, size=2, replace=False)
-                        cargo.add(sender, recipient, 1);
-                    }
-                }
-                cargo.aw[0] = cargo.aw[1] = 0;
-                for (int gg = 0; gg < NW; ++gg) { int sum = 0; for (int w = 0; w < NW; ++w) sum += cargo.get(w, gg); cargo.awaiting_add(gg, sum); }
+                ResetCfg rc;
+                rc.cam_radius = p.cam_radius; rc.cam_min_view = p.cam_min_view; rc.cam_rot_step = p.cam_rot_step;
+                rc.cam_area_product = p.cam_area_product; rc.tgt_step_size = p.tgt_step_size;
+                rc.obs_r_low = p.obs_r_low; rc.obs_r_high = p.obs_r_high;
+                rc.cam_ranges = p.cam_ranges; rc.tgt_ranges = p.tgt_ranges; rc.obs_ranges = p.obs_ranges;
+                rc.shuffle = p.shuffle; rc.num_high_capacity = p.num_high_capacity;
+                rc.num_cargoes_per_target = p.num_cargoes_per_target;
+                RngKey k2 = key;
+                k2.episode = (uint32_t)(episode_id + 1);
+                env_reset<NC, NT, NO, CF>(rc, k2, Ecam, Etgt, Eobs, scr);
             }
             __syncwarp();
-            // distribute lane-0 results to the whole group
-            const int src = gbase;
-            cap2 = __shfl_sync(FULL, cap2, src);
-#pragma unroll
-            for (int k = 0; k < 8; ++k) { const uint32_t v = __shfl_sync(FULL, cargo.rem[k], src); if (do_reset) cargo.rem[k] = v; }
-            { const uint32_t v0 = __shfl_sync(FULL, cargo.aw[0], src), v1 = __shfl_sync(FULL, cargo.aw[1], src); if (do_reset) { cargo.aw[0] = v0; cargo.aw[1] = v1; } }
-            const int eid = __shfl_sync(FULL, episode_id, src);
             if (do_reset) {
-                episode_id = eid; key.episode = (uint32_t)eid;
+#pragma unroll
+                for (int k = 0; k < 8; ++k) cargo.rem[k] = scr[k];
+                cargo.aw[0] = scr[8]; cargo.aw[1] = scr[9];
+                const uint32_t cap2 = scr[10];
+                episode_id += 1; key.episode = (uint32_t)episode_id;
                 episode_step = 0; delivered = 0; ep_reward = 0; delayed_ep_reward = 0; coverage_sum = 0.f;
                 cargo_dirty = true; geometry_dirty = true;
                 if (j < NT) {
@@ -630,77 +837,93 @@ mate_step_kernel(const Params p) {
                 }
                 tdone = 0;
                 draw_step = 0;
+                if (j < NC) camera_derive(Ecam + j * CF, p.cam_area_product);
             }
+            __syncwarp();
         }
         // publish target positions for the view phase
         if (j < NT) { Etgt[2 * j] = tx; Etgt[2 * j + 1] = ty; }
         __syncwarp();
 
         // ============================================================== _update_view (environment.py:1356-1388)
+        // pending bits: 0..15 camera c vs my target, 16..31 camera c vs my camera
+        uint32_t pending = 0;
         if (view_active) {
             ct_col = 0; tt_col = 0; cc_col = 0; tc_col = 0;
-            const double sr = p.tgt_sight_range;
-            if (j < NT) {
-#pragma unroll 1
-                for (int c = 0; c < NC; ++c) {   // Camera.perceive(target j) (entities.py:491-505)
-                    const double cx = Ecam[c * 5], cy = Ecam[c * 5 + 1];
-                    double dist, ang, relx, rely;
-                    if (!fov_reach(cx, cy, Ecam[c * 5 + 2], Ecam[c * 5 + 3], Ecam[c * 5 + 4], tx, ty, &dist, &ang, &relx, &rely)) continue;
-                    bool transmit;
-                    if (p.replay_transmit) transmit = p.replay_transmit[((size_t)er * NC + c) * NT + j] != 0;
-                    else transmit = rng_u01(key, STREAM_TRANSMIT, (uint32_t)draw_step * (uint32_t)(NC * NT) + (uint32_t)(c * NT + j)) < p.transmittance;
-                    bool sees = transmit;
-                    if (!sees) {
-                        double range = p.cam_rmax;
-                        if (NO > 0 && !p.transmittance_is_one)
-                            range = sight_range_at<NO>(Eobs, cx, cy, p.cam_rmax, normalize_angle(ang), relx / dist, rely / dist);
-                        sees = dist <= range * (1.0 + 1e-6);
-                    }
-                    ct_col |= (uint32_t)sees << c;
+            // ---- omnidirectional sensing by targets, Sensor.perceive (entities.py:229-232) ----
+            const bool is_t = j < NT, is_c = j < NC;
+            const double mx = is_c ? Ecam[j * CF] : 0.0, my = is_c ? Ecam[j * CF + 1] : 0.0;
+#pragma unroll 2
+            for (int t = 0; t < NT; ++t) {
+                const double ux = Etgt[2 * t], uy = Etgt[2 * t + 1];
+                if (is_t) {
+                    const double dx = ux - tx, dy = uy - ty;
+                    tt_col |= (uint32_t)((t == j) || dist_le(dx * dx + dy * dy, sr, sr_lo, sr_hi)) << t;
                 }
-#pragma unroll 1
-                for (int t = 0; t < NT; ++t) {   // Sensor.perceive target->target (entities.py:229-232)
-                    const double dx = Etgt[2 * t] - tx, dy = Etgt[2 * t + 1] - ty;
-                    const bool sees = (t == j) || norm2(dx, dy) <= sr + 0.0;
-                    tt_col |= (uint32_t)sees << t;
-                }
-            }
-            if (j < NC) {
-                const double mx = Ecam[j * 5], my = Ecam[j * 5 + 1];
-#pragma unroll 1
-                for (int c = 0; c < NC; ++c) {   // Camera.perceive(camera j), transmittance 0.0
-                    bool sees = (c == j);
-                    if (!sees) {
-                        const double cx = Ecam[c * 5], cy = Ecam[c * 5 + 1];
-                        double dist, ang, relx, rely;
-                        if (fov_reach(cx, cy, Ecam[c * 5 + 2], Ecam[c * 5 + 3], Ecam[c * 5 + 4], mx, my, &dist, &ang, &relx, &rely)) {
-                            double range = p.cam_rmax;
-                            if (NO > 0 && !p.transmittance_is_one)
-                                range = sight_range_at<NO>(Eobs, cx, cy, p.cam_rmax, normalize_angle(ang), relx / dist, rely / dist);
-                            sees = dist <= range * (1.0 + 1e-6);
-                        }
-                    }
-                    cc_col |= (uint32_t)sees << c;
-                }
-#pragma unroll 1
-                for (int t = 0; t < NT; ++t) {   // target t sees camera j
-                    const double dx = Etgt[2 * t] - mx, dy = Etgt[2 * t + 1] - my;
-                    tc_col |= (uint32_t)(norm2(dx, dy) <= sr + p.cam_radius) << t;
+                if (is_c) {
+                    const double dx = ux - mx, dy = uy - my;
+                    tc_col |= (uint32_t)dist_le(dx * dx + dy * dy, src, src_lo, src_hi) << t;
                 }
             }
 #pragma unroll
             for (int s = 0; s < OS; ++s) {
-                const int o = j + s * G;
+                const int o = my_obs[s];
                 co_col[s] = 0; to_col[s] = 0;
-                if (o < NO) {
+                if (o >= 0) {
                     const double ox = Eobs[3 * o], oy = Eobs[3 * o + 1], orad = Eobs[3 * o + 2];
-#pragma unroll 1
-                    for (int c = 0; c < NC; ++c)   // entities.py:363-368 (strict <)
-                        co_col[s] |= (uint32_t)(norm2(Ecam[c * 5] - ox, Ecam[c * 5 + 1] - oy) < p.cam_rmax + orad) << c;
-#pragma unroll 1
-                    for (int t = 0; t < NT; ++t)
-                        to_col[s] |= (uint32_t)(norm2(Etgt[2 * t] - ox, Etgt[2 * t + 1] - oy) <= sr + orad) << t;
+                    const double rc = p.cam_rmax + orad, rt = sr + orad;
+                    const double rc_lo = rc * rc * (1.0 - 1e-12), rc_hi = rc * rc * (1.0 + 1e-12);
+                    const double rt_lo = rt * rt * (1.0 - 1e-12), rt_hi = rt * rt * (1.0 + 1e-12);
+#pragma unroll 2
+                    for (int c = 0; c < NC; ++c) {   // entities.py:363-368 (strict <)
+                        const double dx = Ecam[c * CF] - ox, dy = Ecam[c * CF + 1] - oy;
+                        co_col[s] |= (uint32_t)dist_lt(dx * dx + dy * dy, rc, rc_lo, rc_hi) << c;
+                    }
+#pragma unroll 2
+                    for (int t = 0; t < NT; ++t) {
+                        const double dx = Etgt[2 * t] - ox, dy = Etgt[2 * t + 1] - oy;
+                        to_col[s] |= (uint32_t)dist_le(dx * dx + dy * dy, rt, rt_lo, rt_hi) << t;
+                    }
                 }
+            }
+            // ---- cameras: range + sector first (Camera.perceive, entities.py:494-501) ----
+            if (is_c) cc_col = 1u << j;   // environment.py:1383-1384
+#pragma unroll 1
+            for (int c = 0; c < NC; ++c) {
+                const double* C = Ecam + c * CF;
+                if (is_t && fov_reach(C, tx, ty)) pending |= 1u << c;
+                if (is_c && c != j && fov_reach(C, mx, my)) pending |= 1u << (16 + c);
+            }
+        }
+        // ---- then the stochastic transmittance draw and the occlusion test (entities.py:503-505) ----
+        // (warp-uniform loop: lanes without work keep voting)
+        while (__any_sync(FULL, pending != 0)) {
+            if (pending != 0) {
+                const int b = __ffs(pending) - 1;
+                pending &= pending - 1;
+                const int c = b & 15;
+                const bool is_cam = b >= 16;
+                const double* C = Ecam + c * CF;
+                const double cx = C[0], cy = C[1];
+                const double qx = is_cam ? Ecam[j * CF] : tx, qy = is_cam ? Ecam[j * CF + 1] : ty;
+                bool sees = false;
+                if (!is_cam) {   // camera->camera uses transmittance 0.0: binomial(1, 0) == 0
+                    if (p.replay_transmit) sees = p.replay_transmit[((size_t)er * NC + c) * NT + j] != 0;
+                    else sees = rng_u01(key, STREAM_TRANSMIT, (uint32_t)draw_step * (uint32_t)(NC * NT) + (uint32_t)(c * NT + j)) < p.transmittance;
+                }
+                if (!sees) {
+                    if (NO == 0 || p.transmittance_is_one) {
+                        sees = true;   // polyline is the flat max_sight_range circle; dist <= rs <= Rmax
+                    } else {
+                        const double relx = qx - cx, rely = qy - cy;
+                        const double d2 = relx * relx + rely * rely;
+                        const double dist = sqrt(d2);
+                        const int fast = occlusion_fast<NO>(Eobs, cx, cy, relx, rely, d2, dist, p.cam_rmax);
+                        sees = fast == 1;
+                        if (fast == 2) sees = occlusion_exact<NO>(Eobs, cx, cy, relx, rely, dist, p.cam_rmax);
+                    }
+                }
+                if (is_cam) cc_col |= (uint32_t)sees << c; else ct_col |= (uint32_t)sees << c;
             }
         }
         const bool tracked = (j < NT) && ct_col != 0;
@@ -717,13 +940,18 @@ mate_step_kernel(const Params p) {
             int my_wh = -1;
             if (goals_active && j < NT) {
                 bounty = max(bounty - (int)tracked, 0);
+                // the four warehouses sit at (+-925, +-925): the one this target could be in is
+                // given by the signs of its coordinates (constants.py:70-72 order: ++, -+, --, +-)
+                const int wq = (ty >= 0.0) ? ((tx >= 0.0) ? 0 : 1) : ((tx >= 0.0) ? 3 : 2);
+                const double ax = fabs(tx) - kWarehouseCoord, ay = fabs(ty) - kWarehouseCoord;
+                if (fmax(fabs(ax), fabs(ay)) <= kWarehouseRadius) my_wh = wq;
+                if (p.has_aux && p.aux.warehouse_dist) {
 #pragma unroll
-                for (int w = 0; w < NW; ++w) {
-                    const double wx = (w == 0 || w == 3) ? kWarehouseCoord : -kWarehouseCoord;
-                    const double wy = (w < 2) ? kWarehouseCoord : -kWarehouseCoord;
-                    const double dx = tx - wx, dy = ty - wy;
-                    whd[w] = (float)norm2(dx, dy);
-                    if (fmax(fabs(dx), fabs(dy)) <= kWarehouseRadius) my_wh = w;
+                    for (int w = 0; w < NW; ++w) {
+                        const double wx = (w == 0 || w == 3) ? kWarehouseCoord : -kWarehouseCoord;
+                        const double wy = (w < 2) ? kWarehouseCoord : -kWarehouseCoord;
+                        whd[w] = (float)norm2(tx - wx, ty - wy);
+                    }
                 }
                 tpack = (tpack & ~0xFFFFu) | (uint32_t)bounty;
             }
@@ -762,7 +990,7 @@ mate_step_kernel(const Params p) {
                                 new_goal = p.replay_choice[(size_t)er * NT + t];
                             } else {   // np_random.choice(flatnonzero(remaining[w] > 0))
                                 const uint32_t ncand = (uint32_t)((cargo.get(w, 0) > 0) + (cargo.get(w, 1) > 0) + (cargo.get(w, 2) > 0) + (cargo.get(w, 3) > 0));
-                                int pick = (int)rng_below(key, STREAM_CHOICE, (uint32_t)draw_step * (uint32_t)NT + (uint32_t)t, ncand);
+                                const int pick = (int)rng_below(key, STREAM_CHOICE, (uint32_t)draw_step * (uint32_t)NT + (uint32_t)t, ncand);
                                 new_goal = 0;
                                 int seen = 0;
 #pragma unroll
@@ -859,11 +1087,11 @@ mate_step_kernel(const Params p) {
                 atomicAdd(&p.stats[4], coverage_sum / (float)episode_step);
             }
         }
-        write_aux();   // aux reflects the step just taken (before any auto-reset)
+        emit_aux();   // aux reflects the step just taken (before any auto-reset)
         auto_reset_needed = env_ok && done && (p.flags & MATE_STEP_AUTO_RESET);
         if (!__any_sync(FULL, auto_reset_needed)) break;
     }
-    if (mode != MODE_STEP) write_aux();
+    if (mode != MODE_STEP) emit_aux();
     if (mode == MODE_STEP && lane == 0 && warp == 0) {
         const int first = blockIdx.x * S::ENVS_PER_CTA;
         const int n = min(S::ENVS_PER_CTA, p.num_envs - first);
@@ -872,24 +1100,22 @@ mate_step_kernel(const Params p) {
 
     // ------------------------------------------------------------------ write state back
     if (env_ok) {
-        if (j < NT) {
-            if (mode != MODE_OBSERVE) {
-                p.tgt_x[(size_t)j * bp + e] = tx;
-                p.tgt_y[(size_t)j * bp + e] = ty;
-                p.tgt_pack[(size_t)j * bp + e] = tpack;
-            }
+        if (j < NT && mode != MODE_OBSERVE) {
+            p.tgt_x[(size_t)j * bp + e] = tx;
+            p.tgt_y[(size_t)j * bp + e] = ty;
+            p.tgt_pack[(size_t)j * bp + e] = tpack;
         }
         if (geometry_dirty) {
             if (j < NC) {
-                p.cam_x[(size_t)j * bp + e] = Ecam[j * 5 + 0];
-                p.cam_y[(size_t)j * bp + e] = Ecam[j * 5 + 1];
-                p.cam_phi[(size_t)j * bp + e] = Ecam[j * 5 + 2];
-                p.cam_theta[(size_t)j * bp + e] = Ecam[j * 5 + 3];
+                p.cam_x[(size_t)j * bp + e] = Ecam[j * CF + 0];
+                p.cam_y[(size_t)j * bp + e] = Ecam[j * CF + 1];
+                p.cam_phi[(size_t)j * bp + e] = Ecam[j * CF + 2];
+                p.cam_theta[(size_t)j * bp + e] = Ecam[j * CF + 3];
             }
 #pragma unroll
             for (int s = 0; s < OS; ++s) {
-                const int o = j + s * G;
-                if (o < NO) {
+                const int o = my_obs[s];
+                if (o >= 0) {
                     p.obs_x[(size_t)o * bp + e] = Eobs[3 * o + 0];
                     p.obs_y[(size_t)o * bp + e] = Eobs[3 * o + 1];
                     p.obs_r[(size_t)o * bp + e] = Eobs[3 * o + 2];
@@ -907,7 +1133,8 @@ mate_step_kernel(const Params p) {
     }
 
     // ------------------------------------------------------------------ joint_observation (environment.py:908-983)
-    // Each entity-owning lane scatters its (masked) public state into every observer's row.
+    // Each entity-owning lane scatters its public state into the rows of the observers that see
+    // it (the staged rows were zero-filled above, masked-out entries stay zero).
     float* srow_cam = stage_cam + g * S::CAM_ROW;
     float* srow_tgt = stage_tgt + g * S::TGT_ROW;
     constexpr int C_SELF = 13, C_TGT = 22, C_OBS = 22 + 5 * NT, C_CAM = 22 + 5 * NT + 4 * NO;
@@ -916,17 +1143,17 @@ mate_step_kernel(const Params p) {
         const float fx = (float)tx, fy = (float)ty, fsr = (float)p.tgt_sight_range;
         const int goal = tp_goal(tpack), weight = tp_weight(tpack), capacity = tp_capacity(tpack), empty = tp_empty(tpack);
         const float floaded = (goal >= 0 && weight > 0) ? 1.f : 0.f;
-#pragma unroll
-        for (int c = 0; c < NC; ++c) {
-            float* q = srow_cam + c * DC + C_TGT + 5 * j;
-            const bool m = (ct_col >> c) & 1;
-            q[0] = m ? fx : 0.f; q[1] = m ? fy : 0.f; q[2] = m ? fsr : 0.f; q[3] = m ? floaded : 0.f; q[4] = m ? 1.f : 0.f;
+        {
+            float* q = srow_cam + C_TGT + 5 * j;
+#pragma unroll 2
+            for (int c = 0; c < NC; ++c, q += DC)
+                if ((ct_col >> c) & 1) { q[0] = fx; q[1] = fy; q[2] = fsr; q[3] = floaded; q[4] = 1.f; }
         }
-#pragma unroll
-        for (int t = 0; t < NT; ++t) {
-            float* q = srow_tgt + t * DT + T_TGT + 5 * j;
-            const bool m = (tt_col >> t) & 1;
-            q[0] = m ? fx : 0.f; q[1] = m ? fy : 0.f; q[2] = m ? fsr : 0.f; q[3] = m ? floaded : 0.f; q[4] = m ? 1.f : 0.f;
+        {
+            float* q = srow_tgt + T_TGT + 5 * j;
+#pragma unroll 2
+            for (int t = 0; t < NT; ++t, q += DT)
+                if ((tt_col >> t) & 1) { q[0] = fx; q[1] = fy; q[2] = fsr; q[3] = floaded; q[4] = 1.f; }
         }
         // my own row: preserved data + private state
         float* q = srow_tgt + j * DT;
@@ -940,24 +1167,20 @@ mate_step_kernel(const Params p) {
         for (int w = 0; w < NW; ++w) { q[6 + w] = (goal == w) ? (float)weight : 0.f; q[10 + w] = (float)((empty >> w) & 1); }
     }
     if (j < NC) {   // camera entity j: Camera.state (entities.py:313-324)
-        const double phi = Ecam[j * 5 + 2], rs = Ecam[j * 5 + 4];
-        double sn, cs;
-        sincos_deg(phi, &sn, &cs);
-        const float v0 = (float)Ecam[j * 5], v1 = (float)Ecam[j * 5 + 1], v2 = (float)p.cam_radius;
-        const float v3 = (float)(rs * cs), v4 = (float)(rs * sn), v5 = (float)Ecam[j * 5 + 3];
-#pragma unroll
-        for (int c = 0; c < NC; ++c) {
-            float* q = srow_cam + c * DC + C_CAM + 7 * j;
-            const bool m = (cc_col >> c) & 1;
-            q[0] = m ? v0 : 0.f; q[1] = m ? v1 : 0.f; q[2] = m ? v2 : 0.f; q[3] = m ? v3 : 0.f;
-            q[4] = m ? v4 : 0.f; q[5] = m ? v5 : 0.f; q[6] = m ? 1.f : 0.f;
+        const double* C = Ecam + j * CF;
+        const float v0 = (float)C[0], v1 = (float)C[1], v2 = (float)p.cam_radius;
+        const float v3 = (float)(C[4] * C[6]), v4 = (float)(C[4] * C[7]), v5 = (float)C[3];
+        {
+            float* q = srow_cam + C_CAM + 7 * j;
+#pragma unroll 2
+            for (int c = 0; c < NC; ++c, q += DC)
+                if ((cc_col >> c) & 1) { q[0] = v0; q[1] = v1; q[2] = v2; q[3] = v3; q[4] = v4; q[5] = v5; q[6] = 1.f; }
         }
-#pragma unroll
-        for (int t = 0; t < NT; ++t) {
-            float* q = srow_tgt + t * DT + T_CAM + 7 * j;
-            const bool m = (tc_col >> t) & 1;
-            q[0] = m ? v0 : 0.f; q[1] = m ? v1 : 0.f; q[2] = m ? v2 : 0.f; q[3] = m ? v3 : 0.f;
-            q[4] = m ? v4 : 0.f; q[5] = m ? v5 : 0.f; q[6] = m ? 1.f : 0.f;
+        {
+            float* q = srow_tgt + T_CAM + 7 * j;
+#pragma unroll 2
+            for (int t = 0; t < NT; ++t, q += DT)
+                if ((tc_col >> t) & 1) { q[0] = v0; q[1] = v1; q[2] = v2; q[3] = v3; q[4] = v4; q[5] = v5; q[6] = 1.f; }
         }
         float* q = srow_cam + j * DC;
         q[0] = (float)NC; q[1] = (float)NT; q[2] = (float)NO; q[3] = (float)j;
@@ -969,50 +1192,57 @@ mate_step_kernel(const Params p) {
     }
 #pragma unroll
     for (int s = 0; s < OS; ++s) {   // obstacle entities: Obstacle.state (entities.py:147-148)
-        const int o = j + s * G;
-        if (o < NO) {
+        const int o = my_obs[s];
+        if (o >= 0) {
             const float v0 = (float)Eobs[3 * o], v1 = (float)Eobs[3 * o + 1], v2 = (float)Eobs[3 * o + 2];
-#pragma unroll
-            for (int c = 0; c < NC; ++c) {
-                float* q = srow_cam + c * DC + C_OBS + 4 * o;
-                const bool m = (co_col[s] >> c) & 1;
-                q[0] = m ? v0 : 0.f; q[1] = m ? v1 : 0.f; q[2] = m ? v2 : 0.f; q[3] = m ? 1.f : 0.f;
+            {
+                float* q = srow_cam + C_OBS + 4 * o;
+#pragma unroll 2
+                for (int c = 0; c < NC; ++c, q += DC)
+                    if ((co_col[s] >> c) & 1) { q[0] = v0; q[1] = v1; q[2] = v2; q[3] = 1.f; }
             }
-#pragma unroll
-            for (int t = 0; t < NT; ++t) {
-                float* q = srow_tgt + t * DT + T_OBS + 4 * o;
-                const bool m = (to_col[s] >> t) & 1;
-                q[0] = m ? v0 : 0.f; q[1] = m ? v1 : 0.f; q[2] = m ? v2 : 0.f; q[3] = m ? 1.f : 0.f;
+            {
+                float* q = srow_tgt + T_OBS + 4 * o;
+#pragma unroll 2
+                for (int t = 0; t < NT; ++t, q += DT)
+                    if ((to_col[s] >> t) & 1) { q[0] = v0; q[1] = v1; q[2] = v2; q[3] = 1.f; }
             }
         }
     }
-    __syncwarp();
 
     // ------------------------------------------------------------------ staged rows -> HBM
-    // The warp's EPW environments are contiguous in both output tensors.
+    // The warp's EPW environments are contiguous in both output tensors: one bulk (TMA) copy
+    // per tensor, issued by one lane; tail warps fall back to a plain coalesced copy.
     {
         const int nvalid = min(EPW, p.num_envs - env0);
-        if (nvalid > 0) {
+        constexpr bool BULK = (NC == 0 || S::CAM_VEC) && S::TGT_VEC;
+        if (BULK && nvalid == EPW) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) {
+                if (NC > 0) {
+                    const uint32_t src = (uint32_t)__cvta_generic_to_shared(stage_cam);
+                    float* dst = p.cam_obs + (size_t)env0 * S::CAM_ROW;
+                    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                                 :: "l"(dst), "r"(src), "r"((uint32_t)(EPW * S::CAM_ROW * 4)) : "memory");
+                }
+                const uint32_t src = (uint32_t)__cvta_generic_to_shared(stage_tgt);
+                float* dst = p.tgt_obs + (size_t)env0 * S::TGT_ROW;
+                asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                             :: "l"(dst), "r"(src), "r"((uint32_t)(EPW * S::TGT_ROW * 4)) : "memory");
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            }
+        } else if (nvalid > 0) {
+            __syncwarp();
             if (NC > 0) {
                 const int nfl = nvalid * S::CAM_ROW;
                 float* dst = p.cam_obs + (size_t)env0 * S::CAM_ROW;
-                if (S::CAM_VEC && nvalid == EPW) {
-                    const float4* s4 = reinterpret_cast<const float4*>(stage_cam);
-                    float4* d4 = reinterpret_cast<float4*>(dst);
-                    for (int i = lane; i < nfl / 4; i += 32) d4[i] = s4[i];
-                } else {
-                    for (int i = lane; i < nfl; i += 32) dst[i] = stage_cam[i];
-                }
+                for (int i = lane; i < nfl; i += 32) dst[i] = stage_cam[i];
             }
             const int nfl = nvalid * S::TGT_ROW;
             float* dst = p.tgt_obs + (size_t)env0 * S::TGT_ROW;
-            if (S::TGT_VEC && nvalid == EPW) {
-                const float4* s4 = reinterpret_cast<const float4*>(stage_tgt);
-                float4* d4 = reinterpret_cast<float4*>(dst);
-                for (int i = lane; i < nfl / 4; i += 32) d4[i] = s4[i];
-            } else {
-                for (int i = lane; i < nfl; i += 32) dst[i] = stage_tgt[i];
-            }
+            for (int i = lane; i < nfl; i += 32) dst[i] = stage_tgt[i];
         }
     }
 }
