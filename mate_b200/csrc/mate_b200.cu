@@ -126,7 +126,7 @@ extern "C" int mate_b200_create(const MateConfig* cfg, int32_t num_envs, int32_t
     sim->device = device;
     sim->env_index_base = env_index_base;
     sim->kernel = kernel;
-    const int bpad = (int)align_up((size_t)num_envs, 128);
+    const int bpad = (int)align_up((size_t)num_envs, 256);
     sim->bpad = bpad;
 
     // one allocation, carved into the SoA arrays (each 256-byte aligned)
@@ -138,6 +138,7 @@ extern "C" int mate_b200_create(const MateConfig* cfg, int32_t num_envs, int32_t
     const size_t o_obs_x = carve(sizeof(double) * no * bpad), o_obs_y = carve(sizeof(double) * no * bpad), o_obs_r = carve(sizeof(double) * no * bpad);
     const size_t o_pack = carve(sizeof(uint32_t) * nt * bpad);
     const size_t o_cargo = carve(sizeof(uint4) * 2 * bpad), o_env_a = carve(sizeof(uint4) * bpad), o_env_b = carve(sizeof(int4) * bpad);
+    const size_t o_cc = carve(sizeof(unsigned long long) * bpad);
     const size_t o_stats = carve(sizeof(float) * 16);
     sim->state_bytes = off;
     if (cudaMalloc(&sim->state_block, off) != cudaSuccess) { delete sim; return fail(MATE_ENOMEM, "cudaMalloc(state) failed"); }
@@ -149,6 +150,7 @@ extern "C" int mate_b200_create(const MateConfig* cfg, int32_t num_envs, int32_t
     p.obs_x = (double*)(b + o_obs_x); p.obs_y = (double*)(b + o_obs_y); p.obs_r = (double*)(b + o_obs_r);
     p.tgt_pack = (uint32_t*)(b + o_pack);
     p.cargo = (uint4*)(b + o_cargo); p.env_a = (uint4*)(b + o_env_a); p.env_b = (int4*)(b + o_env_b);
+    p.cc_clear = (unsigned long long*)(b + o_cc);
     p.stats = (float*)(b + o_stats);
 
     // location ranges on device (reset)
@@ -214,7 +216,7 @@ static int launch_range(MateSim* sim, Params p, int begin, int count, cudaStream
     // SoA rows are indexed [row * bpad + env]: shifting the base pointers selects the sub-range
     p.cam_x += begin; p.cam_y += begin; p.cam_phi += begin; p.cam_theta += begin;
     p.tgt_x += begin; p.tgt_y += begin; p.obs_x += begin; p.obs_y += begin; p.obs_r += begin;
-    p.tgt_pack += begin; p.cargo += begin; p.env_a += begin; p.env_b += begin;
+    p.tgt_pack += begin; p.cargo += begin; p.env_a += begin; p.env_b += begin; p.cc_clear += begin;
     if (p.cam_act) p.cam_act += (size_t)begin * nc * 2;
     if (p.tgt_act) p.tgt_act += (size_t)begin * nt * 2;
     if (p.cam_obs) p.cam_obs += (size_t)begin * nc * dc;
@@ -240,7 +242,13 @@ static int check_obs_alignment(const void* cam_obs, const void* tgt_obs) {
 }
 
 static void fill_aux(Params& p, const MateStepAux* aux, const MateReplay* replay) {
-    if (aux) { p.aux = *aux; p.has_aux = 1; } else { memset(&p.aux, 0, sizeof(p.aux)); p.has_aux = 0; }
+    if (aux) {
+        p.aux = *aux; p.has_aux = 1;
+        p.has_aux_detail = aux->mask_ct || aux->mask_cc || aux->mask_co || aux->mask_tc || aux->mask_to || aux->mask_tt ||
+                           aux->target_dones || aux->is_colliding || aux->warehouse_dist;
+    } else {
+        memset(&p.aux, 0, sizeof(p.aux)); p.has_aux = 0; p.has_aux_detail = 0;
+    }
     p.replay_transmit = replay ? replay->transmit : nullptr;
     p.replay_choice = replay ? replay->goal_choice : nullptr;
 }
@@ -430,6 +438,8 @@ extern "C" int mate_b200_set_state(MateSim* sim, const MateStateView* v) {
             }
         if (upload(a, p.cam_x) || upload(b2, p.cam_y) || upload(c, p.cam_phi) || upload(d, p.cam_theta)) return MATE_ECUDA;
     }
+    if (v->cam_xy || v->obs_xyr)   // geometry changed: invalidate the per-episode camera line-of-sight cache
+        CUDA_TRY(cudaMemset(p.cc_clear, 0, sizeof(unsigned long long) * bp));
     if (v->tgt_xy) {
         a.assign(nt * bp, 0.0); b2.assign(nt * bp, 0.0);
         for (size_t e = 0; e < B; ++e)

@@ -72,12 +72,13 @@ struct Params {
     uint4* cargo;      // [2][bpad]  remaining_cargoes as 16 x u16
     uint4* env_a;      // [bpad] x: awaiting0|awaiting1<<16, y: awaiting2|awaiting3<<16, z: episode_step, w: delivered
     int4* env_b;       // [bpad] x: episode reward, y: delayed episode reward, z: coverage_sum (float bits), w: episode_id
+    unsigned long long* cc_clear;   // [bpad] per-episode cache: bit 63 valid, bit (8 j + c) = camera c has a clear line of sight to camera j
     float* stats;      // [16] episode statistics accumulators
     // --- per-call I/O (device) ---
     const float* cam_act; const float* tgt_act;
     float* cam_obs; float* tgt_obs; float* rewards; uint8_t* done;
     const uint8_t* env_mask;
-    MateStepAux aux; int has_aux;
+    MateStepAux aux; int has_aux; int has_aux_detail;   // detail = anything beyond coverage / num_delivered / episode_step
     const uint8_t* replay_transmit; const int8_t* replay_choice;
     // --- scalars ---
     int num_envs; int bpad; int mode; uint32_t flags;
@@ -133,17 +134,23 @@ struct Shape {
     static constexpr int ES = E_RAW | 1;                     // odd stride (doubles) -> conflict-free group broadcast LDS.64
     static constexpr int CAM_ROW = NC * DC;                  // floats per env in cam_obs
     static constexpr int TGT_ROW = NT * DT;
-    static constexpr int WARPS = 4;                          // warps per CTA
-    static constexpr int ENVS_PER_CTA = WARPS * EPW;
-    // per-warp shared memory (bytes): entity blocks + staged observation rows
     static constexpr int STAGE_CAM_FLOATS = ((EPW * CAM_ROW + 3) / 4) * 4;
     static constexpr int STAGE_TGT_FLOATS = ((EPW * TGT_ROW + 3) / 4) * 4;
+    static constexpr int STAGE_BYTES = (STAGE_CAM_FLOATS + STAGE_TGT_FLOATS) * 4;
     static constexpr int E_BYTES = ((EPW * ES * 8 + 15) / 16) * 16;
-    static constexpr int WARP_BYTES = E_BYTES + (STAGE_CAM_FLOATS + STAGE_TGT_FLOATS) * 4;
+    // Shared memory per CTA: one small entity block per warp plus a POOL of staging buffers for
+    // the packed observation rows (a warp borrows one only while it packs and stores), so that
+    // occupancy is not limited by the 6 KB/env of staged rows.
+    static constexpr int WARPS = 8;                          // warps per CTA
+    static constexpr int ENVS_PER_CTA = WARPS * EPW;
+    static constexpr int POOL_BUDGET = 112 * 1024 - WARPS * E_BYTES - 64;
+    static constexpr int NBUF = POOL_BUDGET / STAGE_BYTES >= 3 ? 3 : (POOL_BUDGET / STAGE_BYTES >= 2 ? 2 : 1);
+    static constexpr int LOCK_OFFSET = WARPS * E_BYTES;
+    static constexpr int POOL_OFFSET = LOCK_OFFSET + 64;
+    static constexpr int SMEM_BYTES = POOL_OFFSET + NBUF * STAGE_BYTES;
     // a warp's rows start at a multiple of 4 floats in the output tensors => float4 / bulk copies
     static constexpr bool CAM_VEC = (EPW * CAM_ROW) % 4 == 0;
     static constexpr bool TGT_VEC = (EPW * TGT_ROW) % 4 == 0;
-    static constexpr int SMEM_BYTES = WARPS * WARP_BYTES;
 };
 
 // ---- small math helpers --------------------------------------------------------------------
@@ -295,7 +302,7 @@ template <int NO>
 __device__ __forceinline__ double cast_ray(const double* __restrict__ Eobs, double cx, double cy,
                                            double angle, double n0, int tangent_of) {
     double sn, cs;
-    sincos_deg(angle, &sn, &cs);
+    sincospi(angle * (1.0 / 180.0), &sn, &cs);
     double n = n0;
 #pragma unroll 1
     for (int o = 0; o < NO; ++o) {
@@ -333,14 +340,18 @@ __device__ __noinline__ double sight_range_at(const double* __restrict__ Eobs, d
     for (int o = 0; o < NO; ++o) {
         const double relx = Eobs[3 * o] - cx, rely = Eobs[3 * o + 1] - cy, R = Eobs[3 * o + 2];
         const double d2 = relx * relx + rely * rely;
-        const double d = sqrt(d2);
-        if (!(d < rmax + R)) continue;            // entities.py:365 (strict)
-        if (R > d) return 0.0;                    // camera inside the disc (entities.py:378-387)
+        {   // entities.py:365 (strict <) and :378 (camera inside the disc), on squares
+            const double reach = rmax + R, reach2 = reach * reach;
+            if (d2 > reach2 * (1.0 + 1e-12)) continue;
+            if (d2 > reach2 * (1.0 - 1e-12) && !(sqrt(d2) < reach)) continue;
+            if (d2 < R * R * (1.0 + 1e-12) && R > sqrt(d2)) return 0.0;
+        }
         // prefilter: can any sample angle of this obstacle fall inside (floor(a), floor(a)+1)?
         // angular distance bearing<->centre must be <= half + 1.02 deg
         const double p = relx * ux + rely * uy + R * s1 * 1.0000001;
         if (p < 0.0) continue;
         if (p * p < (d2 - R * R) * (c1 * c1) * 0.9999999) continue;
+        const double d = sqrt(d2);
         const double ang_o = atan2_deg(rely, relx);
         const double half = asin(R / d) * kRad2Deg;
         const double left = ang_o - half, right = ang_o + half;
@@ -417,10 +428,10 @@ __device__ __forceinline__ int fov_reach(const double* __restrict__ C, double qx
 template <int NO>
 __device__ __forceinline__ int occlusion_fast(const double* __restrict__ Eobs, double cx, double cy,
                                               double relx, double rely, double d2, double dist, double rmax) {
-    const double w = 0.018 * dist + 1e-3;
     const double c1sq = 0.99984154 * 0.99984154 * (1.0 + 1e-9);   // cos^2(1.02 deg)
     const double s1 = 0.01780139;                                   // sin(1.02 deg)
     const double s1d = s1 * dist * (1.0 + 1e-9);
+    const double inv_dist = 1.0 / dist;
     bool all_clear = true;
 #pragma unroll 1
     for (int o = 0; o < NO; ++o) {
@@ -429,7 +440,9 @@ __device__ __forceinline__ int occlusion_fast(const double* __restrict__ Eobs, d
         const double reach = rmax + R;
         if (do2 > reach * reach * (1.0 + 1e-9)) continue;     // not in the camera's obstacle set (entities.py:365)
         const double t = ox * relx + oy * rely;                // projection * |rel|
-        const double Rw = R + w;
+        // half-width of the +-1.02 degree fan at the farthest range where it can meet this disc
+        const double far = fmin(dist, fmax(t, 0.0) * inv_dist * (1.0 + 1e-9) + R);
+        const double Rw = R + 0.018 * far + 1e-3;
         double seg;                                            // squared distance centre<->segment, times d2
         if (t <= 0.0) seg = do2 * d2;
         else if (t >= d2) { const double ex = ox - relx, ey = oy - rely; seg = (ex * ex + ey * ey) * d2; }
@@ -651,15 +664,15 @@ mate_step_kernel(const Params p) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int g = lane / G, j = lane % G;
     const int gbase = g * G;                                   // first lane of my group
-    unsigned char* wbase = smem_raw + (size_t)warp * S::WARP_BYTES;
-    double* Ewarp = reinterpret_cast<double*>(wbase);
-    float* stage_cam = reinterpret_cast<float*>(wbase + S::E_BYTES);
-    float* stage_tgt = stage_cam + S::STAGE_CAM_FLOATS;
+    double* Ewarp = reinterpret_cast<double*>(smem_raw + (size_t)warp * S::E_BYTES);
+    uint32_t* locks = reinterpret_cast<uint32_t*>(smem_raw + S::LOCK_OFFSET);
     double* E = Ewarp + g * S::ES;                             // my env's entity block
     double* Ecam = E + S::E_CAM;
     double* Etgt = E + S::E_TGT;
     double* Eobs = E + S::E_OBS;
     uint32_t* scr = reinterpret_cast<uint32_t*>(E + S::E_SCR);
+    if (threadIdx.x < S::NBUF) locks[threadIdx.x] = 0u;
+    __syncthreads();
 
     const int env0 = (blockIdx.x * S::WARPS + warp) * EPW;     // first env of this warp
     const int e = env0 + g;                                    // my env (local index)
@@ -705,16 +718,8 @@ mate_step_kernel(const Params p) {
     }
     const uint4 ea = p.env_a[er];
     const int4 eb = p.env_b[er];
-
-    // zero the staged observation rows while the loads are in flight: masked-out entries of
-    // an observation are all-zero, so the packer below only writes what is visible
-    {
-        float4* z = reinterpret_cast<float4*>(stage_cam);
-        constexpr int NZ = (S::STAGE_CAM_FLOATS + S::STAGE_TGT_FLOATS) / 4;
-        const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll 4
-        for (int i = lane; i < NZ; i += 32) z[i] = zero;
-    }
+    constexpr bool CC_CACHE = NC >= 2 && NC <= 8 && NO > 0;   // static camera<->camera lines of sight fit one u64
+    unsigned long long ccw = CC_CACHE ? p.cc_clear[er] : 0ull;
 
     cargo.aw[0] = ea.x; cargo.aw[1] = ea.y;
     int episode_step = (int)ea.z, delivered = (int)ea.w;
@@ -780,14 +785,26 @@ mate_step_kernel(const Params p) {
 
     auto emit_aux = [&]() {
         if (!p.has_aux || !env_ok) return;
+        const float transport = delivered > 0 ? (float)((double)delayed_ep_reward / ((double)p.reward_scale * (double)delivered)) : 0.f;
+        if (!p.has_aux_detail) {   // the common case: only the info-dict scalars (environment.py:634-639)
+            if (j == 0) {
+                if (p.aux.coverage) {
+                    p.aux.coverage[(size_t)e * 3 + 0] = cov_now;
+                    p.aux.coverage[(size_t)e * 3 + 1] = cov_real;
+                    p.aux.coverage[(size_t)e * 3 + 2] = transport;
+                }
+                if (p.aux.num_delivered) p.aux.num_delivered[e] = delivered;
+                if (p.aux.episode_step) p.aux.episode_step[e] = episode_step;
+            }
+            return;
+        }
         AuxArgs<OSN> a;
         a.ct_col = ct_col; a.tt_col = tt_col; a.cc_col = cc_col; a.tc_col = tc_col;
 #pragma unroll
         for (int s = 0; s < OSN; ++s) { a.co_col[s] = co_col[s]; a.to_col[s] = to_col[s]; a.my_obs[s] = my_obs[s]; }
 #pragma unroll
         for (int w = 0; w < NW; ++w) a.whd[w] = whd[w];
-        a.cov_now = cov_now; a.cov_real = cov_real;
-        a.transport = delivered > 0 ? (float)((double)delayed_ep_reward / ((double)p.reward_scale * (double)delivered)) : 0.f;
+        a.cov_now = cov_now; a.cov_real = cov_real; a.transport = transport;
         a.tdone = tdone; a.colliding = tp_colliding(tpack); a.delivered = delivered; a.episode_step = episode_step;
         a.e = e; a.j = j;
         write_aux<NC, NT, NO, OSN>(p.aux, a);
@@ -830,7 +847,7 @@ mate_step_kernel(const Params p) {
                 const uint32_t cap2 = scr[10];
                 episode_id += 1; key.episode = (uint32_t)episode_id;
                 episode_step = 0; delivered = 0; ep_reward = 0; delayed_ep_reward = 0; coverage_sum = 0.f;
-                cargo_dirty = true; geometry_dirty = true;
+                cargo_dirty = true; geometry_dirty = true; ccw = 0ull;
                 if (j < NT) {
                     tx = Etgt[2 * j]; ty = Etgt[2 * j + 1];
                     tpack = pack_target(0, -1, 0, ((cap2 >> j) & 1) ? 2 : 1, 0, 0);
@@ -847,7 +864,8 @@ mate_step_kernel(const Params p) {
 
         // ============================================================== _update_view (environment.py:1356-1388)
         // pending bits: 0..15 camera c vs my target, 16..31 camera c vs my camera
-        uint32_t pending = 0;
+        uint32_t pending = 0, cc_reach = 0;
+        bool cc_valid = true;
         if (view_active) {
             ct_col = 0; tt_col = 0; cc_col = 0; tc_col = 0;
             // ---- omnidirectional sensing by targets, Sensor.perceive (entities.py:229-232) ----
@@ -887,16 +905,26 @@ mate_step_kernel(const Params p) {
                 }
             }
             // ---- cameras: range + sector first (Camera.perceive, entities.py:494-501) ----
+            // camera->camera occlusion is static within an episode (neither end moves): it is
+            // evaluated once after reset / set_state for ALL ordered pairs and cached in `ccw`.
+            cc_valid = CC_CACHE && (ccw >> 63) != 0ull;
+            cc_reach = 0;
             if (is_c) cc_col = 1u << j;   // environment.py:1383-1384
 #pragma unroll 1
             for (int c = 0; c < NC; ++c) {
                 const double* C = Ecam + c * CF;
                 if (is_t && fov_reach(C, tx, ty)) pending |= 1u << c;
-                if (is_c && c != j && fov_reach(C, mx, my)) pending |= 1u << (16 + c);
+                if (is_c && c != j) {
+                    const bool reach = fov_reach(C, mx, my);
+                    cc_reach |= (uint32_t)reach << c;
+                    if (cc_valid) cc_col |= (uint32_t)(reach && ((ccw >> (8 * j + c)) & 1ull)) << c;
+                    else if (CC_CACHE || reach) pending |= 1u << (16 + c);
+                }
             }
         }
         // ---- then the stochastic transmittance draw and the occlusion test (entities.py:503-505) ----
         // (warp-uniform loop: lanes without work keep voting)
+        uint32_t cc_clear_col = 0;
         while (__any_sync(FULL, pending != 0)) {
             if (pending != 0) {
                 const int b = __ffs(pending) - 1;
@@ -923,7 +951,21 @@ mate_step_kernel(const Params p) {
                         if (fast == 2) sees = occlusion_exact<NO>(Eobs, cx, cy, relx, rely, dist, p.cam_rmax);
                     }
                 }
-                if (is_cam) cc_col |= (uint32_t)sees << c; else ct_col |= (uint32_t)sees << c;
+                if (is_cam) cc_clear_col |= (uint32_t)sees << c; else ct_col |= (uint32_t)sees << c;
+            }
+        }
+        const bool cc_fresh = view_active && !cc_valid && NC >= 2;
+        if (__any_sync(FULL, cc_fresh)) {
+            // fold the freshly evaluated static lines of sight into the mask and the per-episode cache
+            unsigned long long w = 0ull;
+#pragma unroll
+            for (int k = 0; k < NC; ++k) w |= (unsigned long long)(__shfl_sync(FULL, cc_clear_col, gbase + k) & 0xFFu) << (8 * k);
+            if (cc_fresh) {
+                cc_col |= cc_reach & cc_clear_col;
+                if (CC_CACHE) {
+                    ccw = w | (1ull << 63);
+                    if (env_ok && j == 0) p.cc_clear[e] = ccw;
+                }
             }
         }
         const bool tracked = (j < NT) && ct_col != 0;
@@ -1135,6 +1177,27 @@ mate_step_kernel(const Params p) {
     // ------------------------------------------------------------------ joint_observation (environment.py:908-983)
     // Each entity-owning lane scatters its public state into the rows of the observers that see
     // it (the staged rows were zero-filled above, masked-out entries stay zero).
+    // borrow a staging buffer from the CTA's pool (held only while packing + storing)
+    int buf = 0;
+    if (lane == 0) {
+        buf = warp % S::NBUF;
+        while (atomicCAS(&locks[buf], 0u, 1u) != 0u) {
+            buf = (buf + 1 == S::NBUF) ? 0 : buf + 1;
+            __nanosleep(32);
+        }
+        __threadfence_block();
+    }
+    buf = __shfl_sync(FULL, buf, 0);
+    float* stage_cam = reinterpret_cast<float*>(smem_raw + S::POOL_OFFSET + (size_t)buf * S::STAGE_BYTES);
+    float* stage_tgt = stage_cam + S::STAGE_CAM_FLOATS;
+    {   // masked-out entries of an observation are all-zero: clear, then write only what is visible
+        float4* z = reinterpret_cast<float4*>(stage_cam);
+        constexpr int NZ = S::STAGE_BYTES / 16;
+        const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 4
+        for (int i = lane; i < NZ; i += 32) z[i] = zero;
+    }
+    __syncwarp();
     float* srow_cam = stage_cam + g * S::CAM_ROW;
     float* srow_tgt = stage_tgt + g * S::TGT_ROW;
     constexpr int C_SELF = 13, C_TGT = 22, C_OBS = 22 + 5 * NT, C_CAM = 22 + 5 * NT + 4 * NO;
@@ -1232,17 +1295,21 @@ mate_step_kernel(const Params p) {
                              :: "l"(dst), "r"(src), "r"((uint32_t)(EPW * S::TGT_ROW * 4)) : "memory");
                 asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                 asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                __threadfence_block();
+                atomicExch(&locks[buf], 0u);
             }
-        } else if (nvalid > 0) {
+        } else {
             __syncwarp();
             if (NC > 0) {
-                const int nfl = nvalid * S::CAM_ROW;
+                const int nfl = max(nvalid, 0) * S::CAM_ROW;
                 float* dst = p.cam_obs + (size_t)env0 * S::CAM_ROW;
                 for (int i = lane; i < nfl; i += 32) dst[i] = stage_cam[i];
             }
-            const int nfl = nvalid * S::TGT_ROW;
+            const int nfl = max(nvalid, 0) * S::TGT_ROW;
             float* dst = p.tgt_obs + (size_t)env0 * S::TGT_ROW;
             for (int i = lane; i < nfl; i += 32) dst[i] = stage_tgt[i];
+            __syncwarp();
+            if (lane == 0) { __threadfence_block(); atomicExch(&locks[buf], 0u); }
         }
     }
 }
