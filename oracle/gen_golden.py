@@ -356,6 +356,28 @@ def run_resets(mate, config, seed, count, out_path):
     print(f'{os.path.basename(out_path)}: resets={count} size={os.path.getsize(out_path) / 1e6:.2f}MB')
 
 
+def run_reset_samples(mate, config, seed, count, out_path):
+    """Many post-reset states (state only): reference samples for the distributional checks of
+    the Philox-driven reset (tests/test_reset_distribution.py)."""
+    env = mate.make('MultiAgentTracking-v0', config=config)
+    u = env.unwrapped
+    env.seed(seed)
+    keys = ('cam_xy', 'cam_phi', 'cam_theta', 'tgt_xy', 'tgt_capacity', 'tgt_goal', 'tgt_goal_weight',
+            'bounties', 'obs_xyr', 'remaining', 'awaiting')
+    rows = {k: [] for k in keys}
+    for _ in range(count):
+        env.reset()
+        rec = dump_state(u)
+        for k in keys:
+            rows[k].append(np.asarray(rec[k]))
+    out = {'config_name': np.array(config), 'seed': np.int64(seed), 'count': np.int64(count)}
+    out.update(config_scalars(u))
+    for k, v in rows.items():
+        out['sample_' + k] = np.stack(v).astype(np.float32 if v[0].dtype.kind == 'f' else np.int16)
+    np.savez_compressed(out_path, **out)
+    print(f'{os.path.basename(out_path)}: reset samples={count} size={os.path.getsize(out_path) / 1e6:.2f}MB')
+
+
 TRACES = [
     # name, config, seed, steps, policy, obs_stride
     ('4v2-9_random', 'MATE-4v2-9.yaml', 0, 10050, 'random', 64),
@@ -380,6 +402,12 @@ RESETS = [
 ]
 
 
+RESET_SAMPLES = [
+    ('4v8-9_resetsamples', 'MATE-4v8-9.yaml', 200, 250),
+    ('Navigation_resetsamples', 'MATE-Navigation.yaml', 201, 150),
+]
+
+
 def main():
     parser = argparse.ArgumentParser(description=__doc__, formatter_class=argparse.RawTextHelpFormatter)
     parser.add_argument('--out', default=os.path.join(REPO, 'tests', 'golden'))
@@ -394,6 +422,10 @@ def main():
         if args.only and args.only not in name:
             continue
         run_resets(mate, config, seed, count, os.path.join(args.out, name + '.npz'))
+    for name, config, seed, count in RESET_SAMPLES:
+        if args.only and args.only not in name:
+            continue
+        run_reset_samples(mate, config, seed, count, os.path.join(args.out, name + '.npz'))
 
 
 if __name__ == '__main__':

@@ -14,7 +14,7 @@ def trace_names():
     return sorted(
         os.path.basename(p)[:-4]
         for p in glob.glob(os.path.join(GOLDEN_DIR, '*.npz'))
-        if not p.endswith('_resets.npz')
+        if not p.endswith('_resets.npz') and not p.endswith('_resetsamples.npz')
     )
 
 

@@ -1,0 +1,76 @@
+"""The reference-facing Python interface (mate_b200.make / MultiAgentTracking) on the GPU."""
+
+import numpy as np
+import pytest
+
+import golden_util as gu
+
+torch = pytest.importorskip('torch')
+pytestmark = pytest.mark.gpu
+
+
+def test_make_batched_env():
+    import mate_b200 as mate
+
+    env = mate.make('MultiAgentTracking-v0', config='MATE-4v8-9.yaml', num_envs=512)
+    assert isinstance(env, mate.MultiAgentTracking)
+    assert (env.num_cameras, env.num_targets, env.num_obstacles) == (4, 8, 9)
+    assert str(env) == '<MultiAgentTracking<MultiAgentTracking-v0>>(4 cameras, 8 targets, 9 obstacles, 512 envs)'
+    cam_obs, tgt_obs = env.reset(seed=3)
+    assert cam_obs.shape == (512, 4, 126) and tgt_obs.shape == (512, 8, 131) and cam_obs.is_cuda
+    assert env.camera_observation_space.shape == (126,) and env.target_observation_space.shape == (131,)
+    assert env.state_space.shape == (13 + 9 * 4 + 14 * 8 + 3 * 9 + 8 + 8 + 16,)
+    cam_act = torch.zeros((512, 4, 2), device='cuda')
+    tgt_act = torch.ones((512, 8, 2), device='cuda')
+    (cam_obs, tgt_obs), (cam_r, tgt_r), done, (cam_info, tgt_info) = env.step((cam_act, tgt_act))
+    assert cam_r.shape == (512,) and done.dtype == torch.bool and torch.equal(cam_r, -tgt_r)
+    assert set(cam_info) >= {'raw_reward', 'normalized_raw_reward', 'coverage_rate', 'real_coverage_rate',
+                             'mean_transport_rate', 'num_delivered_cargoes'}
+    assert env.camera_target_view_mask.shape == (512, 4, 8)
+    assert env.state().shape == (512, env.state_space.shape[0])
+    # mask attributes agree with the flags inside the observations
+    flags = cam_obs[:, :, 22:22 + 40].reshape(512, 4, 8, 5)[..., 4] > 0
+    assert torch.equal(flags, env.camera_target_view_mask)
+    stats = env.episode_statistics()
+    assert stats['env_steps'] == 512
+    with pytest.raises(ValueError):
+        mate.make('MultiAgentTracking-v0', config='MATE-4v8-9.yaml', num_envs=4, reward_type='bogus')
+    env.close()
+
+
+def test_registered_ids_and_navigation():
+    import mate_b200 as mate
+
+    env = mate.make('MATE-Navigation-v0', num_envs=64)
+    cam_obs, tgt_obs = env.reset(seed=0)
+    assert cam_obs.shape == (64, 0, 190) and tgt_obs.shape == (64, 8, 195)
+    (cam_obs, tgt_obs), rewards, done, infos = env.step((None, torch.zeros((64, 8, 2), device='cuda')))
+    assert tgt_obs.shape == (64, 8, 195)
+    env.load_config('MATE-4v2-9.yaml')
+    assert (env.num_cameras, env.num_targets) == (4, 2)
+    env.close()
+
+
+def test_reference_compatible_single_env_mode_replays_a_reference_trace():
+    """num_envs=None: NumPy float64 / float / bool / list-of-dict types of the reference, no
+    auto-reset; fed with the reference's initial state and actions it returns the reference's
+    observations (deterministic part of the trace: steps before the first stochastic draw)."""
+    import mate_b200 as mate
+
+    g = gu.load('4v8-9_greedy')
+    env = mate.make('MultiAgentTracking-v0', config=str(g['config_name']))
+    env.set_state(gu.state_arrays(g))
+    n = 0
+    for k in range(int(g['num_steps'])):
+        if g['step_reached'][k].any():
+            break
+        obs, rew, done, infos = env.step((g['step_cam_act'][k], g['step_tgt_act'][k]))
+        assert isinstance(rew[0], float) and isinstance(done, bool) and isinstance(infos[0], list)
+        assert obs[0].dtype == np.float64 and obs[0].shape == (4, 126)
+        assert rew[1] == g['step_reward'][k, 1]
+        assert (env.camera_target_view_mask.cpu().numpy() == g['step_mask_ct'][k]).all()
+        n += 1
+    assert n >= 1
+    with pytest.raises(AssertionError):
+        env.step((np.full((4, 2), np.nan), np.zeros((8, 2))))
+    env.close()
