@@ -92,24 +92,17 @@ struct Params {
     const double* cam_ranges; const double* tgt_ranges; const double* obs_ranges;  // device [N][4]
 };
 
-// Static, load-balanced assignment of obstacles to the lanes of a group: every lane already
-// owns camera j and/or target j; obstacles go greedily to the lane with the least packing work.
+// Static assignment of obstacles to the lanes of a group.  A warp executes every slot phase in
+// lock step, so what matters is the NUMBER of slots (max obstacles per lane), not the per-lane
+// total: plain round-robin, obstacle o -> lane o % G, slot o / G.
 template <int NC, int NT, int NO, int G>
 struct ObstacleMap {
     int owner[NO > 0 ? NO : 1] = {};
     int slot[NO > 0 ? NO : 1] = {};
-    int count[G] = {};
     int max_count = 0;
     constexpr ObstacleMap() {
-        int load[G] = {};
-        for (int j = 0; j < G; ++j)
-            load[j] = (j < NT ? 5 * (NC + NT) + 27 : 0) + (j < NC ? 7 * (NC + NT) + 22 : 0);
-        for (int o = 0; o < NO; ++o) {
-            int best = G - 1;
-            for (int j = G - 1; j >= 0; --j) if (load[j] < load[best]) best = j;
-            owner[o] = best; slot[o] = count[best]; count[best] += 1; load[best] += 4 * (NC + NT);
-        }
-        for (int j = 0; j < G; ++j) if (count[j] > max_count) max_count = count[j];
+        for (int o = 0; o < NO; ++o) { owner[o] = o % G; slot[o] = o / G; }
+        max_count = (NO + G - 1) / G;
     }
 };
 
@@ -129,9 +122,19 @@ struct Shape {
     static constexpr int E_CAM = 0;
     static constexpr int E_TGT = E_CAM + CAMF * NC;
     static constexpr int E_OBS = E_TGT + 2 * NT;
-    static constexpr int E_SCR = E_OBS + 3 * NO;             // 16 x u32 scratch (reset results)
-    static constexpr int E_RAW = E_SCR + 8;
-    static constexpr int ES = E_RAW | 1;                     // odd stride (doubles) -> conflict-free group broadcast LDS.64
+    static constexpr int E_SCR = ((E_OBS + 3 * NO + 1) / 2) * 2;  // 16 x u32 scratch (reset results)
+    // fp32 shadow of the entity block for the prefilters (floats, appended after the scratch):
+    // cams {x, y, rs^2, cos phi, sin phi, cos^2(theta/2)}, tgts {x, y}, obstacles {x, y, r, -}
+    static constexpr int FCAMF = 6;
+    static constexpr int F_CAM = 0;
+    static constexpr int F_TGT = F_CAM + FCAMF * NC;
+    static constexpr int F_OBS = ((F_TGT + 2 * NT + 3) / 4) * 4;   // float4 aligned
+    static constexpr int F_FLOATS = F_OBS + 4 * NO;
+    static constexpr int E_F32 = E_SCR + 8;                  // (doubles) start of the fp32 block, 16-byte aligned
+    static constexpr int E_RAW = E_F32 + (F_FLOATS + 1) / 2;
+    // env stride in doubles: == 2 (mod 4) keeps every block 16-byte aligned (float4 shadow entries) and puts
+    // the (up to 8) groups of a warp on different banks for the broadcast LDS.64
+    static constexpr int ES = E_RAW + ((6 - E_RAW % 4) % 4);
     static constexpr int CAM_ROW = NC * DC;                  // floats per env in cam_obs
     static constexpr int TGT_ROW = NT * DT;
     static constexpr int STAGE_CAM_FLOATS = ((EPW * CAM_ROW + 3) / 4) * 4;
@@ -401,58 +404,67 @@ __device__ __noinline__ int fov_reach_exact(double cx, double cy, double phi, do
     return 1;
 }
 
-// The same two tests decided on squares / dot products (no sqrt, no atan2); only when a test
-// falls inside a 1e-9 relative band around its boundary is the exact expression evaluated.
-// C = camera block {x, y, phi, theta, rs, rs^2, cos phi, sin phi, cos^2(theta/2)}.
-__device__ __forceinline__ int fov_reach(const double* __restrict__ C, double qx, double qy) {
-    const double relx = qx - C[0], rely = qy - C[1];
-    const double d2 = relx * relx + rely * rely;
-    const double rs2 = C[5];
-    if (d2 > rs2 * (1.0 + 1e-9)) return 0;
-    const double dot = relx * C[6] + rely * C[7];
-    const double sq = dot >= 0.0 ? dot * dot : -(dot * dot);
-    const double diff = sq - d2 * C[8];          // >= 0  <=>  angle(rel, heading) <= theta / 2
-    const double band = 1e-9 * d2;
+// The same two tests decided in fp32 on squares / dot products (no sqrt, no atan2).  fp32
+// coordinates carry <= 6e-5 absolute error, i.e. <= 1e-5 relative on these quantities; only when
+// a test falls inside a 4e-5 relative band around its boundary is the exact fp64 expression of
+// the reference evaluated (C = fp64 camera block {x, y, phi, theta, rs, ...}).
+// F = fp32 camera block {x, y, rs^2, cos phi, sin phi, cos^2(theta/2)}.
+__device__ __forceinline__ int fov_reach(const float* __restrict__ F, const double* __restrict__ C,
+                                         float fqx, float fqy, double qx, double qy) {
+    const float relx = fqx - F[0], rely = fqy - F[1];
+    const float d2 = relx * relx + rely * rely;
+    const float rs2 = F[2];
+    if (d2 > rs2 * (1.0f + 4e-5f)) return 0;
+    const float dot = relx * F[3] + rely * F[4];
+    const float sq = dot >= 0.0f ? dot * dot : -(dot * dot);
+    const float diff = sq - d2 * F[5];           // >= 0  <=>  angle(rel, heading) <= theta / 2
+    const float band = 4e-5f * d2 + 1e-3f;
     if (diff < -band) return 0;
-    if (diff > band && d2 < rs2 * (1.0 - 1e-9)) return 1;
+    if (diff > band && d2 < rs2 * (1.0f - 4e-5f)) return 1;
     return fov_reach_exact(C[0], C[1], C[2], C[3], C[4], qx, qy);
 }
 
 // Conservative occlusion classification of the query point q = cam + rel (|rel|^2 = d2) against
 // all obstacle discs, WITHOUT evaluating the sampled polyline:
 //   1 = certainly visible  (no disc comes within R + w of the segment cam->q, where w covers
-//       the +-1.02 degree fan in which the two bracketing polyline samples lie),
-//   0 = certainly occluded (q lies >= 1.02 degrees inside some disc's silhouette and beyond
+//       the +-1.05 degree fan in which the two bracketing polyline samples lie),
+//   0 = certainly occluded (q lies >= 1.05 degrees inside some disc's silhouette and beyond
 //       its tangent length, so both bracketing samples are shortened below |rel|),
 //   2 = near a silhouette edge or a disc surface: evaluate the polyline exactly.
+// All margins (>= 0.02 units / 0.04 degrees) are far above fp32 rounding (<= 1e-3 units here), so
+// the classification runs in fp32 on the shadow block Fobs = {x, y, r, -} per obstacle.
 template <int NO>
-__device__ __forceinline__ int occlusion_fast(const double* __restrict__ Eobs, double cx, double cy,
-                                              double relx, double rely, double d2, double dist, double rmax) {
-    const double c1sq = 0.99984154 * 0.99984154 * (1.0 + 1e-9);   // cos^2(1.02 deg)
-    const double s1 = 0.01780139;                                   // sin(1.02 deg)
-    const double s1d = s1 * dist * (1.0 + 1e-9);
-    const double inv_dist = 1.0 / dist;
+__device__ __forceinline__ int occlusion_fast(const float* __restrict__ Fobs, float cx, float cy,
+                                              float relx, float rely, float rmax) {
+    const float d2 = relx * relx + rely * rely;
+    const float dist = sqrtf(d2);
+    const float c1sq = 0.99983209f * 0.99983209f * 1.00001f;   // cos^2(1.05 deg)
+    const float s1 = 0.01832496f;                              // sin(1.05 deg)
+    const float s1d = s1 * dist;
+    const float inv_dist = 1.0f / dist;
     bool all_clear = true;
 #pragma unroll 1
     for (int o = 0; o < NO; ++o) {
-        const double ox = Eobs[3 * o] - cx, oy = Eobs[3 * o + 1] - cy, R = Eobs[3 * o + 2];
-        const double do2 = ox * ox + oy * oy;
-        const double reach = rmax + R;
-        if (do2 > reach * reach * (1.0 + 1e-9)) continue;     // not in the camera's obstacle set (entities.py:365)
-        const double t = ox * relx + oy * rely;                // projection * |rel|
-        // half-width of the +-1.02 degree fan at the farthest range where it can meet this disc
-        const double far = fmin(dist, fmax(t, 0.0) * inv_dist * (1.0 + 1e-9) + R);
-        const double Rw = R + 0.018 * far + 1e-3;
-        double seg;                                            // squared distance centre<->segment, times d2
-        if (t <= 0.0) seg = do2 * d2;
-        else if (t >= d2) { const double ex = ox - relx, ey = oy - rely; seg = (ex * ex + ey * ey) * d2; }
+        const float4 ob = reinterpret_cast<const float4*>(Fobs)[o];
+        const float ox = ob.x - cx, oy = ob.y - cy, R = ob.z;
+        const float do2 = ox * ox + oy * oy;
+        const float reach = rmax + R + 0.05f;
+        if (do2 > reach * reach) continue;                     // certainly not in the camera's obstacle set (entities.py:365)
+        const float t = ox * relx + oy * rely;                 // projection * |rel|
+        // half-width of the fan at the farthest range where it can meet this disc
+        const float far = fminf(dist, fmaxf(t, 0.0f) * inv_dist + R);
+        const float Rw = R + 0.0185f * far + 0.05f;
+        float seg;                                             // squared distance centre<->segment, times d2
+        if (t <= 0.0f) seg = do2 * d2;
+        else if (t >= d2) { const float ex = ox - relx, ey = oy - rely; seg = (ex * ex + ey * ey) * d2; }
         else seg = do2 * d2 - t * t;
-        if (seg > Rw * Rw * d2 * (1.0 + 1e-9)) continue;       // clear of this disc
+        if (seg > Rw * Rw * d2 * 1.0001f) continue;            // clear of this disc
         all_clear = false;
-        const double tl2 = do2 - R * R;                        // squared tangent length
-        const double pm = t - R * s1d;                         // (proj - R sin(1.02)) * |rel|
-        if (tl2 > 0.0 && pm > 0.0 && R * R > s1 * s1 * do2 * (1.0 + 1e-6) && pm * pm > tl2 * c1sq * d2 &&
-            d2 * (1.0 - 4e-6) > tl2 && do2 < reach * reach * (1.0 - 1e-9))
+        const float tl2 = do2 - R * R;                         // squared tangent length
+        const float pm = t - R * s1d;                          // (proj - R sin(1.05)) * |rel|
+        const float inner = rmax + R - 0.05f;
+        if (tl2 > 1.0f && pm > 0.0f && R * R > s1 * s1 * do2 * 1.001f && pm * pm > tl2 * c1sq * d2 &&
+            d2 * (1.0f - 1e-4f) > tl2 + 1.0f && do2 < inner * inner)
             return 0;
     }
     return all_clear ? 1 : 2;
@@ -671,6 +683,11 @@ mate_step_kernel(const Params p) {
     double* Etgt = E + S::E_TGT;
     double* Eobs = E + S::E_OBS;
     uint32_t* scr = reinterpret_cast<uint32_t*>(E + S::E_SCR);
+    float* F = reinterpret_cast<float*>(E + S::E_F32);         // fp32 shadow block for the prefilters
+    float* Fcam = F + S::F_CAM;
+    float* Ftgt = F + S::F_TGT;
+    float* Fobs = F + S::F_OBS;
+    constexpr int FC = S::FCAMF;
     if (threadIdx.x < S::NBUF) locks[threadIdx.x] = 0u;
     __syncthreads();
 
@@ -705,9 +722,9 @@ mate_step_kernel(const Params p) {
     for (int s = 0; s < OS; ++s) {
         const int o = my_obs[s];
         if (o >= 0) {
-            Eobs[3 * o + 0] = p.obs_x[(size_t)o * bp + er];
-            Eobs[3 * o + 1] = p.obs_y[(size_t)o * bp + er];
-            Eobs[3 * o + 2] = p.obs_r[(size_t)o * bp + er];
+            const double x = p.obs_x[(size_t)o * bp + er], y = p.obs_y[(size_t)o * bp + er], r = p.obs_r[(size_t)o * bp + er];
+            Eobs[3 * o + 0] = x; Eobs[3 * o + 1] = y; Eobs[3 * o + 2] = r;
+            reinterpret_cast<float4*>(Fobs)[o] = make_float4((float)x, (float)y, (float)r, 0.f);
         }
     }
     Cargo cargo;
@@ -746,6 +763,8 @@ mate_step_kernel(const Params p) {
             if (env_ok) { p.cam_phi[(size_t)j * bp + e] = phi; p.cam_theta[(size_t)j * bp + e] = theta; }
         }
         camera_derive(C, p.cam_area_product);
+        float* Fc = Fcam + j * FC;
+        Fc[0] = (float)C[0]; Fc[1] = (float)C[1]; Fc[2] = (float)C[5]; Fc[3] = (float)C[6]; Fc[4] = (float)C[7]; Fc[5] = (float)C[8];
     }
     __syncwarp();
     if (mode == MODE_STEP && j < NT) {   // Target.simulate (entities.py:645-668), brute force over all discs
@@ -764,10 +783,24 @@ mate_step_kernel(const Params p) {
             s.bound = s.n * (1.0 + 1e-12);
         }
         const double desx = tx + s.vx, desy = ty + s.vy;
+        {
+            // fp32 broad phase: a disc farther than bound + R (+ slack for fp32 rounding) cannot touch the step
+            const float ftx = (float)tx, fty = (float)ty, fb = (float)s.bound * 1.00001f + 0.01f;
 #pragma unroll 1
-        for (int o = 0; o < NO; ++o) obstruct_step(s, tx, ty, Eobs[3 * o], Eobs[3 * o + 1], Eobs[3 * o + 2]);
+            for (int o = 0; o < NO; ++o) {
+                const float4 ob = reinterpret_cast<const float4*>(Fobs)[o];
+                const float dx = ob.x - ftx, dy = ob.y - fty, reach = fb + ob.z;
+                if (dx * dx + dy * dy > reach * reach && s.bound <= step_size * 1.000001) continue;
+                obstruct_step(s, tx, ty, Eobs[3 * o], Eobs[3 * o + 1], Eobs[3 * o + 2]);
+            }
+            const float reach_c = fb + (float)p.cam_radius, reach_c2 = reach_c * reach_c;
 #pragma unroll 1
-        for (int c = 0; c < NC; ++c) obstruct_step(s, tx, ty, Ecam[c * CF], Ecam[c * CF + 1], p.cam_radius);
+            for (int c = 0; c < NC; ++c) {
+                const float dx = Fcam[c * FC] - ftx, dy = Fcam[c * FC + 1] - fty;
+                if (dx * dx + dy * dy > reach_c2 && s.bound <= step_size * 1.000001) continue;
+                obstruct_step(s, tx, ty, Ecam[c * CF], Ecam[c * CF + 1], p.cam_radius);
+            }
+        }
         const double nx = fmin(fmax(tx + s.vx, -kTerrain), kTerrain);
         const double ny = fmin(fmax(ty + s.vy, -kTerrain), kTerrain);
         const int colliding = !(fabs(nx - desx) <= 1e-6 && fabs(ny - desy) <= 1e-6);
@@ -854,56 +887,100 @@ mate_step_kernel(const Params p) {
                 }
                 tdone = 0;
                 draw_step = 0;
-                if (j < NC) camera_derive(Ecam + j * CF, p.cam_area_product);
+                if (j < NC) {
+                    double* C = Ecam + j * CF;
+                    camera_derive(C, p.cam_area_product);
+                    float* Fc = Fcam + j * FC;
+                    Fc[0] = (float)C[0]; Fc[1] = (float)C[1]; Fc[2] = (float)C[5]; Fc[3] = (float)C[6]; Fc[4] = (float)C[7]; Fc[5] = (float)C[8];
+                }
+#pragma unroll
+                for (int s = 0; s < OS; ++s) {
+                    const int o = my_obs[s];
+                    if (o >= 0) reinterpret_cast<float4*>(Fobs)[o] = make_float4((float)Eobs[3 * o], (float)Eobs[3 * o + 1], (float)Eobs[3 * o + 2], 0.f);
+                }
             }
             __syncwarp();
         }
         // publish target positions for the view phase
-        if (j < NT) { Etgt[2 * j] = tx; Etgt[2 * j + 1] = ty; }
+        if (j < NT) { Etgt[2 * j] = tx; Etgt[2 * j + 1] = ty; Ftgt[2 * j] = (float)tx; Ftgt[2 * j + 1] = (float)ty; }
         __syncwarp();
 
         // ============================================================== _update_view (environment.py:1356-1388)
         // pending bits: 0..15 camera c vs my target, 16..31 camera c vs my camera
         uint32_t pending = 0, cc_reach = 0;
         bool cc_valid = true;
-        if (view_active) {
-            ct_col = 0; tt_col = 0; cc_col = 0; tc_col = 0;
-            // ---- omnidirectional sensing by targets, Sensor.perceive (entities.py:229-232) ----
-            const bool is_t = j < NT, is_c = j < NC;
-            const double mx = is_c ? Ecam[j * CF] : 0.0, my = is_c ? Ecam[j * CF + 1] : 0.0;
+        const bool is_t = j < NT, is_c = j < NC;
+        const double mx = is_c ? Ecam[j * CF] : 0.0, my = is_c ? Ecam[j * CF + 1] : 0.0;
+        const float ftx = (float)tx, fty = (float)ty, fmx = (float)mx, fmy = (float)my;
+        // ---- omnidirectional sensing by targets, Sensor.perceive (entities.py:229-232) ----
+        // fp32 on squares; inside a 4e-6 relative band the fp64 test decides.  Lane t evaluates
+        // "target t senses X" for one entity X per iteration; a ballot hands X's owner the whole
+        // column (who senses X), which is the form the observation packer needs.
+        if (__any_sync(FULL, view_active)) {
+            const float fsr2 = (float)(sr * sr), fsrc2 = (float)(src * src);
+            uint32_t tt_new = 0, tc_new = 0;
+            if (is_t) {   // target <-> target is symmetric: my row is my column
 #pragma unroll 2
-            for (int t = 0; t < NT; ++t) {
-                const double ux = Etgt[2 * t], uy = Etgt[2 * t + 1];
-                if (is_t) {
-                    const double dx = ux - tx, dy = uy - ty;
-                    tt_col |= (uint32_t)((t == j) || dist_le(dx * dx + dy * dy, sr, sr_lo, sr_hi)) << t;
-                }
-                if (is_c) {
-                    const double dx = ux - mx, dy = uy - my;
-                    tc_col |= (uint32_t)dist_le(dx * dx + dy * dy, src, src_lo, src_hi) << t;
+                for (int t = 0; t < NT; ++t) {
+                    const float dx = Ftgt[2 * t] - ftx, dy = Ftgt[2 * t + 1] - fty, d2 = dx * dx + dy * dy;
+                    bool sees = d2 < fsr2 * (1.0f - 4e-6f);
+                    if (!sees && d2 <= fsr2 * (1.0f + 4e-6f)) {
+                        const double ex = Etgt[2 * t] - tx, ey = Etgt[2 * t + 1] - ty;
+                        sees = dist_le(ex * ex + ey * ey, sr, sr_lo, sr_hi);
+                    }
+                    tt_new |= (uint32_t)(sees || t == j) << t;
                 }
             }
+#pragma unroll 1
+            for (int c = 0; c < NC; ++c) {   // target j senses camera c
+                const float dx = Fcam[c * FC] - ftx, dy = Fcam[c * FC + 1] - fty, d2 = dx * dx + dy * dy;
+                bool sees = d2 < fsrc2 * (1.0f - 4e-6f);
+                if (!sees && d2 <= fsrc2 * (1.0f + 4e-6f)) {
+                    const double ex = Ecam[c * CF] - tx, ey = Ecam[c * CF + 1] - ty;
+                    sees = dist_le(ex * ex + ey * ey, src, src_lo, src_hi);
+                }
+                const uint32_t col = (__ballot_sync(FULL, sees && is_t) >> gbase) & GMASK;
+                if (j == c) tc_new = col;
+            }
+            uint32_t co_new[OSN], to_new[OSN];
 #pragma unroll
-            for (int s = 0; s < OS; ++s) {
-                const int o = my_obs[s];
-                co_col[s] = 0; to_col[s] = 0;
-                if (o >= 0) {
-                    const double ox = Eobs[3 * o], oy = Eobs[3 * o + 1], orad = Eobs[3 * o + 2];
-                    const double rc = p.cam_rmax + orad, rt = sr + orad;
-                    const double rc_lo = rc * rc * (1.0 - 1e-12), rc_hi = rc * rc * (1.0 + 1e-12);
-                    const double rt_lo = rt * rt * (1.0 - 1e-12), rt_hi = rt * rt * (1.0 + 1e-12);
-#pragma unroll 2
-                    for (int c = 0; c < NC; ++c) {   // entities.py:363-368 (strict <)
-                        const double dx = Ecam[c * CF] - ox, dy = Ecam[c * CF + 1] - oy;
-                        co_col[s] |= (uint32_t)dist_lt(dx * dx + dy * dy, rc, rc_lo, rc_hi) << c;
-                    }
-#pragma unroll 2
-                    for (int t = 0; t < NT; ++t) {
-                        const double dx = Etgt[2 * t] - ox, dy = Etgt[2 * t + 1] - oy;
-                        to_col[s] |= (uint32_t)dist_le(dx * dx + dy * dy, rt, rt_lo, rt_hi) << t;
-                    }
+            for (int s = 0; s < OSN; ++s) { co_new[s] = 0; to_new[s] = 0; }
+#pragma unroll 1
+            for (int o = 0; o < NO; ++o) {   // target j senses obstacle o; camera j has obstacle o in its set
+                const float4 ob = reinterpret_cast<const float4*>(Fobs)[o];
+                const float rtf = (float)sr + ob.z, rt2 = rtf * rtf;
+                const float dx = ob.x - ftx, dy = ob.y - fty, d2 = dx * dx + dy * dy;
+                bool sees = d2 < rt2 * (1.0f - 4e-6f);
+                if (!sees && d2 <= rt2 * (1.0f + 4e-6f)) {
+                    const double ex = Eobs[3 * o] - tx, ey = Eobs[3 * o + 1] - ty;
+                    const double rt = sr + Eobs[3 * o + 2];
+                    sees = dist_le(ex * ex + ey * ey, rt, rt * rt * (1.0 - 1e-12), rt * rt * (1.0 + 1e-12));
+                }
+                const float rcf = (float)p.cam_rmax + ob.z, rc2 = rcf * rcf;
+                const float cxd = ob.x - fmx, cyd = ob.y - fmy, c2 = cxd * cxd + cyd * cyd;
+                bool inset = c2 < rc2 * (1.0f - 4e-6f);   // entities.py:363-368 (strict <)
+                if (!inset && c2 <= rc2 * (1.0f + 4e-6f)) {
+                    const double ex = Eobs[3 * o] - mx, ey = Eobs[3 * o + 1] - my;
+                    const double rc = p.cam_rmax + Eobs[3 * o + 2];
+                    inset = dist_lt(ex * ex + ey * ey, rc, rc * rc * (1.0 - 1e-12), rc * rc * (1.0 + 1e-12));
+                }
+                const uint32_t tcol = (__ballot_sync(FULL, sees && is_t) >> gbase) & GMASK;
+                const uint32_t ccol = (__ballot_sync(FULL, inset && is_c) >> gbase) & GMASK;
+                const int owner = o % G, slot = o / G;
+                if (j == owner) {
+#pragma unroll
+                    for (int s = 0; s < OSN; ++s) if (s == slot) { to_new[s] = tcol; co_new[s] = ccol; }
                 }
             }
+            if (view_active) {
+                tt_col = tt_new; tc_col = tc_new;
+#pragma unroll
+                for (int s = 0; s < OSN; ++s) { co_col[s] = co_new[s]; to_col[s] = to_new[s]; }
+            }
+        }
+        if (view_active) {
+            ct_col = 0; cc_col = 0;
+            // (the sensing masks are computed below, warp-uniformly, with ballots)
             // ---- cameras: range + sector first (Camera.perceive, entities.py:494-501) ----
             // camera->camera occlusion is static within an episode (neither end moves): it is
             // evaluated once after reset / set_state for ALL ordered pairs and cached in `ccw`.
@@ -913,9 +990,10 @@ mate_step_kernel(const Params p) {
 #pragma unroll 1
             for (int c = 0; c < NC; ++c) {
                 const double* C = Ecam + c * CF;
-                if (is_t && fov_reach(C, tx, ty)) pending |= 1u << c;
+                const float* Fc = Fcam + c * FC;
+                if (is_t && fov_reach(Fc, C, ftx, fty, tx, ty)) pending |= 1u << c;
                 if (is_c && c != j) {
-                    const bool reach = fov_reach(C, mx, my);
+                    const bool reach = fov_reach(Fc, C, fmx, fmy, mx, my);
                     cc_reach |= (uint32_t)reach << c;
                     if (cc_valid) cc_col |= (uint32_t)(reach && ((ccw >> (8 * j + c)) & 1ull)) << c;
                     else if (CC_CACHE || reach) pending |= 1u << (16 + c);
@@ -943,12 +1021,14 @@ mate_step_kernel(const Params p) {
                     if (NO == 0 || p.transmittance_is_one) {
                         sees = true;   // polyline is the flat max_sight_range circle; dist <= rs <= Rmax
                     } else {
-                        const double relx = qx - cx, rely = qy - cy;
-                        const double d2 = relx * relx + rely * rely;
-                        const double dist = sqrt(d2);
-                        const int fast = occlusion_fast<NO>(Eobs, cx, cy, relx, rely, d2, dist, p.cam_rmax);
+                        const float* Fc = Fcam + c * FC;
+                        const float fqx = is_cam ? Fcam[j * FC] : (float)tx, fqy = is_cam ? Fcam[j * FC + 1] : (float)ty;
+                        const int fast = occlusion_fast<NO>(Fobs, Fc[0], Fc[1], fqx - Fc[0], fqy - Fc[1], (float)p.cam_rmax);
                         sees = fast == 1;
-                        if (fast == 2) sees = occlusion_exact<NO>(Eobs, cx, cy, relx, rely, dist, p.cam_rmax);
+                        if (fast == 2) {
+                            const double relx = qx - cx, rely = qy - cy;
+                            sees = occlusion_exact<NO>(Eobs, cx, cy, relx, rely, sqrt(relx * relx + rely * rely), p.cam_rmax);
+                        }
                     }
                 }
                 if (is_cam) cc_clear_col |= (uint32_t)sees << c; else ct_col |= (uint32_t)sees << c;
@@ -1208,13 +1288,13 @@ mate_step_kernel(const Params p) {
         const float floaded = (goal >= 0 && weight > 0) ? 1.f : 0.f;
         {
             float* q = srow_cam + C_TGT + 5 * j;
-#pragma unroll 2
+#pragma unroll
             for (int c = 0; c < NC; ++c, q += DC)
                 if ((ct_col >> c) & 1) { q[0] = fx; q[1] = fy; q[2] = fsr; q[3] = floaded; q[4] = 1.f; }
         }
         {
             float* q = srow_tgt + T_TGT + 5 * j;
-#pragma unroll 2
+#pragma unroll
             for (int t = 0; t < NT; ++t, q += DT)
                 if ((tt_col >> t) & 1) { q[0] = fx; q[1] = fy; q[2] = fsr; q[3] = floaded; q[4] = 1.f; }
         }
@@ -1235,13 +1315,13 @@ mate_step_kernel(const Params p) {
         const float v3 = (float)(C[4] * C[6]), v4 = (float)(C[4] * C[7]), v5 = (float)C[3];
         {
             float* q = srow_cam + C_CAM + 7 * j;
-#pragma unroll 2
+#pragma unroll
             for (int c = 0; c < NC; ++c, q += DC)
                 if ((cc_col >> c) & 1) { q[0] = v0; q[1] = v1; q[2] = v2; q[3] = v3; q[4] = v4; q[5] = v5; q[6] = 1.f; }
         }
         {
             float* q = srow_tgt + T_CAM + 7 * j;
-#pragma unroll 2
+#pragma unroll
             for (int t = 0; t < NT; ++t, q += DT)
                 if ((tc_col >> t) & 1) { q[0] = v0; q[1] = v1; q[2] = v2; q[3] = v3; q[4] = v4; q[5] = v5; q[6] = 1.f; }
         }
@@ -1260,13 +1340,13 @@ mate_step_kernel(const Params p) {
             const float v0 = (float)Eobs[3 * o], v1 = (float)Eobs[3 * o + 1], v2 = (float)Eobs[3 * o + 2];
             {
                 float* q = srow_cam + C_OBS + 4 * o;
-#pragma unroll 2
+#pragma unroll
                 for (int c = 0; c < NC; ++c, q += DC)
                     if ((co_col[s] >> c) & 1) { q[0] = v0; q[1] = v1; q[2] = v2; q[3] = 1.f; }
             }
             {
                 float* q = srow_tgt + T_OBS + 4 * o;
-#pragma unroll 2
+#pragma unroll
                 for (int t = 0; t < NT; ++t, q += DT)
                     if ((to_col[s] >> t) & 1) { q[0] = v0; q[1] = v1; q[2] = v2; q[3] = 1.f; }
             }
