@@ -10,7 +10,7 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, 'csrc', 'libmate_b200.so')
+LIB_PATH = os.environ.get('MATE_B200_LIB') or os.path.join(HERE, 'csrc', 'libmate_b200.so')
 
 c_double_p = ctypes.POINTER(ctypes.c_double)
 c_float_p = ctypes.POINTER(ctypes.c_float)

@@ -33,7 +33,23 @@
 
 #include "../../include/mate_b200.h"
 
+#ifndef MATE_POOL_KB
+#define MATE_POOL_KB 112   // shared-memory budget per CTA (KB): 112 -> 2 CTAs/SM, 74 -> 3 CTAs/SM
+#endif
+#ifndef MATE_MIN_CTAS
+#define MATE_MIN_CTAS 2
+#endif
+#ifndef MATE_UNROLL_SENSE
+#define MATE_UNROLL_SENSE 1
+#endif
+#ifndef MATE_UNROLL_PACK
+#define MATE_UNROLL_PACK 1
+#endif
+
 namespace mate {
+
+constexpr int kUnrollSense = MATE_UNROLL_SENSE;   // tuning knobs: the kernel is instruction-fetch sensitive
+constexpr int kUnrollPack = MATE_UNROLL_PACK;
 
 constexpr int NW = MATE_NUM_WAREHOUSES;
 constexpr double kTerrain = 1000.0;          // mate/constants.py:52
@@ -146,7 +162,7 @@ struct Shape {
     // occupancy is not limited by the 6 KB/env of staged rows.
     static constexpr int WARPS = 8;                          // warps per CTA
     static constexpr int ENVS_PER_CTA = WARPS * EPW;
-    static constexpr int POOL_BUDGET = 112 * 1024 - WARPS * E_BYTES - 64;
+    static constexpr int POOL_BUDGET = MATE_POOL_KB * 1024 - WARPS * E_BYTES - 64;
     static constexpr int NBUF = POOL_BUDGET / STAGE_BYTES >= 3 ? 3 : (POOL_BUDGET / STAGE_BYTES >= 2 ? 2 : 1);
     static constexpr int LOCK_OFFSET = WARPS * E_BYTES;
     static constexpr int POOL_OFFSET = LOCK_OFFSET + 64;
@@ -346,8 +362,8 @@ __device__ __noinline__ double sight_range_at(const double* __restrict__ Eobs, d
         {   // entities.py:365 (strict <) and :378 (camera inside the disc), on squares
             const double reach = rmax + R, reach2 = reach * reach;
             if (d2 > reach2 * (1.0 + 1e-12)) continue;
-            if (d2 > reach2 * (1.0 - 1e-12) && !(sqrt(d2) < reach)) continue;
-            if (d2 < R * R * (1.0 + 1e-12) && R > sqrt(d2)) return 0.0;
+            if (d2 > reach2 * (1.0 - 1e-12) && !dist_cmp_exact(d2, reach, true)) continue;
+            if (d2 < R * R * (1.0 + 1e-12) && dist_cmp_exact(d2, R, true)) return 0.0;
         }
         // prefilter: can any sample angle of this obstacle fall inside (floor(a), floor(a)+1)?
         // angular distance bearing<->centre must be <= half + 1.02 deg
@@ -424,24 +440,29 @@ __device__ __forceinline__ int fov_reach(const float* __restrict__ F, const doub
     return fov_reach_exact(C[0], C[1], C[2], C[3], C[4], qx, qy);
 }
 
-// Conservative occlusion classification of the query point q = cam + rel (|rel|^2 = d2) against
-// all obstacle discs, WITHOUT evaluating the sampled polyline:
-//   1 = certainly visible  (no disc comes within R + w of the segment cam->q, where w covers
-//       the +-1.05 degree fan in which the two bracketing polyline samples lie),
-//   0 = certainly occluded (q lies >= 1.05 degrees inside some disc's silhouette and beyond
-//       its tangent length, so both bracketing samples are shortened below |rel|),
-//   2 = near a silhouette edge or a disc surface: evaluate the polyline exactly.
-// All margins (>= 0.02 units / 0.04 degrees) are far above fp32 rounding (<= 1e-3 units here), so
+// Conservative occlusion classification of the query point q = cam + rel against all obstacle
+// discs, WITHOUT evaluating the sampled polyline.  Both polyline samples that bracket the query
+// bearing lie inside a fan of +-1.05 degrees around it (integer-degree grid).  Per disc, with
+// `perp` the distance of its centre from the line of sight and `w` the half-width of the fan at
+// the farthest range where it can meet the disc, every ray of the fan passes the centre at a
+// lateral offset in [pmin, pmax] = [perp - w, perp + w], and a ray with offset p < R is cut at
+// range rho(p) = sqrt(d_o^2 - p^2) - sqrt(R^2 - p^2), which grows with p.  Hence
+//   * perp - w > R, disc behind the camera or entirely beyond the target: the disc is irrelevant;
+//   * pmax < R and |rel| > rho(pmax): every fan ray is cut short of the target  -> occluded (0);
+//   * |rel| < rho(pmin): no fan ray is cut before the target                    -> irrelevant;
+//   * otherwise (silhouette edge inside the fan, or target at the disc's front surface): exact.
+// Returns 1 = certainly visible, 0 = certainly occluded, 2 = evaluate the polyline exactly.
+// All margins (>= 0.05 units, 0.04 degrees) are far above fp32 rounding (<= 1e-3 units here), so
 // the classification runs in fp32 on the shadow block Fobs = {x, y, r, -} per obstacle.
 template <int NO>
 __device__ __forceinline__ int occlusion_fast(const float* __restrict__ Fobs, float cx, float cy,
                                               float relx, float rely, float rmax) {
     const float d2 = relx * relx + rely * rely;
-    const float dist = sqrtf(d2);
-    const float c1sq = 0.99983209f * 0.99983209f * 1.00001f;   // cos^2(1.05 deg)
-    const float s1 = 0.01832496f;                              // sin(1.05 deg)
-    const float s1d = s1 * dist;
-    const float inv_dist = 1.0f / dist;
+    const float inv_dist = rsqrtf(d2);
+    const float dist = d2 * inv_dist;
+    const float ux = relx * inv_dist, uy = rely * inv_dist;    // unit bearing
+    const float tan_fan = 0.018332f;                           // tan(1.05 deg)
+    const float d_hi = dist * (1.0f + 1e-4f) + 0.05f, d_lo = dist * (1.0f - 1e-4f) - 0.05f;
     bool all_clear = true;
 #pragma unroll 1
     for (int o = 0; o < NO; ++o) {
@@ -450,22 +471,22 @@ __device__ __forceinline__ int occlusion_fast(const float* __restrict__ Fobs, fl
         const float do2 = ox * ox + oy * oy;
         const float reach = rmax + R + 0.05f;
         if (do2 > reach * reach) continue;                     // certainly not in the camera's obstacle set (entities.py:365)
-        const float t = ox * relx + oy * rely;                 // projection * |rel|
-        // half-width of the fan at the farthest range where it can meet this disc
-        const float far = fminf(dist, fmaxf(t, 0.0f) * inv_dist + R);
-        const float Rw = R + 0.0185f * far + 0.05f;
-        float seg;                                             // squared distance centre<->segment, times d2
-        if (t <= 0.0f) seg = do2 * d2;
-        else if (t >= d2) { const float ex = ox - relx, ey = oy - rely; seg = (ex * ex + ey * ey) * d2; }
-        else seg = do2 * d2 - t * t;
-        if (seg > Rw * Rw * d2 * 1.0001f) continue;            // clear of this disc
-        all_clear = false;
-        const float tl2 = do2 - R * R;                         // squared tangent length
-        const float pm = t - R * s1d;                          // (proj - R sin(1.05)) * |rel|
+        const float proj = ox * ux + oy * uy;                  // along the line of sight
+        if (proj + R < 0.0f || proj - R > d_hi) continue;      // behind the camera / beyond the target
+        const float perp = fabsf(ox * uy - oy * ux);           // distance of the centre from the line of sight
+        const float w = tan_fan * fminf(d_hi, proj + R) + 0.05f;
+        const float pmin = fmaxf(perp - w, 0.0f), pmax = perp + w;
+        if (pmin >= R) continue;                               // the fan passes beside the disc
         const float inner = rmax + R - 0.05f;
-        if (tl2 > 1.0f && pm > 0.0f && R * R > s1 * s1 * do2 * 1.001f && pm * pm > tl2 * c1sq * d2 &&
-            d2 * (1.0f - 1e-4f) > tl2 + 1.0f && do2 < inner * inner)
-            return 0;
+        const bool in_set = do2 < inner * inner;               // certainly in the camera's obstacle set
+        const float R2 = R * R;
+        if (pmax < R * 0.9999f && in_set && do2 > R2 + 1.0f) {
+            const float rho_max = sqrtf(do2 - pmax * pmax) - sqrtf(R2 - pmax * pmax);
+            if (d_lo > rho_max * 1.0001f) return 0;            // every ray of the fan is cut before the target
+        }
+        const float rho_min = sqrtf(fmaxf(do2 - pmin * pmin, 0.0f)) - sqrtf(R2 - pmin * pmin);
+        if (d_hi < rho_min * 0.9999f) continue;                // the target is in front of the disc
+        all_clear = false;
     }
     return all_clear ? 1 : 2;
 }
@@ -664,7 +685,7 @@ __device__ __forceinline__ void assign_obstacles(int j, int* my_obs) {
 // The fused kernel
 // =============================================================================================
 template <int NC, int NT, int NO>
-__global__ void __launch_bounds__(Shape<NC, NT, NO>::WARPS * 32)
+__global__ void __launch_bounds__(Shape<NC, NT, NO>::WARPS * 32, MATE_MIN_CTAS)
 mate_step_kernel(const Params p) {
     using S = Shape<NC, NT, NO>;
     constexpr int G = S::G, EPW = S::EPW, OS = S::OS, DC = S::DC, DT = S::DT, CF = S::CAMF;
@@ -920,7 +941,7 @@ mate_step_kernel(const Params p) {
             const float fsr2 = (float)(sr * sr), fsrc2 = (float)(src * src);
             uint32_t tt_new = 0, tc_new = 0;
             if (is_t) {   // target <-> target is symmetric: my row is my column
-#pragma unroll 2
+#pragma unroll kUnrollSense
                 for (int t = 0; t < NT; ++t) {
                     const float dx = Ftgt[2 * t] - ftx, dy = Ftgt[2 * t + 1] - fty, d2 = dx * dx + dy * dy;
                     bool sees = d2 < fsr2 * (1.0f - 4e-6f);
@@ -931,7 +952,7 @@ mate_step_kernel(const Params p) {
                     tt_new |= (uint32_t)(sees || t == j) << t;
                 }
             }
-#pragma unroll 1
+#pragma unroll kUnrollSense
             for (int c = 0; c < NC; ++c) {   // target j senses camera c
                 const float dx = Fcam[c * FC] - ftx, dy = Fcam[c * FC + 1] - fty, d2 = dx * dx + dy * dy;
                 bool sees = d2 < fsrc2 * (1.0f - 4e-6f);
@@ -945,33 +966,34 @@ mate_step_kernel(const Params p) {
             uint32_t co_new[OSN], to_new[OSN];
 #pragma unroll
             for (int s = 0; s < OSN; ++s) { co_new[s] = 0; to_new[s] = 0; }
-#pragma unroll 1
-            for (int o = 0; o < NO; ++o) {   // target j senses obstacle o; camera j has obstacle o in its set
+            auto sense_obstacle = [&](const int o, const int owner, const int slot) {
+                // target j senses obstacle o; camera j has obstacle o in its set
                 const float4 ob = reinterpret_cast<const float4*>(Fobs)[o];
                 const float rtf = (float)sr + ob.z, rt2 = rtf * rtf;
                 const float dx = ob.x - ftx, dy = ob.y - fty, d2 = dx * dx + dy * dy;
                 bool sees = d2 < rt2 * (1.0f - 4e-6f);
-                if (!sees && d2 <= rt2 * (1.0f + 4e-6f)) {
-                    const double ex = Eobs[3 * o] - tx, ey = Eobs[3 * o + 1] - ty;
-                    const double rt = sr + Eobs[3 * o + 2];
-                    sees = dist_le(ex * ex + ey * ey, rt, rt * rt * (1.0 - 1e-12), rt * rt * (1.0 + 1e-12));
-                }
                 const float rcf = (float)p.cam_rmax + ob.z, rc2 = rcf * rcf;
                 const float cxd = ob.x - fmx, cyd = ob.y - fmy, c2 = cxd * cxd + cyd * cyd;
                 bool inset = c2 < rc2 * (1.0f - 4e-6f);   // entities.py:363-368 (strict <)
-                if (!inset && c2 <= rc2 * (1.0f + 4e-6f)) {
-                    const double ex = Eobs[3 * o] - mx, ey = Eobs[3 * o + 1] - my;
+                if ((!sees && d2 <= rt2 * (1.0f + 4e-6f)) || (NC > 0 && !inset && c2 <= rc2 * (1.0f + 4e-6f))) {
+                    // inside the fp32 band: the fp64 tests decide
+                    const double ex = Eobs[3 * o] - tx, ey = Eobs[3 * o + 1] - ty;
+                    const double rt = sr + Eobs[3 * o + 2];
+                    sees = dist_le(ex * ex + ey * ey, rt, rt * rt * (1.0 - 1e-12), rt * rt * (1.0 + 1e-12));
+                    const double fx = Eobs[3 * o] - mx, fy = Eobs[3 * o + 1] - my;
                     const double rc = p.cam_rmax + Eobs[3 * o + 2];
-                    inset = dist_lt(ex * ex + ey * ey, rc, rc * rc * (1.0 - 1e-12), rc * rc * (1.0 + 1e-12));
+                    inset = dist_lt(fx * fx + fy * fy, rc, rc * rc * (1.0 - 1e-12), rc * rc * (1.0 + 1e-12));
                 }
                 const uint32_t tcol = (__ballot_sync(FULL, sees && is_t) >> gbase) & GMASK;
-                const uint32_t ccol = (__ballot_sync(FULL, inset && is_c) >> gbase) & GMASK;
-                const int owner = o % G, slot = o / G;
+                uint32_t ccol = 0;
+                if (NC > 0) ccol = (__ballot_sync(FULL, inset && is_c) >> gbase) & GMASK;
                 if (j == owner) {
 #pragma unroll
                     for (int s = 0; s < OSN; ++s) if (s == slot) { to_new[s] = tcol; co_new[s] = ccol; }
                 }
-            }
+            };
+#pragma unroll kUnrollSense
+            for (int o = 0; o < NO; ++o) sense_obstacle(o, o % G, o / G);
             if (view_active) {
                 tt_col = tt_new; tc_col = tc_new;
 #pragma unroll
@@ -1288,13 +1310,13 @@ mate_step_kernel(const Params p) {
         const float floaded = (goal >= 0 && weight > 0) ? 1.f : 0.f;
         {
             float* q = srow_cam + C_TGT + 5 * j;
-#pragma unroll
+#pragma unroll kUnrollPack
             for (int c = 0; c < NC; ++c, q += DC)
                 if ((ct_col >> c) & 1) { q[0] = fx; q[1] = fy; q[2] = fsr; q[3] = floaded; q[4] = 1.f; }
         }
         {
             float* q = srow_tgt + T_TGT + 5 * j;
-#pragma unroll
+#pragma unroll kUnrollPack
             for (int t = 0; t < NT; ++t, q += DT)
                 if ((tt_col >> t) & 1) { q[0] = fx; q[1] = fy; q[2] = fsr; q[3] = floaded; q[4] = 1.f; }
         }
@@ -1315,13 +1337,13 @@ mate_step_kernel(const Params p) {
         const float v3 = (float)(C[4] * C[6]), v4 = (float)(C[4] * C[7]), v5 = (float)C[3];
         {
             float* q = srow_cam + C_CAM + 7 * j;
-#pragma unroll
+#pragma unroll kUnrollPack
             for (int c = 0; c < NC; ++c, q += DC)
                 if ((cc_col >> c) & 1) { q[0] = v0; q[1] = v1; q[2] = v2; q[3] = v3; q[4] = v4; q[5] = v5; q[6] = 1.f; }
         }
         {
             float* q = srow_tgt + T_CAM + 7 * j;
-#pragma unroll
+#pragma unroll kUnrollPack
             for (int t = 0; t < NT; ++t, q += DT)
                 if ((tc_col >> t) & 1) { q[0] = v0; q[1] = v1; q[2] = v2; q[3] = v3; q[4] = v4; q[5] = v5; q[6] = 1.f; }
         }
@@ -1340,13 +1362,13 @@ mate_step_kernel(const Params p) {
             const float v0 = (float)Eobs[3 * o], v1 = (float)Eobs[3 * o + 1], v2 = (float)Eobs[3 * o + 2];
             {
                 float* q = srow_cam + C_OBS + 4 * o;
-#pragma unroll
+#pragma unroll kUnrollPack
                 for (int c = 0; c < NC; ++c, q += DC)
                     if ((co_col[s] >> c) & 1) { q[0] = v0; q[1] = v1; q[2] = v2; q[3] = 1.f; }
             }
             {
                 float* q = srow_tgt + T_OBS + 4 * o;
-#pragma unroll
+#pragma unroll kUnrollPack
                 for (int t = 0; t < NT; ++t, q += DT)
                     if ((to_col[s] >> t) & 1) { q[0] = v0; q[1] = v1; q[2] = v2; q[3] = 1.f; }
             }
