@@ -12,6 +12,7 @@
 #include <vector>
 
 #include "mate_kernels.cuh"
+#include "mate_step.cuh"
 
 using namespace mate;
 
@@ -52,7 +53,37 @@ static cudaError_t prepare_shape() {
     return cudaFuncSetAttribute(mate_step_kernel<NC, NT, NO>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::SMEM_BYTES);
 }
 
+template <int NC, int NT, int NO>
+static void launch_shape2(const Params& p, int grid, cudaStream_t stream) {
+    using S = Shape2<NC, NT, NO>;
+    mate_step_kernel2<NC, NT, NO><<<grid, S::WARPS * 32, S::SMEM_BYTES, stream>>>(p);
+}
+template <int NC, int NT, int NO>
+static cudaError_t prepare_shape2() {
+    using S = Shape2<NC, NT, NO>;
+    return cudaFuncSetAttribute(mate_step_kernel2<NC, NT, NO>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::SMEM_BYTES);
+}
+
+// MATE_B200_KERNEL=1 selects the first-generation kernel (group of lanes per environment), kept
+// for A/B measurements; the default is the lane-per-environment kernel of mate_step.cuh.
+static bool use_first_generation() {
+    const char* v = getenv("MATE_B200_KERNEL");
+    return v && v[0] == '1';
+}
+
 static bool find_kernel(int nc, int nt, int no, KernelInfo* out) {
+    if (!use_first_generation()) {
+#define X(NC, NT, NO)                                                                          \
+        if (nc == NC && nt == NT && no == NO) {                                                \
+            using S = Shape2<NC, NT, NO>;                                                      \
+            *out = KernelInfo{&launch_shape2<NC, NT, NO>, S::ENVS_PER_CTA, S::SMEM_BYTES, S::DC, S::DT, \
+                              32, &prepare_shape2<NC, NT, NO>};                                \
+            return true;                                                                       \
+        }
+        MATE_SHAPES(X)
+#undef X
+        return false;
+    }
 #define X(NC, NT, NO)                                                                          \
     if (nc == NC && nt == NT && no == NO) {                                                    \
         using S = Shape<NC, NT, NO>;                                                           \
@@ -136,6 +167,7 @@ extern "C" int mate_b200_create(const MateConfig* cfg, int32_t num_envs, int32_t
     const size_t o_cam_phi = carve(sizeof(double) * nc * bpad), o_cam_theta = carve(sizeof(double) * nc * bpad);
     const size_t o_tgt_x = carve(sizeof(double) * nt * bpad), o_tgt_y = carve(sizeof(double) * nt * bpad);
     const size_t o_obs_x = carve(sizeof(double) * no * bpad), o_obs_y = carve(sizeof(double) * no * bpad), o_obs_r = carve(sizeof(double) * no * bpad);
+    const size_t o_obs_f4 = carve(sizeof(float4) * no * bpad);
     const size_t o_pack = carve(sizeof(uint32_t) * nt * bpad);
     const size_t o_cargo = carve(sizeof(uint4) * 2 * bpad), o_env_a = carve(sizeof(uint4) * bpad), o_env_b = carve(sizeof(int4) * bpad);
     const size_t o_cc = carve(sizeof(unsigned long long) * bpad);
@@ -148,6 +180,7 @@ extern "C" int mate_b200_create(const MateConfig* cfg, int32_t num_envs, int32_t
     p.cam_x = (double*)(b + o_cam_x); p.cam_y = (double*)(b + o_cam_y); p.cam_phi = (double*)(b + o_cam_phi); p.cam_theta = (double*)(b + o_cam_theta);
     p.tgt_x = (double*)(b + o_tgt_x); p.tgt_y = (double*)(b + o_tgt_y);
     p.obs_x = (double*)(b + o_obs_x); p.obs_y = (double*)(b + o_obs_y); p.obs_r = (double*)(b + o_obs_r);
+    p.obs_f4 = (float4*)(b + o_obs_f4);
     p.tgt_pack = (uint32_t*)(b + o_pack);
     p.cargo = (uint4*)(b + o_cargo); p.env_a = (uint4*)(b + o_env_a); p.env_b = (int4*)(b + o_env_b);
     p.cc_clear = (unsigned long long*)(b + o_cc);
@@ -215,7 +248,7 @@ static int launch_range(MateSim* sim, Params p, int begin, int count, cudaStream
     const int dc = sim->kernel.dc, dt = sim->kernel.dt;
     // SoA rows are indexed [row * bpad + env]: shifting the base pointers selects the sub-range
     p.cam_x += begin; p.cam_y += begin; p.cam_phi += begin; p.cam_theta += begin;
-    p.tgt_x += begin; p.tgt_y += begin; p.obs_x += begin; p.obs_y += begin; p.obs_r += begin;
+    p.tgt_x += begin; p.tgt_y += begin; p.obs_x += begin; p.obs_y += begin; p.obs_r += begin; p.obs_f4 += begin;
     p.tgt_pack += begin; p.cargo += begin; p.env_a += begin; p.env_b += begin; p.cc_clear += begin;
     if (p.cam_act) p.cam_act += (size_t)begin * nc * 2;
     if (p.tgt_act) p.tgt_act += (size_t)begin * nt * 2;
@@ -451,6 +484,9 @@ extern "C" int mate_b200_set_state(MateSim* sim, const MateStateView* v) {
         for (size_t e = 0; e < B; ++e)
             for (int k = 0; k < no; ++k) { a[k * bp + e] = v->obs_xyr[(e * no + k) * 3]; b2[k * bp + e] = v->obs_xyr[(e * no + k) * 3 + 1]; c[k * bp + e] = v->obs_xyr[(e * no + k) * 3 + 2]; }
         if (upload(a, p.obs_x) || upload(b2, p.obs_y) || upload(c, p.obs_r)) return MATE_ECUDA;
+        std::vector<float4> f4(no * bp);   // fp32 shadow read by the prefilters and the observation packer
+        for (size_t i = 0; i < f4.size(); ++i) f4[i] = make_float4((float)a[i], (float)b2[i], (float)c[i], 0.f);
+        if (upload(f4, p.obs_f4)) return MATE_ECUDA;
     }
     {
         std::vector<uint32_t> pack;

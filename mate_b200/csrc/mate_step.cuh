@@ -1,0 +1,912 @@
+// mate_step.cuh -- fused per-step kernel of the B200-native MultiAgentTracking simulator
+// (second generation: one LANE per environment for the simulation, one WARP per environment
+// for the observation rows).
+//
+// One launch per env.step.  Reference behaviour being restated (paths relative to the
+// reference root): mate/environment.py:590-676 (step), :1271-1388 (_assign_goals / _simulate /
+// _update_view), :908-983 (joint_observation), :679-834 (reset); mate/entities.py:158-184
+// (obstruct), :347-360 (Camera.simulate), :362-511 (FOV polyline + perceive), :645-668
+// (Target.simulate).
+//
+// Mapping (sm_100a; nothing here is a contraction, so no tensor cores):
+//   * A warp owns 32 consecutive environments and never synchronises with other warps.
+//   * SIMULATE / VIEW / GOALS: lane l owns environment env0 + l.  With struct-of-arrays state
+//     every warp-wide load or store of one field is one fully used 256-byte segment, and the
+//     ~250 distance / sector predicates of an environment run without a single idle lane (the
+//     first generation gave a group of 8 lanes to an environment and idled half of them).
+//     Predicates are decided in fp32 on squares with a guard band; inside the band the fp64
+//     expression of the reference decides (out of line, state re-read from HBM/L2).
+//   * Divergent work is not executed where it arises but queued and executed densely:
+//       - (camera, target) pairs that pass the range + sector test go to a per-warp queue in
+//         shared memory; the warp then processes 32 pairs at a time, one per lane (transmittance
+//         draw, conservative occlusion classification, exact polyline only when undecided);
+//       - targets whose step may touch a disc are re-simulated in fp64 after the fast loop;
+//       - targets standing in a warehouse are handled one per lane and iteration.
+//   * OBSERVATIONS: the warp walks over its 32 environments; for each, the lanes are the
+//     ENTITIES (targets, obstacles, cameras): a lane scatters its entity's public state into
+//     the staged rows of the observers whose mask bit is set, rows are zero-filled first, and
+//     the finished 6 KB block leaves the SM as two bulk copies (cp.async.bulk shared->global,
+//     i.e. TMA).  Masks (one or two words per observer row) and the fp32 entity values are
+//     handed from the simulation phase to this phase through shared memory.
+#pragma once
+
+#include "mate_common.cuh"
+
+#ifndef MATE2_WARPS
+#define MATE2_WARPS 2          // warps per CTA (warps are independent; this only sets the CTA granularity)
+#endif
+#ifndef MATE2_MIN_CTAS
+#define MATE2_MIN_CTAS 7       // 14 warps/SM: 65 536 envs = 2048 warp tiles = 13.8 per SM -> one balanced wave
+#endif
+
+namespace mate {
+
+template <int NC, int NT, int NO>
+struct Shape2 {
+    static constexpr int DC = 22 + 5 * NT + 4 * NO + 7 * NC;   // mate/constants.py:267-282
+    static constexpr int DT = 27 + 7 * NC + 4 * NO + 5 * NT;   // mate/constants.py:285-300
+    static constexpr int CAM_ROW = NC * DC, TGT_ROW = NT * DT; // floats per environment
+    static constexpr int R = NC + NT;                          // observer rows per environment
+    // mask words per observer row: word 0 = cameras (bits 0-7), targets (bits 8-15) and, when
+    // they fit, obstacles (bits 16-31); otherwise obstacles take a second word
+    static constexpr int MW = NO <= 16 ? 1 : 2;
+    static constexpr int MSTRIDE = (R * MW) | 1;               // odd stride: lane-per-env access is conflict free
+    // fp32 values per environment: targets {x, y, packed state}, cameras {x, y, Rs cos, Rs sin, theta}
+    static constexpr int V_T = 0, V_C = 3 * NT, VN = 3 * NT + 5 * NC;
+    static constexpr int VSTRIDE = VN | 1;
+    static constexpr int STAGE_CAM = ((CAM_ROW + 3) / 4) * 4;
+    static constexpr int STAGE_FLOATS = STAGE_CAM + ((TGT_ROW + 3) / 4) * 4;
+    static constexpr bool BULK = (CAM_ROW % 4 == 0) && (TGT_ROW % 4 == 0);   // 16-byte aligned blocks per env
+    static constexpr int E = NT + NO + NC;                     // entity slots (lanes of the scatter)
+    static constexpr int WARPS = MATE2_WARPS;
+    static constexpr int ENVS_PER_CTA = WARPS * 32;
+    static constexpr int QCAP = 64;
+    static constexpr int OFF_STAGE = 0;
+    static constexpr int OFF_MASK = OFF_STAGE + STAGE_FLOATS * 4;
+    static constexpr int OFF_VAL = OFF_MASK + 32 * MSTRIDE * 4;
+    static constexpr int OFF_Q = OFF_VAL + 32 * VSTRIDE * 4;
+    static constexpr int WARP_BYTES = ((OFF_Q + QCAP * 2 + 15) / 16) * 16;
+    static constexpr int SMEM_BYTES = WARPS * WARP_BYTES;
+};
+
+// mask bit positions inside an observer row
+__device__ __forceinline__ constexpr uint32_t bit_cam(int c) { return 1u << c; }
+__device__ __forceinline__ constexpr uint32_t bit_tgt(int t) { return 1u << (8 + t); }
+
+// ---- out-of-line exact (fp64) decisions, state re-read from global memory -------------------
+// ||a - b|| <= thr (or <), entities a / b given by their SoA rows
+__device__ __noinline__ bool sense_exact(const double* ax, const double* ay, const double* bx, const double* by,
+                                         double thr, bool strict) {
+    const double ex = *ax - *bx, ey = *ay - *by;
+    const double d2 = ex * ex + ey * ey, t2 = thr * thr;
+    return strict ? dist_lt(d2, thr, t2 * (1.0 - 1e-12), t2 * (1.0 + 1e-12)) : dist_le(d2, thr, t2 * (1.0 - 1e-12), t2 * (1.0 + 1e-12));
+}
+
+// Camera.perceive range + sector test in the reference's arithmetic for camera c of env `er`
+__device__ __noinline__ int fov_reach_global(const Params& p, int er, int c, const double* qx, const double* qy) {
+    const size_t i = (size_t)c * p.bpad + er;
+    const double theta = p.cam_theta[i];
+    return fov_reach_exact(p.cam_x[i], p.cam_y[i], p.cam_phi[i], theta, sqrt(p.cam_area_product / theta), *qx, *qy);
+}
+
+// fp32 prefilter of the same test: 0 = no, 1 = yes, 2 = inside the guard band (ask the fp64 version)
+__device__ __forceinline__ int fov_reach32(float cx, float cy, float rs2, float cs, float sn, float ch2, float qx, float qy) {
+    const float relx = qx - cx, rely = qy - cy;
+    const float d2 = relx * relx + rely * rely;
+    if (d2 > rs2 * (1.0f + 4e-5f)) return 0;
+    const float dot = relx * cs + rely * sn;
+    const float sq = dot >= 0.0f ? dot * dot : -(dot * dot);
+    const float diff = sq - d2 * ch2;             // >= 0  <=>  angle(rel, heading) <= theta / 2
+    const float band = 4e-5f * d2 + 1e-3f;
+    if (diff < -band) return 0;
+    if (diff > band && d2 < rs2 * (1.0f - 4e-5f)) return 1;
+    return 2;
+}
+
+// Target.simulate (entities.py:645-668) in fp64 against all discs (obstacles, then camera barriers),
+// for the targets whose step may touch a disc.  Returns the new location and the colliding flag.
+template <int NC, int NT, int NO>
+__device__ __noinline__ void target_step_exact(const Params& p, int er, int t, uint32_t tpack, double* out_x, double* out_y, int* colliding) {
+    const size_t bp = p.bpad;
+    const double tx = p.tgt_x[(size_t)t * bp + er], ty = p.tgt_y[(size_t)t * bp + er];
+    const float2 a = reinterpret_cast<const float2*>(p.tgt_act)[(size_t)er * NT + t];
+    const double step_size = p.tgt_step_size / (double)tp_capacity(tpack);
+    StepVec s{(double)a.x, (double)a.y, 0.0, 0.0, step_size, false, false};
+    const double n2 = s.vx * s.vx + s.vy * s.vy;
+    if (n2 > step_size * step_size * (1.0 - 1e-12)) {
+        s.n = sqrt(n2); s.has_n = true;
+        if (s.n > step_size) {   // Vector2D.norm setter (utils.py:223-229), see DESIGN.md
+            const double k = step_size / s.n;
+            s.vx *= k; s.vy *= k; s.n = step_size;
+        }
+        s.bound = s.n * (1.0 + 1e-12);
+    }
+    const double desx = tx + s.vx, desy = ty + s.vy;
+#pragma unroll 1
+    for (int o = 0; o < NO; ++o)
+        obstruct_step(s, tx, ty, p.obs_x[(size_t)o * bp + er], p.obs_y[(size_t)o * bp + er], p.obs_r[(size_t)o * bp + er]);
+#pragma unroll 1
+    for (int c = 0; c < NC; ++c)
+        obstruct_step(s, tx, ty, p.cam_x[(size_t)c * bp + er], p.cam_y[(size_t)c * bp + er], p.cam_radius);
+    const double nx = fmin(fmax(tx + s.vx, -kTerrain), kTerrain);
+    const double ny = fmin(fmax(ty + s.vy, -kTerrain), kTerrain);
+    *colliding = !(fabs(nx - desx) <= 1e-6 && fabs(ny - desy) <= 1e-6);
+    *out_x = nx; *out_y = ny;
+}
+
+// occlusion of the segment camera c -> point q of env `er`: fast classification, exact polyline if undecided
+template <int NO>
+__device__ __forceinline__ bool line_of_sight(const Params& p, int er, int c, float fcx, float fcy, float fqx, float fqy,
+                                              const double* qxp, const double* qyp) {
+    const size_t bp = p.bpad;
+    const int fast = occlusion_fast<NO>(p.obs_f4 + er, bp, fcx, fcy, fqx - fcx, fqy - fcy, (float)p.cam_rmax);
+    if (fast != 2) return fast == 1;
+    const double cx = p.cam_x[(size_t)c * bp + er], cy = p.cam_y[(size_t)c * bp + er];
+    const double relx = *qxp - cx, rely = *qyp - cy;
+    return occlusion_exact<NO>(ObsRef{p.obs_x + er, p.obs_y + er, p.obs_r + er, bp}, cx, cy, relx, rely,
+                               sqrt(relx * relx + rely * rely), p.cam_rmax);
+}
+
+// per-episode cache of the static camera -> camera lines of sight (bit 8 j + c: camera c has a clear
+// line of sight to camera j; bit 63: valid)
+template <int NC, int NO>
+__device__ __noinline__ unsigned long long build_cc_cache(const Params& p, int er) {
+    const size_t bp = p.bpad;
+    unsigned long long w = 1ull << 63;
+    for (int c = 0; c < NC; ++c)
+        for (int j = 0; j < NC; ++j) {
+            if (j == c) continue;
+            bool clear = true;
+            if (NO > 0 && !p.transmittance_is_one) {
+                const double* qx = p.cam_x + (size_t)j * bp + er;
+                const double* qy = p.cam_y + (size_t)j * bp + er;
+                clear = line_of_sight<NO>(p, er, c, (float)p.cam_x[(size_t)c * bp + er], (float)p.cam_y[(size_t)c * bp + er],
+                                          (float)*qx, (float)*qy, qx, qy);
+            }
+            w |= (unsigned long long)clear << (8 * j + c);
+        }
+    return w;
+}
+
+// MultiAgentTracking.reset for one environment (one lane): new geometry and cargo table, written
+// straight to the state arrays.  Returns the capacity-2 bit set; cargo goes to `cargo`.
+template <int NC, int NT, int NO>
+__device__ __noinline__ uint32_t reset_env_global(const Params& p, int e, RngKey key, Cargo* cargo) {
+    double Ecam[(NC > 0 ? NC : 1) * 5], Etgt[NT * 2], Eobs[(NO > 0 ? NO : 1) * 3];
+    uint32_t scr[16];
+    ResetCfg rc;
+    rc.cam_radius = p.cam_radius; rc.cam_min_view = p.cam_min_view; rc.cam_rot_step = p.cam_rot_step;
+    rc.cam_area_product = p.cam_area_product; rc.tgt_step_size = p.tgt_step_size;
+    rc.obs_r_low = p.obs_r_low; rc.obs_r_high = p.obs_r_high;
+    rc.cam_ranges = p.cam_ranges; rc.tgt_ranges = p.tgt_ranges; rc.obs_ranges = p.obs_ranges;
+    rc.shuffle = p.shuffle; rc.num_high_capacity = p.num_high_capacity;
+    rc.num_cargoes_per_target = p.num_cargoes_per_target;
+    env_reset<NC, NT, NO, 5>(rc, key, Ecam, Etgt, Eobs, scr);
+    const size_t bp = p.bpad;
+    for (int c = 0; c < NC; ++c) {
+        p.cam_x[(size_t)c * bp + e] = Ecam[c * 5 + 0]; p.cam_y[(size_t)c * bp + e] = Ecam[c * 5 + 1];
+        p.cam_phi[(size_t)c * bp + e] = Ecam[c * 5 + 2]; p.cam_theta[(size_t)c * bp + e] = Ecam[c * 5 + 3];
+    }
+    for (int t = 0; t < NT; ++t) { p.tgt_x[(size_t)t * bp + e] = Etgt[2 * t]; p.tgt_y[(size_t)t * bp + e] = Etgt[2 * t + 1]; }
+    for (int o = 0; o < NO; ++o) {
+        p.obs_x[(size_t)o * bp + e] = Eobs[3 * o]; p.obs_y[(size_t)o * bp + e] = Eobs[3 * o + 1]; p.obs_r[(size_t)o * bp + e] = Eobs[3 * o + 2];
+        p.obs_f4[(size_t)o * bp + e] = make_float4((float)Eobs[3 * o], (float)Eobs[3 * o + 1], (float)Eobs[3 * o + 2], 0.f);
+    }
+    for (int k = 0; k < 8; ++k) cargo->rem[k] = scr[k];
+    cargo->aw[0] = scr[8]; cargo->aw[1] = scr[9];
+    return scr[10];
+}
+
+// aux outputs = the reference's public per-step attributes (environment.py:634-661); one lane = one env
+template <int NC, int NT, int NO, class S>
+__device__ __noinline__ void write_aux_env(const Params& p, int e, const uint32_t* mrow, const float* vrow, uint32_t tdone_bits,
+                                           float cov_now, float cov_real, float transport, int delivered, int episode_step) {
+    const MateStepAux& ax = p.aux;
+    constexpr int MW = S::MW;
+    auto obs_bit = [&](int row, int o) -> uint8_t { return MW == 1 ? (mrow[row] >> (16 + o)) & 1 : (mrow[row * MW + 1] >> o) & 1; };
+    for (int c = 0; c < NC; ++c) {
+        const uint32_t w = mrow[c * MW];
+        if (ax.mask_ct) for (int t = 0; t < NT; ++t) ax.mask_ct[((size_t)e * NC + c) * NT + t] = (w >> (8 + t)) & 1;
+        if (ax.mask_cc) for (int j = 0; j < NC; ++j) ax.mask_cc[((size_t)e * NC + c) * NC + j] = (w >> j) & 1;
+        if (ax.mask_co) for (int o = 0; o < NO; ++o) ax.mask_co[((size_t)e * NC + c) * NO + o] = obs_bit(c, o);
+    }
+    for (int t = 0; t < NT; ++t) {
+        const uint32_t w = mrow[(NC + t) * MW];
+        if (ax.mask_tc) for (int c = 0; c < NC; ++c) ax.mask_tc[((size_t)e * NT + t) * NC + c] = (w >> c) & 1;
+        if (ax.mask_tt) for (int u = 0; u < NT; ++u) ax.mask_tt[((size_t)e * NT + t) * NT + u] = (w >> (8 + u)) & 1;
+        if (ax.mask_to) for (int o = 0; o < NO; ++o) ax.mask_to[((size_t)e * NT + t) * NO + o] = obs_bit(NC + t, o);
+        if (ax.target_dones) ax.target_dones[(size_t)e * NT + t] = (tdone_bits >> t) & 1;
+        if (ax.is_colliding) ax.is_colliding[(size_t)e * NT + t] = (uint8_t)tp_colliding(__float_as_uint(vrow[S::V_T + 3 * t + 2]));
+        if (ax.warehouse_dist) {
+            const double tx = p.tgt_x[(size_t)t * p.bpad + e], ty = p.tgt_y[(size_t)t * p.bpad + e];
+            for (int w4 = 0; w4 < NW; ++w4) {
+                const double wx = (w4 == 0 || w4 == 3) ? kWarehouseCoord : -kWarehouseCoord;
+                const double wy = (w4 < 2) ? kWarehouseCoord : -kWarehouseCoord;
+                ax.warehouse_dist[((size_t)e * NT + t) * NW + w4] = (float)norm2(tx - wx, ty - wy);
+            }
+        }
+    }
+    if (ax.coverage) {   // coverage statistics (environment.py:966-979)
+        ax.coverage[(size_t)e * 3 + 0] = cov_now; ax.coverage[(size_t)e * 3 + 1] = cov_real; ax.coverage[(size_t)e * 3 + 2] = transport;
+    }
+    if (ax.num_delivered) ax.num_delivered[e] = delivered;
+    if (ax.episode_step) ax.episode_step[e] = episode_step;
+}
+
+// =============================================================================================
+// The fused kernel
+// =============================================================================================
+template <int NC, int NT, int NO>
+__global__ void __launch_bounds__(Shape2<NC, NT, NO>::WARPS * 32, MATE2_MIN_CTAS)
+mate_step_kernel2(const Params p) {
+    using S = Shape2<NC, NT, NO>;
+    static_assert(NC <= 8 && NT <= 8 && NO <= 32, "mask layout: 8 cameras, 8 targets, 32 obstacles");
+    constexpr int R = S::R, MW = S::MW, DC = S::DC, DT = S::DT;
+    constexpr int NCX = NC > 0 ? NC : 1;
+    constexpr uint32_t FULL = 0xffffffffu;
+    constexpr bool CC_CACHE = NC >= 2;   // camera <-> camera lines of sight are static within an episode
+
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    unsigned char* wbase = smem_raw + (size_t)warp * S::WARP_BYTES;
+    float* stage = reinterpret_cast<float*>(wbase + S::OFF_STAGE);
+    uint32_t* mk = reinterpret_cast<uint32_t*>(wbase + S::OFF_MASK);      // [32][MSTRIDE]
+    float* val = reinterpret_cast<float*>(wbase + S::OFF_VAL);            // [32][VSTRIDE]
+    uint16_t* queue = reinterpret_cast<uint16_t*>(wbase + S::OFF_Q);
+    uint32_t* mymk = mk + lane * S::MSTRIDE;
+    float* myval = val + lane * S::VSTRIDE;
+
+    const int env0 = (blockIdx.x * S::WARPS + warp) * 32;     // first env of this warp
+    if (env0 >= p.num_envs) return;                            // warps never synchronise with each other
+    const int e = env0 + lane;
+    const bool env_ok = e < p.num_envs;
+    const int er = env_ok ? e : p.num_envs - 1;                // tail lanes mirror the last env (reads only)
+    const size_t bp = p.bpad;
+    const int mode = p.mode;
+
+    // ------------------------------------------------------------------ per-env scalars
+    const uint4 ea = p.env_a[er];
+    const int4 eb = p.env_b[er];
+    unsigned long long ccw = CC_CACHE ? p.cc_clear[er] : 0ull;
+    Cargo cargo;
+    cargo.aw[0] = ea.x; cargo.aw[1] = ea.y;
+    int episode_step = (int)ea.z, delivered = (int)ea.w;
+    int ep_reward = eb.x, delayed_ep_reward = eb.y, episode_id = eb.w;
+    float coverage_sum = __int_as_float(eb.z);
+    bool cargo_loaded = false, cargo_dirty = false;
+    auto load_cargo = [&]() {
+        if (cargo_loaded) return;
+        const uint4 c0 = p.cargo[er], c1 = p.cargo[bp + er];
+        cargo.rem[0] = c0.x; cargo.rem[1] = c0.y; cargo.rem[2] = c0.z; cargo.rem[3] = c0.w;
+        cargo.rem[4] = c1.x; cargo.rem[5] = c1.y; cargo.rem[6] = c1.z; cargo.rem[7] = c1.w;
+        cargo_loaded = true;
+    };
+
+    // fp32 shadow of the cameras for the prefilters (registers)
+    float fcx[NCX], fcy[NCX], f_rs2[NCX], f_cos[NCX], f_sin[NCX], f_ch2[NCX];
+    auto derive_camera = [&](const int c, const double x, const double y, const double phi, const double theta) {
+        const double rs = sqrt(p.cam_area_product / theta);      // entities.py:334,360
+        double sn, cs;
+        sincospi(phi * (1.0 / 180.0), &sn, &cs);
+        fcx[c] = (float)x; fcy[c] = (float)y;
+        f_rs2[c] = (float)(rs * rs); f_cos[c] = (float)cs; f_sin[c] = (float)sn;
+        const float ch = cospif((float)theta * (1.0f / 360.0f));
+        f_ch2[c] = ch * ch;
+        float* v = myval + S::V_C + 5 * c;                        // Camera.state (entities.py:313-324), public part
+        v[0] = fcx[c]; v[1] = fcy[c]; v[2] = (float)(rs * cs); v[3] = (float)(rs * sn); v[4] = (float)theta;
+    };
+
+    // ------------------------------------------------------------------ _simulate (environment.py:1326-1354)
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {   // Camera.simulate (entities.py:347-360)
+        const size_t i = (size_t)c * bp + er;
+        const double x = p.cam_x[i], y = p.cam_y[i];
+        double phi = p.cam_phi[i], theta = p.cam_theta[i];
+        if (mode == MODE_STEP) {
+            const float2 a = reinterpret_cast<const float2*>(p.cam_act)[(size_t)er * NC + c];
+            const double da = fmin(fmax((double)a.x, -p.cam_rot_step), p.cam_rot_step);
+            const double dv = fmin(fmax((double)a.y, -p.cam_zoom_step), p.cam_zoom_step);
+            phi = normalize_angle(phi + da);
+            theta = fmin(fmax(theta + dv, p.cam_min_view), 180.0);
+            if (env_ok) { p.cam_phi[(size_t)c * bp + e] = phi; p.cam_theta[(size_t)c * bp + e] = theta; }
+        }
+        derive_camera(c, x, y, phi, theta);
+    }
+    {   // Target.simulate (entities.py:645-668): fast path = no disc within reach of the step
+        uint32_t slow = 0;     // targets that may touch a disc: re-simulated exactly below
+        if (mode == MODE_STEP) {
+            // fp32 broad phase on the old locations: a disc farther than step_size + R (+ slack for fp32
+            // rounding) cannot touch the step
+            float otx[NT], oty[NT];
+#pragma unroll
+            for (int t = 0; t < NT; ++t) { otx[t] = (float)p.tgt_x[(size_t)t * bp + er]; oty[t] = (float)p.tgt_y[(size_t)t * bp + er]; }
+            const float fb = (float)p.tgt_step_size * 1.00001f + 0.01f;
+#pragma unroll
+            for (int o = 0; o < NO; ++o) {
+                const float4 ob = p.obs_f4[(size_t)o * bp + er];
+                const float reach = fb + ob.z, reach2 = reach * reach;
+#pragma unroll
+                for (int t = 0; t < NT; ++t) {
+                    const float dx = ob.x - otx[t], dy = ob.y - oty[t];
+                    slow |= (uint32_t)(!(dx * dx + dy * dy > reach2)) << t;
+                }
+            }
+            const float reach_c = fb + (float)p.cam_radius, reach_c2 = reach_c * reach_c;
+#pragma unroll
+            for (int c = 0; c < NC; ++c) {
+#pragma unroll
+                for (int t = 0; t < NT; ++t) {
+                    const float dx = fcx[c] - otx[t], dy = fcy[c] - oty[t];
+                    slow |= (uint32_t)(!(dx * dx + dy * dy > reach_c2)) << t;
+                }
+            }
+        }
+#pragma unroll
+        for (int t = 0; t < NT; ++t) {
+            const size_t i = (size_t)t * bp + er;
+            double tx = p.tgt_x[i], ty = p.tgt_y[i];
+            uint32_t tpack = p.tgt_pack[i];
+            if (mode == MODE_STEP && !((slow >> t) & 1)) {
+                const float2 a = reinterpret_cast<const float2*>(p.tgt_act)[(size_t)er * NT + t];
+                const int cap = tp_capacity(tpack);
+                const double step_size = cap == 1 ? p.tgt_step_size : p.tgt_step_size / (double)cap;
+                double vx = (double)a.x, vy = (double)a.y;
+                const double n2 = vx * vx + vy * vy;
+                if (n2 > step_size * step_size * (1.0 - 1e-12)) {
+                    const double n = sqrt(n2);
+                    if (n > step_size) {   // Vector2D.norm setter (utils.py:223-229), see DESIGN.md
+                        const double k = step_size / n;
+                        vx *= k; vy *= k;
+                    }
+                }
+                const double desx = tx + vx, desy = ty + vy;
+                const double nx = fmin(fmax(desx, -kTerrain), kTerrain);
+                const double ny = fmin(fmax(desy, -kTerrain), kTerrain);
+                const int colliding = !(fabs(nx - desx) <= 1e-6 && fabs(ny - desy) <= 1e-6);
+                tx = nx; ty = ny;
+                tpack = (tpack & ~(1u << 27)) | ((uint32_t)colliding << 27);
+                if (env_ok) { p.tgt_x[(size_t)t * bp + e] = tx; p.tgt_y[(size_t)t * bp + e] = ty; }
+            }
+            myval[S::V_T + 3 * t + 0] = (float)tx; myval[S::V_T + 3 * t + 1] = (float)ty;
+            myval[S::V_T + 3 * t + 2] = __uint_as_float(tpack);
+        }
+        // exact re-simulation of the targets near a disc, one target per lane and iteration
+        while (__any_sync(FULL, slow != 0)) {
+            if (slow != 0) {
+                const int t = __ffs(slow) - 1;
+                slow &= slow - 1;
+                uint32_t tpack = __float_as_uint(myval[S::V_T + 3 * t + 2]);
+                double nx, ny; int colliding;
+                target_step_exact<NC, NT, NO>(p, er, t, tpack, &nx, &ny, &colliding);
+                tpack = (tpack & ~(1u << 27)) | ((uint32_t)colliding << 27);
+                if (env_ok) { p.tgt_x[(size_t)t * bp + e] = nx; p.tgt_y[(size_t)t * bp + e] = ny; }
+                myval[S::V_T + 3 * t + 0] = (float)nx; myval[S::V_T + 3 * t + 1] = (float)ny;
+                myval[S::V_T + 3 * t + 2] = __uint_as_float(tpack);
+            }
+        }
+    }
+
+    uint32_t tdone_bits = 0;            // target_dones
+    int reward_i = 0, delayed_i = 0;    // this step's rewards (integers)
+    int done = 0;
+    float cov_now = 0.f, cov_real = 0.f;
+    bool auto_reset_needed = false;
+    int draw_step = (mode == MODE_STEP) ? episode_step + 1 : episode_step;
+    RngKey key{p.seed, (uint32_t)(p.env_index_base + e), (uint32_t)episode_id};
+
+    auto emit_aux = [&]() {
+        if (!p.has_aux || !env_ok) return;
+        const float transport = delivered > 0 ? (float)((double)delayed_ep_reward / ((double)p.reward_scale * (double)delivered)) : 0.f;
+        if (!p.has_aux_detail) {   // the common case: only the info-dict scalars (environment.py:634-639)
+            if (p.aux.coverage) {
+                p.aux.coverage[(size_t)e * 3 + 0] = cov_now;
+                p.aux.coverage[(size_t)e * 3 + 1] = cov_real;
+                p.aux.coverage[(size_t)e * 3 + 2] = transport;
+            }
+            if (p.aux.num_delivered) p.aux.num_delivered[e] = delivered;
+            if (p.aux.episode_step) p.aux.episode_step[e] = episode_step;
+            return;
+        }
+        write_aux_env<NC, NT, NO, S>(p, e, mymk, myval, tdone_bits, cov_now, cov_real, transport, delivered, episode_step);
+    };
+
+    const float fsr = (float)p.tgt_sight_range;
+    const float fsr2 = fsr * fsr, fsrc = fsr + (float)p.cam_radius, fsrc2 = fsrc * fsrc;
+    const double sr = p.tgt_sight_range, src = sr + p.cam_radius;
+
+#pragma unroll 1
+    for (int pass = 0; pass < 2; ++pass) {
+        const bool do_reset = (pass == 0)
+            ? ((mode == MODE_RESET) && env_ok && (p.env_mask == nullptr || p.env_mask[e] != 0))
+            : auto_reset_needed;
+        const bool view_active = (pass == 0) || do_reset;
+        // ============================================================== reset (environment.py:679-775)
+        if (__any_sync(FULL, do_reset)) {
+            if (do_reset) {
+                RngKey k2 = key;
+                k2.episode = (uint32_t)(episode_id + 1);
+                const uint32_t cap2 = reset_env_global<NC, NT, NO>(p, e, k2, &cargo);
+                cargo_loaded = true; cargo_dirty = true;
+                episode_id += 1; key.episode = (uint32_t)episode_id;
+                episode_step = 0; delivered = 0; ep_reward = 0; delayed_ep_reward = 0; coverage_sum = 0.f;
+                ccw = 0ull; tdone_bits = 0; draw_step = 0;
+#pragma unroll
+                for (int c = 0; c < NC; ++c) {
+                    const size_t i = (size_t)c * bp + e;
+                    derive_camera(c, p.cam_x[i], p.cam_y[i], p.cam_phi[i], p.cam_theta[i]);
+                }
+#pragma unroll 1
+                for (int t = 0; t < NT; ++t) {
+                    myval[S::V_T + 3 * t + 0] = (float)p.tgt_x[(size_t)t * bp + e];
+                    myval[S::V_T + 3 * t + 1] = (float)p.tgt_y[(size_t)t * bp + e];
+                    myval[S::V_T + 3 * t + 2] = __uint_as_float(pack_target(0, -1, 0, ((cap2 >> t) & 1) ? 2 : 1, 0, 0));
+                }
+            }
+        }
+
+        // ============================================================== _update_view (environment.py:1356-1388)
+        unsigned long long pend = 0ull;     // bit c * NT + t: camera c reaches target t (range + sector)
+        if (__any_sync(FULL, view_active)) {
+            float ftx[NT], fty[NT];
+#pragma unroll
+            for (int t = 0; t < NT; ++t) { ftx[t] = myval[S::V_T + 3 * t]; fty[t] = myval[S::V_T + 3 * t + 1]; }
+            uint32_t crow[NCX], crow2[NCX], trow[NT], trow2[NT];
+#pragma unroll
+            for (int c = 0; c < NC; ++c) { crow[c] = bit_cam(c); crow2[c] = 0; }   // environment.py:1383-1384
+#pragma unroll
+            for (int t = 0; t < NT; ++t) { trow[t] = bit_tgt(t); trow2[t] = 0; }   // environment.py:1376-1377
+            // ---- omnidirectional sensing by targets, Sensor.perceive (entities.py:229-232) ----
+            // fp32 on squares; inside a 4e-6 relative band the fp64 test decides
+#pragma unroll
+            for (int t = 0; t < NT; ++t) {
+#pragma unroll
+                for (int u = t + 1; u < NT; ++u) {   // symmetric
+                    const float dx = ftx[u] - ftx[t], dy = fty[u] - fty[t], d2 = dx * dx + dy * dy;
+                    bool sees = d2 < fsr2 * (1.0f - 4e-6f);
+                    if (!sees && d2 <= fsr2 * (1.0f + 4e-6f))
+                        sees = sense_exact(p.tgt_x + (size_t)u * bp + er, p.tgt_y + (size_t)u * bp + er,
+                                           p.tgt_x + (size_t)t * bp + er, p.tgt_y + (size_t)t * bp + er, sr, false);
+                    if (sees) { trow[t] |= bit_tgt(u); trow[u] |= bit_tgt(t); }
+                }
+#pragma unroll
+                for (int c = 0; c < NC; ++c) {       // target t senses camera c
+                    const float dx = fcx[c] - ftx[t], dy = fcy[c] - fty[t], d2 = dx * dx + dy * dy;
+                    bool sees = d2 < fsrc2 * (1.0f - 4e-6f);
+                    if (!sees && d2 <= fsrc2 * (1.0f + 4e-6f))
+                        sees = sense_exact(p.cam_x + (size_t)c * bp + er, p.cam_y + (size_t)c * bp + er,
+                                           p.tgt_x + (size_t)t * bp + er, p.tgt_y + (size_t)t * bp + er, src, false);
+                    if (sees) trow[t] |= bit_cam(c);
+                }
+            }
+#pragma unroll
+            for (int o = 0; o < NO; ++o) {
+                const float4 ob = p.obs_f4[(size_t)o * bp + er];
+                const uint32_t obit = MW == 1 ? (1u << (16 + o)) : (1u << (o & 31));
+                const float rtf = fsr + ob.z, rt2 = rtf * rtf;
+#pragma unroll
+                for (int t = 0; t < NT; ++t) {       // target t senses obstacle o
+                    const float dx = ob.x - ftx[t], dy = ob.y - fty[t], d2 = dx * dx + dy * dy;
+                    bool sees = d2 < rt2 * (1.0f - 4e-6f);
+                    if (!sees && d2 <= rt2 * (1.0f + 4e-6f))
+                        sees = sense_exact(p.obs_x + (size_t)o * bp + er, p.obs_y + (size_t)o * bp + er,
+                                           p.tgt_x + (size_t)t * bp + er, p.tgt_y + (size_t)t * bp + er,
+                                           sr + p.obs_r[(size_t)o * bp + er], false);
+                    if (sees) { if (MW == 1) trow[t] |= obit; else trow2[t] |= obit; }
+                }
+                const float rcf = (float)p.cam_rmax + ob.z, rc2 = rcf * rcf;
+#pragma unroll
+                for (int c = 0; c < NC; ++c) {       // camera c has obstacle o in its set (entities.py:363-368, strict <)
+                    const float dx = ob.x - fcx[c], dy = ob.y - fcy[c], d2 = dx * dx + dy * dy;
+                    bool inset = d2 < rc2 * (1.0f - 4e-6f);
+                    if (!inset && d2 <= rc2 * (1.0f + 4e-6f))
+                        inset = sense_exact(p.obs_x + (size_t)o * bp + er, p.obs_y + (size_t)o * bp + er,
+                                            p.cam_x + (size_t)c * bp + er, p.cam_y + (size_t)c * bp + er,
+                                            p.cam_rmax + p.obs_r[(size_t)o * bp + er], true);
+                    if (inset) { if (MW == 1) crow[c] |= obit; else crow2[c] |= obit; }
+                }
+            }
+            // ---- cameras: range + sector (Camera.perceive, entities.py:494-501) ----
+#pragma unroll
+            for (int c = 0; c < NC; ++c) {
+#pragma unroll
+                for (int t = 0; t < NT; ++t) {
+                    int reach = fov_reach32(fcx[c], fcy[c], f_rs2[c], f_cos[c], f_sin[c], f_ch2[c], ftx[t], fty[t]);
+                    if (reach == 2) reach = fov_reach_global(p, er, c, p.tgt_x + (size_t)t * bp + er, p.tgt_y + (size_t)t * bp + er);
+                    if (reach) pend |= 1ull << (c * NT + t);
+                }
+            }
+            if (NC >= 2) {
+                // camera -> camera: the occlusion part is static within an episode and cached in `ccw`
+                if (view_active && (ccw >> 63) == 0ull) {
+                    ccw = build_cc_cache<NC, NO>(p, er);
+                    if (env_ok) p.cc_clear[e] = ccw;
+                }
+#pragma unroll
+                for (int c = 0; c < NC; ++c) {
+#pragma unroll
+                    for (int j = 0; j < NC; ++j) {
+                        if (j == c) continue;
+                        int reach = fov_reach32(fcx[c], fcy[c], f_rs2[c], f_cos[c], f_sin[c], f_ch2[c], fcx[j], fcy[j]);
+                        if (reach == 2) reach = fov_reach_global(p, er, c, p.cam_x + (size_t)j * bp + er, p.cam_y + (size_t)j * bp + er);
+                        if (reach && ((ccw >> (8 * j + c)) & 1ull)) crow[c] |= bit_cam(j);
+                    }
+                }
+            }
+            if (view_active) {
+#pragma unroll
+                for (int c = 0; c < NC; ++c) { mymk[c * MW] = crow[c]; if (MW == 2) mymk[c * MW + 1] = crow2[c]; }
+#pragma unroll
+                for (int t = 0; t < NT; ++t) { mymk[(NC + t) * MW] = trow[t]; if (MW == 2) mymk[(NC + t) * MW + 1] = trow2[t]; }
+            } else {
+                pend = 0ull;
+            }
+        }
+        __syncwarp();
+        // ---- then the stochastic transmittance draw and the occlusion test (entities.py:503-505) ----
+        // All pending (camera, target) pairs of the warp's 32 environments go through a queue in
+        // shared memory and are evaluated 32 at a time, one pair per lane.
+        if (NC > 0) {
+            int count = 0;   // warp-uniform
+            auto process = [&](const int base, const int n) {
+                const bool has = lane < n;
+                const uint32_t item = has ? queue[base + lane] : 0u;
+                const int src = item >> 8, b = item & 0xFF;
+                const int c = b / NT, t = b - c * NT;
+                const uint32_t src_episode = __shfl_sync(FULL, (uint32_t)episode_id, src);
+                const int src_draw = __shfl_sync(FULL, draw_step, src);
+                if (has) {
+                    const int env = env0 + src;
+                    const int envr = min(env, p.num_envs - 1);
+                    bool sees;
+                    if (p.replay_transmit) {
+                        sees = p.replay_transmit[((size_t)envr * NC + c) * NT + t] != 0;
+                    } else {
+                        const RngKey k{p.seed, (uint32_t)(p.env_index_base + env), src_episode};
+                        sees = rng_u01(k, STREAM_TRANSMIT, (uint32_t)src_draw * (uint32_t)(NC * NT) + (uint32_t)(c * NT + t)) < p.transmittance;
+                    }
+                    if (!sees) {
+                        if (NO == 0 || p.transmittance_is_one) {
+                            sees = true;   // polyline is the flat max_sight_range circle; dist <= rs <= Rmax
+                        } else {
+                            const float* v = val + src * S::VSTRIDE;
+                            sees = line_of_sight<NO>(p, envr, c, v[S::V_C + 5 * c], v[S::V_C + 5 * c + 1], v[S::V_T + 3 * t], v[S::V_T + 3 * t + 1],
+                                                     p.tgt_x + (size_t)t * bp + envr, p.tgt_y + (size_t)t * bp + envr);
+                        }
+                    }
+                    if (sees) atomicOr(&mk[src * S::MSTRIDE + c * MW], bit_tgt(t));
+                }
+            };
+            while (__any_sync(FULL, pend != 0ull)) {
+                const bool has = pend != 0ull;
+                const int b = has ? (__ffsll((long long)pend) - 1) : 0;
+                pend &= pend - 1ull;
+                const uint32_t ballot = __ballot_sync(FULL, has);
+                const int pos = count + __popc(ballot & ((1u << lane) - 1u));
+                if (has) queue[pos] = (uint16_t)((lane << 8) | b);
+                count += __popc(ballot);
+                __syncwarp();
+                if (count >= 32) {
+                    count -= 32;
+                    process(count, 32);
+                    __syncwarp();
+                }
+            }
+            if (count > 0) process(0, count);
+            __syncwarp();
+        }
+
+        // ============================================================== _assign_goals (environment.py:1271-1324)
+        const bool step_goals = (pass == 0) && (mode == MODE_STEP);
+        const bool goals_active = step_goals || do_reset;
+        uint32_t tracked_bits = 0;
+        {
+            uint32_t any_c = 0;
+#pragma unroll
+            for (int c = 0; c < NC; ++c) any_c |= mymk[c * MW];
+            tracked_bits = (any_c >> 8) & 0xFFu;
+        }
+        if (__any_sync(FULL, goals_active)) {
+            int r = 0, delayed = 0;
+            uint32_t in_bits = 0, whs = 0, old_goals = 0;
+            if (goals_active) {
+#pragma unroll
+                for (int t = 0; t < NT; ++t) {
+                    uint32_t tpack = __float_as_uint(myval[S::V_T + 3 * t + 2]);
+                    int bounty = tp_bounty(tpack);
+                    const int tracked = (tracked_bits >> t) & 1;
+                    if (tracked && bounty > 0) r -= 1;
+                    bounty = max(bounty - tracked, 0);
+                    tpack = (tpack & ~0xFFFFu) | (uint32_t)bounty;
+                    myval[S::V_T + 3 * t + 2] = __uint_as_float(tpack);
+                    old_goals |= (uint32_t)(tp_goal(tpack) + 1) << (3 * t);
+                    // the four warehouses sit at (+-925, +-925): the one this target could be in is given by
+                    // the signs of its coordinates (constants.py:70-72 order: ++, -+, --, +-)
+                    const float fx = myval[S::V_T + 3 * t], fy = myval[S::V_T + 3 * t + 1];
+                    const float m = fmaxf(fabsf(fabsf(fx) - (float)kWarehouseCoord), fabsf(fabsf(fy) - (float)kWarehouseCoord));
+                    bool inside = m < (float)kWarehouseRadius - 1e-3f;
+                    if (!inside && m <= (float)kWarehouseRadius + 1e-3f) {
+                        const double tx = p.tgt_x[(size_t)t * bp + er], ty = p.tgt_y[(size_t)t * bp + er];
+                        inside = fmax(fabs(fabs(tx) - kWarehouseCoord), fabs(fabs(ty) - kWarehouseCoord)) <= kWarehouseRadius;
+                    }
+                    if (inside) {
+                        const int wq = (fy >= 0.0f) ? ((fx >= 0.0f) ? 0 : 1) : ((fx >= 0.0f) ? 3 : 2);
+                        in_bits |= 1u << t;
+                        whs |= (uint32_t)wq << (2 * t);
+                    }
+                }
+            }
+            // Sequential over the targets standing in a warehouse, ascending index, one per lane and iteration
+            while (__any_sync(FULL, in_bits != 0)) {
+                if (in_bits != 0) {
+                    load_cargo();
+                    const int t = __ffs(in_bits) - 1;
+                    in_bits &= in_bits - 1;
+                    const int w = (whs >> (2 * t)) & 3;
+                    const uint32_t tp_t = __float_as_uint(myval[S::V_T + 3 * t + 2]);
+                    int goal = tp_goal(tp_t), weight = tp_weight(tp_t), bnty = tp_bounty(tp_t);
+                    const int capacity = tp_capacity(tp_t);
+                    int empty = tp_empty(tp_t);
+                    bool proceed = true;
+                    if (goal >= 0) {
+                        if (goal == w) {
+                            const int reward = weight * p.freight_scale + bnty;
+                            r += reward;
+                            delayed += reward - (weight * p.bounty_scale - bnty);
+                            delivered += weight;
+                            cargo.awaiting_add(goal, -weight);
+                        } else {
+                            proceed = false;
+                        }
+                    }
+                    if (proceed) {
+                        bnty = 0; weight = 0; goal = -1;
+                        if (cargo.row_any(w)) {
+                            int new_goal;
+                            if (p.replay_choice) {
+                                new_goal = p.replay_choice[(size_t)er * NT + t];
+                            } else {   // np_random.choice(flatnonzero(remaining[w] > 0))
+                                const uint32_t ncand = (uint32_t)((cargo.get(w, 0) > 0) + (cargo.get(w, 1) > 0) + (cargo.get(w, 2) > 0) + (cargo.get(w, 3) > 0));
+                                const int pick = (int)rng_below(key, STREAM_CHOICE, (uint32_t)draw_step * (uint32_t)NT + (uint32_t)t, ncand);
+                                new_goal = 0;
+                                int seen = 0;
+#pragma unroll
+                                for (int gg = 0; gg < NW; ++gg) {
+                                    if (cargo.get(w, gg) > 0) { if (seen == pick) new_goal = gg; ++seen; }
+                                }
+                            }
+                            new_goal = min(max(new_goal, 0), NW - 1);
+                            const int rem = cargo.get(w, new_goal);
+                            weight = min(capacity, rem);
+                            cargo.add(w, new_goal, -weight);
+                            bnty = weight * p.bounty_scale;
+                            goal = new_goal;
+                        }
+                        cargo_dirty = true;
+                    }
+                    // empty_bits for the warehouse the target stands in (environment.py:1317-1318)
+                    empty = cargo.row_any(w) ? (empty & ~(1 << w)) : (empty | (1 << w));
+                    myval[S::V_T + 3 * t + 2] = __uint_as_float(pack_target(bnty, goal, weight, capacity, empty, tp_colliding(tp_t)));
+                }
+            }
+            if (goals_active) {
+                tdone_bits = 0;
+#pragma unroll
+                for (int t = 0; t < NT; ++t) {
+                    const int old_goal = (int)((old_goals >> (3 * t)) & 7u) - 1;
+                    const int goal = tp_goal(__float_as_uint(myval[S::V_T + 3 * t + 2]));
+                    tdone_bits |= (uint32_t)((goal != old_goal) && (old_goal >= 0)) << t;
+                }
+            }
+            if (step_goals) { reward_i = r; delayed_i = delayed; }
+            if (do_reset) {
+                tdone_bits = 0; delivered = 0;   // environment.py:785-788
+                // targets_start_with_cargoes (environment.py:789-812): sequential over targets without a goal
+                if (p.start_with_cargoes) {
+#pragma unroll 1
+                    for (int t = 0; t < NT; ++t) {
+                        const uint32_t tp_t = __float_as_uint(myval[S::V_T + 3 * t + 2]);
+                        if (tp_goal(tp_t) >= 0) continue;
+                        int perm[NW] = {0, 1, 2, 3};   // np_random.permutation(4)
+#pragma unroll
+                        for (int i = NW - 1; i >= 1; --i) {
+                            const int k = (int)rng_below(key, STREAM_INIT_GOAL, (uint32_t)(t * 8 + i), (uint32_t)(i + 1));
+                            int vi = perm[0], vk = perm[0];
+#pragma unroll
+                            for (int q = 1; q < NW; ++q) { vi = (q == i) ? perm[q] : vi; vk = (q == k) ? perm[q] : vk; }
+#pragma unroll
+                            for (int q = 0; q < NW; ++q) { if (q == i) perm[q] = vk; else if (q == k) perm[q] = vi; }
+                        }
+                        bool assigned = false;
+#pragma unroll
+                        for (int k = 0; k < NW; ++k) {
+                            const int w = perm[k];
+                            if (!assigned && cargo.row_any(w)) {
+                                const uint32_t ncand = (uint32_t)((cargo.get(w, 0) > 0) + (cargo.get(w, 1) > 0) + (cargo.get(w, 2) > 0) + (cargo.get(w, 3) > 0));
+                                const int pick = (int)rng_below(key, STREAM_INIT_GOAL, (uint32_t)(t * 8 + 4), ncand);
+                                int goal = 0, seen = 0;
+#pragma unroll
+                                for (int gg = 0; gg < NW; ++gg) {
+                                    if (cargo.get(w, gg) > 0) { if (seen == pick) goal = gg; ++seen; }
+                                }
+                                const int capacity = tp_capacity(tp_t);
+                                const int weight = min(capacity, cargo.get(w, goal));
+                                cargo.add(w, goal, -weight);
+                                myval[S::V_T + 3 * t + 2] = __uint_as_float(pack_target(weight * p.bounty_scale, goal, weight, capacity, tp_empty(tp_t), 0));
+                                assigned = true;
+                            }
+                        }
+                    }
+                }
+            }
+        }
+        // coverage statistics of the current view (environment.py:966-972)
+        if (view_active || goals_active) {
+            uint32_t wb_bits = 0;
+#pragma unroll
+            for (int t = 0; t < NT; ++t) wb_bits |= (uint32_t)(tp_bounty(__float_as_uint(myval[S::V_T + 3 * t + 2])) > 0) << t;
+            const int nwb = __popc(wb_bits);
+            cov_now = (float)__popc(tracked_bits) / (float)NT;
+            cov_real = nwb > 0 ? (float)__popc(wb_bits & tracked_bits) / (float)nwb : 0.f;
+        }
+
+        if (!step_goals) break;
+
+        // ============================================================== finish step (environment.py:614-632)
+        ep_reward += reward_i;
+        delayed_ep_reward += delayed_i;
+        episode_step += 1;
+        coverage_sum += cov_now;
+        done = !(episode_step <= p.max_episode_steps && cargo.any_awaiting());
+        if (env_ok) {
+            const int r_out = p.reward_sparse ? delayed_i : reward_i;
+            reinterpret_cast<float2*>(p.rewards)[e] = make_float2(-(float)r_out, (float)r_out);
+            p.done[e] = (uint8_t)done;
+            if (done) {
+                atomicAdd(&p.stats[0], 1.0f);
+                atomicAdd(&p.stats[1], (float)ep_reward);
+                atomicAdd(&p.stats[2], (float)episode_step);
+                atomicAdd(&p.stats[3], (float)delivered);
+                atomicAdd(&p.stats[4], coverage_sum / (float)episode_step);
+            }
+        }
+        emit_aux();   // aux reflects the step just taken (before any auto-reset)
+        auto_reset_needed = env_ok && done && (p.flags & MATE_STEP_AUTO_RESET);
+        if (!__any_sync(FULL, auto_reset_needed)) break;
+    }
+    if (mode != MODE_STEP) emit_aux();
+    const int nvalid = min(32, p.num_envs - env0);
+    if (mode == MODE_STEP && lane == 0) atomicAdd(&p.stats[5], (float)nvalid);
+
+    // ------------------------------------------------------------------ write state back
+    if (env_ok && mode != MODE_OBSERVE) {
+#pragma unroll
+        for (int t = 0; t < NT; ++t) p.tgt_pack[(size_t)t * bp + e] = __float_as_uint(myval[S::V_T + 3 * t + 2]);
+        if (cargo_dirty) {
+            p.cargo[e] = make_uint4(cargo.rem[0], cargo.rem[1], cargo.rem[2], cargo.rem[3]);
+            p.cargo[bp + e] = make_uint4(cargo.rem[4], cargo.rem[5], cargo.rem[6], cargo.rem[7]);
+        }
+        p.env_a[e] = make_uint4(cargo.aw[0], cargo.aw[1], (uint32_t)episode_step, (uint32_t)delivered);
+        p.env_b[e] = make_int4(ep_reward, delayed_ep_reward, __float_as_int(coverage_sum), episode_id);
+    }
+    __syncwarp();
+
+    // ------------------------------------------------------------------ joint_observation (environment.py:908-983)
+    // The warp walks over its environments.  Lanes are the ENTITIES of the environment (targets,
+    // then obstacles, then cameras; a second pass if there are more than 32): each lane scatters its
+    // entity's public state into the rows of the observers whose mask bit is set.
+    constexpr int C_SELF = 13, C_TGT = 22, C_OBS = 22 + 5 * NT, C_CAM = 22 + 5 * NT + 4 * NO;
+    constexpr int T_SELF = 13, T_CAM = 27, T_OBS = 27 + 7 * NC, T_TGT = 27 + 7 * NC + 4 * NO;
+    constexpr int EPASS = (S::E + 31) / 32;
+    const float f_sr = (float)p.tgt_sight_range, f_crad = (float)p.cam_radius;
+#pragma unroll 1
+    for (int i = 0; i < nvalid; ++i) {
+        const float* v = val + i * S::VSTRIDE;
+        const uint32_t* m = mk + i * S::MSTRIDE;
+        const int env = env0 + i;
+        if (i > 0) {
+            if (S::BULK) { if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+            __syncwarp();
+        }
+        {   // masked-out entries of an observation are all-zero: clear, then write only what is visible
+            float4* z = reinterpret_cast<float4*>(stage);
+            const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 4
+            for (int k = lane; k < S::STAGE_FLOATS / 4; k += 32) z[k] = zero;
+        }
+        __syncwarp();
+#pragma unroll
+        for (int ep = 0; ep < EPASS; ++ep) {
+            const int slot = ep * 32 + lane;
+            // entity of this lane: kind 0 = target, 1 = obstacle, 2 = camera
+            const int kind = slot < NT ? 0 : (slot < NT + NO ? 1 : 2);
+            const int idx = slot < NT ? slot : (slot < NT + NO ? slot - NT : slot - NT - NO);
+            const bool live = slot < S::E;
+            float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f, a4 = 0.f, a5 = 0.f;
+            int off_c = 0, off_t = 0, word = 0;
+            uint32_t bit = 0;
+            if (live) {
+                if (kind == 0) {          // Target.state public part (entities.py:631-637) + flag
+                    const uint32_t tpk = __float_as_uint(v[S::V_T + 3 * idx + 2]);
+                    a0 = v[S::V_T + 3 * idx]; a1 = v[S::V_T + 3 * idx + 1]; a2 = f_sr;
+                    a3 = (tp_goal(tpk) >= 0 && tp_weight(tpk) > 0) ? 1.f : 0.f; a4 = 1.f;
+                    off_c = C_TGT + 5 * idx; off_t = T_TGT + 5 * idx; bit = bit_tgt(idx);
+                } else if (kind == 1) {   // Obstacle.state (entities.py:147-148) + flag
+                    const float4 ob = p.obs_f4[(size_t)idx * bp + env];
+                    a0 = ob.x; a1 = ob.y; a2 = ob.z; a3 = 1.f;
+                    off_c = C_OBS + 4 * idx; off_t = T_OBS + 4 * idx;
+                    bit = MW == 1 ? (1u << (16 + idx)) : (1u << (idx & 31)); word = MW - 1;
+                } else {                  // Camera.state public part (entities.py:313-324) + flag
+                    const float* cv = v + S::V_C + 5 * idx;
+                    a0 = cv[0]; a1 = cv[1]; a2 = f_crad; a3 = cv[2]; a4 = cv[3]; a5 = cv[4];
+                    off_c = C_CAM + 7 * idx; off_t = T_CAM + 7 * idx; bit = bit_cam(idx);
+                }
+            }
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                const uint32_t w = m[r * MW + word];
+                if (live && (w & bit)) {
+                    float* q = stage + (r < NC ? r * DC + off_c : S::STAGE_CAM + (r - NC) * DT + off_t);
+                    q[0] = a0; q[1] = a1; q[2] = a2; q[3] = a3;
+                    if (kind != 1) q[4] = a4;
+                    if (kind == 2) { q[5] = a5; q[6] = 1.f; }
+                }
+            }
+        }
+        // own rows: preserved data (lanes 0..R-1) and the observer's own state (lanes 16..16+R-1)
+        if (lane < R) {
+            const int r = lane;
+            float* q = stage + (r < NC ? r * DC : S::STAGE_CAM + (r - NC) * DT);
+            q[0] = (float)NC; q[1] = (float)NT; q[2] = (float)NO; q[3] = (float)(r < NC ? r : r - NC);
+            q[4] = 925.f; q[5] = 925.f; q[6] = -925.f; q[7] = 925.f; q[8] = -925.f; q[9] = -925.f; q[10] = 925.f; q[11] = -925.f;
+            q[12] = 75.f;
+        } else if (lane >= 16 && lane < 16 + R) {
+            const int r = lane - 16;
+            if (r < NC) {
+                const float* cv = v + S::V_C + 5 * r;
+                float* q = stage + r * DC + C_SELF;
+                q[0] = cv[0]; q[1] = cv[1]; q[2] = f_crad; q[3] = cv[2]; q[4] = cv[3]; q[5] = cv[4];
+                q[6] = (float)p.cam_rmax; q[7] = (float)p.cam_rot_step; q[8] = (float)p.cam_zoom_step;
+            } else {
+                const int t = r - NC;
+                const uint32_t tpk = __float_as_uint(v[S::V_T + 3 * t + 2]);
+                const int goal = tp_goal(tpk), weight = tp_weight(tpk), capacity = tp_capacity(tpk), empty = tp_empty(tpk);
+                float* q = stage + S::STAGE_CAM + t * DT + T_SELF;
+                q[0] = v[S::V_T + 3 * t]; q[1] = v[S::V_T + 3 * t + 1]; q[2] = f_sr;
+                q[3] = (goal >= 0 && weight > 0) ? 1.f : 0.f;
+                q[4] = (float)(p.tgt_step_size / (double)capacity); q[5] = (float)capacity;
+#pragma unroll
+                for (int w = 0; w < NW; ++w) { q[6 + w] = (goal == w) ? (float)weight : 0.f; q[10 + w] = (float)((empty >> w) & 1); }
+            }
+        }
+        // ---- staged rows -> HBM: one bulk (TMA) copy per tensor, issued by one lane
+        if (S::BULK) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) {
+                if (NC > 0) {
+                    const uint32_t src = (uint32_t)__cvta_generic_to_shared(stage);
+                    float* dst = p.cam_obs + (size_t)env * S::CAM_ROW;
+                    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                                 :: "l"(dst), "r"(src), "r"((uint32_t)(S::CAM_ROW * 4)) : "memory");
+                }
+                const uint32_t src = (uint32_t)__cvta_generic_to_shared(stage + S::STAGE_CAM);
+                float* dst = p.tgt_obs + (size_t)env * S::TGT_ROW;
+                asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                             :: "l"(dst), "r"(src), "r"((uint32_t)(S::TGT_ROW * 4)) : "memory");
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            }
+        } else {
+            __syncwarp();
+            if (NC > 0) {
+                float* dst = p.cam_obs + (size_t)env * S::CAM_ROW;
+                for (int k = lane; k < S::CAM_ROW; k += 32) dst[k] = stage[k];
+            }
+            float* dst = p.tgt_obs + (size_t)env * S::TGT_ROW;
+            for (int k = lane; k < S::TGT_ROW; k += 32) dst[k] = stage[S::STAGE_CAM + k];
+            __syncwarp();
+        }
+    }
+    if (S::BULK && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+
+}  // namespace mate
