@@ -51,8 +51,10 @@ struct Shape2 {
     // they fit, obstacles (bits 16-31); otherwise obstacles take a second word
     static constexpr int MW = NO <= 16 ? 1 : 2;
     static constexpr int MSTRIDE = (R * MW) | 1;               // odd stride: lane-per-env access is conflict free
-    // fp32 values per environment: targets {x, y, packed state}, cameras {x, y, Rs cos, Rs sin, theta}
-    static constexpr int V_T = 0, V_C = 3 * NT, VN = 3 * NT + 5 * NC;
+    // fp32 values per environment: targets {x, y, packed state}, cameras {x, y, theta, Rs, cos phi, sin phi,
+    // cos^2(theta/2)} (the observation packer and the fp32 prefilters read the same entries)
+    static constexpr int CV = 7;
+    static constexpr int V_T = 0, V_C = 3 * NT, VN = 3 * NT + CV * NC;
     static constexpr int VSTRIDE = VN | 1;
     static constexpr int STAGE_CAM = ((CAM_ROW + 3) / 4) * 4;
     static constexpr int STAGE_FLOATS = STAGE_CAM + ((TGT_ROW + 3) / 4) * 4;
@@ -65,7 +67,8 @@ struct Shape2 {
     static constexpr int OFF_MASK = OFF_STAGE + STAGE_FLOATS * 4;
     static constexpr int OFF_VAL = OFF_MASK + 32 * MSTRIDE * 4;
     static constexpr int OFF_Q = OFF_VAL + 32 * VSTRIDE * 4;
-    static constexpr int WARP_BYTES = ((OFF_Q + QCAP * 2 + 15) / 16) * 16;
+    static constexpr int OFF_Q2 = OFF_Q + QCAP * 2;             // second queue: pairs that need the exact polyline
+    static constexpr int WARP_BYTES = ((OFF_Q2 + QCAP * 2 + 15) / 16) * 16;
     static constexpr int SMEM_BYTES = WARPS * WARP_BYTES;
 };
 
@@ -233,6 +236,61 @@ __device__ __noinline__ void write_aux_env(const Params& p, int e, const uint32_
     if (ax.episode_step) ax.episode_step[e] = episode_step;
 }
 
+// Camera.simulate's derived quantities (entities.py:334,360) -> the fp32 entries of one camera
+__device__ __forceinline__ void store_camera(float* v, double x, double y, double phi, double theta, double area_product) {
+    const double rs = sqrt(area_product / theta);
+    double sn, cs;
+    sincospi(phi * (1.0 / 180.0), &sn, &cs);
+    const float ch = cospif((float)theta * (1.0f / 360.0f));
+    v[0] = (float)x; v[1] = (float)y; v[2] = (float)theta; v[3] = (float)rs; v[4] = (float)cs; v[5] = (float)sn; v[6] = ch * ch;
+}
+
+// ---- guard-band resolution (rare): the fp32 test fell inside its band, the fp64 expression decides.
+// One call site per loop nest; `band` has one bit per partner entity, the result has the bits that pass.
+// kind: 0 = partner targets, 1 = partner cameras; (ax, ay) is the fixed entity.
+__device__ __noinline__ uint32_t resolve_band(const Params& p, int er, const double* ax, const double* ay, uint32_t band, int kind,
+                                              double thr, bool strict) {
+    uint32_t out = 0;
+    while (band) {
+        const int k = __ffs(band) - 1;
+        band &= band - 1;
+        const size_t i = (size_t)k * p.bpad + er;
+        const double* bx = kind == 0 ? p.tgt_x + i : p.cam_x + i;
+        const double* by = kind == 0 ? p.tgt_y + i : p.cam_y + i;
+        if (sense_exact(ax, ay, bx, by, thr, strict)) out |= 1u << k;
+    }
+    return out;
+}
+// same for the range + sector test of camera c against partner targets (kind 0) / cameras (kind 1)
+__device__ __noinline__ uint32_t resolve_fov_band(const Params& p, int er, int c, uint32_t band, int kind) {
+    uint32_t out = 0;
+    while (band) {
+        const int k = __ffs(band) - 1;
+        band &= band - 1;
+        const size_t i = (size_t)k * p.bpad + er;
+        if (fov_reach_global(p, er, c, kind == 0 ? p.tgt_x + i : p.cam_x + i, kind == 0 ? p.tgt_y + i : p.cam_y + i)) out |= 1u << k;
+    }
+    return out;
+}
+
+// Exact evaluation of the sampled FOV polyline for the queued (camera, target) pairs whose occlusion the
+// conservative classification could not decide: 32 pairs at a time, one per lane.
+template <int NC, int NT, int NO, class S>
+__device__ __noinline__ void process_exact(const Params& p, int env0, uint32_t* mk, const uint16_t* queue2, int base, int n) {
+    const int lane = threadIdx.x & 31;
+    if (lane >= n) return;
+    const uint32_t item = queue2[base + lane];
+    const int src = item >> 8, b = item & 0xFF;
+    const int c = b / NT, t = b - c * NT;
+    const int envr = min(env0 + src, p.num_envs - 1);
+    const size_t bp = p.bpad;
+    const double cx = p.cam_x[(size_t)c * bp + envr], cy = p.cam_y[(size_t)c * bp + envr];
+    const double relx = p.tgt_x[(size_t)t * bp + envr] - cx, rely = p.tgt_y[(size_t)t * bp + envr] - cy;
+    const bool sees = occlusion_exact<NO>(ObsRef{p.obs_x + envr, p.obs_y + envr, p.obs_r + envr, bp}, cx, cy, relx, rely,
+                                          sqrt(relx * relx + rely * rely), p.cam_rmax);
+    if (sees) atomicOr(&mk[src * S::MSTRIDE + c * S::MW], bit_tgt(t));
+}
+
 // =============================================================================================
 // The fused kernel
 // =============================================================================================
@@ -241,10 +299,9 @@ __global__ void __launch_bounds__(Shape2<NC, NT, NO>::WARPS * 32, MATE2_MIN_CTAS
 mate_step_kernel2(const Params p) {
     using S = Shape2<NC, NT, NO>;
     static_assert(NC <= 8 && NT <= 8 && NO <= 32, "mask layout: 8 cameras, 8 targets, 32 obstacles");
-    constexpr int R = S::R, MW = S::MW, DC = S::DC, DT = S::DT;
+    constexpr int R = S::R, MW = S::MW, DC = S::DC, DT = S::DT, CV = S::CV;
     constexpr int NCX = NC > 0 ? NC : 1;
     constexpr uint32_t FULL = 0xffffffffu;
-    constexpr bool CC_CACHE = NC >= 2;   // camera <-> camera lines of sight are static within an episode
 
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -253,8 +310,10 @@ mate_step_kernel2(const Params p) {
     uint32_t* mk = reinterpret_cast<uint32_t*>(wbase + S::OFF_MASK);      // [32][MSTRIDE]
     float* val = reinterpret_cast<float*>(wbase + S::OFF_VAL);            // [32][VSTRIDE]
     uint16_t* queue = reinterpret_cast<uint16_t*>(wbase + S::OFF_Q);
+    uint16_t* queue2 = reinterpret_cast<uint16_t*>(wbase + S::OFF_Q2);
     uint32_t* mymk = mk + lane * S::MSTRIDE;
     float* myval = val + lane * S::VSTRIDE;
+    float* mycam = myval + S::V_C;
 
     const int env0 = (blockIdx.x * S::WARPS + warp) * 32;     // first env of this warp
     if (env0 >= p.num_envs) return;                            // warps never synchronise with each other
@@ -267,37 +326,16 @@ mate_step_kernel2(const Params p) {
     // ------------------------------------------------------------------ per-env scalars
     const uint4 ea = p.env_a[er];
     const int4 eb = p.env_b[er];
-    unsigned long long ccw = CC_CACHE ? p.cc_clear[er] : 0ull;
+    unsigned long long ccw = NC >= 2 ? p.cc_clear[er] : 0ull;   // static camera <-> camera lines of sight (per episode)
     Cargo cargo;
     cargo.aw[0] = ea.x; cargo.aw[1] = ea.y;
     int episode_step = (int)ea.z, delivered = (int)ea.w;
     int ep_reward = eb.x, delayed_ep_reward = eb.y, episode_id = eb.w;
     float coverage_sum = __int_as_float(eb.z);
     bool cargo_loaded = false, cargo_dirty = false;
-    auto load_cargo = [&]() {
-        if (cargo_loaded) return;
-        const uint4 c0 = p.cargo[er], c1 = p.cargo[bp + er];
-        cargo.rem[0] = c0.x; cargo.rem[1] = c0.y; cargo.rem[2] = c0.z; cargo.rem[3] = c0.w;
-        cargo.rem[4] = c1.x; cargo.rem[5] = c1.y; cargo.rem[6] = c1.z; cargo.rem[7] = c1.w;
-        cargo_loaded = true;
-    };
-
-    // fp32 shadow of the cameras for the prefilters (registers)
-    float fcx[NCX], fcy[NCX], f_rs2[NCX], f_cos[NCX], f_sin[NCX], f_ch2[NCX];
-    auto derive_camera = [&](const int c, const double x, const double y, const double phi, const double theta) {
-        const double rs = sqrt(p.cam_area_product / theta);      // entities.py:334,360
-        double sn, cs;
-        sincospi(phi * (1.0 / 180.0), &sn, &cs);
-        fcx[c] = (float)x; fcy[c] = (float)y;
-        f_rs2[c] = (float)(rs * rs); f_cos[c] = (float)cs; f_sin[c] = (float)sn;
-        const float ch = cospif((float)theta * (1.0f / 360.0f));
-        f_ch2[c] = ch * ch;
-        float* v = myval + S::V_C + 5 * c;                        // Camera.state (entities.py:313-324), public part
-        v[0] = fcx[c]; v[1] = fcy[c]; v[2] = (float)(rs * cs); v[3] = (float)(rs * sn); v[4] = (float)theta;
-    };
 
     // ------------------------------------------------------------------ _simulate (environment.py:1326-1354)
-#pragma unroll
+#pragma unroll 1
     for (int c = 0; c < NC; ++c) {   // Camera.simulate (entities.py:347-360)
         const size_t i = (size_t)c * bp + er;
         const double x = p.cam_x[i], y = p.cam_y[i];
@@ -310,7 +348,7 @@ mate_step_kernel2(const Params p) {
             theta = fmin(fmax(theta + dv, p.cam_min_view), 180.0);
             if (env_ok) { p.cam_phi[(size_t)c * bp + e] = phi; p.cam_theta[(size_t)c * bp + e] = theta; }
         }
-        derive_camera(c, x, y, phi, theta);
+        store_camera(mycam + CV * c, x, y, phi, theta, p.cam_area_product);
     }
     {   // Target.simulate (entities.py:645-668): fast path = no disc within reach of the step
         uint32_t slow = 0;     // targets that may touch a disc: re-simulated exactly below
@@ -321,7 +359,7 @@ mate_step_kernel2(const Params p) {
 #pragma unroll
             for (int t = 0; t < NT; ++t) { otx[t] = (float)p.tgt_x[(size_t)t * bp + er]; oty[t] = (float)p.tgt_y[(size_t)t * bp + er]; }
             const float fb = (float)p.tgt_step_size * 1.00001f + 0.01f;
-#pragma unroll
+#pragma unroll 1
             for (int o = 0; o < NO; ++o) {
                 const float4 ob = p.obs_f4[(size_t)o * bp + er];
                 const float reach = fb + ob.z, reach2 = reach * reach;
@@ -332,16 +370,17 @@ mate_step_kernel2(const Params p) {
                 }
             }
             const float reach_c = fb + (float)p.cam_radius, reach_c2 = reach_c * reach_c;
-#pragma unroll
+#pragma unroll 1
             for (int c = 0; c < NC; ++c) {
+                const float cx = mycam[CV * c], cy = mycam[CV * c + 1];
 #pragma unroll
                 for (int t = 0; t < NT; ++t) {
-                    const float dx = fcx[c] - otx[t], dy = fcy[c] - oty[t];
+                    const float dx = cx - otx[t], dy = cy - oty[t];
                     slow |= (uint32_t)(!(dx * dx + dy * dy > reach_c2)) << t;
                 }
             }
         }
-#pragma unroll
+#pragma unroll 1
         for (int t = 0; t < NT; ++t) {
             const size_t i = (size_t)t * bp + er;
             double tx = p.tgt_x[i], ty = p.tgt_y[i];
@@ -394,22 +433,6 @@ mate_step_kernel2(const Params p) {
     int draw_step = (mode == MODE_STEP) ? episode_step + 1 : episode_step;
     RngKey key{p.seed, (uint32_t)(p.env_index_base + e), (uint32_t)episode_id};
 
-    auto emit_aux = [&]() {
-        if (!p.has_aux || !env_ok) return;
-        const float transport = delivered > 0 ? (float)((double)delayed_ep_reward / ((double)p.reward_scale * (double)delivered)) : 0.f;
-        if (!p.has_aux_detail) {   // the common case: only the info-dict scalars (environment.py:634-639)
-            if (p.aux.coverage) {
-                p.aux.coverage[(size_t)e * 3 + 0] = cov_now;
-                p.aux.coverage[(size_t)e * 3 + 1] = cov_real;
-                p.aux.coverage[(size_t)e * 3 + 2] = transport;
-            }
-            if (p.aux.num_delivered) p.aux.num_delivered[e] = delivered;
-            if (p.aux.episode_step) p.aux.episode_step[e] = episode_step;
-            return;
-        }
-        write_aux_env<NC, NT, NO, S>(p, e, mymk, myval, tdone_bits, cov_now, cov_real, transport, delivered, episode_step);
-    };
-
     const float fsr = (float)p.tgt_sight_range;
     const float fsr2 = fsr * fsr, fsrc = fsr + (float)p.cam_radius, fsrc2 = fsrc * fsrc;
     const double sr = p.tgt_sight_range, src = sr + p.cam_radius;
@@ -430,10 +453,10 @@ mate_step_kernel2(const Params p) {
                 episode_id += 1; key.episode = (uint32_t)episode_id;
                 episode_step = 0; delivered = 0; ep_reward = 0; delayed_ep_reward = 0; coverage_sum = 0.f;
                 ccw = 0ull; tdone_bits = 0; draw_step = 0;
-#pragma unroll
+#pragma unroll 1
                 for (int c = 0; c < NC; ++c) {
                     const size_t i = (size_t)c * bp + e;
-                    derive_camera(c, p.cam_x[i], p.cam_y[i], p.cam_phi[i], p.cam_theta[i]);
+                    store_camera(mycam + CV * c, p.cam_x[i], p.cam_y[i], p.cam_phi[i], p.cam_theta[i], p.cam_area_product);
                 }
 #pragma unroll 1
                 for (int t = 0; t < NT; ++t) {
@@ -450,87 +473,104 @@ mate_step_kernel2(const Params p) {
             float ftx[NT], fty[NT];
 #pragma unroll
             for (int t = 0; t < NT; ++t) { ftx[t] = myval[S::V_T + 3 * t]; fty[t] = myval[S::V_T + 3 * t + 1]; }
+            float fcx[NCX], fcy[NCX];
+#pragma unroll
+            for (int c = 0; c < NC; ++c) { fcx[c] = mycam[CV * c]; fcy[c] = mycam[CV * c + 1]; }
             uint32_t crow[NCX], crow2[NCX], trow[NT], trow2[NT];
 #pragma unroll
             for (int c = 0; c < NC; ++c) { crow[c] = bit_cam(c); crow2[c] = 0; }   // environment.py:1383-1384
 #pragma unroll
             for (int t = 0; t < NT; ++t) { trow[t] = bit_tgt(t); trow2[t] = 0; }   // environment.py:1376-1377
             // ---- omnidirectional sensing by targets, Sensor.perceive (entities.py:229-232) ----
-            // fp32 on squares; inside a 4e-6 relative band the fp64 test decides
+            // fp32 on squares; inside a 4e-6 relative band the fp64 test decides (resolve_band, rare)
 #pragma unroll
             for (int t = 0; t < NT; ++t) {
+                uint32_t band_t = 0, band_c = 0;
 #pragma unroll
                 for (int u = t + 1; u < NT; ++u) {   // symmetric
                     const float dx = ftx[u] - ftx[t], dy = fty[u] - fty[t], d2 = dx * dx + dy * dy;
-                    bool sees = d2 < fsr2 * (1.0f - 4e-6f);
-                    if (!sees && d2 <= fsr2 * (1.0f + 4e-6f))
-                        sees = sense_exact(p.tgt_x + (size_t)u * bp + er, p.tgt_y + (size_t)u * bp + er,
-                                           p.tgt_x + (size_t)t * bp + er, p.tgt_y + (size_t)t * bp + er, sr, false);
-                    if (sees) { trow[t] |= bit_tgt(u); trow[u] |= bit_tgt(t); }
+                    if (d2 < fsr2 * (1.0f - 4e-6f)) { trow[t] |= bit_tgt(u); trow[u] |= bit_tgt(t); }
+                    else if (d2 <= fsr2 * (1.0f + 4e-6f)) band_t |= 1u << u;
                 }
 #pragma unroll
                 for (int c = 0; c < NC; ++c) {       // target t senses camera c
                     const float dx = fcx[c] - ftx[t], dy = fcy[c] - fty[t], d2 = dx * dx + dy * dy;
-                    bool sees = d2 < fsrc2 * (1.0f - 4e-6f);
-                    if (!sees && d2 <= fsrc2 * (1.0f + 4e-6f))
-                        sees = sense_exact(p.cam_x + (size_t)c * bp + er, p.cam_y + (size_t)c * bp + er,
-                                           p.tgt_x + (size_t)t * bp + er, p.tgt_y + (size_t)t * bp + er, src, false);
-                    if (sees) trow[t] |= bit_cam(c);
+                    if (d2 < fsrc2 * (1.0f - 4e-6f)) trow[t] |= bit_cam(c);
+                    else if (d2 <= fsrc2 * (1.0f + 4e-6f)) band_c |= 1u << c;
+                }
+                if (band_t | band_c) {
+                    const double* ax = p.tgt_x + (size_t)t * bp + er;
+                    const double* ay = p.tgt_y + (size_t)t * bp + er;
+                    if (band_t) {
+                        const uint32_t fix = resolve_band(p, er, ax, ay, band_t, 0, sr, false);
+#pragma unroll
+                        for (int u = t + 1; u < NT; ++u) if ((fix >> u) & 1) { trow[t] |= bit_tgt(u); trow[u] |= bit_tgt(t); }
+                    }
+                    if (band_c) trow[t] |= resolve_band(p, er, ax, ay, band_c, 1, src, false);   // bit_cam(c) == 1 << c
                 }
             }
-#pragma unroll
+#pragma unroll 1
             for (int o = 0; o < NO; ++o) {
                 const float4 ob = p.obs_f4[(size_t)o * bp + er];
                 const uint32_t obit = MW == 1 ? (1u << (16 + o)) : (1u << (o & 31));
                 const float rtf = fsr + ob.z, rt2 = rtf * rtf;
+                const float rcf = (float)p.cam_rmax + ob.z, rc2 = rcf * rcf;
+                uint32_t band_t = 0, band_c = 0;
 #pragma unroll
                 for (int t = 0; t < NT; ++t) {       // target t senses obstacle o
                     const float dx = ob.x - ftx[t], dy = ob.y - fty[t], d2 = dx * dx + dy * dy;
-                    bool sees = d2 < rt2 * (1.0f - 4e-6f);
-                    if (!sees && d2 <= rt2 * (1.0f + 4e-6f))
-                        sees = sense_exact(p.obs_x + (size_t)o * bp + er, p.obs_y + (size_t)o * bp + er,
-                                           p.tgt_x + (size_t)t * bp + er, p.tgt_y + (size_t)t * bp + er,
-                                           sr + p.obs_r[(size_t)o * bp + er], false);
-                    if (sees) { if (MW == 1) trow[t] |= obit; else trow2[t] |= obit; }
+                    if (d2 < rt2 * (1.0f - 4e-6f)) { if (MW == 1) trow[t] |= obit; else trow2[t] |= obit; }
+                    else if (d2 <= rt2 * (1.0f + 4e-6f)) band_t |= 1u << t;
                 }
-                const float rcf = (float)p.cam_rmax + ob.z, rc2 = rcf * rcf;
 #pragma unroll
                 for (int c = 0; c < NC; ++c) {       // camera c has obstacle o in its set (entities.py:363-368, strict <)
                     const float dx = ob.x - fcx[c], dy = ob.y - fcy[c], d2 = dx * dx + dy * dy;
-                    bool inset = d2 < rc2 * (1.0f - 4e-6f);
-                    if (!inset && d2 <= rc2 * (1.0f + 4e-6f))
-                        inset = sense_exact(p.obs_x + (size_t)o * bp + er, p.obs_y + (size_t)o * bp + er,
-                                            p.cam_x + (size_t)c * bp + er, p.cam_y + (size_t)c * bp + er,
-                                            p.cam_rmax + p.obs_r[(size_t)o * bp + er], true);
-                    if (inset) { if (MW == 1) crow[c] |= obit; else crow2[c] |= obit; }
+                    if (d2 < rc2 * (1.0f - 4e-6f)) { if (MW == 1) crow[c] |= obit; else crow2[c] |= obit; }
+                    else if (d2 <= rc2 * (1.0f + 4e-6f)) band_c |= 1u << c;
+                }
+                if (band_t | band_c) {
+                    const size_t io = (size_t)o * bp + er;
+                    const double orad = p.obs_r[io];
+                    const uint32_t fix_t = band_t ? resolve_band(p, er, p.obs_x + io, p.obs_y + io, band_t, 0, sr + orad, false) : 0u;
+                    const uint32_t fix_c = band_c ? resolve_band(p, er, p.obs_x + io, p.obs_y + io, band_c, 1, p.cam_rmax + orad, true) : 0u;
+#pragma unroll
+                    for (int t = 0; t < NT; ++t) if ((fix_t >> t) & 1) { if (MW == 1) trow[t] |= obit; else trow2[t] |= obit; }
+#pragma unroll
+                    for (int c = 0; c < NC; ++c) if ((fix_c >> c) & 1) { if (MW == 1) crow[c] |= obit; else crow2[c] |= obit; }
                 }
             }
             // ---- cameras: range + sector (Camera.perceive, entities.py:494-501) ----
+            // camera -> camera: the occlusion part is static within an episode and cached in `ccw`
+            if (NC >= 2 && view_active && (ccw >> 63) == 0ull) {
+                ccw = build_cc_cache<NC, NO>(p, er);
+                if (env_ok) p.cc_clear[e] = ccw;
+            }
 #pragma unroll
             for (int c = 0; c < NC; ++c) {
+                const float* cv = mycam + CV * c;
+                const float rs = cv[3], rs2 = rs * rs, cs = cv[4], sn = cv[5], ch2 = cv[6];
+                uint32_t reach_t = 0, band_t = 0, reach_c = 0, band_c = 0;
 #pragma unroll
                 for (int t = 0; t < NT; ++t) {
-                    int reach = fov_reach32(fcx[c], fcy[c], f_rs2[c], f_cos[c], f_sin[c], f_ch2[c], ftx[t], fty[t]);
-                    if (reach == 2) reach = fov_reach_global(p, er, c, p.tgt_x + (size_t)t * bp + er, p.tgt_y + (size_t)t * bp + er);
-                    if (reach) pend |= 1ull << (c * NT + t);
-                }
-            }
-            if (NC >= 2) {
-                // camera -> camera: the occlusion part is static within an episode and cached in `ccw`
-                if (view_active && (ccw >> 63) == 0ull) {
-                    ccw = build_cc_cache<NC, NO>(p, er);
-                    if (env_ok) p.cc_clear[e] = ccw;
+                    const int reach = fov_reach32(fcx[c], fcy[c], rs2, cs, sn, ch2, ftx[t], fty[t]);
+                    reach_t |= (uint32_t)(reach == 1) << t;
+                    band_t |= (uint32_t)(reach == 2) << t;
                 }
 #pragma unroll
-                for (int c = 0; c < NC; ++c) {
-#pragma unroll
-                    for (int j = 0; j < NC; ++j) {
-                        if (j == c) continue;
-                        int reach = fov_reach32(fcx[c], fcy[c], f_rs2[c], f_cos[c], f_sin[c], f_ch2[c], fcx[j], fcy[j]);
-                        if (reach == 2) reach = fov_reach_global(p, er, c, p.cam_x + (size_t)j * bp + er, p.cam_y + (size_t)j * bp + er);
-                        if (reach && ((ccw >> (8 * j + c)) & 1ull)) crow[c] |= bit_cam(j);
-                    }
+                for (int j = 0; j < NC; ++j) {
+                    if (j == c) continue;
+                    const int reach = fov_reach32(fcx[c], fcy[c], rs2, cs, sn, ch2, fcx[j], fcy[j]);
+                    reach_c |= (uint32_t)(reach == 1) << j;
+                    band_c |= (uint32_t)(reach == 2) << j;
                 }
+                if (band_t) reach_t |= resolve_fov_band(p, er, c, band_t, 0);
+                if (band_c) reach_c |= resolve_fov_band(p, er, c, band_c, 1);
+                pend |= (unsigned long long)reach_t << (c * NT);
+                // bits 8 j + c of ccw, j = 0..NC-1: camera c has a clear line of sight to camera j
+                uint32_t clear_c = 0;
+#pragma unroll
+                for (int j = 0; j < NC; ++j) clear_c |= (uint32_t)((ccw >> (8 * j + c)) & 1ull) << j;
+                crow[c] |= reach_c & clear_c;   // bit_cam(j) == 1 << j
             }
             if (view_active) {
 #pragma unroll
@@ -543,55 +583,69 @@ mate_step_kernel2(const Params p) {
         }
         __syncwarp();
         // ---- then the stochastic transmittance draw and the occlusion test (entities.py:503-505) ----
-        // All pending (camera, target) pairs of the warp's 32 environments go through a queue in
-        // shared memory and are evaluated 32 at a time, one pair per lane.
+        // All pending (camera, target) pairs of the warp's 32 environments go through a queue in shared
+        // memory and are evaluated 32 at a time, one pair per lane; pairs the conservative occlusion
+        // classification cannot decide go through a second queue to the exact polyline.
         if (NC > 0) {
-            int count = 0;   // warp-uniform
-            auto process = [&](const int base, const int n) {
-                const bool has = lane < n;
-                const uint32_t item = has ? queue[base + lane] : 0u;
-                const int src = item >> 8, b = item & 0xFF;
-                const int c = b / NT, t = b - c * NT;
-                const uint32_t src_episode = __shfl_sync(FULL, (uint32_t)episode_id, src);
-                const int src_draw = __shfl_sync(FULL, draw_step, src);
-                if (has) {
-                    const int env = env0 + src;
-                    const int envr = min(env, p.num_envs - 1);
-                    bool sees;
-                    if (p.replay_transmit) {
-                        sees = p.replay_transmit[((size_t)envr * NC + c) * NT + t] != 0;
-                    } else {
-                        const RngKey k{p.seed, (uint32_t)(p.env_index_base + env), src_episode};
-                        sees = rng_u01(k, STREAM_TRANSMIT, (uint32_t)src_draw * (uint32_t)(NC * NT) + (uint32_t)(c * NT + t)) < p.transmittance;
-                    }
-                    if (!sees) {
-                        if (NO == 0 || p.transmittance_is_one) {
-                            sees = true;   // polyline is the flat max_sight_range circle; dist <= rs <= Rmax
-                        } else {
-                            const float* v = val + src * S::VSTRIDE;
-                            sees = line_of_sight<NO>(p, envr, c, v[S::V_C + 5 * c], v[S::V_C + 5 * c + 1], v[S::V_T + 3 * t], v[S::V_T + 3 * t + 1],
-                                                     p.tgt_x + (size_t)t * bp + envr, p.tgt_y + (size_t)t * bp + envr);
-                        }
-                    }
-                    if (sees) atomicOr(&mk[src * S::MSTRIDE + c * MW], bit_tgt(t));
-                }
-            };
-            while (__any_sync(FULL, pend != 0ull)) {
-                const bool has = pend != 0ull;
-                const int b = has ? (__ffsll((long long)pend) - 1) : 0;
-                pend &= pend - 1ull;
-                const uint32_t ballot = __ballot_sync(FULL, has);
-                const int pos = count + __popc(ballot & ((1u << lane) - 1u));
-                if (has) queue[pos] = (uint16_t)((lane << 8) | b);
-                count += __popc(ballot);
-                __syncwarp();
-                if (count >= 32) {
-                    count -= 32;
-                    process(count, 32);
+            int count = 0, count2 = 0;   // warp-uniform
+            for (;;) {
+                const bool more = __any_sync(FULL, pend != 0ull);
+                if (more) {
+                    const bool has = pend != 0ull;
+                    const int b = has ? (__ffsll((long long)pend) - 1) : 0;
+                    pend &= pend - 1ull;
+                    const uint32_t ballot = __ballot_sync(FULL, has);
+                    const int pos = count + __popc(ballot & ((1u << lane) - 1u));
+                    if (has) queue[pos] = (uint16_t)((lane << 8) | b);
+                    count += __popc(ballot);
                     __syncwarp();
                 }
+                if (count >= 32 || (!more && count > 0)) {
+                    const int n = min(count, 32);
+                    count -= n;
+                    const bool has = lane < n;
+                    const uint32_t item = has ? queue[count + lane] : 0u;
+                    const int src = item >> 8, b = item & 0xFF;
+                    const int c = b / NT, t = b - c * NT;
+                    const uint32_t src_episode = __shfl_sync(FULL, (uint32_t)episode_id, src);
+                    const int src_draw = __shfl_sync(FULL, draw_step, src);
+                    bool need_exact = false;
+                    if (has) {
+                        const int env = env0 + src;
+                        const int envr = min(env, p.num_envs - 1);
+                        bool sees;
+                        if (p.replay_transmit) {
+                            sees = p.replay_transmit[((size_t)envr * NC + c) * NT + t] != 0;
+                        } else {
+                            const RngKey k{p.seed, (uint32_t)(p.env_index_base + env), src_episode};
+                            sees = rng_u01(k, STREAM_TRANSMIT, (uint32_t)src_draw * (uint32_t)(NC * NT) + (uint32_t)(c * NT + t)) < p.transmittance;
+                        }
+                        if (!sees) {
+                            if (NO == 0 || p.transmittance_is_one) {
+                                sees = true;   // polyline is the flat max_sight_range circle; dist <= rs <= Rmax
+                            } else {
+                                const float* v = val + src * S::VSTRIDE;
+                                const float cx = v[S::V_C + CV * c], cy = v[S::V_C + CV * c + 1];
+                                const int fast = occlusion_fast<NO>(p.obs_f4 + envr, bp, cx, cy, v[S::V_T + 3 * t] - cx, v[S::V_T + 3 * t + 1] - cy, (float)p.cam_rmax);
+                                sees = fast == 1;
+                                need_exact = fast == 2;
+                            }
+                        }
+                        if (sees) atomicOr(&mk[src * S::MSTRIDE + c * MW], bit_tgt(t));
+                    }
+                    const uint32_t ballot2 = __ballot_sync(FULL, need_exact);
+                    if (need_exact) queue2[count2 + __popc(ballot2 & ((1u << lane) - 1u))] = (uint16_t)item;
+                    count2 += __popc(ballot2);
+                    __syncwarp();
+                }
+                if (count2 >= 32 || (!more && count == 0 && count2 > 0)) {
+                    const int n = min(count2, 32);
+                    count2 -= n;
+                    process_exact<NC, NT, NO, S>(p, env0, mk, queue2, count2, n);
+                    __syncwarp();
+                }
+                if (!more && count == 0 && count2 == 0) break;
             }
-            if (count > 0) process(0, count);
             __syncwarp();
         }
 
@@ -638,7 +692,12 @@ mate_step_kernel2(const Params p) {
             // Sequential over the targets standing in a warehouse, ascending index, one per lane and iteration
             while (__any_sync(FULL, in_bits != 0)) {
                 if (in_bits != 0) {
-                    load_cargo();
+                    if (!cargo_loaded) {
+                        const uint4 c0 = p.cargo[er], c1 = p.cargo[bp + er];
+                        cargo.rem[0] = c0.x; cargo.rem[1] = c0.y; cargo.rem[2] = c0.z; cargo.rem[3] = c0.w;
+                        cargo.rem[4] = c1.x; cargo.rem[5] = c1.y; cargo.rem[6] = c1.z; cargo.rem[7] = c1.w;
+                        cargo_loaded = true;
+                    }
                     const int t = __ffs(in_bits) - 1;
                     in_bits &= in_bits - 1;
                     const int w = (whs >> (2 * t)) & 3;
@@ -749,31 +808,45 @@ mate_step_kernel2(const Params p) {
             cov_real = nwb > 0 ? (float)__popc(wb_bits & tracked_bits) / (float)nwb : 0.f;
         }
 
-        if (!step_goals) break;
-
-        // ============================================================== finish step (environment.py:614-632)
-        ep_reward += reward_i;
-        delayed_ep_reward += delayed_i;
-        episode_step += 1;
-        coverage_sum += cov_now;
-        done = !(episode_step <= p.max_episode_steps && cargo.any_awaiting());
-        if (env_ok) {
-            const int r_out = p.reward_sparse ? delayed_i : reward_i;
-            reinterpret_cast<float2*>(p.rewards)[e] = make_float2(-(float)r_out, (float)r_out);
-            p.done[e] = (uint8_t)done;
-            if (done) {
-                atomicAdd(&p.stats[0], 1.0f);
-                atomicAdd(&p.stats[1], (float)ep_reward);
-                atomicAdd(&p.stats[2], (float)episode_step);
-                atomicAdd(&p.stats[3], (float)delivered);
-                atomicAdd(&p.stats[4], coverage_sum / (float)episode_step);
+        const bool last_pass = !step_goals;
+        if (step_goals) {
+            // ============================================================== finish step (environment.py:614-632)
+            ep_reward += reward_i;
+            delayed_ep_reward += delayed_i;
+            episode_step += 1;
+            coverage_sum += cov_now;
+            done = !(episode_step <= p.max_episode_steps && cargo.any_awaiting());
+            if (env_ok) {
+                const int r_out = p.reward_sparse ? delayed_i : reward_i;
+                reinterpret_cast<float2*>(p.rewards)[e] = make_float2(-(float)r_out, (float)r_out);
+                p.done[e] = (uint8_t)done;
+                if (done) {
+                    atomicAdd(&p.stats[0], 1.0f);
+                    atomicAdd(&p.stats[1], (float)ep_reward);
+                    atomicAdd(&p.stats[2], (float)episode_step);
+                    atomicAdd(&p.stats[3], (float)delivered);
+                    atomicAdd(&p.stats[4], coverage_sum / (float)episode_step);
+                }
+            }
+            auto_reset_needed = env_ok && done && (p.flags & MATE_STEP_AUTO_RESET);
+        }
+        // aux reflects the step just taken (before any auto-reset) / the observed or reset state
+        if (p.has_aux && env_ok && (step_goals || mode != MODE_STEP)) {
+            const float transport = delivered > 0 ? (float)((double)delayed_ep_reward / ((double)p.reward_scale * (double)delivered)) : 0.f;
+            if (!p.has_aux_detail) {   // the common case: only the info-dict scalars (environment.py:634-639)
+                if (p.aux.coverage) {
+                    p.aux.coverage[(size_t)e * 3 + 0] = cov_now;
+                    p.aux.coverage[(size_t)e * 3 + 1] = cov_real;
+                    p.aux.coverage[(size_t)e * 3 + 2] = transport;
+                }
+                if (p.aux.num_delivered) p.aux.num_delivered[e] = delivered;
+                if (p.aux.episode_step) p.aux.episode_step[e] = episode_step;
+            } else {
+                write_aux_env<NC, NT, NO, S>(p, e, mymk, myval, tdone_bits, cov_now, cov_real, transport, delivered, episode_step);
             }
         }
-        emit_aux();   // aux reflects the step just taken (before any auto-reset)
-        auto_reset_needed = env_ok && done && (p.flags & MATE_STEP_AUTO_RESET);
-        if (!__any_sync(FULL, auto_reset_needed)) break;
+        if (last_pass || !__any_sync(FULL, auto_reset_needed)) break;
     }
-    if (mode != MODE_STEP) emit_aux();
     const int nvalid = min(32, p.num_envs - env0);
     if (mode == MODE_STEP && lane == 0) atomicAdd(&p.stats[5], (float)nvalid);
 
@@ -793,11 +866,15 @@ mate_step_kernel2(const Params p) {
     // ------------------------------------------------------------------ joint_observation (environment.py:908-983)
     // The warp walks over its environments.  Lanes are the ENTITIES of the environment (targets,
     // then obstacles, then cameras; a second pass if there are more than 32): each lane scatters its
-    // entity's public state into the rows of the observers whose mask bit is set.
+    // entity's public state into the rows of the observers whose mask bit is set; target and camera
+    // lanes also write their own row's preserved block and private state.
     constexpr int C_SELF = 13, C_TGT = 22, C_OBS = 22 + 5 * NT, C_CAM = 22 + 5 * NT + 4 * NO;
     constexpr int T_SELF = 13, T_CAM = 27, T_OBS = 27 + 7 * NC, T_TGT = 27 + 7 * NC + 4 * NO;
     constexpr int EPASS = (S::E + 31) / 32;
+    constexpr int NZ = S::STAGE_FLOATS / 4;
     const float f_sr = (float)p.tgt_sight_range, f_crad = (float)p.cam_radius;
+    const float f_rmax = (float)p.cam_rmax, f_rot = (float)p.cam_rot_step, f_zoom = (float)p.cam_zoom_step;
+    const float f_step1 = (float)p.tgt_step_size, f_step2 = (float)(p.tgt_step_size / 2.0);
 #pragma unroll 1
     for (int i = 0; i < nvalid; ++i) {
         const float* v = val + i * S::VSTRIDE;
@@ -810,8 +887,9 @@ mate_step_kernel2(const Params p) {
         {   // masked-out entries of an observation are all-zero: clear, then write only what is visible
             float4* z = reinterpret_cast<float4*>(stage);
             const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll 4
-            for (int k = lane; k < S::STAGE_FLOATS / 4; k += 32) z[k] = zero;
+#pragma unroll
+            for (int k = 0; k < (NZ + 31) / 32; ++k)
+                if (k * 32 + 32 <= NZ || k * 32 + lane < NZ) z[k * 32 + lane] = zero;
         }
         __syncwarp();
 #pragma unroll
@@ -825,57 +903,52 @@ mate_step_kernel2(const Params p) {
             int off_c = 0, off_t = 0, word = 0;
             uint32_t bit = 0;
             if (live) {
-                if (kind == 0) {          // Target.state public part (entities.py:631-637) + flag
-                    const uint32_t tpk = __float_as_uint(v[S::V_T + 3 * idx + 2]);
-                    a0 = v[S::V_T + 3 * idx]; a1 = v[S::V_T + 3 * idx + 1]; a2 = f_sr;
-                    a3 = (tp_goal(tpk) >= 0 && tp_weight(tpk) > 0) ? 1.f : 0.f; a4 = 1.f;
-                    off_c = C_TGT + 5 * idx; off_t = T_TGT + 5 * idx; bit = bit_tgt(idx);
-                } else if (kind == 1) {   // Obstacle.state (entities.py:147-148) + flag
+                if (kind == 1) {          // Obstacle.state (entities.py:147-148) + flag
                     const float4 ob = p.obs_f4[(size_t)idx * bp + env];
                     a0 = ob.x; a1 = ob.y; a2 = ob.z; a3 = 1.f;
                     off_c = C_OBS + 4 * idx; off_t = T_OBS + 4 * idx;
                     bit = MW == 1 ? (1u << (16 + idx)) : (1u << (idx & 31)); word = MW - 1;
-                } else {                  // Camera.state public part (entities.py:313-324) + flag
-                    const float* cv = v + S::V_C + 5 * idx;
-                    a0 = cv[0]; a1 = cv[1]; a2 = f_crad; a3 = cv[2]; a4 = cv[3]; a5 = cv[4];
-                    off_c = C_CAM + 7 * idx; off_t = T_CAM + 7 * idx; bit = bit_cam(idx);
+                } else {
+                    // own row: preserved block (environment.py:921-934)
+                    const int row = kind == 0 ? NC + idx : idx;
+                    float* q = stage + (kind == 0 ? S::STAGE_CAM + idx * DT : idx * DC);
+                    q[0] = (float)NC; q[1] = (float)NT; q[2] = (float)NO; q[3] = (float)idx;
+                    q[4] = 925.f; q[5] = 925.f; q[6] = -925.f; q[7] = 925.f; q[8] = -925.f; q[9] = -925.f; q[10] = 925.f; q[11] = -925.f;
+                    q[12] = 75.f;
+                    (void)row;
+                    if (kind == 0) {      // Target.state (entities.py:631-637): public part + flag, private part
+                        const uint32_t tpk = __float_as_uint(v[S::V_T + 3 * idx + 2]);
+                        const int goal = tp_goal(tpk), weight = tp_weight(tpk), capacity = tp_capacity(tpk), empty = tp_empty(tpk);
+                        a0 = v[S::V_T + 3 * idx]; a1 = v[S::V_T + 3 * idx + 1]; a2 = f_sr;
+                        a3 = (goal >= 0 && weight > 0) ? 1.f : 0.f; a4 = 1.f;
+                        off_c = C_TGT + 5 * idx; off_t = T_TGT + 5 * idx; bit = bit_tgt(idx);
+                        q += T_SELF;
+                        q[0] = a0; q[1] = a1; q[2] = a2; q[3] = a3;
+                        q[4] = capacity == 1 ? f_step1 : (capacity == 2 ? f_step2 : (float)(p.tgt_step_size / (double)capacity));
+                        q[5] = (float)capacity;
+#pragma unroll
+                        for (int w = 0; w < NW; ++w) { q[6 + w] = (goal == w) ? (float)weight : 0.f; q[10 + w] = (float)((empty >> w) & 1); }
+                    } else {              // Camera.state (entities.py:313-324): public part + flag, private part
+                        const float* cv = v + S::V_C + CV * idx;
+                        a0 = cv[0]; a1 = cv[1]; a2 = f_crad; a3 = cv[3] * cv[4]; a4 = cv[3] * cv[5]; a5 = cv[2];
+                        off_c = C_CAM + 7 * idx; off_t = T_CAM + 7 * idx; bit = bit_cam(idx);
+                        q += C_SELF;
+                        q[0] = a0; q[1] = a1; q[2] = a2; q[3] = a3; q[4] = a4; q[5] = a5;
+                        q[6] = f_rmax; q[7] = f_rot; q[8] = f_zoom;
+                    }
                 }
             }
+            const bool five = live && kind != 1, seven = live && kind == 2;
+            if (kind == 2) a4 = a4;   // (cameras: a4 = Rs sin, a5 = theta, flag in slot 6)
+            const float s4 = kind == 2 ? a4 : 1.f;   // slot 4: target flag or camera Rs sin
 #pragma unroll
             for (int r = 0; r < R; ++r) {
                 const uint32_t w = m[r * MW + word];
-                if (live && (w & bit)) {
-                    float* q = stage + (r < NC ? r * DC + off_c : S::STAGE_CAM + (r - NC) * DT + off_t);
-                    q[0] = a0; q[1] = a1; q[2] = a2; q[3] = a3;
-                    if (kind != 1) q[4] = a4;
-                    if (kind == 2) { q[5] = a5; q[6] = 1.f; }
-                }
-            }
-        }
-        // own rows: preserved data (lanes 0..R-1) and the observer's own state (lanes 16..16+R-1)
-        if (lane < R) {
-            const int r = lane;
-            float* q = stage + (r < NC ? r * DC : S::STAGE_CAM + (r - NC) * DT);
-            q[0] = (float)NC; q[1] = (float)NT; q[2] = (float)NO; q[3] = (float)(r < NC ? r : r - NC);
-            q[4] = 925.f; q[5] = 925.f; q[6] = -925.f; q[7] = 925.f; q[8] = -925.f; q[9] = -925.f; q[10] = 925.f; q[11] = -925.f;
-            q[12] = 75.f;
-        } else if (lane >= 16 && lane < 16 + R) {
-            const int r = lane - 16;
-            if (r < NC) {
-                const float* cv = v + S::V_C + 5 * r;
-                float* q = stage + r * DC + C_SELF;
-                q[0] = cv[0]; q[1] = cv[1]; q[2] = f_crad; q[3] = cv[2]; q[4] = cv[3]; q[5] = cv[4];
-                q[6] = (float)p.cam_rmax; q[7] = (float)p.cam_rot_step; q[8] = (float)p.cam_zoom_step;
-            } else {
-                const int t = r - NC;
-                const uint32_t tpk = __float_as_uint(v[S::V_T + 3 * t + 2]);
-                const int goal = tp_goal(tpk), weight = tp_weight(tpk), capacity = tp_capacity(tpk), empty = tp_empty(tpk);
-                float* q = stage + S::STAGE_CAM + t * DT + T_SELF;
-                q[0] = v[S::V_T + 3 * t]; q[1] = v[S::V_T + 3 * t + 1]; q[2] = f_sr;
-                q[3] = (goal >= 0 && weight > 0) ? 1.f : 0.f;
-                q[4] = (float)(p.tgt_step_size / (double)capacity); q[5] = (float)capacity;
-#pragma unroll
-                for (int w = 0; w < NW; ++w) { q[6 + w] = (goal == w) ? (float)weight : 0.f; q[10 + w] = (float)((empty >> w) & 1); }
+                const bool hit = live && (w & bit);
+                float* q = stage + (r < NC ? r * DC + off_c : S::STAGE_CAM + (r - NC) * DT + off_t);
+                if (hit) { q[0] = a0; q[1] = a1; q[2] = a2; q[3] = a3; }
+                if (hit && five) q[4] = s4;
+                if (hit && seven) { q[5] = a5; q[6] = 1.f; }
             }
         }
         // ---- staged rows -> HBM: one bulk (TMA) copy per tensor, issued by one lane
