@@ -179,9 +179,10 @@ __device__ __noinline__ StepVec obstruct_exact(StepVec s, double ox, double oy, 
             const double hc = sqrt(R * R - perp * perp);
             const double nn = fmax(0.0, reln * c - hc);
             if (nn < norm) {
-                if (!s.has_ang) { s.ang = atan2_deg(s.vy, s.vx); s.has_ang = true; }
-                double sn, cs;
-                sincos_deg(s.ang, &sn, &cs);
+                // unit vector of the step: the reference goes through (cos, sin) of atan2(v); v / |v| is the
+                // same direction to 1 ulp (same class of deviation as the step-size clamp)
+                const double inv = 1.0 / norm;
+                const double cs = s.vx * inv, sn = s.vy * inv;
                 const double radx = (ox + nn * cs) - px, rady = (oy + nn * sn) - py;
                 const double k = (norm - nn) * hc / (R * R);
                 s.vx = s.vx + radx * k; s.vy = s.vy + rady * k;
@@ -252,6 +253,9 @@ __device__ __noinline__ double sight_range_at(const ObsRef ob, double cx, double
     RaySample P{fl, rmax, -1}, S{fl + 1.0, rmax, -1};
     const double c1 = 0.99984154; // cos(1.02 deg)
     const double s1 = 0.01780139; // sin(1.02 deg)
+    // phase 1: which obstacles of the camera's set can have a sample angle inside (floor(a), floor(a) + 1)?
+    unsigned long long passing = 0ull;
+    bool inside = false;
 #pragma unroll 1
     for (int o = 0; o < NO; ++o) {
         const double relx = ob.x[o * ob.stride] - cx, rely = ob.y[o * ob.stride] - cy, R = ob.r[o * ob.stride];
@@ -260,13 +264,22 @@ __device__ __noinline__ double sight_range_at(const ObsRef ob, double cx, double
             const double reach = rmax + R, reach2 = reach * reach;
             if (d2 > reach2 * (1.0 + 1e-12)) continue;
             if (d2 > reach2 * (1.0 - 1e-12) && !dist_cmp_exact(d2, reach, true)) continue;
-            if (d2 < R * R * (1.0 + 1e-12) && dist_cmp_exact(d2, R, true)) return 0.0;
+            if (d2 < R * R * (1.0 + 1e-12) && dist_cmp_exact(d2, R, true)) { inside = true; continue; }
         }
-        // prefilter: can any sample angle of this obstacle fall inside (floor(a), floor(a)+1)?
         // angular distance bearing<->centre must be <= half + 1.02 deg
         const double p = relx * ux + rely * uy + R * s1 * 1.0000001;
         if (p < 0.0) continue;
         if (p * p < (d2 - R * R) * (c1 * c1) * 0.9999999) continue;
+        passing |= 1ull << o;
+    }
+    if (inside) return 0.0;
+    // phase 2: the sample angles of those obstacles, one obstacle per iteration (lanes of a warp that
+    // evaluate different obstacles stay converged)
+    while (passing != 0ull) {
+        const int o = __ffsll((long long)passing) - 1;
+        passing &= passing - 1ull;
+        const double relx = ob.x[o * ob.stride] - cx, rely = ob.y[o * ob.stride] - cy, R = ob.r[o * ob.stride];
+        const double d2 = relx * relx + rely * rely;
         const double d = sqrt(d2);
         const double ang_o = atan2_deg(rely, relx);
         const double half = asin(R / d) * kRad2Deg;
@@ -361,9 +374,11 @@ __device__ __forceinline__ int occlusion_fast(const float4* __restrict__ Fobs, s
     const float tan_fan = 0.018332f;                           // tan(1.05 deg)
     const float d_hi = dist * (1.0f + 1e-4f) + 0.05f, d_lo = dist * (1.0f - 1e-4f) - 0.05f;
     bool all_clear = true;
+    float4 nxt = Fobs[0];
 #pragma unroll 1
     for (int o = 0; o < NO; ++o) {
-        const float4 ob = Fobs[o * fstride];
+        const float4 ob = nxt;
+        if (o + 1 < NO) nxt = Fobs[(o + 1) * fstride];        // fetched while this disc is classified
         const float ox = ob.x - cx, oy = ob.y - cy, R = ob.z;
         const float do2 = ox * ox + oy * oy;
         const float reach = rmax + R + 0.05f;

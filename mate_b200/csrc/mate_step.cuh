@@ -36,7 +36,7 @@
 #define MATE2_WARPS 2          // warps per CTA (warps are independent; this only sets the CTA granularity)
 #endif
 #ifndef MATE2_MIN_CTAS
-#define MATE2_MIN_CTAS 7       // 14 warps/SM: 65 536 envs = 2048 warp tiles = 13.8 per SM -> one balanced wave
+#define MATE2_MIN_CTAS 8       // caps registers at 128 (4 warps per SM sub-partition); 65 536 envs = 2048 warp tiles = 13.8 per SM -> one wave
 #endif
 
 namespace mate {
@@ -64,7 +64,7 @@ struct Shape2 {
     static constexpr int ENVS_PER_CTA = WARPS * 32;
     static constexpr int QCAP = 64;
     static constexpr int OFF_STAGE = 0;
-    static constexpr int OFF_MASK = OFF_STAGE + STAGE_FLOATS * 4;
+    static constexpr int OFF_MASK = OFF_STAGE + (STAGE_FLOATS + 8) * 4;   // + a dummy slot for inactive lanes
     static constexpr int OFF_VAL = OFF_MASK + 32 * MSTRIDE * 4;
     static constexpr int OFF_Q = OFF_VAL + 32 * VSTRIDE * 4;
     static constexpr int OFF_Q2 = OFF_Q + QCAP * 2;             // second queue: pairs that need the exact polyline
@@ -108,8 +108,10 @@ __device__ __forceinline__ int fov_reach32(float cx, float cy, float rs2, float 
 
 // Target.simulate (entities.py:645-668) in fp64 against all discs (obstacles, then camera barriers),
 // for the targets whose step may touch a disc.  Returns the new location and the colliding flag.
-template <int NC, int NT, int NO>
-__device__ __noinline__ void target_step_exact(const Params& p, int er, int t, uint32_t tpack, double* out_x, double* out_y, int* colliding) {
+// `camv` = the fp32 camera entries of this environment in shared memory.
+template <int NC, int NT, int NO, class S>
+__device__ __noinline__ void target_step_exact(const Params& p, int er, int t, uint32_t tpack, const float* camv,
+                                               double* out_x, double* out_y, int* colliding) {
     const size_t bp = p.bpad;
     const double tx = p.tgt_x[(size_t)t * bp + er], ty = p.tgt_y[(size_t)t * bp + er];
     const float2 a = reinterpret_cast<const float2*>(p.tgt_act)[(size_t)er * NT + t];
@@ -125,12 +127,33 @@ __device__ __noinline__ void target_step_exact(const Params& p, int er, int t, u
         s.bound = s.n * (1.0 + 1e-12);
     }
     const double desx = tx + s.vx, desy = ty + s.vy;
+    // fp32 candidates: discs within bound + R of the origin (one batch of loads); as long as the step is
+    // unmodified every other disc fails Obstacle.obstruct's `relative.norm >= norm + radius` test anyway
+    unsigned long long cand = 0ull;
+    {
+        const float ftx = (float)tx, fty = (float)ty, fb = (float)s.bound * 1.00001f + 0.01f;
+#pragma unroll
+        for (int o = 0; o < NO; ++o) {
+            const float4 ob = p.obs_f4[(size_t)o * bp + er];
+            const float dx = ob.x - ftx, dy = ob.y - fty, reach = fb + ob.z;
+            cand |= (unsigned long long)(!(dx * dx + dy * dy > reach * reach)) << o;
+        }
+        const float reach_c = fb + (float)p.cam_radius;
+#pragma unroll
+        for (int c = 0; c < NC; ++c) {
+            const float dx = camv[S::CV * c] - ftx, dy = camv[S::CV * c + 1] - fty;
+            cand |= (unsigned long long)(!(dx * dx + dy * dy > reach_c * reach_c)) << (NO + c);
+        }
+    }
+    bool modified = false;
 #pragma unroll 1
-    for (int o = 0; o < NO; ++o)
-        obstruct_step(s, tx, ty, p.obs_x[(size_t)o * bp + er], p.obs_y[(size_t)o * bp + er], p.obs_r[(size_t)o * bp + er]);
-#pragma unroll 1
-    for (int c = 0; c < NC; ++c)
-        obstruct_step(s, tx, ty, p.cam_x[(size_t)c * bp + er], p.cam_y[(size_t)c * bp + er], p.cam_radius);
+    for (int d = 0; d < NO + NC; ++d) {
+        if (!modified && !((cand >> d) & 1ull)) continue;
+        const double ovx = s.vx, ovy = s.vy;
+        if (d < NO) obstruct_step(s, tx, ty, p.obs_x[(size_t)d * bp + er], p.obs_y[(size_t)d * bp + er], p.obs_r[(size_t)d * bp + er]);
+        else obstruct_step(s, tx, ty, p.cam_x[(size_t)(d - NO) * bp + er], p.cam_y[(size_t)(d - NO) * bp + er], p.cam_radius);
+        modified = modified || s.vx != ovx || s.vy != ovy;
+    }
     const double nx = fmin(fmax(tx + s.vx, -kTerrain), kTerrain);
     const double ny = fmin(fmax(ty + s.vy, -kTerrain), kTerrain);
     *colliding = !(fabs(nx - desx) <= 1e-6 && fabs(ny - desy) <= 1e-6);
@@ -286,8 +309,12 @@ __device__ __noinline__ void process_exact(const Params& p, int env0, uint32_t* 
     const size_t bp = p.bpad;
     const double cx = p.cam_x[(size_t)c * bp + envr], cy = p.cam_y[(size_t)c * bp + envr];
     const double relx = p.tgt_x[(size_t)t * bp + envr] - cx, rely = p.tgt_y[(size_t)t * bp + envr] - cy;
-    const bool sees = occlusion_exact<NO>(ObsRef{p.obs_x + envr, p.obs_y + envr, p.obs_r + envr, bp}, cx, cy, relx, rely,
-                                          sqrt(relx * relx + rely * rely), p.cam_rmax);
+    double E[3 * (NO > 0 ? NO : 1)];   // the discs are read several times: one batch of loads into local memory
+#pragma unroll
+    for (int o = 0; o < NO; ++o) {
+        E[3 * o] = p.obs_x[(size_t)o * bp + envr]; E[3 * o + 1] = p.obs_y[(size_t)o * bp + envr]; E[3 * o + 2] = p.obs_r[(size_t)o * bp + envr];
+    }
+    const bool sees = occlusion_exact<NO>(ObsRef{E, E + 1, E + 2, 3}, cx, cy, relx, rely, sqrt(relx * relx + rely * rely), p.cam_rmax);
     if (sees) atomicOr(&mk[src * S::MSTRIDE + c * S::MW], bit_tgt(t));
 }
 
@@ -335,20 +362,32 @@ mate_step_kernel2(const Params p) {
     bool cargo_loaded = false, cargo_dirty = false;
 
     // ------------------------------------------------------------------ _simulate (environment.py:1326-1354)
-#pragma unroll 1
-    for (int c = 0; c < NC; ++c) {   // Camera.simulate (entities.py:347-360)
-        const size_t i = (size_t)c * bp + er;
-        const double x = p.cam_x[i], y = p.cam_y[i];
-        double phi = p.cam_phi[i], theta = p.cam_theta[i];
-        if (mode == MODE_STEP) {
-            const float2 a = reinterpret_cast<const float2*>(p.cam_act)[(size_t)er * NC + c];
-            const double da = fmin(fmax((double)a.x, -p.cam_rot_step), p.cam_rot_step);
-            const double dv = fmin(fmax((double)a.y, -p.cam_zoom_step), p.cam_zoom_step);
-            phi = normalize_angle(phi + da);
-            theta = fmin(fmax(theta + dv, p.cam_min_view), 180.0);
-            if (env_ok) { p.cam_phi[(size_t)c * bp + e] = phi; p.cam_theta[(size_t)c * bp + e] = theta; }
+    {   // Camera.simulate (entities.py:347-360); the next camera's state is fetched while this one is derived
+        double nx_ = 0, ny_ = 0, nphi_ = 0, nth_ = 0;
+        float2 na_ = make_float2(0.f, 0.f);
+        if (NC > 0) {
+            nx_ = p.cam_x[er]; ny_ = p.cam_y[er]; nphi_ = p.cam_phi[er]; nth_ = p.cam_theta[er];
+            if (mode == MODE_STEP) na_ = reinterpret_cast<const float2*>(p.cam_act)[(size_t)er * NC];
         }
-        store_camera(mycam + CV * c, x, y, phi, theta, p.cam_area_product);
+#pragma unroll 1
+        for (int c = 0; c < NC; ++c) {
+            const double x = nx_, y = ny_;
+            double phi = nphi_, theta = nth_;
+            const float2 a = na_;
+            if (c + 1 < NC) {
+                const size_t i = (size_t)(c + 1) * bp + er;
+                nx_ = p.cam_x[i]; ny_ = p.cam_y[i]; nphi_ = p.cam_phi[i]; nth_ = p.cam_theta[i];
+                if (mode == MODE_STEP) na_ = reinterpret_cast<const float2*>(p.cam_act)[(size_t)er * NC + c + 1];
+            }
+            if (mode == MODE_STEP) {
+                const double da = fmin(fmax((double)a.x, -p.cam_rot_step), p.cam_rot_step);
+                const double dv = fmin(fmax((double)a.y, -p.cam_zoom_step), p.cam_zoom_step);
+                phi = normalize_angle(phi + da);
+                theta = fmin(fmax(theta + dv, p.cam_min_view), 180.0);
+                if (env_ok) { p.cam_phi[(size_t)c * bp + e] = phi; p.cam_theta[(size_t)c * bp + e] = theta; }
+            }
+            store_camera(mycam + CV * c, x, y, phi, theta, p.cam_area_product);
+        }
     }
     {   // Target.simulate (entities.py:645-668): fast path = no disc within reach of the step
         uint32_t slow = 0;     // targets that may touch a disc: re-simulated exactly below
@@ -359,9 +398,12 @@ mate_step_kernel2(const Params p) {
 #pragma unroll
             for (int t = 0; t < NT; ++t) { otx[t] = (float)p.tgt_x[(size_t)t * bp + er]; oty[t] = (float)p.tgt_y[(size_t)t * bp + er]; }
             const float fb = (float)p.tgt_step_size * 1.00001f + 0.01f;
+            float4 ob_n = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (NO > 0) ob_n = p.obs_f4[er];
 #pragma unroll 1
             for (int o = 0; o < NO; ++o) {
-                const float4 ob = p.obs_f4[(size_t)o * bp + er];
+                const float4 ob = ob_n;
+                if (o + 1 < NO) ob_n = p.obs_f4[(size_t)(o + 1) * bp + er];
                 const float reach = fb + ob.z, reach2 = reach * reach;
 #pragma unroll
                 for (int t = 0; t < NT; ++t) {
@@ -380,15 +422,23 @@ mate_step_kernel2(const Params p) {
                 }
             }
         }
+        double ntx_ = p.tgt_x[er], nty_ = p.tgt_y[er];
+        uint32_t npk_ = p.tgt_pack[er];
+        float2 nta_ = make_float2(0.f, 0.f);
+        if (mode == MODE_STEP) nta_ = reinterpret_cast<const float2*>(p.tgt_act)[(size_t)er * NT];
 #pragma unroll 1
-        for (int t = 0; t < NT; ++t) {
-            const size_t i = (size_t)t * bp + er;
-            double tx = p.tgt_x[i], ty = p.tgt_y[i];
-            uint32_t tpack = p.tgt_pack[i];
+        for (int t = 0; t < NT; ++t) {   // the next target's state is fetched while this one is stepped
+            double tx = ntx_, ty = nty_;
+            uint32_t tpack = npk_;
+            const float2 a = nta_;
+            if (t + 1 < NT) {
+                const size_t i = (size_t)(t + 1) * bp + er;
+                ntx_ = p.tgt_x[i]; nty_ = p.tgt_y[i]; npk_ = p.tgt_pack[i];
+                if (mode == MODE_STEP) nta_ = reinterpret_cast<const float2*>(p.tgt_act)[(size_t)er * NT + t + 1];
+            }
             if (mode == MODE_STEP && !((slow >> t) & 1)) {
-                const float2 a = reinterpret_cast<const float2*>(p.tgt_act)[(size_t)er * NT + t];
-                const int cap = tp_capacity(tpack);
-                const double step_size = cap == 1 ? p.tgt_step_size : p.tgt_step_size / (double)cap;
+                const int cap = tp_capacity(tpack);   // 1 or 2
+                const double step_size = cap == 1 ? p.tgt_step_size : p.tgt_step_size * 0.5;
                 double vx = (double)a.x, vy = (double)a.y;
                 const double n2 = vx * vx + vy * vy;
                 if (n2 > step_size * step_size * (1.0 - 1e-12)) {
@@ -416,7 +466,7 @@ mate_step_kernel2(const Params p) {
                 slow &= slow - 1;
                 uint32_t tpack = __float_as_uint(myval[S::V_T + 3 * t + 2]);
                 double nx, ny; int colliding;
-                target_step_exact<NC, NT, NO>(p, er, t, tpack, &nx, &ny, &colliding);
+                target_step_exact<NC, NT, NO, S>(p, er, t, tpack, mycam, &nx, &ny, &colliding);
                 tpack = (tpack & ~(1u << 27)) | ((uint32_t)colliding << 27);
                 if (env_ok) { p.tgt_x[(size_t)t * bp + e] = nx; p.tgt_y[(size_t)t * bp + e] = ny; }
                 myval[S::V_T + 3 * t + 0] = (float)nx; myval[S::V_T + 3 * t + 1] = (float)ny;
@@ -509,9 +559,12 @@ mate_step_kernel2(const Params p) {
                     if (band_c) trow[t] |= resolve_band(p, er, ax, ay, band_c, 1, src, false);   // bit_cam(c) == 1 << c
                 }
             }
+            float4 ob_n = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (NO > 0) ob_n = p.obs_f4[er];
 #pragma unroll 1
             for (int o = 0; o < NO; ++o) {
-                const float4 ob = p.obs_f4[(size_t)o * bp + er];
+                const float4 ob = ob_n;
+                if (o + 1 < NO) ob_n = p.obs_f4[(size_t)(o + 1) * bp + er];
                 const uint32_t obit = MW == 1 ? (1u << (16 + o)) : (1u << (o & 31));
                 const float rtf = fsr + ob.z, rt2 = rtf * rtf;
                 const float rcf = (float)p.cam_rmax + ob.z, rc2 = rcf * rcf;
@@ -864,92 +917,128 @@ mate_step_kernel2(const Params p) {
     __syncwarp();
 
     // ------------------------------------------------------------------ joint_observation (environment.py:908-983)
-    // The warp walks over its environments.  Lanes are the ENTITIES of the environment (targets,
-    // then obstacles, then cameras; a second pass if there are more than 32): each lane scatters its
-    // entity's public state into the rows of the observers whose mask bit is set; target and camera
-    // lanes also write their own row's preserved block and private state.
+    // The warp walks over its environments and assembles the 6 KB block of observation rows of one
+    // environment in shared memory, every float written exactly once and without branches:
+    //   * (observer row, entity) PAIRS are spread over the lanes, one entity kind at a time (a lane keeps
+    //     the same entity for all rounds of a kind); a pair writes the entity's public state and flag if
+    //     the observer's mask bit is set and zeros otherwise (masked-out entries are all-zero);
+    //   * lanes 0..R-1 write the preserved block and the private state of "their" observer row.
     constexpr int C_SELF = 13, C_TGT = 22, C_OBS = 22 + 5 * NT, C_CAM = 22 + 5 * NT + 4 * NO;
     constexpr int T_SELF = 13, T_CAM = 27, T_OBS = 27 + 7 * NC, T_TGT = 27 + 7 * NC + 4 * NO;
-    constexpr int EPASS = (S::E + 31) / 32;
-    constexpr int NZ = S::STAGE_FLOATS / 4;
+    constexpr int NOX = NO > 0 ? NO : 1;
+    constexpr int RPR_T = 32 / NT, RPR_O = 32 / NOX, RPR_C = 32 / NCX;          // observer rows per round
+    constexpr int RND_T = (R + RPR_T - 1) / RPR_T, RND_O = (R + RPR_O - 1) / RPR_O, RND_C = (R + RPR_C - 1) / RPR_C;
     const float f_sr = (float)p.tgt_sight_range, f_crad = (float)p.cam_radius;
     const float f_rmax = (float)p.cam_rmax, f_rot = (float)p.cam_rot_step, f_zoom = (float)p.cam_zoom_step;
     const float f_step1 = (float)p.tgt_step_size, f_step2 = (float)(p.tgt_step_size / 2.0);
+    // per-lane constants of the scatter, hoisted out of the environment loop: for every round the offset
+    // of this lane's slot in the staged block (inactive lanes write to a dummy slot behind the block, so
+    // the code is branch-free) and the mask word + bit that decide it
+    constexpr int DUMMY = S::STAGE_FLOATS;
+    constexpr int NRND = RND_T + (NO > 0 ? RND_O : 0) + (NC > 0 ? RND_C : 0);
+    const int t_idx = lane % NT, t_sub = lane / NT;
+    const int o_idx = lane % NOX, o_sub = lane / NOX;
+    const int c_idx = lane % NCX, c_sub = lane / NCX;
+    auto row_base = [&](const int row) { return row < NC ? row * DC : S::STAGE_CAM + (row - NC) * DT; };
+    int q_off[NRND], m_idx[NRND];
+#pragma unroll
+    for (int rd = 0; rd < RND_T; ++rd) {
+        const int row = rd * RPR_T + t_sub;
+        const bool on = t_sub < RPR_T && row < R;
+        q_off[rd] = on ? row_base(row) + (row < NC ? C_TGT : T_TGT) + 5 * t_idx : DUMMY;
+        m_idx[rd] = on ? row * MW : 0;
+    }
+    if (NO > 0) {
+#pragma unroll
+        for (int rd = 0; rd < RND_O; ++rd) {
+            const int row = rd * RPR_O + o_sub;
+            const bool on = o_sub < RPR_O && row < R;
+            q_off[RND_T + rd] = on ? row_base(row) + (row < NC ? C_OBS : T_OBS) + 4 * o_idx : DUMMY;
+            m_idx[RND_T + rd] = on ? row * MW + (MW - 1) : 0;
+        }
+    }
+    if (NC > 0) {
+#pragma unroll
+        for (int rd = 0; rd < RND_C; ++rd) {
+            const int row = rd * RPR_C + c_sub;
+            const bool on = c_sub < RPR_C && row < R;
+            q_off[NRND - RND_C + rd] = on ? row_base(row) + (row < NC ? C_CAM : T_CAM) + 7 * c_idx : DUMMY;
+            m_idx[NRND - RND_C + rd] = on ? row * MW : 0;
+        }
+    }
+    const uint32_t t_bit = bit_tgt(t_idx), o_bit = MW == 1 ? (1u << (16 + o_idx)) : (1u << o_idx), c_bit = bit_cam(c_idx);
+    // the own-row entries that never change are staged once: preserved block (environment.py:921-934)
+    // and the constant entries of the private state
+    if (lane < R) {
+        const int row = lane;
+        float* q = stage + row_base(row);
+        q[0] = (float)NC; q[1] = (float)NT; q[2] = (float)NO; q[3] = (float)(row < NC ? row : row - NC);
+        q[4] = 925.f; q[5] = 925.f; q[6] = -925.f; q[7] = 925.f; q[8] = -925.f; q[9] = -925.f; q[10] = 925.f; q[11] = -925.f;
+        q[12] = 75.f;
+        if (row < NC) { q[C_SELF + 2] = f_crad; q[C_SELF + 6] = f_rmax; q[C_SELF + 7] = f_rot; q[C_SELF + 8] = f_zoom; }
+        else q[T_SELF + 2] = f_sr;
+    }
+    float* const self_t = stage + S::STAGE_CAM + t_idx * DT + T_SELF;   // used by lanes 0..NT-1
+    float* const self_c = stage + c_idx * DC + C_SELF;                   // used by lanes 0..NC-1
+    float4 ob_next = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (NO > 0) ob_next = p.obs_f4[(size_t)o_idx * bp + env0];
+    __syncwarp();
 #pragma unroll 1
     for (int i = 0; i < nvalid; ++i) {
         const float* v = val + i * S::VSTRIDE;
         const uint32_t* m = mk + i * S::MSTRIDE;
         const int env = env0 + i;
-        if (i > 0) {
+        const float4 ob = ob_next;
+        if (NO > 0 && i + 1 < nvalid) ob_next = p.obs_f4[(size_t)o_idx * bp + env + 1];   // fetched one environment ahead
+        // Target.state public part (entities.py:631-637), Camera.state public part (entities.py:313-324)
+        const uint32_t tpk = __float_as_uint(v[S::V_T + 3 * t_idx + 2]);
+        const float t0 = v[S::V_T + 3 * t_idx], t1 = v[S::V_T + 3 * t_idx + 1];
+        const int goal = tp_goal(tpk), weight = tp_weight(tpk);
+        const float t3 = (goal >= 0 && weight > 0) ? 1.f : 0.f;
+        float c0 = 0.f, c1 = 0.f, c3 = 0.f, c4 = 0.f, c5 = 0.f;
+        if (NC > 0) {
+            const float* cv = v + S::V_C + CV * c_idx;
+            c0 = cv[0]; c1 = cv[1]; c3 = cv[3] * cv[4]; c4 = cv[3] * cv[5]; c5 = cv[2];
+        }
+        if (i > 0) {   // the previous environment's bulk copy must have read the staged block
             if (S::BULK) { if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
             __syncwarp();
         }
-        {   // masked-out entries of an observation are all-zero: clear, then write only what is visible
-            float4* z = reinterpret_cast<float4*>(stage);
-            const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-            for (int k = 0; k < (NZ + 31) / 32; ++k)
-                if (k * 32 + 32 <= NZ || k * 32 + lane < NZ) z[k * 32 + lane] = zero;
+        for (int rd = 0; rd < RND_T; ++rd) {   // targets + flag
+            const bool hit = (m[m_idx[rd]] & t_bit) != 0u;
+            float* q = stage + q_off[rd];
+            q[0] = hit ? t0 : 0.f; q[1] = hit ? t1 : 0.f; q[2] = hit ? f_sr : 0.f; q[3] = hit ? t3 : 0.f; q[4] = hit ? 1.f : 0.f;
         }
-        __syncwarp();
+        if (NO > 0) {
 #pragma unroll
-        for (int ep = 0; ep < EPASS; ++ep) {
-            const int slot = ep * 32 + lane;
-            // entity of this lane: kind 0 = target, 1 = obstacle, 2 = camera
-            const int kind = slot < NT ? 0 : (slot < NT + NO ? 1 : 2);
-            const int idx = slot < NT ? slot : (slot < NT + NO ? slot - NT : slot - NT - NO);
-            const bool live = slot < S::E;
-            float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f, a4 = 0.f, a5 = 0.f;
-            int off_c = 0, off_t = 0, word = 0;
-            uint32_t bit = 0;
-            if (live) {
-                if (kind == 1) {          // Obstacle.state (entities.py:147-148) + flag
-                    const float4 ob = p.obs_f4[(size_t)idx * bp + env];
-                    a0 = ob.x; a1 = ob.y; a2 = ob.z; a3 = 1.f;
-                    off_c = C_OBS + 4 * idx; off_t = T_OBS + 4 * idx;
-                    bit = MW == 1 ? (1u << (16 + idx)) : (1u << (idx & 31)); word = MW - 1;
-                } else {
-                    // own row: preserved block (environment.py:921-934)
-                    const int row = kind == 0 ? NC + idx : idx;
-                    float* q = stage + (kind == 0 ? S::STAGE_CAM + idx * DT : idx * DC);
-                    q[0] = (float)NC; q[1] = (float)NT; q[2] = (float)NO; q[3] = (float)idx;
-                    q[4] = 925.f; q[5] = 925.f; q[6] = -925.f; q[7] = 925.f; q[8] = -925.f; q[9] = -925.f; q[10] = 925.f; q[11] = -925.f;
-                    q[12] = 75.f;
-                    (void)row;
-                    if (kind == 0) {      // Target.state (entities.py:631-637): public part + flag, private part
-                        const uint32_t tpk = __float_as_uint(v[S::V_T + 3 * idx + 2]);
-                        const int goal = tp_goal(tpk), weight = tp_weight(tpk), capacity = tp_capacity(tpk), empty = tp_empty(tpk);
-                        a0 = v[S::V_T + 3 * idx]; a1 = v[S::V_T + 3 * idx + 1]; a2 = f_sr;
-                        a3 = (goal >= 0 && weight > 0) ? 1.f : 0.f; a4 = 1.f;
-                        off_c = C_TGT + 5 * idx; off_t = T_TGT + 5 * idx; bit = bit_tgt(idx);
-                        q += T_SELF;
-                        q[0] = a0; q[1] = a1; q[2] = a2; q[3] = a3;
-                        q[4] = capacity == 1 ? f_step1 : (capacity == 2 ? f_step2 : (float)(p.tgt_step_size / (double)capacity));
-                        q[5] = (float)capacity;
-#pragma unroll
-                        for (int w = 0; w < NW; ++w) { q[6 + w] = (goal == w) ? (float)weight : 0.f; q[10 + w] = (float)((empty >> w) & 1); }
-                    } else {              // Camera.state (entities.py:313-324): public part + flag, private part
-                        const float* cv = v + S::V_C + CV * idx;
-                        a0 = cv[0]; a1 = cv[1]; a2 = f_crad; a3 = cv[3] * cv[4]; a4 = cv[3] * cv[5]; a5 = cv[2];
-                        off_c = C_CAM + 7 * idx; off_t = T_CAM + 7 * idx; bit = bit_cam(idx);
-                        q += C_SELF;
-                        q[0] = a0; q[1] = a1; q[2] = a2; q[3] = a3; q[4] = a4; q[5] = a5;
-                        q[6] = f_rmax; q[7] = f_rot; q[8] = f_zoom;
-                    }
-                }
+            for (int rd = 0; rd < RND_O; ++rd) {   // obstacles: Obstacle.state (entities.py:147-148) + flag
+                const bool hit = (m[m_idx[RND_T + rd]] & o_bit) != 0u;
+                float* q = stage + q_off[RND_T + rd];
+                q[0] = hit ? ob.x : 0.f; q[1] = hit ? ob.y : 0.f; q[2] = hit ? ob.z : 0.f; q[3] = hit ? 1.f : 0.f;
             }
-            const bool five = live && kind != 1, seven = live && kind == 2;
-            if (kind == 2) a4 = a4;   // (cameras: a4 = Rs sin, a5 = theta, flag in slot 6)
-            const float s4 = kind == 2 ? a4 : 1.f;   // slot 4: target flag or camera Rs sin
+        }
+        if (NC > 0) {
 #pragma unroll
-            for (int r = 0; r < R; ++r) {
-                const uint32_t w = m[r * MW + word];
-                const bool hit = live && (w & bit);
-                float* q = stage + (r < NC ? r * DC + off_c : S::STAGE_CAM + (r - NC) * DT + off_t);
-                if (hit) { q[0] = a0; q[1] = a1; q[2] = a2; q[3] = a3; }
-                if (hit && five) q[4] = s4;
-                if (hit && seven) { q[5] = a5; q[6] = 1.f; }
+            for (int rd = 0; rd < RND_C; ++rd) {   // cameras + flag
+                const bool hit = (m[m_idx[NRND - RND_C + rd]] & c_bit) != 0u;
+                float* q = stage + q_off[NRND - RND_C + rd];
+                q[0] = hit ? c0 : 0.f; q[1] = hit ? c1 : 0.f; q[2] = hit ? f_crad : 0.f; q[3] = hit ? c3 : 0.f;
+                q[4] = hit ? c4 : 0.f; q[5] = hit ? c5 : 0.f; q[6] = hit ? 1.f : 0.f;
             }
+        }
+        // own rows, the entries that change: lane t < NT holds target t, lane c < NC holds camera c
+        if (lane < NT) {
+            const int capacity = tp_capacity(tpk), empty = tp_empty(tpk);
+            float* q = self_t;
+            q[0] = t0; q[1] = t1; q[3] = t3;
+            q[4] = capacity == 1 ? f_step1 : f_step2; q[5] = (float)capacity;
+#pragma unroll
+            for (int w = 0; w < NW; ++w) { q[6 + w] = (goal == w) ? (float)weight : 0.f; q[10 + w] = (float)((empty >> w) & 1); }
+        }
+        if (NC > 0 && lane < NC) {
+            float* q = self_c;
+            q[0] = c0; q[1] = c1; q[3] = c3; q[4] = c4; q[5] = c5;
         }
         // ---- staged rows -> HBM: one bulk (TMA) copy per tensor, issued by one lane
         if (S::BULK) {
