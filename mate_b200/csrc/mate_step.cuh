@@ -319,6 +319,175 @@ __device__ __noinline__ void process_exact(const Params& p, int env0, uint32_t* 
 }
 
 // =============================================================================================
+// joint_observation (environment.py:908-983) for the warp's environments [env0, env0 + nvalid).
+// Out of line on purpose: the packer gets its own register allocation.
+// =============================================================================================
+template <int NC, int NT, int NO>
+__device__ __noinline__ void pack_observations(const Params& p, const int env0, const int nvalid, float* stage,
+                                               const uint32_t* mk, const float* val) {
+    using S = Shape2<NC, NT, NO>;
+    constexpr int R = S::R, MW = S::MW, DC = S::DC, DT = S::DT, CV = S::CV;
+    constexpr int NCX = NC > 0 ? NC : 1;
+    const int lane = threadIdx.x & 31;
+    const size_t bp = p.bpad;
+    // The warp walks over its environments and assembles the 6 KB block of observation rows of one
+    // environment in shared memory, every float written exactly once and without branches:
+    //   * (observer row, entity) PAIRS are spread over the lanes, one entity kind at a time (a lane keeps
+    //     the same entity for all rounds of a kind); a pair writes the entity's public state and flag if
+    //     the observer's mask bit is set and zeros otherwise (masked-out entries are all-zero);
+    //   * lanes 0..R-1 write the preserved block and the private state of "their" observer row.
+    constexpr int C_SELF = 13, C_TGT = 22, C_OBS = 22 + 5 * NT, C_CAM = 22 + 5 * NT + 4 * NO;
+    constexpr int T_SELF = 13, T_CAM = 27, T_OBS = 27 + 7 * NC, T_TGT = 27 + 7 * NC + 4 * NO;
+    constexpr int NOX = NO > 0 ? NO : 1;
+    constexpr int RPR_T = 32 / NT, RPR_O = 32 / NOX, RPR_C = 32 / NCX;          // observer rows per round
+    constexpr int RND_T = (R + RPR_T - 1) / RPR_T, RND_O = (R + RPR_O - 1) / RPR_O, RND_C = (R + RPR_C - 1) / RPR_C;
+    const float f_sr = (float)p.tgt_sight_range, f_crad = (float)p.cam_radius;
+    const float f_rmax = (float)p.cam_rmax, f_rot = (float)p.cam_rot_step, f_zoom = (float)p.cam_zoom_step;
+    const float f_step1 = (float)p.tgt_step_size, f_step2 = (float)(p.tgt_step_size / 2.0);
+    // per-lane constants of the scatter, hoisted out of the environment loop: for every round the offset
+    // of this lane's slot in the staged block (inactive lanes write to a dummy slot behind the block, so
+    // the code is branch-free) and the mask word + bit that decide it
+    constexpr int DUMMY = S::STAGE_FLOATS;
+    constexpr int NRND = RND_T + (NO > 0 ? RND_O : 0) + (NC > 0 ? RND_C : 0);
+    const int t_idx = lane % NT, t_sub = lane / NT;
+    const int o_idx = lane % NOX, o_sub = lane / NOX;
+    const int c_idx = lane % NCX, c_sub = lane / NCX;
+    auto row_base = [&](const int row) { return row < NC ? row * DC : S::STAGE_CAM + (row - NC) * DT; };
+    int q_off[NRND], m_idx[NRND];
+#pragma unroll
+    for (int rd = 0; rd < RND_T; ++rd) {
+        const int row = rd * RPR_T + t_sub;
+        const bool on = t_sub < RPR_T && row < R;
+        q_off[rd] = on ? row_base(row) + (row < NC ? C_TGT : T_TGT) + 5 * t_idx : DUMMY;
+        m_idx[rd] = on ? row * MW : 0;
+    }
+    if (NO > 0) {
+#pragma unroll
+        for (int rd = 0; rd < RND_O; ++rd) {
+            const int row = rd * RPR_O + o_sub;
+            const bool on = o_sub < RPR_O && row < R;
+            q_off[RND_T + rd] = on ? row_base(row) + (row < NC ? C_OBS : T_OBS) + 4 * o_idx : DUMMY;
+            m_idx[RND_T + rd] = on ? row * MW + (MW - 1) : 0;
+        }
+    }
+    if (NC > 0) {
+#pragma unroll
+        for (int rd = 0; rd < RND_C; ++rd) {
+            const int row = rd * RPR_C + c_sub;
+            const bool on = c_sub < RPR_C && row < R;
+            q_off[NRND - RND_C + rd] = on ? row_base(row) + (row < NC ? C_CAM : T_CAM) + 7 * c_idx : DUMMY;
+            m_idx[NRND - RND_C + rd] = on ? row * MW : 0;
+        }
+    }
+    const uint32_t t_bit = bit_tgt(t_idx), o_bit = MW == 1 ? (1u << (16 + o_idx)) : (1u << o_idx), c_bit = bit_cam(c_idx);
+    // the own-row entries that never change are staged once: preserved block (environment.py:921-934)
+    // and the constant entries of the private state
+    if (lane < R) {
+        const int row = lane;
+        float* q = stage + row_base(row);
+        q[0] = (float)NC; q[1] = (float)NT; q[2] = (float)NO; q[3] = (float)(row < NC ? row : row - NC);
+        q[4] = 925.f; q[5] = 925.f; q[6] = -925.f; q[7] = 925.f; q[8] = -925.f; q[9] = -925.f; q[10] = 925.f; q[11] = -925.f;
+        q[12] = 75.f;
+        if (row < NC) { q[C_SELF + 2] = f_crad; q[C_SELF + 6] = f_rmax; q[C_SELF + 7] = f_rot; q[C_SELF + 8] = f_zoom; }
+        else q[T_SELF + 2] = f_sr;
+    }
+    float* const self_t = stage + S::STAGE_CAM + t_idx * DT + T_SELF;   // used by lanes 0..NT-1
+    float* const self_c = stage + c_idx * DC + C_SELF;                   // used by lanes 0..NC-1
+    // obstacle entries are fetched two environments ahead (an L2 round trip is longer than one iteration)
+    const float4* ob_ptr = p.obs_f4 + (size_t)o_idx * bp + env0;
+    float4 ob_next = make_float4(0.f, 0.f, 0.f, 0.f), ob_next2 = ob_next;
+    if (NO > 0) { ob_next = ob_ptr[0]; if (nvalid > 1) ob_next2 = ob_ptr[1]; }
+    __syncwarp();
+#pragma unroll 1
+    for (int i = 0; i < nvalid; ++i) {
+        const float* v = val + i * S::VSTRIDE;
+        const uint32_t* m = mk + i * S::MSTRIDE;
+        const int env = env0 + i;
+        const float4 ob = ob_next;
+        ob_next = ob_next2;
+        if (NO > 0 && i + 2 < nvalid) ob_next2 = ob_ptr[i + 2];
+        // Target.state public part (entities.py:631-637), Camera.state public part (entities.py:313-324)
+        const uint32_t tpk = __float_as_uint(v[S::V_T + 3 * t_idx + 2]);
+        const float t0 = v[S::V_T + 3 * t_idx], t1 = v[S::V_T + 3 * t_idx + 1];
+        const int goal = tp_goal(tpk), weight = tp_weight(tpk);
+        const float t3 = (goal >= 0 && weight > 0) ? 1.f : 0.f;
+        float c0 = 0.f, c1 = 0.f, c3 = 0.f, c4 = 0.f, c5 = 0.f;
+        if (NC > 0) {
+            const float* cv = v + S::V_C + CV * c_idx;
+            c0 = cv[0]; c1 = cv[1]; c3 = cv[3] * cv[4]; c4 = cv[3] * cv[5]; c5 = cv[2];
+        }
+        if (i > 0) {   // the previous environment's bulk copy must have read the staged block
+            if (S::BULK) { if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+            __syncwarp();
+        }
+#pragma unroll
+        for (int rd = 0; rd < RND_T; ++rd) {   // targets + flag
+            const bool hit = (m[m_idx[rd]] & t_bit) != 0u;
+            float* q = stage + q_off[rd];
+            q[0] = hit ? t0 : 0.f; q[1] = hit ? t1 : 0.f; q[2] = hit ? f_sr : 0.f; q[3] = hit ? t3 : 0.f; q[4] = hit ? 1.f : 0.f;
+        }
+        if (NO > 0) {
+#pragma unroll
+            for (int rd = 0; rd < RND_O; ++rd) {   // obstacles: Obstacle.state (entities.py:147-148) + flag
+                const bool hit = (m[m_idx[RND_T + rd]] & o_bit) != 0u;
+                float* q = stage + q_off[RND_T + rd];
+                q[0] = hit ? ob.x : 0.f; q[1] = hit ? ob.y : 0.f; q[2] = hit ? ob.z : 0.f; q[3] = hit ? 1.f : 0.f;
+            }
+        }
+        if (NC > 0) {
+#pragma unroll
+            for (int rd = 0; rd < RND_C; ++rd) {   // cameras + flag
+                const bool hit = (m[m_idx[NRND - RND_C + rd]] & c_bit) != 0u;
+                float* q = stage + q_off[NRND - RND_C + rd];
+                q[0] = hit ? c0 : 0.f; q[1] = hit ? c1 : 0.f; q[2] = hit ? f_crad : 0.f; q[3] = hit ? c3 : 0.f;
+                q[4] = hit ? c4 : 0.f; q[5] = hit ? c5 : 0.f; q[6] = hit ? 1.f : 0.f;
+            }
+        }
+        // own rows, the entries that change: lane t < NT holds target t, lane c < NC holds camera c
+        if (lane < NT) {
+            const int capacity = tp_capacity(tpk), empty = tp_empty(tpk);
+            float* q = self_t;
+            q[0] = t0; q[1] = t1; q[3] = t3;
+            q[4] = capacity == 1 ? f_step1 : f_step2; q[5] = (float)capacity;
+#pragma unroll
+            for (int w = 0; w < NW; ++w) { q[6 + w] = (goal == w) ? (float)weight : 0.f; q[10 + w] = (float)((empty >> w) & 1); }
+        }
+        if (NC > 0 && lane < NC) {
+            float* q = self_c;
+            q[0] = c0; q[1] = c1; q[3] = c3; q[4] = c4; q[5] = c5;
+        }
+        // ---- staged rows -> HBM: one bulk (TMA) copy per tensor, issued by one lane
+        if (S::BULK) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) {
+                if (NC > 0) {
+                    const uint32_t src = (uint32_t)__cvta_generic_to_shared(stage);
+                    float* dst = p.cam_obs + (size_t)env * S::CAM_ROW;
+                    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                                 :: "l"(dst), "r"(src), "r"((uint32_t)(S::CAM_ROW * 4)) : "memory");
+                }
+                const uint32_t src = (uint32_t)__cvta_generic_to_shared(stage + S::STAGE_CAM);
+                float* dst = p.tgt_obs + (size_t)env * S::TGT_ROW;
+                asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                             :: "l"(dst), "r"(src), "r"((uint32_t)(S::TGT_ROW * 4)) : "memory");
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            }
+        } else {
+            __syncwarp();
+            if (NC > 0) {
+                float* dst = p.cam_obs + (size_t)env * S::CAM_ROW;
+                for (int k = lane; k < S::CAM_ROW; k += 32) dst[k] = stage[k];
+            }
+            float* dst = p.tgt_obs + (size_t)env * S::TGT_ROW;
+            for (int k = lane; k < S::TGT_ROW; k += 32) dst[k] = stage[S::STAGE_CAM + k];
+            __syncwarp();
+        }
+    }
+    if (S::BULK && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+
+// =============================================================================================
 // The fused kernel
 // =============================================================================================
 template <int NC, int NT, int NO>
@@ -326,7 +495,7 @@ __global__ void __launch_bounds__(Shape2<NC, NT, NO>::WARPS * 32, MATE2_MIN_CTAS
 mate_step_kernel2(const Params p) {
     using S = Shape2<NC, NT, NO>;
     static_assert(NC <= 8 && NT <= 8 && NO <= 32, "mask layout: 8 cameras, 8 targets, 32 obstacles");
-    constexpr int R = S::R, MW = S::MW, DC = S::DC, DT = S::DT, CV = S::CV;
+    constexpr int MW = S::MW, CV = S::CV;
     constexpr int NCX = NC > 0 ? NC : 1;
     constexpr uint32_t FULL = 0xffffffffu;
 
@@ -398,12 +567,10 @@ mate_step_kernel2(const Params p) {
 #pragma unroll
             for (int t = 0; t < NT; ++t) { otx[t] = (float)p.tgt_x[(size_t)t * bp + er]; oty[t] = (float)p.tgt_y[(size_t)t * bp + er]; }
             const float fb = (float)p.tgt_step_size * 1.00001f + 0.01f;
-            float4 ob_n = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (NO > 0) ob_n = p.obs_f4[er];
-#pragma unroll 1
+            // (unrolled for small NO: the loads of all discs are in flight together)
+#pragma unroll (NO <= 12 ? 12 : 4)
             for (int o = 0; o < NO; ++o) {
-                const float4 ob = ob_n;
-                if (o + 1 < NO) ob_n = p.obs_f4[(size_t)(o + 1) * bp + er];
+                const float4 ob = p.obs_f4[(size_t)o * bp + er];
                 const float reach = fb + ob.z, reach2 = reach * reach;
 #pragma unroll
                 for (int t = 0; t < NT; ++t) {
@@ -559,12 +726,9 @@ mate_step_kernel2(const Params p) {
                     if (band_c) trow[t] |= resolve_band(p, er, ax, ay, band_c, 1, src, false);   // bit_cam(c) == 1 << c
                 }
             }
-            float4 ob_n = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (NO > 0) ob_n = p.obs_f4[er];
-#pragma unroll 1
+#pragma unroll (NO <= 12 ? 3 : 4)
             for (int o = 0; o < NO; ++o) {
-                const float4 ob = ob_n;
-                if (o + 1 < NO) ob_n = p.obs_f4[(size_t)(o + 1) * bp + er];
+                const float4 ob = p.obs_f4[(size_t)o * bp + er];
                 const uint32_t obit = MW == 1 ? (1u << (16 + o)) : (1u << (o & 31));
                 const float rtf = fsr + ob.z, rt2 = rtf * rtf;
                 const float rcf = (float)p.cam_rmax + ob.z, rc2 = rcf * rcf;
@@ -917,158 +1081,7 @@ mate_step_kernel2(const Params p) {
     __syncwarp();
 
     // ------------------------------------------------------------------ joint_observation (environment.py:908-983)
-    // The warp walks over its environments and assembles the 6 KB block of observation rows of one
-    // environment in shared memory, every float written exactly once and without branches:
-    //   * (observer row, entity) PAIRS are spread over the lanes, one entity kind at a time (a lane keeps
-    //     the same entity for all rounds of a kind); a pair writes the entity's public state and flag if
-    //     the observer's mask bit is set and zeros otherwise (masked-out entries are all-zero);
-    //   * lanes 0..R-1 write the preserved block and the private state of "their" observer row.
-    constexpr int C_SELF = 13, C_TGT = 22, C_OBS = 22 + 5 * NT, C_CAM = 22 + 5 * NT + 4 * NO;
-    constexpr int T_SELF = 13, T_CAM = 27, T_OBS = 27 + 7 * NC, T_TGT = 27 + 7 * NC + 4 * NO;
-    constexpr int NOX = NO > 0 ? NO : 1;
-    constexpr int RPR_T = 32 / NT, RPR_O = 32 / NOX, RPR_C = 32 / NCX;          // observer rows per round
-    constexpr int RND_T = (R + RPR_T - 1) / RPR_T, RND_O = (R + RPR_O - 1) / RPR_O, RND_C = (R + RPR_C - 1) / RPR_C;
-    const float f_sr = (float)p.tgt_sight_range, f_crad = (float)p.cam_radius;
-    const float f_rmax = (float)p.cam_rmax, f_rot = (float)p.cam_rot_step, f_zoom = (float)p.cam_zoom_step;
-    const float f_step1 = (float)p.tgt_step_size, f_step2 = (float)(p.tgt_step_size / 2.0);
-    // per-lane constants of the scatter, hoisted out of the environment loop: for every round the offset
-    // of this lane's slot in the staged block (inactive lanes write to a dummy slot behind the block, so
-    // the code is branch-free) and the mask word + bit that decide it
-    constexpr int DUMMY = S::STAGE_FLOATS;
-    constexpr int NRND = RND_T + (NO > 0 ? RND_O : 0) + (NC > 0 ? RND_C : 0);
-    const int t_idx = lane % NT, t_sub = lane / NT;
-    const int o_idx = lane % NOX, o_sub = lane / NOX;
-    const int c_idx = lane % NCX, c_sub = lane / NCX;
-    auto row_base = [&](const int row) { return row < NC ? row * DC : S::STAGE_CAM + (row - NC) * DT; };
-    int q_off[NRND], m_idx[NRND];
-#pragma unroll
-    for (int rd = 0; rd < RND_T; ++rd) {
-        const int row = rd * RPR_T + t_sub;
-        const bool on = t_sub < RPR_T && row < R;
-        q_off[rd] = on ? row_base(row) + (row < NC ? C_TGT : T_TGT) + 5 * t_idx : DUMMY;
-        m_idx[rd] = on ? row * MW : 0;
-    }
-    if (NO > 0) {
-#pragma unroll
-        for (int rd = 0; rd < RND_O; ++rd) {
-            const int row = rd * RPR_O + o_sub;
-            const bool on = o_sub < RPR_O && row < R;
-            q_off[RND_T + rd] = on ? row_base(row) + (row < NC ? C_OBS : T_OBS) + 4 * o_idx : DUMMY;
-            m_idx[RND_T + rd] = on ? row * MW + (MW - 1) : 0;
-        }
-    }
-    if (NC > 0) {
-#pragma unroll
-        for (int rd = 0; rd < RND_C; ++rd) {
-            const int row = rd * RPR_C + c_sub;
-            const bool on = c_sub < RPR_C && row < R;
-            q_off[NRND - RND_C + rd] = on ? row_base(row) + (row < NC ? C_CAM : T_CAM) + 7 * c_idx : DUMMY;
-            m_idx[NRND - RND_C + rd] = on ? row * MW : 0;
-        }
-    }
-    const uint32_t t_bit = bit_tgt(t_idx), o_bit = MW == 1 ? (1u << (16 + o_idx)) : (1u << o_idx), c_bit = bit_cam(c_idx);
-    // the own-row entries that never change are staged once: preserved block (environment.py:921-934)
-    // and the constant entries of the private state
-    if (lane < R) {
-        const int row = lane;
-        float* q = stage + row_base(row);
-        q[0] = (float)NC; q[1] = (float)NT; q[2] = (float)NO; q[3] = (float)(row < NC ? row : row - NC);
-        q[4] = 925.f; q[5] = 925.f; q[6] = -925.f; q[7] = 925.f; q[8] = -925.f; q[9] = -925.f; q[10] = 925.f; q[11] = -925.f;
-        q[12] = 75.f;
-        if (row < NC) { q[C_SELF + 2] = f_crad; q[C_SELF + 6] = f_rmax; q[C_SELF + 7] = f_rot; q[C_SELF + 8] = f_zoom; }
-        else q[T_SELF + 2] = f_sr;
-    }
-    float* const self_t = stage + S::STAGE_CAM + t_idx * DT + T_SELF;   // used by lanes 0..NT-1
-    float* const self_c = stage + c_idx * DC + C_SELF;                   // used by lanes 0..NC-1
-    float4 ob_next = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (NO > 0) ob_next = p.obs_f4[(size_t)o_idx * bp + env0];
-    __syncwarp();
-#pragma unroll 1
-    for (int i = 0; i < nvalid; ++i) {
-        const float* v = val + i * S::VSTRIDE;
-        const uint32_t* m = mk + i * S::MSTRIDE;
-        const int env = env0 + i;
-        const float4 ob = ob_next;
-        if (NO > 0 && i + 1 < nvalid) ob_next = p.obs_f4[(size_t)o_idx * bp + env + 1];   // fetched one environment ahead
-        // Target.state public part (entities.py:631-637), Camera.state public part (entities.py:313-324)
-        const uint32_t tpk = __float_as_uint(v[S::V_T + 3 * t_idx + 2]);
-        const float t0 = v[S::V_T + 3 * t_idx], t1 = v[S::V_T + 3 * t_idx + 1];
-        const int goal = tp_goal(tpk), weight = tp_weight(tpk);
-        const float t3 = (goal >= 0 && weight > 0) ? 1.f : 0.f;
-        float c0 = 0.f, c1 = 0.f, c3 = 0.f, c4 = 0.f, c5 = 0.f;
-        if (NC > 0) {
-            const float* cv = v + S::V_C + CV * c_idx;
-            c0 = cv[0]; c1 = cv[1]; c3 = cv[3] * cv[4]; c4 = cv[3] * cv[5]; c5 = cv[2];
-        }
-        if (i > 0) {   // the previous environment's bulk copy must have read the staged block
-            if (S::BULK) { if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
-            __syncwarp();
-        }
-#pragma unroll
-        for (int rd = 0; rd < RND_T; ++rd) {   // targets + flag
-            const bool hit = (m[m_idx[rd]] & t_bit) != 0u;
-            float* q = stage + q_off[rd];
-            q[0] = hit ? t0 : 0.f; q[1] = hit ? t1 : 0.f; q[2] = hit ? f_sr : 0.f; q[3] = hit ? t3 : 0.f; q[4] = hit ? 1.f : 0.f;
-        }
-        if (NO > 0) {
-#pragma unroll
-            for (int rd = 0; rd < RND_O; ++rd) {   // obstacles: Obstacle.state (entities.py:147-148) + flag
-                const bool hit = (m[m_idx[RND_T + rd]] & o_bit) != 0u;
-                float* q = stage + q_off[RND_T + rd];
-                q[0] = hit ? ob.x : 0.f; q[1] = hit ? ob.y : 0.f; q[2] = hit ? ob.z : 0.f; q[3] = hit ? 1.f : 0.f;
-            }
-        }
-        if (NC > 0) {
-#pragma unroll
-            for (int rd = 0; rd < RND_C; ++rd) {   // cameras + flag
-                const bool hit = (m[m_idx[NRND - RND_C + rd]] & c_bit) != 0u;
-                float* q = stage + q_off[NRND - RND_C + rd];
-                q[0] = hit ? c0 : 0.f; q[1] = hit ? c1 : 0.f; q[2] = hit ? f_crad : 0.f; q[3] = hit ? c3 : 0.f;
-                q[4] = hit ? c4 : 0.f; q[5] = hit ? c5 : 0.f; q[6] = hit ? 1.f : 0.f;
-            }
-        }
-        // own rows, the entries that change: lane t < NT holds target t, lane c < NC holds camera c
-        if (lane < NT) {
-            const int capacity = tp_capacity(tpk), empty = tp_empty(tpk);
-            float* q = self_t;
-            q[0] = t0; q[1] = t1; q[3] = t3;
-            q[4] = capacity == 1 ? f_step1 : f_step2; q[5] = (float)capacity;
-#pragma unroll
-            for (int w = 0; w < NW; ++w) { q[6 + w] = (goal == w) ? (float)weight : 0.f; q[10 + w] = (float)((empty >> w) & 1); }
-        }
-        if (NC > 0 && lane < NC) {
-            float* q = self_c;
-            q[0] = c0; q[1] = c1; q[3] = c3; q[4] = c4; q[5] = c5;
-        }
-        // ---- staged rows -> HBM: one bulk (TMA) copy per tensor, issued by one lane
-        if (S::BULK) {
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            __syncwarp();
-            if (lane == 0) {
-                if (NC > 0) {
-                    const uint32_t src = (uint32_t)__cvta_generic_to_shared(stage);
-                    float* dst = p.cam_obs + (size_t)env * S::CAM_ROW;
-                    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
-                                 :: "l"(dst), "r"(src), "r"((uint32_t)(S::CAM_ROW * 4)) : "memory");
-                }
-                const uint32_t src = (uint32_t)__cvta_generic_to_shared(stage + S::STAGE_CAM);
-                float* dst = p.tgt_obs + (size_t)env * S::TGT_ROW;
-                asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
-                             :: "l"(dst), "r"(src), "r"((uint32_t)(S::TGT_ROW * 4)) : "memory");
-                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-            }
-        } else {
-            __syncwarp();
-            if (NC > 0) {
-                float* dst = p.cam_obs + (size_t)env * S::CAM_ROW;
-                for (int k = lane; k < S::CAM_ROW; k += 32) dst[k] = stage[k];
-            }
-            float* dst = p.tgt_obs + (size_t)env * S::TGT_ROW;
-            for (int k = lane; k < S::TGT_ROW; k += 32) dst[k] = stage[S::STAGE_CAM + k];
-            __syncwarp();
-        }
-    }
-    if (S::BULK && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    pack_observations<NC, NT, NO>(p, env0, nvalid, stage, mk, val);
 }
 
 }  // namespace mate
