@@ -106,12 +106,22 @@ __device__ __forceinline__ int fov_reach32(float cx, float cy, float rs2, float 
     return 2;
 }
 
-// Target.simulate (entities.py:645-668) in fp64 against all discs (obstacles, then camera barriers),
-// for the targets whose step may touch a disc.  Returns the new location and the colliding flag.
-// `camv` = the fp32 camera entries of this environment in shared memory.
+// Target.simulate (entities.py:645-668) in fp64 for the queued targets whose step may touch a disc:
+// 32 (environment, target) items at a time, one per lane.  An fp32 segment-to-centre distance test picks
+// the discs that can modify the step (Obstacle.obstruct changes a ray only if the ray meets the disc, i.e.
+// the disc centre is within R of the segment); only those go through the fp64 Obstacle.obstruct.
 template <int NC, int NT, int NO, class S>
-__device__ __noinline__ void target_step_exact(const Params& p, int er, int t, uint32_t tpack, const float* camv,
-                                               double* out_x, double* out_y, int* colliding) {
+__device__ __noinline__ void process_slow_targets(const Params& p, int env0, float* val, const uint16_t* queue, int base, int n) {
+    const int lane = threadIdx.x & 31;
+    if (lane >= n) return;
+    const uint32_t item = queue[base + lane];
+    const int src = item >> 8, t = item & 0xFF;
+    const int env = env0 + src;
+    const bool env_ok = env < p.num_envs;
+    const int er = env_ok ? env : p.num_envs - 1;
+    float* v = val + src * S::VSTRIDE;
+    const float* camv = v + S::V_C;
+    uint32_t tpack = __float_as_uint(v[S::V_T + 3 * t + 2]);
     const size_t bp = p.bpad;
     const double tx = p.tgt_x[(size_t)t * bp + er], ty = p.tgt_y[(size_t)t * bp + er];
     const float2 a = reinterpret_cast<const float2*>(p.tgt_act)[(size_t)er * NT + t];
@@ -127,37 +137,48 @@ __device__ __noinline__ void target_step_exact(const Params& p, int er, int t, u
         s.bound = s.n * (1.0 + 1e-12);
     }
     const double desx = tx + s.vx, desy = ty + s.vy;
-    // fp32 candidates: discs within bound + R of the origin (one batch of loads); as long as the step is
-    // unmodified every other disc fails Obstacle.obstruct's `relative.norm >= norm + radius` test anyway
+    // fp32 candidates: centre within R (+ slack) of the segment [origin, origin + v]
     unsigned long long cand = 0ull;
     {
-        const float ftx = (float)tx, fty = (float)ty, fb = (float)s.bound * 1.00001f + 0.01f;
-#pragma unroll
+        const float ftx = (float)tx, fty = (float)ty, fvx = (float)s.vx, fvy = (float)s.vy;
+        const float vv = fvx * fvx + fvy * fvy, inv_vv = vv > 0.f ? 1.0f / vv : 0.f;
+        auto near_segment = [&](const float cx, const float cy, const float R) {
+            const float rx = cx - ftx, ry = cy - fty;
+            const float tt = fminf(fmaxf((rx * fvx + ry * fvy) * inv_vv, 0.f), 1.f);
+            const float ex = rx - tt * fvx, ey = ry - tt * fvy;
+            const float reach = R * 1.0001f + 0.02f;
+            return !(ex * ex + ey * ey > reach * reach);
+        };
+        float4 nxt = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (NO > 0) nxt = p.obs_f4[er];
+#pragma unroll 4
         for (int o = 0; o < NO; ++o) {
-            const float4 ob = p.obs_f4[(size_t)o * bp + er];
-            const float dx = ob.x - ftx, dy = ob.y - fty, reach = fb + ob.z;
-            cand |= (unsigned long long)(!(dx * dx + dy * dy > reach * reach)) << o;
+            const float4 ob = nxt;
+            if (o + 1 < NO) nxt = p.obs_f4[(size_t)(o + 1) * bp + er];
+            cand |= (unsigned long long)near_segment(ob.x, ob.y, ob.z) << o;
         }
-        const float reach_c = fb + (float)p.cam_radius;
 #pragma unroll
-        for (int c = 0; c < NC; ++c) {
-            const float dx = camv[S::CV * c] - ftx, dy = camv[S::CV * c + 1] - fty;
-            cand |= (unsigned long long)(!(dx * dx + dy * dy > reach_c * reach_c)) << (NO + c);
-        }
+        for (int c = 0; c < NC; ++c)
+            cand |= (unsigned long long)near_segment(camv[S::CV * c], camv[S::CV * c + 1], (float)p.cam_radius) << (NO + c);
     }
     bool modified = false;
+    if (cand != 0ull) {
 #pragma unroll 1
-    for (int d = 0; d < NO + NC; ++d) {
-        if (!modified && !((cand >> d) & 1ull)) continue;
-        const double ovx = s.vx, ovy = s.vy;
-        if (d < NO) obstruct_step(s, tx, ty, p.obs_x[(size_t)d * bp + er], p.obs_y[(size_t)d * bp + er], p.obs_r[(size_t)d * bp + er]);
-        else obstruct_step(s, tx, ty, p.cam_x[(size_t)(d - NO) * bp + er], p.cam_y[(size_t)(d - NO) * bp + er], p.cam_radius);
-        modified = modified || s.vx != ovx || s.vy != ovy;
+        for (int d = 0; d < NO + NC; ++d) {
+            if (!modified && !((cand >> d) & 1ull)) continue;
+            const double ovx = s.vx, ovy = s.vy;
+            if (d < NO) obstruct_step(s, tx, ty, p.obs_x[(size_t)d * bp + er], p.obs_y[(size_t)d * bp + er], p.obs_r[(size_t)d * bp + er]);
+            else obstruct_step(s, tx, ty, p.cam_x[(size_t)(d - NO) * bp + er], p.cam_y[(size_t)(d - NO) * bp + er], p.cam_radius);
+            modified = modified || s.vx != ovx || s.vy != ovy;
+        }
     }
     const double nx = fmin(fmax(tx + s.vx, -kTerrain), kTerrain);
     const double ny = fmin(fmax(ty + s.vy, -kTerrain), kTerrain);
-    *colliding = !(fabs(nx - desx) <= 1e-6 && fabs(ny - desy) <= 1e-6);
-    *out_x = nx; *out_y = ny;
+    const int colliding = !(fabs(nx - desx) <= 1e-6 && fabs(ny - desy) <= 1e-6);
+    tpack = (tpack & ~(1u << 27)) | ((uint32_t)colliding << 27);
+    if (env_ok) { p.tgt_x[(size_t)t * bp + env] = nx; p.tgt_y[(size_t)t * bp + env] = ny; }
+    v[S::V_T + 3 * t + 0] = (float)nx; v[S::V_T + 3 * t + 1] = (float)ny;
+    v[S::V_T + 3 * t + 2] = __uint_as_float(tpack);
 }
 
 // occlusion of the segment camera c -> point q of env `er`: fast classification, exact polyline if undecided
@@ -626,18 +647,28 @@ mate_step_kernel2(const Params p) {
             myval[S::V_T + 3 * t + 0] = (float)tx; myval[S::V_T + 3 * t + 1] = (float)ty;
             myval[S::V_T + 3 * t + 2] = __uint_as_float(tpack);
         }
-        // exact re-simulation of the targets near a disc, one target per lane and iteration
-        while (__any_sync(FULL, slow != 0)) {
-            if (slow != 0) {
-                const int t = __ffs(slow) - 1;
-                slow &= slow - 1;
-                uint32_t tpack = __float_as_uint(myval[S::V_T + 3 * t + 2]);
-                double nx, ny; int colliding;
-                target_step_exact<NC, NT, NO, S>(p, er, t, tpack, mycam, &nx, &ny, &colliding);
-                tpack = (tpack & ~(1u << 27)) | ((uint32_t)colliding << 27);
-                if (env_ok) { p.tgt_x[(size_t)t * bp + e] = nx; p.tgt_y[(size_t)t * bp + e] = ny; }
-                myval[S::V_T + 3 * t + 0] = (float)nx; myval[S::V_T + 3 * t + 1] = (float)ny;
-                myval[S::V_T + 3 * t + 2] = __uint_as_float(tpack);
+        // exact re-simulation of the targets near a disc: queued and processed 32 at a time, one per lane
+        __syncwarp();
+        {
+            int count = 0;   // warp-uniform
+            for (;;) {
+                const bool more = __any_sync(FULL, slow != 0);
+                if (more) {
+                    const bool has = slow != 0;
+                    const int t = has ? (__ffs(slow) - 1) : 0;
+                    slow &= slow - 1;
+                    const uint32_t ballot = __ballot_sync(FULL, has);
+                    if (has) queue[count + __popc(ballot & ((1u << lane) - 1u))] = (uint16_t)((lane << 8) | t);
+                    count += __popc(ballot);
+                    __syncwarp();
+                }
+                if (count >= 32 || (!more && count > 0)) {
+                    const int n = min(count, 32);
+                    count -= n;
+                    process_slow_targets<NC, NT, NO, S>(p, env0, val, queue, count, n);
+                    __syncwarp();
+                }
+                if (!more && count == 0) break;
             }
         }
     }
