@@ -123,6 +123,10 @@ __device__ __noinline__ void process_slow_targets(const Params& p, int env0, flo
     const float* camv = v + S::V_C;
     uint32_t tpack = __float_as_uint(v[S::V_T + 3 * t + 2]);
     const size_t bp = p.bpad;
+    const float4* const obs_f4 = p.obs_f4 + er;
+    const double* const obs_x = p.obs_x + er; const double* const obs_y = p.obs_y + er; const double* const obs_r = p.obs_r + er;
+    const double* const cam_x = p.cam_x + er; const double* const cam_y = p.cam_y + er;
+    const double cam_radius = p.cam_radius;
     const double tx = p.tgt_x[(size_t)t * bp + er], ty = p.tgt_y[(size_t)t * bp + er];
     const float2 a = reinterpret_cast<const float2*>(p.tgt_act)[(size_t)er * NT + t];
     const double step_size = p.tgt_step_size / (double)tp_capacity(tpack);
@@ -150,16 +154,16 @@ __device__ __noinline__ void process_slow_targets(const Params& p, int env0, flo
             return !(ex * ex + ey * ey > reach * reach);
         };
         float4 nxt = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (NO > 0) nxt = p.obs_f4[er];
+        if (NO > 0) nxt = obs_f4[0];
 #pragma unroll 4
         for (int o = 0; o < NO; ++o) {
             const float4 ob = nxt;
-            if (o + 1 < NO) nxt = p.obs_f4[(size_t)(o + 1) * bp + er];
+            if (o + 1 < NO) nxt = obs_f4[(size_t)(o + 1) * bp];
             cand |= (unsigned long long)near_segment(ob.x, ob.y, ob.z) << o;
         }
 #pragma unroll
         for (int c = 0; c < NC; ++c)
-            cand |= (unsigned long long)near_segment(camv[S::CV * c], camv[S::CV * c + 1], (float)p.cam_radius) << (NO + c);
+            cand |= (unsigned long long)near_segment(camv[S::CV * c], camv[S::CV * c + 1], (float)cam_radius) << (NO + c);
     }
     bool modified = false;
     if (cand != 0ull) {
@@ -167,8 +171,8 @@ __device__ __noinline__ void process_slow_targets(const Params& p, int env0, flo
         for (int d = 0; d < NO + NC; ++d) {
             if (!modified && !((cand >> d) & 1ull)) continue;
             const double ovx = s.vx, ovy = s.vy;
-            if (d < NO) obstruct_step(s, tx, ty, p.obs_x[(size_t)d * bp + er], p.obs_y[(size_t)d * bp + er], p.obs_r[(size_t)d * bp + er]);
-            else obstruct_step(s, tx, ty, p.cam_x[(size_t)(d - NO) * bp + er], p.cam_y[(size_t)(d - NO) * bp + er], p.cam_radius);
+            if (d < NO) obstruct_step(s, tx, ty, obs_x[(size_t)d * bp], obs_y[(size_t)d * bp], obs_r[(size_t)d * bp]);
+            else obstruct_step(s, tx, ty, cam_x[(size_t)(d - NO) * bp], cam_y[(size_t)(d - NO) * bp], cam_radius);
             modified = modified || s.vx != ovx || s.vy != ovy;
         }
     }
@@ -350,7 +354,12 @@ __device__ __noinline__ void pack_observations(const Params& p, const int env0, 
     constexpr int R = S::R, MW = S::MW, DC = S::DC, DT = S::DT, CV = S::CV;
     constexpr int NCX = NC > 0 ? NC : 1;
     const int lane = threadIdx.x & 31;
+    // launch parameters used inside the loop, read once (a reference to the parameter block is a generic
+    // pointer: the compiler would re-load through it after every store)
     const size_t bp = p.bpad;
+    float* const cam_obs0 = p.cam_obs + (size_t)env0 * S::CAM_ROW;
+    float* const tgt_obs0 = p.tgt_obs + (size_t)env0 * S::TGT_ROW;
+    const float4* const obs_f4 = p.obs_f4;
     // The warp walks over its environments and assembles the 6 KB block of observation rows of one
     // environment in shared memory, every float written exactly once and without branches:
     //   * (observer row, entity) PAIRS are spread over the lanes, one entity kind at a time (a lane keeps
@@ -415,7 +424,7 @@ __device__ __noinline__ void pack_observations(const Params& p, const int env0, 
     float* const self_t = stage + S::STAGE_CAM + t_idx * DT + T_SELF;   // used by lanes 0..NT-1
     float* const self_c = stage + c_idx * DC + C_SELF;                   // used by lanes 0..NC-1
     // obstacle entries are fetched two environments ahead (an L2 round trip is longer than one iteration)
-    const float4* ob_ptr = p.obs_f4 + (size_t)o_idx * bp + env0;
+    const float4* ob_ptr = obs_f4 + (size_t)o_idx * bp + env0;
     float4 ob_next = make_float4(0.f, 0.f, 0.f, 0.f), ob_next2 = ob_next;
     if (NO > 0) { ob_next = ob_ptr[0]; if (nvalid > 1) ob_next2 = ob_ptr[1]; }
     __syncwarp();
@@ -423,7 +432,6 @@ __device__ __noinline__ void pack_observations(const Params& p, const int env0, 
     for (int i = 0; i < nvalid; ++i) {
         const float* v = val + i * S::VSTRIDE;
         const uint32_t* m = mk + i * S::MSTRIDE;
-        const int env = env0 + i;
         const float4 ob = ob_next;
         ob_next = ob_next2;
         if (NO > 0 && i + 2 < nvalid) ob_next2 = ob_ptr[i + 2];
@@ -484,12 +492,12 @@ __device__ __noinline__ void pack_observations(const Params& p, const int env0, 
             if (lane == 0) {
                 if (NC > 0) {
                     const uint32_t src = (uint32_t)__cvta_generic_to_shared(stage);
-                    float* dst = p.cam_obs + (size_t)env * S::CAM_ROW;
+                    float* dst = cam_obs0 + (size_t)i * S::CAM_ROW;
                     asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
                                  :: "l"(dst), "r"(src), "r"((uint32_t)(S::CAM_ROW * 4)) : "memory");
                 }
                 const uint32_t src = (uint32_t)__cvta_generic_to_shared(stage + S::STAGE_CAM);
-                float* dst = p.tgt_obs + (size_t)env * S::TGT_ROW;
+                float* dst = tgt_obs0 + (size_t)i * S::TGT_ROW;
                 asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
                              :: "l"(dst), "r"(src), "r"((uint32_t)(S::TGT_ROW * 4)) : "memory");
                 asm volatile("cp.async.bulk.commit_group;" ::: "memory");
@@ -497,10 +505,10 @@ __device__ __noinline__ void pack_observations(const Params& p, const int env0, 
         } else {
             __syncwarp();
             if (NC > 0) {
-                float* dst = p.cam_obs + (size_t)env * S::CAM_ROW;
+                float* dst = cam_obs0 + (size_t)i * S::CAM_ROW;
                 for (int k = lane; k < S::CAM_ROW; k += 32) dst[k] = stage[k];
             }
-            float* dst = p.tgt_obs + (size_t)env * S::TGT_ROW;
+            float* dst = tgt_obs0 + (size_t)i * S::TGT_ROW;
             for (int k = lane; k < S::TGT_ROW; k += 32) dst[k] = stage[S::STAGE_CAM + k];
             __syncwarp();
         }
@@ -513,7 +521,7 @@ __device__ __noinline__ void pack_observations(const Params& p, const int env0, 
 // =============================================================================================
 template <int NC, int NT, int NO>
 __global__ void __launch_bounds__(Shape2<NC, NT, NO>::WARPS * 32, MATE2_MIN_CTAS)
-mate_step_kernel2(const Params p) {
+mate_step_kernel2(const __grid_constant__ Params p) {
     using S = Shape2<NC, NT, NO>;
     static_assert(NC <= 8 && NT <= 8 && NO <= 32, "mask layout: 8 cameras, 8 targets, 32 obstacles");
     constexpr int MW = S::MW, CV = S::CV;
