@@ -35,6 +35,9 @@
 #ifndef MATE2_WARPS
 #define MATE2_WARPS 2          // warps per CTA (warps are independent; this only sets the CTA granularity)
 #endif
+#ifndef MATE2_COPYOUT
+#define MATE2_COPYOUT 1        // staged observation block -> HBM: 0 = bulk copy (TMA), 1 = 16-byte vector stores
+#endif
 #ifndef MATE2_MIN_CTAS
 #define MATE2_MIN_CTAS 8       // caps registers at 128 (4 warps per SM sub-partition); 65 536 envs = 2048 warp tiles = 13.8 per SM -> one wave
 #endif
@@ -435,6 +438,8 @@ __device__ __noinline__ void pack_observations(const Params& p, const int env0, 
         const float4 ob = ob_next;
         ob_next = ob_next2;
         if (NO > 0 && i + 2 < nvalid) ob_next2 = ob_ptr[i + 2];
+        // ---- everything is computed into registers first: the previous environment's bulk copy is
+        //      still reading the staged block, only the stores have to wait for it
         // Target.state public part (entities.py:631-637), Camera.state public part (entities.py:313-324)
         const uint32_t tpk = __float_as_uint(v[S::V_T + 3 * t_idx + 2]);
         const float t0 = v[S::V_T + 3 * t_idx], t1 = v[S::V_T + 3 * t_idx + 1];
@@ -445,48 +450,87 @@ __device__ __noinline__ void pack_observations(const Params& p, const int env0, 
             const float* cv = v + S::V_C + CV * c_idx;
             c0 = cv[0]; c1 = cv[1]; c3 = cv[3] * cv[4]; c4 = cv[3] * cv[5]; c5 = cv[2];
         }
-        if (i > 0) {   // the previous environment's bulk copy must have read the staged block
-            if (S::BULK) { if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
-            __syncwarp();
-        }
+        float vt[RND_T][5], vo[NO > 0 ? RND_O : 1][4], vc[NC > 0 ? RND_C : 1][7];
 #pragma unroll
         for (int rd = 0; rd < RND_T; ++rd) {   // targets + flag
             const bool hit = (m[m_idx[rd]] & t_bit) != 0u;
-            float* q = stage + q_off[rd];
-            q[0] = hit ? t0 : 0.f; q[1] = hit ? t1 : 0.f; q[2] = hit ? f_sr : 0.f; q[3] = hit ? t3 : 0.f; q[4] = hit ? 1.f : 0.f;
+            vt[rd][0] = hit ? t0 : 0.f; vt[rd][1] = hit ? t1 : 0.f; vt[rd][2] = hit ? f_sr : 0.f; vt[rd][3] = hit ? t3 : 0.f; vt[rd][4] = hit ? 1.f : 0.f;
         }
         if (NO > 0) {
 #pragma unroll
             for (int rd = 0; rd < RND_O; ++rd) {   // obstacles: Obstacle.state (entities.py:147-148) + flag
                 const bool hit = (m[m_idx[RND_T + rd]] & o_bit) != 0u;
-                float* q = stage + q_off[RND_T + rd];
-                q[0] = hit ? ob.x : 0.f; q[1] = hit ? ob.y : 0.f; q[2] = hit ? ob.z : 0.f; q[3] = hit ? 1.f : 0.f;
+                vo[rd][0] = hit ? ob.x : 0.f; vo[rd][1] = hit ? ob.y : 0.f; vo[rd][2] = hit ? ob.z : 0.f; vo[rd][3] = hit ? 1.f : 0.f;
             }
         }
         if (NC > 0) {
 #pragma unroll
             for (int rd = 0; rd < RND_C; ++rd) {   // cameras + flag
                 const bool hit = (m[m_idx[NRND - RND_C + rd]] & c_bit) != 0u;
-                float* q = stage + q_off[NRND - RND_C + rd];
-                q[0] = hit ? c0 : 0.f; q[1] = hit ? c1 : 0.f; q[2] = hit ? f_crad : 0.f; q[3] = hit ? c3 : 0.f;
-                q[4] = hit ? c4 : 0.f; q[5] = hit ? c5 : 0.f; q[6] = hit ? 1.f : 0.f;
+                vc[rd][0] = hit ? c0 : 0.f; vc[rd][1] = hit ? c1 : 0.f; vc[rd][2] = hit ? f_crad : 0.f; vc[rd][3] = hit ? c3 : 0.f;
+                vc[rd][4] = hit ? c4 : 0.f; vc[rd][5] = hit ? c5 : 0.f; vc[rd][6] = hit ? 1.f : 0.f;
             }
         }
         // own rows, the entries that change: lane t < NT holds target t, lane c < NC holds camera c
-        if (lane < NT) {
-            const int capacity = tp_capacity(tpk), empty = tp_empty(tpk);
-            float* q = self_t;
-            q[0] = t0; q[1] = t1; q[3] = t3;
-            q[4] = capacity == 1 ? f_step1 : f_step2; q[5] = (float)capacity;
+        const int capacity = tp_capacity(tpk), empty = tp_empty(tpk);
+        float sg[NW], se[NW];
 #pragma unroll
-            for (int w = 0; w < NW; ++w) { q[6 + w] = (goal == w) ? (float)weight : 0.f; q[10 + w] = (float)((empty >> w) & 1); }
+        for (int w = 0; w < NW; ++w) { sg[w] = (goal == w) ? (float)weight : 0.f; se[w] = (float)((empty >> w) & 1); }
+        const float s_step = capacity == 1 ? f_step1 : f_step2, s_cap = (float)capacity;
+
+        if (i > 0 && MATE2_COPYOUT == 0) {   // the previous environment's bulk copy must have read the staged block
+            if (S::BULK) { if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+            __syncwarp();
+        }
+#pragma unroll
+        for (int rd = 0; rd < RND_T; ++rd) {
+            float* q = stage + q_off[rd];
+            q[0] = vt[rd][0]; q[1] = vt[rd][1]; q[2] = vt[rd][2]; q[3] = vt[rd][3]; q[4] = vt[rd][4];
+        }
+        if (NO > 0) {
+#pragma unroll
+            for (int rd = 0; rd < RND_O; ++rd) {
+                float* q = stage + q_off[RND_T + rd];
+                q[0] = vo[rd][0]; q[1] = vo[rd][1]; q[2] = vo[rd][2]; q[3] = vo[rd][3];
+            }
+        }
+        if (NC > 0) {
+#pragma unroll
+            for (int rd = 0; rd < RND_C; ++rd) {
+                float* q = stage + q_off[NRND - RND_C + rd];
+                q[0] = vc[rd][0]; q[1] = vc[rd][1]; q[2] = vc[rd][2]; q[3] = vc[rd][3]; q[4] = vc[rd][4]; q[5] = vc[rd][5]; q[6] = vc[rd][6];
+            }
+        }
+        if (lane < NT) {
+            float* q = self_t;
+            q[0] = t0; q[1] = t1; q[3] = t3; q[4] = s_step; q[5] = s_cap;
+#pragma unroll
+            for (int w = 0; w < NW; ++w) { q[6 + w] = sg[w]; q[10 + w] = se[w]; }
         }
         if (NC > 0 && lane < NC) {
             float* q = self_c;
             q[0] = c0; q[1] = c1; q[3] = c3; q[4] = c4; q[5] = c5;
         }
-        // ---- staged rows -> HBM: one bulk (TMA) copy per tensor, issued by one lane
-        if (S::BULK) {
+        // ---- staged rows -> HBM
+        if (S::BULK && MATE2_COPYOUT == 1) {
+            // plain 16-byte copies: every warp store covers 512 contiguous bytes; unlike the bulk copy there
+            // is nothing to wait for before the block is reused (MATE2_COPYOUT)
+            __syncwarp();
+            const float4* src4 = reinterpret_cast<const float4*>(stage);
+            float4* cam4 = reinterpret_cast<float4*>(cam_obs0 + (size_t)i * S::CAM_ROW);
+            float4* tgt4 = reinterpret_cast<float4*>(tgt_obs0 + (size_t)i * S::TGT_ROW) - S::CAM_ROW / 4;
+            constexpr int NZ = S::STAGE_FLOATS / 4;
+#pragma unroll
+            for (int it = 0; it < (NZ + 31) / 32; ++it) {
+                const int k = it * 32 + lane;
+                if (it * 32 + 32 <= NZ || k < NZ) {
+                    const float4 x = src4[k];
+                    float4* dst = (k < S::CAM_ROW / 4 ? cam4 : tgt4) + k;
+                    __stcs(dst, x);
+                }
+            }
+            __syncwarp();
+        } else if (S::BULK) {
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             __syncwarp();
             if (lane == 0) {
@@ -513,7 +557,7 @@ __device__ __noinline__ void pack_observations(const Params& p, const int env0, 
             __syncwarp();
         }
     }
-    if (S::BULK && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    if (S::BULK && MATE2_COPYOUT == 0 && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
 
 // =============================================================================================
