@@ -146,13 +146,14 @@ def load_library():
     global _LIB  # pylint: disable=global-statement
     if _LIB is not None:
         return _LIB
-    if not os.path.exists(LIB_PATH):
+    path = os.environ.get('MATE_B200_LIB', LIB_PATH)   # override: A/B builds with other tuning knobs
+    if not os.path.exists(path):
         raise RuntimeError(
-            f'{LIB_PATH} is missing: the CUDA extension has not been built. '
+            f'{path} is missing: the CUDA extension has not been built. '
             'Run `python -c "import __graft_entry__ as g; g.build()"` in the repo root. '
             'mate_b200 has no CPU fallback.'
         )
-    lib = ctypes.CDLL(LIB_PATH)
+    lib = ctypes.CDLL(path)
     void_p = ctypes.c_void_p
     lib.mate_b200_last_error.restype = ctypes.c_char_p
     lib.mate_b200_abi_version.restype = ctypes.c_int

@@ -38,6 +38,9 @@
 #ifndef MATE2_COPYOUT
 #define MATE2_COPYOUT 1        // staged observation block -> HBM: 0 = bulk copy (TMA), 1 = 16-byte vector stores
 #endif
+#ifndef MATE2_STREAMING
+#define MATE2_STREAMING 1       // evict-first stores for the observation rows (written once, read by another kernel)
+#endif
 #ifndef MATE2_MIN_CTAS
 #define MATE2_MIN_CTAS 8       // caps registers at 128 (4 warps per SM sub-partition); 65 536 envs = 2048 warp tiles = 13.8 per SM -> one wave
 #endif
@@ -526,7 +529,7 @@ __device__ __noinline__ void pack_observations(const Params& p, const int env0, 
                 if (it * 32 + 32 <= NZ || k < NZ) {
                     const float4 x = src4[k];
                     float4* dst = (k < S::CAM_ROW / 4 ? cam4 : tgt4) + k;
-                    __stcs(dst, x);
+                    if (MATE2_STREAMING) __stcs(dst, x); else *dst = x;
                 }
             }
             __syncwarp();
