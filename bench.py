@@ -85,7 +85,7 @@ class ClockSampler:
                             self.reasons.add(name)
             except (OSError, ValueError, subprocess.SubprocessError, IndexError):
                 pass
-            self._stop.wait(0.1)
+            self._stop.wait(0.02)
 
     def __enter__(self):
         self._thread.start()
@@ -188,7 +188,7 @@ def run_reference(args, cfg, workload):
 def main():
     parser = argparse.ArgumentParser()
     parser.add_argument('--gpus', type=int, default=1)
-    parser.add_argument('--steps', type=int, default=200)
+    parser.add_argument('--steps', type=int, default=2000)
     parser.add_argument('--warmup', type=int, default=20)
     parser.add_argument('--impl', default='mine', choices=['mine', 'reference'])
     parser.add_argument('--config', default='MATE-4v8-9.yaml')
@@ -198,6 +198,7 @@ def main():
     parser.add_argument('--e2e-steps', type=int, default=10)
     parser.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
     parser.add_argument('--no-e2e', action='store_true', help='skip the host-buffer e2e leg')
+    parser.add_argument('--no-stagger', action='store_true', help='do not stagger the episode clocks (no resets in the timed region)')
     args = parser.parse_args()
 
     from mate_b200.config import flatten_config, read_config
@@ -224,6 +225,14 @@ def main():
     B = args.envs
     sim = BatchedSim(cfg, B, device=local_rank, env_index_base=rank * B)
     sim.reset(seed=0)
+    # Steady state: under random actions an episode lasts max_episode_steps + 1 steps, so a fresh batch would
+    # never reach a reset inside the timed region.  Stagger the episode clocks uniformly over one episode
+    # length: B / (max_episode_steps + 1) environments finish and are re-initialised in EVERY step.
+    if not args.no_stagger:
+        import numpy as np
+
+        steps0 = np.random.RandomState(1234 + rank).randint(0, cfg['max_episode_steps'] + 1, size=B).astype(np.int32)
+        sim.set_state({'episode_step': steps0})
     ring = 8
     cams, tgts = make_actions(cfg, B, device, ring, seed=rank)
     aux = sim.alloc_aux()
@@ -300,7 +309,7 @@ def main():
 
     A = algorithmic_bytes(nc, nt, no)
     peak, peak_src = measured_peak_gbs()
-    kernel_ms = elapsed_ms / max(launches, 1)
+    kernel_ms = elapsed_ms / max(args.steps, 1)   # one step kernel per step (the launch count also has the prepare launches)
     achieved = A * B / (kernel_ms * 1e-3) / 1e9
     line = {
         'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
@@ -308,18 +317,21 @@ def main():
         'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64 decision state, f32 I/O', 'data': 'synthetic',
         'config': {
             'workload': workload, 'envs_per_gpu': B, 'actions': 'uniform random joint actions (ring of 8 pre-generated batches)',
-            'auto_reset': True, 'l2': 'per-step working set (observations %.0f MB + state) exceeds the 126 MB L2' % (B * 4 * (nc * sim.dc + nt * sim.dt) / 1e6),
+            'auto_reset': True,
+            'episode_clocks': 'all zero' if args.no_stagger else 'staggered uniformly over one episode: %.1f resets per step' % (B / (cfg['max_episode_steps'] + 1.0)),
+            'l2': 'per-step working set (observations %.0f MB + state) exceeds the 126 MB L2' % (B * 4 * (nc * sim.dc + nt * sim.dt) / 1e6),
         },
         'agent_steps_per_s': value * (nc + nt),
         'gpu_launches': launches,
         'roofline': {
             'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
             'traffic': ncu_traffic_bytes(args.config.replace('.yaml', '')),
-            'kernel': 'mate_step_kernel<%d,%d,%d>' % (nc, nt, no), 'algorithmic_bytes_per_env_step': A,
+            'kernel': ('mate_step_kernel<%d,%d,%d>' if os.environ.get('MATE_B200_KERNEL', '2')[:1] == '1' else 'mate_step_kernel2<%d,%d,%d>') % (nc, nt, no), 'algorithmic_bytes_per_env_step': A,
             'kernel_ms': kernel_ms, 'peak_source': peak_src,
         },
         'clocks': clocks.summary(),
-        'episode_stats': {'episodes': stats[0], 'sum_return': stats[1], 'sum_length': stats[2], 'env_steps': stats[5]},
+        'episode_stats': {'episodes': stats[0], 'sum_return': stats[1], 'sum_length': stats[2], 'env_steps': stats[5],
+                          'resets_from_prepared_state': stats[6], 'resets_in_place': stats[7]},
     }
     if e2e is not None:
         line['e2e'] = e2e

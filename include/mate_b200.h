@@ -179,7 +179,8 @@ int mate_b200_set_state(MateSim* sim, const MateStateView* view);
 /* Episode statistics accumulated on device since the last call with reset_after != 0:
  * out[0]=episodes finished, [1]=sum return (target team), [2]=sum length,
  * [3]=sum delivered cargoes, [4]=sum of per-episode mean coverage, [5]=env-steps,
- * [6..15] reserved (0).  `out16` is a dev pointer to 16 floats; the optional multi-GPU
+ * [6]=auto-resets served from the prepared next-episode state, [7]=auto-resets computed in place,
+ * [8..15] reserved (0).  `out16` is a dev pointer to 16 floats; the optional multi-GPU
  * all-reduce of this vector is done by the caller (torch.distributed / NCCL). */
 int mate_b200_episode_stats(MateSim* sim, float* out16, int32_t reset_after, void* stream);
 

@@ -111,6 +111,15 @@ struct MateSim {
     double* d_ranges = nullptr;
     unsigned long long seed = 0;
     long long launches = 0;
+    // prepared resets (mate_step.cuh): second state block, parameter block that addresses it, side stream
+    void* next_block = nullptr;
+    Params next_base{};       // = base with the state pointers of the second block
+    Params* d_next = nullptr; // device copy of next_base (Params::next of the step launches)
+    cudaStream_t side = nullptr;
+    cudaEvent_t side_event = nullptr;
+    int refill_mode = 0;      // 0 = off, 1 = side stream every refill_period steps, 2 = same stream after every step (tests)
+    int refill_period = 32;
+    long long steps_since_refill = 0;
     // host-path (step_host) resources
     static constexpr int kHostStreams = 4;
     cudaStream_t hstreams[kHostStreams] = {};
@@ -190,6 +199,41 @@ extern "C" int mate_b200_create(const MateConfig* cfg, int32_t num_envs, int32_t
     p.cc_clear = (unsigned long long*)(b + o_cc);
     p.stats = (float*)(b + o_stats);
 
+    // prepared resets: a second state block of the same layout + first-view masks + the ready tags
+    sim->refill_mode = use_first_generation() ? 0 : 1;
+    if (const char* v = getenv("MATE_B200_REFILL")) {
+        if (!strcmp(v, "0") || !strcmp(v, "off")) sim->refill_mode = 0;
+        else if (!strcmp(v, "sync")) sim->refill_mode = sim->refill_mode ? 2 : 0;
+        else if (atoi(v) > 0) sim->refill_period = atoi(v);
+    }
+    if (sim->refill_mode) {
+        const int mask_words = (nc + nt) * (no <= 16 ? 1 : 2);
+        const size_t o_masks = carve(sizeof(uint32_t) * mask_words * bpad);
+        const size_t o_vals = carve(sizeof(float) * (3 * nt + 5 * nc) * bpad);
+        const size_t o_ready = carve(sizeof(uint32_t) * bpad);
+        const size_t block2 = off;
+        if (cudaMalloc(&sim->next_block, block2) != cudaSuccess) { cudaFree(sim->state_block); delete sim; return fail(MATE_ENOMEM, "cudaMalloc(prepared state) failed"); }
+        CUDA_TRY(cudaMemset(sim->next_block, 0, block2));
+        char* b2 = (char*)sim->next_block;
+        Params& n = sim->next_base;
+        n = p;   // scalars are copied again below, once they are set
+        n.cam_x = (double*)(b2 + o_cam_x); n.cam_y = (double*)(b2 + o_cam_y); n.cam_phi = (double*)(b2 + o_cam_phi); n.cam_theta = (double*)(b2 + o_cam_theta);
+        n.tgt_x = (double*)(b2 + o_tgt_x); n.tgt_y = (double*)(b2 + o_tgt_y);
+        n.obs_x = (double*)(b2 + o_obs_x); n.obs_y = (double*)(b2 + o_obs_y); n.obs_r = (double*)(b2 + o_obs_r);
+        n.obs_f4 = (float4*)(b2 + o_obs_f4);
+        n.tgt_pack = (uint32_t*)(b2 + o_pack);
+        n.cargo = (uint4*)(b2 + o_cargo); n.env_a = (uint4*)(b2 + o_env_a); n.env_b = (int4*)(b2 + o_env_b);
+        n.cc_clear = (unsigned long long*)(b2 + o_cc);
+        n.stats = (float*)(b2 + o_stats);
+        n.masks = (uint32_t*)(b2 + o_masks);
+        n.vals = (float*)(b2 + o_vals);
+        n.ready = (uint32_t*)(b2 + o_ready);
+        p.ready = n.ready;
+        CUDA_TRY(cudaMalloc(&sim->d_next, sizeof(Params)));
+        CUDA_TRY(cudaStreamCreateWithFlags(&sim->side, cudaStreamNonBlocking));
+        CUDA_TRY(cudaEventCreateWithFlags(&sim->side_event, cudaEventDisableTiming));
+    }
+
     // location ranges on device (reset)
     std::vector<double> ranges((size_t)4 * (nc + nt + no) + 4, 0.0);
     if (nc) memcpy(ranges.data(), cfg->camera_location_ranges, sizeof(double) * 4 * nc);
@@ -212,6 +256,18 @@ extern "C" int mate_b200_create(const MateConfig* cfg, int32_t num_envs, int32_t
     p.tgt_step_size = cfg->target_step_size; p.tgt_sight_range = cfg->target_sight_range;
     p.obs_r_low = cfg->obstacle_radius_low; p.obs_r_high = cfg->obstacle_radius_high;
 
+    if (sim->refill_mode) {
+        Params n = p;   // all scalars / range pointers of the live block ...
+        const Params& o = sim->next_base;   // ... with the state pointers of the second block
+        n.cam_x = o.cam_x; n.cam_y = o.cam_y; n.cam_phi = o.cam_phi; n.cam_theta = o.cam_theta; n.tgt_x = o.tgt_x; n.tgt_y = o.tgt_y;
+        n.obs_x = o.obs_x; n.obs_y = o.obs_y; n.obs_r = o.obs_r; n.obs_f4 = o.obs_f4; n.tgt_pack = o.tgt_pack;
+        n.cargo = o.cargo; n.env_a = o.env_a; n.env_b = o.env_b; n.cc_clear = o.cc_clear; n.stats = o.stats;
+        n.masks = o.masks; n.vals = o.vals; n.ready = o.ready; n.live_env_b = p.env_b; n.next = nullptr;
+        sim->next_base = n;
+        CUDA_TRY(cudaMemcpy(sim->d_next, &sim->next_base, sizeof(Params), cudaMemcpyHostToDevice));
+        p.next = sim->d_next;
+    }
+
     // neutral initial state so that a step before reset/set_state is well defined
     {
         std::vector<double> theta((size_t)nc * bpad, cfg->camera_min_viewing_angle > 0 ? cfg->camera_min_viewing_angle : 90.0);
@@ -231,6 +287,10 @@ extern "C" int mate_b200_destroy(MateSim* sim) {
         cudaFree(sim->h_cam_act); cudaFree(sim->h_tgt_act); cudaFree(sim->h_cam_obs); cudaFree(sim->h_tgt_obs);
         cudaFree(sim->h_rewards); cudaFree(sim->h_done);
     }
+    if (sim->side) { cudaStreamSynchronize(sim->side); cudaStreamDestroy(sim->side); }
+    if (sim->side_event) cudaEventDestroy(sim->side_event);
+    cudaFree(sim->next_block);
+    cudaFree(sim->d_next);
     cudaFree(sim->state_block);
     cudaFree(sim->d_ranges);
     delete sim;
@@ -263,6 +323,8 @@ static int launch_range(MateSim* sim, Params p, int begin, int count, cudaStream
     if (p.env_mask) p.env_mask += begin;
     if (p.replay_transmit) p.replay_transmit += (size_t)begin * nc * nt;
     if (p.replay_choice) p.replay_choice += (size_t)begin * nt;
+    if (p.ready) p.ready += begin;
+    if (begin != 0 || count != sim->num_envs) p.next = nullptr;   // prepared resets address whole-batch arrays
     p.env_index_base += begin;
     p.num_envs = count;
     const int grid = (count + sim->kernel.envs_per_cta - 1) / sim->kernel.envs_per_cta;
@@ -290,6 +352,38 @@ static void fill_aux(Params& p, const MateStepAux* aux, const MateReplay* replay
     p.replay_choice = replay ? replay->goal_choice : nullptr;
 }
 
+// Launch MODE_PREPARE over the second state block: re-initialises the prepared next episode of every env
+// whose tag is stale.  Off the step path: on the side stream, ordered after the work already enqueued on
+// `stream` (refill_mode 2: on `stream` itself, used by the tests to make the prepared path deterministic).
+static int launch_prepare(MateSim* sim, cudaStream_t stream) {
+    if (!sim->refill_mode) return MATE_OK;
+    cudaStream_t target = stream;
+    if (sim->refill_mode == 1) {
+        CUDA_TRY(cudaEventRecord(sim->side_event, stream));
+        CUDA_TRY(cudaStreamWaitEvent(sim->side, sim->side_event, 0));
+        target = sim->side;
+    }
+    Params n = sim->next_base;
+    n.mode = MODE_PREPARE; n.flags = 0; n.seed = sim->seed;
+    n.cam_act = n.tgt_act = nullptr; n.cam_obs = n.tgt_obs = n.rewards = nullptr; n.done = nullptr; n.env_mask = nullptr;
+    fill_aux(n, nullptr, nullptr);
+    const int grid = (sim->num_envs + sim->kernel.envs_per_cta - 1) / sim->kernel.envs_per_cta;
+    sim->kernel.launch(n, grid, target);
+    sim->launches += 1;
+    sim->steps_since_refill = 0;
+    cudaError_t err = cudaGetLastError();
+    if (err != cudaSuccess) return fail(MATE_ECUDA, std::string("prepare launch: ") + cudaGetErrorString(err));
+    return MATE_OK;
+}
+
+// the prepared episodes no longer match the live state (explicit reset with a new seed, set_state)
+static int invalidate_prepared(MateSim* sim, cudaStream_t stream) {
+    if (!sim->refill_mode) return MATE_OK;
+    CUDA_TRY(cudaStreamSynchronize(sim->side));
+    CUDA_TRY(cudaMemsetAsync(sim->base.ready, 0, sizeof(uint32_t) * sim->bpad, stream));
+    return MATE_OK;
+}
+
 extern "C" int mate_b200_reset(MateSim* sim, const uint8_t* env_mask, uint64_t seed, float* cam_obs,
                                float* tgt_obs, void* stream) {
     if (!sim || !tgt_obs || (sim->cfg.num_cameras > 0 && !cam_obs)) return fail(MATE_EINVAL, "null argument");
@@ -300,7 +394,9 @@ extern "C" int mate_b200_reset(MateSim* sim, const uint8_t* env_mask, uint64_t s
     p.mode = MODE_RESET; p.flags = 0; p.seed = seed;
     p.cam_obs = cam_obs; p.tgt_obs = tgt_obs; p.env_mask = env_mask;
     fill_aux(p, nullptr, nullptr);
-    return launch_range(sim, p, 0, sim->num_envs, (cudaStream_t)stream);
+    if (int rc = invalidate_prepared(sim, (cudaStream_t)stream)) return rc;
+    if (int rc = launch_range(sim, p, 0, sim->num_envs, (cudaStream_t)stream)) return rc;
+    return launch_prepare(sim, (cudaStream_t)stream);
 }
 
 extern "C" int mate_b200_step(MateSim* sim, const float* cam_act, const float* tgt_act, float* cam_obs,
@@ -315,7 +411,11 @@ extern "C" int mate_b200_step(MateSim* sim, const float* cam_act, const float* t
     p.mode = MODE_STEP; p.flags = flags; p.seed = sim->seed;
     p.cam_act = cam_act; p.tgt_act = tgt_act; p.cam_obs = cam_obs; p.tgt_obs = tgt_obs; p.rewards = rewards; p.done = done;
     fill_aux(p, aux, replay);
-    return launch_range(sim, p, 0, sim->num_envs, (cudaStream_t)stream);
+    if (int rc = launch_range(sim, p, 0, sim->num_envs, (cudaStream_t)stream)) return rc;
+    if ((flags & MATE_STEP_AUTO_RESET) && sim->refill_mode &&
+        (sim->refill_mode == 2 || ++sim->steps_since_refill >= sim->refill_period))
+        return launch_prepare(sim, (cudaStream_t)stream);
+    return MATE_OK;
 }
 
 extern "C" int mate_b200_observe(MateSim* sim, float* cam_obs, float* tgt_obs, const MateStepAux* aux,
@@ -457,6 +557,7 @@ extern "C" int mate_b200_set_state(MateSim* sim, const MateStateView* v) {
     if (!sim || !v) return fail(MATE_EINVAL, "null argument");
     CUDA_TRY(cudaSetDevice(sim->device));
     CUDA_TRY(cudaDeviceSynchronize());
+    if (sim->refill_mode) CUDA_TRY(cudaMemset(sim->base.ready, 0, sizeof(uint32_t) * sim->bpad));   // prepared episodes may no longer match
     const int nc = sim->cfg.num_cameras, nt = sim->cfg.num_targets, no = sim->cfg.num_obstacles;
     const size_t bp = sim->bpad, B = sim->num_envs;
     const Params& p = sim->base;
@@ -531,7 +632,7 @@ extern "C" int mate_b200_set_state(MateSim* sim, const MateStateView* v) {
         }
         if (upload(cargo, p.cargo) || upload(ea, p.env_a) || upload(eb, p.env_b)) return MATE_ECUDA;
     }
-    return MATE_OK;
+    return launch_prepare(sim, nullptr);   // prepare the next episodes of the new state right away
 }
 
 extern "C" int mate_b200_episode_stats(MateSim* sim, float* out16, int32_t reset_after, void* stream) {

@@ -17,7 +17,7 @@ constexpr double kRad2Deg = 57.295779513082320876798154814105;
 constexpr double kDeg2Rad = 0.017453292519943295769236907684886;
 constexpr int kResetRetries = 500;           // mate/environment.py:53
 
-enum Mode : int { MODE_STEP = 0, MODE_OBSERVE = 1, MODE_RESET = 2 };
+enum Mode : int { MODE_STEP = 0, MODE_OBSERVE = 1, MODE_RESET = 2, MODE_PREPARE = 3 };
 
 enum Stream : uint32_t {
     STREAM_SHUFFLE_CAM = 0, STREAM_SHUFFLE_TGT = 1, STREAM_SHUFFLE_OBS = 2, STREAM_CAPACITY = 3,
@@ -49,6 +49,13 @@ struct Params {
     int4* env_b;       // [bpad] x: episode reward, y: delayed episode reward, z: coverage_sum (float bits), w: episode_id
     unsigned long long* cc_clear;   // [bpad] per-episode cache: bit 63 valid, bit (8 j + c) = camera c has a clear line of sight to camera j
     float* stats;      // [16] episode statistics accumulators
+    // --- prepared next episodes (mate_step.cuh, "prepared resets"): a second state block holds, per env, the
+    //     complete initial state of its NEXT episode; auto-reset adopts it instead of running the reset ---
+    uint32_t* masks;          // [R * MW][bpad] observer mask words of the initial view (filled by MODE_PREPARE in the second block)
+    float* vals;              // [3 NT + 5 NC][bpad] fp32 entity entries of the initial state (same, second block only)
+    uint32_t* ready;          // [bpad] episode id the prepared state of an env is valid for (0 = none)
+    const int4* live_env_b;   // MODE_PREPARE: env_b of the live state (current episode ids)
+    const Params* next;       // MODE_STEP: device copy of the parameter block that addresses the second state block (nullptr = none)
     // --- per-call I/O (device) ---
     const float* cam_act; const float* tgt_act;
     float* cam_obs; float* tgt_obs; float* rewards; uint8_t* done;

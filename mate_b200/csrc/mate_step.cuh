@@ -57,9 +57,9 @@ struct Shape2 {
     // they fit, obstacles (bits 16-31); otherwise obstacles take a second word
     static constexpr int MW = NO <= 16 ? 1 : 2;
     static constexpr int MSTRIDE = (R * MW) | 1;               // odd stride: lane-per-env access is conflict free
-    // fp32 values per environment: targets {x, y, packed state}, cameras {x, y, theta, Rs, cos phi, sin phi,
-    // cos^2(theta/2)} (the observation packer and the fp32 prefilters read the same entries)
-    static constexpr int CV = 7;
+    // fp32 values per environment: targets {x, y, packed state}, cameras {x, y, theta, Rs cos phi, Rs sin phi}
+    // (the observation packer and the fp32 prefilters read the same entries)
+    static constexpr int CV = 5;
     static constexpr int V_T = 0, V_C = 3 * NT, VN = 3 * NT + CV * NC;
     static constexpr int VSTRIDE = VN | 1;
     static constexpr int STAGE_CAM = ((CAM_ROW + 3) / 4) * 4;
@@ -70,7 +70,7 @@ struct Shape2 {
     static constexpr int ENVS_PER_CTA = WARPS * 32;
     static constexpr int QCAP = 64;
     static constexpr int OFF_STAGE = 0;
-    static constexpr int OFF_MASK = OFF_STAGE + (STAGE_FLOATS + 8) * 4;   // + a dummy slot for inactive lanes
+    static constexpr int OFF_MASK = OFF_STAGE + STAGE_FLOATS * 4;
     static constexpr int OFF_VAL = OFF_MASK + 32 * MSTRIDE * 4;
     static constexpr int OFF_Q = OFF_VAL + 32 * VSTRIDE * 4;
     static constexpr int OFF_Q2 = OFF_Q + QCAP * 2;             // second queue: pairs that need the exact polyline
@@ -98,15 +98,17 @@ __device__ __noinline__ int fov_reach_global(const Params& p, int er, int c, con
     return fov_reach_exact(p.cam_x[i], p.cam_y[i], p.cam_phi[i], theta, sqrt(p.cam_area_product / theta), *qx, *qy);
 }
 
-// fp32 prefilter of the same test: 0 = no, 1 = yes, 2 = inside the guard band (ask the fp64 version)
-__device__ __forceinline__ int fov_reach32(float cx, float cy, float rs2, float cs, float sn, float ch2, float qx, float qy) {
+// fp32 prefilter of the same test: 0 = no, 1 = yes, 2 = inside the guard band (ask the fp64 version).
+// (hx, hy) = Rs (cos phi, sin phi) is the heading scaled by the sensing radius, rs2 = Rs^2, ch2 = cos^2(theta/2);
+// every term of the sector test is scaled by Rs^2, which leaves the decisions unchanged.
+__device__ __forceinline__ int fov_reach32(float cx, float cy, float rs2, float hx, float hy, float ch2, float qx, float qy) {
     const float relx = qx - cx, rely = qy - cy;
     const float d2 = relx * relx + rely * rely;
     if (d2 > rs2 * (1.0f + 4e-5f)) return 0;
-    const float dot = relx * cs + rely * sn;
+    const float dot = relx * hx + rely * hy;
     const float sq = dot >= 0.0f ? dot * dot : -(dot * dot);
-    const float diff = sq - d2 * ch2;             // >= 0  <=>  angle(rel, heading) <= theta / 2
-    const float band = 4e-5f * d2 + 1e-3f;
+    const float diff = sq - d2 * ch2 * rs2;       // >= 0  <=>  angle(rel, heading) <= theta / 2
+    const float band = (4e-5f * d2 + 1e-3f) * rs2;
     if (diff < -band) return 0;
     if (diff > band && d2 < rs2 * (1.0f - 4e-5f)) return 1;
     return 2;
@@ -295,8 +297,7 @@ __device__ __forceinline__ void store_camera(float* v, double x, double y, doubl
     const double rs = sqrt(area_product / theta);
     double sn, cs;
     sincospi(phi * (1.0 / 180.0), &sn, &cs);
-    const float ch = cospif((float)theta * (1.0f / 360.0f));
-    v[0] = (float)x; v[1] = (float)y; v[2] = (float)theta; v[3] = (float)rs; v[4] = (float)cs; v[5] = (float)sn; v[6] = ch * ch;
+    v[0] = (float)x; v[1] = (float)y; v[2] = (float)theta; v[3] = (float)(rs * cs); v[4] = (float)(rs * sn);
 }
 
 // ---- guard-band resolution (rare): the fp32 test fell inside its band, the fp64 expression decides.
@@ -349,6 +350,113 @@ __device__ __noinline__ void process_exact(const Params& p, int env0, uint32_t* 
     if (sees) atomicOr(&mk[src * S::MSTRIDE + c * S::MW], bit_tgt(t));
 }
 
+// Prepared resets.  MultiAgentTracking.reset costs tens of thousands of dependent instructions for ONE lane
+// (rejection placement, cargo table, camera lines of sight, first view) while the other 31 lanes of the
+// warp wait, and the launch ends with its slowest warp.  A reset depends only on (seed, env, episode id),
+// so it is computed ahead of time: mate_step_kernel2 in MODE_PREPARE runs on a second state block (its
+// Params address that block) for every env whose prepared state is not valid for episode id + 1, on a side
+// stream, off the step path.  When an episode ends, the step kernel checks the `ready` tag and simply
+// copies the prepared state and first-view masks; if the tag does not match it runs the reset in place
+// (identical result, same counter-based draws).
+__device__ __forceinline__ uint32_t ld_acquire_u32(const uint32_t* ptr) {
+    uint32_t v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ptr) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_u32(uint32_t* ptr, uint32_t v) {
+    asm volatile("st.release.gpu.global.u32 [%0], %1;" :: "l"(ptr), "r"(v) : "memory");
+}
+
+// The time limit announces a reset one step ahead: pull the prepared state of env e into L2 now, so that the
+// copy in the next step does not pay one DRAM round trip per group of loads.
+template <int NC, int NT, int NO, class S>
+__device__ __noinline__ void prefetch_prepared(const Params& nx, int e) {
+    const size_t bp = nx.bpad;
+    // evict_last: 450 MB of observation rows stream through the L2 before the copy reads these lines
+    auto pf = [](const void* ptr) { asm volatile("prefetch.global.L2::evict_last [%0];" :: "l"(ptr)); };
+    pf(nx.ready + e);
+#pragma unroll 1
+    for (int c = 0; c < NC; ++c) { const size_t i = (size_t)c * bp + e; pf(nx.cam_x + i); pf(nx.cam_y + i); pf(nx.cam_phi + i); pf(nx.cam_theta + i); }
+#pragma unroll 1
+    for (int t = 0; t < NT; ++t) { const size_t i = (size_t)t * bp + e; pf(nx.tgt_x + i); pf(nx.tgt_y + i); }
+#pragma unroll 1
+    for (int k = 0; k < S::VN; ++k) pf(nx.vals + (size_t)k * bp + e);
+#pragma unroll 1
+    for (int o = 0; o < NO; ++o) { const size_t i = (size_t)o * bp + e; pf(nx.obs_x + i); pf(nx.obs_y + i); pf(nx.obs_r + i); pf(nx.obs_f4 + i); }
+#pragma unroll 1
+    for (int w = 0; w < S::R * S::MW; ++w) pf(nx.masks + (size_t)w * bp + e);
+    pf(nx.cargo + e); pf(nx.cargo + bp + e); pf(nx.env_a + e); pf(nx.cc_clear + e);
+}
+
+// copy the prepared initial state of env e from block `nx` into the live block `p`, the fp32 entries and
+// the first-view masks into shared memory; cargo / line-of-sight cache are returned
+template <int NC, int NT, int NO, class S>
+__device__ __noinline__ void adopt_prepared(const Params& p, const Params& nx, int e, float* myval, uint32_t* mymk,
+                                            Cargo* cargo, unsigned long long* ccw) {
+    // One lane copies ~90 scattered words that nobody has touched for a whole episode (DRAM latency each):
+    // the loads of a group are all issued before the first one is used.
+    const size_t bp = p.bpad;
+    const double* const ncx = nx.cam_x + e; const double* const ncy = nx.cam_y + e;
+    const double* const nph = nx.cam_phi + e; const double* const nth = nx.cam_theta + e;
+    const double* const ntx = nx.tgt_x + e; const double* const nty = nx.tgt_y + e;
+    const double* const nox = nx.obs_x + e; const double* const noy = nx.obs_y + e; const double* const nor = nx.obs_r + e;
+    const float4* const nof = nx.obs_f4 + e;
+    const uint32_t* const nmk = nx.masks + e;
+    const uint4 c0 = nx.cargo[e], c1 = nx.cargo[bp + e], ea = nx.env_a[e];
+    const unsigned long long cc = NC >= 2 ? nx.cc_clear[e] : 0ull;
+    // group 1: masks, cargo (above), cameras, targets
+    uint32_t mw[S::R * S::MW];
+#pragma unroll
+    for (int w = 0; w < S::R * S::MW; ++w) mw[w] = nmk[(size_t)w * bp];
+    {
+        double cx[NC > 0 ? NC : 1], cy[NC > 0 ? NC : 1], ph[NC > 0 ? NC : 1], th[NC > 0 ? NC : 1], tx[NT], ty[NT];
+#pragma unroll
+        for (int c = 0; c < NC; ++c) { cx[c] = ncx[(size_t)c * bp]; cy[c] = ncy[(size_t)c * bp]; ph[c] = nph[(size_t)c * bp]; th[c] = nth[(size_t)c * bp]; }
+#pragma unroll
+        for (int t = 0; t < NT; ++t) { tx[t] = ntx[(size_t)t * bp]; ty[t] = nty[(size_t)t * bp]; }
+#pragma unroll
+        for (int c = 0; c < NC; ++c) {
+            const size_t i = (size_t)c * bp + e;
+            p.cam_x[i] = cx[c]; p.cam_y[i] = cy[c]; p.cam_phi[i] = ph[c]; p.cam_theta[i] = th[c];
+        }
+#pragma unroll
+        for (int t = 0; t < NT; ++t) {
+            const size_t i = (size_t)t * bp + e;
+            p.tgt_x[i] = tx[t]; p.tgt_y[i] = ty[t];
+        }
+    }
+    {   // group 2: fp32 entity entries (targets incl. their packed state, cameras incl. the derived heading)
+        const float* const nv = nx.vals + e;
+        float f[S::VN];
+#pragma unroll
+        for (int k = 0; k < S::VN; ++k) f[k] = nv[(size_t)k * bp];
+#pragma unroll
+        for (int k = 0; k < S::VN; ++k) myval[k] = f[k];
+    }
+    constexpr int OB = 12;   // group 3 (+): obstacles, 12 at a time
+#pragma unroll 1
+    for (int o0 = 0; o0 < NO; o0 += OB) {
+        double x[OB], y[OB], r[OB]; float4 f[OB];
+#pragma unroll
+        for (int k = 0; k < OB; ++k) if (o0 + k < NO) {
+            const size_t i = (size_t)(o0 + k) * bp;
+            x[k] = nox[i]; y[k] = noy[i]; r[k] = nor[i]; f[k] = nof[i];
+        }
+#pragma unroll
+        for (int k = 0; k < OB; ++k) if (o0 + k < NO) {
+            const size_t i = (size_t)(o0 + k) * bp + e;
+            p.obs_x[i] = x[k]; p.obs_y[i] = y[k]; p.obs_r[i] = r[k]; p.obs_f4[i] = f[k];
+        }
+    }
+#pragma unroll
+    for (int w = 0; w < S::R * S::MW; ++w) mymk[w] = mw[w];
+    cargo->rem[0] = c0.x; cargo->rem[1] = c0.y; cargo->rem[2] = c0.z; cargo->rem[3] = c0.w;
+    cargo->rem[4] = c1.x; cargo->rem[5] = c1.y; cargo->rem[6] = c1.z; cargo->rem[7] = c1.w;
+    cargo->aw[0] = ea.x; cargo->aw[1] = ea.y;
+    *ccw = cc;
+    if (NC >= 2) p.cc_clear[e] = cc;
+}
+
 // =============================================================================================
 // joint_observation (environment.py:908-983) for the warp's environments [env0, env0 + nvalid).
 // Out of line on purpose: the packer gets its own register allocation.
@@ -383,18 +491,19 @@ __device__ __noinline__ void pack_observations(const Params& p, const int env0, 
     // per-lane constants of the scatter, hoisted out of the environment loop: for every round the offset
     // of this lane's slot in the staged block (inactive lanes write to a dummy slot behind the block, so
     // the code is branch-free) and the mask word + bit that decide it
-    constexpr int DUMMY = S::STAGE_FLOATS;
+    constexpr int DUMMY = (S::OFF_Q - S::OFF_STAGE) / 4;   // the pair queues are idle while the rows are packed
     constexpr int NRND = RND_T + (NO > 0 ? RND_O : 0) + (NC > 0 ? RND_C : 0);
     const int t_idx = lane % NT, t_sub = lane / NT;
     const int o_idx = lane % NOX, o_sub = lane / NOX;
     const int c_idx = lane % NCX, c_sub = lane / NCX;
     auto row_base = [&](const int row) { return row < NC ? row * DC : S::STAGE_CAM + (row - NC) * DT; };
-    int q_off[NRND], m_idx[NRND];
+    float* q_ptr[NRND];   // this lane's slot in the staged block, per round
+    int m_idx[NRND];      // and the mask word that decides it
 #pragma unroll
     for (int rd = 0; rd < RND_T; ++rd) {
         const int row = rd * RPR_T + t_sub;
         const bool on = t_sub < RPR_T && row < R;
-        q_off[rd] = on ? row_base(row) + (row < NC ? C_TGT : T_TGT) + 5 * t_idx : DUMMY;
+        q_ptr[rd] = stage + (on ? row_base(row) + (row < NC ? C_TGT : T_TGT) + 5 * t_idx : DUMMY);
         m_idx[rd] = on ? row * MW : 0;
     }
     if (NO > 0) {
@@ -402,7 +511,7 @@ __device__ __noinline__ void pack_observations(const Params& p, const int env0, 
         for (int rd = 0; rd < RND_O; ++rd) {
             const int row = rd * RPR_O + o_sub;
             const bool on = o_sub < RPR_O && row < R;
-            q_off[RND_T + rd] = on ? row_base(row) + (row < NC ? C_OBS : T_OBS) + 4 * o_idx : DUMMY;
+            q_ptr[RND_T + rd] = stage + (on ? row_base(row) + (row < NC ? C_OBS : T_OBS) + 4 * o_idx : DUMMY);
             m_idx[RND_T + rd] = on ? row * MW + (MW - 1) : 0;
         }
     }
@@ -411,7 +520,7 @@ __device__ __noinline__ void pack_observations(const Params& p, const int env0, 
         for (int rd = 0; rd < RND_C; ++rd) {
             const int row = rd * RPR_C + c_sub;
             const bool on = c_sub < RPR_C && row < R;
-            q_off[NRND - RND_C + rd] = on ? row_base(row) + (row < NC ? C_CAM : T_CAM) + 7 * c_idx : DUMMY;
+            q_ptr[NRND - RND_C + rd] = stage + (on ? row_base(row) + (row < NC ? C_CAM : T_CAM) + 7 * c_idx : DUMMY);
             m_idx[NRND - RND_C + rd] = on ? row * MW : 0;
         }
     }
@@ -451,7 +560,7 @@ __device__ __noinline__ void pack_observations(const Params& p, const int env0, 
         float c0 = 0.f, c1 = 0.f, c3 = 0.f, c4 = 0.f, c5 = 0.f;
         if (NC > 0) {
             const float* cv = v + S::V_C + CV * c_idx;
-            c0 = cv[0]; c1 = cv[1]; c3 = cv[3] * cv[4]; c4 = cv[3] * cv[5]; c5 = cv[2];
+            c0 = cv[0]; c1 = cv[1]; c3 = cv[3]; c4 = cv[4]; c5 = cv[2];
         }
         float vt[RND_T][5], vo[NO > 0 ? RND_O : 1][4], vc[NC > 0 ? RND_C : 1][7];
 #pragma unroll
@@ -487,20 +596,20 @@ __device__ __noinline__ void pack_observations(const Params& p, const int env0, 
         }
 #pragma unroll
         for (int rd = 0; rd < RND_T; ++rd) {
-            float* q = stage + q_off[rd];
+            float* q = q_ptr[rd];
             q[0] = vt[rd][0]; q[1] = vt[rd][1]; q[2] = vt[rd][2]; q[3] = vt[rd][3]; q[4] = vt[rd][4];
         }
         if (NO > 0) {
 #pragma unroll
             for (int rd = 0; rd < RND_O; ++rd) {
-                float* q = stage + q_off[RND_T + rd];
+                float* q = q_ptr[RND_T + rd];
                 q[0] = vo[rd][0]; q[1] = vo[rd][1]; q[2] = vo[rd][2]; q[3] = vo[rd][3];
             }
         }
         if (NC > 0) {
 #pragma unroll
             for (int rd = 0; rd < RND_C; ++rd) {
-                float* q = stage + q_off[NRND - RND_C + rd];
+                float* q = q_ptr[NRND - RND_C + rd];
                 q[0] = vc[rd][0]; q[1] = vc[rd][1]; q[2] = vc[rd][2]; q[3] = vc[rd][3]; q[4] = vc[rd][4]; q[5] = vc[rd][5]; q[6] = vc[rd][6];
             }
         }
@@ -529,7 +638,7 @@ __device__ __noinline__ void pack_observations(const Params& p, const int env0, 
                 if (it * 32 + 32 <= NZ || k < NZ) {
                     const float4 x = src4[k];
                     float4* dst = (k < S::CAM_ROW / 4 ? cam4 : tgt4) + k;
-                    if (MATE2_STREAMING) __stcs(dst, x); else *dst = x;
+                    if (MATE2_STREAMING == 1) __stcs(dst, x); else if (MATE2_STREAMING == 2) __stcg(dst, x); else if (MATE2_STREAMING == 3) __stwt(dst, x); else *dst = x;
                 }
             }
             __syncwarp();
@@ -605,6 +714,14 @@ mate_step_kernel2(const __grid_constant__ Params p) {
     int ep_reward = eb.x, delayed_ep_reward = eb.y, episode_id = eb.w;
     float coverage_sum = __int_as_float(eb.z);
     bool cargo_loaded = false, cargo_dirty = false;
+    // MODE_PREPARE (this launch's Params address the second state block): the envs whose prepared state is
+    // not the one for their next episode are re-initialised here, everything else is left alone
+    bool need = false;
+    if (mode == MODE_PREPARE) {
+        episode_id = p.live_env_b[er].w;
+        need = env_ok && p.ready[e] != (uint32_t)(episode_id + 1);
+        if (!__any_sync(FULL, need)) return;
+    }
 
     // ------------------------------------------------------------------ _simulate (environment.py:1326-1354)
     {   // Camera.simulate (entities.py:347-360); the next camera's state is fetched while this one is derived
@@ -743,12 +860,24 @@ mate_step_kernel2(const __grid_constant__ Params p) {
 #pragma unroll 1
     for (int pass = 0; pass < 2; ++pass) {
         const bool do_reset = (pass == 0)
-            ? ((mode == MODE_RESET) && env_ok && (p.env_mask == nullptr || p.env_mask[e] != 0))
+            ? (mode == MODE_PREPARE ? need : ((mode == MODE_RESET) && env_ok && (p.env_mask == nullptr || p.env_mask[e] != 0)))
             : auto_reset_needed;
-        const bool view_active = (pass == 0) || do_reset;
+        // auto-reset: adopt the prepared state (and first view) of the next episode if it is ready
+        bool adopted = false;
+        if (do_reset && mode == MODE_STEP && p.next != nullptr && p.replay_transmit == nullptr && p.replay_choice == nullptr)
+            adopted = ld_acquire_u32(p.ready + e) == (uint32_t)(episode_id + 1);
+        const bool view_active = mode == MODE_PREPARE ? need : (((pass == 0) || do_reset) && !adopted);
         // ============================================================== reset (environment.py:679-775)
         if (__any_sync(FULL, do_reset)) {
-            if (do_reset) {
+            if (adopted) {
+                atomicAdd(&p.stats[6], 1.0f);   // auto-resets served from the prepared state
+                adopt_prepared<NC, NT, NO, S>(p, *p.next, e, myval, mymk, &cargo, &ccw);
+                cargo_loaded = true; cargo_dirty = true;
+                episode_id += 1; key.episode = (uint32_t)episode_id;
+                episode_step = 0; delivered = 0; ep_reward = 0; delayed_ep_reward = 0; coverage_sum = 0.f;
+                tdone_bits = 0; draw_step = 0;
+            } else if (do_reset) {
+                if (mode == MODE_STEP) atomicAdd(&p.stats[7], 1.0f);   // auto-resets computed in place
                 RngKey k2 = key;
                 k2.episode = (uint32_t)(episode_id + 1);
                 const uint32_t cap2 = reset_env_global<NC, NT, NO>(p, e, k2, &cargo);
@@ -851,7 +980,8 @@ mate_step_kernel2(const __grid_constant__ Params p) {
 #pragma unroll
             for (int c = 0; c < NC; ++c) {
                 const float* cv = mycam + CV * c;
-                const float rs = cv[3], rs2 = rs * rs, cs = cv[4], sn = cv[5], ch2 = cv[6];
+                const float cs = cv[3], sn = cv[4], rs2 = cs * cs + sn * sn;   // heading scaled by Rs
+                const float ch = cospif(cv[2] * (1.0f / 360.0f)), ch2 = ch * ch;
                 uint32_t reach_t = 0, band_t = 0, reach_c = 0, band_c = 0;
 #pragma unroll
                 for (int t = 0; t < NT; ++t) {
@@ -954,7 +1084,7 @@ mate_step_kernel2(const __grid_constant__ Params p) {
 
         // ============================================================== _assign_goals (environment.py:1271-1324)
         const bool step_goals = (pass == 0) && (mode == MODE_STEP);
-        const bool goals_active = step_goals || do_reset;
+        const bool goals_active = step_goals || (do_reset && !adopted);
         uint32_t tracked_bits = 0;
         {
             uint32_t any_c = 0;
@@ -1060,7 +1190,7 @@ mate_step_kernel2(const __grid_constant__ Params p) {
                 }
             }
             if (step_goals) { reward_i = r; delayed_i = delayed; }
-            if (do_reset) {
+            if (do_reset && !adopted) {
                 tdone_bits = 0; delivered = 0;   // environment.py:785-788
                 // targets_start_with_cargoes (environment.py:789-812): sequential over targets without a goal
                 if (p.start_with_cargoes) {
@@ -1102,7 +1232,7 @@ mate_step_kernel2(const __grid_constant__ Params p) {
             }
         }
         // coverage statistics of the current view (environment.py:966-972)
-        if (view_active || goals_active) {
+        if (view_active || goals_active || adopted) {
             uint32_t wb_bits = 0;
 #pragma unroll
             for (int t = 0; t < NT; ++t) wb_bits |= (uint32_t)(tp_bounty(__float_as_uint(myval[S::V_T + 3 * t + 2])) > 0) << t;
@@ -1132,6 +1262,8 @@ mate_step_kernel2(const __grid_constant__ Params p) {
                 }
             }
             auto_reset_needed = env_ok && done && (p.flags & MATE_STEP_AUTO_RESET);
+            if (env_ok && !done && p.next != nullptr && (p.flags & MATE_STEP_AUTO_RESET) && episode_step == p.max_episode_steps)
+                prefetch_prepared<NC, NT, NO, S>(*p.next, e);   // the next step ends this episode (time limit)
         }
         // aux reflects the step just taken (before any auto-reset) / the observed or reset state
         if (p.has_aux && env_ok && (step_goals || mode != MODE_STEP)) {
@@ -1154,7 +1286,7 @@ mate_step_kernel2(const __grid_constant__ Params p) {
     if (mode == MODE_STEP && lane == 0) atomicAdd(&p.stats[5], (float)nvalid);
 
     // ------------------------------------------------------------------ write state back
-    if (env_ok && mode != MODE_OBSERVE) {
+    if (env_ok && mode != MODE_OBSERVE && (mode != MODE_PREPARE || need)) {
 #pragma unroll
         for (int t = 0; t < NT; ++t) p.tgt_pack[(size_t)t * bp + e] = __float_as_uint(myval[S::V_T + 3 * t + 2]);
         if (cargo_dirty) {
@@ -1163,6 +1295,17 @@ mate_step_kernel2(const __grid_constant__ Params p) {
         }
         p.env_a[e] = make_uint4(cargo.aw[0], cargo.aw[1], (uint32_t)episode_step, (uint32_t)delivered);
         p.env_b[e] = make_int4(ep_reward, delayed_ep_reward, __float_as_int(coverage_sum), episode_id);
+    }
+    if (mode == MODE_PREPARE) {   // first-view masks of the prepared episode, then publish the tag
+        if (need) {
+#pragma unroll 1
+            for (int w = 0; w < S::R * MW; ++w) p.masks[(size_t)w * bp + e] = mymk[w];
+#pragma unroll 1
+            for (int k = 0; k < S::VN; ++k) p.vals[(size_t)k * bp + e] = myval[k];
+            __threadfence();
+            st_release_u32(p.ready + e, (uint32_t)episode_id);
+        }
+        return;
     }
     __syncwarp();
 
