@@ -326,7 +326,7 @@ def main():
         'roofline': {
             'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
             'traffic': ncu_traffic_bytes(args.config.replace('.yaml', '')),
-            'kernel': ('mate_step_kernel<%d,%d,%d>' if os.environ.get('MATE_B200_KERNEL', '2')[:1] == '1' else 'mate_step_kernel2<%d,%d,%d>') % (nc, nt, no), 'algorithmic_bytes_per_env_step': A,
+            'kernel': 'mate_step_kernel2<%d,%d,%d>' % (nc, nt, no), 'algorithmic_bytes_per_env_step': A,
             'kernel_ms': kernel_ms, 'peak_source': peak_src,
         },
         'clocks': clocks.summary(),

@@ -1,7 +1,7 @@
 // mate_b200.cu -- host side of the C ABI declared in include/mate_b200.h.
 //
 // Owns the struct-of-arrays device state of one batch of environments and launches the
-// fused step kernel (mate_kernels.cuh).  No torch types, no CPU simulation fallback.
+// fused step kernel (mate_step.cuh).  No torch types, no CPU simulation fallback.
 #include <cuda_runtime.h>
 
 #include <cmath>
@@ -11,7 +11,6 @@
 #include <string>
 #include <vector>
 
-#include "mate_kernels.cuh"
 #include "mate_step.cuh"
 
 using namespace mate;
@@ -47,17 +46,6 @@ struct KernelInfo {
 };
 
 template <int NC, int NT, int NO>
-static void launch_shape(const Params& p, int grid, cudaStream_t stream) {
-    using S = Shape<NC, NT, NO>;
-    mate_step_kernel<NC, NT, NO><<<grid, S::WARPS * 32, S::SMEM_BYTES, stream>>>(p);
-}
-template <int NC, int NT, int NO>
-static cudaError_t prepare_shape() {
-    using S = Shape<NC, NT, NO>;
-    return cudaFuncSetAttribute(mate_step_kernel<NC, NT, NO>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::SMEM_BYTES);
-}
-
-template <int NC, int NT, int NO>
 static void launch_shape2(const Params& p, int grid, cudaStream_t stream) {
     using S = Shape2<NC, NT, NO>;
     mate_step_kernel2<NC, NT, NO><<<grid, S::WARPS * 32, S::SMEM_BYTES, stream>>>(p);
@@ -68,31 +56,12 @@ static cudaError_t prepare_shape2() {
     return cudaFuncSetAttribute(mate_step_kernel2<NC, NT, NO>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::SMEM_BYTES);
 }
 
-// MATE_B200_KERNEL=1 selects the first-generation kernel (group of lanes per environment), kept
-// for A/B measurements; the default is the lane-per-environment kernel of mate_step.cuh.
-static bool use_first_generation() {
-    const char* v = getenv("MATE_B200_KERNEL");
-    return v && v[0] == '1';
-}
-
 static bool find_kernel(int nc, int nt, int no, KernelInfo* out) {
-    if (!use_first_generation()) {
-#define X(NC, NT, NO)                                                                          \
-        if (nc == NC && nt == NT && no == NO) {                                                \
-            using S = Shape2<NC, NT, NO>;                                                      \
-            *out = KernelInfo{&launch_shape2<NC, NT, NO>, S::ENVS_PER_CTA, S::SMEM_BYTES, S::DC, S::DT, \
-                              32, &prepare_shape2<NC, NT, NO>};                                \
-            return true;                                                                       \
-        }
-        MATE_SHAPES(X)
-#undef X
-        return false;
-    }
 #define X(NC, NT, NO)                                                                          \
     if (nc == NC && nt == NT && no == NO) {                                                    \
-        using S = Shape<NC, NT, NO>;                                                           \
-        *out = KernelInfo{&launch_shape<NC, NT, NO>, S::ENVS_PER_CTA, S::SMEM_BYTES, S::DC, S::DT, \
-                          S::EPW, &prepare_shape<NC, NT, NO>};                                 \
+        using S = Shape2<NC, NT, NO>;                                                          \
+        *out = KernelInfo{&launch_shape2<NC, NT, NO>, S::ENVS_PER_CTA, S::SMEM_BYTES, S::DC, S::DT, \
+                          32, &prepare_shape2<NC, NT, NO>};                                    \
         return true;                                                                           \
     }
     MATE_SHAPES(X)
@@ -200,7 +169,7 @@ extern "C" int mate_b200_create(const MateConfig* cfg, int32_t num_envs, int32_t
     p.stats = (float*)(b + o_stats);
 
     // prepared resets: a second state block of the same layout + first-view masks + the ready tags
-    sim->refill_mode = use_first_generation() ? 0 : 1;
+    sim->refill_mode = 1;
     if (const char* v = getenv("MATE_B200_REFILL")) {
         if (!strcmp(v, "0") || !strcmp(v, "off")) sim->refill_mode = 0;
         else if (!strcmp(v, "sync")) sim->refill_mode = sim->refill_mode ? 2 : 0;

@@ -163,8 +163,8 @@ struct Cargo {
 
 // =============================================================================================
 // Obstacle.obstruct(ray, keep_tangential=True) for target motion (mate/entities.py:158-184).
-// (vx, vy) is the step vector with cached norm n (n < 0 => recompute), cached angle `ang`
-// (valid if has_ang), origin (ox, oy); disc centre (px, py), radius R.
+// (vx, vy) is the step vector with cached norm n (valid if has_n), origin (ox, oy); disc centre
+// (px, py), radius R.
 // =============================================================================================
 struct StepVec { double vx, vy, n, ang, bound; bool has_n, has_ang; };   // bound >= |v| for the cheap reject
 
@@ -337,26 +337,6 @@ __device__ __noinline__ int fov_reach_exact(double cx, double cy, double phi, do
     return 1;
 }
 
-// The same two tests decided in fp32 on squares / dot products (no sqrt, no atan2).  fp32
-// coordinates carry <= 6e-5 absolute error, i.e. <= 1e-5 relative on these quantities; only when
-// a test falls inside a 4e-5 relative band around its boundary is the exact fp64 expression of
-// the reference evaluated (C = fp64 camera block {x, y, phi, theta, rs, ...}).
-// F = fp32 camera block {x, y, rs^2, cos phi, sin phi, cos^2(theta/2)}.
-__device__ __forceinline__ int fov_reach(const float* __restrict__ F, const double* __restrict__ C,
-                                         float fqx, float fqy, double qx, double qy) {
-    const float relx = fqx - F[0], rely = fqy - F[1];
-    const float d2 = relx * relx + rely * rely;
-    const float rs2 = F[2];
-    if (d2 > rs2 * (1.0f + 4e-5f)) return 0;
-    const float dot = relx * F[3] + rely * F[4];
-    const float sq = dot >= 0.0f ? dot * dot : -(dot * dot);
-    const float diff = sq - d2 * F[5];           // >= 0  <=>  angle(rel, heading) <= theta / 2
-    const float band = 4e-5f * d2 + 1e-3f;
-    if (diff < -band) return 0;
-    if (diff > band && d2 < rs2 * (1.0f - 4e-5f)) return 1;
-    return fov_reach_exact(C[0], C[1], C[2], C[3], C[4], qx, qy);
-}
-
 // Conservative occlusion classification of the query point q = cam + rel against all obstacle
 // discs, WITHOUT evaluating the sampled polyline.  Both polyline samples that bracket the query
 // bearing lie inside a fan of +-1.05 degrees around it (integer-degree grid).  Per disc, with
@@ -422,17 +402,6 @@ __device__ __noinline__ bool occlusion_exact(const ObsRef ob, double cx, double 
 // =============================================================================================
 // Rare paths, kept out of line so that the hot path stays inside the instruction cache
 // =============================================================================================
-
-// C = {x, y, phi, theta, rs, rs^2, cos phi, sin phi, cos^2(theta/2)}
-__device__ __noinline__ void camera_derive(double* C, double area_product) {
-    const double rs = sqrt(area_product / C[3]);      // entities.py:334,360
-    C[4] = rs; C[5] = rs * rs;
-    double sn, cs;
-    sincospi(C[2] * (1.0 / 180.0), &sn, &cs);
-    C[6] = cs; C[7] = sn;
-    const double ch = cospi(C[3] * (1.0 / 360.0));
-    C[8] = ch * ch;
-}
 
 struct ResetCfg {
     double cam_radius, cam_min_view, cam_rot_step, cam_area_product, tgt_step_size, obs_r_low, obs_r_high;
