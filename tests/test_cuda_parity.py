@@ -228,6 +228,45 @@ def test_step_host_matches_device_step():
         assert torch.equal(rew.cpu(), out[2]) and torch.equal(done.cpu(), out[3])
 
 
+@pytest.mark.parametrize('preset,overrides', [('MATE-4v8-9.yaml', {'max_episode_steps': 9}),
+                                              ('MATE-Navigation.yaml', {'max_episode_steps': 7}),
+                                              ('MATE-2v4-9.yaml', {'max_episode_steps': 1})])
+def test_prepared_resets_equal_resets_in_place(preset, overrides, monkeypatch):
+    """Auto-reset through the prepared next-episode state (MATE_B200_REFILL=sync: prepared after every
+    step, so always adopted) gives bit-identical observations, rewards, done flags and state to the reset
+    computed in place (MATE_B200_REFILL=0), and both paths are really taken."""
+    from mate_b200.config import flatten_config, read_config
+
+    cfg = flatten_config(read_config(preset, **overrides))
+    nc, nt = cfg['num_cameras'], cfg['num_targets']
+    B = 200
+    monkeypatch.setenv('MATE_B200_REFILL', 'sync')
+    a = _sim(cfg, B)
+    monkeypatch.setenv('MATE_B200_REFILL', '0')
+    b = _sim(cfg, B)
+    a.reset(seed=11)
+    b.reset(seed=11)
+    rng = np.random.RandomState(3)
+    for k in range(40):
+        cam_act = torch.from_numpy((rng.uniform(-1, 1, (B, nc, 2)) * [cfg['camera_rotation_step'], cfg['camera_zooming_step']]).astype(np.float32)).cuda()
+        tgt_act = torch.from_numpy((rng.uniform(-1, 1, (B, nt, 2)) * cfg['target_step_size']).astype(np.float32)).cuda()
+        (cam_a, tgt_a), rew_a, done_a = a.step(cam_act, tgt_act, auto_reset=True)
+        (cam_b, tgt_b), rew_b, done_b = b.step(cam_act, tgt_act, auto_reset=True)
+        assert torch.equal(tgt_a, tgt_b) and torch.equal(rew_a, rew_b) and torch.equal(done_a, done_b), k
+        if nc:
+            assert torch.equal(cam_a, cam_b), k
+    sa, sb = a.get_state(), b.get_state()
+    for key in sa:
+        assert (sa[key] == sb[key]).all(), key
+    stats_a, stats_b = _np(a.episode_stats()), _np(b.episode_stats())
+    assert stats_a[0] == stats_b[0] > 0
+    if overrides['max_episode_steps'] > 1:
+        assert stats_a[6] == stats_a[0] and stats_a[7] == 0      # every reset adopted the prepared state
+    else:
+        assert stats_a[6] + stats_a[7] == stats_a[0] and stats_a[6] > 0   # two-step episodes: both paths, same results
+    assert stats_b[7] == stats_b[0] and stats_b[6] == 0          # every reset computed in place
+
+
 def test_invalid_shape_and_alignment_errors():
     from mate_b200.config import flatten_config, read_config
 
