@@ -184,6 +184,32 @@ int mate_b200_set_state(MateSim* sim, const MateStateView* view);
  * all-reduce of this vector is done by the caller (torch.distributed / NCCL). */
 int mate_b200_episode_stats(MateSim* sim, float* out16, int32_t reset_after, void* stream);
 
+/* The reference's observation wrappers applied IN PLACE to the joint observations of the current state, in
+ * the given order, in one pass over the tensors:
+ *   MATE_OBS_ENHANCED_CAMERA / _TARGET  EnhancedObservation.observation, mate/wrappers/enhanced_observation.py:72-123
+ *   MATE_OBS_SHARED_CAMERA / _TARGET    SharedFieldOfView.observation,   mate/wrappers/shared_field_of_view.py:74-145
+ *   MATE_OBS_RELATIVE                   convert_coordinates,  mate/agents/utils.py:40-94  (RelativeCoordinates)
+ *   MATE_OBS_RESCALED                   normalize_observation, mate/agents/utils.py:97-127 (RescaledObservation)
+ * `ops` is a HOST array of num_ops <= MATE_MAX_OBS_OPS codes.  cam_affine [Dc][2] / tgt_affine [Dt][2] are dev
+ * arrays of (scale, shift) per observation column, needed (non-NULL) only with MATE_OBS_RESCALED.  cam_obs /
+ * tgt_obs must hold the observations the last step/reset/observe call wrote for this handle. */
+#define MATE_OBS_ENHANCED_CAMERA 1
+#define MATE_OBS_ENHANCED_TARGET 2
+#define MATE_OBS_SHARED_CAMERA 3
+#define MATE_OBS_SHARED_TARGET 4
+#define MATE_OBS_RELATIVE 5
+#define MATE_OBS_RESCALED 6
+#define MATE_MAX_OBS_OPS 8
+int mate_b200_transform_observations(MateSim* sim, float* cam_obs, float* tgt_obs, const int32_t* ops,
+                                     int32_t num_ops, const float* cam_affine, const float* tgt_affine,
+                                     void* stream);
+
+/* DiscreteCamera / DiscreteTarget.action (mate/wrappers/discrete_action_spaces.py:98-117, 204-228): grid
+ * indices (dev int64 [count]) -> continuous actions (dev float32 [count][2]) through the wrapper's table
+ * (dev float32 [table_size][2]). */
+int mate_b200_decode_actions(const int64_t* index, const float* table, int32_t table_size, float* out,
+                             int64_t count, void* stream);
+
 /* Number of kernels this handle has launched since creation (bench bookkeeping). */
 int64_t mate_b200_launch_count(const MateSim* sim);
 

@@ -64,7 +64,16 @@ register('MATE-Navigation-v0', make_environment, {'config': 'MATE-Navigation.yam
 del _nc, _nt, _no
 
 
+_WRAPPERS = ('EnhancedObservation', 'SharedFieldOfView', 'RelativeCoordinates', 'RescaledObservation',
+             'DiscreteCamera', 'DiscreteTarget', 'RepeatedRewardIndividualDone')
+
+
 def __getattr__(name):
+    if name in _WRAPPERS or name == 'wrappers':   # lazy for the same reason as below
+        import importlib  # pylint: disable=import-outside-toplevel
+
+        module = importlib.import_module('mate_b200.wrappers')
+        return module if name == 'wrappers' else getattr(module, name)
     if name == 'MultiAgentTracking':   # lazy: importing torch is slow and not needed for config work
         from mate_b200.environment import MultiAgentTracking  # pylint: disable=import-outside-toplevel
 

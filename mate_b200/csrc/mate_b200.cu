@@ -12,6 +12,7 @@
 #include <vector>
 
 #include "mate_step.cuh"
+#include "mate_wrappers.cuh"
 
 using namespace mate;
 
@@ -40,6 +41,8 @@ static int fail(int code, const std::string& msg) {
 #endif
 
 struct KernelInfo {
+    void (*launch_wrappers)(const Params&, const ObsOps&, const float*, const float*, int num_envs, cudaStream_t);
+    cudaError_t (*prepare_wrappers)();
     void (*launch)(const Params&, int grid, cudaStream_t);
     int envs_per_cta, smem_bytes, dc, dt, epw;
     cudaError_t (*prepare)();
@@ -56,11 +59,25 @@ static cudaError_t prepare_shape2() {
     return cudaFuncSetAttribute(mate_step_kernel2<NC, NT, NO>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::SMEM_BYTES);
 }
 
+template <int NC, int NT, int NO>
+static void launch_wrappers_shape(const Params& p, const ObsOps& ops, const float* cam_affine, const float* tgt_affine,
+                                  int num_envs, cudaStream_t stream) {
+    using W = WShape<NC, NT, NO>;
+    const int grid = (num_envs + W::WARPS - 1) / W::WARPS;
+    obs_transform_kernel<NC, NT, NO><<<grid, W::WARPS * 32, W::SMEM_BYTES, stream>>>(p, ops, cam_affine, tgt_affine);
+}
+template <int NC, int NT, int NO>
+static cudaError_t prepare_wrappers_shape() {
+    return cudaFuncSetAttribute(obs_transform_kernel<NC, NT, NO>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                WShape<NC, NT, NO>::SMEM_BYTES);
+}
+
 static bool find_kernel(int nc, int nt, int no, KernelInfo* out) {
 #define X(NC, NT, NO)                                                                          \
     if (nc == NC && nt == NT && no == NO) {                                                    \
         using S = Shape2<NC, NT, NO>;                                                          \
-        *out = KernelInfo{&launch_shape2<NC, NT, NO>, S::ENVS_PER_CTA, S::SMEM_BYTES, S::DC, S::DT, \
+        *out = KernelInfo{&launch_wrappers_shape<NC, NT, NO>, &prepare_wrappers_shape<NC, NT, NO>,       \
+                          &launch_shape2<NC, NT, NO>, S::ENVS_PER_CTA, S::SMEM_BYTES, S::DC, S::DT, \
                           32, &prepare_shape2<NC, NT, NO>};                                    \
         return true;                                                                           \
     }
@@ -132,6 +149,7 @@ extern "C" int mate_b200_create(const MateConfig* cfg, int32_t num_envs, int32_t
 
     CUDA_TRY(cudaSetDevice(device));
     CUDA_TRY(kernel.prepare());
+    CUDA_TRY(kernel.prepare_wrappers());
     MateSim* sim = new MateSim();
     sim->cfg = *cfg;
     sim->cfg.camera_location_ranges = sim->cfg.target_location_ranges = sim->cfg.obstacle_location_ranges = nullptr;
@@ -274,6 +292,42 @@ extern "C" int mate_b200_obs_dims(const MateSim* sim, int32_t* cam_dim, int32_t*
 }
 
 extern "C" int64_t mate_b200_launch_count(const MateSim* sim) { return sim ? sim->launches : 0; }
+
+extern "C" int mate_b200_transform_observations(MateSim* sim, float* cam_obs, float* tgt_obs, const int32_t* ops,
+                                                int32_t num_ops, const float* cam_affine, const float* tgt_affine,
+                                                void* stream) {
+    if (!sim || !tgt_obs || (sim->cfg.num_cameras > 0 && !cam_obs) || (num_ops > 0 && !ops)) return fail(MATE_EINVAL, "null argument");
+    if (num_ops < 0 || num_ops > MATE_MAX_OBS_OPS) return fail(MATE_EINVAL, "too many observation wrappers (MATE_MAX_OBS_OPS)");
+    if (num_ops == 0) return MATE_OK;
+    if (((uintptr_t)cam_obs & 15) || ((uintptr_t)tgt_obs & 15)) return fail(MATE_EINVAL, "observation buffers must be 16-byte aligned");
+    ObsOps o{};
+    o.n = num_ops;
+    for (int i = 0; i < num_ops; ++i) {
+        if (ops[i] < MATE_OBS_ENHANCED_CAMERA || ops[i] > MATE_OBS_RESCALED) return fail(MATE_EINVAL, "unknown observation wrapper code");
+        if (ops[i] == MATE_OBS_RESCALED && (!tgt_affine || (sim->cfg.num_cameras > 0 && !cam_affine)))
+            return fail(MATE_EINVAL, "MATE_OBS_RESCALED needs the affine tables");
+        o.op[i] = ops[i];
+    }
+    CUDA_TRY(cudaSetDevice(sim->device));
+    Params p = sim->base;
+    p.cam_obs = cam_obs; p.tgt_obs = tgt_obs;
+    sim->kernel.launch_wrappers(p, o, cam_affine, tgt_affine, sim->num_envs, (cudaStream_t)stream);
+    sim->launches += 1;
+    cudaError_t err = cudaGetLastError();
+    if (err != cudaSuccess) return fail(MATE_ECUDA, std::string("wrapper kernel launch: ") + cudaGetErrorString(err));
+    return MATE_OK;
+}
+
+extern "C" int mate_b200_decode_actions(const int64_t* index, const float* table, int32_t table_size, float* out,
+                                        int64_t count, void* stream) {
+    if (!index || !table || !out || table_size <= 0 || count < 0) return fail(MATE_EINVAL, "bad argument");
+    if (count == 0) return MATE_OK;
+    if (((uintptr_t)out & 7) || ((uintptr_t)table & 7)) return fail(MATE_EINVAL, "action buffers must be 8-byte aligned");
+    decode_actions_kernel<<<(unsigned)((count + 255) / 256), 256, 0, (cudaStream_t)stream>>>(index, table, table_size, out, count);
+    cudaError_t err = cudaGetLastError();
+    if (err != cudaSuccess) return fail(MATE_ECUDA, std::string("decode launch: ") + cudaGetErrorString(err));
+    return MATE_OK;
+}
 
 // Launch the fused kernel over envs [begin, begin + count); I/O pointers are for env 0.
 static int launch_range(MateSim* sim, Params p, int begin, int count, cudaStream_t stream) {

@@ -1,0 +1,254 @@
+// mate_wrappers.cuh -- the reference's observation wrappers as ONE in-place pass over the joint
+// observation tensors.  Restated behaviour (reference root):
+//   mate/wrappers/enhanced_observation.py:72-123 (EnhancedObservation.observation),
+//   mate/wrappers/shared_field_of_view.py:74-145 (SharedFieldOfView.observation),
+//   mate/agents/utils.py:40-94 (convert_coordinates, used by RelativeCoordinates),
+//   mate/agents/utils.py:97-127 (normalize_observation, used by RescaledObservation).
+//
+// The reference applies each wrapper as NumPy slicing on the [N, D] joint observation of ONE environment.
+// Here a warp loads the 6 KB block of one environment into shared memory (16-byte coalesced loads),
+// applies the requested wrappers in the reference's order, lanes = (observer row, entity slot) pairs, and
+// stores the block back: one read and one write of the observation tensors whatever the number of
+// stacked wrappers.  The kernel is HBM bound (2 x 407 MB for MATE-4v8-9 x 65 536).
+#pragma once
+
+#include <type_traits>
+
+#include "mate_common.cuh"
+
+namespace mate {
+
+constexpr int kMaxObsOps = 8;
+struct ObsOps { int n; int op[kMaxObsOps]; };
+
+template <int NC, int NT, int NO>
+struct WShape {
+    static constexpr int DC = 22 + 5 * NT + 4 * NO + 7 * NC, DT = 27 + 7 * NC + 4 * NO + 5 * NT;
+    static constexpr int CAM_ROW = NC * DC, TGT_ROW = NT * DT;
+    static constexpr int BLOCK = CAM_ROW + TGT_ROW;            // floats per environment
+    static constexpr int E = NT + NO + NC;                     // entity slots per observer row
+    static constexpr int R = NC + NT;
+    static constexpr int SCR = 4 * (NO > 0 ? NO : 1) + 2 * E + 8 + 4 * E + 2;   // obstacle entries, shared masks, shared empty bits, fp64 locations
+    static constexpr int WARP_FLOATS = ((BLOCK + SCR + 3) / 4) * 4;
+    static constexpr int WARPS = 4;
+    static constexpr int SMEM_BYTES = (WARPS * WARP_FLOATS + 2 * (DC + DT)) * 4;
+    static constexpr bool VEC = (CAM_ROW % 4 == 0) && (TGT_ROW % 4 == 0);
+};
+
+// slot k of an observer row: kind 0 = target, 1 = obstacle, 2 = camera; camera rows list targets,
+// obstacles, cameras; target rows list cameras, obstacles, targets (mate/constants.py:267-300)
+template <int NC, int NT, int NO>
+__device__ __forceinline__ void slot_of(bool cam_row, int k, int* kind, int* idx, int* off, int* width) {
+    if (cam_row) {
+        if (k < NT) { *kind = 0; *idx = k; *off = 22 + 5 * k; *width = 5; }
+        else if (k < NT + NO) { *kind = 1; *idx = k - NT; *off = 22 + 5 * NT + 4 * (k - NT); *width = 4; }
+        else { *kind = 2; *idx = k - NT - NO; *off = 22 + 5 * NT + 4 * NO + 7 * (k - NT - NO); *width = 7; }
+    } else {
+        if (k < NC) { *kind = 2; *idx = k; *off = 27 + 7 * k; *width = 7; }
+        else if (k < NC + NO) { *kind = 1; *idx = k - NC; *off = 27 + 7 * NC + 4 * (k - NC); *width = 4; }
+        else { *kind = 0; *idx = k - NC - NO; *off = 27 + 7 * NC + 4 * NO + 5 * (k - NC - NO); *width = 5; }
+    }
+}
+
+template <int NC, int NT, int NO>
+__global__ void __launch_bounds__(WShape<NC, NT, NO>::WARPS * 32)
+obs_transform_kernel(const __grid_constant__ Params p, const ObsOps ops, const float* __restrict__ cam_affine,
+                     const float* __restrict__ tgt_affine) {
+    using S = WShape<NC, NT, NO>;
+    constexpr int DC = S::DC, DT = S::DT, E = S::E, R = S::R;
+    extern __shared__ __align__(16) float wsm[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float* aff = wsm + S::WARPS * S::WARP_FLOATS;              // [DC + DT][2] scale, shift (RescaledObservation)
+    bool rescale = false;
+    for (int i = 0; i < ops.n; ++i) rescale = rescale || ops.op[i] == MATE_OBS_RESCALED;
+    if (rescale) {
+        for (int k = threadIdx.x; k < 2 * DC; k += blockDim.x) aff[k] = NC > 0 ? cam_affine[k] : 0.f;
+        for (int k = threadIdx.x; k < 2 * DT; k += blockDim.x) aff[2 * DC + k] = tgt_affine[k];
+    }
+    __syncthreads();
+    const int env = blockIdx.x * S::WARPS + warp;
+    if (env >= p.num_envs) return;
+    float* B = wsm + warp * S::WARP_FLOATS;                    // cam rows, then target rows
+    float* ob = B + S::BLOCK;                                  // [NO][4] obstacle_states_flagged
+    float* shm = ob + 4 * (NO > 0 ? NO : 1);                   // [2][E] shared view masks (camera team, target team)
+    float* she = shm + 2 * E;                                  // [4] shared empty bits
+    double* pos = reinterpret_cast<double*>((reinterpret_cast<uintptr_t>(she + 8) + 7) & ~(uintptr_t)7);   // [E][2] fp64 locations: targets, obstacles, cameras
+    float* cam_g = p.cam_obs + (size_t)env * S::CAM_ROW;
+    float* tgt_g = p.tgt_obs + (size_t)env * S::TGT_ROW;
+    // ---- load
+    if (S::VEC) {
+        // all 16-byte loads of the block are issued before the first one is stored to shared memory
+        const float4* c4 = reinterpret_cast<const float4*>(cam_g);
+        const float4* t4 = reinterpret_cast<const float4*>(tgt_g) - S::CAM_ROW / 4;
+        float4* b4 = reinterpret_cast<float4*>(B);
+        constexpr int NV = S::BLOCK / 4, NIT = (NV + 31) / 32;
+        float4 v[NIT];
+#pragma unroll
+        for (int it = 0; it < NIT; ++it) {
+            const int k = it * 32 + lane;
+            if (it * 32 + 32 <= NV || k < NV) v[it] = __ldcs((k < S::CAM_ROW / 4 ? c4 : t4) + k);
+        }
+#pragma unroll
+        for (int it = 0; it < NIT; ++it) {
+            const int k = it * 32 + lane;
+            if (it * 32 + 32 <= NV || k < NV) b4[k] = v[it];
+        }
+    } else {
+        for (int k = lane; k < S::CAM_ROW; k += 32) B[k] = cam_g[k];
+        for (int k = lane; k < S::TGT_ROW; k += 32) B[S::CAM_ROW + k] = tgt_g[k];
+    }
+    for (int o = lane; o < NO; o += 32) {
+        const float4 f = p.obs_f4[(size_t)o * p.bpad + env];
+        ob[4 * o] = f.x; ob[4 * o + 1] = f.y; ob[4 * o + 2] = f.z; ob[4 * o + 3] = 1.f;
+    }
+    for (int k = lane; k < E; k += 32) {   // RelativeCoordinates subtracts in fp64 (fp32 would lose ~1e-4 to cancellation)
+        const size_t bp = p.bpad;
+        double x, y;
+        if (k < NT) { x = p.tgt_x[(size_t)k * bp + env]; y = p.tgt_y[(size_t)k * bp + env]; }
+        else if (k < NT + NO) { x = p.obs_x[(size_t)(k - NT) * bp + env]; y = p.obs_y[(size_t)(k - NT) * bp + env]; }
+        else { x = p.cam_x[(size_t)(k - NT - NO) * bp + env]; y = p.cam_y[(size_t)(k - NT - NO) * bp + env]; }
+        pos[2 * k] = x; pos[2 * k + 1] = y;
+    }
+    __syncwarp();
+    auto row_ptr = [&](int r) { return r < NC ? B + r * DC : B + S::CAM_ROW + (r - NC) * DT; };
+    // Entity kinds with compile-time widths: 0 = target (x, y, sight range, loaded | flag), 1 = obstacle
+    // (x, y, r | flag), 2 = camera (x, y, r, Rs cos, Rs sin, theta | flag).  `pairs<K>(r0, n, f)` spreads the
+    // (observer row in [r0, r0 + n), entity of kind K) pairs over the lanes and calls
+    // f(row pointer, row, entity index, slot offset in that row).
+    auto pairs = [&](auto k, const int r0, const int n, auto&& f) {
+        constexpr int K = decltype(k)::value;
+        constexpr int N = K == 0 ? NT : (K == 1 ? NO : NC);
+        constexpr int W = K == 0 ? 5 : (K == 1 ? 4 : 7);
+        if constexpr (N > 0) {
+        for (int q = lane; q < n * N; q += 32) {
+            const int r = r0 + q / (N > 0 ? N : 1), idx = q % (N > 0 ? N : 1);
+            const int off = r < NC ? (K == 0 ? 22 : (K == 1 ? 22 + 5 * NT : 22 + 5 * NT + 4 * NO)) + W * idx
+                                   : (K == 2 ? 27 : (K == 1 ? 27 + 7 * NC : 27 + 7 * NC + 4 * NO)) + W * idx;
+            f(row_ptr(r), r, idx, off);
+        }
+        }
+    };
+    using K0 = std::integral_constant<int, 0>;
+    using K1 = std::integral_constant<int, 1>;
+    using K2 = std::integral_constant<int, 2>;
+    // write the public state (+ flag 1) of entity `idx` of kind K, or zeros
+    auto fill = [&](auto k, float* dst, const int idx, const bool on) {
+        constexpr int K = decltype(k)::value;
+        constexpr int W = K == 0 ? 5 : (K == 1 ? 4 : 7);
+        const float* src = K == 0 ? B + S::CAM_ROW + idx * DT + 13 : (K == 1 ? ob + 4 * idx : B + idx * DC + 13);
+#pragma unroll
+        for (int j = 0; j < W - 1; ++j) dst[j] = on ? src[j] : 0.f;
+        dst[W - 1] = on ? 1.f : 0.f;
+    };
+    // shm layout: targets [0, NT), obstacles [NT, NT + NO), cameras [NT + NO, E)  (same as `pos`)
+    constexpr int SH0 = 0, SH1 = NT, SH2 = NT + NO;
+
+#pragma unroll 1
+    for (int i = 0; i < ops.n; ++i) {
+        const int op = ops.op[i];
+        if (op == MATE_OBS_ENHANCED_CAMERA || op == MATE_OBS_ENHANCED_TARGET || op == MATE_OBS_SHARED_CAMERA || op == MATE_OBS_SHARED_TARGET) {
+            const bool cam_team = op == MATE_OBS_ENHANCED_CAMERA || op == MATE_OBS_SHARED_CAMERA;
+            const bool shared = op == MATE_OBS_SHARED_CAMERA || op == MATE_OBS_SHARED_TARGET;
+            const int r0 = cam_team ? 0 : NC, nrows = cam_team ? NC : NT;
+            if (nrows == 0) continue;
+            if (shared) {   // "or" of the team's view masks (flag entries), and of the targets' empty bits
+                for (int k = lane; k < E; k += 32) {
+                    const int kind = k < NT ? 0 : (k < NT + NO ? 1 : 2);
+                    const int idx = k < NT ? k : (k < NT + NO ? k - NT : k - NT - NO);
+                    const int w = kind == 0 ? 5 : (kind == 1 ? 4 : 7);
+                    const int off = cam_team ? (kind == 0 ? 22 : (kind == 1 ? 22 + 5 * NT : 22 + 5 * NT + 4 * NO)) + w * idx
+                                             : (kind == 2 ? 27 : (kind == 1 ? 27 + 7 * NC : 27 + 7 * NC + 4 * NO)) + w * idx;
+                    bool any = cam_team ? kind == 2 : kind == 0;   // teammates are always shared (flag 1)
+                    for (int r = 0; r < nrows; ++r) any = any || row_ptr(r0 + r)[off + w - 1] != 0.f;
+                    shm[k] = any ? 1.f : 0.f;
+                }
+                if (!cam_team && lane < NW) {
+                    bool any = false;
+                    for (int t = 0; t < NT; ++t) any = any || row_ptr(NC + t)[13 + 10 + lane] != 0.f;
+                    she[lane] = any ? 1.f : 0.f;
+                }
+            } else if (!cam_team && lane < NW) {   // np.logical_not(remaining_cargoes).all(axis=-1)
+                const uint4 c0 = p.cargo[env], c1 = p.cargo[(size_t)p.bpad + env];
+                const uint32_t w0 = lane == 0 ? c0.x : (lane == 1 ? c0.z : (lane == 2 ? c1.x : c1.z));
+                const uint32_t w1 = lane == 0 ? c0.y : (lane == 1 ? c0.w : (lane == 2 ? c1.y : c1.w));
+                she[lane] = (w0 | w1) == 0u ? 1.f : 0.f;
+            }
+            __syncwarp();
+            pairs(K0{}, r0, nrows, [&](float* row, int, int idx, int off) { fill(K0{}, row + off, idx, !shared || shm[SH0 + idx] != 0.f); });
+            pairs(K1{}, r0, nrows, [&](float* row, int, int idx, int off) { fill(K1{}, row + off, idx, !shared || shm[SH1 + idx] != 0.f); });
+            pairs(K2{}, r0, nrows, [&](float* row, int, int idx, int off) { fill(K2{}, row + off, idx, !shared || shm[SH2 + idx] != 0.f); });
+            if (!cam_team) {
+                for (int q = lane; q < NT * NW; q += 32) row_ptr(NC + q / NW)[13 + 10 + (q % NW)] = she[q % NW];
+            }
+            __syncwarp();
+        } else if (op == MATE_OBS_RELATIVE) {
+            // locations still hold the simulator's values unless a rescale came first: subtract in fp64 from
+            // the state (entity - observer), else in place on whatever the entries hold now
+            bool exact = true;
+            for (int j = 0; j < i; ++j) exact = exact && ops.op[j] != MATE_OBS_RESCALED;
+            auto relative = [&](auto k, float* row, const int r, const int idx, const int off) {
+                constexpr int K = decltype(k)::value;
+                constexpr int W = K == 0 ? 5 : (K == 1 ? 4 : 7);
+                if (row[off + W - 1] == 0.f) return;
+                if (exact) {
+                    const int ke = (K == 0 ? SH0 : (K == 1 ? SH1 : SH2)) + idx, ko = r < NC ? SH2 + r : r - NC;
+                    row[off] = (float)(pos[2 * ke] - pos[2 * ko]); row[off + 1] = (float)(pos[2 * ke + 1] - pos[2 * ko + 1]);
+                } else {
+                    row[off] -= row[13]; row[off + 1] -= row[14];
+                }
+            };
+            pairs(K0{}, 0, R, [&](float* row, int r, int idx, int off) { relative(K0{}, row, r, idx, off); });
+            pairs(K1{}, 0, R, [&](float* row, int r, int idx, int off) { relative(K1{}, row, r, idx, off); });
+            pairs(K2{}, 0, R, [&](float* row, int r, int idx, int off) { relative(K2{}, row, r, idx, off); });
+            for (int q = lane; q < R * 2 * NW; q += 32) {   // the warehouse locations in the preserved block
+                const int r = q / (2 * NW), j = q % (2 * NW);
+                float* row = row_ptr(r);
+                const int ko = r < NC ? SH2 + r : r - NC;
+                if (exact) row[4 + j] = (float)((double)row[4 + j] - pos[2 * ko + (j & 1)]);
+                else row[4 + j] -= row[13 + (j & 1)];
+            }
+            __syncwarp();
+        } else if (op == MATE_OBS_RESCALED) {
+            // a lane keeps its columns' (scale, shift) in registers and walks down the rows of a team
+            for (int col = lane; col < DC; col += 32) {
+                const float sc = aff[2 * col], sh = aff[2 * col + 1];
+#pragma unroll
+                for (int r = 0; r < NC; ++r) B[r * DC + col] = B[r * DC + col] * sc + sh;
+            }
+            for (int col = lane; col < DT; col += 32) {
+                const float sc = aff[2 * DC + 2 * col], sh = aff[2 * DC + 2 * col + 1];
+#pragma unroll
+                for (int t = 0; t < NT; ++t) B[S::CAM_ROW + t * DT + col] = B[S::CAM_ROW + t * DT + col] * sc + sh;
+            }
+            __syncwarp();
+        }
+    }
+    // ---- store
+    if (S::VEC) {
+        float4* c4 = reinterpret_cast<float4*>(cam_g);
+        float4* t4 = reinterpret_cast<float4*>(tgt_g) - S::CAM_ROW / 4;
+        const float4* b4 = reinterpret_cast<const float4*>(B);
+        constexpr int NV = S::BLOCK / 4, NIT = (NV + 31) / 32;
+#pragma unroll
+        for (int it = 0; it < NIT; ++it) {
+            const int k = it * 32 + lane;
+            if (it * 32 + 32 <= NV || k < NV) (k < S::CAM_ROW / 4 ? c4 : t4)[k] = b4[k];
+        }
+    } else {
+        for (int k = lane; k < S::CAM_ROW; k += 32) cam_g[k] = B[k];
+        for (int k = lane; k < S::TGT_ROW; k += 32) tgt_g[k] = B[S::CAM_ROW + k];
+    }
+}
+
+// DiscreteCamera / DiscreteTarget (mate/wrappers/discrete_action_spaces.py:98-117, 204-228): grid index ->
+// continuous action through the wrapper's action table [levels * levels][2]
+__global__ void decode_actions_kernel(const int64_t* __restrict__ index, const float* __restrict__ table, int table_size,
+                                      float* __restrict__ out, long long n) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    long long k = index[i];
+    k = k < 0 ? 0 : (k >= table_size ? table_size - 1 : k);
+    reinterpret_cast<float2*>(out)[i] = reinterpret_cast<const float2*>(table)[k];
+}
+
+}  // namespace mate

@@ -28,6 +28,24 @@ def _dptr(t):
     return None if t is None else ctypes.c_void_p(t.data_ptr())
 
 
+def rescale_tables(nc, nt, no):
+    """(scale, shift) per observation column so that ``x * scale + shift`` equals the reference's
+    ``normalize_observation`` (mate/agents/utils.py:97-127): subtract ``low`` where it is finite, then map the
+    columns that are bounded on both sides (and not degenerate) to [-1, 1].  float32 [D][2] per team."""
+    from mate_b200 import constants as consts  # pylint: disable=import-outside-toplevel
+
+    tables = []
+    for space in (consts.camera_observation_space_of(nc, nt, no), consts.target_observation_space_of(nc, nt, no)):
+        low, high = np.asarray(space.low, dtype=np.float64), np.asarray(space.high, dtype=np.float64)
+        below, above = np.isfinite(low), np.isfinite(high)
+        both = below & above & (np.where(below & above, high - low, 0.0) > 0.0)
+        span = np.where(both, high - low, 1.0)
+        scale = np.where(both, 2.0 / span, 1.0)
+        shift = np.where(below, -low, 0.0) * scale + np.where(both, -1.0, 0.0)
+        tables.append(np.stack([scale, shift], axis=-1).astype(np.float32))
+    return tuple(tables)
+
+
 class BatchedSim:
     """One batch of MultiAgentTracking environments resident on one GPU."""
 
@@ -58,6 +76,7 @@ class BatchedSim:
         self._aux = None
         self._aux_struct = None
         self._zero_cam_act = torch.zeros((self.B, max(self.nc, 1), 2), dtype=torch.float32, device=dev)
+        self._obs_ops, self._obs_ops_c, self._affine = [], None, None
 
     def close(self):
         if getattr(self, 'handle', None) is not None and self.handle:
@@ -121,6 +140,36 @@ class BatchedSim:
             cam_act = self._zero_cam_act
         return cam_act, tgt_act
 
+    # ------------------------------------------------------------------ observation wrappers (N1)
+    def set_observation_wrappers(self, ops):
+        """Observation wrapper codes (``_abi.OBS_*``), innermost first; applied in ONE extra kernel after every
+        reset / step / observe (mate_b200_transform_observations)."""
+        ops = [int(op) for op in ops]
+        if len(ops) > _abi.MAX_OBS_OPS:
+            raise ValueError(f'at most {_abi.MAX_OBS_OPS} observation wrappers can be stacked')
+        self._obs_ops = ops
+        self._obs_ops_c = (ctypes.c_int32 * max(len(ops), 1))(*ops)
+        if _abi.OBS_RESCALED in ops and self._affine is None:
+            self._affine = tuple(torch.from_numpy(t).to(self.device) for t in rescale_tables(self.nc, self.nt, self.no))
+
+    def _apply_observation_wrappers(self):
+        if not self._obs_ops:
+            return
+        cam_aff, tgt_aff = self._affine if self._affine is not None else (None, None)
+        with torch.cuda.device(self.device):
+            _check(self.lib, self.lib.mate_b200_transform_observations(
+                self.handle, _dptr(self.cam_obs), _dptr(self.tgt_obs), self._obs_ops_c, len(self._obs_ops),
+                _dptr(cam_aff) if self.nc else None, _dptr(tgt_aff), self._stream()))
+
+    def decode_actions(self, index, table):
+        """DiscreteCamera / DiscreteTarget: int64 grid indices [B, N] -> float32 actions [B, N, 2]."""
+        index = torch.as_tensor(index, device=self.device).to(torch.int64).contiguous()
+        out = torch.empty(tuple(index.shape) + (2,), dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            _check(self.lib, self.lib.mate_b200_decode_actions(_dptr(index), _dptr(table), int(table.shape[0]), _dptr(out),
+                                                               index.numel(), self._stream()))
+        return out
+
     # ------------------------------------------------------------------ API
     def reset(self, seed=0, env_mask=None):
         mask = None
@@ -129,6 +178,7 @@ class BatchedSim:
         with torch.cuda.device(self.device):
             _check(self.lib, self.lib.mate_b200_reset(self.handle, _dptr(mask), int(seed), _dptr(self.cam_obs),
                                                       _dptr(self.tgt_obs), self._stream()))
+        self._apply_observation_wrappers()
         return self.cam_obs, self.tgt_obs
 
     def step(self, cam_act, tgt_act, auto_reset=True, replay=None, aux=False):
@@ -144,6 +194,7 @@ class BatchedSim:
                 ctypes.byref(rs) if rs is not None else None,
                 _abi.MATE_STEP_AUTO_RESET if auto_reset else 0, self._stream()))
         del keep
+        self._apply_observation_wrappers()
         return (self.cam_obs, self.tgt_obs), self.rewards, self.done
 
     def observe(self, replay=None, aux=False):
@@ -156,6 +207,7 @@ class BatchedSim:
                 ctypes.byref(self._aux_struct) if aux else None,
                 ctypes.byref(rs) if rs is not None else None, self._stream()))
         del keep
+        self._apply_observation_wrappers()
         return self.cam_obs, self.tgt_obs
 
     def step_host(self, cam_act, tgt_act, out, auto_reset=True):

@@ -54,6 +54,28 @@ class Box(Space):
             and np.array_equal(self.high, other.high)
 
 
+class Discrete(Space):
+    def __init__(self, n):
+        super().__init__((), np.int64)
+        self.n = int(n)
+
+    def sample(self):
+        return int(self.np_random.randint(self.n))
+
+    def contains(self, x):
+        try:
+            value = int(x)
+        except (TypeError, ValueError):
+            return False
+        return 0 <= value < self.n and value == x
+
+    def __repr__(self):
+        return f'Discrete({self.n})'
+
+    def __eq__(self, other):
+        return isinstance(other, Discrete) and self.n == other.n
+
+
 class Tuple(Space):
     def __init__(self, spaces):
         super().__init__(None, None)
