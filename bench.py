@@ -335,7 +335,7 @@ def main():
     }
     if e2e is not None:
         line['e2e'] = e2e
-    if not args.no_cpu:
+    if not args.no_cpu and world == 1:   # the CPU baseline is reported at N = 1 only
         threads = os.cpu_count() or 1
         cpu_value, cpu_steps, cpu_elapsed = cpu_arm(cfg, args.cpu_envs, args.cpu_seconds, threads)
         line['cpu_baseline'] = {
