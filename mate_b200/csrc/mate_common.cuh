@@ -222,14 +222,16 @@ struct RaySample { double angle; double n0; int tangent_of; };
 // fp64 obstacle discs of one environment: element o of field f is f[o * stride]
 struct ObsRef { const double* x; const double* y; const double* r; size_t stride; };
 
+// `discs`: the discs that can meet the ray (a superset is fine: a disc the ray misses changes nothing)
 template <int NO>
 __device__ __forceinline__ double cast_ray(const ObsRef ob, double cx, double cy,
-                                           double angle, double n0, int tangent_of) {
+                                           double angle, double n0, int tangent_of, unsigned long long discs) {
     double sn, cs;
     sincospi(angle * (1.0 / 180.0), &sn, &cs);
     double n = n0;
-#pragma unroll 1
-    for (int o = 0; o < NO; ++o) {
+    while (discs != 0ull) {
+        const int o = __ffsll((long long)discs) - 1;
+        discs &= discs - 1ull;
         if (o == tangent_of) continue;   // exact tangent ray: never shortened by its own disc
         const double relx = ob.x[o * ob.stride] - cx, rely = ob.y[o * ob.stride] - cy, R = ob.r[o * ob.stride];
         const double proj = relx * cs + rely * sn;
@@ -280,6 +282,14 @@ __device__ __noinline__ double sight_range_at(const ObsRef ob, double cx, double
         passing |= 1ull << o;
     }
     if (inside) return 0.0;
+    // Both bracketing samples lie within 1 degree of the bearing, so a disc that cuts one of those two rays
+    // is at an angular distance <= half + 1 degree from the bearing: it is in `passing` (discs outside the
+    // camera's obstacle set are farther than rmax + R and cannot shorten a ray of length <= rmax).
+#ifdef MATE2_NO_CASTMASK
+    const unsigned long long near_discs = NO >= 64 ? ~0ull : ((1ull << NO) - 1ull);
+#else
+    const unsigned long long near_discs = passing;
+#endif
     // phase 2: the sample angles of those obstacles, one obstacle per iteration (lanes of a warp that
     // evaluate different obstacles stay converged)
     while (passing != 0ull) {
@@ -314,11 +324,11 @@ __device__ __noinline__ double sight_range_at(const ObsRef ob, double cx, double
             }
         }
     }
-    const double rho_p = cast_ray<NO>(ob, cx, cy, P.angle, P.n0, P.tangent_of);
+    const double rho_p = cast_ray<NO>(ob, cx, cy, P.angle, P.n0, P.tangent_of, near_discs);
     if (a == P.angle) return rho_p;                // np.interp: exact hit on a sample
     // the closing sample (phi0 + 360, rho0) of the polyline is the -180 grid ray (entities.py:470-471)
     const double s_angle = (S.angle >= 180.0) ? -180.0 : S.angle;
-    const double rho_s = cast_ray<NO>(ob, cx, cy, s_angle, S.n0, S.tangent_of);
+    const double rho_s = cast_ray<NO>(ob, cx, cy, s_angle, S.n0, S.tangent_of, near_discs);
     const double slope = (rho_s - rho_p) / (S.angle - P.angle);
     return slope * (a - P.angle) + rho_p;
 }

@@ -41,6 +41,9 @@
 #ifndef MATE2_STREAMING
 #define MATE2_STREAMING 1       // evict-first stores for the observation rows (written once, read by another kernel)
 #endif
+#ifndef MATE2_PF_OBS
+#define MATE2_PF_OBS 1         // fp64 obstacle discs -> L2 ahead of the exact paths: 0 = off, 1 = envs that will need them, 2 = all envs
+#endif
 #ifndef MATE2_MIN_CTAS
 #define MATE2_MIN_CTAS 8       // caps registers at 128 (4 warps per SM sub-partition); 65 536 envs = 2048 warp tiles = 13.8 per SM -> one wave
 #endif
@@ -81,6 +84,21 @@ struct Shape2 {
 // mask bit positions inside an observer row
 __device__ __forceinline__ constexpr uint32_t bit_cam(int c) { return 1u << c; }
 __device__ __forceinline__ constexpr uint32_t bit_tgt(int t) { return 1u << (8 + t); }
+
+// The exact (fp64) paths read the discs of an environment from arrays nobody else touches in a step: a
+// DRAM round trip for a handful of lanes.  The lines are requested as soon as it is known that an
+// environment will take such a path (a target within reach of a disc, a pair the classification left open).
+template <int NO>
+__device__ __forceinline__ void prefetch_discs64(const Params& p, int er) {
+    const size_t bp = p.bpad;
+#pragma unroll
+    for (int o = 0; o < NO; ++o) {
+        const size_t i = (size_t)o * bp + er;
+        asm volatile("prefetch.global.L2 [%0];" :: "l"(p.obs_x + i));
+        asm volatile("prefetch.global.L2 [%0];" :: "l"(p.obs_y + i));
+        asm volatile("prefetch.global.L2 [%0];" :: "l"(p.obs_r + i));
+    }
+}
 
 // ---- out-of-line exact (fp64) decisions, state re-read from global memory -------------------
 // ||a - b|| <= thr (or <), entities a / b given by their SoA rows
@@ -723,6 +741,8 @@ mate_step_kernel2(const __grid_constant__ Params p) {
         if (!__any_sync(FULL, need)) return;
     }
 
+    if (MATE2_PF_OBS == 2 && NO > 0 && mode == MODE_STEP) prefetch_discs64<NO>(p, er);
+
     // ------------------------------------------------------------------ _simulate (environment.py:1326-1354)
     {   // Camera.simulate (entities.py:347-360); the next camera's state is fetched while this one is derived
         double nx_ = 0, ny_ = 0, nphi_ = 0, nth_ = 0;
@@ -782,6 +802,7 @@ mate_step_kernel2(const __grid_constant__ Params p) {
                 }
             }
         }
+        if (MATE2_PF_OBS == 1 && NO > 0 && slow != 0) prefetch_discs64<NO>(p, er);
         double ntx_ = p.tgt_x[er], nty_ = p.tgt_y[er];
         uint32_t npk_ = p.tgt_pack[er];
         float2 nta_ = make_float2(0.f, 0.f);
@@ -1062,6 +1083,7 @@ mate_step_kernel2(const __grid_constant__ Params p) {
                                 const int fast = occlusion_fast<NO>(p.obs_f4 + envr, bp, cx, cy, v[S::V_T + 3 * t] - cx, v[S::V_T + 3 * t + 1] - cy, (float)p.cam_rmax);
                                 sees = fast == 1;
                                 need_exact = fast == 2;
+                                if (MATE2_PF_OBS == 1 && need_exact) prefetch_discs64<NO>(p, envr);
                             }
                         }
                         if (sees) atomicOr(&mk[src * S::MSTRIDE + c * MW], bit_tgt(t));
