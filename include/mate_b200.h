@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define MATE_B200_ABI_VERSION 1
+#define MATE_B200_ABI_VERSION 2
 #define MATE_NUM_WAREHOUSES 4   /* mate/constants.py:70-75 */
 #define MATE_MAX_CAMERAS 32
 #define MATE_MAX_TARGETS 32
@@ -114,6 +114,8 @@ typedef struct MateStepAux {
     uint8_t* is_colliding;   /* [B, Nt] Target.is_colliding, entities.py:668                 */
     float* warehouse_dist;   /* [B, Nt, 4] target_warehouse_distances                        */
     int32_t* episode_step;   /* [B] episode_step after this step (before auto-reset)         */
+    int32_t* tgt_goal;       /* [B, Nt] target_goals (-1 = none), environment.py:1271-1324   */
+    uint8_t* tgt_empty_bits; /* [B, Nt] Target.empty_bits as bit set (bit w = warehouse w)   */
 } MateStepAux;
 
 /* Parity mode: recorded outcomes of the reference's two stochastic step-path draws
@@ -203,6 +205,26 @@ int mate_b200_episode_stats(MateSim* sim, float* out16, int32_t reset_after, voi
 int mate_b200_transform_observations(MateSim* sim, float* cam_obs, float* tgt_obs, const int32_t* ops,
                                      int32_t num_ops, const float* cam_affine, const float* tgt_affine,
                                      void* stream);
+
+/* Per-agent terms of the reference's auxiliary-reward and training-information wrappers (SURVEY.md section
+ * 8f, N3) from the auxiliary outputs of the LAST step (so they describe the finished step even where the
+ * environment was auto-reset), one pass, no host round trip:
+ *   cam_terms [B, Nc, MATE_CAM_TERMS]: the keys of AuxiliaryCameraRewards.ACCEPTABLE_KEYS in order
+ *     (mate/wrappers/auxiliary_camera_rewards.py:38-46, 140-149): raw_reward, coverage_rate, real_coverage_rate,
+ *     mean_transport_rate, soft_coverage_score (not computed: 0), num_tracked, baseline; then is_sensed
+ *     (mate/wrappers/more_training_information.py:61-65);
+ *   tgt_terms [B, Nt, MATE_TGT_TERMS]: the keys of AuxiliaryTargetRewards.ACCEPTABLE_KEYS in order
+ *     (mate/wrappers/auxiliary_target_rewards.py:135-177): raw_reward, coverage_rate, real_coverage_rate,
+ *     mean_transport_rate, normalized_goal_distance, sparse_delivery, soft_coverage_score (0), is_tracked,
+ *     is_colliding, baseline; then goal, goal_distance and the four clipped warehouse distances of
+ *     MoreTrainingInformation (more_training_information.py:68-82).
+ * `aux` must be the struct the last mate_b200_step / observe call filled, with mask_ct, mask_tc, coverage,
+ * target_dones, is_colliding, warehouse_dist, tgt_goal and tgt_empty_bits non-NULL; rewards [B, 2] as written
+ * by mate_b200_step. */
+#define MATE_CAM_TERMS 8
+#define MATE_TGT_TERMS 16
+int mate_b200_auxiliary_terms(MateSim* sim, const MateStepAux* aux, const float* rewards, float* cam_terms,
+                              float* tgt_terms, void* stream);
 
 /* DiscreteCamera / DiscreteTarget.action (mate/wrappers/discrete_action_spaces.py:98-117, 204-228): grid
  * indices (dev int64 [count]) -> continuous actions (dev float32 [count][2]) through the wrapper's table

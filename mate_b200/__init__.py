@@ -65,7 +65,8 @@ del _nc, _nt, _no
 
 
 _WRAPPERS = ('EnhancedObservation', 'SharedFieldOfView', 'RelativeCoordinates', 'RescaledObservation',
-             'DiscreteCamera', 'DiscreteTarget', 'RepeatedRewardIndividualDone')
+             'DiscreteCamera', 'DiscreteTarget', 'RepeatedRewardIndividualDone', 'MoreTrainingInformation',
+             'AuxiliaryCameraRewards', 'AuxiliaryTargetRewards')
 
 
 def __getattr__(name):

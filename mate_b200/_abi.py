@@ -88,6 +88,8 @@ AUX_FIELDS = [
     ('is_colliding', c_uint8_p, np.uint8, lambda B, nc, nt, no: (B, nt)),
     ('warehouse_dist', c_float_p, np.float32, lambda B, nc, nt, no: (B, nt, 4)),
     ('episode_step', c_int32_p, np.int32, lambda B, nc, nt, no: (B,)),
+    ('tgt_goal', c_int32_p, np.int32, lambda B, nc, nt, no: (B, nt)),
+    ('tgt_empty_bits', c_uint8_p, np.uint8, lambda B, nc, nt, no: (B, nt)),
 ]
 
 
@@ -172,8 +174,9 @@ def load_library():
     lib.mate_b200_launch_count.restype = ctypes.c_int64
     lib.mate_b200_transform_observations.argtypes = [void_p, void_p, void_p, c_int32_p, ctypes.c_int32, void_p, void_p, void_p]
     lib.mate_b200_decode_actions.argtypes = [void_p, void_p, ctypes.c_int32, void_p, ctypes.c_int64, void_p]
+    lib.mate_b200_auxiliary_terms.argtypes = [void_p, ctypes.POINTER(MateStepAux), void_p, void_p, void_p, void_p]
     for name in ('create', 'destroy', 'obs_dims', 'reset', 'step', 'observe', 'step_host',
-                 'get_state', 'set_state', 'episode_stats', 'transform_observations', 'decode_actions'):
+                 'get_state', 'set_state', 'episode_stats', 'transform_observations', 'decode_actions', 'auxiliary_terms'):
         getattr(lib, 'mate_b200_' + name).restype = ctypes.c_int
     _LIB = lib
     return lib
@@ -184,9 +187,10 @@ EXPORTED_SYMBOLS = [
     'mate_b200_obs_dims', 'mate_b200_reset', 'mate_b200_step', 'mate_b200_observe',
     'mate_b200_step_host', 'mate_b200_get_state', 'mate_b200_set_state',
     'mate_b200_episode_stats', 'mate_b200_launch_count', 'mate_b200_transform_observations',
-    'mate_b200_decode_actions',
+    'mate_b200_decode_actions', 'mate_b200_auxiliary_terms',
 ]
 
 # observation wrapper codes (include/mate_b200.h)
 OBS_ENHANCED_CAMERA, OBS_ENHANCED_TARGET, OBS_SHARED_CAMERA, OBS_SHARED_TARGET, OBS_RELATIVE, OBS_RESCALED = range(1, 7)
 MAX_OBS_OPS = 8
+CAM_TERMS, TGT_TERMS = 8, 16   # MATE_CAM_TERMS / MATE_TGT_TERMS

@@ -318,6 +318,22 @@ extern "C" int mate_b200_transform_observations(MateSim* sim, float* cam_obs, fl
     return MATE_OK;
 }
 
+extern "C" int mate_b200_auxiliary_terms(MateSim* sim, const MateStepAux* aux, const float* rewards, float* cam_terms,
+                                         float* tgt_terms, void* stream) {
+    if (!sim || !aux || !rewards || !tgt_terms || (sim->cfg.num_cameras > 0 && !cam_terms)) return fail(MATE_EINVAL, "null argument");
+    if (!aux->coverage || !aux->target_dones || !aux->is_colliding || !aux->warehouse_dist || !aux->tgt_goal || !aux->tgt_empty_bits ||
+        (sim->cfg.num_cameras > 0 && (!aux->mask_ct || !aux->mask_tc)))
+        return fail(MATE_EINVAL, "auxiliary_terms needs mask_ct, mask_tc, coverage, target_dones, is_colliding, warehouse_dist, tgt_goal, tgt_empty_bits");
+    CUDA_TRY(cudaSetDevice(sim->device));
+    const int threads = 128;
+    aux_terms_kernel<<<(sim->num_envs + threads - 1) / threads, threads, 0, (cudaStream_t)stream>>>(
+        *aux, rewards, cam_terms, tgt_terms, sim->num_envs, sim->cfg.num_cameras, sim->cfg.num_targets);
+    sim->launches += 1;
+    cudaError_t err = cudaGetLastError();
+    if (err != cudaSuccess) return fail(MATE_ECUDA, std::string("auxiliary terms launch: ") + cudaGetErrorString(err));
+    return MATE_OK;
+}
+
 extern "C" int mate_b200_decode_actions(const int64_t* index, const float* table, int32_t table_size, float* out,
                                         int64_t count, void* stream) {
     if (!index || !table || !out || table_size <= 0 || count < 0) return fail(MATE_EINVAL, "bad argument");
@@ -367,7 +383,7 @@ static void fill_aux(Params& p, const MateStepAux* aux, const MateReplay* replay
     if (aux) {
         p.aux = *aux; p.has_aux = 1;
         p.has_aux_detail = aux->mask_ct || aux->mask_cc || aux->mask_co || aux->mask_tc || aux->mask_to || aux->mask_tt ||
-                           aux->target_dones || aux->is_colliding || aux->warehouse_dist;
+                           aux->target_dones || aux->is_colliding || aux->warehouse_dist || aux->tgt_goal || aux->tgt_empty_bits;
     } else {
         memset(&p.aux, 0, sizeof(p.aux)); p.has_aux = 0; p.has_aux_detail = 0;
     }

@@ -294,6 +294,8 @@ __device__ __noinline__ void write_aux_env(const Params& p, int e, const uint32_
         if (ax.mask_to) for (int o = 0; o < NO; ++o) ax.mask_to[((size_t)e * NT + t) * NO + o] = obs_bit(NC + t, o);
         if (ax.target_dones) ax.target_dones[(size_t)e * NT + t] = (tdone_bits >> t) & 1;
         if (ax.is_colliding) ax.is_colliding[(size_t)e * NT + t] = (uint8_t)tp_colliding(__float_as_uint(vrow[S::V_T + 3 * t + 2]));
+        if (ax.tgt_goal) ax.tgt_goal[(size_t)e * NT + t] = tp_goal(__float_as_uint(vrow[S::V_T + 3 * t + 2]));
+        if (ax.tgt_empty_bits) ax.tgt_empty_bits[(size_t)e * NT + t] = (uint8_t)tp_empty(__float_as_uint(vrow[S::V_T + 3 * t + 2]));
         if (ax.warehouse_dist) {
             const double tx = p.tgt_x[(size_t)t * p.bpad + e], ty = p.tgt_y[(size_t)t * p.bpad + e];
             for (int w4 = 0; w4 < NW; ++w4) {

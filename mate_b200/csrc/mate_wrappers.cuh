@@ -251,4 +251,49 @@ __global__ void decode_actions_kernel(const int64_t* __restrict__ index, const f
     reinterpret_cast<float2*>(out)[i] = reinterpret_cast<const float2*>(table)[k];
 }
 
+// Per-agent terms of AuxiliaryCameraRewards / AuxiliaryTargetRewards / MoreTrainingInformation
+// (mate/wrappers/auxiliary_camera_rewards.py:140-149, auxiliary_target_rewards.py:135-177,
+// more_training_information.py:61-82) from the auxiliary outputs of the last step.  One thread per
+// environment: the inputs are ~150 bytes per environment, the outputs 4 (8 Nc + 16 Nt) bytes.
+__global__ void aux_terms_kernel(const MateStepAux ax, const float* __restrict__ rewards, float* __restrict__ cam_terms,
+                                 float* __restrict__ tgt_terms, int num_envs, int nc, int nt) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= num_envs) return;
+    const float cov = ax.coverage[(size_t)e * 3], cov_real = ax.coverage[(size_t)e * 3 + 1], transport = ax.coverage[(size_t)e * 3 + 2];
+    const float cam_reward = rewards[(size_t)e * 2], tgt_reward = rewards[(size_t)e * 2 + 1];
+    uint32_t tracked = 0;   // bit t: some camera sees target t
+    for (int c = 0; c < nc; ++c) {
+        int num_tracked = 0, sensed = 0;
+        for (int t = 0; t < nt; ++t) {
+            const int seen = ax.mask_ct[((size_t)e * nc + c) * nt + t] != 0;
+            num_tracked += seen;
+            tracked |= (uint32_t)seen << t;
+            sensed |= ax.mask_tc[((size_t)e * nt + t) * nc + c] != 0;
+        }
+        float* q = cam_terms + ((size_t)e * nc + c) * MATE_CAM_TERMS;
+        q[0] = cam_reward; q[1] = cov; q[2] = cov_real; q[3] = transport; q[4] = 0.f;
+        q[5] = (float)num_tracked; q[6] = 1.f; q[7] = (float)sensed;
+    }
+    for (int t = 0; t < nt; ++t) {
+        const size_t i = (size_t)e * nt + t;
+        const int goal = ax.tgt_goal[i], empty = ax.tgt_empty_bits[i];
+        float wd[NW];
+        float nearest_open = (float)kTerrain;   // TERRAIN_WIDTH / 2 when every warehouse is known to be empty
+        bool any_open = false;
+        for (int w = 0; w < NW; ++w) {
+            wd[w] = fmaxf(ax.warehouse_dist[i * NW + w] - (float)kWarehouseRadius, 0.f);
+            if (!((empty >> w) & 1)) { nearest_open = any_open ? fminf(nearest_open, wd[w]) : wd[w]; any_open = true; }
+        }
+        const float goal_distance = goal >= 0 ? wd[goal] : nearest_open;               // auxiliary_target_rewards.py:143-149
+        const float info_goal_distance = goal >= 0 ? wd[goal] : (float)kTerrain;       // more_training_information.py:72
+        float* q = tgt_terms + i * MATE_TGT_TERMS;
+        q[0] = tgt_reward; q[1] = cov; q[2] = cov_real; q[3] = transport;
+        q[4] = goal_distance / (float)(2.0 * kTerrain);
+        q[5] = (float)(ax.target_dones[i] != 0); q[6] = 0.f; q[7] = (float)((tracked >> t) & 1u);
+        q[8] = (float)(ax.is_colliding[i] != 0); q[9] = 1.f;
+        q[10] = (float)goal; q[11] = info_goal_distance;
+        for (int w = 0; w < NW; ++w) q[12 + w] = wd[w];
+    }
+}
+
 }  // namespace mate

@@ -82,6 +82,9 @@ class MultiAgentTracking:  # pylint: disable=too-many-instance-attributes,too-ma
         self._seed = 0
         self._np_random = np.random.RandomState(0)
         self._needs_reset = True
+        self._step_serial = 0
+        self._terms_serial = -1
+        self._terms = None
         self._aux = self.sim.alloc_aux()
         self.viewer = None
 
@@ -173,7 +176,10 @@ class MultiAgentTracking:  # pylint: disable=too-many-instance-attributes,too-ma
         if self._needs_reset:
             raise RuntimeError('call reset() before step()')
         cam, tgt = self._check_actions(action)
-        (cam_obs, tgt_obs), rewards, done = self.sim.step(cam, tgt, auto_reset=self.batched, aux=True)
+        # parity hook: `env.replay_next = (transmit, goal_choice)` replays recorded draws of the reference in this step
+        replay = self.__dict__.pop('replay_next', None)
+        (cam_obs, tgt_obs), rewards, done = self.sim.step(cam, tgt, auto_reset=self.batched, aux=True, replay=replay)
+        self._step_serial += 1
         if self.batched:
             aux = self._aux
             common = {
@@ -277,6 +283,17 @@ class MultiAgentTracking:  # pylint: disable=too-many-instance-attributes,too-ma
     awaiting_cargo_counts = property(lambda self: self._maybe_single(self.sim.get_state()['awaiting']))
     target_goals = property(lambda self: self._maybe_single(self.sim.get_state()['tgt_goal']))
     obstacle_states = property(lambda self: self._maybe_single(self.sim.get_state()['obs_xyr']))
+
+    target_goals_of_last_step = property(lambda self: self._maybe_single(self._aux['tgt_goal']))
+
+    def auxiliary_terms(self):
+        """``(cam_terms [B, Nc, 8], tgt_terms [B, Nt, 16])`` of the last step, computed once per step by one kernel
+        and shared by the auxiliary-reward / training-information wrappers (``include/mate_b200.h``,
+        ``mate_b200_auxiliary_terms``)."""
+        if self._terms_serial != self._step_serial:
+            self._terms = self.sim.auxiliary_terms()
+            self._terms_serial = self._step_serial
+        return self._terms
 
     def episode_statistics(self, reduce_across_ranks: bool = False, reset: bool = False) -> Dict[str, float]:
         """Episode statistics accumulated on the device; with ``reduce_across_ranks`` the

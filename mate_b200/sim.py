@@ -210,6 +210,21 @@ class BatchedSim:
         self._apply_observation_wrappers()
         return self.cam_obs, self.tgt_obs
 
+    def auxiliary_terms(self):
+        """Per-agent terms of the auxiliary-reward / training-information wrappers for the LAST step
+        (mate_b200_auxiliary_terms): ``(cam_terms [B, Nc, CAM_TERMS], tgt_terms [B, Nt, TGT_TERMS])``."""
+        if self._aux is None:
+            raise RuntimeError('auxiliary_terms needs a step / observe call with aux=True first')
+        if getattr(self, '_terms', None) is None:
+            self._terms = (torch.zeros((self.B, self.nc, _abi.CAM_TERMS), dtype=torch.float32, device=self.device),
+                           torch.zeros((self.B, self.nt, _abi.TGT_TERMS), dtype=torch.float32, device=self.device))
+        cam_terms, tgt_terms = self._terms
+        with torch.cuda.device(self.device):
+            _check(self.lib, self.lib.mate_b200_auxiliary_terms(
+                self.handle, ctypes.byref(self._aux_struct), _dptr(self.rewards), _dptr(cam_terms) if self.nc else None,
+                _dptr(tgt_terms), self._stream()))
+        return cam_terms, tgt_terms
+
     def step_host(self, cam_act, tgt_act, out, auto_reset=True):
         """Host-buffer step: `cam_act`/`tgt_act` and the tensors in `out` (cam_obs, tgt_obs,
         rewards, done) are CPU tensors (pinned for full PCIe speed)."""

@@ -248,3 +248,198 @@ class RepeatedRewardIndividualDone(Wrapper):
         target_dones = [bool(x) for x in np.asarray(base.target_dones).reshape(-1)] if self.target_done_at_destination else [done] * nt
         reward = ([camera_team_reward] * nc, [target_team_reward] * nt)
         return observation, reward, ([done] * nc, target_dones), info
+
+
+# ------------------------------------------------------------------------------------------------------------
+# MoreTrainingInformation and the auxiliary-reward wrappers.  The per-agent terms come
+# from ONE kernel per step over the auxiliary outputs of the step kernel (``mate_b200_auxiliary_terms``); the
+# wrappers only combine columns of that tensor.  Batched: rewards / infos are ``[B, N]`` CUDA tensors (infos: two
+# dicts of tensors); reference-compatible single env: Python floats and the reference's list-of-dict infos.
+# ------------------------------------------------------------------------------------------------------------
+
+CAMERA_REWARD_KEYS = ('raw_reward', 'coverage_rate', 'real_coverage_rate', 'mean_transport_rate',
+                      'soft_coverage_score', 'num_tracked', 'baseline')
+TARGET_REWARD_KEYS = ('raw_reward', 'coverage_rate', 'real_coverage_rate', 'mean_transport_rate',
+                      'normalized_goal_distance', 'sparse_delivery', 'soft_coverage_score', 'is_tracked',
+                      'is_colliding', 'baseline')
+_REDUCERS = {
+    'mean': lambda x: x.mean(dim=-1, keepdim=True), 'sum': lambda x: x.sum(dim=-1, keepdim=True),
+    'max': lambda x: x.max(dim=-1, keepdim=True).values, 'min': lambda x: x.min(dim=-1, keepdim=True).values,
+}
+
+
+def _update_infos(base, infos, per_agent, shared=None):
+    """Merge ``{key: [B, N] tensor}`` into the infos of one team (dict of tensors, or the reference's list of dicts)."""
+    if base.batched:
+        infos.update(per_agent)
+        if shared:
+            infos.update(shared)
+        return
+    host = {k: v[0].tolist() for k, v in per_agent.items()}
+    for i, info in enumerate(infos):
+        for k, values in host.items():
+            info[k] = values[i]
+        if shared:
+            info.update(shared)
+
+
+class MoreTrainingInformation(Wrapper):
+    """mate/wrappers/more_training_information.py: more entries in the info dicts.  Cameras: ``num_tracked``,
+    ``is_sensed``; targets: ``goal``, ``goal_distance``, ``warehouse_distances``, ``individual_done``, ``is_tracked``,
+    ``is_colliding``; both: the private states of all agents and the view masks.  The entries that need the cargo
+    tables / the global state on the host (``state``, ``remaining_cargoes``, ``remaining_cargo_counts``,
+    ``awaiting_cargo_counts``, ``obstacle_states``) cost a device synchronisation and are added only with
+    ``full_observability=True`` (the default for the reference-compatible single env)."""
+
+    def __init__(self, env, full_observability=None):
+        assert not _has_wrapper(env, MoreTrainingInformation), f'You should not use wrapper `{type(self)}` more than once.'
+        super().__init__(env)
+        base = self.unwrapped
+        self.full_observability = (not base.batched) if full_observability is None else bool(full_observability)
+
+    def step(self, action):
+        results = self.env.step(action)
+        (camera_joint_observation, target_joint_observation), _, _, (camera_infos, target_infos) = results
+        base = self.unwrapped
+        cam_terms, tgt_terms = base.auxiliary_terms()
+        aux = base._aux  # pylint: disable=protected-access
+        if base.num_cameras:
+            _update_infos(base, camera_infos, {'num_tracked': cam_terms[..., 5].long(), 'is_sensed': cam_terms[..., 7] != 0})
+        _update_infos(base, target_infos, {
+            'goal': tgt_terms[..., 10].long(), 'goal_distance': tgt_terms[..., 11], 'warehouse_distances': tgt_terms[..., 12:16],
+            'individual_done': tgt_terms[..., 5] != 0, 'is_tracked': tgt_terms[..., 7] != 0, 'is_colliding': tgt_terms[..., 8] != 0,
+        })
+        # full observability (more_training_information.py:84-98)
+        offset = 13   # PRESERVED_DIM
+        shared = {
+            'camera_target_view_mask': aux['mask_ct'].bool(), 'camera_obstacle_view_mask': aux['mask_co'].bool(),
+            'target_camera_view_mask': aux['mask_tc'].bool(), 'target_obstacle_view_mask': aux['mask_to'].bool(),
+            'target_target_view_mask': aux['mask_tt'].bool(),
+        }
+        if base.batched:
+            shared['camera_states'] = camera_joint_observation[..., offset:offset + 9]
+            shared['target_states'] = target_joint_observation[..., offset:offset + 14]
+        else:
+            shared = {k: v[0].cpu().numpy() for k, v in shared.items()}
+            shared['camera_states'] = np.array(camera_joint_observation[..., offset:offset + 9])
+            shared['target_states'] = np.array(target_joint_observation[..., offset:offset + 14])
+        if self.full_observability:
+            remaining = np.asarray(base.remaining_cargoes)
+            shared.update(state=base.state(), obstacle_states=np.asarray(base.obstacle_states), remaining_cargoes=remaining,
+                          remaining_cargo_counts=remaining.sum(axis=-1), awaiting_cargo_counts=np.asarray(base.awaiting_cargo_counts))
+        if base.batched:
+            camera_infos.update(shared)
+            target_infos.update(shared)
+        else:
+            for info in list(camera_infos) + list(target_infos):
+                info.update({k: (v.copy() if hasattr(v, 'copy') else v) for k, v in shared.items()})
+        return results
+
+
+class _AuxiliaryRewards(Wrapper):
+    """Weighted sum of per-agent reward terms (shared implementation of the two wrappers below)."""
+
+    ACCEPTABLE_KEYS = ()
+    TEAM = 0   # index into the (camera, target) tuples
+
+    def __init__(self, env, coefficients, reduction='none'):
+        cls = type(self)
+        assert _has_wrapper(env, RepeatedRewardIndividualDone), (
+            f'You should use wrapper `{cls}` with wrapper `RepeatedRewardIndividualDone`. '
+            f'Please wrap the environment with wrapper `RepeatedRewardIndividualDone` first. Got env = {env}.')
+        assert not _has_wrapper(env, cls), f'You should not use wrapper `{cls}` more than once. Got env = {env}.'
+        assert reduction in ('mean', 'sum', 'max', 'min', 'none'), f'Invalid reduction method {reduction}.'
+        assert set(self.ACCEPTABLE_KEYS).issuperset(coefficients.keys()), (
+            f'The coefficient mapping only accepts keys in {self.ACCEPTABLE_KEYS}. '
+            f'Got list(coefficients.keys()) = {list(coefficients.keys())}.')
+        if 'soft_coverage_score' in coefficients:
+            raise NotImplementedError(
+                "'soft_coverage_score' needs the outer field-of-view boundary (mate/entities.py:419-448), which the CUDA "
+                'path does not build yet (DESIGN.md, section 7c); all other keys are supported')
+        self.coefficients = {}
+        for key, coefficient in coefficients.items():
+            assert callable(coefficient) or isinstance(coefficient, (float, int)), (
+                f'The argument `coefficient` should be a callable function or a float number. '
+                f'Got coefficients[{key!r}] = {coefficient!r}.')
+            self.coefficients[key] = coefficient if not isinstance(coefficient, int) else float(coefficient)
+        super().__init__(env)
+        self.episode_id = -1
+        self.reduction = reduction
+
+    def reset(self, **kwargs):
+        self.episode_id += 1
+        return self.env.reset(**kwargs)
+
+    def _terms(self, base):
+        raise NotImplementedError
+
+    def step(self, action):
+        observations, rewards, dones, infos = self.env.step(action)
+        base = self.unwrapped
+        terms = self._terms(base)                              # [B, N, K] in ACCEPTABLE_KEYS order
+        num_agents = terms.shape[1]
+        team_infos = infos[self.TEAM]
+        if num_agents == 0:
+            return observations, rewards, dones, infos
+        raw_reward = terms[..., 0]
+        reward = torch.zeros_like(raw_reward)
+        per_agent = {}
+        episode_step = base._aux['episode_step']  # pylint: disable=protected-access
+        for key, coefficient in self.coefficients.items():
+            value = terms[..., self.ACCEPTABLE_KEYS.index(key)]
+            if callable(coefficient):
+                if base.batched:   # vectorised call: agent ids [1, N], episode steps [B, 1], values [B, N]
+                    agent_ids = torch.arange(num_agents, device=value.device).unsqueeze(0)
+                    coefficient = coefficient(agent_ids, self.episode_id, episode_step.unsqueeze(-1), raw_reward, value)
+                else:              # the reference's call, one agent at a time
+                    coefficient = torch.tensor([[coefficient(i, self.episode_id, int(episode_step[0]), float(raw_reward[0, i]), float(value[0, i]))
+                                                 for i in range(num_agents)]], dtype=value.dtype, device=value.device)
+            reward = reward + coefficient * value
+            per_agent.setdefault(key, value)
+            per_agent[f'auxiliary_reward_{key}'] = value
+            per_agent[f'reward_coefficient_{key}'] = coefficient if torch.is_tensor(coefficient) else torch.full_like(value, float(coefficient))
+        per_agent['reward'] = reward
+        if self.reduction in _REDUCERS:
+            reward = _REDUCERS[self.reduction](reward).expand(-1, num_agents)
+            per_agent['shared_reward'] = reward
+        if base.batched:
+            for key in self.coefficients:   # info.setdefault(key, ...): keep what an inner wrapper / the env already put there
+                if key in team_infos:
+                    per_agent.pop(key, None)
+            team_infos.update(per_agent)
+            team_reward = reward
+        else:
+            host = {k: v[0].tolist() for k, v in per_agent.items()}
+            for i, info in enumerate(team_infos):
+                for k, values in host.items():
+                    if k in self.coefficients:
+                        info.setdefault(k, values[i])
+                    else:
+                        info[k] = values[i]
+            team_reward = reward[0].tolist()
+        rewards = (team_reward, rewards[1]) if self.TEAM == 0 else (rewards[0], team_reward)
+        return observations, rewards, dones, infos
+
+
+class AuxiliaryCameraRewards(_AuxiliaryRewards):
+    """mate/wrappers/auxiliary_camera_rewards.py: weighted sum of ``raw_reward``, ``coverage_rate``,
+    ``real_coverage_rate``, ``mean_transport_rate``, ``num_tracked`` and ``baseline`` per camera
+    (``soft_coverage_score`` is not built yet)."""
+
+    ACCEPTABLE_KEYS = CAMERA_REWARD_KEYS
+    TEAM = 0
+
+    def _terms(self, base):
+        return base.auxiliary_terms()[0][..., :len(CAMERA_REWARD_KEYS)]
+
+
+class AuxiliaryTargetRewards(_AuxiliaryRewards):
+    """mate/wrappers/auxiliary_target_rewards.py: weighted sum of ``raw_reward``, ``coverage_rate``,
+    ``real_coverage_rate``, ``mean_transport_rate``, ``normalized_goal_distance``, ``sparse_delivery``,
+    ``is_tracked``, ``is_colliding`` and ``baseline`` per target (``soft_coverage_score`` is not built yet)."""
+
+    ACCEPTABLE_KEYS = TARGET_REWARD_KEYS
+    TEAM = 1
+
+    def _terms(self, base):
+        return base.auxiliary_terms()[1][..., :len(TARGET_REWARD_KEYS)]

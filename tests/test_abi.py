@@ -33,14 +33,14 @@ def test_header_and_binding_agree():
 def test_library_exports_every_declared_symbol(lib):
     for name in declared_symbols():
         assert hasattr(lib, name), name
-    assert lib.mate_b200_abi_version() == 1
+    assert lib.mate_b200_abi_version() == 2
 
 
 def test_struct_layouts_match_the_header(lib):
     # sizes computed from the header's field lists (LP64)
     assert ctypes.sizeof(_abi.MateConfig) == 10 * 4 + 11 * 8 + 3 * 8
     assert ctypes.sizeof(_abi.MateStateView) == 16 * 8
-    assert ctypes.sizeof(_abi.MateStepAux) == 12 * 8
+    assert ctypes.sizeof(_abi.MateStepAux) == 14 * 8
     assert ctypes.sizeof(_abi.MateReplay) == 2 * 8
 
 

@@ -1,0 +1,182 @@
+"""Auxiliary-reward / training-information wrappers against the reference's own wrapper
+classes: ``tests/golden/aux_*.npz`` hold, for sampled steps of greedy-agent episodes, the state before the step, the
+action, the recorded draws, and what ``MoreTrainingInformation`` / ``AuxiliaryCameraRewards`` /
+``AuxiliaryTargetRewards`` of the reference reported after it (written by ``oracle/gen_aux_golden.py``)."""
+
+import glob
+import os
+
+import numpy as np
+import pytest
+
+import golden_util as gu
+
+NAMES = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(gu.GOLDEN_DIR, 'aux_*.npz')))
+WAREHOUSES = np.array([[925.0, 925.0], [-925.0, 925.0], [-925.0, -925.0], [925.0, -925.0]])   # constants.py:70-72
+CAM_SOFT, TGT_SOFT = 4, 6   # column of soft_coverage_score in the two key lists
+
+
+def terms_numpy(g, i):
+    """Plain restatement of the terms (auxiliary_camera_rewards.py:140-149, auxiliary_target_rewards.py:135-177,
+    more_training_information.py:61-82) from the recorded after-step pieces of sample i."""
+    nc, nt, _ = (int(x) for x in g['cfg_counts'])
+    mask_ct, mask_tc = g['a_out_mask_ct'][i].astype(bool), g['a_out_mask_tc'][i].astype(bool)
+    cov = g['a_out_tgt_terms'][i][0, 1:4]
+    cam = np.zeros((nc, 8))
+    for c in range(nc):
+        cam[c] = [g['a_out_team_reward'][i][0], cov[0], cov[1], cov[2], 0.0, mask_ct[c].sum(), 1.0, mask_tc[:, c].any()]
+    tgt = np.zeros((nt, 16))
+    xy, empty, goal = g['a_out_tgt_xy'][i], g['a_out_tgt_empty_bits'][i].astype(bool), g['a_out_tgt_goal'][i]
+    for t in range(nt):
+        wd = np.maximum(np.linalg.norm(xy[t] - WAREHOUSES, axis=-1) - 75.0, 0.0)
+        if goal[t] >= 0:
+            goal_distance = wd[goal[t]]
+        elif not empty[t].all():
+            goal_distance = wd[~empty[t]].min()
+        else:
+            goal_distance = 1000.0
+        tgt[t, :10] = [g['a_out_team_reward'][i][1], cov[0], cov[1], cov[2], goal_distance / 2000.0, g['a_out_tgt_individual_done'][i][t],
+                       0.0, mask_ct[:, t].any() if nc else 0.0, g['a_out_tgt_is_colliding'][i][t], 1.0]
+        tgt[t, 10] = goal[t]
+        tgt[t, 11] = wd[goal[t]] if goal[t] >= 0 else 1000.0
+        tgt[t, 12:16] = wd
+    return cam, tgt
+
+
+def expected(g):
+    """Golden terms with the soft coverage score (not built) zeroed, and the rewards without its contribution."""
+    cam_terms, tgt_terms = g['a_out_cam_terms'].copy(), g['a_out_tgt_terms'].copy()
+    nc = int(g['cfg_counts'][0])
+    cam_reward = g['a_out_cam_reward'] - g['camera_coef'][CAM_SOFT] * cam_terms[..., CAM_SOFT] if nc else g['a_out_cam_reward']
+    tgt_reward = g['a_out_tgt_reward'] - g['target_coef'][TGT_SOFT] * tgt_terms[..., TGT_SOFT]
+    cam_terms[..., CAM_SOFT] = 0.0
+    tgt_terms[..., TGT_SOFT] = 0.0
+    return cam_terms, tgt_terms, cam_reward, tgt_reward
+
+
+@pytest.mark.parametrize('name', NAMES)
+def test_term_formulas_match_the_reference_wrappers(name):
+    """CPU: the formulas the CUDA kernel implements reproduce the reference wrappers' info entries."""
+    g = gu.load(name)
+    cam_terms, tgt_terms, _, _ = expected(g)
+    for i in range(int(g['count'])):
+        cam, tgt = terms_numpy(g, i)
+        np.testing.assert_allclose(cam[:, :7], cam_terms[i], rtol=1e-12, atol=1e-12)
+        np.testing.assert_allclose(tgt[:, :10], tgt_terms[i], rtol=1e-12, atol=1e-12)
+        np.testing.assert_array_equal(cam[:, 5], g['a_out_cam_num_tracked'][i])
+        np.testing.assert_array_equal(cam[:, 7], g['a_out_cam_is_sensed'][i])
+        np.testing.assert_allclose(tgt[:, 11], g['a_out_tgt_goal_distance'][i], rtol=1e-12, atol=1e-12)
+        np.testing.assert_allclose(tgt[:, 12:16], g['a_out_tgt_warehouse_distances'][i], rtol=1e-12, atol=1e-12)
+        np.testing.assert_array_equal(tgt[:, 7], g['a_out_tgt_is_tracked'][i])
+
+
+def test_wrapper_assertions():
+    """Ordering / key rules of the reference (auxiliary_camera_rewards.py:60-82)."""
+    from mate_b200 import wrappers
+
+    class Fake:
+        num_cameras = 4
+        unwrapped = None
+
+    fake = Fake()
+    fake.unwrapped = fake
+    inner = wrappers.Wrapper(fake)
+    with pytest.raises(AssertionError):
+        wrappers.AuxiliaryCameraRewards(inner, coefficients={'raw_reward': 1.0})   # needs RepeatedRewardIndividualDone
+    repeated = wrappers.RepeatedRewardIndividualDone(inner)
+    with pytest.raises(AssertionError):
+        wrappers.AuxiliaryCameraRewards(repeated, coefficients={'no_such_key': 1.0})
+    with pytest.raises(AssertionError):
+        wrappers.AuxiliaryTargetRewards(repeated, coefficients={'raw_reward': 1.0}, reduction='median')
+    with pytest.raises(NotImplementedError):
+        wrappers.AuxiliaryCameraRewards(repeated, coefficients={'soft_coverage_score': 1.0})
+    once = wrappers.AuxiliaryTargetRewards(repeated, coefficients={'raw_reward': 1.0})
+    with pytest.raises(AssertionError):
+        wrappers.AuxiliaryTargetRewards(once, coefficients={'raw_reward': 1.0})
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('name', NAMES)
+def test_auxiliary_wrappers_match_the_reference(name):
+    """GPU: every sampled reference state is injected into its own environment of one batch, the recorded step is
+    repeated (recorded action and draws), and the wrapper stack's rewards and infos are compared with the
+    reference's."""
+    import torch
+
+    import mate_b200
+
+    g = gu.load(name)
+    nc, nt, _ = (int(x) for x in g['cfg_counts'])
+    count = int(g['count'])
+    config = str(g['config_name'])
+    cam_keys, tgt_keys = [str(k) for k in g['camera_keys']], [str(k) for k in g['target_keys']]
+    cam_coef = {k: float(v) for k, v in zip(cam_keys, g['camera_coef']) if k != 'soft_coverage_score'}
+    tgt_coef = {k: float(v) for k, v in zip(tgt_keys, g['target_coef']) if k != 'soft_coverage_score'}
+    wrappers = [mate_b200.MoreTrainingInformation, mate_b200.RepeatedRewardIndividualDone]
+    if nc:
+        wrappers.append(lambda env: mate_b200.AuxiliaryCameraRewards(env, coefficients=cam_coef))
+    wrappers.append(lambda env: mate_b200.AuxiliaryTargetRewards(env, coefficients=tgt_coef))
+    env = mate_b200.make('MultiAgentTracking-v0', config=config, num_envs=count, wrappers=wrappers)
+    base = env.unwrapped
+    base.set_state(gu.stack_states([gu.state_arrays(g, 'a_', i) for i in range(count)]))
+    base.replay_next = (g['a_transmit'], g['a_goal_choice'])
+    cam_act = torch.from_numpy(g['a_cam_act'].astype(np.float32)).cuda()
+    tgt_act = torch.from_numpy(g['a_tgt_act'].astype(np.float32)).cuda()
+    _, (cam_reward, tgt_reward), _, (cam_infos, tgt_infos) = env.step((cam_act, tgt_act))
+    torch.cuda.synchronize()
+    exp_cam_terms, exp_tgt_terms, exp_cam_reward, exp_tgt_reward = expected(g)
+    cam_terms, tgt_terms = (t.cpu().numpy() for t in base.auxiliary_terms())
+    # the step itself must have reproduced the reference (masks bit-exact), otherwise the comparison is void
+    np.testing.assert_array_equal(base.camera_target_view_mask.cpu().numpy(), g['a_out_mask_ct'].astype(bool))
+    np.testing.assert_array_equal(base.target_camera_view_mask.cpu().numpy(), g['a_out_mask_tc'].astype(bool))
+    tol = dict(rtol=1e-5, atol=1e-5)
+    if nc:
+        np.testing.assert_allclose(cam_terms[..., :7], exp_cam_terms, **tol)
+        np.testing.assert_allclose(cam_reward.cpu().numpy(), exp_cam_reward, rtol=1e-5, atol=1e-3)
+        np.testing.assert_array_equal(cam_infos['num_tracked'].cpu().numpy(), g['a_out_cam_num_tracked'])
+        np.testing.assert_array_equal(cam_infos['is_sensed'].cpu().numpy(), g['a_out_cam_is_sensed'].astype(bool))
+        np.testing.assert_allclose(cam_infos['auxiliary_reward_coverage_rate'].cpu().numpy(), exp_cam_terms[..., 1], **tol)
+    np.testing.assert_allclose(tgt_terms[..., :10], exp_tgt_terms, **tol)
+    np.testing.assert_allclose(tgt_reward.cpu().numpy(), exp_tgt_reward, rtol=1e-5, atol=1e-3)
+    np.testing.assert_array_equal(tgt_infos['goal'].cpu().numpy(), g['a_out_tgt_goal'])
+    # distances: float32 of a float64 norm minus the warehouse radius
+    np.testing.assert_allclose(tgt_infos['goal_distance'].cpu().numpy(), g['a_out_tgt_goal_distance'], rtol=1e-5, atol=2e-4)
+    np.testing.assert_allclose(tgt_infos['warehouse_distances'].cpu().numpy(), g['a_out_tgt_warehouse_distances'], rtol=1e-5, atol=2e-4)
+    np.testing.assert_array_equal(tgt_infos['individual_done'].cpu().numpy(), g['a_out_tgt_individual_done'].astype(bool))
+    np.testing.assert_array_equal(tgt_infos['is_tracked'].cpu().numpy(), g['a_out_tgt_is_tracked'].astype(bool))
+    np.testing.assert_array_equal(tgt_infos['is_colliding'].cpu().numpy(), g['a_out_tgt_is_colliding'].astype(bool))
+    np.testing.assert_allclose(tgt_infos['auxiliary_reward_normalized_goal_distance'].cpu().numpy(), exp_tgt_terms[..., 4], **tol)
+    base.close()
+
+
+@pytest.mark.gpu
+def test_reductions_and_callable_coefficients():
+    """`reduction` shares one reward per team; a callable coefficient is called once per key with tensors."""
+    import torch
+
+    import mate_b200
+
+    B = 32
+    calls = []
+
+    def schedule(agent_ids, episode_id, episode_step, raw_reward, value):
+        calls.append((tuple(agent_ids.shape), episode_id, tuple(episode_step.shape), tuple(value.shape)))
+        return 0.5 + 0.0 * value
+
+    env = mate_b200.make('MultiAgentTracking-v0', config='MATE-4v8-9.yaml', num_envs=B, wrappers=[
+        mate_b200.RepeatedRewardIndividualDone,
+        lambda e: mate_b200.AuxiliaryCameraRewards(e, coefficients={'num_tracked': schedule, 'baseline': 2}, reduction='mean'),
+        lambda e: mate_b200.AuxiliaryTargetRewards(e, coefficients={'raw_reward': 1.0, 'is_tracked': -1.0}, reduction='min')])
+    env.reset(seed=11)
+    rng = np.random.RandomState(1)
+    cam_act = torch.from_numpy((rng.uniform(-1, 1, (B, 4, 2)) * [5.0, 2.5]).astype(np.float32)).cuda()
+    tgt_act = torch.from_numpy((rng.uniform(-1, 1, (B, 8, 2)) * 20.0).astype(np.float32)).cuda()
+    _, (cam_reward, tgt_reward), _, (cam_infos, tgt_infos) = env.step((cam_act, tgt_act))
+    assert calls == [((1, 4), 0, (B, 1), (B, 4))]
+    individual = 0.5 * cam_infos['auxiliary_reward_num_tracked'] + 2.0
+    assert torch.allclose(cam_infos['reward'], individual)
+    assert torch.allclose(cam_reward, individual.mean(dim=-1, keepdim=True).expand(-1, 4))
+    assert torch.equal(cam_infos['shared_reward'], cam_reward)
+    individual = tgt_infos['auxiliary_reward_raw_reward'] - tgt_infos['auxiliary_reward_is_tracked']
+    assert torch.allclose(tgt_reward, individual.min(dim=-1, keepdim=True).values.expand(-1, 8))
+    env.unwrapped.close()
