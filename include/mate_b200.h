@@ -206,6 +206,14 @@ int mate_b200_transform_observations(MateSim* sim, float* cam_obs, float* tgt_ob
                                      int32_t num_ops, const float* cam_affine, const float* tgt_affine,
                                      void* stream);
 
+/* Camera.sight_range_at (mate/entities.py:507-511): value of the sampled field-of-view polyline of camera
+ * camera[i] of environment env[i] at bearing angle_deg[i] (any angle; normalised like the reference), for n
+ * queries.  The polyline (Camera.add_obstacles, entities.py:362-479) is never materialised: this evaluates the
+ * same routine the step kernel uses for its occlusion tests, which makes the routine testable against the
+ * reference's tables directly.  All pointers are dev pointers. */
+int mate_b200_fov_range(MateSim* sim, const int32_t* env, const int32_t* camera, const double* angle_deg,
+                        double* out, int64_t n, void* stream);
+
 /* Per-agent terms of the reference's auxiliary-reward and training-information wrappers (SURVEY.md section
  * 8f, N3) from the auxiliary outputs of the LAST step (so they describe the finished step even where the
  * environment was auto-reset), one pass, no host round trip:

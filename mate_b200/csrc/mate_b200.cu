@@ -46,12 +46,18 @@ struct KernelInfo {
     void (*launch)(const Params&, int grid, cudaStream_t);
     int envs_per_cta, smem_bytes, dc, dt, epw;
     cudaError_t (*prepare)();
+    void (*launch_fov)(const Params&, const int32_t*, const int32_t*, const double*, double*, long long, cudaStream_t);
 };
 
 template <int NC, int NT, int NO>
 static void launch_shape2(const Params& p, int grid, cudaStream_t stream) {
     using S = Shape2<NC, NT, NO>;
     mate_step_kernel2<NC, NT, NO><<<grid, S::WARPS * 32, S::SMEM_BYTES, stream>>>(p);
+}
+template <int NC, int NT, int NO>
+static void launch_fov_shape(const Params& p, const int32_t* env, const int32_t* camera, const double* angle, double* out,
+                             long long n, cudaStream_t stream) {
+    fov_range_kernel<NC, NO><<<(unsigned)((n + 127) / 128), 128, 0, stream>>>(p, env, camera, angle, out, n);
 }
 template <int NC, int NT, int NO>
 static cudaError_t prepare_shape2() {
@@ -78,7 +84,7 @@ static bool find_kernel(int nc, int nt, int no, KernelInfo* out) {
         using S = Shape2<NC, NT, NO>;                                                          \
         *out = KernelInfo{&launch_wrappers_shape<NC, NT, NO>, &prepare_wrappers_shape<NC, NT, NO>,       \
                           &launch_shape2<NC, NT, NO>, S::ENVS_PER_CTA, S::SMEM_BYTES, S::DC, S::DT, \
-                          32, &prepare_shape2<NC, NT, NO>};                                    \
+                          32, &prepare_shape2<NC, NT, NO>, &launch_fov_shape<NC, NT, NO>};       \
         return true;                                                                           \
     }
     MATE_SHAPES(X)
@@ -288,6 +294,19 @@ extern "C" int mate_b200_obs_dims(const MateSim* sim, int32_t* cam_dim, int32_t*
     if (!sim) return fail(MATE_EINVAL, "null handle");
     if (cam_dim) *cam_dim = sim->kernel.dc;
     if (tgt_dim) *tgt_dim = sim->kernel.dt;
+    return MATE_OK;
+}
+
+extern "C" int mate_b200_fov_range(MateSim* sim, const int32_t* env, const int32_t* camera, const double* angle_deg,
+                                   double* out, int64_t n, void* stream) {
+    if (!sim || !env || !camera || !angle_deg || !out || n < 0) return fail(MATE_EINVAL, "bad argument");
+    if (sim->cfg.num_cameras == 0) return fail(MATE_EINVAL, "the configuration has no cameras");
+    if (n == 0) return MATE_OK;
+    CUDA_TRY(cudaSetDevice(sim->device));
+    sim->kernel.launch_fov(sim->base, env, camera, angle_deg, out, n, (cudaStream_t)stream);
+    sim->launches += 1;
+    cudaError_t err = cudaGetLastError();
+    if (err != cudaSuccess) return fail(MATE_ECUDA, std::string("fov_range launch: ") + cudaGetErrorString(err));
     return MATE_OK;
 }
 

@@ -692,6 +692,26 @@ __device__ __noinline__ void pack_observations(const Params& p, const int env0, 
     if (S::BULK && MATE2_COPYOUT == 0 && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
 
+// Camera.sight_range_at (entities.py:507-511) for a list of (environment, camera, bearing) queries: the same
+// on-the-fly polyline evaluation the occlusion tests use, exposed for direct comparison with the reference's tables.
+template <int NC, int NO>
+__global__ void fov_range_kernel(const Params p, const int32_t* __restrict__ env, const int32_t* __restrict__ camera,
+                                 const double* __restrict__ angle_deg, double* __restrict__ out, long long n) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int e = min(max(env[i], 0), p.num_envs - 1), c = min(max(camera[i], 0), (NC > 0 ? NC : 1) - 1);
+    double a = fmod(angle_deg[i] + 180.0, 360.0);   // mate/utils.py:155-158
+    if (a < 0.0) a += 360.0;
+    a -= 180.0;
+    if (NC == 0) { out[i] = 0.0; return; }
+    if (NO == 0) { out[i] = p.cam_rmax; return; }
+    const size_t bp = p.bpad;
+    double sn, cs;
+    sincospi(a * (1.0 / 180.0), &sn, &cs);
+    out[i] = sight_range_at<NO>(ObsRef{p.obs_x + e, p.obs_y + e, p.obs_r + e, bp}, p.cam_x[(size_t)c * bp + e],
+                                p.cam_y[(size_t)c * bp + e], p.cam_rmax, a, cs, sn);
+}
+
 // =============================================================================================
 // The fused kernel
 // =============================================================================================

@@ -210,6 +210,19 @@ class BatchedSim:
         self._apply_observation_wrappers()
         return self.cam_obs, self.tgt_obs
 
+    def fov_range(self, env, camera, angle_deg):
+        """``Camera.sight_range_at`` (mate/entities.py:507-511) for equally shaped arrays of environment indices,
+        camera indices and bearings in degrees; float64 tensor of the same shape."""
+        env = torch.as_tensor(env, device=self.device).to(torch.int32).contiguous()
+        camera = torch.as_tensor(camera, device=self.device).to(torch.int32).contiguous()
+        angle = torch.as_tensor(angle_deg, device=self.device).to(torch.float64).contiguous()
+        assert env.shape == camera.shape == angle.shape
+        out = torch.empty_like(angle)
+        with torch.cuda.device(self.device):
+            _check(self.lib, self.lib.mate_b200_fov_range(self.handle, _dptr(env), _dptr(camera), _dptr(angle), _dptr(out),
+                                                          angle.numel(), self._stream()))
+        return out
+
     def auxiliary_terms(self):
         """Per-agent terms of the auxiliary-reward / training-information wrappers for the LAST step
         (mate_b200_auxiliary_terms): ``(cam_terms [B, Nc, CAM_TERMS], tgt_terms [B, Nt, TGT_TERMS])``."""

@@ -1,0 +1,82 @@
+"""The on-the-fly field-of-view polyline of the CUDA path (``sight_range_at``, never materialised) against the
+reference's own tables ``Camera.sight_range_func.x/.y``: the fixtures
+hold the table of every camera after the reference's ``reset`` (``oracle/gen_golden.py``)."""
+
+import numpy as np
+import pytest
+
+import golden_util as gu
+from test_oracle_golden import tangent_ray_mask
+
+
+def _cases():
+    for name in gu.reset_names():
+        yield name, 'reset'
+    for name in gu.trace_names():
+        yield name, 'trace'
+
+
+def _tables(g, kind):
+    """[(state arrays, [(phi, rho) per camera], cam_xy, obs_xyr)] of a fixture."""
+    nc = int(g['cfg_counts'][0])
+    if kind == 'trace':
+        off = g['fov_off']
+        tables = [(g['fov_phi'][off[c]:off[c + 1]], g['fov_rho'][off[c]:off[c + 1]]) for c in range(nc)]
+        return [(gu.state_arrays(g), tables, g['init_cam_xy'], g['init_obs_xyr'])]
+    out = []
+    lens = g['reset_fov_phi_len']
+    offs_all = np.concatenate([[0], np.cumsum(lens)])
+    for i in range(int(g['count'])):
+        off, base = g['reset_fov_off'][i], offs_all[i]
+        tables = [(g['reset_fov_phi'][base + off[c]: base + off[c + 1]], g['reset_fov_rho'][base + off[c]: base + off[c + 1]])
+                  for c in range(nc)]
+        out.append((gu.state_arrays(g, 'reset_', i), tables, g['reset_cam_xy'][i], g['reset_obs_xyr'][i]))
+    return out
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('name,kind', list(_cases()))
+def test_fov_range_matches_the_reference_tables(name, kind):
+    import torch
+
+    from mate_b200.sim import BatchedSim
+
+    g = gu.load(name)
+    cfg = gu.flat_config(g)
+    nc, no = cfg['num_cameras'], cfg['num_obstacles']
+    if nc == 0:
+        pytest.skip('no cameras')
+    rmax = cfg['camera_max_sight_range']
+    cases = _tables(g, kind)
+    sim = BatchedSim(cfg, len(cases), device=0)
+    sim.set_state(gu.stack_states([c[0] for c in cases]))
+    rng = np.random.RandomState(5)
+    checked = skipped = 0
+    for i, (_, tables, cam_xy, obs_xyr) in enumerate(cases):
+        for c, (phi, rho) in enumerate(tables):
+            tangent = tangent_ray_mask(phi, cam_xy[c], obs_xyr, rmax) if no else np.zeros(len(phi), dtype=bool)
+            # (1) at the table's own sample angles (np.interp returns the sample itself); the closing sample
+            #     phi[0] + 360 normalises to phi[0]
+            got = sim.fov_range(np.full(len(phi), i), np.full(len(phi), c), phi).cpu().numpy()
+            ok = ~tangent
+            ok[-1] = ok[0]
+            # duplicates of one angle keep the smaller range (entities.py:455-462): the table has one entry per angle
+            np.testing.assert_allclose(got[ok], rho[ok], rtol=0, atol=1e-7, err_msg=f'{name} state {i} camera {c} samples')
+            assert (got[~ok] >= rho[~ok] - 1e-7).all()
+            # (2) between the samples: linear interpolation like scipy's interp1d / np.interp
+            q = rng.uniform(-180.0, 180.0, size=4000)
+            k = np.searchsorted(phi, q, side='right')        # phi[k-1] <= q < phi[k]
+            k = np.clip(k, 1, len(phi) - 1)
+            usable = ~(tangent[k - 1] | tangent[k]) & (q >= phi[0]) & (q <= phi[-1])
+            want = np.interp(q, phi, rho)
+            got = sim.fov_range(np.full(len(q), i), np.full(len(q), c), q).cpu().numpy()
+            # steep flanks: an error of 1e-12 degrees in a sample angle moves the value by slope * 1e-12
+            slope = np.abs((rho[k] - rho[k - 1]) / np.maximum(phi[k] - phi[k - 1], 1e-300))
+            tol = 1e-7 + slope * 1e-9
+            bad = usable & (np.abs(got - want) > tol)
+            assert not bad.any(), (name, i, c, q[bad][:5], got[bad][:5], want[bad][:5])
+            checked += int(usable.sum())
+            skipped += int((~usable).sum())
+    torch.cuda.synchronize()
+    assert checked > 10 * skipped   # the tangent-ray brackets are a small minority
+    sim.close()
