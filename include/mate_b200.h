@@ -219,7 +219,7 @@ int mate_b200_fov_range(MateSim* sim, const int32_t* env, const int32_t* camera,
  * environment was auto-reset), one pass, no host round trip:
  *   cam_terms [B, Nc, MATE_CAM_TERMS]: the keys of AuxiliaryCameraRewards.ACCEPTABLE_KEYS in order
  *     (mate/wrappers/auxiliary_camera_rewards.py:38-46, 140-149): raw_reward, coverage_rate, real_coverage_rate,
- *     mean_transport_rate, soft_coverage_score (not computed: 0), num_tracked, baseline; then is_sensed
+ *     mean_transport_rate, soft_coverage_score (0 unless soft_matrix is given), num_tracked, baseline; then is_sensed
  *     (mate/wrappers/more_training_information.py:61-65);
  *   tgt_terms [B, Nt, MATE_TGT_TERMS]: the keys of AuxiliaryTargetRewards.ACCEPTABLE_KEYS in order
  *     (mate/wrappers/auxiliary_target_rewards.py:135-177): raw_reward, coverage_rate, real_coverage_rate,
@@ -231,8 +231,16 @@ int mate_b200_fov_range(MateSim* sim, const int32_t* env, const int32_t* camera,
  * by mate_b200_step. */
 #define MATE_CAM_TERMS 8
 #define MATE_TGT_TERMS 16
-int mate_b200_auxiliary_terms(MateSim* sim, const MateStepAux* aux, const float* rewards, float* cam_terms,
-                              float* tgt_terms, void* stream);
+int mate_b200_auxiliary_terms(MateSim* sim, const MateStepAux* aux, const float* rewards, const float* soft_matrix,
+                              float* cam_terms, float* tgt_terms, void* stream);
+
+/* AuxiliaryCameraRewards.compute_soft_coverage_scores (mate/wrappers/auxiliary_camera_rewards.py:182-233): the
+ * [B, Nc, Nt] matrix of signed distances of every target to the boundary of every camera's field of view (outer
+ * polyline of Camera.add_obstacles / boundary_between(outer=True), mate/entities.py:362-479, 484-511, restricted
+ * to the current sector), in units of the inscribed-circle radius.  mask_ct [B, Nc, Nt] as written by the last
+ * step; `done` (nullable, [B]) marks the environments that were auto-reset in that step: they get zeros.  Pass the
+ * result as `soft_matrix` to mate_b200_auxiliary_terms to fill the soft_coverage_score columns. */
+int mate_b200_soft_coverage(MateSim* sim, const uint8_t* mask_ct, const uint8_t* done, float* soft_matrix, void* stream);
 
 /* DiscreteCamera / DiscreteTarget.action (mate/wrappers/discrete_action_spaces.py:98-117, 204-228): grid
  * indices (dev int64 [count]) -> continuous actions (dev float32 [count][2]) through the wrapper's table

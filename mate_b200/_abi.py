@@ -175,9 +175,10 @@ def load_library():
     lib.mate_b200_transform_observations.argtypes = [void_p, void_p, void_p, c_int32_p, ctypes.c_int32, void_p, void_p, void_p]
     lib.mate_b200_decode_actions.argtypes = [void_p, void_p, ctypes.c_int32, void_p, ctypes.c_int64, void_p]
     lib.mate_b200_fov_range.argtypes = [void_p, void_p, void_p, void_p, void_p, ctypes.c_int64, void_p]
-    lib.mate_b200_auxiliary_terms.argtypes = [void_p, ctypes.POINTER(MateStepAux), void_p, void_p, void_p, void_p]
+    lib.mate_b200_auxiliary_terms.argtypes = [void_p, ctypes.POINTER(MateStepAux), void_p, void_p, void_p, void_p, void_p]
+    lib.mate_b200_soft_coverage.argtypes = [void_p, void_p, void_p, void_p, void_p]
     for name in ('create', 'destroy', 'obs_dims', 'reset', 'step', 'observe', 'step_host',
-                 'get_state', 'set_state', 'episode_stats', 'transform_observations', 'decode_actions', 'auxiliary_terms', 'fov_range'):
+                 'get_state', 'set_state', 'episode_stats', 'transform_observations', 'decode_actions', 'auxiliary_terms', 'fov_range', 'soft_coverage'):
         getattr(lib, 'mate_b200_' + name).restype = ctypes.c_int
     _LIB = lib
     return lib
@@ -188,7 +189,7 @@ EXPORTED_SYMBOLS = [
     'mate_b200_obs_dims', 'mate_b200_reset', 'mate_b200_step', 'mate_b200_observe',
     'mate_b200_step_host', 'mate_b200_get_state', 'mate_b200_set_state',
     'mate_b200_episode_stats', 'mate_b200_launch_count', 'mate_b200_transform_observations',
-    'mate_b200_decode_actions', 'mate_b200_auxiliary_terms', 'mate_b200_fov_range',
+    'mate_b200_decode_actions', 'mate_b200_auxiliary_terms', 'mate_b200_fov_range', 'mate_b200_soft_coverage',
 ]
 
 # observation wrapper codes (include/mate_b200.h)

@@ -47,6 +47,7 @@ struct KernelInfo {
     int envs_per_cta, smem_bytes, dc, dt, epw;
     cudaError_t (*prepare)();
     void (*launch_fov)(const Params&, const int32_t*, const int32_t*, const double*, double*, long long, cudaStream_t);
+    void (*launch_soft)(const Params&, const uint8_t*, const uint8_t*, float*, cudaStream_t);
 };
 
 template <int NC, int NT, int NO>
@@ -58,6 +59,11 @@ template <int NC, int NT, int NO>
 static void launch_fov_shape(const Params& p, const int32_t* env, const int32_t* camera, const double* angle, double* out,
                              long long n, cudaStream_t stream) {
     fov_range_kernel<NC, NO><<<(unsigned)((n + 127) / 128), 128, 0, stream>>>(p, env, camera, angle, out, n);
+}
+template <int NC, int NT, int NO>
+static void launch_soft_shape(const Params& p, const uint8_t* mask_ct, const uint8_t* done, float* out, cudaStream_t stream) {
+    const long long warps = (long long)p.num_envs * (NC > 0 ? NC : 1);
+    soft_coverage_kernel<NC, NT, NO><<<(unsigned)((warps + 3) / 4), 128, 0, stream>>>(p, mask_ct, done, out);
 }
 template <int NC, int NT, int NO>
 static cudaError_t prepare_shape2() {
@@ -84,7 +90,8 @@ static bool find_kernel(int nc, int nt, int no, KernelInfo* out) {
         using S = Shape2<NC, NT, NO>;                                                          \
         *out = KernelInfo{&launch_wrappers_shape<NC, NT, NO>, &prepare_wrappers_shape<NC, NT, NO>,       \
                           &launch_shape2<NC, NT, NO>, S::ENVS_PER_CTA, S::SMEM_BYTES, S::DC, S::DT, \
-                          32, &prepare_shape2<NC, NT, NO>, &launch_fov_shape<NC, NT, NO>};       \
+                          32, &prepare_shape2<NC, NT, NO>, &launch_fov_shape<NC, NT, NO>,        \
+                          &launch_soft_shape<NC, NT, NO>};                                      \
         return true;                                                                           \
     }
     MATE_SHAPES(X)
@@ -337,8 +344,19 @@ extern "C" int mate_b200_transform_observations(MateSim* sim, float* cam_obs, fl
     return MATE_OK;
 }
 
-extern "C" int mate_b200_auxiliary_terms(MateSim* sim, const MateStepAux* aux, const float* rewards, float* cam_terms,
-                                         float* tgt_terms, void* stream) {
+extern "C" int mate_b200_soft_coverage(MateSim* sim, const uint8_t* mask_ct, const uint8_t* done, float* soft_matrix, void* stream) {
+    if (!sim || !mask_ct || !soft_matrix) return fail(MATE_EINVAL, "null argument");
+    if (sim->cfg.num_cameras == 0) return fail(MATE_EINVAL, "the configuration has no cameras");
+    CUDA_TRY(cudaSetDevice(sim->device));
+    sim->kernel.launch_soft(sim->base, mask_ct, done, soft_matrix, (cudaStream_t)stream);
+    sim->launches += 1;
+    cudaError_t err = cudaGetLastError();
+    if (err != cudaSuccess) return fail(MATE_ECUDA, std::string("soft coverage launch: ") + cudaGetErrorString(err));
+    return MATE_OK;
+}
+
+extern "C" int mate_b200_auxiliary_terms(MateSim* sim, const MateStepAux* aux, const float* rewards, const float* soft_matrix,
+                                         float* cam_terms, float* tgt_terms, void* stream) {
     if (!sim || !aux || !rewards || !tgt_terms || (sim->cfg.num_cameras > 0 && !cam_terms)) return fail(MATE_EINVAL, "null argument");
     if (!aux->coverage || !aux->target_dones || !aux->is_colliding || !aux->warehouse_dist || !aux->tgt_goal || !aux->tgt_empty_bits ||
         (sim->cfg.num_cameras > 0 && (!aux->mask_ct || !aux->mask_tc)))
@@ -346,7 +364,7 @@ extern "C" int mate_b200_auxiliary_terms(MateSim* sim, const MateStepAux* aux, c
     CUDA_TRY(cudaSetDevice(sim->device));
     const int threads = 128;
     aux_terms_kernel<<<(sim->num_envs + threads - 1) / threads, threads, 0, (cudaStream_t)stream>>>(
-        *aux, rewards, cam_terms, tgt_terms, sim->num_envs, sim->cfg.num_cameras, sim->cfg.num_targets);
+        *aux, rewards, soft_matrix, cam_terms, tgt_terms, sim->num_envs, sim->cfg.num_cameras, sim->cfg.num_targets);
     sim->launches += 1;
     cudaError_t err = cudaGetLastError();
     if (err != cudaSuccess) return fail(MATE_ECUDA, std::string("auxiliary terms launch: ") + cudaGetErrorString(err));

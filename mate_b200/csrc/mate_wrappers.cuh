@@ -255,8 +255,8 @@ __global__ void decode_actions_kernel(const int64_t* __restrict__ index, const f
 // (mate/wrappers/auxiliary_camera_rewards.py:140-149, auxiliary_target_rewards.py:135-177,
 // more_training_information.py:61-82) from the auxiliary outputs of the last step.  One thread per
 // environment: the inputs are ~150 bytes per environment, the outputs 4 (8 Nc + 16 Nt) bytes.
-__global__ void aux_terms_kernel(const MateStepAux ax, const float* __restrict__ rewards, float* __restrict__ cam_terms,
-                                 float* __restrict__ tgt_terms, int num_envs, int nc, int nt) {
+__global__ void aux_terms_kernel(const MateStepAux ax, const float* __restrict__ rewards, const float* __restrict__ soft,
+                                 float* __restrict__ cam_terms, float* __restrict__ tgt_terms, int num_envs, int nc, int nt) {
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= num_envs) return;
     const float cov = ax.coverage[(size_t)e * 3], cov_real = ax.coverage[(size_t)e * 3 + 1], transport = ax.coverage[(size_t)e * 3 + 2];
@@ -264,14 +264,21 @@ __global__ void aux_terms_kernel(const MateStepAux ax, const float* __restrict__
     uint32_t tracked = 0;   // bit t: some camera sees target t
     for (int c = 0; c < nc; ++c) {
         int num_tracked = 0, sensed = 0;
+        float soft_sum = 0.f, soft_max = -3.0e38f;   // auxiliary_camera_rewards.py:130-138
         for (int t = 0; t < nt; ++t) {
             const int seen = ax.mask_ct[((size_t)e * nc + c) * nt + t] != 0;
             num_tracked += seen;
             tracked |= (uint32_t)seen << t;
             sensed |= ax.mask_tc[((size_t)e * nt + t) * nc + c] != 0;
+            if (soft) {
+                const float v = soft[((size_t)e * nc + c) * nt + t];
+                soft_sum += seen ? v : 0.f;
+                soft_max = fmaxf(soft_max, v);
+            }
         }
         float* q = cam_terms + ((size_t)e * nc + c) * MATE_CAM_TERMS;
-        q[0] = cam_reward; q[1] = cov; q[2] = cov_real; q[3] = transport; q[4] = 0.f;
+        q[0] = cam_reward; q[1] = cov; q[2] = cov_real; q[3] = transport;
+        q[4] = soft ? (num_tracked > 0 ? soft_sum : tanhf(soft_max)) : 0.f;
         q[5] = (float)num_tracked; q[6] = 1.f; q[7] = (float)sensed;
     }
     for (int t = 0; t < nt; ++t) {
@@ -289,10 +296,188 @@ __global__ void aux_terms_kernel(const MateStepAux ax, const float* __restrict__
         float* q = tgt_terms + i * MATE_TGT_TERMS;
         q[0] = tgt_reward; q[1] = cov; q[2] = cov_real; q[3] = transport;
         q[4] = goal_distance / (float)(2.0 * kTerrain);
-        q[5] = (float)(ax.target_dones[i] != 0); q[6] = 0.f; q[7] = (float)((tracked >> t) & 1u);
+        float soft_t = 0.f;                           // auxiliary_target_rewards.py:151-162
+        if (soft && nc > 0) {
+            float soft_sum = 0.f, soft_max = -3.0e38f;
+            for (int c = 0; c < nc; ++c) {
+                const float v = soft[((size_t)e * nc + c) * nt + t];
+                soft_sum += ax.mask_ct[((size_t)e * nc + c) * nt + t] != 0 ? v : 0.f;
+                soft_max = fmaxf(soft_max, v);
+            }
+            soft_t = ((tracked >> t) & 1u) ? soft_sum : tanhf(soft_max);
+        }
+        q[5] = (float)(ax.target_dones[i] != 0); q[6] = soft_t; q[7] = (float)((tracked >> t) & 1u);
         q[8] = (float)(ax.is_colliding[i] != 0); q[9] = 1.f;
         q[10] = (float)goal; q[11] = info_goal_distance;
         for (int w = 0; w < NW; ++w) q[12 + w] = wd[w];
+    }
+}
+
+// =============================================================================================
+// AuxiliaryCameraRewards.compute_soft_coverage_scores (mate/wrappers/auxiliary_camera_rewards.py:182-233):
+// signed distance of every target to the boundary of the camera's field of view, in units of the radius of the
+// sector's inscribed circle.  The boundary is the OUTER sampled polyline of the camera
+// (Camera.add_obstacles / boundary_between(outer=True), mate/entities.py:362-479, 484-511) restricted to the
+// current sector, plus the two sector edges (end points from the inner polyline, 16 points along each edge).
+// Like the inner polyline it is never materialised: one warp per (environment, camera) enumerates the sample rays
+// (integer-degree grid; per obstacle the lattice at max_rho and the two 21-point edge segments), keeps those
+// inside the sector, cuts each at the FAR side of the discs it crosses (Obstacle.obstruct(outer=True),
+// entities.py:158-184) and keeps, per target, the minimum squared distance in registers.
+// Exactly tangent rays are not cut by their own disc (the reference decides them by rounding noise, DESIGN.md
+// "Tangent rays").  Environments that were auto-reset in the last step get zeros (their state already belongs to
+// the next episode).
+// =============================================================================================
+template <int NC, int NT, int NO>
+__global__ void soft_coverage_kernel(const Params p, const uint8_t* __restrict__ mask_ct, const uint8_t* __restrict__ done,
+                                     float* __restrict__ out) {
+    constexpr int NCX = NC > 0 ? NC : 1;
+    constexpr uint32_t FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const long long item = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;   // (environment, camera)
+    if (item >= (long long)p.num_envs * NCX) return;
+    const int e = (int)(item / NCX), c = (int)(item - (long long)e * NCX);
+    float* const row = out + ((size_t)e * NCX + c) * NT;
+    if (done != nullptr && done[e] != 0) {
+        if (lane < NT) row[lane] = 0.f;
+        return;
+    }
+    const size_t bp = p.bpad;
+    const double cx = p.cam_x[(size_t)c * bp + e], cy = p.cam_y[(size_t)c * bp + e];
+    const double phi = p.cam_phi[(size_t)c * bp + e], theta = p.cam_theta[(size_t)c * bp + e];
+    const double rmax = p.cam_rmax;
+    // the camera's obstacle set (entities.py:363-368), one disc per lane
+    double ox = 0.0, oy = 0.0, orad = 0.0, od = 0.0;
+    bool member = false, inside_disc = false;
+    if (lane < NO) {
+        ox = p.obs_x[(size_t)lane * bp + e] - cx; oy = p.obs_y[(size_t)lane * bp + e] - cy; orad = p.obs_r[(size_t)lane * bp + e];
+        od = sqrt(ox * ox + oy * oy);
+        member = od < rmax + orad;
+        inside_disc = member && orad > od;
+    }
+    const uint32_t members = __ballot_sync(FULL, member);
+    const bool collapsed = __any_sync(FULL, inside_disc);   // entities.py:378-388: every ray has norm 0
+    // sector (boundary_between, entities.py:484-511)
+    const double left = normalize_angle(phi - theta * 0.5), right = left + theta;
+    const bool wraps = right > 180.0;
+    auto in_sector = [&](const double a) {
+        return wraps ? (a > left || a < right - 360.0 || a == -180.0) : (a > left && a < right);
+    };
+    double tx[NT], ty[NT], best[NT];
+#pragma unroll
+    for (int t = 0; t < NT; ++t) {
+        tx[t] = p.tgt_x[(size_t)t * bp + e] - cx; ty[t] = p.tgt_y[(size_t)t * bp + e] - cy;
+        best[t] = 1e300;
+    }
+    auto visit = [&](const double rho, const double cs, const double sn) {
+        const double px = rho * cs, py = rho * sn;
+#pragma unroll
+        for (int t = 0; t < NT; ++t) {
+            const double dx = tx[t] - px, dy = ty[t] - py;
+            best[t] = fmin(best[t], dx * dx + dy * dy);
+        }
+    };
+    // One sample ray (angle in degrees, normalised; norm): cut at the far side of the discs it crosses, then visit.
+    // The discs are broadcast with shuffles, so this is always called by all lanes; lanes without a sample (or with
+    // a sample outside the sector) pass live = false.
+    auto sample_if = [&](const bool live, const double a, const double norm) {
+        double sn, cs;
+        sincospi(a * (1.0 / 180.0), &sn, &cs);
+        double n = collapsed ? 0.0 : norm;
+        uint32_t m = members;
+        while (m != 0u) {
+            const int o = __ffs(m) - 1;
+            m &= m - 1u;
+            const double rx = __shfl_sync(FULL, ox, o), ry = __shfl_sync(FULL, oy, o);
+            const double R = __shfl_sync(FULL, orad, o), d = __shfl_sync(FULL, od, o);
+            if (!(n > 0.0) || d >= n + R) continue;
+            const double proj = rx * cs + ry * sn;
+            if (proj < 0.0) continue;
+            const double cosv = fmin(1.0, proj / d);
+            const double perp = d * sqrt(fmax(1.0 - cosv * cosv, 0.0));
+            if (!(R > perp * (1.0 + 1e-9))) continue;
+            const double far_side = fmax(0.0, d * cosv + sqrt(fmax(R * R - perp * perp, 0.0)));
+            if (far_side < n) n = far_side;
+        }
+        if (live) visit(n, cs, sn);
+    };
+    // (a) the integer-degree grid (entities.py:339-342)
+    for (int k0 = 0; k0 < 360; k0 += 32) {
+        const int k = k0 + lane;
+        const double a = (double)(k < 360 ? k : 0) - 180.0;
+        sample_if(k < 360 && in_sector(a), a, rmax);
+    }
+    // (b) per obstacle of the set: lattice rays at max_rho and the two edge segments (entities.py:419-448)
+    if (!collapsed) {
+        uint32_t m = members;
+        while (m != 0u) {
+            const int o = __ffs(m) - 1;
+            m &= m - 1u;
+            const double rx = __shfl_sync(FULL, ox, o), ry = __shfl_sync(FULL, oy, o);
+            const double R = __shfl_sync(FULL, orad, o), d = __shfl_sync(FULL, od, o);
+            const double ang = atan2(ry, rx) * kRad2Deg, half = asin(R / d) * kRad2Deg;
+            const double aL = ang - half, aR = ang + half;
+            const double max_rho = fmin(rmax, d + R);
+            const int two_half = (int)(2.0 * half);
+            const int nlat = two_half > 16 ? two_half : 16;
+            const double step = (aR - aL) / (double)nlat;   // np.linspace
+            for (int j0 = 0; j0 <= nlat; j0 += 32) {
+                const int j = j0 + lane;
+                const double a = normalize_angle(j >= nlat ? aR : ((double)j * step + aL));
+                sample_if(j <= nlat && in_sector(a), a, max_rho);
+            }
+            const double near_rho = fmin(rmax, sqrt(d * d + R * R));
+            for (int j0 = 0; j0 < 42; j0 += 32) {
+                const int j = j0 + lane;
+                const bool is_right = j >= 21;
+                const int k = is_right ? j - 21 : j;
+                const double edge = is_right ? aR : aL, far_angle = is_right ? aR + 0.01 : aL - 0.01;
+                double ns, nc_, fs, fc;
+                sincospi(normalize_angle(edge) * (1.0 / 180.0), &ns, &nc_);
+                sincospi(normalize_angle(far_angle) * (1.0 / 180.0), &fs, &fc);
+                const double t = k >= 20 ? 1.0 : (double)k * 0.05;
+                const double vx = (1.0 - t) * (near_rho * nc_) + t * (rmax * fc), vy = (1.0 - t) * (near_rho * ns) + t * (rmax * fs);
+                const double a = atan2(vy, vx) * kRad2Deg;
+                sample_if(j < 42 && in_sector(a), a, sqrt(vx * vx + vy * vy));
+            }
+        }
+    }
+    // (c) the two sector edges: end point from the INNER polyline (boundary_between uses sight_range_at), then 16
+    //     points from the camera to it (auxiliary_camera_rewards.py:203-214)
+    {
+        const double a_mine = normalize_angle(lane < 16 ? left : right);
+        double sn, cs;
+        sincospi(a_mine * (1.0 / 180.0), &sn, &cs);
+        double rho_mine = rmax;
+        if (collapsed) rho_mine = 0.0;
+        else if (NO > 0) rho_mine = sight_range_at<NO>(ObsRef{p.obs_x + e, p.obs_y + e, p.obs_r + e, bp}, cx, cy, rmax, a_mine, cs, sn);
+        const double rho_l = __shfl_sync(FULL, rho_mine, 0), rho_r = __shfl_sync(FULL, rho_mine, 16);
+        for (int q0 = 0; q0 < 34; q0 += 32) {
+            const int q = q0 + lane;
+            if (q < 34) {
+                const bool is_right = q >= 17;
+                const int k = is_right ? q - 17 : q;          // k = 16: the end point itself
+                const double rho = is_right ? rho_r : rho_l;
+                sincospi((is_right ? right : left) * (1.0 / 180.0), &sn, &cs);
+                visit(k >= 16 ? rho : (double)k * (rho / 16.0), cs, sn);
+            }
+        }
+    }
+#pragma unroll
+    for (int t = 0; t < NT; ++t) {
+#pragma unroll
+        for (int sh = 16; sh >= 1; sh >>= 1) best[t] = fmin(best[t], __shfl_xor_sync(FULL, best[t], sh));
+    }
+    const double sight_range = sqrt(p.cam_area_product / theta);
+    double sn_h, cs_h;
+    sincospi(theta * (0.5 / 180.0), &sn_h, &cs_h);
+    const double dist_max = theta < 180.0 ? sight_range / (1.0 + 1.0 / sn_h) : sight_range * 0.5;
+    if (lane == 0) {
+#pragma unroll
+        for (int t = 0; t < NT; ++t) {
+            const double dist = sqrt(best[t]);
+            const bool tracked = mask_ct[((size_t)e * NCX + c) * NT + t] != 0;
+            row[t] = (float)((tracked ? dist : -dist) / dist_max);
+        }
     }
 }
 

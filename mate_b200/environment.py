@@ -85,6 +85,7 @@ class MultiAgentTracking:  # pylint: disable=too-many-instance-attributes,too-ma
         self._step_serial = 0
         self._terms_serial = -1
         self._terms = None
+        self.want_soft_coverage = False   # set by an auxiliary-reward wrapper that uses 'soft_coverage_score'
         self._aux = self.sim.alloc_aux()
         self.viewer = None
 
@@ -291,7 +292,8 @@ class MultiAgentTracking:  # pylint: disable=too-many-instance-attributes,too-ma
         and shared by the auxiliary-reward / training-information wrappers (``include/mate_b200.h``,
         ``mate_b200_auxiliary_terms``)."""
         if self._terms_serial != self._step_serial:
-            self._terms = self.sim.auxiliary_terms()
+            soft = self.sim.soft_coverage(auto_reset=self.batched) if (self.want_soft_coverage and self.num_cameras) else None
+            self._terms = self.sim.auxiliary_terms(soft)
             self._terms_serial = self._step_serial
         return self._terms
 

@@ -223,9 +223,23 @@ class BatchedSim:
                                                           angle.numel(), self._stream()))
         return out
 
-    def auxiliary_terms(self):
+    def soft_coverage(self, auto_reset=True):
+        """``AuxiliaryCameraRewards.compute_soft_coverage_scores`` for the current state and the camera-target masks
+        of the last step: ``[B, Nc, Nt]`` float32 (mate_b200_soft_coverage).  With ``auto_reset`` the environments
+        that were reset in the last step get zeros."""
+        if self._aux is None:
+            raise RuntimeError('soft_coverage needs a step / observe call with aux=True first')
+        if getattr(self, '_soft', None) is None:
+            self._soft = torch.zeros((self.B, self.nc, self.nt), dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            _check(self.lib, self.lib.mate_b200_soft_coverage(
+                self.handle, _dptr(self._aux['mask_ct']), _dptr(self.done) if auto_reset else None, _dptr(self._soft), self._stream()))
+        return self._soft
+
+    def auxiliary_terms(self, soft_matrix=None):
         """Per-agent terms of the auxiliary-reward / training-information wrappers for the LAST step
-        (mate_b200_auxiliary_terms): ``(cam_terms [B, Nc, CAM_TERMS], tgt_terms [B, Nt, TGT_TERMS])``."""
+        (mate_b200_auxiliary_terms): ``(cam_terms [B, Nc, CAM_TERMS], tgt_terms [B, Nt, TGT_TERMS])``; the
+        ``soft_coverage_score`` columns are filled when ``soft_matrix`` (from :meth:`soft_coverage`) is given."""
         if self._aux is None:
             raise RuntimeError('auxiliary_terms needs a step / observe call with aux=True first')
         if getattr(self, '_terms', None) is None:
@@ -234,8 +248,8 @@ class BatchedSim:
         cam_terms, tgt_terms = self._terms
         with torch.cuda.device(self.device):
             _check(self.lib, self.lib.mate_b200_auxiliary_terms(
-                self.handle, ctypes.byref(self._aux_struct), _dptr(self.rewards), _dptr(cam_terms) if self.nc else None,
-                _dptr(tgt_terms), self._stream()))
+                self.handle, ctypes.byref(self._aux_struct), _dptr(self.rewards), _dptr(soft_matrix),
+                _dptr(cam_terms) if self.nc else None, _dptr(tgt_terms), self._stream()))
         return cam_terms, tgt_terms
 
     def step_host(self, cam_act, tgt_act, out, auto_reset=True):

@@ -352,10 +352,6 @@ class _AuxiliaryRewards(Wrapper):
         assert set(self.ACCEPTABLE_KEYS).issuperset(coefficients.keys()), (
             f'The coefficient mapping only accepts keys in {self.ACCEPTABLE_KEYS}. '
             f'Got list(coefficients.keys()) = {list(coefficients.keys())}.')
-        if 'soft_coverage_score' in coefficients:
-            raise NotImplementedError(
-                "'soft_coverage_score' needs the outer field-of-view boundary (mate/entities.py:419-448), which the CUDA "
-                'path does not build yet (DESIGN.md, section 7c); all other keys are supported')
         self.coefficients = {}
         for key, coefficient in coefficients.items():
             assert callable(coefficient) or isinstance(coefficient, (float, int)), (
@@ -365,6 +361,9 @@ class _AuxiliaryRewards(Wrapper):
         super().__init__(env)
         self.episode_id = -1
         self.reduction = reduction
+        if 'soft_coverage_score' in self.coefficients:
+            assert self.unwrapped.num_cameras > 0, "'soft_coverage_score' needs at least one camera."
+            self.unwrapped.want_soft_coverage = True   # one more kernel per step (mate_b200_soft_coverage)
 
     def reset(self, **kwargs):
         self.episode_id += 1
@@ -423,8 +422,8 @@ class _AuxiliaryRewards(Wrapper):
 
 class AuxiliaryCameraRewards(_AuxiliaryRewards):
     """mate/wrappers/auxiliary_camera_rewards.py: weighted sum of ``raw_reward``, ``coverage_rate``,
-    ``real_coverage_rate``, ``mean_transport_rate``, ``num_tracked`` and ``baseline`` per camera
-    (``soft_coverage_score`` is not built yet)."""
+    ``real_coverage_rate``, ``mean_transport_rate``, ``soft_coverage_score``, ``num_tracked`` and ``baseline`` per
+    camera."""
 
     ACCEPTABLE_KEYS = CAMERA_REWARD_KEYS
     TEAM = 0
@@ -436,7 +435,7 @@ class AuxiliaryCameraRewards(_AuxiliaryRewards):
 class AuxiliaryTargetRewards(_AuxiliaryRewards):
     """mate/wrappers/auxiliary_target_rewards.py: weighted sum of ``raw_reward``, ``coverage_rate``,
     ``real_coverage_rate``, ``mean_transport_rate``, ``normalized_goal_distance``, ``sparse_delivery``,
-    ``is_tracked``, ``is_colliding`` and ``baseline`` per target (``soft_coverage_score`` is not built yet)."""
+    ``soft_coverage_score``, ``is_tracked``, ``is_colliding`` and ``baseline`` per target."""
 
     ACCEPTABLE_KEYS = TARGET_REWARD_KEYS
     TEAM = 1

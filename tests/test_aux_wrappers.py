@@ -88,8 +88,6 @@ def test_wrapper_assertions():
         wrappers.AuxiliaryCameraRewards(repeated, coefficients={'no_such_key': 1.0})
     with pytest.raises(AssertionError):
         wrappers.AuxiliaryTargetRewards(repeated, coefficients={'raw_reward': 1.0}, reduction='median')
-    with pytest.raises(NotImplementedError):
-        wrappers.AuxiliaryCameraRewards(repeated, coefficients={'soft_coverage_score': 1.0})
     once = wrappers.AuxiliaryTargetRewards(repeated, coefficients={'raw_reward': 1.0})
     with pytest.raises(AssertionError):
         wrappers.AuxiliaryTargetRewards(once, coefficients={'raw_reward': 1.0})
@@ -146,6 +144,87 @@ def test_auxiliary_wrappers_match_the_reference(name):
     np.testing.assert_array_equal(tgt_infos['is_tracked'].cpu().numpy(), g['a_out_tgt_is_tracked'].astype(bool))
     np.testing.assert_array_equal(tgt_infos['is_colliding'].cpu().numpy(), g['a_out_tgt_is_colliding'].astype(bool))
     np.testing.assert_allclose(tgt_infos['auxiliary_reward_normalized_goal_distance'].cpu().numpy(), exp_tgt_terms[..., 4], **tol)
+    base.close()
+
+
+def _soft_reference(g, limit):
+    """(matrix without tangent cuts, matrix with tangent cuts) of the NumPy restatement for the first samples."""
+    import soft_coverage_ref as sr
+    from oracle.oracle import Oracle
+
+    cfg = gu.flat_config(g)
+    nc, rmax = cfg['num_cameras'], cfg['camera_max_sight_range']
+    area_product = cfg['camera_min_viewing_angle'] * rmax ** 2
+    sim = Oracle(cfg, 1)
+    sim.set_state(gu.state_arrays(g, 'a_', 0))   # one episode per fixture: the geometry is that of sample 0
+    tables = [sim.get_fov(0, c) for c in range(nc)]
+    n = min(int(g['count']), limit)
+    out = []
+    for eps in (1e-9, -1e-9):
+        rows = []
+        for i in range(n):
+            phi, theta = sr.after_step_cameras(g, i)
+            rows.append(sr.soft_coverage_matrix(g['a_cam_xy'][i], phi, theta, rmax, area_product, g['a_obs_xyr'][i], g['a_out_tgt_xy'][i],
+                                                g['a_out_mask_ct'][i].astype(bool), tables, tangent_eps=eps))
+        out.append(np.array(rows))
+    return out
+
+
+@pytest.mark.parametrize('name', [n for n in NAMES if 'Navigation' not in n])
+def test_soft_coverage_restatement_matches_the_reference(name):
+    """CPU: the NumPy restatement of compute_soft_coverage_scores (the checker of the CUDA kernel) against the
+    reference's matrices.  The reference decides every exactly tangent ray by rounding noise (DESIGN.md "Tangent
+    rays"), so an entry equals the restatement with those rays all cut or all not cut unless its nearest boundary
+    point is decided by two such rays with different luck (measured: < 1 % of the entries)."""
+    g = gu.load(name)
+    no_cut, cut = _soft_reference(g, 60)
+    gold = g['a_out_soft_matrix'][:len(no_cut)]
+    err = np.minimum(np.abs(no_cut - gold), np.abs(cut - gold))
+    assert (err < 1e-6).mean() > 0.99, (err < 1e-6).mean()
+    assert err.max() < 0.1, err.max()
+    assert (np.abs(no_cut - gold) < 1e-6).mean() > 0.85   # the convention of the CUDA path alone
+    if int(g['cfg_counts'][2]) == 0:
+        np.testing.assert_allclose(no_cut, gold, rtol=0, atol=1e-9)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('name', [n for n in NAMES if 'Navigation' not in n])
+def test_soft_coverage_matches_the_restatement(name):
+    """GPU: the soft coverage matrix of the recorded steps against the NumPy restatement (exactly tangent rays not
+    cut, the convention of the CUDA path), and the soft_coverage_score terms of both teams against the reference's
+    aggregation of it."""
+    import torch
+
+    import mate_b200
+
+    g = gu.load(name)
+    nc, nt, _ = (int(x) for x in g['cfg_counts'])
+    limit = 96
+    want, _ = _soft_reference(g, limit)
+    n = len(want)
+    env = mate_b200.make('MultiAgentTracking-v0', config=str(g['config_name']), num_envs=n, wrappers=[
+        mate_b200.RepeatedRewardIndividualDone,
+        lambda e: mate_b200.AuxiliaryCameraRewards(e, coefficients={'soft_coverage_score': 1.0}),
+        lambda e: mate_b200.AuxiliaryTargetRewards(e, coefficients={'soft_coverage_score': 1.0})])
+    base = env.unwrapped
+    base.set_state(gu.stack_states([gu.state_arrays(g, 'a_', i) for i in range(n)]))
+    base.replay_next = (g['a_transmit'][:n], g['a_goal_choice'][:n])
+    cam_act = torch.from_numpy(g['a_cam_act'][:n].astype(np.float32)).cuda()
+    tgt_act = torch.from_numpy(g['a_tgt_act'][:n].astype(np.float32)).cuda()
+    _, (cam_reward, tgt_reward), (cam_done, _), _ = env.step((cam_act, tgt_act))
+    torch.cuda.synchronize()
+    live = ~cam_done[:, 0].cpu().numpy().astype(bool)     # auto-reset environments report zeros
+    assert live.sum() >= n - 1
+    mask = g['a_out_mask_ct'][:n].astype(bool)
+    np.testing.assert_array_equal(base.camera_target_view_mask.cpu().numpy(), mask)
+    got = base.sim._soft.cpu().numpy()  # pylint: disable=protected-access
+    np.testing.assert_allclose(got[live], want[live], rtol=2e-5, atol=2e-5)
+    # aggregation (auxiliary_camera_rewards.py:130-138, auxiliary_target_rewards.py:151-162)
+    cam_want = np.where(mask.any(-1), (want * mask).sum(-1), np.tanh(want.max(-1)))
+    tgt_want = np.where(mask.any(-2), (want * mask).sum(-2), np.tanh(want.max(-2)))
+    np.testing.assert_allclose(cam_reward.cpu().numpy()[live], cam_want[live], rtol=1e-4, atol=1e-4)
+    np.testing.assert_allclose(tgt_reward.cpu().numpy()[live], tgt_want[live], rtol=1e-4, atol=1e-4)
+    assert not got[~live].any()
     base.close()
 
 
