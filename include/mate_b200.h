@@ -242,6 +242,27 @@ int mate_b200_auxiliary_terms(MateSim* sim, const MateStepAux* aux, const float*
  * result as `soft_matrix` to mate_b200_auxiliary_terms to fill the soft_coverage_score columns. */
 int mate_b200_soft_coverage(MateSim* sim, const uint8_t* mask_ct, const uint8_t* done, float* soft_matrix, void* stream);
 
+/* Batched opponents for the single-team wrappers: GreedyTargetAgent
+ * (mate/agents/greedy.py:235-365) for every target of every environment, driven like MultiCamera drives its
+ * opponents (mate/wrappers/single_team.py:79-92, 261-279: observe -> communicate -> act).
+ *   memory     dev double [B, Nt, MATE_AGENT_MEMORY], owned by the caller, carried from step to step: goal (-1 = none),
+ *              remembered non-empty warehouses (bit set), previous location x, y, previous noise x, y;
+ *   reset_mask dev uint8 [B], nullable: environments whose agents are reset on the current state first
+ *              (GreedyTargetAgent.reset: after env.reset and after an auto-reset);
+ *   seed / serial  key and per-step counter of the agents' counter-based (Philox) draws;
+ *   replay     parity mode: recorded outcomes of the agents' draws (NULL members = live draws);
+ *   tgt_act    dev float [B, Nt, 2]: the joint target action for mate_b200_step. */
+#define MATE_AGENT_MEMORY 6
+typedef struct MateAgentReplay {
+    const uint8_t* binomial;     /* [B, Nt] outcome of binomial(1, prob), greedy.py:315            */
+    const double* sample;        /* [B, Nt, 2] action_space.sample() of a redraw, greedy.py:316     */
+    const int8_t* choice;        /* [B, Nt] np_random.choice(non-empty warehouses), greedy.py:303   */
+    const double* reset_sample;  /* [B, Nt, 2] action_space.sample() in reset(), greedy.py:271      */
+} MateAgentReplay;
+int mate_b200_greedy_target_actions(MateSim* sim, double* memory, const uint8_t* reset_mask, double noise_scale,
+                                    uint64_t seed, uint64_t serial, const MateAgentReplay* replay, float* tgt_act,
+                                    void* stream);
+
 /* DiscreteCamera / DiscreteTarget.action (mate/wrappers/discrete_action_spaces.py:98-117, 204-228): grid
  * indices (dev int64 [count]) -> continuous actions (dev float32 [count][2]) through the wrapper's table
  * (dev float32 [table_size][2]). */

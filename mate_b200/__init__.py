@@ -66,7 +66,8 @@ del _nc, _nt, _no
 
 _WRAPPERS = ('EnhancedObservation', 'SharedFieldOfView', 'RelativeCoordinates', 'RescaledObservation',
              'DiscreteCamera', 'DiscreteTarget', 'RepeatedRewardIndividualDone', 'MoreTrainingInformation',
-             'AuxiliaryCameraRewards', 'AuxiliaryTargetRewards')
+             'AuxiliaryCameraRewards', 'AuxiliaryTargetRewards', 'MultiCamera')
+_AGENTS = ('GreedyTargetAgent', 'TargetAgentBase', 'CameraAgentBase')
 
 
 def __getattr__(name):
@@ -75,6 +76,11 @@ def __getattr__(name):
 
         module = importlib.import_module('mate_b200.wrappers')
         return module if name == 'wrappers' else getattr(module, name)
+    if name in _AGENTS or name == 'agents':
+        import importlib  # pylint: disable=import-outside-toplevel
+
+        module = importlib.import_module('mate_b200.agents')
+        return module if name == 'agents' else getattr(module, name)
     if name == 'MultiAgentTracking':   # lazy: importing torch is slow and not needed for config work
         from mate_b200.environment import MultiAgentTracking  # pylint: disable=import-outside-toplevel
 

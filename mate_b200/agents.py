@@ -1,0 +1,82 @@
+"""Batched rule-based opponents.
+
+``GreedyTargetAgent`` mirrors the reference's constructor (mate/agents/greedy.py:241-256).  One instance stands for
+the whole target team of every environment of a batch: its memory (goal, remembered non-empty warehouses, previous
+location, previous noise per target) is a ``[B, Nt, 6]`` CUDA tensor and one kernel per step
+(``mate_b200_greedy_target_actions``) runs observe -> communicate -> act for all of them.  The agents' random draws
+are counter-based (Philox), keyed on ``seed``, the global environment index and the step.
+"""
+
+import ctypes
+
+import numpy as np
+import torch
+
+from mate_b200 import _abi
+from mate_b200.sim import _check, _dptr
+
+
+class TargetAgentBase:   # marker base, like mate.agents.base.TargetAgentBase
+    TEAM = 'target'
+
+
+class CameraAgentBase:   # marker base, like mate.agents.base.CameraAgentBase
+    TEAM = 'camera'
+
+
+class GreedyTargetAgent(TargetAgentBase):
+    """Greedy Target Agent: runs towards the destination (desired warehouse) with some noise."""
+
+    def __init__(self, seed=None, noise_scale=0.5):
+        self.noise_scale = float(noise_scale)
+        self._seed = 0
+        self.seed(seed)
+        self.memory = None
+        self.actions = None
+        self._serial = 0
+        self._sim = None
+
+    def seed(self, seed=None):
+        if seed is None:
+            seed = int(np.random.SeedSequence().entropy % (2 ** 63))
+        self._seed = int(seed)
+        return [self._seed]
+
+    def clone(self):
+        return GreedyTargetAgent(seed=self._seed + 1, noise_scale=self.noise_scale)
+
+    def spawn(self, num_agents):   # one batched instance plays every agent of the team
+        return [self] * num_agents
+
+    def bind(self, sim):
+        """Allocate the team memory for a simulator (``mate_b200.sim.BatchedSim``)."""
+        self._sim = sim
+        self.memory = torch.zeros((sim.B, sim.nt, _abi.AGENT_MEMORY), dtype=torch.float64, device=sim.device)
+        self.actions = torch.zeros((sim.B, sim.nt, 2), dtype=torch.float32, device=sim.device)
+        self._serial = 0
+
+    def act(self, reset_mask=None, replay=None):
+        """Joint target action ``[B, Nt, 2]`` for the simulator's current state.  ``reset_mask`` ``[B]`` (uint8 / bool
+        CUDA tensor, or ``True`` for all): environments whose agents are reset first.  ``replay``: dict with the
+        recorded draws ``binomial`` / ``sample`` / ``choice`` / ``reset_sample`` (parity tests)."""
+        sim = self._sim
+        if reset_mask is True:
+            reset_mask = torch.ones(sim.B, dtype=torch.uint8, device=sim.device)
+        elif reset_mask is not None:
+            reset_mask = torch.as_tensor(reset_mask, device=sim.device).to(torch.uint8).contiguous()
+        rs, keep = None, []
+        if replay is not None:
+            rs = _abi.MateAgentReplay()
+            for name, dtype, ctype in (('binomial', torch.uint8, _abi.c_uint8_p), ('sample', torch.float64, _abi.c_double_p),
+                                       ('choice', torch.int8, _abi.c_int8_p), ('reset_sample', torch.float64, _abi.c_double_p)):
+                if replay.get(name) is not None:
+                    t = torch.as_tensor(np.ascontiguousarray(replay[name])).to(dtype).to(sim.device).contiguous()
+                    keep.append(t)
+                    setattr(rs, name, ctypes.cast(ctypes.c_void_p(t.data_ptr()), ctype))
+        with torch.cuda.device(sim.device):
+            _check(sim.lib, sim.lib.mate_b200_greedy_target_actions(
+                sim.handle, _dptr(self.memory), _dptr(reset_mask), self.noise_scale, self._seed % (2 ** 64), self._serial,
+                ctypes.byref(rs) if rs is not None else None, _dptr(self.actions), sim._stream()))  # pylint: disable=protected-access
+        del keep
+        self._serial += 1
+        return self.actions

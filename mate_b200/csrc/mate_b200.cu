@@ -13,6 +13,7 @@
 
 #include "mate_step.cuh"
 #include "mate_wrappers.cuh"
+#include "mate_agents.cuh"
 
 using namespace mate;
 
@@ -368,6 +369,23 @@ extern "C" int mate_b200_auxiliary_terms(MateSim* sim, const MateStepAux* aux, c
     sim->launches += 1;
     cudaError_t err = cudaGetLastError();
     if (err != cudaSuccess) return fail(MATE_ECUDA, std::string("auxiliary terms launch: ") + cudaGetErrorString(err));
+    return MATE_OK;
+}
+
+extern "C" int mate_b200_greedy_target_actions(MateSim* sim, double* memory, const uint8_t* reset_mask, double noise_scale,
+                                               uint64_t seed, uint64_t serial, const MateAgentReplay* replay, float* tgt_act,
+                                               void* stream) {
+    if (!sim || !memory || !tgt_act) return fail(MATE_EINVAL, "null argument");
+    if (((uintptr_t)tgt_act & 7) || ((uintptr_t)memory & 7)) return fail(MATE_EINVAL, "agent buffers must be 8-byte aligned");
+    CUDA_TRY(cudaSetDevice(sim->device));
+    MateAgentReplay r{};
+    if (replay) r = *replay;
+    const int threads = 128;
+    greedy_target_kernel<<<(sim->num_envs + threads - 1) / threads, threads, 0, (cudaStream_t)stream>>>(
+        sim->base, sim->cfg.num_targets, memory, reset_mask, noise_scale, seed, serial, r, tgt_act);
+    sim->launches += 1;
+    cudaError_t err = cudaGetLastError();
+    if (err != cudaSuccess) return fail(MATE_ECUDA, std::string("greedy target launch: ") + cudaGetErrorString(err));
     return MATE_OK;
 }
 

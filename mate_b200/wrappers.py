@@ -442,3 +442,54 @@ class AuxiliaryTargetRewards(_AuxiliaryRewards):
 
     def _terms(self, base):
         return base.auxiliary_terms()[1][..., :len(TARGET_REWARD_KEYS)]
+
+
+# ------------------------------------------------------------------------------------------------------------
+# single-team wrapper with a batched built-in opponent.
+# ------------------------------------------------------------------------------------------------------------
+
+class MultiCamera(Wrapper):
+    """mate/wrappers/single_team.py:281-292: a single-team multi-agent environment for the camera team; the targets
+    are played by ``target_agent`` (``mate_b200.agents.GreedyTargetAgent``), whose whole team acts in one kernel per
+    step on the GPU.  ``reset`` returns the camera joint observation, ``step(camera_joint_action)`` returns
+    ``(camera_joint_observation, camera_reward, done, camera_infos)``."""
+
+    def __init__(self, env, target_agent):
+        from mate_b200 import agents  # pylint: disable=import-outside-toplevel
+
+        assert isinstance(target_agent, agents.TargetAgentBase), (
+            f'You should provide an instance of target agent. Got target_agent = {target_agent!r}.')
+        assert not _has_wrapper(env, MultiCamera), f'You should not use wrapper `{type(self)}` more than once.'
+        assert env.num_cameras > 0, 'There must be at least one camera in the environment.'
+        super().__init__(env)
+        self.opponent_agent = target_agent
+        self.num_teammates, self.num_opponents = env.num_cameras, env.num_targets
+        self.action_space = env.action_space.spaces[0]
+        self.observation_space = env.observation_space.spaces[0]
+        self.repeated_reward_individual_done = _has_wrapper(env, RepeatedRewardIndividualDone)
+        self.opponent_joint_observation = None
+        self.opponent_infos = None
+        self._reset_mask = True
+        target_agent.bind(self.unwrapped.sim)
+
+    def reset(self, **kwargs):
+        joint_observation, self.opponent_joint_observation = self.env.reset(**kwargs)
+        self.opponent_infos = None
+        self._reset_mask = True          # group_reset(opponent_agents, ...), single_team.py:209-219
+        return joint_observation
+
+    def step(self, action):
+        base = self.unwrapped
+        opponent_joint_action = self.opponent_agent.act(reset_mask=self._reset_mask)
+        if not base.batched:
+            opponent_joint_action = opponent_joint_action[0].double().cpu().numpy()
+        (joint_observation, self.opponent_joint_observation), (reward, _), done, (infos, self.opponent_infos) = \
+            self.env.step((action, opponent_joint_action))
+        # finished episodes were auto-reset inside the step: their opponents start over on the new state
+        self._reset_mask = base.sim.done if base.batched else None
+        if self.repeated_reward_individual_done:
+            done = done[0]
+        return joint_observation, reward, done, infos
+
+    def __str__(self):
+        return f'<{type(self).__name__}(opponent={type(self.opponent_agent).__module__}.{type(self.opponent_agent).__name__}){self.env}>'

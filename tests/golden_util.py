@@ -15,7 +15,7 @@ def trace_names():
         os.path.basename(p)[:-4]
         for p in glob.glob(os.path.join(GOLDEN_DIR, '*.npz'))
         if not p.endswith('_resets.npz') and not p.endswith('_resetsamples.npz')
-        and not os.path.basename(p).startswith(('wrappers_', 'aux_'))
+        and not os.path.basename(p).startswith(('wrappers_', 'aux_', 'agents_'))
     )
 
 
