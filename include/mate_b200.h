@@ -263,6 +263,20 @@ int mate_b200_greedy_target_actions(MateSim* sim, double* memory, const uint8_t*
                                     uint64_t seed, uint64_t serial, const MateAgentReplay* replay, float* tgt_act,
                                     void* stream);
 
+/* GreedyCameraAgent (mate/agents/greedy.py:14-232) for every camera of every environment, driven like MultiTarget
+ * drives its opponents.  memory: dev double [B, Nc, 6 Nt + Nc + 4] owned by the caller (per camera: remembered target
+ * states [Nt][4], time2forget [Nt], never_loaded [Nt], previous action [2], communication delay [Nc], known teammates
+ * (bit set), own-state message pending); tracked: dev uint8 [B, Nc, Nt], the target flags of the cameras' CURRENT
+ * observations; cam_act: dev float [B, Nc, 2].  Other arguments as for mate_b200_greedy_target_actions. */
+typedef struct MateCameraAgentReplay {
+    const int8_t* binomial;   /* [B, Nc] outcome of binomial(1, 0.1), greedy.py:96 (-1 = not drawn)          */
+    const double* sample;     /* [B, Nc, 2] action_space.sample(), greedy.py:97                                */
+    const int32_t* delay;     /* [B, Nc, Nc] randint(memory_period // 4, 2 * memory_period) per message sent   */
+} MateCameraAgentReplay;
+int mate_b200_greedy_camera_actions(MateSim* sim, double* memory, const uint8_t* tracked, const uint8_t* reset_mask,
+                                    uint64_t seed, uint64_t serial, const MateCameraAgentReplay* replay, float* cam_act,
+                                    void* stream);
+
 /* DiscreteCamera / DiscreteTarget.action (mate/wrappers/discrete_action_spaces.py:98-117, 204-228): grid
  * indices (dev int64 [count]) -> continuous actions (dev float32 [count][2]) through the wrapper's table
  * (dev float32 [table_size][2]). */

@@ -66,8 +66,8 @@ del _nc, _nt, _no
 
 _WRAPPERS = ('EnhancedObservation', 'SharedFieldOfView', 'RelativeCoordinates', 'RescaledObservation',
              'DiscreteCamera', 'DiscreteTarget', 'RepeatedRewardIndividualDone', 'MoreTrainingInformation',
-             'AuxiliaryCameraRewards', 'AuxiliaryTargetRewards', 'MultiCamera')
-_AGENTS = ('GreedyTargetAgent', 'TargetAgentBase', 'CameraAgentBase')
+             'AuxiliaryCameraRewards', 'AuxiliaryTargetRewards', 'MultiCamera', 'MultiTarget')
+_AGENTS = ('GreedyTargetAgent', 'GreedyCameraAgent', 'TargetAgentBase', 'CameraAgentBase')
 
 
 def __getattr__(name):

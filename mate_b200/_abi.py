@@ -101,6 +101,10 @@ class MateAgentReplay(ctypes.Structure):
     _fields_ = [('binomial', c_uint8_p), ('sample', c_double_p), ('choice', c_int8_p), ('reset_sample', c_double_p)]
 
 
+class MateCameraAgentReplay(ctypes.Structure):
+    _fields_ = [('binomial', c_int8_p), ('sample', c_double_p), ('delay', c_int32_p)]
+
+
 AGENT_MEMORY = 6   # MATE_AGENT_MEMORY
 
 
@@ -185,9 +189,11 @@ def load_library():
     lib.mate_b200_auxiliary_terms.argtypes = [void_p, ctypes.POINTER(MateStepAux), void_p, void_p, void_p, void_p, void_p]
     lib.mate_b200_greedy_target_actions.argtypes = [void_p, void_p, void_p, ctypes.c_double, ctypes.c_uint64, ctypes.c_uint64,
                                                     ctypes.POINTER(MateAgentReplay), void_p, void_p]
+    lib.mate_b200_greedy_camera_actions.argtypes = [void_p, void_p, void_p, void_p, ctypes.c_uint64, ctypes.c_uint64,
+                                                    ctypes.POINTER(MateCameraAgentReplay), void_p, void_p]
     lib.mate_b200_soft_coverage.argtypes = [void_p, void_p, void_p, void_p, void_p]
     for name in ('create', 'destroy', 'obs_dims', 'reset', 'step', 'observe', 'step_host',
-                 'get_state', 'set_state', 'episode_stats', 'transform_observations', 'decode_actions', 'auxiliary_terms', 'fov_range', 'soft_coverage', 'greedy_target_actions'):
+                 'get_state', 'set_state', 'episode_stats', 'transform_observations', 'decode_actions', 'auxiliary_terms', 'fov_range', 'soft_coverage', 'greedy_target_actions', 'greedy_camera_actions'):
         getattr(lib, 'mate_b200_' + name).restype = ctypes.c_int
     _LIB = lib
     return lib
@@ -198,7 +204,7 @@ EXPORTED_SYMBOLS = [
     'mate_b200_obs_dims', 'mate_b200_reset', 'mate_b200_step', 'mate_b200_observe',
     'mate_b200_step_host', 'mate_b200_get_state', 'mate_b200_set_state',
     'mate_b200_episode_stats', 'mate_b200_launch_count', 'mate_b200_transform_observations',
-    'mate_b200_decode_actions', 'mate_b200_auxiliary_terms', 'mate_b200_fov_range', 'mate_b200_soft_coverage', 'mate_b200_greedy_target_actions',
+    'mate_b200_decode_actions', 'mate_b200_auxiliary_terms', 'mate_b200_fov_range', 'mate_b200_soft_coverage', 'mate_b200_greedy_target_actions', 'mate_b200_greedy_camera_actions',
 ]
 
 # observation wrapper codes (include/mate_b200.h)

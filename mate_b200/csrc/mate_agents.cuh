@@ -12,7 +12,7 @@
 
 namespace mate {
 
-constexpr uint32_t STREAM_AGENT_BINOMIAL = 16, STREAM_AGENT_SAMPLE = 17, STREAM_AGENT_CHOICE = 18, STREAM_AGENT_RESET = 19;
+constexpr uint32_t STREAM_AGENT_BINOMIAL = 16, STREAM_AGENT_SAMPLE = 17, STREAM_AGENT_CHOICE = 18, STREAM_AGENT_RESET = 19, STREAM_AGENT_DELAY = 20;
 constexpr int kAgentMemory = 6;   // per target: goal, non-empty warehouse set, previous x, y, previous noise x, y
 
 __global__ void greedy_target_kernel(const Params p, const int nt, double* __restrict__ memory, const uint8_t* __restrict__ reset_mask,
@@ -96,6 +96,164 @@ __global__ void greedy_target_kernel(const Params p, const int nt, double* __res
         ay = fmin(fmax(ay + ny, -step_size), step_size);
         reinterpret_cast<float2*>(tgt_act)[(size_t)e * nt + t] = make_float2((float)ax, (float)ay);
         m[0] = (double)goal; m[1] = (double)non_empty; m[2] = x; m[3] = y; m[4] = nx; m[5] = ny;
+    }
+}
+
+// =============================================================================================
+// GreedyCameraAgent (mate/agents/greedy.py:14-232) for the camera team of every environment, driven like
+// MultiTarget drives its opponents (observe -> communicate -> act).  One thread = one environment.  Per camera the
+// memory holds what the reference agent keeps between steps: the remembered public state of every target, the
+// time-to-forget counters, never_loaded, the previous action, the communication delays per teammate, the set of
+// known teammates and whether the agent's own state is still to be sent (first step after reset).  The
+// peer-to-peer messages of one step (teammate state, tracked target states filtered by the recipient's range) live
+// in two small per-thread tables between the send and the receive phase.
+// Layout per camera (doubles): [4 Nt] memory (x, y, sight range, is_loaded) | [Nt] time2forget | [Nt] never_loaded |
+// [2] previous action | [Nc] communication delay | neighbours (bit set) | has_state_message.
+// =============================================================================================
+__host__ __device__ inline int camera_agent_memory(int nc, int nt) { return 6 * nt + nc + 4; }
+
+__global__ void greedy_camera_kernel(const Params p, const int nc, const int nt, double* __restrict__ memory,
+                                     const uint8_t* __restrict__ tracked, const uint8_t* __restrict__ reset_mask,
+                                     const unsigned long long seed, const unsigned long long serial,
+                                     const MateCameraAgentReplay replay, float* __restrict__ cam_act) {
+    constexpr int MAXN = 8;
+    constexpr double kMemoryPeriod = 25.0, kRangeFactor = 1.1;   // greedy.py:22, 32
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= p.num_envs) return;
+    const size_t bp = p.bpad;
+    const int M = camera_agent_memory(nc, nt);
+    const bool reset = reset_mask != nullptr && reset_mask[e] != 0;
+    const RngKey key{seed, (uint32_t)(p.env_index_base + e), 0x4341474Eu /* 'CAGN' */};
+    const uint32_t draw = (uint32_t)serial * 64u;
+    const double threshold = kRangeFactor * p.cam_rmax;
+    double tx[MAXN], ty[MAXN];
+    uint32_t loaded = 0;
+    for (int t = 0; t < nt; ++t) {
+        tx[t] = p.tgt_x[(size_t)t * bp + e]; ty[t] = p.tgt_y[(size_t)t * bp + e];
+        const uint32_t tp = p.tgt_pack[(size_t)t * bp + e];
+        loaded |= (uint32_t)(tp_goal(tp) >= 0 && tp_weight(tp) > 0) << t;
+    }
+    double cx[MAXN], cy[MAXN];
+    for (int c = 0; c < nc; ++c) { cx[c] = p.cam_x[(size_t)c * bp + e]; cy[c] = p.cam_y[(size_t)c * bp + e]; }
+    uint8_t msg_state[MAXN], msg_targets[MAXN][MAXN];   // msg_state[sender] bit recipient, msg_targets[sender][recipient]
+    // observe -> process_messages (greedy.py:104-115); send_responses (greedy.py:156-194)
+    for (int c = 0; c < nc; ++c) {
+        double* m = memory + ((size_t)e * nc + c) * M;
+        double* mem = m, *t2f = m + 4 * nt, *never = m + 5 * nt, *prev = m + 6 * nt, *delay = m + 6 * nt + 2;
+        uint32_t seen = 0;
+        for (int t = 0; t < nt; ++t) seen |= (uint32_t)(tracked[((size_t)e * nc + c) * nt + t] != 0) << t;
+        if (reset) {   // reset(observation), greedy.py:44-66: untracked targets read as zeros in the observation
+            for (int t = 0; t < nt; ++t) {
+                const bool s = (seen >> t) & 1u;
+                mem[4 * t] = s ? tx[t] : 0.0; mem[4 * t + 1] = s ? ty[t] : 0.0; mem[4 * t + 2] = s ? p.tgt_sight_range : 0.0;
+                mem[4 * t + 3] = s ? (double)((loaded >> t) & 1u) : 0.0;
+                t2f[t] = s ? kMemoryPeriod : 0.0;
+                never[t] = 1.0;
+            }
+            prev[0] = prev[1] = 0.0;
+            for (int k = 0; k < nc; ++k) delay[k] = 0.0;
+            m[6 * nt + 2 + nc] = 0.0;      // neighbours
+            m[6 * nt + 3 + nc] = 1.0;      // message2send['state']
+        }
+        for (int t = 0; t < nt; ++t) {
+            t2f[t] = fmax(t2f[t] - 1.0, 0.0);
+            if ((seen >> t) & 1u) {
+                t2f[t] = kMemoryPeriod;
+                mem[4 * t] = tx[t]; mem[4 * t + 1] = ty[t]; mem[4 * t + 2] = p.tgt_sight_range; mem[4 * t + 3] = (double)((loaded >> t) & 1u);
+                if ((loaded >> t) & 1u) never[t] = 0.0;
+            }
+        }
+        const uint32_t neighbours = (uint32_t)m[6 * nt + 2 + nc];
+        const bool has_state = m[6 * nt + 3 + nc] != 0.0;
+        msg_state[c] = 0;
+        for (int k = 0; k < nc; ++k) {
+            msg_targets[c][k] = 0;
+            delay[k] = fmax(delay[k] - 1.0, 0.0);
+        }
+        if (has_state || seen != 0u) {
+            for (int k = 0; k < nc; ++k) {
+                if (k == c || delay[k] > 0.0) continue;
+                uint32_t targets = 0;
+                if (seen != 0u && ((neighbours >> k) & 1u)) {   // the recipient's range (all cameras share max_sight_range)
+                    for (int t = 0; t < nt; ++t) {
+                        const double dx = tx[t] - cx[k], dy = ty[t] - cy[k];
+                        if (((seen >> t) & 1u) && sqrt(dx * dx + dy * dy) < threshold) targets |= 1u << t;
+                    }
+                }
+                if (has_state || targets != 0u) {
+                    msg_state[c] |= (uint8_t)(has_state ? (1u << k) : 0u);
+                    msg_targets[c][k] = (uint8_t)targets;
+                    int d;   // np_random.randint(memory_period // 4, 2 * memory_period)
+                    if (replay.delay) d = replay.delay[((size_t)e * nc + c) * nc + k];
+                    else d = 6 + (int)rng_below(key, STREAM_AGENT_DELAY, draw + (uint32_t)(c * MAXN + k), 44u);
+                    delay[k] = (double)d;
+                }
+            }
+            m[6 * nt + 3 + nc] = 0.0;
+        }
+    }
+    // receive_responses (greedy.py:196-232) + act (greedy.py:68-102)
+    for (int c = 0; c < nc; ++c) {
+        double* m = memory + ((size_t)e * nc + c) * M;
+        double* mem = m, *t2f = m + 4 * nt, *never = m + 5 * nt, *prev = m + 6 * nt;
+        uint32_t neighbours = (uint32_t)m[6 * nt + 2 + nc];
+        for (int s = 0; s < nc; ++s) {
+            if (s == c) continue;
+            if ((msg_state[s] >> c) & 1u) neighbours |= 1u << s;   // greedy.py:219 adds the sender unconditionally
+            const uint32_t targets = msg_targets[s][c];
+            for (int t = 0; t < nt; ++t) {
+                if (!((targets >> t) & 1u)) continue;
+                mem[4 * t] = tx[t]; mem[4 * t + 1] = ty[t]; mem[4 * t + 2] = p.tgt_sight_range; mem[4 * t + 3] = (double)((loaded >> t) & 1u);
+                t2f[t] = kMemoryPeriod;
+                if ((loaded >> t) & 1u) never[t] = 0.0;
+            }
+        }
+        m[6 * nt + 2 + nc] = (double)neighbours;
+        // nearest remembered target within range_factor * max_sight_range (first minimum, ascending index)
+        int nearest = -1;
+        double best = 0.0;
+        for (int t = 0; t < nt; ++t) {
+            if (!(t2f[t] > 0.0)) continue;
+            const double dx = mem[4 * t] - cx[c], dy = mem[4 * t + 1] - cy[c];
+            const double dist = sqrt(dx * dx + dy * dy);
+            if (!(dist < threshold)) continue;
+            if (nearest < 0 || dist < best) { nearest = t; best = dist; }
+        }
+        double a0, a1;
+        if (nearest >= 0) {   // act_from_target_states (greedy.py:117-154)
+            const double phi = p.cam_phi[(size_t)c * bp + e], theta = p.cam_theta[(size_t)c * bp + e];
+            const double dx = mem[4 * nearest] - cx[c], dy = mem[4 * nearest + 1] - cy[c];
+            const double orientation = atan2(dy, dx) * kRad2Deg;
+            double view;
+            double sn, cs;
+            sincospi(p.cam_min_view * (0.5 / 180.0), &sn, &cs);
+            if (best * (1.0 + sn) >= p.cam_rmax) view = p.cam_min_view;
+            else if (best <= sqrt(p.cam_area_product / 180.0) * 0.5) view = 180.0;
+            else {
+                double b = 180.0;
+                for (int it = 0; it < 20; ++it) {
+                    sincospi(fmin(b * 0.5, 90.0) * (1.0 / 180.0), &sn, &cs);
+                    const double sight = best * (1.0 + sn);
+                    b = p.cam_area_product / (sight * sight);
+                }
+                view = fmin(fmax(b, p.cam_min_view), 180.0);
+            }
+            a0 = fmin(fmax(normalize_angle(orientation - phi), -p.cam_rot_step), p.cam_rot_step);
+            a1 = fmin(fmax(view - theta, -p.cam_zoom_step), p.cam_zoom_step);
+        } else {
+            bool fresh;
+            if (replay.binomial) fresh = replay.binomial[(size_t)e * nc + c] == 1;
+            else fresh = rng_u01(key, STREAM_AGENT_BINOMIAL, draw + (uint32_t)c) < 0.1;
+            if (fresh) {
+                if (replay.sample) { a0 = replay.sample[((size_t)e * nc + c) * 2]; a1 = replay.sample[((size_t)e * nc + c) * 2 + 1]; }
+                else {
+                    a0 = (2.0 * rng_u01(key, STREAM_AGENT_SAMPLE, draw + (uint32_t)c * 2u) - 1.0) * p.cam_rot_step;
+                    a1 = (2.0 * rng_u01(key, STREAM_AGENT_SAMPLE, draw + (uint32_t)c * 2u + 1u) - 1.0) * p.cam_zoom_step;
+                }
+            } else { a0 = prev[0]; a1 = prev[1]; }
+        }
+        prev[0] = a0; prev[1] = a1;
+        reinterpret_cast<float2*>(cam_act)[(size_t)e * nc + c] = make_float2((float)a0, (float)a1);
     }
 }
 

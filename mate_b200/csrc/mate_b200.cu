@@ -389,6 +389,24 @@ extern "C" int mate_b200_greedy_target_actions(MateSim* sim, double* memory, con
     return MATE_OK;
 }
 
+extern "C" int mate_b200_greedy_camera_actions(MateSim* sim, double* memory, const uint8_t* tracked, const uint8_t* reset_mask,
+                                               uint64_t seed, uint64_t serial, const MateCameraAgentReplay* replay, float* cam_act,
+                                               void* stream) {
+    if (!sim || !memory || !tracked || !cam_act) return fail(MATE_EINVAL, "null argument");
+    if (sim->cfg.num_cameras == 0) return fail(MATE_EINVAL, "the configuration has no cameras");
+    if (((uintptr_t)cam_act & 7) || ((uintptr_t)memory & 7)) return fail(MATE_EINVAL, "agent buffers must be 8-byte aligned");
+    CUDA_TRY(cudaSetDevice(sim->device));
+    MateCameraAgentReplay r{};
+    if (replay) r = *replay;
+    const int threads = 64;
+    greedy_camera_kernel<<<(sim->num_envs + threads - 1) / threads, threads, 0, (cudaStream_t)stream>>>(
+        sim->base, sim->cfg.num_cameras, sim->cfg.num_targets, memory, tracked, reset_mask, seed, serial, r, cam_act);
+    sim->launches += 1;
+    cudaError_t err = cudaGetLastError();
+    if (err != cudaSuccess) return fail(MATE_ECUDA, std::string("greedy camera launch: ") + cudaGetErrorString(err));
+    return MATE_OK;
+}
+
 extern "C" int mate_b200_decode_actions(const int64_t* index, const float* table, int32_t table_size, float* out,
                                         int64_t count, void* stream) {
     if (!index || !table || !out || table_size <= 0 || count < 0) return fail(MATE_EINVAL, "bad argument");

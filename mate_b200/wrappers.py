@@ -493,3 +493,58 @@ class MultiCamera(Wrapper):
 
     def __str__(self):
         return f'<{type(self).__name__}(opponent={type(self.opponent_agent).__module__}.{type(self.opponent_agent).__name__}){self.env}>'
+
+
+class MultiTarget(Wrapper):
+    """mate/wrappers/single_team.py:295-306: a single-team multi-agent environment for the target team; the cameras
+    are played by ``camera_agent`` (``mate_b200.agents.GreedyCameraAgent``), whose whole team acts in one kernel per
+    step on the GPU.  ``reset`` returns the target joint observation, ``step(target_joint_action)`` returns
+    ``(target_joint_observation, target_reward, done, target_infos)``."""
+
+    def __init__(self, env, camera_agent):
+        from mate_b200 import agents  # pylint: disable=import-outside-toplevel
+
+        assert isinstance(camera_agent, agents.CameraAgentBase), (
+            f'You should provide an instance of camera agent. Got camera_agent = {camera_agent!r}.')
+        assert not _has_wrapper(env, MultiTarget) and not _has_wrapper(env, MultiCamera), (
+            f'You should not use wrapper `{type(self)}` with another single-team wrapper.')
+        assert env.num_cameras > 0, 'There must be at least one camera in the environment.'
+        super().__init__(env)
+        self.opponent_agent = camera_agent
+        self.num_teammates, self.num_opponents = env.num_targets, env.num_cameras
+        self.action_space = env.action_space.spaces[1]
+        self.observation_space = env.observation_space.spaces[1]
+        self.repeated_reward_individual_done = _has_wrapper(env, RepeatedRewardIndividualDone)
+        self.opponent_joint_observation = None
+        self.opponent_infos = None
+        self._reset_mask = True
+        camera_agent.bind(self.unwrapped.sim)
+
+    def reset(self, **kwargs):
+        self.opponent_joint_observation, joint_observation = self.env.reset(**kwargs)
+        self.opponent_infos = None
+        self._reset_mask = True
+        return joint_observation
+
+    def _tracked_flags(self):
+        """Target flags of the cameras' current observations ``[B, Nc, Nt]`` (also right for environments that were
+        auto-reset in the last step, whose auxiliary masks still describe the finished step)."""
+        base = self.unwrapped
+        nt = base.num_targets
+        flags = base.sim.cam_obs[..., 22 + 4:22 + 5 * nt:5]   # camera observation layout, mate/constants.py:267-282
+        return (flags > 0.5).to(torch.uint8)
+
+    def step(self, action):
+        base = self.unwrapped
+        opponent_joint_action = self.opponent_agent.act(self._tracked_flags(), reset_mask=self._reset_mask)
+        if not base.batched:
+            opponent_joint_action = opponent_joint_action[0].double().cpu().numpy()
+        (self.opponent_joint_observation, joint_observation), (_, reward), done, (self.opponent_infos, infos) = \
+            self.env.step((opponent_joint_action, action))
+        self._reset_mask = base.sim.done if base.batched else None
+        if self.repeated_reward_individual_done:
+            done = done[1]
+        return joint_observation, reward, done, infos
+
+    def __str__(self):
+        return f'<{type(self).__name__}(opponent={type(self.opponent_agent).__module__}.{type(self.opponent_agent).__name__}){self.env}>'

@@ -37,6 +37,7 @@ class DrawLog:
         self._rng = rng
         self.binomial_out = None
         self.choice_out = None
+        self.randint_out = None
 
     def __getattr__(self, name):
         return getattr(self._rng, name)
@@ -49,6 +50,12 @@ class DrawLog:
     def choice(self, a, *args, **kwargs):
         out = self._rng.choice(a, *args, **kwargs)
         self.choice_out = int(out)
+        return out
+
+    def randint(self, *args, **kwargs):
+        out = self._rng.randint(*args, **kwargs)
+        if self.randint_out is not None:
+            self.randint_out.append(int(out))
         return out
 
 
@@ -74,6 +81,18 @@ def memory(agent):
             np.asarray(agent.prev_noise, dtype=np.float64))
 
 
+def camera_memory(agent, nc, nt):
+    """GreedyCameraAgent's memory as arrays (mate/agents/greedy.py:21-66)."""
+    mem = np.array([[ts.state[0], ts.state[1], ts.state[2], ts.state[3]] for ts in agent.memory], dtype=np.float64).reshape(nt, 4)
+    neighbors = sum(1 << c for c in agent.neighboring_teammate_states)
+    return {
+        'cam_mem': mem, 'cam_time2forget': np.asarray(agent.time2forget, dtype=np.int64), 'cam_never_loaded': np.asarray(agent.never_loaded, dtype=np.uint8),
+        'cam_prev_action': np.asarray(agent.prev_action, dtype=np.float64).reshape(2),
+        'cam_delay': np.asarray(agent.communication_delay, dtype=np.int64).reshape(nc), 'cam_neighbors': np.int64(neighbors),
+        'cam_has_state_message': np.uint8('state' in agent.message2send),
+    }
+
+
 def run(mate, name, config, seed, num_steps, out_dir):
     from mate.wrappers.single_team import group_reset, group_step  # pylint: disable=import-outside-toplevel
 
@@ -87,6 +106,7 @@ def run(mate, name, config, seed, num_steps, out_dir):
     group_reset(camera_agents, cam_obs)
     group_reset(target_agents, tgt_obs)
     logs = [instrument(agent) for agent in target_agents]   # after reset: action_space exists now
+    cam_logs = [instrument(agent) for agent in camera_agents]
     reset_noise = np.array([agent.prev_noise for agent in target_agents], dtype=np.float64)
 
     rows = {}
@@ -103,7 +123,31 @@ def run(mate, name, config, seed, num_steps, out_dir):
         for log, samples in logs:
             log.binomial_out = log.choice_out = None
             samples.clear()
+        if nc:
+            push('mask_ct', np.array(u.camera_target_view_mask, dtype=np.uint8))
+            cam_before = [camera_memory(agent, nc, nt) for agent in camera_agents]
+            for log, samples in cam_logs:
+                log.binomial_out = None
+                log.randint_out = []
+                samples.clear()
         cam_act = np.asarray(group_step(env, camera_agents, cam_obs, cam_infos), dtype=np.float64) if nc else np.zeros((0, 2))
+        if nc:
+            cam_after = [camera_memory(agent, nc, nt) for agent in camera_agents]
+            for key in cam_before[0]:
+                push(key + '_before', [m[key] for m in cam_before])
+                push(key + '_after', [m[key] for m in cam_after])
+            push('cam_draw_binomial', [-1 if log.binomial_out is None else log.binomial_out for log, _ in cam_logs])
+            push('cam_draw_sample', [samples[0] if samples else np.zeros(2) for _, samples in cam_logs])
+            # one randint per message sent, in recipient order: recover the recipients from the delays that changed
+            delays = np.full((nc, nc), -1, dtype=np.int64)
+            for c, ((log, _), before_c, after_c) in enumerate(zip(cam_logs, cam_before, cam_after)):
+                sent_to = [k for k in range(nc) if k != c and max(before_c['cam_delay'][k] - 1, 0) == 0 and after_c['cam_delay'][k] > 0]
+                assert len(sent_to) == len(log.randint_out), (sent_to, log.randint_out)
+                for k, value in zip(sent_to, log.randint_out):
+                    assert after_c['cam_delay'][k] == value
+                    delays[c, k] = value
+            push('cam_draw_delay', delays)
+            push('cam_act', cam_act.reshape(nc, 2))
         tgt_act = np.asarray(group_step(env, target_agents, tgt_obs, tgt_infos), dtype=np.float64)
         after = [memory(agent) for agent in target_agents]
         push('agent_goal_before', [m[0] for m in before])

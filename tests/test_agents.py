@@ -80,6 +80,120 @@ def test_greedy_target_kernel_matches_the_reference_agents(name):
     sim.close()
 
 
+CAMERA_NAMES = [n for n in NAMES if 'Navigation' not in n]
+
+
+def _camera_inputs(g, i):
+    nt = int(g['cfg_counts'][1])
+    loaded = (g['g_tgt_goal'][i] >= 0) & (g['g_tgt_goal_weight'][i] > 0)
+    tgt_state = np.c_[g['g_tgt_xy'][i], np.full(nt, g['cfg_target'][1]), loaded.astype(float)]
+    mem = {'memory': g['g_cam_mem_before'][i], 'time2forget': g['g_cam_time2forget_before'][i],
+           'never_loaded': g['g_cam_never_loaded_before'][i], 'prev_action': g['g_cam_prev_action_before'][i],
+           'delay': g['g_cam_delay_before'][i], 'neighbors': g['g_cam_neighbors_before'][i],
+           'has_state': g['g_cam_has_state_message_before'][i]}
+    draws = {'binomial': g['g_cam_draw_binomial'][i], 'sample': g['g_cam_draw_sample'][i], 'delay': g['g_cam_draw_delay'][i]}
+    return tgt_state, mem, draws
+
+
+def _pack_camera_memory(g, suffix):
+    """[n, Nc, 6 Nt + Nc + 4] in the layout of include/mate_b200.h."""
+    n, nc, nt = g['g_cam_mem' + suffix].shape[:3]
+    return np.concatenate([
+        g['g_cam_mem' + suffix].reshape(n, nc, 4 * nt), g['g_cam_time2forget' + suffix], g['g_cam_never_loaded' + suffix],
+        g['g_cam_prev_action' + suffix], g['g_cam_delay' + suffix], g['g_cam_neighbors' + suffix][..., None],
+        g['g_cam_has_state_message' + suffix][..., None]], axis=-1).astype(np.float64)
+
+
+@pytest.mark.parametrize('name', CAMERA_NAMES)
+def test_camera_restatement_matches_the_reference_agents(name):
+    """CPU: the NumPy restatement of GreedyCameraAgent reproduces actions, memory, delays and known teammates of the
+    recorded reference agents at every step."""
+    from greedy_camera_ref import team_step as camera_team_step
+
+    g = gu.load(name)
+    cam = g['cfg_camera']
+    for i in range(int(g['count'])):
+        tgt_state, mem, draws = _camera_inputs(g, i)
+        act, after = camera_team_step(g['g_cam_xy'][i], g['g_cam_phi'][i], g['g_cam_theta'][i], tgt_state, g['g_mask_ct'][i].astype(bool),
+                                      mem, draws, (cam[1], cam[2], cam[3], cam[4]))
+        np.testing.assert_allclose(act, g['g_cam_act'][i], rtol=0, atol=1e-9)
+        np.testing.assert_array_equal(after['time2forget'], g['g_cam_time2forget_after'][i])
+        np.testing.assert_array_equal(after['never_loaded'], g['g_cam_never_loaded_after'][i])
+        np.testing.assert_array_equal(after['delay'], g['g_cam_delay_after'][i])
+        np.testing.assert_array_equal(after['neighbors'], g['g_cam_neighbors_after'][i])
+        np.testing.assert_allclose(after['memory'], g['g_cam_mem_after'][i], rtol=0, atol=1e-12)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('name', CAMERA_NAMES)
+def test_greedy_camera_kernel_matches_the_reference_agents(name):
+    """GPU: every recorded step is one environment of a batch (state and agent memory injected, draws replayed)."""
+    import torch
+
+    import mate_b200
+    from mate_b200.sim import BatchedSim
+
+    g = gu.load(name)
+    n = int(g['count'])
+    sim = BatchedSim(gu.flat_config(g), n, device=0)
+    sim.set_state(gu.stack_states([gu.state_arrays(g, 'g_', i) for i in range(n)]))
+    agent = mate_b200.GreedyCameraAgent(seed=1)
+    agent.bind(sim)
+    agent.memory.copy_(torch.from_numpy(_pack_camera_memory(g, '_before')))
+    actions = agent.act(g['g_mask_ct'], replay={'binomial': g['g_cam_draw_binomial'], 'sample': g['g_cam_draw_sample'],
+                                                'delay': g['g_cam_draw_delay']})
+    torch.cuda.synchronize()
+    np.testing.assert_allclose(actions.cpu().numpy(), g['g_cam_act'], rtol=1e-6, atol=1e-5)
+    want = _pack_camera_memory(g, '_after')
+    got = agent.memory.cpu().numpy()
+    nt = int(g['cfg_counts'][1])
+    np.testing.assert_allclose(got[..., :6 * nt], want[..., :6 * nt], rtol=0, atol=1e-12)          # memory, time2forget, never_loaded
+    np.testing.assert_allclose(got[..., 6 * nt:6 * nt + 2], g['g_cam_act'], rtol=0, atol=1e-9)      # previous action
+    np.testing.assert_array_equal(got[..., 6 * nt + 2:], want[..., 6 * nt + 2:])                   # delays, teammates, pending state
+    # reset(observation), greedy.py:44-66
+    agent.act(g['g_mask_ct'], reset_mask=True, replay={'binomial': np.zeros_like(g['g_cam_draw_binomial']), 'sample': g['g_cam_draw_sample'],
+                                                      'delay': np.full_like(g['g_cam_draw_delay'], 7)})
+    torch.cuda.synchronize()
+    got = agent.memory.cpu().numpy()
+    seen = g['g_mask_ct'].astype(bool)
+    np.testing.assert_array_equal(got[..., 4 * nt:5 * nt], np.where(seen, 25.0, 0.0))
+    assert (got[..., 6 * nt + 3 + seen.shape[1]] == 0).all()       # the state message went out in the first step
+    assert (got[..., 6 * nt + 2 + seen.shape[1]] == (2 ** seen.shape[1] - 1) - 2 ** np.arange(seen.shape[1])).all()   # everyone knows everyone else
+    sim.close()
+
+
+@pytest.mark.gpu
+def test_multi_target_with_live_greedy_cameras():
+    """MultiTarget with the batched GreedyCameraAgent on its own Philox draws: target-side API shapes, camera actions
+    inside the action box, the greedy cameras track (coverage well above what idle cameras get), reproducible."""
+    import torch
+
+    import mate_b200
+
+    def run(agent_seed, idle=False):
+        env = mate_b200.make('MultiAgentTracking-v0', config='MATE-4v8-9.yaml', num_envs=64, wrappers=[
+            lambda e: mate_b200.MultiTarget(e, camera_agent=mate_b200.GreedyCameraAgent(seed=agent_seed))])
+        obs = env.reset(seed=3)
+        assert obs.shape == (64, 8, env.unwrapped.sim.dt)
+        rng = np.random.RandomState(0)
+        coverage = 0.0
+        for _ in range(300):
+            act = torch.from_numpy((rng.uniform(-1, 1, (64, 8, 2)) * 20.0).astype(np.float32)).cuda()
+            if idle:
+                env.opponent_agent.act = lambda tracked, reset_mask=None, replay=None: torch.zeros((64, 4, 2), device='cuda')
+            obs, reward, done, infos = env.step(act)
+            cam_act = env.opponent_agent.actions
+            assert float(cam_act[..., 0].abs().max()) <= 5.0 + 1e-5 and float(cam_act[..., 1].abs().max()) <= 2.5 + 1e-5
+            coverage += float(infos['coverage_rate'].mean())
+        assert reward.shape == (64,) and done.shape == (64,)
+        env.unwrapped.close()
+        return coverage / 300
+
+    tracked_a, tracked_b, idle = run(5), run(5), run(5, idle=True)
+    assert tracked_a == tracked_b
+    assert tracked_a > idle + 0.05, (tracked_a, idle)
+
+
 @pytest.mark.gpu
 def test_multi_camera_with_live_greedy_targets():
     """MultiCamera with the batched GreedyTargetAgent on its own Philox draws: the camera-side API shapes, actions
