@@ -333,6 +333,131 @@ __device__ __noinline__ double sight_range_at(const ObsRef ob, double cx, double
     return slope * (a - P.angle) + rho_p;
 }
 
+// The same evaluation by a QUAD of lanes (lanes 4k .. 4k+3 of a warp work on one query; all 32 lanes must call
+// this together).  Lane q of the quad owns the discs o = q, q + 4, q + 8, ... in registers: the disc loops are a
+// quarter as long, the candidate samples P / S and the two ray casts are reduced over the quad with shuffles
+// (lexicographic max / min, exactly the order `consider` imposes; minimum over the cut lengths).  Arithmetic per
+// disc is the scalar routine's, so the result is the same.
+template <int NO>
+__device__ __forceinline__ double sight_range_quad(const ObsRef ob, double cx, double cy, double rmax, double a,
+                                                   double ux, double uy, const int q) {
+    constexpr uint32_t FULL = 0xffffffffu;
+    constexpr int SL = (NO + 3) / 4 > 0 ? (NO + 3) / 4 : 1;
+    double X[SL], Y[SL], R[SL];
+#pragma unroll
+    for (int s = 0; s < SL; ++s) {
+        const int o = q + 4 * s;
+        const bool has = o < NO;
+        X[s] = has ? ob.x[o * ob.stride] - cx : 0.0; Y[s] = has ? ob.y[o * ob.stride] - cy : 0.0; R[s] = has ? ob.r[o * ob.stride] : -1.0;
+    }
+    const double fl = floor(a);
+    RaySample P{fl, rmax, -1}, S{fl + 1.0, rmax, -1};
+    const double c1 = 0.99984154; // cos(1.02 deg)
+    const double s1 = 0.01780139; // sin(1.02 deg)
+    uint32_t mine = 0;            // bit s: my disc of slot s can have a sample angle inside (floor(a), floor(a) + 1)
+    bool inside = false;
+#pragma unroll
+    for (int s = 0; s < SL; ++s) {
+        const double relx = X[s], rely = Y[s], Rr = R[s];
+        if (Rr < 0.0) continue;
+        const double d2 = relx * relx + rely * rely;
+        {
+            const double reach = rmax + Rr, reach2 = reach * reach;
+            if (d2 > reach2 * (1.0 + 1e-12)) continue;
+            if (d2 > reach2 * (1.0 - 1e-12) && !dist_cmp_exact(d2, reach, true)) continue;
+            if (d2 < Rr * Rr * (1.0 + 1e-12) && dist_cmp_exact(d2, Rr, true)) { inside = true; continue; }
+        }
+        const double pp = relx * ux + rely * uy + Rr * s1 * 1.0000001;
+        if (pp < 0.0) continue;
+        if (pp * pp < (d2 - Rr * Rr) * (c1 * c1) * 0.9999999) continue;
+        mine |= 1u << s;
+    }
+    {
+        uint32_t any_inside = inside ? 1u : 0u;
+        any_inside |= __shfl_xor_sync(FULL, any_inside, 1);
+        any_inside |= __shfl_xor_sync(FULL, any_inside, 2);
+        inside = any_inside != 0u;
+    }
+    // sample angles of my passing discs
+#pragma unroll 1
+    for (int s = 0; s < SL; ++s) {
+        if (!((mine >> s) & 1u)) continue;
+        double relx = X[0], rely = Y[0], Rr = R[0];
+#pragma unroll
+        for (int k = 1; k < SL; ++k) { relx = s == k ? X[k] : relx; rely = s == k ? Y[k] : rely; Rr = s == k ? R[k] : Rr; }
+        const int o = q + 4 * s;
+        const double d2 = relx * relx + rely * rely;
+        const double d = sqrt(d2);
+        const double ang_o = atan2_deg(rely, relx);
+        const double half = asin(Rr / d) * kRad2Deg;
+        const double left = ang_o - half, right = ang_o + half;
+        consider(P, S, a, normalize_angle(left - 0.01), rmax, -1);
+        consider(P, S, a, normalize_angle(left + 0.01), rmax, -1);
+        consider(P, S, a, normalize_angle(right - 0.01), rmax, -1);
+        consider(P, S, a, normalize_angle(right + 0.01), rmax, -1);
+        const int two_half = (int)(2.0 * half);
+        const int nlat = two_half > 16 ? two_half : 16;
+        const double step = (right - left) / (double)nlat;
+        const double max_rho = fmin(rmax, d + Rr);
+        if (step > 0.0) {
+#pragma unroll 1
+            for (int k = -1; k <= 1; ++k) {
+                const double ap = a + 360.0 * (double)k;
+                if (ap < left - step || ap > right + step) continue;
+                const int i0 = (int)floor((ap - left) / step);
+#pragma unroll 1
+                for (int i = i0 - 1; i <= i0 + 2; ++i) {
+                    if (i < 0 || i > nlat) continue;
+                    const double raw = (i == nlat) ? right : ((double)i * step + left);
+                    consider(P, S, a, normalize_angle(raw), max_rho, (i == 0 || i == nlat) ? o : -1);
+                }
+            }
+        }
+    }
+    // the quad's best samples: P = latest angle <= a (ties: smaller range), S = earliest angle > a (ties: smaller range)
+#pragma unroll
+    for (int sh = 1; sh <= 2; sh <<= 1) {
+        const double pa = __shfl_xor_sync(FULL, P.angle, sh), pn = __shfl_xor_sync(FULL, P.n0, sh);
+        const int pt = __shfl_xor_sync(FULL, P.tangent_of, sh);
+        if (pa > P.angle || (pa == P.angle && pn < P.n0)) { P.angle = pa; P.n0 = pn; P.tangent_of = pt; }
+        const double sa = __shfl_xor_sync(FULL, S.angle, sh), sn = __shfl_xor_sync(FULL, S.n0, sh);
+        const int st = __shfl_xor_sync(FULL, S.tangent_of, sh);
+        if (sa < S.angle || (sa == S.angle && sn < S.n0)) { S.angle = sa; S.n0 = sn; S.tangent_of = st; }
+    }
+    // both bracketing rays against my discs near the bearing, minimum over the quad
+    const double s_angle = (S.angle >= 180.0) ? -180.0 : S.angle;
+    double sn_p, cs_p, sn_s, cs_s;
+    sincospi(P.angle * (1.0 / 180.0), &sn_p, &cs_p);
+    sincospi(s_angle * (1.0 / 180.0), &sn_s, &cs_s);
+    double rho_p = P.n0, rho_s = S.n0;
+#pragma unroll
+    for (int s = 0; s < SL; ++s) {
+        if (!((mine >> s) & 1u)) continue;
+        const int o = q + 4 * s;
+        const double relx = X[s], rely = Y[s], Rr = R[s];
+        const double d2 = relx * relx + rely * rely;
+        if (o != P.tangent_of) {
+            const double proj = relx * cs_p + rely * sn_p;
+            const double perp2 = d2 - proj * proj;
+            if (proj >= 0.0 && Rr * Rr > perp2) rho_p = fmin(rho_p, fmax(0.0, proj - sqrt(Rr * Rr - fmax(perp2, 0.0))));
+        }
+        if (o != S.tangent_of) {
+            const double proj = relx * cs_s + rely * sn_s;
+            const double perp2 = d2 - proj * proj;
+            if (proj >= 0.0 && Rr * Rr > perp2) rho_s = fmin(rho_s, fmax(0.0, proj - sqrt(Rr * Rr - fmax(perp2, 0.0))));
+        }
+    }
+#pragma unroll
+    for (int sh = 1; sh <= 2; sh <<= 1) {
+        rho_p = fmin(rho_p, __shfl_xor_sync(FULL, rho_p, sh));
+        rho_s = fmin(rho_s, __shfl_xor_sync(FULL, rho_s, sh));
+    }
+    if (inside) return 0.0;
+    if (a == P.angle) return rho_p;
+    const double slope = (rho_s - rho_p) / (S.angle - P.angle);
+    return slope * (a - P.angle) + rho_p;
+}
+
 // Camera.perceive (mate/entities.py:491-505) up to the stochastic draw, exact arithmetic of
 // the reference: returns 0 = not in range/sector, 1 = reached the draw.
 __device__ __noinline__ int fov_reach_exact(double cx, double cy, double phi, double theta, double rs,

@@ -349,25 +349,29 @@ __device__ __noinline__ uint32_t resolve_fov_band(const Params& p, int er, int c
 }
 
 // Exact evaluation of the sampled FOV polyline for the queued (camera, target) pairs whose occlusion the
-// conservative classification could not decide: 32 pairs at a time, one per lane.
+// conservative classification could not decide.  A warp tile has ~7 such pairs per step: one pair per lane would
+// leave 25 lanes idle through the longest dependent chain of the kernel, so a QUAD of lanes evaluates one pair
+// (sight_range_quad: each lane owns a quarter of the discs, in registers) and the warp takes 8 pairs per pass.
+// Called by all 32 lanes.
 template <int NC, int NT, int NO, class S>
 __device__ __noinline__ void process_exact(const Params& p, int env0, uint32_t* mk, const uint16_t* queue2, int base, int n) {
-    const int lane = threadIdx.x & 31;
-    if (lane >= n) return;
-    const uint32_t item = queue2[base + lane];
-    const int src = item >> 8, b = item & 0xFF;
-    const int c = b / NT, t = b - c * NT;
-    const int envr = min(env0 + src, p.num_envs - 1);
+    const int lane = threadIdx.x & 31, q = lane & 3, slot = lane >> 2;
     const size_t bp = p.bpad;
-    const double cx = p.cam_x[(size_t)c * bp + envr], cy = p.cam_y[(size_t)c * bp + envr];
-    const double relx = p.tgt_x[(size_t)t * bp + envr] - cx, rely = p.tgt_y[(size_t)t * bp + envr] - cy;
-    double E[3 * (NO > 0 ? NO : 1)];   // the discs are read several times: one batch of loads into local memory
-#pragma unroll
-    for (int o = 0; o < NO; ++o) {
-        E[3 * o] = p.obs_x[(size_t)o * bp + envr]; E[3 * o + 1] = p.obs_y[(size_t)o * bp + envr]; E[3 * o + 2] = p.obs_r[(size_t)o * bp + envr];
+#pragma unroll 1
+    for (int i0 = 0; i0 < n; i0 += 8) {
+        const bool live = i0 + slot < n;
+        const uint32_t item = queue2[base + (live ? i0 + slot : 0)];   // idle quads shadow pair 0 (results discarded)
+        const int src = item >> 8, b = item & 0xFF;
+        const int c = b / NT, t = b - c * NT;
+        const int envr = min(env0 + src, p.num_envs - 1);
+        const double cx = p.cam_x[(size_t)c * bp + envr], cy = p.cam_y[(size_t)c * bp + envr];
+        const double relx = p.tgt_x[(size_t)t * bp + envr] - cx, rely = p.tgt_y[(size_t)t * bp + envr] - cy;
+        const double dist = sqrt(relx * relx + rely * rely);
+        const double ang = normalize_angle(atan2_deg(rely, relx));
+        const double range = sight_range_quad<NO>(ObsRef{p.obs_x + envr, p.obs_y + envr, p.obs_r + envr, bp}, cx, cy, p.cam_rmax, ang,
+                                                  relx / dist, rely / dist, q);
+        if (live && q == 0 && dist <= range * (1.0 + 1e-6)) atomicOr(&mk[src * S::MSTRIDE + c * S::MW], bit_tgt(t));   // entities.py:505
     }
-    const bool sees = occlusion_exact<NO>(ObsRef{E, E + 1, E + 2, 3}, cx, cy, relx, rely, sqrt(relx * relx + rely * rely), p.cam_rmax);
-    if (sees) atomicOr(&mk[src * S::MSTRIDE + c * S::MW], bit_tgt(t));
 }
 
 // Prepared resets.  MultiAgentTracking.reset costs tens of thousands of dependent instructions for ONE lane
