@@ -378,10 +378,12 @@ __device__ __forceinline__ double sight_range_quad(const ObsRef ob, double cx, d
         any_inside |= __shfl_xor_sync(FULL, any_inside, 2);
         inside = any_inside != 0u;
     }
-    // sample angles of my passing discs
+    // sample angles of my passing discs (compacted: the warp iterates max-popcount times, not once per slot)
+    uint32_t todo = mine;
 #pragma unroll 1
-    for (int s = 0; s < SL; ++s) {
-        if (!((mine >> s) & 1u)) continue;
+    while (todo != 0u) {
+        const int s = __ffs(todo) - 1;
+        todo &= todo - 1u;
         double relx = X[0], rely = Y[0], Rr = R[0];
 #pragma unroll
         for (int k = 1; k < SL; ++k) { relx = s == k ? X[k] : relx; rely = s == k ? Y[k] : rely; Rr = s == k ? R[k] : Rr; }
