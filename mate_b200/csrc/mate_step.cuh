@@ -191,15 +191,22 @@ __device__ __noinline__ void process_slow_targets(const Params& p, int env0, flo
         for (int c = 0; c < NC; ++c)
             cand |= (unsigned long long)near_segment(camv[S::CV * c], camv[S::CV * c + 1], (float)cam_radius) << (NO + c);
     }
-    bool modified = false;
+    // Discs in the reference's order; a disc that is not a candidate cannot change the step unless an earlier one
+    // has already bent it.  Every lane walks its OWN candidates (most targets have exactly one), so the warp pays
+    // one round trip for the fp64 disc per candidate rank instead of one per disc index.
     if (cand != 0ull) {
+        bool modified = false;
+        int d = __ffsll((long long)cand) - 1;
 #pragma unroll 1
-        for (int d = 0; d < NO + NC; ++d) {
-            if (!modified && !((cand >> d) & 1ull)) continue;
+        while (d < NO + NC) {
             const double ovx = s.vx, ovy = s.vy;
             if (d < NO) obstruct_step(s, tx, ty, obs_x[(size_t)d * bp], obs_y[(size_t)d * bp], obs_r[(size_t)d * bp]);
             else obstruct_step(s, tx, ty, cam_x[(size_t)(d - NO) * bp], cam_y[(size_t)(d - NO) * bp], cam_radius);
             modified = modified || s.vx != ovx || s.vy != ovy;
+            if (modified) { ++d; continue; }
+            cand &= ~((2ull << d) - 1ull);
+            if (cand == 0ull) break;
+            d = __ffsll((long long)cand) - 1;
         }
     }
     const double nx = fmin(fmax(tx + s.vx, -kTerrain), kTerrain);
