@@ -226,3 +226,26 @@ def test_multi_camera_with_live_greedy_targets():
     total_b, delivered_b = run(5)
     assert total_a == total_b and delivered_a == delivered_b
     assert delivered_a > 1.0     # greedy targets haul cargo (the reference's agents deliver ~43 in 700 steps)
+
+
+@pytest.mark.gpu
+def test_single_team_wrappers_in_reference_compatible_mode():
+    """num_envs=None: MultiCamera / MultiTarget keep the reference's single-env types."""
+    import mate_b200
+
+    env = mate_b200.make('MultiAgentTracking-v0', config='MATE-4v2-9.yaml',
+                         wrappers=[lambda e: mate_b200.MultiCamera(e, target_agent=mate_b200.GreedyTargetAgent(seed=0))])
+    obs = env.reset(seed=1)
+    assert isinstance(obs, np.ndarray) and obs.shape == (4, 96)
+    for _ in range(20):
+        obs, reward, done, infos = env.step(np.zeros((4, 2)))
+    assert isinstance(reward, float) and isinstance(done, bool) and len(infos) == 4 and obs.shape == (4, 96)
+    env.unwrapped.close()
+    env = mate_b200.make('MultiAgentTracking-v0', config='MATE-4v2-9.yaml',
+                         wrappers=[lambda e: mate_b200.MultiTarget(e, camera_agent=mate_b200.GreedyCameraAgent(seed=0))])
+    obs = env.reset(seed=1)
+    assert isinstance(obs, np.ndarray) and obs.shape == (2, 101)
+    for _ in range(20):
+        obs, reward, done, infos = env.step(np.zeros((2, 2)))
+    assert isinstance(reward, float) and isinstance(done, bool) and len(infos) == 2
+    env.unwrapped.close()

@@ -259,3 +259,37 @@ def test_reductions_and_callable_coefficients():
     individual = tgt_infos['auxiliary_reward_raw_reward'] - tgt_infos['auxiliary_reward_is_tracked']
     assert torch.allclose(tgt_reward, individual.min(dim=-1, keepdim=True).values.expand(-1, 8))
     env.unwrapped.close()
+
+
+@pytest.mark.gpu
+def test_reference_compatible_single_env_types():
+    """num_envs=None: the wrappers return the reference's types (lists of Python floats, list-of-dict infos)."""
+    import mate_b200
+
+    coefficients = {'raw_reward': 1.0, 'coverage_rate': 2.0, 'soft_coverage_score': 0.5, 'num_tracked': lambda c, ep, step, raw, value: 0.25}
+    env = mate_b200.make('MultiAgentTracking-v0', config='MATE-4v2-9.yaml', wrappers=[
+        mate_b200.MoreTrainingInformation, mate_b200.RepeatedRewardIndividualDone,
+        lambda e: mate_b200.AuxiliaryCameraRewards(e, coefficients=coefficients, reduction='mean'),
+        lambda e: mate_b200.AuxiliaryTargetRewards(e, coefficients={'normalized_goal_distance': -1.0, 'sparse_delivery': 10.0})])
+    cam_obs, tgt_obs = env.reset(seed=2)
+    assert isinstance(cam_obs, np.ndarray) and cam_obs.shape == (4, 96) and tgt_obs.shape == (2, 101)
+    rng = np.random.RandomState(0)
+    for _ in range(5):
+        action = (rng.uniform(-1, 1, (4, 2)) * [5.0, 2.5], rng.uniform(-1, 1, (2, 2)) * 20.0)
+        (cam_obs, tgt_obs), (cam_reward, tgt_reward), (cam_done, tgt_done), (cam_infos, tgt_infos) = env.step(action)
+    assert isinstance(cam_reward, list) and len(cam_reward) == 4 and isinstance(cam_reward[0], float)
+    assert isinstance(tgt_reward, list) and len(tgt_reward) == 2 and cam_done == [False] * 4 and tgt_done == [False] * 2
+    assert len(cam_infos) == 4 and len(tgt_infos) == 2
+    info = cam_infos[1]
+    for key in ('num_tracked', 'is_sensed', 'auxiliary_reward_soft_coverage_score', 'reward_coefficient_num_tracked', 'reward',
+                'shared_reward', 'camera_states', 'target_states', 'state', 'remaining_cargoes', 'camera_target_view_mask'):
+        assert key in info, key
+    assert info['reward_coefficient_num_tracked'] == 0.25 and cam_reward[0] == cam_reward[3] == info['shared_reward']
+    expected = (info['auxiliary_reward_raw_reward'] + 2.0 * info['auxiliary_reward_coverage_rate']
+                + 0.5 * info['auxiliary_reward_soft_coverage_score'] + 0.25 * info['auxiliary_reward_num_tracked'])
+    assert abs(info['reward'] - expected) < 1e-4
+    tinfo = tgt_infos[0]
+    assert tinfo['goal'] in (-1, 0, 1, 2, 3) and len(tinfo['warehouse_distances']) == 4
+    assert abs(tinfo['reward'] - (-tinfo['auxiliary_reward_normalized_goal_distance'] + 10.0 * tinfo['auxiliary_reward_sparse_delivery'])) < 1e-5
+    assert info['state'].shape == env.unwrapped.state_space.shape
+    env.unwrapped.close()
