@@ -9,7 +9,7 @@ import numpy as np
 import pytest
 
 import golden_util as gu
-from greedy_target_ref import team_step
+from oracle.greedy_target_ref import team_step
 
 NAMES = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(gu.GOLDEN_DIR, 'agents_*.npz')))
 
@@ -108,7 +108,7 @@ def _pack_camera_memory(g, suffix):
 def test_camera_restatement_matches_the_reference_agents(name):
     """CPU: the NumPy restatement of GreedyCameraAgent reproduces actions, memory, delays and known teammates of the
     recorded reference agents at every step."""
-    from greedy_camera_ref import team_step as camera_team_step
+    from oracle.greedy_camera_ref import team_step as camera_team_step
 
     g = gu.load(name)
     cam = g['cfg_camera']

@@ -149,7 +149,7 @@ def test_auxiliary_wrappers_match_the_reference(name):
 
 def _soft_reference(g, limit):
     """(matrix without tangent cuts, matrix with tangent cuts) of the NumPy restatement for the first samples."""
-    import soft_coverage_ref as sr
+    from oracle import soft_coverage_ref as sr
     from oracle.oracle import Oracle
 
     cfg = gu.flat_config(g)
