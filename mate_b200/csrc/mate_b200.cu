@@ -118,7 +118,7 @@ struct MateSim {
     cudaStream_t side = nullptr;
     cudaEvent_t side_event = nullptr;
     int refill_mode = 0;      // 0 = off, 1 = side stream every refill_period steps, 2 = same stream after every step (tests)
-    int refill_period = 256;
+    int refill_period = 512;
     long long steps_since_refill = 0;
     // host-path (step_host) resources
     static constexpr int kHostStreams = 4;
