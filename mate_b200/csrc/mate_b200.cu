@@ -452,6 +452,16 @@ static int check_obs_alignment(const void* cam_obs, const void* tgt_obs) {
     return MATE_OK;
 }
 
+// the view masks / per-target flags are written with 4-, 8- and 16-byte stores
+static int check_aux_alignment(const MateStepAux* aux) {
+    if (!aux) return MATE_OK;
+    const void* ptrs[] = {aux->mask_ct, aux->mask_cc, aux->mask_co, aux->mask_tc, aux->mask_to, aux->mask_tt, aux->target_dones,
+                          aux->is_colliding, aux->warehouse_dist};
+    for (const void* ptr : ptrs)
+        if ((uintptr_t)ptr & 15) return fail(MATE_EINVAL, "auxiliary output buffers must be 16-byte aligned");
+    return MATE_OK;
+}
+
 static void fill_aux(Params& p, const MateStepAux* aux, const MateReplay* replay) {
     if (aux) {
         p.aux = *aux; p.has_aux = 1;
@@ -518,6 +528,7 @@ extern "C" int mate_b200_step(MateSim* sim, const float* cam_act, const float* t
     if (sim->cfg.num_cameras > 0 && (!cam_act || !cam_obs)) return fail(MATE_EINVAL, "null camera buffers");
     if (int rc = check_obs_alignment(cam_obs, tgt_obs)) return rc;
     if (((uintptr_t)cam_act & 7) || ((uintptr_t)tgt_act & 7) || ((uintptr_t)rewards & 7)) return fail(MATE_EINVAL, "action/reward buffers must be 8-byte aligned");
+    if (int rc = check_aux_alignment(aux)) return rc;
     CUDA_TRY(cudaSetDevice(sim->device));
     Params p = sim->base;
     p.mode = MODE_STEP; p.flags = flags; p.seed = sim->seed;
@@ -534,6 +545,7 @@ extern "C" int mate_b200_observe(MateSim* sim, float* cam_obs, float* tgt_obs, c
                                  const MateReplay* replay, void* stream) {
     if (!sim || !tgt_obs || (sim->cfg.num_cameras > 0 && !cam_obs)) return fail(MATE_EINVAL, "null argument");
     if (int rc = check_obs_alignment(cam_obs, tgt_obs)) return rc;
+    if (int rc = check_aux_alignment(aux)) return rc;
     CUDA_TRY(cudaSetDevice(sim->device));
     Params p = sim->base;
     p.mode = MODE_OBSERVE; p.flags = 0; p.seed = sim->seed;

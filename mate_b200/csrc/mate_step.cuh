@@ -281,35 +281,100 @@ __device__ __noinline__ uint32_t reset_env_global(const Params& p, int e, RngKey
     return scr[10];
 }
 
+// One view mask of one environment ([ROWS][COLS] uint8 in the caller's tensor): the rows' bits are concatenated
+// into a bit string, four bits at a time become four bytes with one multiply ((x & 15) * 0x00204081 & 0x01010101
+// puts bit j into byte j), and the bytes leave with the widest store the row length allows -- instead of one
+// byte store per mask entry (a lane owns an environment, so every store of the warp touches 32 sectors).
+template <int ROWS, int COLS>
+struct MaskBytes {
+    static constexpr int L = ROWS * COLS, NB = (L + 31) / 32 > 0 ? (L + 31) / 32 : 1;
+    uint32_t w[NB];
+    __device__ __forceinline__ MaskBytes() {
+#pragma unroll
+        for (int i = 0; i < NB; ++i) w[i] = 0u;
+    }
+    __device__ __forceinline__ void row(const int r, uint32_t bits) {   // r must be a compile-time constant after unrolling
+        if (COLS < 32) bits &= (1u << (COLS & 31)) - 1u;
+        const int off = r * COLS, word = off >> 5, sh = off & 31;
+        w[word] |= bits << sh;
+        if (sh + COLS > 32) w[word + 1] |= bits >> (32 - sh);
+    }
+    __device__ __forceinline__ uint32_t bytes4(const int j) const {   // bytes 4 j .. 4 j + 3 of the row-major byte array
+        const uint32_t nib = (w[(4 * j) >> 5] >> ((4 * j) & 31)) & 15u;
+        return (nib * 0x00204081u) & 0x01010101u;
+    }
+    __device__ __forceinline__ void store(uint8_t* base, const size_t e) const {
+        if (L == 0) return;
+        uint8_t* dst = base + e * L;
+        if (L % 16 == 0) {
+#pragma unroll
+            for (int i = 0; i < L / 16; ++i)
+                reinterpret_cast<uint4*>(dst)[i] = make_uint4(bytes4(4 * i), bytes4(4 * i + 1), bytes4(4 * i + 2), bytes4(4 * i + 3));
+        } else if (L % 8 == 0) {
+#pragma unroll
+            for (int i = 0; i < L / 8; ++i) reinterpret_cast<uint2*>(dst)[i] = make_uint2(bytes4(2 * i), bytes4(2 * i + 1));
+        } else if (L % 4 == 0) {
+#pragma unroll
+            for (int i = 0; i < L / 4; ++i) reinterpret_cast<uint32_t*>(dst)[i] = bytes4(i);
+        } else {
+#pragma unroll
+            for (int i = 0; i < L; ++i) dst[i] = (uint8_t)((w[i >> 5] >> (i & 31)) & 1u);
+        }
+    }
+};
+
 // aux outputs = the reference's public per-step attributes (environment.py:634-661); one lane = one env
 template <int NC, int NT, int NO, class S>
 __device__ __noinline__ void write_aux_env(const Params& p, int e, const uint32_t* mrow, const float* vrow, uint32_t tdone_bits,
                                            float cov_now, float cov_real, float transport, int delivered, int episode_step) {
     const MateStepAux& ax = p.aux;
     constexpr int MW = S::MW;
-    auto obs_bit = [&](int row, int o) -> uint8_t { return MW == 1 ? (mrow[row] >> (16 + o)) & 1 : (mrow[row * MW + 1] >> o) & 1; };
-    for (int c = 0; c < NC; ++c) {
-        const uint32_t w = mrow[c * MW];
-        if (ax.mask_ct) for (int t = 0; t < NT; ++t) ax.mask_ct[((size_t)e * NC + c) * NT + t] = (w >> (8 + t)) & 1;
-        if (ax.mask_cc) for (int j = 0; j < NC; ++j) ax.mask_cc[((size_t)e * NC + c) * NC + j] = (w >> j) & 1;
-        if (ax.mask_co) for (int o = 0; o < NO; ++o) ax.mask_co[((size_t)e * NC + c) * NO + o] = obs_bit(c, o);
+    auto obs_bits = [&](int row) -> uint32_t { return MW == 1 ? (mrow[row] >> 16) : mrow[row * MW + 1]; };
+    {
+        MaskBytes<NC, NT> ct; MaskBytes<NC, NC> cc; MaskBytes<NC, NO> co;
+#pragma unroll
+        for (int c = 0; c < NC; ++c) {
+            const uint32_t w = mrow[c * MW];
+            ct.row(c, w >> 8); cc.row(c, w); co.row(c, obs_bits(c));
+        }
+        if (ax.mask_ct) ct.store(ax.mask_ct, (size_t)e);
+        if (ax.mask_cc) cc.store(ax.mask_cc, (size_t)e);
+        if (ax.mask_co) co.store(ax.mask_co, (size_t)e);
+    }
+    {
+        MaskBytes<NT, NC> tc; MaskBytes<NT, NT> tt; MaskBytes<NT, NO> to;
+#pragma unroll
+        for (int t = 0; t < NT; ++t) {
+            const uint32_t w = mrow[(NC + t) * MW];
+            tc.row(t, w); tt.row(t, w >> 8); to.row(t, obs_bits(NC + t));
+        }
+        if (ax.mask_tc) tc.store(ax.mask_tc, (size_t)e);
+        if (ax.mask_tt) tt.store(ax.mask_tt, (size_t)e);
+        if (ax.mask_to) to.store(ax.mask_to, (size_t)e);
+    }
+    {   // per-target flags and integers
+        MaskBytes<1, NT> dones, colliding;
+        uint32_t coll = 0;
+#pragma unroll
+        for (int t = 0; t < NT; ++t) coll |= (uint32_t)tp_colliding(__float_as_uint(vrow[S::V_T + 3 * t + 2])) << t;
+        dones.row(0, tdone_bits); colliding.row(0, coll);
+        if (ax.target_dones) dones.store(ax.target_dones, (size_t)e);
+        if (ax.is_colliding) colliding.store(ax.is_colliding, (size_t)e);
     }
     for (int t = 0; t < NT; ++t) {
-        const uint32_t w = mrow[(NC + t) * MW];
-        if (ax.mask_tc) for (int c = 0; c < NC; ++c) ax.mask_tc[((size_t)e * NT + t) * NC + c] = (w >> c) & 1;
-        if (ax.mask_tt) for (int u = 0; u < NT; ++u) ax.mask_tt[((size_t)e * NT + t) * NT + u] = (w >> (8 + u)) & 1;
-        if (ax.mask_to) for (int o = 0; o < NO; ++o) ax.mask_to[((size_t)e * NT + t) * NO + o] = obs_bit(NC + t, o);
-        if (ax.target_dones) ax.target_dones[(size_t)e * NT + t] = (tdone_bits >> t) & 1;
-        if (ax.is_colliding) ax.is_colliding[(size_t)e * NT + t] = (uint8_t)tp_colliding(__float_as_uint(vrow[S::V_T + 3 * t + 2]));
-        if (ax.tgt_goal) ax.tgt_goal[(size_t)e * NT + t] = tp_goal(__float_as_uint(vrow[S::V_T + 3 * t + 2]));
-        if (ax.tgt_empty_bits) ax.tgt_empty_bits[(size_t)e * NT + t] = (uint8_t)tp_empty(__float_as_uint(vrow[S::V_T + 3 * t + 2]));
+        const uint32_t tp = __float_as_uint(vrow[S::V_T + 3 * t + 2]);
+        if (ax.tgt_goal) ax.tgt_goal[(size_t)e * NT + t] = tp_goal(tp);
+        if (ax.tgt_empty_bits) ax.tgt_empty_bits[(size_t)e * NT + t] = (uint8_t)tp_empty(tp);
         if (ax.warehouse_dist) {
             const double tx = p.tgt_x[(size_t)t * p.bpad + e], ty = p.tgt_y[(size_t)t * p.bpad + e];
+            float wd[NW];
+#pragma unroll
             for (int w4 = 0; w4 < NW; ++w4) {
                 const double wx = (w4 == 0 || w4 == 3) ? kWarehouseCoord : -kWarehouseCoord;
                 const double wy = (w4 < 2) ? kWarehouseCoord : -kWarehouseCoord;
-                ax.warehouse_dist[((size_t)e * NT + t) * NW + w4] = (float)norm2(tx - wx, ty - wy);
+                wd[w4] = (float)norm2(tx - wx, ty - wy);
             }
+            reinterpret_cast<float4*>(ax.warehouse_dist)[(size_t)e * NT + t] = make_float4(wd[0], wd[1], wd[2], wd[3]);
         }
     }
     if (ax.coverage) {   // coverage statistics (environment.py:966-979)

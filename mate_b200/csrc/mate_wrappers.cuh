@@ -380,6 +380,7 @@ __global__ void soft_coverage_kernel(const Params p, const uint8_t* __restrict__
     // The discs are broadcast with shuffles, so this is always called by all lanes; lanes without a sample (or with
     // a sample outside the sector) pass live = false.
     auto sample_if = [&](const bool live, const double a, const double norm) {
+        if (!__any_sync(FULL, live)) return;   // the whole batch of 32 samples lies outside the sector
         double sn, cs;
         sincospi(a * (1.0 / 180.0), &sn, &cs);
         double n = collapsed ? 0.0 : norm;
@@ -416,6 +417,10 @@ __global__ void soft_coverage_kernel(const Params p, const uint8_t* __restrict__
             const double R = __shfl_sync(FULL, orad, o), d = __shfl_sync(FULL, od, o);
             const double ang = atan2(ry, rx) * kRad2Deg, half = asin(R / d) * kRad2Deg;
             const double aL = ang - half, aR = ang + half;
+            {   // angular distance between the disc's bearing and the sector axis vs. the two half widths (+ slack)
+                const double off = fabs(normalize_angle(ang - phi));
+                if (off > half + theta * 0.5 + 0.02) continue;
+            }
             const double max_rho = fmin(rmax, d + R);
             const int two_half = (int)(2.0 * half);
             const int nlat = two_half > 16 ? two_half : 16;
