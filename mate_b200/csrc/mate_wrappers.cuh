@@ -320,9 +320,10 @@ __global__ void aux_terms_kernel(const MateStepAux ax, const float* __restrict__
 // (Camera.add_obstacles / boundary_between(outer=True), mate/entities.py:362-479, 484-511) restricted to the
 // current sector, plus the two sector edges (end points from the inner polyline, 16 points along each edge).
 // Like the inner polyline it is never materialised: one warp per (environment, camera) enumerates the sample rays
-// (integer-degree grid; per obstacle the lattice at max_rho and the two 21-point edge segments), keeps those
-// inside the sector, cuts each at the FAR side of the discs it crosses (Obstacle.obstruct(outer=True),
-// entities.py:158-184) and keeps, per target, the minimum squared distance in registers.
+// (integer-degree grid; per obstacle the lattice at max_rho and the two 21-point edge segments), one per lane, keeps
+// those inside the sector, cuts each at the FAR side of the discs it crosses (Obstacle.obstruct(outer=True),
+// entities.py:158-184; the discs sit in shared memory, a bearing test rejects the ones a ray cannot cross) and keeps,
+// per target, the minimum squared distance in registers.
 // Exactly tangent rays are not cut by their own disc (the reference decides them by rounding noise, DESIGN.md
 // "Tangent rays").  Environments that were auto-reset in the last step get zeros (their state already belongs to
 // the next episode).
@@ -330,9 +331,14 @@ __global__ void aux_terms_kernel(const MateStepAux ax, const float* __restrict__
 template <int NC, int NT, int NO>
 __global__ void soft_coverage_kernel(const Params p, const uint8_t* __restrict__ mask_ct, const uint8_t* __restrict__ done,
                                      float* __restrict__ out) {
-    constexpr int NCX = NC > 0 ? NC : 1;
+    constexpr int NCX = NC > 0 ? NC : 1, NOX = NO > 0 ? NO : 1;
     constexpr uint32_t FULL = 0xffffffffu;
+    constexpr int WARPS = 4;   // launch: 128 threads per block
+    // per warp: the discs of the camera's obstacle set {x, y, R, distance, bearing, half opening angle} relative to
+    // the camera; read by all lanes at the same address (broadcast)
+    __shared__ double sdisc[WARPS][NOX][6];
     const int lane = threadIdx.x & 31;
+    double (*disc)[6] = sdisc[(threadIdx.x >> 5) & (WARPS - 1)];
     const long long item = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;   // (environment, camera)
     if (item >= (long long)p.num_envs * NCX) return;
     const int e = (int)(item / NCX), c = (int)(item - (long long)e * NCX);
@@ -346,16 +352,19 @@ __global__ void soft_coverage_kernel(const Params p, const uint8_t* __restrict__
     const double phi = p.cam_phi[(size_t)c * bp + e], theta = p.cam_theta[(size_t)c * bp + e];
     const double rmax = p.cam_rmax;
     // the camera's obstacle set (entities.py:363-368), one disc per lane
-    double ox = 0.0, oy = 0.0, orad = 0.0, od = 0.0;
     bool member = false, inside_disc = false;
     if (lane < NO) {
-        ox = p.obs_x[(size_t)lane * bp + e] - cx; oy = p.obs_y[(size_t)lane * bp + e] - cy; orad = p.obs_r[(size_t)lane * bp + e];
-        od = sqrt(ox * ox + oy * oy);
+        const double ox = p.obs_x[(size_t)lane * bp + e] - cx, oy = p.obs_y[(size_t)lane * bp + e] - cy, orad = p.obs_r[(size_t)lane * bp + e];
+        const double od = sqrt(ox * ox + oy * oy);
         member = od < rmax + orad;
         inside_disc = member && orad > od;
+        disc[lane][0] = ox; disc[lane][1] = oy; disc[lane][2] = orad; disc[lane][3] = od;
+        disc[lane][4] = atan2(oy, ox) * kRad2Deg;
+        disc[lane][5] = od > orad ? asin(orad / od) * kRad2Deg : 90.0;
     }
     const uint32_t members = __ballot_sync(FULL, member);
     const bool collapsed = __any_sync(FULL, inside_disc);   // entities.py:378-388: every ray has norm 0
+    __syncwarp();
     // sector (boundary_between, entities.py:484-511)
     const double left = normalize_angle(phi - theta * 0.5), right = left + theta;
     const bool wraps = right > 180.0;
@@ -376,11 +385,11 @@ __global__ void soft_coverage_kernel(const Params p, const uint8_t* __restrict__
             best[t] = fmin(best[t], dx * dx + dy * dy);
         }
     };
-    // One sample ray (angle in degrees, normalised; norm): cut at the far side of the discs it crosses, then visit.
-    // The discs are broadcast with shuffles, so this is always called by all lanes; lanes without a sample (or with
-    // a sample outside the sector) pass live = false.
+    // One sample ray (angle in degrees, normalised; norm): cut at the far side of the discs it crosses
+    // (Obstacle.obstruct(outer=True)), then visit.  A ray can only cross a disc whose bearing is within the disc's
+    // half opening angle of the ray: everything else is rejected on two shared-memory reads.
     auto sample_if = [&](const bool live, const double a, const double norm) {
-        if (!__any_sync(FULL, live)) return;   // the whole batch of 32 samples lies outside the sector
+        if (!live) return;
         double sn, cs;
         sincospi(a * (1.0 / 180.0), &sn, &cs);
         double n = collapsed ? 0.0 : norm;
@@ -388,8 +397,8 @@ __global__ void soft_coverage_kernel(const Params p, const uint8_t* __restrict__
         while (m != 0u) {
             const int o = __ffs(m) - 1;
             m &= m - 1u;
-            const double rx = __shfl_sync(FULL, ox, o), ry = __shfl_sync(FULL, oy, o);
-            const double R = __shfl_sync(FULL, orad, o), d = __shfl_sync(FULL, od, o);
+            if (fabs(normalize_angle(a - disc[o][4])) > disc[o][5] + 1e-4) continue;
+            const double rx = disc[o][0], ry = disc[o][1], R = disc[o][2], d = disc[o][3];
             if (!(n > 0.0) || d >= n + R) continue;
             const double proj = rx * cs + ry * sn;
             if (proj < 0.0) continue;
@@ -399,7 +408,7 @@ __global__ void soft_coverage_kernel(const Params p, const uint8_t* __restrict__
             const double far_side = fmax(0.0, d * cosv + sqrt(fmax(R * R - perp * perp, 0.0)));
             if (far_side < n) n = far_side;
         }
-        if (live) visit(n, cs, sn);
+        visit(n, cs, sn);
     };
     // (a) the integer-degree grid (entities.py:339-342)
     for (int k0 = 0; k0 < 360; k0 += 32) {
@@ -413,9 +422,7 @@ __global__ void soft_coverage_kernel(const Params p, const uint8_t* __restrict__
         while (m != 0u) {
             const int o = __ffs(m) - 1;
             m &= m - 1u;
-            const double rx = __shfl_sync(FULL, ox, o), ry = __shfl_sync(FULL, oy, o);
-            const double R = __shfl_sync(FULL, orad, o), d = __shfl_sync(FULL, od, o);
-            const double ang = atan2(ry, rx) * kRad2Deg, half = asin(R / d) * kRad2Deg;
+            const double R = disc[o][2], d = disc[o][3], ang = disc[o][4], half = disc[o][5];
             const double aL = ang - half, aR = ang + half;
             {   // angular distance between the disc's bearing and the sector axis vs. the two half widths (+ slack)
                 const double off = fabs(normalize_angle(ang - phi));
