@@ -4,13 +4,13 @@ import numpy as np, torch, mate_b200
 B = 128
 env = mate_b200.make('MultiAgentTracking-v0', config='MATE-8v8-9.yaml', num_envs=B, wrappers=[
     lambda e: mate_b200.MoreTrainingInformation(e, full_observability=True), mate_b200.SharedFieldOfView, mate_b200.RescaledObservation,
-    mate_b200.DiscreteTarget, mate_b200.RepeatedRewardIndividualDone,
+    mate_b200.DiscreteCamera, mate_b200.RepeatedRewardIndividualDone,
     lambda e: mate_b200.AuxiliaryCameraRewards(e, coefficients={'soft_coverage_score': 1.0, 'coverage_rate': 1.0}, reduction='sum'),
     lambda e: mate_b200.MultiCamera(e, target_agent=mate_b200.GreedyTargetAgent(seed=3))])
 print(env)
 obs = env.reset(seed=1)
 for k in range(30):
-    obs, reward, done, infos = env.step(torch.zeros((B, 8, 2), device='cuda'))
+    obs, reward, done, infos = env.step(torch.randint(0, 25, (B, 8), device="cuda"))
 print(obs.shape, reward.shape, done.shape, sorted(infos)[:8], float(reward.mean()))
 assert infos['remaining_cargoes'].shape == (B, 4, 4) and infos['state'].shape[0] == B
 env.unwrapped.close()
