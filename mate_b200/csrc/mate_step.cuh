@@ -484,73 +484,54 @@ __device__ __noinline__ void prefetch_prepared(const Params& nx, int e) {
     pf(nx.cargo + e); pf(nx.cargo + bp + e); pf(nx.env_a + e); pf(nx.cc_clear + e);
 }
 
-// copy the prepared initial state of env e from block `nx` into the live block `p`, the fp32 entries and
-// the first-view masks into shared memory; cargo / line-of-sight cache are returned
+// Copy the prepared initial state of the adopting environments (bit set `adopting`) from block `nx` into the live
+// block `p`, the fp32 entries and the first-view masks into shared memory.  The whole warp copies: one lane copying
+// ~180 scattered words that nobody has touched for an episode needs three to four dependent round trips while its
+// warp (and, at the end of the launch, the whole grid) waits; spread over the 32 lanes every lane has 4-5 loads in
+// flight and the copy is one round trip.  Cargo, the awaiting counts and the line-of-sight cache go to registers of
+// the adopting lane and are loaded by that lane itself.
 template <int NC, int NT, int NO, class S>
-__device__ __noinline__ void adopt_prepared(const Params& p, const Params& nx, int e, float* myval, uint32_t* mymk,
-                                            Cargo* cargo, unsigned long long* ccw) {
-    // One lane copies ~90 scattered words that nobody has touched for a whole episode (DRAM latency each):
-    // the loads of a group are all issued before the first one is used.
+__device__ __noinline__ void adopt_prepared_warp(const Params& p, const Params& nx, const int env0, uint32_t adopting,
+                                                 float* val, uint32_t* mk) {
+    constexpr int ND = 4 * NC + 2 * NT + 3 * NO, NV = S::VN, NM = S::R * S::MW;
+    constexpr int JD = (ND + 31) / 32, JV = (NV + 31) / 32, JM = (NM + 31) / 32, JF = (NO + 31) / 32 > 0 ? (NO + 31) / 32 : 1;
+    const int lane = threadIdx.x & 31;
     const size_t bp = p.bpad;
-    const double* const ncx = nx.cam_x + e; const double* const ncy = nx.cam_y + e;
-    const double* const nph = nx.cam_phi + e; const double* const nth = nx.cam_theta + e;
-    const double* const ntx = nx.tgt_x + e; const double* const nty = nx.tgt_y + e;
-    const double* const nox = nx.obs_x + e; const double* const noy = nx.obs_y + e; const double* const nor = nx.obs_r + e;
-    const float4* const nof = nx.obs_f4 + e;
-    const uint32_t* const nmk = nx.masks + e;
-    const uint4 c0 = nx.cargo[e], c1 = nx.cargo[bp + e], ea = nx.env_a[e];
-    const unsigned long long cc = NC >= 2 ? nx.cc_clear[e] : 0ull;
-    // group 1: masks, cargo (above), cameras, targets
-    uint32_t mw[S::R * S::MW];
+    while (adopting != 0u) {
+        const int src = __ffs(adopting) - 1;
+        adopting &= adopting - 1u;
+        const int e = env0 + src;
+        auto field = [&](const Params& q, const int k) -> double* {   // k-th double of an environment's state
+            if (k < 4 * NC) {
+                const int f = k / (NC > 0 ? NC : 1), c = k - f * NC;
+                double* base = f == 0 ? q.cam_x : (f == 1 ? q.cam_y : (f == 2 ? q.cam_phi : q.cam_theta));
+                return base + (size_t)c * bp + e;
+            }
+            if (k < 4 * NC + 2 * NT) {
+                const int r = k - 4 * NC, f = r / NT, t = r - f * NT;
+                return (f == 0 ? q.tgt_x : q.tgt_y) + (size_t)t * bp + e;
+            }
+            const int r = k - 4 * NC - 2 * NT, f = r / (NO > 0 ? NO : 1), o = r - f * NO;
+            return (f == 0 ? q.obs_x : (f == 1 ? q.obs_y : q.obs_r)) + (size_t)o * bp + e;
+        };
+        double d[JD]; float v[JV]; uint32_t m[JM]; float4 f4[JF];
 #pragma unroll
-    for (int w = 0; w < S::R * S::MW; ++w) mw[w] = nmk[(size_t)w * bp];
-    {
-        double cx[NC > 0 ? NC : 1], cy[NC > 0 ? NC : 1], ph[NC > 0 ? NC : 1], th[NC > 0 ? NC : 1], tx[NT], ty[NT];
+        for (int j = 0; j < JD; ++j) { const int k = lane + 32 * j; d[j] = k < ND ? *field(nx, k) : 0.0; }
 #pragma unroll
-        for (int c = 0; c < NC; ++c) { cx[c] = ncx[(size_t)c * bp]; cy[c] = ncy[(size_t)c * bp]; ph[c] = nph[(size_t)c * bp]; th[c] = nth[(size_t)c * bp]; }
+        for (int j = 0; j < JV; ++j) { const int k = lane + 32 * j; v[j] = k < NV ? nx.vals[(size_t)k * bp + e] : 0.f; }
 #pragma unroll
-        for (int t = 0; t < NT; ++t) { tx[t] = ntx[(size_t)t * bp]; ty[t] = nty[(size_t)t * bp]; }
+        for (int j = 0; j < JM; ++j) { const int k = lane + 32 * j; m[j] = k < NM ? nx.masks[(size_t)k * bp + e] : 0u; }
 #pragma unroll
-        for (int c = 0; c < NC; ++c) {
-            const size_t i = (size_t)c * bp + e;
-            p.cam_x[i] = cx[c]; p.cam_y[i] = cy[c]; p.cam_phi[i] = ph[c]; p.cam_theta[i] = th[c];
-        }
+        for (int j = 0; j < JF; ++j) { const int k = lane + 32 * j; f4[j] = k < NO ? nx.obs_f4[(size_t)k * bp + e] : make_float4(0.f, 0.f, 0.f, 0.f); }
 #pragma unroll
-        for (int t = 0; t < NT; ++t) {
-            const size_t i = (size_t)t * bp + e;
-            p.tgt_x[i] = tx[t]; p.tgt_y[i] = ty[t];
-        }
+        for (int j = 0; j < JD; ++j) { const int k = lane + 32 * j; if (k < ND) *field(p, k) = d[j]; }
+#pragma unroll
+        for (int j = 0; j < JV; ++j) { const int k = lane + 32 * j; if (k < NV) val[src * S::VSTRIDE + k] = v[j]; }
+#pragma unroll
+        for (int j = 0; j < JM; ++j) { const int k = lane + 32 * j; if (k < NM) mk[src * S::MSTRIDE + k] = m[j]; }
+#pragma unroll
+        for (int j = 0; j < JF; ++j) { const int k = lane + 32 * j; if (k < NO) p.obs_f4[(size_t)k * bp + e] = f4[j]; }
     }
-    {   // group 2: fp32 entity entries (targets incl. their packed state, cameras incl. the derived heading)
-        const float* const nv = nx.vals + e;
-        float f[S::VN];
-#pragma unroll
-        for (int k = 0; k < S::VN; ++k) f[k] = nv[(size_t)k * bp];
-#pragma unroll
-        for (int k = 0; k < S::VN; ++k) myval[k] = f[k];
-    }
-    constexpr int OB = 12;   // group 3 (+): obstacles, 12 at a time
-#pragma unroll 1
-    for (int o0 = 0; o0 < NO; o0 += OB) {
-        double x[OB], y[OB], r[OB]; float4 f[OB];
-#pragma unroll
-        for (int k = 0; k < OB; ++k) if (o0 + k < NO) {
-            const size_t i = (size_t)(o0 + k) * bp;
-            x[k] = nox[i]; y[k] = noy[i]; r[k] = nor[i]; f[k] = nof[i];
-        }
-#pragma unroll
-        for (int k = 0; k < OB; ++k) if (o0 + k < NO) {
-            const size_t i = (size_t)(o0 + k) * bp + e;
-            p.obs_x[i] = x[k]; p.obs_y[i] = y[k]; p.obs_r[i] = r[k]; p.obs_f4[i] = f[k];
-        }
-    }
-#pragma unroll
-    for (int w = 0; w < S::R * S::MW; ++w) mymk[w] = mw[w];
-    cargo->rem[0] = c0.x; cargo->rem[1] = c0.y; cargo->rem[2] = c0.z; cargo->rem[3] = c0.w;
-    cargo->rem[4] = c1.x; cargo->rem[5] = c1.y; cargo->rem[6] = c1.z; cargo->rem[7] = c1.w;
-    cargo->aw[0] = ea.x; cargo->aw[1] = ea.y;
-    *ccw = cc;
-    if (NC >= 2) p.cc_clear[e] = cc;
 }
 
 // =============================================================================================
@@ -988,9 +969,27 @@ mate_step_kernel2(const __grid_constant__ Params p) {
         const bool view_active = mode == MODE_PREPARE ? need : (((pass == 0) || do_reset) && !adopted);
         // ============================================================== reset (environment.py:679-775)
         if (__any_sync(FULL, do_reset)) {
+            {
+                uint4 c0 = make_uint4(0, 0, 0, 0), c1 = c0, ea2 = c0;
+                unsigned long long cc = 0ull;
+                if (adopted) {   // lane-private part: in flight while the warp copies the rest
+                    const Params& nx = *p.next;
+                    c0 = nx.cargo[e]; c1 = nx.cargo[bp + e]; ea2 = nx.env_a[e];
+                    if (NC >= 2) cc = nx.cc_clear[e];
+                }
+                const uint32_t adopting = __ballot_sync(FULL, adopted);
+                if (adopting != 0u) adopt_prepared_warp<NC, NT, NO, S>(p, *p.next, env0, adopting, val, mk);
+                __syncwarp();
+                if (adopted) {
+                    cargo.rem[0] = c0.x; cargo.rem[1] = c0.y; cargo.rem[2] = c0.z; cargo.rem[3] = c0.w;
+                    cargo.rem[4] = c1.x; cargo.rem[5] = c1.y; cargo.rem[6] = c1.z; cargo.rem[7] = c1.w;
+                    cargo.aw[0] = ea2.x; cargo.aw[1] = ea2.y;
+                    ccw = cc;
+                    if (NC >= 2) p.cc_clear[e] = cc;
+                }
+            }
             if (adopted) {
                 atomicAdd(&p.stats[6], 1.0f);   // auto-resets served from the prepared state
-                adopt_prepared<NC, NT, NO, S>(p, *p.next, e, myval, mymk, &cargo, &ccw);
                 cargo_loaded = true; cargo_dirty = true;
                 episode_id += 1; key.episode = (uint32_t)episode_id;
                 episode_step = 0; delivered = 0; ep_reward = 0; delayed_ep_reward = 0; coverage_sum = 0.f;
