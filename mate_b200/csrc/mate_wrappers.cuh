@@ -371,18 +371,20 @@ __global__ void soft_coverage_kernel(const Params p, const uint8_t* __restrict__
     auto in_sector = [&](const double a) {
         return wraps ? (a > left || a < right - 360.0 || a == -180.0) : (a > left && a < right);
     };
-    double tx[NT], ty[NT], best[NT];
+    // the boundary points are computed in fp64; the distances of the targets to them (relative to the camera, at
+    // most ~4000 units) in fp32: the score is a float32 anyway and loses < 1e-6 of dist_max here
+    float tx[NT], ty[NT], best[NT];
 #pragma unroll
     for (int t = 0; t < NT; ++t) {
-        tx[t] = p.tgt_x[(size_t)t * bp + e] - cx; ty[t] = p.tgt_y[(size_t)t * bp + e] - cy;
-        best[t] = 1e300;
+        tx[t] = (float)(p.tgt_x[(size_t)t * bp + e] - cx); ty[t] = (float)(p.tgt_y[(size_t)t * bp + e] - cy);
+        best[t] = 3.0e38f;
     }
     auto visit = [&](const double rho, const double cs, const double sn) {
-        const double px = rho * cs, py = rho * sn;
+        const float px = (float)(rho * cs), py = (float)(rho * sn);
 #pragma unroll
         for (int t = 0; t < NT; ++t) {
-            const double dx = tx[t] - px, dy = ty[t] - py;
-            best[t] = fmin(best[t], dx * dx + dy * dy);
+            const float dx = tx[t] - px, dy = ty[t] - py;
+            best[t] = fminf(best[t], dx * dx + dy * dy);
         }
     };
     // One sample ray (angle in degrees, normalised; norm): cut at the far side of the discs it crosses
@@ -477,7 +479,7 @@ __global__ void soft_coverage_kernel(const Params p, const uint8_t* __restrict__
 #pragma unroll
     for (int t = 0; t < NT; ++t) {
 #pragma unroll
-        for (int sh = 16; sh >= 1; sh >>= 1) best[t] = fmin(best[t], __shfl_xor_sync(FULL, best[t], sh));
+        for (int sh = 16; sh >= 1; sh >>= 1) best[t] = fminf(best[t], __shfl_xor_sync(FULL, best[t], sh));
     }
     const double sight_range = sqrt(p.cam_area_product / theta);
     double sn_h, cs_h;
@@ -486,7 +488,7 @@ __global__ void soft_coverage_kernel(const Params p, const uint8_t* __restrict__
     if (lane == 0) {
 #pragma unroll
         for (int t = 0; t < NT; ++t) {
-            const double dist = sqrt(best[t]);
+            const double dist = (double)sqrtf(best[t]);
             const bool tracked = mask_ct[((size_t)e * NCX + c) * NT + t] != 0;
             row[t] = (float)((tracked ? dist : -dist) / dist_max);
         }
