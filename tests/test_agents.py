@@ -249,3 +249,41 @@ def test_single_team_wrappers_in_reference_compatible_mode():
         obs, reward, done, infos = env.step(np.zeros((2, 2)))
     assert isinstance(reward, float) and isinstance(done, bool) and len(infos) == 2
     env.unwrapped.close()
+
+
+@pytest.mark.gpu
+def test_agent_draws_do_not_depend_on_the_batch_split():
+    """Multi-GPU sharding: the agents' Philox streams are keyed on the GLOBAL environment index,
+    so one batch of 128 environments and two shards of 64 (env_index_base 0 / 64) produce the same joint actions."""
+    import torch
+
+    import mate_b200
+    from mate_b200.config import flatten_config, read_config
+    from mate_b200.sim import BatchedSim
+
+    cfg = flatten_config(read_config('MATE-4v8-9.yaml'))
+
+    def run(num_envs, base):
+        sim = BatchedSim(cfg, num_envs, device=0, env_index_base=base)
+        sim.reset(seed=9)
+        sim.observe(aux=True)
+        targets = mate_b200.GreedyTargetAgent(seed=5)
+        cameras = mate_b200.GreedyCameraAgent(seed=6)
+        targets.bind(sim)
+        cameras.bind(sim)
+        out = []
+        reset = True
+        for _ in range(40):
+            tracked = (sim.cam_obs[..., 26:22 + 5 * 8:5] > 0.5).to(torch.uint8)
+            tgt_act = targets.act(reset_mask=reset).clone()
+            cam_act = cameras.act(tracked, reset_mask=reset).clone()
+            reset = None
+            sim.step(cam_act, tgt_act, auto_reset=True, aux=True)
+            out.append((cam_act.cpu().numpy(), tgt_act.cpu().numpy()))
+        sim.close()
+        return out
+
+    whole, lo, hi = run(128, 0), run(64, 0), run(64, 64)
+    for (cam_w, tgt_w), (cam_l, tgt_l), (cam_h, tgt_h) in zip(whole, lo, hi):
+        np.testing.assert_array_equal(cam_w, np.concatenate([cam_l, cam_h]))
+        np.testing.assert_array_equal(tgt_w, np.concatenate([tgt_l, tgt_h]))
