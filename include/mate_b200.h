@@ -151,6 +151,13 @@ int mate_b200_obs_dims(const MateSim* sim, int32_t* cam_dim, int32_t* tgt_dim);
 int mate_b200_reset(MateSim* sim, const uint8_t* env_mask, uint64_t seed,
                     float* cam_obs, float* tgt_obs, void* stream);
 
+/* MultiAgentTracking.seed / reset(seed=...) (environment.py:700-701, 1203-1227): an explicit seed makes the
+ * following resets reproducible.  Stores `seed` as the key of the handle's Philox streams and rewinds the
+ * episode counter (the RNG counter field mate_b200_reset advances) of the envs with env_mask[b] != 0 (dev,
+ * NULL = all), so that seed(s) followed by reset gives the same initial states every time.  Without this call
+ * successive resets draw independent episodes, like the reference's reset() without a seed. */
+int mate_b200_seed(MateSim* sim, const uint8_t* env_mask, uint64_t seed, void* stream);
+
 /* MultiAgentTracking.step (environment.py:590-676) for all envs: _simulate,
  * _update_view, _assign_goals, joint_observation, reward/done.
  *   cam_act [B,Nc,2], tgt_act [B,Nt,2] float32 dev (finite);

@@ -174,6 +174,7 @@ def load_library():
     lib.mate_b200_destroy.argtypes = [void_p]
     lib.mate_b200_obs_dims.argtypes = [void_p, c_int32_p, c_int32_p]
     lib.mate_b200_reset.argtypes = [void_p, void_p, ctypes.c_uint64, void_p, void_p, void_p]
+    lib.mate_b200_seed.argtypes = [void_p, void_p, ctypes.c_uint64, void_p]
     lib.mate_b200_step.argtypes = [void_p, void_p, void_p, void_p, void_p, void_p, void_p,
                                    ctypes.POINTER(MateStepAux), ctypes.POINTER(MateReplay), ctypes.c_uint32, void_p]
     lib.mate_b200_observe.argtypes = [void_p, void_p, void_p, ctypes.POINTER(MateStepAux), ctypes.POINTER(MateReplay), void_p]
@@ -192,7 +193,7 @@ def load_library():
     lib.mate_b200_greedy_camera_actions.argtypes = [void_p, void_p, void_p, void_p, ctypes.c_uint64, ctypes.c_uint64,
                                                     ctypes.POINTER(MateCameraAgentReplay), void_p, void_p]
     lib.mate_b200_soft_coverage.argtypes = [void_p, void_p, void_p, void_p, void_p]
-    for name in ('create', 'destroy', 'obs_dims', 'reset', 'step', 'observe', 'step_host',
+    for name in ('create', 'destroy', 'obs_dims', 'reset', 'seed', 'step', 'observe', 'step_host',
                  'get_state', 'set_state', 'episode_stats', 'transform_observations', 'decode_actions', 'auxiliary_terms', 'fov_range', 'soft_coverage', 'greedy_target_actions', 'greedy_camera_actions'):
         getattr(lib, 'mate_b200_' + name).restype = ctypes.c_int
     _LIB = lib
@@ -201,7 +202,7 @@ def load_library():
 
 EXPORTED_SYMBOLS = [
     'mate_b200_last_error', 'mate_b200_abi_version', 'mate_b200_create', 'mate_b200_destroy',
-    'mate_b200_obs_dims', 'mate_b200_reset', 'mate_b200_step', 'mate_b200_observe',
+    'mate_b200_obs_dims', 'mate_b200_reset', 'mate_b200_seed', 'mate_b200_step', 'mate_b200_observe',
     'mate_b200_step_host', 'mate_b200_get_state', 'mate_b200_set_state',
     'mate_b200_episode_stats', 'mate_b200_launch_count', 'mate_b200_transform_observations',
     'mate_b200_decode_actions', 'mate_b200_auxiliary_terms', 'mate_b200_fov_range', 'mate_b200_soft_coverage', 'mate_b200_greedy_target_actions', 'mate_b200_greedy_camera_actions',

@@ -23,7 +23,9 @@ __global__ void greedy_target_kernel(const Params p, const int nt, double* __res
     const size_t bp = p.bpad;
     const bool reset = reset_mask != nullptr && reset_mask[e] != 0;
     const RngKey key{seed, (uint32_t)(p.env_index_base + e), 0x41474E54u /* 'AGNT' */};
-    const uint32_t draw = (uint32_t)serial * 8u;
+    // per-step stride 16 = 2 * (at most 8 targets): the SAMPLE / RESET streams read draw + 2 t + {0, 1}, so with a
+    // stride of 8 target t >= 4 at step s would have re-read the draw of target t - 4 at step s + 1
+    const uint32_t draw = (uint32_t)serial * 16u;
     // observe -> process_messages (greedy.py:330-336), and the sets that are broadcast
     uint32_t sent_and = 15u;
     for (int t = 0; t < nt; ++t) {

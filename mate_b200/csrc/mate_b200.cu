@@ -506,6 +506,22 @@ static int invalidate_prepared(MateSim* sim, cudaStream_t stream) {
     return MATE_OK;
 }
 
+__global__ void rewind_episode_kernel(int4* __restrict__ env_b, const uint8_t* __restrict__ env_mask, int num_envs) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e < num_envs && (env_mask == nullptr || env_mask[e] != 0)) env_b[e].w = 0;
+}
+
+extern "C" int mate_b200_seed(MateSim* sim, const uint8_t* env_mask, uint64_t seed, void* stream) {
+    if (!sim) return fail(MATE_EINVAL, "null handle");
+    CUDA_TRY(cudaSetDevice(sim->device));
+    sim->seed = seed;
+    if (int rc = invalidate_prepared(sim, (cudaStream_t)stream)) return rc;
+    rewind_episode_kernel<<<(sim->num_envs + 255) / 256, 256, 0, (cudaStream_t)stream>>>(sim->base.env_b, env_mask, sim->num_envs);
+    cudaError_t err = cudaGetLastError();
+    if (err != cudaSuccess) return fail(MATE_ECUDA, std::string("seed launch: ") + cudaGetErrorString(err));
+    return MATE_OK;
+}
+
 extern "C" int mate_b200_reset(MateSim* sim, const uint8_t* env_mask, uint64_t seed, float* cam_obs,
                                float* tgt_obs, void* stream) {
     if (!sim || !tgt_obs || (sim->cfg.num_cameras > 0 && !cam_obs)) return fail(MATE_EINVAL, "null argument");

@@ -136,6 +136,7 @@ class MultiAgentTracking:  # pylint: disable=too-many-instance-attributes,too-ma
             seed = int(np.random.SeedSequence().entropy % (2 ** 63))
         self._seed = int(seed)
         self._np_random = np.random.RandomState(self._seed % (2 ** 32))
+        self.sim.seed(self._seed % (2 ** 64))   # rewinds the episode counters: seed(s) + reset() is reproducible
         return [self._seed]
 
     def load_config(self, config=None) -> None:
@@ -150,7 +151,7 @@ class MultiAgentTracking:  # pylint: disable=too-many-instance-attributes,too-ma
         """Reset every environment; returns the first joint observation (environment.py:679-834)."""
         if seed is not None:
             self.seed(seed)
-        cam_obs, tgt_obs = self.sim.reset(seed=self._seed)
+        cam_obs, tgt_obs = self.sim.reset()
         self.sim.observe(aux=True)   # refresh the mask attributes for the new episode
         self._needs_reset = False
         return self._format_obs(cam_obs, tgt_obs)

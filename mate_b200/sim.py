@@ -77,6 +77,7 @@ class BatchedSim:
         self._aux_struct = None
         self._zero_cam_act = torch.zeros((self.B, max(self.nc, 1), 2), dtype=torch.float32, device=dev)
         self._obs_ops, self._obs_ops_c, self._affine = [], None, None
+        self._seed = 0
 
     def close(self):
         if getattr(self, 'handle', None) is not None and self.handle:
@@ -171,12 +172,27 @@ class BatchedSim:
         return out
 
     # ------------------------------------------------------------------ API
-    def reset(self, seed=0, env_mask=None):
+    def seed(self, seed, env_mask=None):
+        """``MultiAgentTracking.seed``: new key for the Philox streams, episode counters rewound (mate_b200_seed), so
+        that the following resets are reproducible."""
         mask = None
         if env_mask is not None:
             mask = torch.as_tensor(env_mask, device=self.device).to(torch.uint8).contiguous()
+        self._seed = int(seed)
         with torch.cuda.device(self.device):
-            _check(self.lib, self.lib.mate_b200_reset(self.handle, _dptr(mask), int(seed), _dptr(self.cam_obs),
+            _check(self.lib, self.lib.mate_b200_seed(self.handle, _dptr(mask), self._seed, self._stream()))
+
+    def reset(self, seed=None, env_mask=None):
+        """Reset the environments of ``env_mask`` (default: all).  With an explicit ``seed`` the reset is reproducible
+        (``reset(seed=s)`` twice gives the same states, like the reference); without one it draws the next episodes
+        of the current seed."""
+        mask = None
+        if env_mask is not None:
+            mask = torch.as_tensor(env_mask, device=self.device).to(torch.uint8).contiguous()
+        if seed is not None:
+            self.seed(seed, mask)
+        with torch.cuda.device(self.device):
+            _check(self.lib, self.lib.mate_b200_reset(self.handle, _dptr(mask), self._seed, _dptr(self.cam_obs),
                                                       _dptr(self.tgt_obs), self._stream()))
         self._apply_observation_wrappers()
         return self.cam_obs, self.tgt_obs

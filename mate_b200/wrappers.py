@@ -13,6 +13,8 @@ wrappers costs one extra read + write of the observations, not one per wrapper.
                                    mate_b200.RescaledObservation, mate_b200.DiscreteCamera])
 """
 
+import functools
+
 import numpy as np
 import torch
 
@@ -26,6 +28,21 @@ class Wrapper:
 
     def __init__(self, env):
         self.env = env
+
+    def __init_subclass__(cls, **kwargs):
+        # remember the constructor arguments of the outermost __init__ call: load_config re-runs it
+        super().__init_subclass__(**kwargs)
+        init = cls.__dict__.get('__init__')
+        if init is None:
+            return
+
+        @functools.wraps(init)
+        def remembering_init(self, env, *args, **kw):
+            if type(self) is cls:
+                self.__dict__['_ctor_args'] = (args, kw)
+            init(self, env, *args, **kw)
+
+        cls.__init__ = remembering_init
 
     def __getattr__(self, name):
         if name.startswith('_'):
@@ -46,7 +63,13 @@ class Wrapper:
         return self.env.joint_observation()
 
     def load_config(self, config=None):
+        """Like every wrapper of the reference (``self.env.load_config(config); self.__init__(self.env, ...)``):
+        the wrapped environment is re-initialised first, then this wrapper re-runs its own constructor on it, which
+        re-registers observation transformations, rebuilds action tables and spaces and re-binds opponent agents
+        to the new simulator."""
         self.env.load_config(config=config)
+        args, kw = self.__dict__.get('_ctor_args', ((), {}))
+        self.__init__(self.env, *args, **kw)  # pylint: disable=unnecessary-dunder-call
 
     def close(self):
         return self.env.close()

@@ -287,3 +287,39 @@ def test_agent_draws_do_not_depend_on_the_batch_split():
     for (cam_w, tgt_w), (cam_l, tgt_l), (cam_h, tgt_h) in zip(whole, lo, hi):
         np.testing.assert_array_equal(cam_w, np.concatenate([cam_l, cam_h]))
         np.testing.assert_array_equal(tgt_w, np.concatenate([tgt_l, tgt_h]))
+
+
+@pytest.mark.gpu
+def test_greedy_target_noise_draws_are_distinct_across_steps_and_targets():
+    """The noise sample of target t at step s must be its own Philox draw: with 8 targets the per-step counter stride has
+    to cover 2 * Nt indices (a stride of 8 made target t >= 4 at step s re-read the draw of target t - 4 at step s + 1).
+    The remembered noise (memory[..., 4:6]) equals noise_scale * U(-1, 1) * step_size of the step that drew it."""
+    import mate_b200
+    from mate_b200.config import flatten_config, read_config
+    from mate_b200.sim import BatchedSim
+
+    cfg = flatten_config(read_config('MATE-4v8-9.yaml'))
+    sim = BatchedSim(cfg, 32, device=0)
+    sim.reset(seed=2)
+    agent = mate_b200.GreedyTargetAgent(seed=11, noise_scale=1.0)
+    agent.bind(sim)
+    step_size = cfg['target_step_size'] / sim.get_state()['tgt_capacity']          # [B, Nt]
+    zeros = np.zeros((32, 4, 2), dtype=np.float32)
+    seen = {}
+    prev = None
+    reset = True
+    for s in range(60):
+        act = agent.act(reset_mask=reset).clone()
+        reset = None
+        noise = agent.memory[..., 4:6].cpu().numpy() / step_size[..., None]          # u in (-1, 1)
+        for e in range(32):
+            for t in range(8):
+                if prev is not None and (noise[e, t] == prev[e, t]).all():
+                    continue   # not redrawn in this step
+                key = (e, round(float(noise[e, t, 0]), 12), round(float(noise[e, t, 1]), 12))
+                assert key not in seen, f'env {e}: target {t} at step {s} repeats the draw of {seen[key]}'
+                seen[key] = (t, s)
+        prev = noise
+        sim.step(zeros, act, auto_reset=False)
+    assert len(seen) > 32 * 8 * 3   # the noise is redrawn often enough for the check to mean something
+    sim.close()

@@ -74,3 +74,50 @@ def test_reference_compatible_single_env_mode_replays_a_reference_trace():
     with pytest.raises(AssertionError):
         env.step((np.full((4, 2), np.nan), np.zeros((8, 2))))
     env.close()
+
+
+def test_reset_with_an_explicit_seed_is_reproducible():
+    """reset(seed=s) reseeds (mate/environment.py:700-701): the same seed gives the same episode on a long-lived
+    environment; reset() without a seed continues with independent episodes."""
+    import mate_b200
+
+    env = mate_b200.make('MultiAgentTracking-v0', config='MATE-4v8-9.yaml', num_envs=96)
+    cam_a, tgt_a = (x.clone() for x in env.reset(seed=21))
+    zeros = (torch.zeros((96, 4, 2), device='cuda'), torch.zeros((96, 8, 2), device='cuda'))
+    for _ in range(3):
+        env.step(zeros)
+    cam_n, tgt_n = (x.clone() for x in env.reset())
+    assert not torch.equal(tgt_n, tgt_a)
+    cam_b, tgt_b = (x.clone() for x in env.reset(seed=21))
+    assert torch.equal(cam_a, cam_b) and torch.equal(tgt_a, tgt_b)
+    cam_c, tgt_c = (x.clone() for x in env.reset())       # ... and so is the episode that follows it
+    assert torch.equal(cam_n, cam_c) and torch.equal(tgt_n, tgt_c)
+    env.seed(22)
+    cam_d, tgt_d = (x.clone() for x in env.reset())
+    assert not torch.equal(tgt_d, tgt_a)
+    env.close()
+
+
+def test_wrappers_survive_load_config():
+    """Wrapper.load_config re-runs every wrapper's constructor on the re-initialised environment (like the
+    reference's wrappers): observation transformations, action tables, spaces and opponents follow the new config."""
+    import mate_b200
+
+    stack = [mate_b200.EnhancedObservation, mate_b200.RelativeCoordinates, mate_b200.RescaledObservation,
+             mate_b200.RepeatedRewardIndividualDone, lambda e: mate_b200.DiscreteCamera(e, levels=7),
+             lambda e: mate_b200.MultiCamera(e, target_agent=mate_b200.GreedyTargetAgent(seed=4))]
+    env = mate_b200.make('MultiAgentTracking-v0', config='MATE-4v8-9.yaml', num_envs=48, wrappers=stack)
+    env.reset(seed=1)
+    env.load_config('MATE-4v2-9.yaml')
+    fresh = mate_b200.make('MultiAgentTracking-v0', config='MATE-4v2-9.yaml', num_envs=48, wrappers=stack)
+    assert env.unwrapped.num_targets == 2 and env.levels == 7
+    assert env.unwrapped.sim._obs_ops == fresh.unwrapped.sim._obs_ops and len(env.unwrapped.sim._obs_ops) == 4
+    assert env.observation_space.spaces[0].shape == fresh.observation_space.spaces[0].shape
+    obs_a, obs_b = env.reset(seed=8), fresh.reset(seed=8)
+    assert obs_a.shape == (48, 4, env.unwrapped.sim.dc) and torch.equal(obs_a, obs_b)
+    action = torch.randint(0, 49, (48, 4), device='cuda')
+    for _ in range(5):
+        out_a, out_b = env.step(action), fresh.step(action)
+        assert torch.equal(out_a[0], out_b[0]) and torch.equal(out_a[1], out_b[1])
+    env.close()
+    fresh.close()
