@@ -44,48 +44,95 @@ def measured_peak_gbs():
         return 6650.0, 'fallback (B200_PROFILING.md)'
 
 
-def ncu_traffic_bytes(workload):
-    """dram read+write bytes per launch from the committed ncu --set full capture, if any."""
+def ncu_traffic(workload):
+    """dram read+write bytes per launch from the committed ncu --set full capture, with the hash of the kernel
+    sources the capture was taken on: {'bytes': ..., 'kernel_sources_sha16': ..., 'capture': ...} or {}."""
     path = os.path.join(ROOT, 'profiles', 'traffic.json')
     try:
         with open(path, encoding='UTF-8') as f:
-            return json.load(f).get(workload)
+            entry = json.load(f).get(workload)
     except (OSError, ValueError):
-        return None
+        return {}
+    if isinstance(entry, dict):
+        return entry
+    return {'bytes': entry} if entry else {}
 
 
 class ClockSampler:
-    """Samples nvidia-smi SM clocks and throttle reasons while the timed region runs."""
+    """Samples SM clocks and throttle reasons while the timed region runs.
+
+    NVML is queried in-process (nvidia_ml_py): forking ``nvidia-smi`` from a thread holds the GIL of the thread
+    that launches the kernels, which showed up as +0.1 ms on a 2.9 ms timed region (profiles/r2h_summary.md).
+    ``nvidia-smi`` is only the fallback when the NVML binding is missing."""
 
     QUERY = ('clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,'
              'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
              'clocks_event_reasons.sw_power_cap')
     NAMES = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
 
-    def __init__(self, index):
+    def __init__(self, index, period=0.002):
         self.index = index
+        self.period = period
         self.samples = []
         self.reasons = set()
         self.max_mhz = None
+        self.source = 'nvml'
         self._stop = threading.Event()
         self._thread = threading.Thread(target=self._run, daemon=True)
+        self._nvml = None
+        self._handle = None
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            self._nvml = pynvml
+            # NVML enumerates physical devices; honour CUDA_VISIBLE_DEVICES when it lists indices
+            visible = os.environ.get('CUDA_VISIBLE_DEVICES', '')
+            ids = [x for x in visible.split(',') if x.strip().isdigit()]
+            physical = int(ids[index]) if index < len(ids) else index
+            self._handle = pynvml.nvmlDeviceGetHandleByIndex(physical)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self._handle, pynvml.NVML_CLOCK_SM))
+        except Exception:  # pylint: disable=broad-except
+            self._nvml = None
+            self.source = 'nvidia-smi'
+
+    def _sample_nvml(self):
+        nv = self._nvml
+        self.samples.append(float(nv.nvmlDeviceGetClockInfo(self._handle, nv.NVML_CLOCK_SM)))
+        reasons = nv.nvmlDeviceGetCurrentClocksEventReasons(self._handle) if hasattr(nv, 'nvmlDeviceGetCurrentClocksEventReasons') \
+            else nv.nvmlDeviceGetCurrentClocksThrottleReasons(self._handle)
+        table = {
+            'hw_slowdown': getattr(nv, 'nvmlClocksThrottleReasonHwSlowdown', 0x8),
+            'hw_thermal_slowdown': getattr(nv, 'nvmlClocksThrottleReasonHwThermalSlowdown', 0x40),
+            'sw_thermal_slowdown': getattr(nv, 'nvmlClocksThrottleReasonSwThermalSlowdown', 0x20),
+            'sw_power_cap': getattr(nv, 'nvmlClocksThrottleReasonSwPowerCap', 0x4),
+        }
+        for name, bit in table.items():
+            if reasons & bit:
+                self.reasons.add(name)
+
+    def _sample_smi(self):
+        out = subprocess.run(
+            ['nvidia-smi', f'--id={self.index}', f'--query-gpu={self.QUERY}', '--format=csv,noheader,nounits'],
+            capture_output=True, text=True, timeout=5).stdout.strip().splitlines()
+        if out:
+            parts = [x.strip() for x in out[0].split(',')]
+            self.samples.append(float(parts[0]))
+            self.max_mhz = float(parts[1])
+            for name, value in zip(self.NAMES, parts[2:]):
+                if value.lower().startswith('active'):
+                    self.reasons.add(name)
 
     def _run(self):
         while not self._stop.is_set():
             try:
-                out = subprocess.run(
-                    ['nvidia-smi', f'--id={self.index}', f'--query-gpu={self.QUERY}', '--format=csv,noheader,nounits'],
-                    capture_output=True, text=True, timeout=5).stdout.strip().splitlines()
-                if out:
-                    parts = [x.strip() for x in out[0].split(',')]
-                    self.samples.append(float(parts[0]))
-                    self.max_mhz = float(parts[1])
-                    for name, value in zip(self.NAMES, parts[2:]):
-                        if value.lower().startswith('active'):
-                            self.reasons.add(name)
-            except (OSError, ValueError, subprocess.SubprocessError, IndexError):
+                if self._nvml is not None:
+                    self._sample_nvml()
+                else:
+                    self._sample_smi()
+            except Exception:  # pylint: disable=broad-except
                 pass
-            self._stop.wait(0.02)
+            self._stop.wait(self.period if self._nvml is not None else 0.02)
 
     def __enter__(self):
         self._thread.start()
@@ -101,6 +148,7 @@ class ClockSampler:
             'sm_max_mhz': self.max_mhz,
             'reasons': sorted(self.reasons),
             'samples': len(self.samples),
+            'source': self.source,
         }
 
 
@@ -128,6 +176,7 @@ def cpu_arm(cfg, envs, seconds, threads, seed=0):
     nc, nt = cfg['num_cameras'], cfg['num_targets']
     ref = Oracle(cfg, envs, num_threads=threads)
     ref.reset(seed=seed)
+    ref.set_state({'episode_step': np.random.RandomState(1234).randint(0, cfg['max_episode_steps'] + 1, size=envs).astype(np.int32)})
     rng = np.random.RandomState(seed)
     ring = 4
     cams = [rng.uniform(-1, 1, (envs, nc, 2)) * [cfg['camera_rotation_step'], cfg['camera_zooming_step']] for _ in range(ring)]
@@ -138,7 +187,7 @@ def cpu_arm(cfg, envs, seconds, threads, seed=0):
     t0 = time.perf_counter()
     ref.step(cams[1], tgts[1], seed=seed, auto_reset=True, aux=aux)
     per_step = max(time.perf_counter() - t0, 1e-6)
-    steps = max(3, min(2000, int(seconds / per_step)))
+    steps = max(3, min(2000, int(seconds / per_step)))   # a bounded sample: about `seconds` of CPU work
     t0 = time.perf_counter()
     for k in range(steps):
         ref.step(cams[k % ring], tgts[k % ring], seed=seed, auto_reset=True, aux=aux)
@@ -160,6 +209,8 @@ def run_reference(args, cfg, workload):
     nc, nt = cfg['num_cameras'], cfg['num_targets']
     ref = Oracle(cfg, envs, num_threads=threads)
     ref.reset(seed=0)
+    # the same steady state as the GPU arm: episode clocks staggered uniformly over one episode length
+    ref.set_state({'episode_step': np.random.RandomState(1234).randint(0, cfg['max_episode_steps'] + 1, size=envs).astype(np.int32)})
     rng = np.random.RandomState(0)
     ring = 4
     cams = [rng.uniform(-1, 1, (envs, nc, 2)) * [cfg['camera_rotation_step'], cfg['camera_zooming_step']] for _ in range(ring)]
@@ -177,12 +228,103 @@ def run_reference(args, cfg, workload):
         'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus,
         'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * elapsed / args.steps,
         'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
-        'config': {'workload': workload, 'envs_per_step': envs, 'actions': 'uniform random joint actions', 'auto_reset': True},
+        'config': {'workload': workload, 'envs_per_gpu': envs, 'actions': 'uniform random joint actions (ring of 4 pre-generated batches)', 'auto_reset': True,
+                   'episode_clocks': 'staggered uniformly over one episode: %.1f resets per step' % (envs / (cfg['max_episode_steps'] + 1.0))},
         'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': threads, 'kind': 'port', 'sample': sample},
         'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'agent_steps_per_s': value * (nc + nt),
     }
     print(json.dumps(line), flush=True)
+
+
+def kernel_sources_sha16():
+    """Identifies the kernel build a committed ncu traffic figure belongs to."""
+    import hashlib
+
+    h = hashlib.sha256()
+    for name in ('mate_step.cuh', 'mate_common.cuh'):
+        with open(os.path.join(ROOT, 'mate_b200', 'csrc', name), 'rb') as f:
+            h.update(f.read())
+    return h.hexdigest()[:16]
+
+
+# the other workloads BASELINE.json names (the headline one is --config / --envs): (config, environments per GPU)
+OTHER_CONFIGS = [('MATE-4v2-9.yaml', 65536), ('MATE-4v8-0.yaml', 65536), ('MATE-Navigation.yaml', 65536), ('MATE-8v8-9.yaml', 32768)]
+
+
+def time_workload(config_name, B, steps, warmup, rank, world, local_rank, stagger=True, sample_clocks=False):
+    """W untimed + K timed steps of one workload on this rank's GPU; CUDA events, max over ranks.
+    Returns (record, sim, cfg, (cams, tgts))."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    from mate_b200 import _abi
+    from mate_b200.config import flatten_config, read_config
+    from mate_b200.sim import BatchedSim
+
+    cfg = flatten_config(read_config(config_name))
+    nc, nt, no = cfg['num_cameras'], cfg['num_targets'], cfg['num_obstacles']
+    device = torch.device('cuda', local_rank)
+    sim = BatchedSim(cfg, B, device=local_rank, env_index_base=rank * B)
+    sim.reset(seed=0)
+    # Steady state: under random actions an episode lasts max_episode_steps + 1 steps, so a fresh batch would
+    # never reach a reset inside the timed region.  Stagger the episode clocks uniformly over one episode
+    # length: B / (max_episode_steps + 1) environments finish and are re-initialised in EVERY step.
+    if stagger:
+        steps0 = np.random.RandomState(1234 + rank).randint(0, cfg['max_episode_steps'] + 1, size=B).astype(np.int32)
+        sim.set_state({'episode_step': steps0})
+    ring = 8
+    cams, tgts = make_actions(cfg, B, device, ring, seed=rank)
+    sim.alloc_aux()
+    # per-step info tensors the reference returns in its info dicts: keep only the cheap ones
+    for name, ctype, _, _ in _abi.AUX_FIELDS:
+        if name not in ('coverage', 'num_delivered'):
+            setattr(sim._aux_struct, name, ctype())
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(device)
+
+    for k in range(warmup):
+        sim.step(cams[k % ring], tgts[k % ring], auto_reset=True, aux=True)
+    barrier()
+    launches0 = sim.launch_count
+    start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sampler = ClockSampler(local_rank) if sample_clocks else None
+    if sampler is not None:
+        sampler.__enter__()
+        time.sleep(0.01)   # the sampling thread is up and has taken its first sample before the region starts
+    barrier()
+    # The timed launches are enqueued behind a short device-side delay (1 ms), so that the host is ahead of the
+    # device for the whole region and no launch gap is timed; the events bracket exactly the K step launches.
+    torch.cuda._sleep(2_000_000)   # pylint: disable=protected-access
+    start.record()
+    for k in range(steps):
+        sim.step(cams[k % ring], tgts[k % ring], auto_reset=True, aux=True)
+    stop.record()
+    barrier()
+    if sampler is not None:
+        sampler.__exit__(None, None, None)
+    elapsed_ms = start.elapsed_time(stop)
+    launches = sim.launch_count - launches0
+    if world > 1:
+        t = torch.tensor([elapsed_ms], device=device, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        elapsed_ms = float(t.item())
+    A = algorithmic_bytes(nc, nt, no)
+    peak, peak_src = measured_peak_gbs()
+    ms = elapsed_ms / max(steps, 1)
+    record = {
+        'workload': f'{config_name.replace(".yaml", "")} x {B} envs/GPU', 'ms_per_step': ms,
+        'env_steps_per_s': world * B * steps / (elapsed_ms * 1e-3), 'steps': steps, 'warmup': warmup,
+        'algorithmic_bytes_per_env_step': A, 'achieved_gbs': A * B / (ms * 1e-3) / 1e9,
+        'frac': A * B / (ms * 1e-3) / 1e9 / peak, 'kernel': 'mate_step_kernel2<%d,%d,%d>' % (nc, nt, no),
+        'gpu_launches': launches, 'elapsed_ms': elapsed_ms, 'peak': peak, 'peak_source': peak_src,
+        'clocks': sampler.summary() if sampler is not None else None,
+    }
+    return record, sim, cfg, (cams, tgts)
 
 
 def main():
@@ -193,13 +335,17 @@ def main():
     parser.add_argument('--impl', default='mine', choices=['mine', 'reference'])
     parser.add_argument('--config', default='MATE-4v8-9.yaml')
     parser.add_argument('--envs', type=int, default=65536, help='environments per GPU')
-    parser.add_argument('--cpu-envs', type=int, default=4096, help='environments per CPU-arm step')
+    parser.add_argument('--cpu-envs', type=int, default=0, help='environments per CPU-arm step (0 = the same batch as the GPU arm)')
     parser.add_argument('--cpu-seconds', type=float, default=12.0)
     parser.add_argument('--e2e-steps', type=int, default=10)
+    parser.add_argument('--other-steps', type=int, default=200, help='timed steps of each of the other BASELINE workloads (`configs` key)')
     parser.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
     parser.add_argument('--no-e2e', action='store_true', help='skip the host-buffer e2e leg')
+    parser.add_argument('--no-configs', action='store_true', help='skip the other BASELINE workloads')
     parser.add_argument('--no-stagger', action='store_true', help='do not stagger the episode clocks (no resets in the timed region)')
     args = parser.parse_args()
+    if args.cpu_envs <= 0:
+        args.cpu_envs = args.envs
 
     from mate_b200.config import flatten_config, read_config
 
@@ -213,8 +359,6 @@ def main():
     import torch
     import torch.distributed as dist
 
-    from mate_b200.sim import BatchedSim
-
     world = int(os.environ.get('WORLD_SIZE', '1'))
     rank = int(os.environ.get('RANK', '0'))
     local_rank = int(os.environ.get('LOCAL_RANK', '0'))
@@ -223,52 +367,17 @@ def main():
     torch.cuda.set_device(local_rank)
     device = torch.device('cuda', local_rank)
     B = args.envs
-    sim = BatchedSim(cfg, B, device=local_rank, env_index_base=rank * B)
-    sim.reset(seed=0)
-    # Steady state: under random actions an episode lasts max_episode_steps + 1 steps, so a fresh batch would
-    # never reach a reset inside the timed region.  Stagger the episode clocks uniformly over one episode
-    # length: B / (max_episode_steps + 1) environments finish and are re-initialised in EVERY step.
-    if not args.no_stagger:
-        import numpy as np
-
-        steps0 = np.random.RandomState(1234 + rank).randint(0, cfg['max_episode_steps'] + 1, size=B).astype(np.int32)
-        sim.set_state({'episode_step': steps0})
-    ring = 8
-    cams, tgts = make_actions(cfg, B, device, ring, seed=rank)
-    aux = sim.alloc_aux()
-    # per-step info tensors the reference returns in its info dicts: keep only the cheap ones
-    import ctypes
-
-    from mate_b200 import _abi
-    for name, ctype, _, _ in _abi.AUX_FIELDS:
-        if name not in ('coverage', 'num_delivered'):
-            setattr(sim._aux_struct, name, ctype())
-    del aux
+    warmup = max(args.warmup, 3)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize(device)
 
-    for k in range(max(args.warmup, 3)):
-        sim.step(cams[k % ring], tgts[k % ring], auto_reset=True, aux=True)
-    barrier()
-    launches0 = sim.launch_count
-    start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    with ClockSampler(local_rank) as clocks:
-        barrier()
-        start.record()
-        for k in range(args.steps):
-            sim.step(cams[k % ring], tgts[k % ring], auto_reset=True, aux=True)
-        stop.record()
-        barrier()
-    elapsed_ms = start.elapsed_time(stop)
-    launches = sim.launch_count - launches0
-    if world > 1:
-        t = torch.tensor([elapsed_ms], device=device, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        elapsed_ms = float(t.item())
-    value = world * B * args.steps / (elapsed_ms * 1e-3)
+    head, sim, cfg, (cams, tgts) = time_workload(args.config, B, args.steps, warmup, rank, world, local_rank,
+                                                 stagger=not args.no_stagger, sample_clocks=True)
+    elapsed_ms, launches = head['elapsed_ms'], head['gpu_launches']
+    value = head['env_steps_per_s']
 
     # optional all-reduce of the episode statistics (outside the timed region)
     stats = sim.episode_stats().clone()
@@ -301,38 +410,57 @@ def main():
             'steps': args.e2e_steps,
             'note': 'mate_b200_step_host: pinned host actions in, observations/rewards/done out, chunked over 4 streams',
         }
+        del out, host_cam_act, host_tgt_act
+    sim.close()
+    del sim, cams, tgts
+    torch.cuda.empty_cache()
+
+    # ---- the other workloads BASELINE.json names, same protocol, short runs (device-resident, CUDA events) ----
+    others = []
+    if not args.no_configs:
+        for name, envs in OTHER_CONFIGS:
+            if name == args.config and envs == B:
+                continue
+            rec, osim, _, _ = time_workload(name, envs, args.other_steps, warmup, rank, world, local_rank, stagger=not args.no_stagger)
+            osim.close()
+            del osim
+            torch.cuda.empty_cache()
+            others.append({k: rec[k] for k in ('workload', 'ms_per_step', 'env_steps_per_s', 'steps', 'warmup', 'frac',
+                                               'achieved_gbs', 'algorithmic_bytes_per_env_step', 'kernel')})
 
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
 
-    A = algorithmic_bytes(nc, nt, no)
-    peak, peak_src = measured_peak_gbs()
-    kernel_ms = elapsed_ms / max(args.steps, 1)   # one step kernel per step (the launch count also has the prepare launches)
-    achieved = A * B / (kernel_ms * 1e-3) / 1e9
+    A = head['algorithmic_bytes_per_env_step']
+    traffic = ncu_traffic(args.config.replace('.yaml', ''))
     line = {
         'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
-        'warmup': max(args.warmup, 3), 'ms_per_step': elapsed_ms / args.steps, 'higher_is_better': True,
+        'warmup': warmup, 'ms_per_step': elapsed_ms / args.steps, 'higher_is_better': True,
         'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64 decision state, f32 I/O', 'data': 'synthetic',
         'config': {
             'workload': workload, 'envs_per_gpu': B, 'actions': 'uniform random joint actions (ring of 8 pre-generated batches)',
             'auto_reset': True,
             'episode_clocks': 'all zero' if args.no_stagger else 'staggered uniformly over one episode: %.1f resets per step' % (B / (cfg['max_episode_steps'] + 1.0)),
-            'l2': 'per-step working set (observations %.0f MB + state) exceeds the 126 MB L2' % (B * 4 * (nc * sim.dc + nt * sim.dt) / 1e6),
+            'l2': 'per-step working set (observations %.0f MB + state) exceeds the 126 MB L2' % (B * 4 * (nc * head_dims(cfg)[0] + nt * head_dims(cfg)[1]) / 1e6),
+            'timing': 'CUDA events around the K step launches, enqueued behind a 1 ms device-side delay (no launch gap inside the region)',
         },
         'agent_steps_per_s': value * (nc + nt),
         'gpu_launches': launches,
         'roofline': {
-            'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
-            'traffic': ncu_traffic_bytes(args.config.replace('.yaml', '')),
-            'kernel': 'mate_step_kernel2<%d,%d,%d>' % (nc, nt, no), 'algorithmic_bytes_per_env_step': A,
-            'kernel_ms': kernel_ms, 'peak_source': peak_src,
+            'bound': 'hbm', 'achieved': head['achieved_gbs'], 'peak': head['peak'], 'unit': 'GB/s', 'frac': head['frac'],
+            'traffic': traffic.get('bytes'), 'traffic_kernel_sources_sha16': traffic.get('kernel_sources_sha16'),
+            'traffic_matches_this_build': traffic.get('kernel_sources_sha16') == kernel_sources_sha16() if traffic.get('bytes') else None,
+            'kernel': head['kernel'], 'algorithmic_bytes_per_env_step': A,
+            'kernel_ms': head['ms_per_step'], 'peak_source': head['peak_source'],
         },
-        'clocks': clocks.summary(),
+        'clocks': head['clocks'],
         'episode_stats': {'episodes': stats[0], 'sum_return': stats[1], 'sum_length': stats[2], 'env_steps': stats[5],
                           'resets_from_prepared_state': stats[6], 'resets_in_place': stats[7]},
     }
+    if others:
+        line['configs'] = others
     if e2e is not None:
         line['e2e'] = e2e
     if not args.no_cpu and world == 1:   # the CPU baseline is reported at N = 1 only
@@ -346,6 +474,11 @@ def main():
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def head_dims(cfg):
+    nc, nt, no = cfg['num_cameras'], cfg['num_targets'], cfg['num_obstacles']
+    return 22 + 5 * nt + 4 * no + 7 * nc, 27 + 7 * nc + 4 * no + 5 * nt
 
 
 if __name__ == '__main__':

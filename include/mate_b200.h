@@ -176,7 +176,12 @@ int mate_b200_observe(MateSim* sim, float* cam_obs, float* tgt_obs,
 
 /* Same as mate_b200_step but with HOST buffers (pinned or pageable): actions are copied
  * host->device, results device->host, chunked over internal streams so that copies
- * overlap the kernel.  Returns after the results are in the host buffers. */
+ * overlap the kernel.  Returns after the results are in the host buffers.
+ * Ordering: the chunks run on internal non-blocking streams that first wait for everything
+ * already queued on the legacy default stream (and on blocking streams, e.g. torch's default
+ * stream); a caller that queued reset / step / set_state work on a NON-BLOCKING stream of its
+ * own synchronises that stream before this call.  Auto-resets adopt the prepared next
+ * episodes exactly like mate_b200_step (the refill runs on the side stream). */
 int mate_b200_step_host(MateSim* sim, const float* cam_act, const float* tgt_act,
                         float* cam_obs, float* tgt_obs, float* rewards, uint8_t* done,
                         uint32_t flags);

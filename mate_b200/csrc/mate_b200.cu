@@ -436,7 +436,7 @@ static int launch_range(MateSim* sim, Params p, int begin, int count, cudaStream
     if (p.replay_transmit) p.replay_transmit += (size_t)begin * nc * nt;
     if (p.replay_choice) p.replay_choice += (size_t)begin * nt;
     if (p.ready) p.ready += begin;
-    if (begin != 0 || count != sim->num_envs) p.next = nullptr;   // prepared resets address whole-batch arrays
+    p.next_offset = begin;   // `next` addresses whole-batch arrays
     p.env_index_base += begin;
     p.num_envs = count;
     const int grid = (count + sim->kernel.envs_per_cta - 1) / sim->kernel.envs_per_cta;
@@ -607,6 +607,10 @@ extern "C" int mate_b200_step_host(MateSim* sim, const float* cam_act, const flo
     p.cam_act = sim->h_cam_act; p.tgt_act = sim->h_tgt_act; p.cam_obs = sim->h_cam_obs; p.tgt_obs = sim->h_tgt_obs;
     p.rewards = sim->h_rewards; p.done = sim->h_done;
     fill_aux(p, nullptr, nullptr);
+    // work queued earlier on the legacy default stream (torch's default) or on blocking streams is finished first;
+    // callers that use non-blocking streams of their own synchronise them before this call (include/mate_b200.h)
+    CUDA_TRY(cudaEventRecord(sim->hevents[0], nullptr));
+    for (int i = 0; i < MateSim::kHostStreams; ++i) CUDA_TRY(cudaStreamWaitEvent(sim->hstreams[i], sim->hevents[0], 0));
     int k = 0;
     for (int begin = 0; begin < B; begin += chunk, ++k) {
         const int count = std::min(chunk, B - begin);
@@ -620,6 +624,10 @@ extern "C" int mate_b200_step_host(MateSim* sim, const float* cam_act, const flo
         CUDA_TRY(cudaMemcpyAsync(done + begin, sim->h_done + begin, count, cudaMemcpyDeviceToHost, s));
     }
     for (int i = 0; i < MateSim::kHostStreams; ++i) CUDA_TRY(cudaStreamSynchronize(sim->hstreams[i]));
+    // the prepared episodes are refilled on the side stream like on the device path
+    if ((flags & MATE_STEP_AUTO_RESET) && sim->refill_mode &&
+        (sim->refill_mode == 2 || ++sim->steps_since_refill >= sim->refill_period))
+        return launch_prepare(sim, nullptr);
     return MATE_OK;
 }
 
@@ -782,3 +790,11 @@ extern "C" int mate_b200_episode_stats(MateSim* sim, float* out16, int32_t reset
     if (reset_after) CUDA_TRY(cudaMemsetAsync(sim->base.stats, 0, sizeof(float) * 16, (cudaStream_t)stream));
     return MATE_OK;
 }
+
+#ifdef MATE_DEV_TIMELINE   // development builds only (scratch/timeline.py): per-tile phase time stamps of the last step launch
+extern "C" int mate_b200_debug_timeline(unsigned long long* out, int32_t count) {
+    CUDA_TRY(cudaDeviceSynchronize());
+    CUDA_TRY(cudaMemcpyFromSymbol(out, mate::g_timeline, sizeof(unsigned long long) * (size_t)count));
+    return MATE_OK;
+}
+#endif

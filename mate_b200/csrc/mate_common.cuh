@@ -64,6 +64,7 @@ struct Params {
     const uint8_t* replay_transmit; const int8_t* replay_choice;
     // --- scalars ---
     int num_envs; int bpad; int mode; uint32_t flags;
+    int next_offset;   // a launch over [begin, begin + num_envs) of the batch: env e of the launch is env e + next_offset of the arrays `next` addresses
     long long env_index_base; unsigned long long seed;
     int max_episode_steps; int num_cargoes_per_target; int num_high_capacity; int start_with_cargoes;
     int shuffle; int reward_sparse; int transmittance_is_one;

@@ -22,12 +22,12 @@
 //         draw, conservative occlusion classification, exact polyline only when undecided);
 //       - targets whose step may touch a disc are re-simulated in fp64 after the fast loop;
 //       - targets standing in a warehouse are handled one per lane and iteration.
-//   * OBSERVATIONS: the warp walks over its 32 environments; for each, the lanes are the
-//     ENTITIES (targets, obstacles, cameras): a lane scatters its entity's public state into
-//     the staged rows of the observers whose mask bit is set, rows are zero-filled first, and
-//     the finished 6 KB block leaves the SM as two bulk copies (cp.async.bulk shared->global,
-//     i.e. TMA).  Masks (one or two words per observer row) and the fp32 entity values are
-//     handed from the simulation phase to this phase through shared memory.
+//   * OBSERVATIONS: the warp walks over its 32 environments; for each, the lanes are (observer row,
+//     entity) PAIRS: a pair writes the entity's public state + flag into the staged row if the observer's
+//     mask bit is set and zeros otherwise, every float of the block exactly once, and the finished block
+//     leaves the SM with 16-byte streaming stores (bulk copies are kept behind MATE2_COPYOUT=0; they were
+//     slower here).  Masks (one or two words per observer row) and the fp32 entity values
+//     are handed from the simulation phase to this phase through shared memory.
 #pragma once
 
 #include "mate_common.cuh"
@@ -44,11 +44,28 @@
 #ifndef MATE2_PF_OBS
 #define MATE2_PF_OBS 1         // fp64 obstacle discs -> L2 ahead of the exact paths: 0 = off, 1 = envs that will need them, 2 = all envs
 #endif
+#ifndef MATE2_PF_CARGO
+#define MATE2_PF_CARGO 1       // cargo tables -> L2 at the start of the step (read by _assign_goals, late in the chain)
+#endif
 #ifndef MATE2_MIN_CTAS
 #define MATE2_MIN_CTAS 8       // caps registers at 128 (4 warps per SM sub-partition); 65 536 envs = 2048 warp tiles = 13.8 per SM -> one wave
 #endif
 
 namespace mate {
+
+#ifdef MATE_DEV_TIMELINE   // development builds only: per-tile phase time stamps (scratch/timeline.py)
+__device__ unsigned long long g_timeline[4096 * 8];
+__device__ __forceinline__ void tl_mark(const int env0, const int k) {
+    if ((threadIdx.x & 31) == 0 && (env0 >> 5) < 4096) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+        g_timeline[(env0 >> 5) * 8 + k] = t;
+    }
+}
+#define TL_MARK(k) tl_mark(env0, k)
+#else
+#define TL_MARK(k)
+#endif
 
 template <int NC, int NT, int NO>
 struct Shape2 {
@@ -493,6 +510,7 @@ __device__ __noinline__ void prefetch_prepared(const Params& nx, int e) {
 template <int NC, int NT, int NO, class S>
 __device__ __noinline__ void adopt_prepared_warp(const Params& p, const Params& nx, const int env0, uint32_t adopting,
                                                  float* val, uint32_t* mk) {
+    const int noff = p.next_offset;   // index shift between this launch's (offset) live arrays and the whole-batch prepared arrays
     constexpr int ND = 4 * NC + 2 * NT + 3 * NO, NV = S::VN, NM = S::R * S::MW;
     constexpr int JD = (ND + 31) / 32, JV = (NV + 31) / 32, JM = (NM + 31) / 32, JF = (NO + 31) / 32 > 0 ? (NO + 31) / 32 : 1;
     const int lane = threadIdx.x & 31;
@@ -501,7 +519,7 @@ __device__ __noinline__ void adopt_prepared_warp(const Params& p, const Params& 
         const int src = __ffs(adopting) - 1;
         adopting &= adopting - 1u;
         const int e = env0 + src;
-        auto field = [&](const Params& q, const int k) -> double* {   // k-th double of an environment's state
+        auto field = [&](const Params& q, const int k, const int e) -> double* {   // k-th double of an environment's state
             if (k < 4 * NC) {
                 const int f = k / (NC > 0 ? NC : 1), c = k - f * NC;
                 double* base = f == 0 ? q.cam_x : (f == 1 ? q.cam_y : (f == 2 ? q.cam_phi : q.cam_theta));
@@ -516,15 +534,15 @@ __device__ __noinline__ void adopt_prepared_warp(const Params& p, const Params& 
         };
         double d[JD]; float v[JV]; uint32_t m[JM]; float4 f4[JF];
 #pragma unroll
-        for (int j = 0; j < JD; ++j) { const int k = lane + 32 * j; d[j] = k < ND ? *field(nx, k) : 0.0; }
+        for (int j = 0; j < JD; ++j) { const int k = lane + 32 * j; d[j] = k < ND ? *field(nx, k, e + noff) : 0.0; }
 #pragma unroll
-        for (int j = 0; j < JV; ++j) { const int k = lane + 32 * j; v[j] = k < NV ? nx.vals[(size_t)k * bp + e] : 0.f; }
+        for (int j = 0; j < JV; ++j) { const int k = lane + 32 * j; v[j] = k < NV ? nx.vals[(size_t)k * bp + e + noff] : 0.f; }
 #pragma unroll
-        for (int j = 0; j < JM; ++j) { const int k = lane + 32 * j; m[j] = k < NM ? nx.masks[(size_t)k * bp + e] : 0u; }
+        for (int j = 0; j < JM; ++j) { const int k = lane + 32 * j; m[j] = k < NM ? nx.masks[(size_t)k * bp + e + noff] : 0u; }
 #pragma unroll
-        for (int j = 0; j < JF; ++j) { const int k = lane + 32 * j; f4[j] = k < NO ? nx.obs_f4[(size_t)k * bp + e] : make_float4(0.f, 0.f, 0.f, 0.f); }
+        for (int j = 0; j < JF; ++j) { const int k = lane + 32 * j; f4[j] = k < NO ? nx.obs_f4[(size_t)k * bp + e + noff] : make_float4(0.f, 0.f, 0.f, 0.f); }
 #pragma unroll
-        for (int j = 0; j < JD; ++j) { const int k = lane + 32 * j; if (k < ND) *field(p, k) = d[j]; }
+        for (int j = 0; j < JD; ++j) { const int k = lane + 32 * j; if (k < ND) *field(p, k, e) = d[j]; }
 #pragma unroll
         for (int j = 0; j < JV; ++j) { const int k = lane + 32 * j; if (k < NV) val[src * S::VSTRIDE + k] = v[j]; }
 #pragma unroll
@@ -565,10 +583,9 @@ __device__ __noinline__ void pack_observations(const Params& p, const int env0, 
     const float f_sr = (float)p.tgt_sight_range, f_crad = (float)p.cam_radius;
     const float f_rmax = (float)p.cam_rmax, f_rot = (float)p.cam_rot_step, f_zoom = (float)p.cam_zoom_step;
     const float f_step1 = (float)p.tgt_step_size, f_step2 = (float)(p.tgt_step_size / 2.0);
-    // per-lane constants of the scatter, hoisted out of the environment loop: for every round the offset
-    // of this lane's slot in the staged block (inactive lanes write to a dummy slot behind the block, so
-    // the code is branch-free) and the mask word + bit that decide it
-    constexpr int DUMMY = (S::OFF_Q - S::OFF_STAGE) / 4;   // the pair queues are idle while the rows are packed
+    // per-lane constants of the scatter, hoisted out of the environment loop: for every round the address of
+    // this lane's slot in the staged block, the mask word that decides it, and whether the lane has a pair in
+    // that round at all (its stores are predicated off otherwise)
     constexpr int NRND = RND_T + (NO > 0 ? RND_O : 0) + (NC > 0 ? RND_C : 0);
     const int t_idx = lane % NT, t_sub = lane / NT;
     const int o_idx = lane % NOX, o_sub = lane / NOX;
@@ -576,20 +593,23 @@ __device__ __noinline__ void pack_observations(const Params& p, const int env0, 
     auto row_base = [&](const int row) { return row < NC ? row * DC : S::STAGE_CAM + (row - NC) * DT; };
     float* q_ptr[NRND];   // this lane's slot in the staged block, per round
     int m_idx[NRND];      // and the mask word that decides it
+    uint32_t on_bits = 0; // bit rd: the lane has a pair in round rd
 #pragma unroll
     for (int rd = 0; rd < RND_T; ++rd) {
         const int row = rd * RPR_T + t_sub;
         const bool on = t_sub < RPR_T && row < R;
-        q_ptr[rd] = stage + (on ? row_base(row) + (row < NC ? C_TGT : T_TGT) + 5 * t_idx : DUMMY);
+        q_ptr[rd] = stage + (on ? row_base(row) + (row < NC ? C_TGT : T_TGT) + 5 * t_idx : 0);
         m_idx[rd] = on ? row * MW : 0;
+        on_bits |= (uint32_t)on << rd;
     }
     if (NO > 0) {
 #pragma unroll
         for (int rd = 0; rd < RND_O; ++rd) {
             const int row = rd * RPR_O + o_sub;
             const bool on = o_sub < RPR_O && row < R;
-            q_ptr[RND_T + rd] = stage + (on ? row_base(row) + (row < NC ? C_OBS : T_OBS) + 4 * o_idx : DUMMY);
+            q_ptr[RND_T + rd] = stage + (on ? row_base(row) + (row < NC ? C_OBS : T_OBS) + 4 * o_idx : 0);
             m_idx[RND_T + rd] = on ? row * MW + (MW - 1) : 0;
+            on_bits |= (uint32_t)on << (RND_T + rd);
         }
     }
     if (NC > 0) {
@@ -597,8 +617,9 @@ __device__ __noinline__ void pack_observations(const Params& p, const int env0, 
         for (int rd = 0; rd < RND_C; ++rd) {
             const int row = rd * RPR_C + c_sub;
             const bool on = c_sub < RPR_C && row < R;
-            q_ptr[NRND - RND_C + rd] = stage + (on ? row_base(row) + (row < NC ? C_CAM : T_CAM) + 7 * c_idx : DUMMY);
+            q_ptr[NRND - RND_C + rd] = stage + (on ? row_base(row) + (row < NC ? C_CAM : T_CAM) + 7 * c_idx : 0);
             m_idx[NRND - RND_C + rd] = on ? row * MW : 0;
+            on_bits |= (uint32_t)on << (NRND - RND_C + rd);
         }
     }
     const uint32_t t_bit = bit_tgt(t_idx), o_bit = MW == 1 ? (1u << (16 + o_idx)) : (1u << o_idx), c_bit = bit_cam(c_idx);
@@ -673,21 +694,27 @@ __device__ __noinline__ void pack_observations(const Params& p, const int env0, 
         }
 #pragma unroll
         for (int rd = 0; rd < RND_T; ++rd) {
-            float* q = q_ptr[rd];
-            q[0] = vt[rd][0]; q[1] = vt[rd][1]; q[2] = vt[rd][2]; q[3] = vt[rd][3]; q[4] = vt[rd][4];
+            if ((on_bits >> rd) & 1u) {
+                float* q = q_ptr[rd];
+                q[0] = vt[rd][0]; q[1] = vt[rd][1]; q[2] = vt[rd][2]; q[3] = vt[rd][3]; q[4] = vt[rd][4];
+            }
         }
         if (NO > 0) {
 #pragma unroll
             for (int rd = 0; rd < RND_O; ++rd) {
-                float* q = q_ptr[RND_T + rd];
-                q[0] = vo[rd][0]; q[1] = vo[rd][1]; q[2] = vo[rd][2]; q[3] = vo[rd][3];
+                if ((on_bits >> (RND_T + rd)) & 1u) {
+                    float* q = q_ptr[RND_T + rd];
+                    q[0] = vo[rd][0]; q[1] = vo[rd][1]; q[2] = vo[rd][2]; q[3] = vo[rd][3];
+                }
             }
         }
         if (NC > 0) {
 #pragma unroll
             for (int rd = 0; rd < RND_C; ++rd) {
-                float* q = q_ptr[NRND - RND_C + rd];
-                q[0] = vc[rd][0]; q[1] = vc[rd][1]; q[2] = vc[rd][2]; q[3] = vc[rd][3]; q[4] = vc[rd][4]; q[5] = vc[rd][5]; q[6] = vc[rd][6];
+                if ((on_bits >> (NRND - RND_C + rd)) & 1u) {
+                    float* q = q_ptr[NRND - RND_C + rd];
+                    q[0] = vc[rd][0]; q[1] = vc[rd][1]; q[2] = vc[rd][2]; q[3] = vc[rd][3]; q[4] = vc[rd][4]; q[5] = vc[rd][5]; q[6] = vc[rd][6];
+                }
             }
         }
         if (lane < NT) {
@@ -801,6 +828,7 @@ mate_step_kernel2(const __grid_constant__ Params p) {
     const size_t bp = p.bpad;
     const int mode = p.mode;
 
+    TL_MARK(0);
     // ------------------------------------------------------------------ per-env scalars
     const uint4 ea = p.env_a[er];
     const int4 eb = p.env_b[er];
@@ -821,6 +849,10 @@ mate_step_kernel2(const __grid_constant__ Params p) {
     }
 
     if (MATE2_PF_OBS == 2 && NO > 0 && mode == MODE_STEP) prefetch_discs64<NO>(p, er);
+    if (MATE2_PF_CARGO && mode == MODE_STEP) {   // _assign_goals reads them ~50 us from now, when every other warp is storing rows
+        asm volatile("prefetch.global.L2 [%0];" :: "l"(p.cargo + er));
+        asm volatile("prefetch.global.L2 [%0];" :: "l"(p.cargo + bp + er));
+    }
 
     // ------------------------------------------------------------------ _simulate (environment.py:1326-1354)
     {   // Camera.simulate (entities.py:347-360); the next camera's state is fetched while this one is derived
@@ -921,6 +953,7 @@ mate_step_kernel2(const __grid_constant__ Params p) {
         }
         // exact re-simulation of the targets near a disc: queued and processed 32 at a time, one per lane
         __syncwarp();
+        TL_MARK(1);
         {
             int count = 0;   // warp-uniform
             for (;;) {
@@ -945,6 +978,7 @@ mate_step_kernel2(const __grid_constant__ Params p) {
         }
     }
 
+    TL_MARK(2);
     uint32_t tdone_bits = 0;            // target_dones
     int reward_i = 0, delayed_i = 0;    // this step's rewards (integers)
     int done = 0;
@@ -974,8 +1008,9 @@ mate_step_kernel2(const __grid_constant__ Params p) {
                 unsigned long long cc = 0ull;
                 if (adopted) {   // lane-private part: in flight while the warp copies the rest
                     const Params& nx = *p.next;
-                    c0 = nx.cargo[e]; c1 = nx.cargo[bp + e]; ea2 = nx.env_a[e];
-                    if (NC >= 2) cc = nx.cc_clear[e];
+                    const int en = e + p.next_offset;
+                    c0 = nx.cargo[en]; c1 = nx.cargo[bp + en]; ea2 = nx.env_a[en];
+                    if (NC >= 2) cc = nx.cc_clear[en];
                 }
                 const uint32_t adopting = __ballot_sync(FULL, adopted);
                 if (adopting != 0u) adopt_prepared_warp<NC, NT, NO, S>(p, *p.next, env0, adopting, val, mk);
@@ -1133,6 +1168,7 @@ mate_step_kernel2(const __grid_constant__ Params p) {
             }
         }
         __syncwarp();
+        if (pass == 0) TL_MARK(3);
         // ---- then the stochastic transmittance draw and the occlusion test (entities.py:503-505) ----
         // All pending (camera, target) pairs of the warp's 32 environments go through a queue in shared
         // memory and are evaluated 32 at a time, one pair per lane; pairs the conservative occlusion
@@ -1201,6 +1237,7 @@ mate_step_kernel2(const __grid_constant__ Params p) {
             __syncwarp();
         }
 
+        if (pass == 0) TL_MARK(4);
         // ============================================================== _assign_goals (environment.py:1271-1324)
         const bool step_goals = (pass == 0) && (mode == MODE_STEP);
         const bool goals_active = step_goals || (do_reset && !adopted);
@@ -1382,7 +1419,7 @@ mate_step_kernel2(const __grid_constant__ Params p) {
             }
             auto_reset_needed = env_ok && done && (p.flags & MATE_STEP_AUTO_RESET);
             if (env_ok && !done && p.next != nullptr && (p.flags & MATE_STEP_AUTO_RESET) && episode_step == p.max_episode_steps)
-                prefetch_prepared<NC, NT, NO, S>(*p.next, e);   // the next step ends this episode (time limit)
+                prefetch_prepared<NC, NT, NO, S>(*p.next, e + p.next_offset);   // the next step ends this episode (time limit)
         }
         // aux reflects the step just taken (before any auto-reset) / the observed or reset state
         if (p.has_aux && env_ok && (step_goals || mode != MODE_STEP)) {
@@ -1429,7 +1466,9 @@ mate_step_kernel2(const __grid_constant__ Params p) {
     __syncwarp();
 
     // ------------------------------------------------------------------ joint_observation (environment.py:908-983)
+    TL_MARK(5);
     pack_observations<NC, NT, NO>(p, env0, nvalid, stage, mk, val);
+    TL_MARK(6);
 }
 
 }  // namespace mate

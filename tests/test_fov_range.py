@@ -9,6 +9,14 @@ import golden_util as gu
 from test_oracle_golden import tangent_ray_mask
 
 
+# SURVEY.md section 8f N2 asks for 1e-9.  The sample values are ranges up to 2000 computed in float64 by two
+# different operation orders (NumPy's vectorised polar round trip in the reference, scalar ray casts here):
+# 1e-9 is 2000 x 4 ulp.  Between samples the interpolation weight carries the rounding of the sample ANGLES
+# (angles up to 180 degrees: 1e-11 degrees is 350 ulp), multiplied by the local slope of the polyline.
+SAMPLE_ATOL = 1e-9
+ANGLE_ATOL = 1e-11
+
+
 def _cases():
     for name in gu.reset_names():
         yield name, 'reset'
@@ -61,8 +69,8 @@ def test_fov_range_matches_the_reference_tables(name, kind):
             ok = ~tangent
             ok[-1] = ok[0]
             # duplicates of one angle keep the smaller range (entities.py:455-462): the table has one entry per angle
-            np.testing.assert_allclose(got[ok], rho[ok], rtol=0, atol=1e-7, err_msg=f'{name} state {i} camera {c} samples')
-            assert (got[~ok] >= rho[~ok] - 1e-7).all()
+            np.testing.assert_allclose(got[ok], rho[ok], rtol=0, atol=SAMPLE_ATOL, err_msg=f'{name} state {i} camera {c} samples')
+            assert (got[~ok] >= rho[~ok] - SAMPLE_ATOL).all()
             # (2) between the samples: linear interpolation like scipy's interp1d / np.interp
             q = rng.uniform(-180.0, 180.0, size=4000)
             k = np.searchsorted(phi, q, side='right')        # phi[k-1] <= q < phi[k]
@@ -72,7 +80,7 @@ def test_fov_range_matches_the_reference_tables(name, kind):
             got = sim.fov_range(np.full(len(q), i), np.full(len(q), c), q).cpu().numpy()
             # steep flanks: an error of 1e-12 degrees in a sample angle moves the value by slope * 1e-12
             slope = np.abs((rho[k] - rho[k - 1]) / np.maximum(phi[k] - phi[k - 1], 1e-300))
-            tol = 1e-7 + slope * 1e-9
+            tol = SAMPLE_ATOL + slope * ANGLE_ATOL
             bad = usable & (np.abs(got - want) > tol)
             assert not bad.any(), (name, i, c, q[bad][:5], got[bad][:5], want[bad][:5])
             checked += int(usable.sum())

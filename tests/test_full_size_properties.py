@@ -101,3 +101,68 @@ def test_observe_is_idempotent_and_set_get_state_roundtrip():
     c = other.observe()
     # preserved data + private state do not depend on the (seed-keyed) transmittance draws
     assert torch.equal(a[1][:, :, :27], c[1][:, :, :27])
+
+
+@pytest.mark.parametrize('preset,B', [('MATE-4v8-9.yaml', B_FULL), ('MATE-4v8-0.yaml', B_FULL), ('MATE-Navigation.yaml', B_FULL),
+                                      ('MATE-8v8-9.yaml', B_FULL // 2)])
+def test_values_against_the_oracle_at_full_size(preset, B, monkeypatch):
+    """CUDA against the float64 C oracle at BASELINE.json's sizes, in the regime bench.py times: episode clocks
+    staggered over one episode (time-limit resets in every step), prepared episodes refilled asynchronously on the side
+    stream (a short period, so that auto-resets both adopt prepared episodes and run in place).  Masks, flags, rewards,
+    done, cargo counts bit-exact; observations to 1e-5."""
+    from mate_b200.config import flatten_config, read_config
+    from mate_b200.sim import BatchedSim
+    from oracle.oracle import Oracle
+
+    steps, horizon = 64, 40
+    cfg = flatten_config(read_config(preset, max_episode_steps=horizon))
+    nc, nt = cfg['num_cameras'], cfg['num_targets']
+    monkeypatch.setenv('MATE_B200_REFILL', '8')
+    sim = BatchedSim(cfg, B, device=0)
+    ref = Oracle(cfg, B, num_threads=16)
+    seed = 77
+    sim.reset(seed=seed)
+    ref.reset(seed=seed)
+    stagger = np.random.RandomState(3).randint(0, horizon + 1, size=B).astype(np.int32)
+    sim.set_state({'episode_step': stagger})
+    ref.set_state({'episode_step': stagger})
+    aux, raux = sim.alloc_aux(), ref.alloc_aux()
+    rng = np.random.RandomState(8)
+    wh = 925.0 * np.array([[1.0, 1.0], [-1.0, 1.0], [-1.0, -1.0], [1.0, -1.0]])
+
+    def close(got, want, what):   # compared on the device: 10^8 floats per step
+        want = torch.from_numpy(want).cuda()
+        bad = (got - want).abs() > 1e-5 + 1e-5 * want.abs()
+        assert not bool(bad.any()), (what, int(bad.sum()))
+
+    n_done = 0
+    for k in range(steps):
+        cam_act = (rng.uniform(-1, 1, (B, nc, 2)) * [cfg['camera_rotation_step'], cfg['camera_zooming_step']]).astype(np.float32)
+        tgt_act = (rng.uniform(-1, 1, (B, nt, 2)) * cfg['target_step_size']).astype(np.float32)
+        if k % 2 == 0:   # every other step the targets head for their goal warehouse, so that cargo moves
+            st = ref.get_state()
+            goal = st['tgt_goal']
+            direction = wh[np.where(goal >= 0, goal, 0)] - st['tgt_xy']
+            direction /= np.maximum(np.linalg.norm(direction, axis=-1, keepdims=True), 1e-9)
+            tgt_act = np.where((goal >= 0)[..., None], cfg['target_step_size'] * direction + 0.3 * tgt_act, tgt_act).astype(np.float32)
+        (cam, tgt), rew, done = sim.step(torch.from_numpy(cam_act).cuda(), torch.from_numpy(tgt_act).cuda(), auto_reset=True, aux=True)
+        (rcam, rtgt), rrew, rdone = ref.step(cam_act, tgt_act, seed=seed, auto_reset=True, aux=raux)
+        ctx = f'{preset} step {k}'
+        for key in ('mask_ct', 'mask_cc', 'mask_co', 'mask_tc', 'mask_to', 'mask_tt', 'target_dones', 'is_colliding',
+                    'num_delivered', 'episode_step'):
+            assert torch.equal(aux[key].cpu(), torch.from_numpy(raux[key])), (ctx, key)
+        assert torch.equal(rew.cpu(), torch.from_numpy(rrew)) and torch.equal(done.cpu(), torch.from_numpy(rdone)), ctx
+        if nc:
+            close(cam, rcam, ctx + ' camera observations')
+        close(tgt, rtgt, ctx + ' target observations')
+        n_done += int(rdone.sum())
+    assert n_done >= B   # every environment ended an episode at least once
+    s_cuda, s_ref = sim.get_state(), ref.get_state()
+    for key in s_ref:
+        if s_ref[key].dtype.kind == 'f':
+            np.testing.assert_allclose(s_cuda[key], s_ref[key], rtol=0, atol=1e-8, err_msg=key)
+        else:
+            assert (s_cuda[key] == s_ref[key]).all(), key
+    stats = sim.episode_stats().cpu().numpy()
+    assert stats[6] > 0 and stats[6] + stats[7] == stats[0] == n_done, stats[:8]
+    sim.close()
