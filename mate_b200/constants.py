@@ -98,3 +98,64 @@ def camera_observation_slices_of(num_cameras, num_targets, num_obstacles):
 def target_observation_slices_of(num_cameras, num_targets, num_obstacles):
     return _slices(target_observation_indices_of(num_cameras, num_targets, num_obstacles),
                    CAMERA_STATE_DIM_PUBLIC, TARGET_STATE_DIM_PUBLIC)
+
+
+CAMERA_DEFAULT_ACTION = np.asarray([0.0, 0.0], dtype=np.float64)
+TARGET_DEFAULT_ACTION = np.asarray([0.0, 0.0], dtype=np.float64)
+
+
+def _team_index(team):
+    """0 = camera team, 1 = target team; accepts the reference's ``Team`` enum (``.value``), an int or a name."""
+    if isinstance(team, str):
+        return {'camera': 0, 'target': 1}[team.lower()]
+    return int(getattr(team, 'value', team))
+
+
+def observation_space_of(team, num_cameras, num_targets, num_obstacles):
+    """mate/constants.py:257-265."""
+    return (camera_observation_space_of, target_observation_space_of)[_team_index(team)](num_cameras, num_targets, num_obstacles)
+
+
+def observation_indices_of(team, num_cameras, num_targets, num_obstacles):
+    """mate/constants.py:304-312."""
+    return (camera_observation_indices_of, target_observation_indices_of)[_team_index(team)](num_cameras, num_targets, num_obstacles)
+
+
+def observation_slices_of(team, num_cameras, num_targets, num_obstacles):
+    """mate/constants.py:361-369."""
+    return (camera_observation_slices_of, target_observation_slices_of)[_team_index(team)](num_cameras, num_targets, num_obstacles)
+
+
+def _coordinate_mask(private_dim, first_dim, first_count, num_obstacles, last_dim, last_count):
+    preserved = np.zeros(PRESERVED_DIM, dtype=bool)
+    preserved[-1 - 2 * NUM_WAREHOUSES:-1] = True           # the warehouse locations
+    own = np.zeros(private_dim, dtype=bool)                # the agent's own state is not a relative coordinate
+
+    def flagged(dim, count):                               # first two entries (x, y) of every flagged entity block
+        block = np.zeros(dim + 1, dtype=bool)
+        block[:2] = True
+        return np.tile(block, count)
+
+    return np.concatenate([preserved, own, flagged(first_dim, first_count), flagged(OBSTACLE_STATE_DIM, num_obstacles),
+                           flagged(last_dim, last_count)])
+
+
+@functools.lru_cache(maxsize=None)
+def camera_coordinate_mask_of(num_cameras, num_targets, num_obstacles):
+    """True where an entry of a camera's observation is a coordinate of another entity or of a warehouse
+    (mate/constants.py:372-398)."""
+    return _coordinate_mask(CAMERA_STATE_DIM_PRIVATE, TARGET_STATE_DIM_PUBLIC, num_targets, num_obstacles,
+                            CAMERA_STATE_DIM_PUBLIC, num_cameras)
+
+
+@functools.lru_cache(maxsize=None)
+def target_coordinate_mask_of(num_cameras, num_targets, num_obstacles):
+    """True where an entry of a target's observation is a coordinate of another entity or of a warehouse
+    (mate/constants.py:401-427)."""
+    return _coordinate_mask(TARGET_STATE_DIM_PRIVATE, CAMERA_STATE_DIM_PUBLIC, num_cameras, num_obstacles,
+                            TARGET_STATE_DIM_PUBLIC, num_targets)
+
+
+def coordinate_mask_of(team, num_cameras, num_targets, num_obstacles):
+    """mate/constants.py:430-440."""
+    return (camera_coordinate_mask_of, target_coordinate_mask_of)[_team_index(team)](num_cameras, num_targets, num_obstacles)

@@ -511,6 +511,7 @@ template <int NC, int NT, int NO, class S>
 __device__ __noinline__ void adopt_prepared_warp(const Params& p, const Params& nx, const int env0, uint32_t adopting,
                                                  float* val, uint32_t* mk) {
     const int noff = p.next_offset;   // index shift between this launch's (offset) live arrays and the whole-batch prepared arrays
+    __syncwarp();   // the lanes are about to overwrite shared-memory rows their owners read and wrote a moment ago (racecheck)
     constexpr int ND = 4 * NC + 2 * NT + 3 * NO, NV = S::VN, NM = S::R * S::MW;
     constexpr int JD = (ND + 31) / 32, JV = (NV + 31) / 32, JM = (NM + 31) / 32, JF = (NO + 31) / 32 > 0 ? (NO + 31) / 32 : 1;
     const int lane = threadIdx.x & 31;

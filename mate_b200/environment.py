@@ -29,17 +29,38 @@ import torch
 from mate_b200 import constants as consts
 from mate_b200 import spaces
 from mate_b200.config import DEFAULT_CONFIG_FILE, flatten_config, read_config
+from mate_b200.entities import CameraView, ObstacleView, TargetView
 from mate_b200.sim import BatchedSim
 
-__all__ = ['MultiAgentTracking', 'read_config', 'DEFAULT_CONFIG_FILE']
+__all__ = ['MultiAgentTracking', 'EnvMeta', 'read_config', 'DEFAULT_CONFIG_FILE']
 
 
-class MultiAgentTracking:  # pylint: disable=too-many-instance-attributes,too-many-public-methods
+class EnvMeta(type):
+    """``isinstance(wrapped_env, MultiAgentTracking)`` sees through wrappers, like the reference's metaclass
+    (mate/environment.py:272-284): any object that reaches a ``MultiAgentTracking`` through a chain of ``.env``
+    attributes (``mate_b200.wrappers.Wrapper``, ``gym.Wrapper``) is an instance."""
+
+    def __instancecheck__(cls, instance):
+        if super().__instancecheck__(instance):
+            return True
+        seen = 0
+        while hasattr(type(instance), 'env') or 'env' in getattr(instance, '__dict__', {}):
+            instance = instance.env
+            seen += 1
+            if super().__instancecheck__(instance):
+                return True
+            if seen > 64:
+                break
+        return False
+
+
+class MultiAgentTracking(metaclass=EnvMeta):  # pylint: disable=too-many-instance-attributes,too-many-public-methods
     """Batched Multi-Agent Tracking Environment (cameras vs. cargo-hauling targets)."""
 
     metadata = {'render.modes': []}
     DEFAULT_CONFIG_FILE = DEFAULT_CONFIG_FILE
     spec = None
+    _sim_class = BatchedSim   # the simulator behind the class (tests substitute a recorded one to exercise this host layer without a GPU)
 
     def __init__(self, config: Optional[Union[Dict[str, Any], str]] = None, num_envs: Optional[int] = None,
                  device: Union[int, str, torch.device] = 0, env_index_base: int = 0, **kwargs) -> None:
@@ -50,7 +71,7 @@ class MultiAgentTracking:  # pylint: disable=too-many-instance-attributes,too-ma
         self.flat_config = flatten_config(self.config)
         self.batched = num_envs is not None
         self.num_envs = int(num_envs) if self.batched else 1
-        self.sim = BatchedSim(self.flat_config, self.num_envs, device=device, env_index_base=env_index_base)
+        self.sim = self._sim_class(self.flat_config, self.num_envs, device=device, env_index_base=env_index_base)
         self.device = self.sim.device
         nc, nt, no = self.num_cameras, self.num_targets, self.num_obstacles
 
@@ -87,6 +108,13 @@ class MultiAgentTracking:  # pylint: disable=too-many-instance-attributes,too-ma
         self._terms = None
         self.want_soft_coverage = False   # set by an auxiliary-reward wrapper that uses 'soft_coverage_score'
         self._aux = self.sim.alloc_aux()
+        self._snapshot_cache = (None, None)
+        self._state_serial = 0
+        self.cameras = [CameraView(self, c) for c in range(nc)]       # mate/environment.py:392-398
+        self.targets = [TargetView(self, t) for t in range(nt)]
+        self.obstacles = [ObstacleView(self, o) for o in range(no)]
+        self.cameras_ordered, self.targets_ordered, self.obstacles_ordered = self.cameras, self.targets, self.obstacles
+        self.preserved_data = np.concatenate([[nc, nt, no, 0.0], consts.WAREHOUSES.ravel(), [consts.WAREHOUSE_RADIUS]]).astype(np.float64)
         self.viewer = None
 
     # ------------------------------------------------------------------ configuration properties
@@ -154,6 +182,7 @@ class MultiAgentTracking:  # pylint: disable=too-many-instance-attributes,too-ma
         cam_obs, tgt_obs = self.sim.reset()
         self.sim.observe(aux=True)   # refresh the mask attributes for the new episode
         self._needs_reset = False
+        self._state_serial += 1
         return self._format_obs(cam_obs, tgt_obs)
 
     def _check_actions(self, action):
@@ -182,6 +211,7 @@ class MultiAgentTracking:  # pylint: disable=too-many-instance-attributes,too-ma
         replay = self.__dict__.pop('replay_next', None)
         (cam_obs, tgt_obs), rewards, done = self.sim.step(cam, tgt, auto_reset=self.batched, aux=True, replay=replay)
         self._step_serial += 1
+        self._state_serial += 1
         if self.batched:
             aux = self._aux
             common = {
@@ -235,6 +265,7 @@ class MultiAgentTracking:  # pylint: disable=too-many-instance-attributes,too-ma
         self.sim.set_state(arrays)
         self.sim.observe(aux=True)
         self._needs_reset = False
+        self._state_serial += 1
 
     def state(self) -> np.ndarray:
         """The global state vector (environment.py:894-906), ``[B, D]`` float64 (``[D]`` in
@@ -264,27 +295,81 @@ class MultiAgentTracking:  # pylint: disable=too-many-instance-attributes,too-ma
                               s['tgt_bounty'], s['remaining'].reshape(B, 16)], axis=-1).astype(np.float64)
         return self._maybe_single(out)
 
-    # view masks / cargo attributes read by wrappers (environment.py:475-519)
-    def _mask(self, key):
-        return self._maybe_single(self._aux[key].bool())
+    # ------------------------------------------------------------------ attributes wrappers and agents read
+    def _snapshot(self):
+        """Host copy of the simulator state, taken once per step / reset / set_state on first use: the entity
+        views and the cargo attributes below all read the same snapshot."""
+        serial, snap = self._snapshot_cache
+        if serial != self._state_serial:
+            snap = self.sim.get_state()
+            self._snapshot_cache = (self._state_serial, snap)
+        return snap
 
-    camera_target_view_mask = property(lambda self: self._mask('mask_ct'))
-    camera_camera_view_mask = property(lambda self: self._mask('mask_cc'))
-    camera_obstacle_view_mask = property(lambda self: self._mask('mask_co'))
-    target_camera_view_mask = property(lambda self: self._mask('mask_tc'))
-    target_obstacle_view_mask = property(lambda self: self._mask('mask_to'))
-    target_target_view_mask = property(lambda self: self._mask('mask_tt'))
-    target_dones = property(lambda self: self._mask('target_dones'))
-    target_warehouse_distances = property(lambda self: self._maybe_single(self._aux['warehouse_dist']))
-    coverage_rate = property(lambda self: self._maybe_single(self._aux['coverage'][:, 0]))
-    real_coverage_rate = property(lambda self: self._maybe_single(self._aux['coverage'][:, 1]))
-    mean_transport_rate = property(lambda self: self._maybe_single(self._aux['coverage'][:, 2]))
-    num_delivered_cargoes = property(lambda self: self._maybe_single(self._aux['num_delivered']))
-    episode_step = property(lambda self: self._maybe_single(self._aux['episode_step']))
-    remaining_cargoes = property(lambda self: self._maybe_single(self.sim.get_state()['remaining']))
-    awaiting_cargo_counts = property(lambda self: self._maybe_single(self.sim.get_state()['awaiting']))
-    target_goals = property(lambda self: self._maybe_single(self.sim.get_state()['tgt_goal']))
-    obstacle_states = property(lambda self: self._maybe_single(self.sim.get_state()['obs_xyr']))
+    def _aux_numpy(self, key):
+        return self._aux[key].cpu().numpy()
+
+    def _host(self, tensor, dtype=None):
+        """A per-step device tensor in the type of the calling convention: the tensor itself (``[B, ...]``) in
+        batched mode, a NumPy array without the batch dimension in reference-compatible mode."""
+        if self.batched:
+            return tensor if dtype is not bool else tensor.bool()
+        out = tensor[0].cpu().numpy()
+        return out.astype(dtype) if dtype is not None else out
+
+    # view masks (mate/environment.py:475-495)
+    camera_target_view_mask = property(lambda self: self._host(self._aux['mask_ct'], bool))
+    camera_camera_view_mask = property(lambda self: self._host(self._aux['mask_cc'], bool))
+    camera_obstacle_view_mask = property(lambda self: self._host(self._aux['mask_co'], bool))
+    target_camera_view_mask = property(lambda self: self._host(self._aux['mask_tc'], bool))
+    target_obstacle_view_mask = property(lambda self: self._host(self._aux['mask_to'], bool))
+    target_target_view_mask = property(lambda self: self._host(self._aux['mask_tt'], bool))
+    target_dones = property(lambda self: self._host(self._aux['target_dones'], bool))
+    target_warehouse_distances = property(lambda self: self._host(self._aux['warehouse_dist'], np.float64))
+
+    @property
+    def tracked_bits(self):
+        """camera_target_view_mask.any(axis=0) (mate/environment.py:1387)."""
+        mask = self.camera_target_view_mask
+        return mask.any(dim=1) if self.batched else mask.any(axis=0)
+
+    def _scalar(self, tensor, cast):
+        return tensor if self.batched else cast(tensor[0].item())
+
+    coverage_rate = property(lambda self: self._scalar(self._aux['coverage'][:, 0], float))
+    real_coverage_rate = property(lambda self: self._scalar(self._aux['coverage'][:, 1], float))
+    mean_transport_rate = property(lambda self: self._scalar(self._aux['coverage'][:, 2], float))
+    num_delivered_cargoes = property(lambda self: self._scalar(self._aux['num_delivered'], int))
+    episode_step = property(lambda self: self._scalar(self._aux['episode_step'], int))
+    # cargo tables and per-target integers (mate/environment.py:503-519): from the host snapshot
+    remaining_cargoes = property(lambda self: self._maybe_single(self._snapshot()['remaining'].astype(np.int64)))
+    awaiting_cargo_counts = property(lambda self: self._maybe_single(self._snapshot()['awaiting'].astype(np.int64)))
+    target_goals = property(lambda self: self._maybe_single(self._snapshot()['tgt_goal'].astype(np.int64)))
+    target_capacities = property(lambda self: self._maybe_single(self._snapshot()['tgt_capacity'].astype(np.int64)))
+    target_team_episode_reward = property(lambda self: self._maybe_single(self._snapshot()['episode_reward'][:, 0]))
+    delayed_target_team_episode_reward = property(lambda self: self._maybe_single(self._snapshot()['episode_reward'][:, 1]))
+    obstacle_states = property(lambda self: self._maybe_single(self._snapshot()['obs_xyr'].astype(np.float64)))
+
+    @property
+    def target_goal_bits(self):
+        """[Nt, 4]: the cargo weight at the index of each target's goal warehouse (mate/environment.py:1305-1309)."""
+        snap = self._snapshot()
+        bits = (np.arange(consts.NUM_WAREHOUSES) == snap['tgt_goal'][..., None]) * snap['tgt_weight'][..., None]
+        return self._maybe_single(bits.astype(np.int64))
+
+    @property
+    def obstacle_states_flagged(self):
+        """Obstacle states with a trailing 1 (mate/environment.py:471, 747-750)."""
+        states = self._snapshot()['obs_xyr'].astype(np.float64)
+        return self._maybe_single(np.concatenate([states, np.ones(states.shape[:-1] + (1,))], axis=-1))
+
+    @property
+    def camera_obstacle_observations(self):
+        """Per camera, the flagged obstacle states masked by its obstacle set, flattened (mate/environment.py:757-764)."""
+        flagged = self._snapshot()['obs_xyr'].astype(np.float64)
+        flagged = np.concatenate([flagged, np.ones(flagged.shape[:-1] + (1,))], axis=-1)            # [B, No, 4]
+        mask = self._aux_numpy('mask_co').astype(bool)                                              # [B, Nc, No]
+        out = np.where(mask[..., None], flagged[:, None], 0.0).reshape(self.num_envs, self.num_cameras, -1)
+        return self._maybe_single(out)
 
     target_goals_of_last_step = property(lambda self: self._maybe_single(self._aux['tgt_goal']))
 

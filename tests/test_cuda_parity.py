@@ -274,7 +274,7 @@ def test_async_refill_equals_resets_in_place(monkeypatch):
     cfg = flatten_config(read_config('MATE-4v8-9.yaml', max_episode_steps=5))
     nc, nt = cfg['num_cameras'], cfg['num_targets']
     B = 8192
-    monkeypatch.setenv('MATE_B200_REFILL', '3')     # side stream, every 3 steps: episodes of 6 steps often find a stale tag
+    monkeypatch.setenv('MATE_B200_REFILL', '16')    # side stream, every 16 steps: an episode of 6 steps that follows an adopted one finds a stale tag
     a = _sim(cfg, B)
     monkeypatch.setenv('MATE_B200_REFILL', '0')
     b = _sim(cfg, B)
