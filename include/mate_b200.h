@@ -218,6 +218,13 @@ int mate_b200_transform_observations(MateSim* sim, float* cam_obs, float* tgt_ob
                                      int32_t num_ops, const float* cam_affine, const float* tgt_affine,
                                      void* stream);
 
+/* The same wrappers REGISTERED with the simulator: from now on every mate_b200_reset / _step / _step_host / _observe
+ * applies them to an environment's rows while they are still in shared memory (the packer of the step kernel), i.e.
+ * without the extra read + write pass over the observation tensors mate_b200_transform_observations costs.
+ * num_ops = 0 unregisters.  The affine tables must stay valid until they are replaced. */
+int mate_b200_set_observation_ops(MateSim* sim, const int32_t* ops, int32_t num_ops,
+                                  const float* cam_affine, const float* tgt_affine);
+
 /* Camera.sight_range_at (mate/entities.py:507-511): value of the sampled field-of-view polyline of camera
  * camera[i] of environment env[i] at bearing angle_deg[i] (any angle; normalised like the reference), for n
  * queries.  The polyline (Camera.add_obstacles, entities.py:362-479) is never materialised: this evaluates the

@@ -185,6 +185,7 @@ def load_library():
     lib.mate_b200_launch_count.argtypes = [void_p]
     lib.mate_b200_launch_count.restype = ctypes.c_int64
     lib.mate_b200_transform_observations.argtypes = [void_p, void_p, void_p, c_int32_p, ctypes.c_int32, void_p, void_p, void_p]
+    lib.mate_b200_set_observation_ops.argtypes = [void_p, c_int32_p, ctypes.c_int32, void_p, void_p]
     lib.mate_b200_decode_actions.argtypes = [void_p, void_p, ctypes.c_int32, void_p, ctypes.c_int64, void_p]
     lib.mate_b200_fov_range.argtypes = [void_p, void_p, void_p, void_p, void_p, ctypes.c_int64, void_p]
     lib.mate_b200_auxiliary_terms.argtypes = [void_p, ctypes.POINTER(MateStepAux), void_p, void_p, void_p, void_p, void_p]
@@ -194,7 +195,7 @@ def load_library():
                                                     ctypes.POINTER(MateCameraAgentReplay), void_p, void_p]
     lib.mate_b200_soft_coverage.argtypes = [void_p, void_p, void_p, void_p, void_p]
     for name in ('create', 'destroy', 'obs_dims', 'reset', 'seed', 'step', 'observe', 'step_host',
-                 'get_state', 'set_state', 'episode_stats', 'transform_observations', 'decode_actions', 'auxiliary_terms', 'fov_range', 'soft_coverage', 'greedy_target_actions', 'greedy_camera_actions'):
+                 'get_state', 'set_state', 'episode_stats', 'transform_observations', 'set_observation_ops', 'decode_actions', 'auxiliary_terms', 'fov_range', 'soft_coverage', 'greedy_target_actions', 'greedy_camera_actions'):
         getattr(lib, 'mate_b200_' + name).restype = ctypes.c_int
     _LIB = lib
     return lib
@@ -204,7 +205,7 @@ EXPORTED_SYMBOLS = [
     'mate_b200_last_error', 'mate_b200_abi_version', 'mate_b200_create', 'mate_b200_destroy',
     'mate_b200_obs_dims', 'mate_b200_reset', 'mate_b200_seed', 'mate_b200_step', 'mate_b200_observe',
     'mate_b200_step_host', 'mate_b200_get_state', 'mate_b200_set_state',
-    'mate_b200_episode_stats', 'mate_b200_launch_count', 'mate_b200_transform_observations',
+    'mate_b200_episode_stats', 'mate_b200_launch_count', 'mate_b200_transform_observations', 'mate_b200_set_observation_ops',
     'mate_b200_decode_actions', 'mate_b200_auxiliary_terms', 'mate_b200_fov_range', 'mate_b200_soft_coverage', 'mate_b200_greedy_target_actions', 'mate_b200_greedy_camera_actions',
 ]
 

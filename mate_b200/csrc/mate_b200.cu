@@ -54,7 +54,9 @@ struct KernelInfo {
 template <int NC, int NT, int NO>
 static void launch_shape2(const Params& p, int grid, cudaStream_t stream) {
     using S = Shape2<NC, NT, NO>;
-    mate_step_kernel2<NC, NT, NO><<<grid, S::WARPS * 32, S::SMEM_BYTES, stream>>>(p);
+    Params q = p;
+    q.warp_stride = S::WARP_BYTES + (p.obs_ops.n > 0 ? S::OPS_BYTES : 0);   // scratch of the folded observation wrappers
+    mate_step_kernel2<NC, NT, NO><<<grid, S::WARPS * 32, S::WARPS * q.warp_stride, stream>>>(q);
 }
 template <int NC, int NT, int NO>
 static void launch_fov_shape(const Params& p, const int32_t* env, const int32_t* camera, const double* angle, double* out,
@@ -69,7 +71,8 @@ static void launch_soft_shape(const Params& p, const uint8_t* mask_ct, const uin
 template <int NC, int NT, int NO>
 static cudaError_t prepare_shape2() {
     using S = Shape2<NC, NT, NO>;
-    return cudaFuncSetAttribute(mate_step_kernel2<NC, NT, NO>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::SMEM_BYTES);
+    return cudaFuncSetAttribute(mate_step_kernel2<NC, NT, NO>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                S::SMEM_BYTES + S::WARPS * S::OPS_BYTES);
 }
 
 template <int NC, int NT, int NO>
@@ -342,6 +345,63 @@ extern "C" int mate_b200_transform_observations(MateSim* sim, float* cam_obs, fl
     sim->launches += 1;
     cudaError_t err = cudaGetLastError();
     if (err != cudaSuccess) return fail(MATE_ECUDA, std::string("wrapper kernel launch: ") + cudaGetErrorString(err));
+    return MATE_OK;
+}
+
+extern "C" int mate_b200_set_observation_ops(MateSim* sim, const int32_t* ops, int32_t num_ops, const float* cam_affine,
+                                             const float* tgt_affine) {
+    if (!sim || (num_ops > 0 && !ops)) return fail(MATE_EINVAL, "null argument");
+    if (num_ops < 0 || num_ops > MATE_MAX_OBS_OPS) return fail(MATE_EINVAL, "too many observation wrappers (MATE_MAX_OBS_OPS)");
+    ObsOps o{};
+    o.n = num_ops;
+    for (int i = 0; i < num_ops; ++i) {
+        if (ops[i] < MATE_OBS_ENHANCED_CAMERA || ops[i] > MATE_OBS_RESCALED) return fail(MATE_EINVAL, "unknown observation wrapper code");
+        if (ops[i] == MATE_OBS_RESCALED && (!tgt_affine || (sim->cfg.num_cameras > 0 && !cam_affine)))
+            return fail(MATE_EINVAL, "MATE_OBS_RESCALED needs the affine tables");
+        o.op[i] = ops[i];
+    }
+    // canonical stacks -- (Enhanced | Shared)* Relative? Rescaled? -- are applied while the rows are composed (FoldOps)
+    FoldOps f{};
+    int k = 0;
+    while (k < num_ops && ops[k] >= MATE_OBS_ENHANCED_CAMERA && ops[k] <= MATE_OBS_SHARED_TARGET) f.mask_op[f.n_mask++] = ops[k++];
+    if (k < num_ops && ops[k] == MATE_OBS_RELATIVE) { f.relative = 1; ++k; }
+    if (k < num_ops && ops[k] == MATE_OBS_RESCALED) { f.rescaled = 1; ++k; }
+    f.fast = (num_ops > 0 && k == num_ops) ? 1 : 0;
+    if (f.fast && f.rescaled) {
+        CUDA_TRY(cudaSetDevice(sim->device));
+        const int nc = sim->cfg.num_cameras, nt = sim->cfg.num_targets, no = sim->cfg.num_obstacles;
+        const int dc = sim->kernel.dc, dt = sim->kernel.dt;
+        std::vector<float> cam((size_t)2 * std::max(dc, 1), 0.f), tgt((size_t)2 * dt, 0.f);
+        if (nc) CUDA_TRY(cudaMemcpy(cam.data(), cam_affine, sizeof(float) * 2 * dc, cudaMemcpyDeviceToHost));
+        CUDA_TRY(cudaMemcpy(tgt.data(), tgt_affine, sizeof(float) * 2 * dt, cudaMemcpyDeviceToHost));
+        auto col = [](const std::vector<float>& t, int c) { return make_float2(t[2 * c], t[2 * c + 1]); };
+        auto same = [](float2 a, float2 b) { return a.x == b.x && a.y == b.y; };
+        bool uniform = true;
+        for (int j = 0; j < 13; ++j) { f.pres[j] = col(tgt, j); if (nc) uniform = uniform && same(f.pres[j], col(cam, j)); }
+        for (int j = 0; j < 14; ++j) f.tself[j] = col(tgt, 13 + j);
+        for (int j = 0; j < 9 && nc; ++j) f.cself[j] = col(cam, 13 + j);
+        const int t_tgt = 27 + 7 * nc + 4 * no, t_obs = 27 + 7 * nc, t_cam = 27, c_tgt = 22, c_obs = 22 + 5 * nt, c_cam = 22 + 5 * nt + 4 * no;
+        for (int j = 0; j < 5; ++j) f.tgt[j] = col(tgt, t_tgt + j);
+        for (int j = 0; j < 4 && no; ++j) f.obs[j] = col(tgt, t_obs + j);
+        for (int j = 0; j < 7 && nc; ++j) f.cam[j] = col(tgt, t_cam + j);
+        // every entry of a kind has the same bounds in both teams' rows (mate/constants.py:195-254): checked, not assumed
+        for (int e = 0; e < nt; ++e) for (int j = 0; j < 5; ++j) {
+            uniform = uniform && same(f.tgt[j], col(tgt, t_tgt + 5 * e + j));
+            if (nc) uniform = uniform && same(f.tgt[j], col(cam, c_tgt + 5 * e + j));
+        }
+        for (int e = 0; e < no; ++e) for (int j = 0; j < 4; ++j) {
+            uniform = uniform && same(f.obs[j], col(tgt, t_obs + 4 * e + j));
+            if (nc) uniform = uniform && same(f.obs[j], col(cam, c_obs + 4 * e + j));
+        }
+        for (int e = 0; e < nc; ++e) for (int j = 0; j < 7; ++j)
+            uniform = uniform && same(f.cam[j], col(tgt, t_cam + 7 * e + j)) && same(f.cam[j], col(cam, c_cam + 7 * e + j));
+        if (!uniform) f.fast = 0;   // tables of the caller's own: generic path
+    }
+    if (const char* v = getenv("MATE_B200_FOLD")) { if (v[0] == '0') f.fast = 0; }   // tests: force the generic shared-memory path
+    sim->base.obs_ops = o;
+    sim->base.cam_affine = cam_affine;
+    sim->base.tgt_affine = tgt_affine;
+    sim->base.fold = f;
     return MATE_OK;
 }
 

@@ -37,6 +37,26 @@ __host__ __device__ inline int tp_capacity(uint32_t p) { return (int)((p >> 21) 
 __host__ __device__ inline int tp_empty(uint32_t p) { return (int)((p >> 23) & 15); }
 __host__ __device__ inline int tp_colliding(uint32_t p) { return (int)((p >> 27) & 1); }
 
+// observation wrappers (mate_wrappers.cuh), innermost first
+constexpr int kMaxObsOps = MATE_MAX_OBS_OPS;
+struct ObsOps { int n; int op[kMaxObsOps]; };
+
+// The reference's wrapper ordering rules (enhanced_observation.py:33-47, shared_field_of_view.py:35-49,
+// relative_coordinates / rescaled_observation asserts) only admit stacks of the form
+//   (EnhancedObservation | SharedFieldOfView)*  RelativeCoordinates?  RescaledObservation?
+// For those the packer of the step kernel applies the wrappers while it composes the rows (mate_step.cuh, FOLD):
+// mask ops act on the observer rows' mask words, RelativeCoordinates subtracts the observer's fp64 location from the
+// visible entities' locations, RescaledObservation is one FMA per entry with (scale, shift) read from this block
+// (kernel parameters live in the constant bank).
+struct FoldOps {
+    int fast;                           // the registered stack has the canonical form; 0 = generic shared-memory path
+    int n_mask; int mask_op[kMaxObsOps];
+    int relative, rescaled;
+    float2 pres[13];                    // (scale, shift) of the preserved block's columns (the same for both teams)
+    float2 cself[9], tself[14];         // private state of a camera / a target row
+    float2 tgt[5], obs[4], cam[7];      // a target / obstacle / camera entry with its flag
+};
+
 struct Params {
     // --- state (device, struct-of-arrays, row stride = bpad) ---
     double* cam_x; double* cam_y; double* cam_phi; double* cam_theta;   // [NC][bpad]
@@ -62,6 +82,9 @@ struct Params {
     const uint8_t* env_mask;
     MateStepAux aux; int has_aux; int has_aux_detail;   // detail = anything beyond coverage / num_delivered / episode_step
     const uint8_t* replay_transmit; const int8_t* replay_choice;
+    // observation wrappers applied to the rows before they leave the SM (mate_b200_set_observation_ops)
+    ObsOps obs_ops; const float* cam_affine; const float* tgt_affine; FoldOps fold;
+    int warp_stride;   // bytes between the shared-memory blocks of two warps of a CTA (Shape2::WARP_BYTES, + scratch with obs_ops)
     // --- scalars ---
     int num_envs; int bpad; int mode; uint32_t flags;
     int next_offset;   // a launch over [begin, begin + num_envs) of the batch: env e of the launch is env e + next_offset of the arrays `next` addresses

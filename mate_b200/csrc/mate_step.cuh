@@ -31,6 +31,7 @@
 #pragma once
 
 #include "mate_common.cuh"
+#include "mate_wrappers.cuh"
 
 #ifndef MATE2_WARPS
 #define MATE2_WARPS 2          // warps per CTA (warps are independent; this only sets the CTA granularity)
@@ -95,6 +96,10 @@ struct Shape2 {
     static constexpr int OFF_Q = OFF_VAL + 32 * VSTRIDE * 4;
     static constexpr int OFF_Q2 = OFF_Q + QCAP * 2;             // second queue: pairs that need the exact polyline
     static constexpr int WARP_BYTES = ((OFF_Q2 + QCAP * 2 + 15) / 16) * 16;
+    // scratch of the observation wrappers folded into the packer (apply_obs_ops), behind the block, only when some are registered
+    static constexpr int FOLD_SCR = 4 * (NT + NO + NC) + R * MW + 1 + 2 * (13 + 14 + 9 + 5 + 4 + 7);   // fp64 locations, mask words, (scale, shift) of the own-row columns
+    static constexpr int OPS_FLOATS = WShape<NC, NT, NO>::SCR > FOLD_SCR ? WShape<NC, NT, NO>::SCR : FOLD_SCR;
+    static constexpr int OPS_BYTES = ((OPS_FLOATS * 4 + 15) / 16) * 16;
     static constexpr int SMEM_BYTES = WARPS * WARP_BYTES;
 };
 
@@ -557,13 +562,34 @@ __device__ __noinline__ void adopt_prepared_warp(const Params& p, const Params& 
 // joint_observation (environment.py:908-983) for the warp's environments [env0, env0 + nvalid).
 // Out of line on purpose: the packer gets its own register allocation.
 // =============================================================================================
+// the registered observation wrappers on the staged rows of one environment; out of line: the common case has none
 template <int NC, int NT, int NO>
+__device__ __noinline__ void fold_obs_ops(const Params& p, const int env, float* stage, float* scratch) {
+    using S = Shape2<NC, NT, NO>;
+    apply_obs_ops<NC, NT, NO>(p, p.obs_ops, env, stage, stage + S::STAGE_CAM, scratch, p.cam_affine, p.tgt_affine);
+}
+
+// FOLD = the instantiation that also applies the registered observation wrappers (FoldOps, mate_common.cuh) while
+// the rows are composed; the common case (no wrappers) runs the FOLD = false instantiation, which has none of it.
+template <int NC, int NT, int NO, bool FOLD>
 __device__ __noinline__ void pack_observations(const Params& p, const int env0, const int nvalid, float* stage,
-                                               const uint32_t* mk, const float* val) {
+                                               const uint32_t* mk, const float* val, float* ops_scratch) {
     using S = Shape2<NC, NT, NO>;
     constexpr int R = S::R, MW = S::MW, DC = S::DC, DT = S::DT, CV = S::CV;
     constexpr int NCX = NC > 0 ? NC : 1;
+    constexpr uint32_t FULLMASK = 0xffffffffu;
     const int lane = threadIdx.x & 31;
+    // ---- folded wrappers: which ones, and the scratch they use (behind the warp's block, present when wrappers are registered)
+    const bool fast = FOLD && p.fold.fast != 0;
+    const bool f_rel = fast && p.fold.relative != 0, f_resc = fast && p.fold.rescaled != 0, f_mask = fast && p.fold.n_mask > 0;
+    constexpr int EALL = NT + NO + NC;
+    double* const fpos = reinterpret_cast<double*>(ops_scratch);                       // [EALL][2] fp64 locations: targets, obstacles, cameras
+    uint32_t* const mmod = reinterpret_cast<uint32_t*>(ops_scratch) + 4 * EALL;       // [R * MW] mask words after the mask wrappers
+    float2* const aff_own = reinterpret_cast<float2*>(ops_scratch + 4 * EALL + R * MW + ((R * MW) & 1));   // [13 | 14 | 9 | 5 | 4 | 7] preserved, target private, camera private, target / obstacle / camera entries
+    if (FOLD && f_resc) {   // staged once per tile: the parameter block is only reachable through slow generic loads here
+        for (int k = lane; k < 52; k += 32)
+            aff_own[k] = k < 13 ? p.fold.pres[k] : (k < 27 ? p.fold.tself[k - 13] : (k < 36 ? p.fold.cself[k - 27] : (k < 41 ? p.fold.tgt[k - 36] : (k < 45 ? p.fold.obs[k - 41] : p.fold.cam[k - 45]))));
+    }
     // launch parameters used inside the loop, read once (a reference to the parameter block is a generic
     // pointer: the compiler would re-load through it after every store)
     const size_t bp = p.bpad;
@@ -624,23 +650,43 @@ __device__ __noinline__ void pack_observations(const Params& p, const int env0, 
         }
     }
     const uint32_t t_bit = bit_tgt(t_idx), o_bit = MW == 1 ? (1u << (16 + o_idx)) : (1u << o_idx), c_bit = bit_cam(c_idx);
-    // the own-row entries that never change are staged once: preserved block (environment.py:921-934)
-    // and the constant entries of the private state
-    if (lane < R) {
-        const int row = lane;
-        float* q = stage + row_base(row);
-        q[0] = (float)NC; q[1] = (float)NT; q[2] = (float)NO; q[3] = (float)(row < NC ? row : row - NC);
-        q[4] = 925.f; q[5] = 925.f; q[6] = -925.f; q[7] = 925.f; q[8] = -925.f; q[9] = -925.f; q[10] = 925.f; q[11] = -925.f;
-        q[12] = 75.f;
-        if (row < NC) { q[C_SELF + 2] = f_crad; q[C_SELF + 6] = f_rmax; q[C_SELF + 7] = f_rot; q[C_SELF + 8] = f_zoom; }
-        else q[T_SELF + 2] = f_sr;
-    }
+    // the own-row entries that never change are staged once per tile: preserved block (environment.py:921-934)
+    // and the constant entries of the private state -- unless observation wrappers are folded in, which rewrite
+    // them in place for every environment
+    const bool has_ops = FOLD && !fast && p.obs_ops.n > 0;   // a stack outside the canonical form: generic shared-memory path
+    auto stage_constants = [&]() {
+        if (lane < R) {
+            const int row = lane;
+            float* q = stage + row_base(row);
+            q[0] = (float)NC; q[1] = (float)NT; q[2] = (float)NO; q[3] = (float)(row < NC ? row : row - NC);
+            q[4] = 925.f; q[5] = 925.f; q[6] = -925.f; q[7] = 925.f; q[8] = -925.f; q[9] = -925.f; q[10] = 925.f; q[11] = -925.f;
+            q[12] = 75.f;
+            if (row < NC) { q[C_SELF + 2] = f_crad; q[C_SELF + 6] = f_rmax; q[C_SELF + 7] = f_rot; q[C_SELF + 8] = f_zoom; }
+            else q[T_SELF + 2] = f_sr;
+        }
+    };
+    stage_constants();
     float* const self_t = stage + S::STAGE_CAM + t_idx * DT + T_SELF;   // used by lanes 0..NT-1
     float* const self_c = stage + c_idx * DC + C_SELF;                   // used by lanes 0..NC-1
     // obstacle entries are fetched two environments ahead (an L2 round trip is longer than one iteration)
     const float4* ob_ptr = obs_f4 + (size_t)o_idx * bp + env0;
     float4 ob_next = make_float4(0.f, 0.f, 0.f, 0.f), ob_next2 = ob_next;
     if (NO > 0) { ob_next = ob_ptr[0]; if (nvalid > 1) ob_next2 = ob_ptr[1]; }
+    // RelativeCoordinates: the fp64 locations of the next environment's entities are fetched one environment ahead
+    constexpr int FJ = (EALL + 31) / 32;
+    double fx_next[FJ], fy_next[FJ];
+    auto load_locations = [&](const int env) {
+#pragma unroll
+        for (int j = 0; j < FJ; ++j) {
+            const int k = lane + 32 * j;
+            double x = 0.0, y = 0.0;
+            if (k < NT) { x = p.tgt_x[(size_t)k * bp + env]; y = p.tgt_y[(size_t)k * bp + env]; }
+            else if (k < NT + NO) { x = p.obs_x[(size_t)(k - NT) * bp + env]; y = p.obs_y[(size_t)(k - NT) * bp + env]; }
+            else if (k < EALL) { x = p.cam_x[(size_t)(k - NT - NO) * bp + env]; y = p.cam_y[(size_t)(k - NT - NO) * bp + env]; }
+            fx_next[j] = x; fy_next[j] = y;
+        }
+    };
+    if (FOLD && f_rel) load_locations(env0);
     __syncwarp();
 #pragma unroll 1
     for (int i = 0; i < nvalid; ++i) {
@@ -649,6 +695,54 @@ __device__ __noinline__ void pack_observations(const Params& p, const int env0, 
         const float4 ob = ob_next;
         ob_next = ob_next2;
         if (NO > 0 && i + 2 < nvalid) ob_next2 = ob_ptr[i + 2];
+        int empty_fold = 0;   // lanes < NT: the empty bits of "their" target after the mask wrappers
+        if (FOLD && fast) {
+            const int env = env0 + i;
+            if (f_rel) {   // fp64 locations of all entities (RelativeCoordinates subtracts in fp64: fp32 would lose 1e-4 to cancellation)
+#pragma unroll
+                for (int j = 0; j < FJ; ++j) {
+                    const int k = lane + 32 * j;
+                    if (k < EALL) { fpos[2 * k] = fx_next[j]; fpos[2 * k + 1] = fy_next[j]; }
+                }
+                if (i + 1 < nvalid) load_locations(env + 1);   // in flight while this environment is packed
+            }
+            if (f_mask) {
+                // lane r < R owns observer row r: its mask words go through the mask wrappers in their order;
+                // lanes < NT also carry target t's empty bits (EnhancedObservation / SharedFieldOfView rewrite them)
+                constexpr uint32_t CAMS = NC > 0 ? ((1u << NC) - 1u) : 0u, TGTS = ((1u << NT) - 1u) << 8;
+                constexpr uint32_t OBS0 = MW == 1 ? (NO > 0 ? (((1u << NO) - 1u) << 16) : 0u) : 0u;
+                constexpr uint32_t OBS1 = MW == 2 ? (NO >= 32 ? 0xffffffffu : ((1u << (NO & 31)) - 1u)) : 0u;
+                constexpr uint32_t CAM_LANES = NC > 0 ? ((1u << NC) - 1u) : 0u, TGT_LANES = ((1u << NT) - 1u) << NC, TLOW = (1u << NT) - 1u;
+                uint32_t w0 = lane < R ? m[lane * MW] : 0u, w1 = (MW == 2 && lane < R) ? m[lane * MW + 1] : 0u;
+                int emp = lane < NT ? tp_empty(__float_as_uint(v[S::V_T + 3 * lane + 2])) : 0;
+                const bool cam_lane = lane < NC, tgt_lane = lane >= NC && lane < R;
+                for (int k = 0; k < p.fold.n_mask; ++k) {   // warp-uniform
+                    const int op = p.fold.mask_op[k];
+                    if (op == MATE_OBS_ENHANCED_CAMERA) { if (cam_lane) { w0 = CAMS | TGTS | OBS0; w1 = OBS1; } }
+                    else if (op == MATE_OBS_ENHANCED_TARGET) {
+                        if (tgt_lane) { w0 = CAMS | TGTS | OBS0; w1 = OBS1; }
+                        // np.logical_not(remaining_cargoes).all(axis=-1) (enhanced_observation.py:107-109)
+                        const uint4 c0 = p.cargo[env], c1 = p.cargo[bp + env];
+                        emp = (int)((c0.x | c0.y) == 0u) | ((int)((c0.z | c0.w) == 0u) << 1) | ((int)((c1.x | c1.y) == 0u) << 2) | ((int)((c1.z | c1.w) == 0u) << 3);
+                    } else if (op == MATE_OBS_SHARED_CAMERA) {
+                        if (NC > 0 && cam_lane) {   // "or" over the team's rows, teammates always (shared_field_of_view.py:90-110)
+                            w0 = __reduce_or_sync(CAM_LANES, w0) | CAMS;
+                            if (MW == 2) w1 = __reduce_or_sync(CAM_LANES, w1);
+                        }
+                    } else if (op == MATE_OBS_SHARED_TARGET) {
+                        if (tgt_lane) {
+                            w0 = __reduce_or_sync(TGT_LANES, w0) | TGTS;
+                            if (MW == 2) w1 = __reduce_or_sync(TGT_LANES, w1);
+                        }
+                        if (lane < NT) emp = (int)__reduce_or_sync(TLOW, (uint32_t)emp);
+                    }
+                }
+                if (lane < R) { mmod[lane * MW] = w0; if (MW == 2) mmod[lane * MW + 1] = w1; }
+                empty_fold = emp;
+                m = mmod;
+            }
+            __syncwarp();
+        }
         // ---- everything is computed into registers first: the previous environment's bulk copy is
         //      still reading the staged block, only the stores have to wait for it
         // Target.state public part (entities.py:631-637), Camera.state public part (entities.py:313-324)
@@ -661,29 +755,9 @@ __device__ __noinline__ void pack_observations(const Params& p, const int env0, 
             const float* cv = v + S::V_C + CV * c_idx;
             c0 = cv[0]; c1 = cv[1]; c3 = cv[3]; c4 = cv[4]; c5 = cv[2];
         }
-        float vt[RND_T][5], vo[NO > 0 ? RND_O : 1][4], vc[NC > 0 ? RND_C : 1][7];
-#pragma unroll
-        for (int rd = 0; rd < RND_T; ++rd) {   // targets + flag
-            const bool hit = (m[m_idx[rd]] & t_bit) != 0u;
-            vt[rd][0] = hit ? t0 : 0.f; vt[rd][1] = hit ? t1 : 0.f; vt[rd][2] = hit ? f_sr : 0.f; vt[rd][3] = hit ? t3 : 0.f; vt[rd][4] = hit ? 1.f : 0.f;
-        }
-        if (NO > 0) {
-#pragma unroll
-            for (int rd = 0; rd < RND_O; ++rd) {   // obstacles: Obstacle.state (entities.py:147-148) + flag
-                const bool hit = (m[m_idx[RND_T + rd]] & o_bit) != 0u;
-                vo[rd][0] = hit ? ob.x : 0.f; vo[rd][1] = hit ? ob.y : 0.f; vo[rd][2] = hit ? ob.z : 0.f; vo[rd][3] = hit ? 1.f : 0.f;
-            }
-        }
-        if (NC > 0) {
-#pragma unroll
-            for (int rd = 0; rd < RND_C; ++rd) {   // cameras + flag
-                const bool hit = (m[m_idx[NRND - RND_C + rd]] & c_bit) != 0u;
-                vc[rd][0] = hit ? c0 : 0.f; vc[rd][1] = hit ? c1 : 0.f; vc[rd][2] = hit ? f_crad : 0.f; vc[rd][3] = hit ? c3 : 0.f;
-                vc[rd][4] = hit ? c4 : 0.f; vc[rd][5] = hit ? c5 : 0.f; vc[rd][6] = hit ? 1.f : 0.f;
-            }
-        }
+        const bool plain = !(FOLD && fast);
         // own rows, the entries that change: lane t < NT holds target t, lane c < NC holds camera c
-        const int capacity = tp_capacity(tpk), empty = tp_empty(tpk);
+        const int capacity = tp_capacity(tpk), empty = (FOLD && f_mask) ? empty_fold : tp_empty(tpk);
         float sg[NW], se[NW];
 #pragma unroll
         for (int w = 0; w < NW; ++w) { sg[w] = (goal == w) ? (float)weight : 0.f; se[w] = (float)((empty >> w) & 1); }
@@ -693,31 +767,143 @@ __device__ __noinline__ void pack_observations(const Params& p, const int env0, 
             if (S::BULK) { if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
             __syncwarp();
         }
+        if constexpr (FOLD) {
+            if (fast) {
+                // one entity kind at a time (values -> wrappers -> staged rows): fewer live registers than the plain path
+                auto observer = [&](const int midx) { const int row = midx / MW; return row < NC ? NT + NO + row : row - NC; };
+                uint32_t mw[NRND];   // all mask words first: the loads are in flight together
 #pragma unroll
-        for (int rd = 0; rd < RND_T; ++rd) {
-            if ((on_bits >> rd) & 1u) {
-                float* q = q_ptr[rd];
-                q[0] = vt[rd][0]; q[1] = vt[rd][1]; q[2] = vt[rd][2]; q[3] = vt[rd][3]; q[4] = vt[rd][4];
-            }
-        }
-        if (NO > 0) {
+                for (int rd = 0; rd < NRND; ++rd) mw[rd] = m[m_idx[rd]];
+                {   // targets + flag
+                    float2 a[5];
 #pragma unroll
-            for (int rd = 0; rd < RND_O; ++rd) {
-                if ((on_bits >> (RND_T + rd)) & 1u) {
-                    float* q = q_ptr[RND_T + rd];
-                    q[0] = vo[rd][0]; q[1] = vo[rd][1]; q[2] = vo[rd][2]; q[3] = vo[rd][3];
+                    for (int j = 0; j < 5; ++j) a[j] = f_resc ? aff_own[36 + j] : make_float2(1.f, 0.f);
+                    double ex = 0.0, ey = 0.0;
+                    if (f_rel) { ex = fpos[2 * t_idx]; ey = fpos[2 * t_idx + 1]; }
+#pragma unroll
+                    for (int rd = 0; rd < RND_T; ++rd) {
+                        const bool hit = (mw[rd] & t_bit) != 0u;
+                        float x[5] = {hit ? t0 : 0.f, hit ? t1 : 0.f, hit ? f_sr : 0.f, hit ? t3 : 0.f, hit ? 1.f : 0.f};
+                        if (f_rel && hit) { const int ko = observer(m_idx[rd]); x[0] = (float)(ex - fpos[2 * ko]); x[1] = (float)(ey - fpos[2 * ko + 1]); }
+                        if ((on_bits >> rd) & 1u) {
+                            float* q = q_ptr[rd];
+#pragma unroll
+                            for (int j = 0; j < 5; ++j) q[j] = f_resc ? fmaf(x[j], a[j].x, a[j].y) : x[j];
+                        }
+                    }
+                }
+                if (NO > 0) {   // obstacles + flag
+                    float2 a[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) a[j] = f_resc ? aff_own[41 + j] : make_float2(1.f, 0.f);
+                    double ex = 0.0, ey = 0.0;
+                    if (f_rel) { ex = fpos[2 * (NT + o_idx)]; ey = fpos[2 * (NT + o_idx) + 1]; }
+#pragma unroll
+                    for (int rd = 0; rd < RND_O; ++rd) {
+                        const bool hit = (mw[RND_T + rd] & o_bit) != 0u;
+                        float x[4] = {hit ? ob.x : 0.f, hit ? ob.y : 0.f, hit ? ob.z : 0.f, hit ? 1.f : 0.f};
+                        if (f_rel && hit) { const int ko = observer(m_idx[RND_T + rd]); x[0] = (float)(ex - fpos[2 * ko]); x[1] = (float)(ey - fpos[2 * ko + 1]); }
+                        if ((on_bits >> (RND_T + rd)) & 1u) {
+                            float* q = q_ptr[RND_T + rd];
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) q[j] = f_resc ? fmaf(x[j], a[j].x, a[j].y) : x[j];
+                        }
+                    }
+                }
+                if (NC > 0) {   // cameras + flag
+                    float2 a[7];
+#pragma unroll
+                    for (int j = 0; j < 7; ++j) a[j] = f_resc ? aff_own[45 + j] : make_float2(1.f, 0.f);
+                    double ex = 0.0, ey = 0.0;
+                    if (f_rel) { ex = fpos[2 * (NT + NO + c_idx)]; ey = fpos[2 * (NT + NO + c_idx) + 1]; }
+#pragma unroll
+                    for (int rd = 0; rd < RND_C; ++rd) {
+                        const bool hit = (mw[NRND - RND_C + rd] & c_bit) != 0u;
+                        float x[7] = {hit ? c0 : 0.f, hit ? c1 : 0.f, hit ? f_crad : 0.f, hit ? c3 : 0.f, hit ? c4 : 0.f, hit ? c5 : 0.f, hit ? 1.f : 0.f};
+                        if (f_rel && hit) { const int ko = observer(m_idx[NRND - RND_C + rd]); x[0] = (float)(ex - fpos[2 * ko]); x[1] = (float)(ey - fpos[2 * ko + 1]); }
+                        if ((on_bits >> (NRND - RND_C + rd)) & 1u) {
+                            float* q = q_ptr[NRND - RND_C + rd];
+#pragma unroll
+                            for (int j = 0; j < 7; ++j) q[j] = f_resc ? fmaf(x[j], a[j].x, a[j].y) : x[j];
+                        }
+                    }
                 }
             }
         }
-        if (NC > 0) {
+        if (plain) {
+        float vt[RND_T][5], vo[NO > 0 ? RND_O : 1][4], vc[NC > 0 ? RND_C : 1][7];
 #pragma unroll
-            for (int rd = 0; rd < RND_C; ++rd) {
-                if ((on_bits >> (NRND - RND_C + rd)) & 1u) {
-                    float* q = q_ptr[NRND - RND_C + rd];
-                    q[0] = vc[rd][0]; q[1] = vc[rd][1]; q[2] = vc[rd][2]; q[3] = vc[rd][3]; q[4] = vc[rd][4]; q[5] = vc[rd][5]; q[6] = vc[rd][6];
+            for (int rd = 0; rd < RND_T; ++rd) {   // targets + flag
+                const bool hit = (m[m_idx[rd]] & t_bit) != 0u;
+                vt[rd][0] = hit ? t0 : 0.f; vt[rd][1] = hit ? t1 : 0.f; vt[rd][2] = hit ? f_sr : 0.f; vt[rd][3] = hit ? t3 : 0.f; vt[rd][4] = hit ? 1.f : 0.f;
+            }
+            if (NO > 0) {
+#pragma unroll
+                for (int rd = 0; rd < RND_O; ++rd) {   // obstacles: Obstacle.state (entities.py:147-148) + flag
+                    const bool hit = (m[m_idx[RND_T + rd]] & o_bit) != 0u;
+                    vo[rd][0] = hit ? ob.x : 0.f; vo[rd][1] = hit ? ob.y : 0.f; vo[rd][2] = hit ? ob.z : 0.f; vo[rd][3] = hit ? 1.f : 0.f;
+                }
+            }
+            if (NC > 0) {
+#pragma unroll
+                for (int rd = 0; rd < RND_C; ++rd) {   // cameras + flag
+                    const bool hit = (m[m_idx[NRND - RND_C + rd]] & c_bit) != 0u;
+                    vc[rd][0] = hit ? c0 : 0.f; vc[rd][1] = hit ? c1 : 0.f; vc[rd][2] = hit ? f_crad : 0.f; vc[rd][3] = hit ? c3 : 0.f;
+                    vc[rd][4] = hit ? c4 : 0.f; vc[rd][5] = hit ? c5 : 0.f; vc[rd][6] = hit ? 1.f : 0.f;
+                }
+            }
+        if (has_ops && i > 0) stage_constants();
+#pragma unroll
+            for (int rd = 0; rd < RND_T; ++rd) {
+                if ((on_bits >> rd) & 1u) {
+                    float* q = q_ptr[rd];
+                    q[0] = vt[rd][0]; q[1] = vt[rd][1]; q[2] = vt[rd][2]; q[3] = vt[rd][3]; q[4] = vt[rd][4];
+                }
+            }
+            if (NO > 0) {
+#pragma unroll
+                for (int rd = 0; rd < RND_O; ++rd) {
+                    if ((on_bits >> (RND_T + rd)) & 1u) {
+                        float* q = q_ptr[RND_T + rd];
+                        q[0] = vo[rd][0]; q[1] = vo[rd][1]; q[2] = vo[rd][2]; q[3] = vo[rd][3];
+                    }
+                }
+            }
+            if (NC > 0) {
+#pragma unroll
+                for (int rd = 0; rd < RND_C; ++rd) {
+                    if ((on_bits >> (NRND - RND_C + rd)) & 1u) {
+                        float* q = q_ptr[NRND - RND_C + rd];
+                        q[0] = vc[rd][0]; q[1] = vc[rd][1]; q[2] = vc[rd][2]; q[3] = vc[rd][3]; q[4] = vc[rd][4]; q[5] = vc[rd][5]; q[6] = vc[rd][6];
+                    }
                 }
             }
         }
+        if (FOLD && fast) {
+            // with wrappers folded in, a row's preserved block and private state are written per environment:
+            // RelativeCoordinates moves the warehouse locations, RescaledObservation touches every column
+            auto own_row = [&](float* q, const int ko, const float* self, auto nself_c, const float2* aff_self) {
+                constexpr int nself = decltype(nself_c)::value;
+                float pres[13] = {(float)NC, (float)NT, (float)NO, 0.f, 925.f, 925.f, -925.f, 925.f, -925.f, -925.f, 925.f, -925.f, 75.f};
+                pres[3] = self[nself];   // the row's index in its team (passed behind the private state)
+                if (f_rel) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) pres[4 + j] = (float)((double)pres[4 + j] - fpos[2 * ko + (j & 1)]);
+                }
+#pragma unroll
+                for (int j = 0; j < 13; ++j) q[j] = f_resc ? fmaf(pres[j], aff_own[j].x, aff_own[j].y) : pres[j];
+#pragma unroll
+                for (int j = 0; j < nself; ++j) q[13 + j] = f_resc ? fmaf(self[j], aff_self[j].x, aff_self[j].y) : self[j];
+            };
+            if (lane < NT) {
+                const float self[15] = {t0, t1, f_sr, t3, s_step, s_cap, sg[0], sg[1], sg[2], sg[3], se[0], se[1], se[2], se[3], (float)lane};
+                own_row(stage + S::STAGE_CAM + lane * DT, lane, self, std::integral_constant<int, 14>{}, aff_own + 13);
+            }
+            if (NC > 0 && lane < NC) {
+                const float self[10] = {c0, c1, f_crad, c3, c4, c5, f_rmax, f_rot, f_zoom, (float)lane};
+                own_row(stage + lane * DC, NT + NO + lane, self, std::integral_constant<int, 9>{}, aff_own + 27);
+            }
+        } else {
         if (lane < NT) {
             float* q = self_t;
             q[0] = t0; q[1] = t1; q[3] = t3; q[4] = s_step; q[5] = s_cap;
@@ -727,6 +913,14 @@ __device__ __noinline__ void pack_observations(const Params& p, const int env0, 
         if (NC > 0 && lane < NC) {
             float* q = self_c;
             q[0] = c0; q[1] = c1; q[3] = c3; q[4] = c4; q[5] = c5;
+        }
+        }
+        // ---- registered observation wrappers (EnhancedObservation, SharedFieldOfView, RelativeCoordinates,
+        //      RescaledObservation): applied to the staged rows, no extra pass over the observation tensors
+        if (FOLD && has_ops) {
+            __syncwarp();
+            fold_obs_ops<NC, NT, NO>(p, env0 + i, stage, ops_scratch);
+            __syncwarp();
         }
         // ---- staged rows -> HBM
         if (S::BULK && MATE2_COPYOUT == 1) {
@@ -811,7 +1005,7 @@ mate_step_kernel2(const __grid_constant__ Params p) {
 
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    unsigned char* wbase = smem_raw + (size_t)warp * S::WARP_BYTES;
+    unsigned char* wbase = smem_raw + (size_t)warp * p.warp_stride;
     float* stage = reinterpret_cast<float*>(wbase + S::OFF_STAGE);
     uint32_t* mk = reinterpret_cast<uint32_t*>(wbase + S::OFF_MASK);      // [32][MSTRIDE]
     float* val = reinterpret_cast<float*>(wbase + S::OFF_VAL);            // [32][VSTRIDE]
@@ -1468,7 +1662,8 @@ mate_step_kernel2(const __grid_constant__ Params p) {
 
     // ------------------------------------------------------------------ joint_observation (environment.py:908-983)
     TL_MARK(5);
-    pack_observations<NC, NT, NO>(p, env0, nvalid, stage, mk, val);
+    if (p.obs_ops.n > 0) pack_observations<NC, NT, NO, true>(p, env0, nvalid, stage, mk, val, reinterpret_cast<float*>(wbase + S::WARP_BYTES));
+    else pack_observations<NC, NT, NO, false>(p, env0, nvalid, stage, mk, val, nullptr);
     TL_MARK(6);
 }
 

@@ -18,9 +18,6 @@
 
 namespace mate {
 
-constexpr int kMaxObsOps = 8;
-struct ObsOps { int n; int op[kMaxObsOps]; };
-
 template <int NC, int NT, int NO>
 struct WShape {
     static constexpr int DC = 22 + 5 * NT + 4 * NO + 7 * NC, DT = 27 + 7 * NC + 4 * NO + 5 * NT;
@@ -50,67 +47,38 @@ __device__ __forceinline__ void slot_of(bool cam_row, int k, int* kind, int* idx
     }
 }
 
+// The registered observation wrappers applied IN PLACE to the rows of one environment that a warp holds in shared
+// memory: B = camera rows [NC][DC], T = target rows [NT][DT]; `scr` = S::SCR floats of scratch (8-byte aligned).
+// Called by all 32 lanes.  Used by obs_transform_kernel (a pass over observation tensors) and by the step kernel's
+// packer (mate_step.cuh: the wrappers registered with mate_b200_set_observation_ops cost no extra pass at all).
 template <int NC, int NT, int NO>
-__global__ void __launch_bounds__(WShape<NC, NT, NO>::WARPS * 32)
-obs_transform_kernel(const __grid_constant__ Params p, const ObsOps ops, const float* __restrict__ cam_affine,
-                     const float* __restrict__ tgt_affine) {
+__device__ __forceinline__ void apply_obs_ops(const Params& p, const ObsOps& ops, const int env, float* B, float* T, float* scr,
+                                              const float* aff_cam, const float* aff_tgt) {
     using S = WShape<NC, NT, NO>;
     constexpr int DC = S::DC, DT = S::DT, E = S::E, R = S::R;
-    extern __shared__ __align__(16) float wsm[];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    float* aff = wsm + S::WARPS * S::WARP_FLOATS;              // [DC + DT][2] scale, shift (RescaledObservation)
-    bool rescale = false;
-    for (int i = 0; i < ops.n; ++i) rescale = rescale || ops.op[i] == MATE_OBS_RESCALED;
-    if (rescale) {
-        for (int k = threadIdx.x; k < 2 * DC; k += blockDim.x) aff[k] = NC > 0 ? cam_affine[k] : 0.f;
-        for (int k = threadIdx.x; k < 2 * DT; k += blockDim.x) aff[2 * DC + k] = tgt_affine[k];
-    }
-    __syncthreads();
-    const int env = blockIdx.x * S::WARPS + warp;
-    if (env >= p.num_envs) return;
-    float* B = wsm + warp * S::WARP_FLOATS;                    // cam rows, then target rows
-    float* ob = B + S::BLOCK;                                  // [NO][4] obstacle_states_flagged
+    const int lane = threadIdx.x & 31;
+    float* ob = scr;                                           // [NO][4] obstacle_states_flagged
     float* shm = ob + 4 * (NO > 0 ? NO : 1);                   // [2][E] shared view masks (camera team, target team)
     float* she = shm + 2 * E;                                  // [4] shared empty bits
     double* pos = reinterpret_cast<double*>((reinterpret_cast<uintptr_t>(she + 8) + 7) & ~(uintptr_t)7);   // [E][2] fp64 locations: targets, obstacles, cameras
-    float* cam_g = p.cam_obs + (size_t)env * S::CAM_ROW;
-    float* tgt_g = p.tgt_obs + (size_t)env * S::TGT_ROW;
-    // ---- load
-    if (S::VEC) {
-        // all 16-byte loads of the block are issued before the first one is stored to shared memory
-        const float4* c4 = reinterpret_cast<const float4*>(cam_g);
-        const float4* t4 = reinterpret_cast<const float4*>(tgt_g) - S::CAM_ROW / 4;
-        float4* b4 = reinterpret_cast<float4*>(B);
-        constexpr int NV = S::BLOCK / 4, NIT = (NV + 31) / 32;
-        float4 v[NIT];
-#pragma unroll
-        for (int it = 0; it < NIT; ++it) {
-            const int k = it * 32 + lane;
-            if (it * 32 + 32 <= NV || k < NV) v[it] = __ldcs((k < S::CAM_ROW / 4 ? c4 : t4) + k);
-        }
-#pragma unroll
-        for (int it = 0; it < NIT; ++it) {
-            const int k = it * 32 + lane;
-            if (it * 32 + 32 <= NV || k < NV) b4[k] = v[it];
-        }
-    } else {
-        for (int k = lane; k < S::CAM_ROW; k += 32) B[k] = cam_g[k];
-        for (int k = lane; k < S::TGT_ROW; k += 32) B[S::CAM_ROW + k] = tgt_g[k];
-    }
     for (int o = lane; o < NO; o += 32) {
         const float4 f = p.obs_f4[(size_t)o * p.bpad + env];
         ob[4 * o] = f.x; ob[4 * o + 1] = f.y; ob[4 * o + 2] = f.z; ob[4 * o + 3] = 1.f;
     }
-    for (int k = lane; k < E; k += 32) {   // RelativeCoordinates subtracts in fp64 (fp32 would lose ~1e-4 to cancellation)
-        const size_t bp = p.bpad;
-        double x, y;
-        if (k < NT) { x = p.tgt_x[(size_t)k * bp + env]; y = p.tgt_y[(size_t)k * bp + env]; }
-        else if (k < NT + NO) { x = p.obs_x[(size_t)(k - NT) * bp + env]; y = p.obs_y[(size_t)(k - NT) * bp + env]; }
-        else { x = p.cam_x[(size_t)(k - NT - NO) * bp + env]; y = p.cam_y[(size_t)(k - NT - NO) * bp + env]; }
-        pos[2 * k] = x; pos[2 * k + 1] = y;
+    bool relative_op = false;
+    for (int i = 0; i < ops.n; ++i) relative_op = relative_op || ops.op[i] == MATE_OBS_RELATIVE;
+    if (relative_op) {
+        for (int k = lane; k < E; k += 32) {   // RelativeCoordinates subtracts in fp64 (fp32 would lose ~1e-4 to cancellation)
+            const size_t bp = p.bpad;
+            double x, y;
+            if (k < NT) { x = p.tgt_x[(size_t)k * bp + env]; y = p.tgt_y[(size_t)k * bp + env]; }
+            else if (k < NT + NO) { x = p.obs_x[(size_t)(k - NT) * bp + env]; y = p.obs_y[(size_t)(k - NT) * bp + env]; }
+            else { x = p.cam_x[(size_t)(k - NT - NO) * bp + env]; y = p.cam_y[(size_t)(k - NT - NO) * bp + env]; }
+            pos[2 * k] = x; pos[2 * k + 1] = y;
+        }
     }
     __syncwarp();
-    auto row_ptr = [&](int r) { return r < NC ? B + r * DC : B + S::CAM_ROW + (r - NC) * DT; };
+    auto row_ptr = [&](int r) { return r < NC ? B + r * DC : T + (r - NC) * DT; };
     // Entity kinds with compile-time widths: 0 = target (x, y, sight range, loaded | flag), 1 = obstacle
     // (x, y, r | flag), 2 = camera (x, y, r, Rs cos, Rs sin, theta | flag).  `pairs<K>(r0, n, f)` spreads the
     // (observer row in [r0, r0 + n), entity of kind K) pairs over the lanes and calls
@@ -135,7 +103,7 @@ obs_transform_kernel(const __grid_constant__ Params p, const ObsOps ops, const f
     auto fill = [&](auto k, float* dst, const int idx, const bool on) {
         constexpr int K = decltype(k)::value;
         constexpr int W = K == 0 ? 5 : (K == 1 ? 4 : 7);
-        const float* src = K == 0 ? B + S::CAM_ROW + idx * DT + 13 : (K == 1 ? ob + 4 * idx : B + idx * DC + 13);
+        const float* src = K == 0 ? T + idx * DT + 13 : (K == 1 ? ob + 4 * idx : B + idx * DC + 13);
 #pragma unroll
         for (int j = 0; j < W - 1; ++j) dst[j] = on ? src[j] : 0.f;
         dst[W - 1] = on ? 1.f : 0.f;
@@ -211,18 +179,65 @@ obs_transform_kernel(const __grid_constant__ Params p, const ObsOps ops, const f
         } else if (op == MATE_OBS_RESCALED) {
             // a lane keeps its columns' (scale, shift) in registers and walks down the rows of a team
             for (int col = lane; col < DC; col += 32) {
-                const float sc = aff[2 * col], sh = aff[2 * col + 1];
+                const float sc = aff_cam[2 * col], sh = aff_cam[2 * col + 1];
 #pragma unroll
                 for (int r = 0; r < NC; ++r) B[r * DC + col] = B[r * DC + col] * sc + sh;
             }
             for (int col = lane; col < DT; col += 32) {
-                const float sc = aff[2 * DC + 2 * col], sh = aff[2 * DC + 2 * col + 1];
+                const float sc = aff_tgt[2 * col], sh = aff_tgt[2 * col + 1];
 #pragma unroll
-                for (int t = 0; t < NT; ++t) B[S::CAM_ROW + t * DT + col] = B[S::CAM_ROW + t * DT + col] * sc + sh;
+                for (int t = 0; t < NT; ++t) T[t * DT + col] = T[t * DT + col] * sc + sh;
             }
             __syncwarp();
         }
     }
+}
+
+template <int NC, int NT, int NO>
+__global__ void __launch_bounds__(WShape<NC, NT, NO>::WARPS * 32)
+obs_transform_kernel(const __grid_constant__ Params p, const ObsOps ops, const float* __restrict__ cam_affine,
+                     const float* __restrict__ tgt_affine) {
+    using S = WShape<NC, NT, NO>;
+    constexpr int DC = S::DC, DT = S::DT;
+    extern __shared__ __align__(16) float wsm[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float* aff = wsm + S::WARPS * S::WARP_FLOATS;              // [DC + DT][2] scale, shift (RescaledObservation)
+    bool rescale = false;
+    for (int i = 0; i < ops.n; ++i) rescale = rescale || ops.op[i] == MATE_OBS_RESCALED;
+    if (rescale) {
+        for (int k = threadIdx.x; k < 2 * DC; k += blockDim.x) aff[k] = NC > 0 ? cam_affine[k] : 0.f;
+        for (int k = threadIdx.x; k < 2 * DT; k += blockDim.x) aff[2 * DC + k] = tgt_affine[k];
+    }
+    __syncthreads();
+    const int env = blockIdx.x * S::WARPS + warp;
+    if (env >= p.num_envs) return;
+    float* B = wsm + warp * S::WARP_FLOATS;                    // cam rows, then target rows
+    float* cam_g = p.cam_obs + (size_t)env * S::CAM_ROW;
+    float* tgt_g = p.tgt_obs + (size_t)env * S::TGT_ROW;
+    // ---- load
+    if (S::VEC) {
+        // all 16-byte loads of the block are issued before the first one is stored to shared memory
+        const float4* c4 = reinterpret_cast<const float4*>(cam_g);
+        const float4* t4 = reinterpret_cast<const float4*>(tgt_g) - S::CAM_ROW / 4;
+        float4* b4 = reinterpret_cast<float4*>(B);
+        constexpr int NV = S::BLOCK / 4, NIT = (NV + 31) / 32;
+        float4 v[NIT];
+#pragma unroll
+        for (int it = 0; it < NIT; ++it) {
+            const int k = it * 32 + lane;
+            if (it * 32 + 32 <= NV || k < NV) v[it] = __ldcs((k < S::CAM_ROW / 4 ? c4 : t4) + k);
+        }
+#pragma unroll
+        for (int it = 0; it < NIT; ++it) {
+            const int k = it * 32 + lane;
+            if (it * 32 + 32 <= NV || k < NV) b4[k] = v[it];
+        }
+    } else {
+        for (int k = lane; k < S::CAM_ROW; k += 32) B[k] = cam_g[k];
+        for (int k = lane; k < S::TGT_ROW; k += 32) B[S::CAM_ROW + k] = tgt_g[k];
+    }
+    __syncwarp();
+    apply_obs_ops<NC, NT, NO>(p, ops, env, B, B + S::CAM_ROW, B + S::BLOCK, aff, aff + 2 * DC);
     // ---- store
     if (S::VEC) {
         float4* c4 = reinterpret_cast<float4*>(cam_g);

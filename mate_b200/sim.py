@@ -143,8 +143,9 @@ class BatchedSim:
 
     # ------------------------------------------------------------------ observation wrappers (N1)
     def set_observation_wrappers(self, ops):
-        """Observation wrapper codes (``_abi.OBS_*``), innermost first; applied in ONE extra kernel after every
-        reset / step / observe (mate_b200_transform_observations)."""
+        """Observation wrapper codes (``_abi.OBS_*``), innermost first.  They are registered with the simulator
+        (``mate_b200_set_observation_ops``): every reset / step / observe applies them to an environment's rows while
+        the rows are still in shared memory, at no extra pass over the observation tensors."""
         ops = [int(op) for op in ops]
         if len(ops) > _abi.MAX_OBS_OPS:
             raise ValueError(f'at most {_abi.MAX_OBS_OPS} observation wrappers can be stacked')
@@ -152,8 +153,14 @@ class BatchedSim:
         self._obs_ops_c = (ctypes.c_int32 * max(len(ops), 1))(*ops)
         if _abi.OBS_RESCALED in ops and self._affine is None:
             self._affine = tuple(torch.from_numpy(t).to(self.device) for t in rescale_tables(self.nc, self.nt, self.no))
+        cam_aff, tgt_aff = self._affine if self._affine is not None else (None, None)
+        _check(self.lib, self.lib.mate_b200_set_observation_ops(
+            self.handle, self._obs_ops_c, len(ops), _dptr(cam_aff) if (self.nc and cam_aff is not None) else None, _dptr(tgt_aff)))
 
-    def _apply_observation_wrappers(self):
+    def transform_observations(self):
+        """The registered wrappers as a separate in-place pass over the current observation tensors
+        (``mate_b200_transform_observations``); only for tensors that did NOT come out of reset / step / observe with
+        the wrappers registered (those are transformed already)."""
         if not self._obs_ops:
             return
         cam_aff, tgt_aff = self._affine if self._affine is not None else (None, None)
@@ -194,7 +201,6 @@ class BatchedSim:
         with torch.cuda.device(self.device):
             _check(self.lib, self.lib.mate_b200_reset(self.handle, _dptr(mask), self._seed, _dptr(self.cam_obs),
                                                       _dptr(self.tgt_obs), self._stream()))
-        self._apply_observation_wrappers()
         return self.cam_obs, self.tgt_obs
 
     def step(self, cam_act, tgt_act, auto_reset=True, replay=None, aux=False):
@@ -210,7 +216,6 @@ class BatchedSim:
                 ctypes.byref(rs) if rs is not None else None,
                 _abi.MATE_STEP_AUTO_RESET if auto_reset else 0, self._stream()))
         del keep
-        self._apply_observation_wrappers()
         return (self.cam_obs, self.tgt_obs), self.rewards, self.done
 
     def observe(self, replay=None, aux=False):
@@ -223,7 +228,6 @@ class BatchedSim:
                 ctypes.byref(self._aux_struct) if aux else None,
                 ctypes.byref(rs) if rs is not None else None, self._stream()))
         del keep
-        self._apply_observation_wrappers()
         return self.cam_obs, self.tgt_obs
 
     def fov_range(self, env, camera, angle_deg):

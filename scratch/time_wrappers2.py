@@ -1,7 +1,6 @@
 import sys, os; sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch, mate_b200
-for wr in ([], [mate_b200.RescaledObservation], [mate_b200.SharedFieldOfView, mate_b200.RelativeCoordinates, mate_b200.RescaledObservation],
-           [mate_b200.EnhancedObservation, mate_b200.RelativeCoordinates, mate_b200.RescaledObservation]):
+for wr in ([], [mate_b200.RescaledObservation], [mate_b200.SharedFieldOfView], [mate_b200.RelativeCoordinates]):
     env = mate_b200.make("MultiAgentTracking-v0", config="MATE-4v8-9.yaml", num_envs=65536, wrappers=wr)
     env.reset(seed=0)
     base = env.unwrapped
@@ -11,5 +10,5 @@ for wr in ([], [mate_b200.RescaledObservation], [mate_b200.SharedFieldOfView, ma
     a.record()
     for _ in range(200): base.sim.step(ca, ta)
     b.record(); torch.cuda.synchronize()
-    print([w.__name__ for w in wr], a.elapsed_time(b)/200, "ms/step")
+    print([w.__name__ for w in wr], round(a.elapsed_time(b)/200, 4), "ms/step")
     base.close()

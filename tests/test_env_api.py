@@ -68,7 +68,7 @@ def test_reference_compatible_single_env_mode_replays_a_reference_trace():
         assert isinstance(rew[0], float) and isinstance(done, bool) and isinstance(infos[0], list)
         assert obs[0].dtype == np.float64 and obs[0].shape == (4, 126)
         assert rew[1] == g['step_reward'][k, 1]
-        assert (env.camera_target_view_mask.cpu().numpy() == g['step_mask_ct'][k]).all()
+        assert (env.camera_target_view_mask == g['step_mask_ct'][k]).all()
         n += 1
     assert n >= 1
     with pytest.raises(AssertionError):

@@ -156,3 +156,51 @@ def test_wrapper_stack_on_odd_shapes_runs_and_keeps_invariants(preset):
     assert torch.isfinite(cam_w).all() and torch.isfinite(tgt_w).all()
     # teammates are always shared: every teammate flag is set (1 stays 1 under the flag columns' [-1, 1] bounds)
     assert bool((tgt_w[..., raw.sim.dt - 5 * nt + 4::5] == 1.0).all())
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('fold', ['fast', 'generic'])
+@pytest.mark.parametrize('preset', ['MATE-4v8-9.yaml', 'MATE-Navigation.yaml', 'MATE-2v2-9.yaml', 'MATE-8v8-9.yaml'])
+def test_wrappers_folded_into_the_step_equal_the_separate_pass(preset, fold, monkeypatch):
+    """The wrappers registered with the simulator (applied by the packer of the step kernel while the rows are in
+    shared memory) give bit-identical rows to ``mate_b200_transform_observations`` run as a separate pass over the
+    raw rows, through reset, steps with auto-reset and observe."""
+    import torch
+
+    import mate_b200
+    from mate_b200 import _abi
+
+    # 'fast': the wrappers are applied while the packer composes the rows (FoldOps); 'generic': on the staged rows
+    monkeypatch.setenv('MATE_B200_FOLD', '1' if fold == 'fast' else '0')
+    B = 1000
+    ops = [_abi.OBS_SHARED_CAMERA, _abi.OBS_ENHANCED_TARGET, _abi.OBS_RELATIVE, _abi.OBS_RESCALED]
+    folded = mate_b200.make('MultiAgentTracking-v0', config=preset, num_envs=B, max_episode_steps=6).unwrapped
+    plain = mate_b200.make('MultiAgentTracking-v0', config=preset, num_envs=B, max_episode_steps=6).unwrapped
+    if folded.num_cameras == 0:
+        ops = ops[1:]
+    folded.sim.set_observation_wrappers(ops)
+
+    def separate_pass(cam, tgt):
+        plain.sim.set_observation_wrappers(ops)          # registers ...
+        plain.sim.transform_observations()               # ... and transforms the raw rows in place, as a pass of its own
+        out = cam.clone(), tgt.clone()
+        plain.sim.set_observation_wrappers([])
+        return out
+
+    a = folded.sim.reset(seed=3)
+    b = separate_pass(*plain.sim.reset(seed=3))
+    assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])
+    gen = torch.Generator(device='cuda')
+    gen.manual_seed(1)
+    nc, nt = folded.num_cameras, folded.num_targets
+    for k in range(15):
+        cam_act = (torch.rand((B, max(nc, 1), 2), device='cuda', generator=gen) * 2 - 1)[:, :nc] * 2.0
+        tgt_act = (torch.rand((B, nt, 2), device='cuda', generator=gen) * 2 - 1) * folded.target_step_size
+        (ca, ta), ra, da = folded.sim.step(cam_act, tgt_act, auto_reset=True)
+        (cb, tb), rb, db = plain.sim.step(cam_act, tgt_act, auto_reset=True)
+        cb, tb = separate_pass(cb, tb)
+        assert torch.equal(ca, cb) and torch.equal(ta, tb), k
+        assert torch.equal(ra, rb) and torch.equal(da, db), k
+    a = folded.sim.observe()
+    b = separate_pass(*plain.sim.observe())
+    assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])
