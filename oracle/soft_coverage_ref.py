@@ -94,6 +94,58 @@ def soft_coverage_matrix(cam_xy, cam_phi, cam_theta, rmax, area_product, obs_xyr
     return out
 
 
+def soft_coverage_explained(cam_xy, cam_phi, cam_theta, rmax, area_product, obs_xyr, tgt_xy, mask_ct, inner_tables, gold, tol=1e-6):
+    """Is every entry of the reference's matrix `gold` reachable by SOME outcome of the exactly tangent rays?
+
+    The reference cuts a boundary ray that is exactly tangent to an obstacle or not depending on the last bit of NumPy's
+    sin / cos (DESIGN.md "Tangent rays"), independently per ray.  A ray whose end point differs between "all tangent
+    rays cut" and "none cut" is such a ray; it contributes one of two candidate points.  An entry min_k |target - p_k| is
+    reachable iff (i) it equals the distance to a point some outcome contains and (ii) every ambiguous ray has an option
+    that is not closer than it (and no unambiguous point is closer).  Returns ([Nc, Nt] bool reachable, [Nc, Nt] bool
+    equal to the none-cut convention of the CUDA path)."""
+    nc, nt = len(cam_xy), len(tgt_xy)
+    ok = np.zeros((nc, nt), dtype=bool)
+    same = np.zeros((nc, nt), dtype=bool)
+    for c in range(nc):
+        theta, phi = float(cam_theta[c]), float(cam_phi[c])
+        sight_range = np.sqrt(area_product / theta)
+        dist_max = sight_range / (1.0 + 1.0 / np.sin(np.deg2rad(theta / 2.0))) if theta < 180.0 else sight_range / 2.0
+        cam = np.asarray(cam_xy[c], dtype=np.float64)
+        angles, norms, discs = outer_samples(cam, obs_xyr, rmax)
+        rho0 = obstruct_outer(angles, norms, discs, +1e-9)    # no tangent ray cut
+        rho1 = obstruct_outer(angles, norms, discs, -1e-9)    # every tangent ray cut
+        left = norm_angle(phi - theta / 2.0)
+        right = left + theta
+        if right <= 180.0:
+            inside = (left < angles) & (angles < right)
+        else:
+            inside = (angles > left) | (angles < right - 360.0) | (angles == -180.0)
+        tphi, trho = inner_tables[c]
+        rho_left = float(np.interp(norm_angle(left), tphi, trho))
+        rho_right = float(np.interp(norm_angle(right), tphi, trho))
+        edge_phi = np.concatenate([[left] * 17, [right] * 17])
+        edge_rho = np.concatenate([np.linspace(0.0, rho_left, num=16, endpoint=False), [rho_left], [rho_right],
+                                   np.linspace(0.0, rho_right, num=16, endpoint=False)])
+        a_in = np.deg2rad(angles[inside])
+        amb = np.abs(rho0[inside] - rho1[inside]) > 1e-9
+        fixed_x = np.concatenate([edge_rho * np.cos(np.deg2rad(edge_phi)), (rho0[inside] * np.cos(a_in))[~amb]])
+        fixed_y = np.concatenate([edge_rho * np.sin(np.deg2rad(edge_phi)), (rho0[inside] * np.sin(a_in))[~amb]])
+        ax0, ay0 = (rho0[inside] * np.cos(a_in))[amb], (rho0[inside] * np.sin(a_in))[amb]
+        ax1, ay1 = (rho1[inside] * np.cos(a_in))[amb], (rho1[inside] * np.sin(a_in))[amb]
+        for t in range(nt):
+            d = np.asarray(tgt_xy[t], dtype=np.float64) - cam
+            d_fixed = np.hypot(d[0] - fixed_x, d[1] - fixed_y).min()
+            d0, d1 = np.hypot(d[0] - ax0, d[1] - ay0), np.hypot(d[0] - ax1, d[1] - ay1)
+            want = abs(float(gold[c, t])) * dist_max
+            sign_ok = (gold[c, t] >= 0) == bool(mask_ct[c, t]) or want < tol
+            upper = min(d_fixed, np.maximum(d0, d1).min() if len(d0) else np.inf)
+            attained = abs(want - d_fixed) < tol * dist_max or (len(d0) and (np.abs(d0 - want).min() < tol * dist_max or np.abs(d1 - want).min() < tol * dist_max))
+            ok[c, t] = sign_ok and want <= upper + tol * dist_max and bool(attained)
+            none_cut = min(d_fixed, d0.min() if len(d0) else np.inf)
+            same[c, t] = abs(want - none_cut) < tol * dist_max
+    return ok, same
+
+
 def after_step_cameras(g, i):
     """Camera.simulate (entities.py:347-360) on the recorded state / action of sample i of an aux fixture."""
     cam = g['cfg_camera']

@@ -172,19 +172,43 @@ def _soft_reference(g, limit):
 
 @pytest.mark.parametrize('name', [n for n in NAMES if 'Navigation' not in n])
 def test_soft_coverage_restatement_matches_the_reference(name):
-    """CPU: the NumPy restatement of compute_soft_coverage_scores (the checker of the CUDA kernel) against the
-    reference's matrices.  The reference decides every exactly tangent ray by rounding noise (DESIGN.md "Tangent
-    rays"), so an entry equals the restatement with those rays all cut or all not cut unless its nearest boundary
-    point is decided by two such rays with different luck (measured: < 1 % of the entries)."""
+    """CPU: the NumPy restatement of compute_soft_coverage_scores (the checker of the CUDA kernel) against ALL of the
+    reference's recorded matrices.  The reference decides every exactly tangent boundary ray by rounding noise
+    (DESIGN.md "Tangent rays"), independently per ray, so a recorded entry need not equal the restatement under one
+    global convention; what is proven instead, entry by entry (``soft_coverage_explained``): the recorded value is the
+    distance to a boundary point that SOME outcome of the tangent rays contains, and no point that every outcome
+    contains is closer.  The share of entries that equal the convention of the CUDA path (no tangent ray cut) is
+    reported and bounded."""
+    from oracle import soft_coverage_ref as sr
+    from oracle.oracle import Oracle
+
     g = gu.load(name)
-    no_cut, cut = _soft_reference(g, 60)
-    gold = g['a_out_soft_matrix'][:len(no_cut)]
-    err = np.minimum(np.abs(no_cut - gold), np.abs(cut - gold))
-    assert (err < 1e-6).mean() > 0.99, (err < 1e-6).mean()
-    assert err.max() < 0.1, err.max()
-    assert (np.abs(no_cut - gold) < 1e-6).mean() > 0.85   # the convention of the CUDA path alone
+    cfg = gu.flat_config(g)
+    nc, rmax = cfg['num_cameras'], cfg['camera_max_sight_range']
+    area_product = cfg['camera_min_viewing_angle'] * rmax ** 2
+    sim = Oracle(cfg, 1)
+    sim.set_state(gu.state_arrays(g, 'a_', 0))   # one episode per fixture: the geometry is that of sample 0
+    tables = [sim.get_fov(0, c) for c in range(nc)]
+    n = int(g['count'])
+    same = total = 0
+    unexplained = []
+    for i in range(n):
+        phi, theta = sr.after_step_cameras(g, i)
+        ok, eq = sr.soft_coverage_explained(g['a_cam_xy'][i], phi, theta, rmax, area_product, g['a_obs_xyr'][i], g['a_out_tgt_xy'][i],
+                                            g['a_out_mask_ct'][i].astype(bool), tables, g['a_out_soft_matrix'][i])
+        same += int(eq.sum())
+        total += ok.size
+        for c, t in np.argwhere(~ok):
+            plain = sr.soft_coverage_matrix(g['a_cam_xy'][i], phi, theta, rmax, area_product, g['a_obs_xyr'][i], g['a_out_tgt_xy'][i],
+                                            g['a_out_mask_ct'][i].astype(bool), tables)[c, t]
+            unexplained.append((i, int(c), int(t), float(theta[c]), float(abs(plain - g['a_out_soft_matrix'][i][c, t]))))
+    # 40 383 of the 40 384 recorded entries are proven.  The one that is not (aux_4v8-9 sample 541, camera 3 at a
+    # viewing angle of exactly 180 degrees, target 3) differs by 7.7e-4 at a value of 4.07 under every outcome of the
+    # tangent rays; its cause is not identified.  More than that, or a larger deviation, fails.
+    assert len(unexplained) <= 1 and all(dev < 1e-3 and theta == 180.0 for *_, theta, dev in unexplained), unexplained
+    assert same / total > 0.85, same / total     # measured: 0.91 (4v8-9), 0.985 (8v8-9), 1.0 without obstacles
     if int(g['cfg_counts'][2]) == 0:
-        np.testing.assert_allclose(no_cut, gold, rtol=0, atol=1e-9)
+        assert same == total
 
 
 @pytest.mark.gpu
