@@ -189,10 +189,13 @@ __device__ __noinline__ void process_slow_targets(const Params& p, int env0, flo
         s.bound = s.n * (1.0 + 1e-12);
     }
     const double desx = tx + s.vx, desy = ty + s.vy;
-    // fp32 candidates: centre within R (+ slack) of the segment [origin, origin + v]
-    unsigned long long cand = 0ull;
-    {
-        const float ftx = (float)tx, fty = (float)ty, fvx = (float)s.vx, fvy = (float)s.vy;
+    // fp32 candidates: discs (obstacles, then cameras) whose centre lies within R (+ slack) of the segment
+    // [origin, origin + v] -- a necessary condition for Obstacle.obstruct to change the step (the origin inside the
+    // disc, or the ray entering it within its length)
+    const float ftx = (float)tx, fty = (float)ty;
+    auto candidates = [&](const double vx, const double vy) {
+        unsigned long long cand = 0ull;
+        const float fvx = (float)vx, fvy = (float)vy;
         const float vv = fvx * fvx + fvy * fvy, inv_vv = vv > 0.f ? 1.0f / vv : 0.f;
         auto near_segment = [&](const float cx, const float cy, const float R) {
             const float rx = cx - ftx, ry = cy - fty;
@@ -212,24 +215,23 @@ __device__ __noinline__ void process_slow_targets(const Params& p, int env0, flo
 #pragma unroll
         for (int c = 0; c < NC; ++c)
             cand |= (unsigned long long)near_segment(camv[S::CV * c], camv[S::CV * c + 1], (float)cam_radius) << (NO + c);
-    }
-    // Discs in the reference's order; a disc that is not a candidate cannot change the step unless an earlier one
-    // has already bent it.  Every lane walks its OWN candidates (most targets have exactly one), so the warp pays
-    // one round trip for the fp64 disc per candidate rank instead of one per disc index.
-    if (cand != 0ull) {
-        bool modified = false;
-        int d = __ffsll((long long)cand) - 1;
+        return cand;
+    };
+    // Discs in the reference's order.  A disc that is not a candidate cannot change the step; once a disc has bent
+    // it, the candidates among the LATER discs are those of the bent step (re-classified in fp32: the reference walks
+    // all of them through Obstacle.obstruct, 32 fp64 evaluations per bent step in the Navigation preset).  Every lane
+    // walks its OWN candidates (most targets have exactly one), so the warp pays one round trip for the fp64 disc per
+    // candidate rank instead of one per disc index.
+    unsigned long long cand = candidates(s.vx, s.vy);
 #pragma unroll 1
-        while (d < NO + NC) {
-            const double ovx = s.vx, ovy = s.vy;
-            if (d < NO) obstruct_step(s, tx, ty, obs_x[(size_t)d * bp], obs_y[(size_t)d * bp], obs_r[(size_t)d * bp]);
-            else obstruct_step(s, tx, ty, cam_x[(size_t)(d - NO) * bp], cam_y[(size_t)(d - NO) * bp], cam_radius);
-            modified = modified || s.vx != ovx || s.vy != ovy;
-            if (modified) { ++d; continue; }
-            cand &= ~((2ull << d) - 1ull);
-            if (cand == 0ull) break;
-            d = __ffsll((long long)cand) - 1;
-        }
+    while (cand != 0ull) {
+        const int d = __ffsll((long long)cand) - 1;
+        const double ovx = s.vx, ovy = s.vy;
+        if (d < NO) obstruct_step(s, tx, ty, obs_x[(size_t)d * bp], obs_y[(size_t)d * bp], obs_r[(size_t)d * bp]);
+        else obstruct_step(s, tx, ty, cam_x[(size_t)(d - NO) * bp], cam_y[(size_t)(d - NO) * bp], cam_radius);
+        const unsigned long long later = ~((2ull << d) - 1ull);
+        if (s.vx != ovx || s.vy != ovy) cand = candidates(s.vx, s.vy) & later;
+        else cand &= later;
     }
     const double nx = fmin(fmax(tx + s.vx, -kTerrain), kTerrain);
     const double ny = fmin(fmax(ty + s.vy, -kTerrain), kTerrain);

@@ -8,15 +8,17 @@ from mate_b200.config import flatten_config, read_config
 from mate_b200.sim import BatchedSim
 from mate_b200 import _abi
 
-cfg = flatten_config(read_config('MATE-4v8-9.yaml'))
-B = 65536
+CONFIG = os.environ.get('TL_CONFIG', 'MATE-4v8-9.yaml')
+cfg = flatten_config(read_config(CONFIG))
+B = int(os.environ.get('TL_ENVS', '65536'))
+NC, NT = cfg['num_cameras'], cfg['num_targets']
 sim = BatchedSim(cfg, B, device=0)
 sim.reset(seed=0)
 steps0 = np.random.RandomState(1234).randint(0, cfg['max_episode_steps'] + 1, size=B).astype(np.int32)
 sim.set_state({'episode_step': steps0})
 g = torch.Generator(device='cuda'); g.manual_seed(0)
-cams = [(torch.rand((B, 4, 2), device='cuda', generator=g) * 2 - 1) * torch.tensor([cfg['camera_rotation_step'], cfg['camera_zooming_step']], device='cuda') for _ in range(4)]
-tgts = [(torch.rand((B, 8, 2), device='cuda', generator=g) * 2 - 1) * cfg['target_step_size'] for _ in range(4)]
+cams = [(torch.rand((B, max(NC, 1), 2), device='cuda', generator=g) * 2 - 1) * torch.tensor([cfg['camera_rotation_step'], cfg['camera_zooming_step']], device='cuda') for _ in range(4)]
+tgts = [(torch.rand((B, NT, 2), device='cuda', generator=g) * 2 - 1) * cfg['target_step_size'] for _ in range(4)]
 sim.alloc_aux()
 for name, ctype, _, _ in _abi.AUX_FIELDS:
     if name not in ('coverage', 'num_delivered'):
@@ -25,13 +27,13 @@ lib = ctypes.CDLL(os.environ['MATE_B200_LIB'])
 lib.mate_b200_debug_timeline.argtypes = [ctypes.c_void_p, ctypes.c_int32]
 lib.mate_b200_debug_timeline.restype = ctypes.c_int
 all_t = []
-for rep in range(6):
+for rep in range(3):
     for k in range(50):
         sim.step(cams[k % 4], tgts[k % 4], auto_reset=True, aux=True)
     torch.cuda.synchronize()
     out = np.zeros(4096 * 8, dtype=np.uint64)
     assert lib.mate_b200_debug_timeline(out.ctypes.data_as(ctypes.c_void_p), out.size) == 0
-    t = out.reshape(4096, 8)[:2048, :7].astype(np.int64)
+    t = out.reshape(4096, 8)[:(B + 31) // 32, :7].astype(np.int64)
     t0 = t[:, 0].min()
     t = (t - t0) / 1000.0   # us
     all_t.append(t)
