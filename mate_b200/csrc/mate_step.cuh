@@ -159,11 +159,21 @@ __device__ __forceinline__ int fov_reach32(float cx, float cy, float rs2, float 
 // the discs that can modify the step (Obstacle.obstruct changes a ray only if the ray meets the disc, i.e.
 // the disc centre is within R of the segment); only those go through the fp64 Obstacle.obstruct.
 template <int NC, int NT, int NO, class S>
-__device__ __noinline__ void process_slow_targets(const Params& p, int env0, float* val, const uint16_t* queue, int base, int n) {
+__device__ __noinline__ void process_slow_targets(const Params& p, int env0, float* val, const uint16_t* queue, int base, int n,
+                                                  const uint32_t (&near)[NT]) {
     const int lane = threadIdx.x & 31;
-    if (lane >= n) return;
-    const uint32_t item = queue[base + lane];
+    const bool live = lane < n;
+    const uint32_t item = live ? queue[base + lane] : 0u;
     const int src = item >> 8, t = item & 0xFF;
+    // the discs within reach of this target's step, from the lane that owns its environment (called by all 32 lanes)
+    constexpr bool REACH_MASKS = NO > 16 && NO + NC <= 32;
+    uint32_t reach_set = 0xffffffffu;
+    if (REACH_MASKS) {
+        reach_set = 0u;
+#pragma unroll
+        for (int k = 0; k < NT; ++k) { const uint32_t m = __shfl_sync(0xffffffffu, near[k], src); if (k == t) reach_set = m; }
+    }
+    if (!live) return;
     const int env = env0 + src;
     const bool env_ok = env < p.num_envs;
     const int er = env_ok ? env : p.num_envs - 1;
@@ -204,6 +214,19 @@ __device__ __noinline__ void process_slow_targets(const Params& p, int env0, flo
             const float reach = R * 1.0001f + 0.02f;
             return !(ex * ex + ey * ey > reach * reach);
         };
+        if (REACH_MASKS) {   // only the discs within reach of the step (a bent step is never longer than the straight one)
+            uint32_t rm = reach_set;
+#pragma unroll 1
+            while (rm != 0u) {
+                const int d = __ffs(rm) - 1;
+                rm &= rm - 1u;
+                bool hit;
+                if (d < NO) { const float4 ob = obs_f4[(size_t)d * bp]; hit = near_segment(ob.x, ob.y, ob.z); }
+                else hit = near_segment(camv[S::CV * (d - NO)], camv[S::CV * (d - NO) + 1], (float)cam_radius);
+                cand |= (unsigned long long)hit << d;
+            }
+            return cand;
+        }
         float4 nxt = make_float4(0.f, 0.f, 0.f, 0.f);
         if (NO > 0) nxt = obs_f4[0];
 #pragma unroll 4
@@ -1081,6 +1104,12 @@ mate_step_kernel2(const __grid_constant__ Params p) {
     }
     {   // Target.simulate (entities.py:645-668): fast path = no disc within reach of the step
         uint32_t slow = 0;     // targets that may touch a disc: re-simulated exactly below
+        // per target, the discs (obstacles, then cameras) within reach of its step: the exact re-simulation only looks at those
+        // (worth its registers where there are many discs: Navigation's 32; with 9 the full scan is as fast, measured)
+        constexpr bool REACH_MASKS = NO > 16 && NO + NC <= 32;
+        uint32_t near[NT];
+#pragma unroll
+        for (int t = 0; t < NT; ++t) near[t] = 0u;
         if (mode == MODE_STEP) {
             // fp32 broad phase on the old locations: a disc farther than step_size + R (+ slack for fp32
             // rounding) cannot touch the step
@@ -1096,7 +1125,9 @@ mate_step_kernel2(const __grid_constant__ Params p) {
 #pragma unroll
                 for (int t = 0; t < NT; ++t) {
                     const float dx = ob.x - otx[t], dy = ob.y - oty[t];
-                    slow |= (uint32_t)(!(dx * dx + dy * dy > reach2)) << t;
+                    const uint32_t hit = (uint32_t)(!(dx * dx + dy * dy > reach2));
+                    slow |= hit << t;
+                    if (REACH_MASKS) near[t] |= hit << o;
                 }
             }
             const float reach_c = fb + (float)p.cam_radius, reach_c2 = reach_c * reach_c;
@@ -1106,7 +1137,9 @@ mate_step_kernel2(const __grid_constant__ Params p) {
 #pragma unroll
                 for (int t = 0; t < NT; ++t) {
                     const float dx = cx - otx[t], dy = cy - oty[t];
-                    slow |= (uint32_t)(!(dx * dx + dy * dy > reach_c2)) << t;
+                    const uint32_t hit = (uint32_t)(!(dx * dx + dy * dy > reach_c2));
+                    slow |= hit << t;
+                    if (REACH_MASKS) near[t] |= hit << ((NO + c) & 31);
                 }
             }
         }
@@ -1167,7 +1200,7 @@ mate_step_kernel2(const __grid_constant__ Params p) {
                 if (count >= 32 || (!more && count > 0)) {
                     const int n = min(count, 32);
                     count -= n;
-                    process_slow_targets<NC, NT, NO, S>(p, env0, val, queue, count, n);
+                    process_slow_targets<NC, NT, NO, S>(p, env0, val, queue, count, n, near);
                     __syncwarp();
                 }
                 if (!more && count == 0) break;
