@@ -32,7 +32,9 @@ static int fail(int code, const std::string& msg) {
 
 // ---- supported entity-count shapes (compile-time specialisations of the kernel) ------------
 // All 17 presets of the reference (mate/assets/MATE-*.yaml).
-#ifdef MATE_DEV_SHAPE   // development builds: a single specialisation (scratch/build_variant.sh)
+#if defined(MATE_DEV_SHAPE_OTHERS)   // development builds: the other BASELINE shapes
+#define MATE_SHAPES(X) X(4, 2, 9) X(4, 8, 0) X(8, 8, 9) X(0, 8, 32)
+#elif defined(MATE_DEV_SHAPE)   // development builds: a single specialisation (scratch/build_variant.sh)
 #define MATE_SHAPES(X) X(4, 8, 9)
 #else
 #define MATE_SHAPES(X)                                                                        \
