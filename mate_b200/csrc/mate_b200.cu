@@ -50,7 +50,7 @@ struct KernelInfo {
     int envs_per_cta, smem_bytes, dc, dt, epw;
     cudaError_t (*prepare)();
     void (*launch_fov)(const Params&, const int32_t*, const int32_t*, const double*, double*, long long, cudaStream_t);
-    void (*launch_soft)(const Params&, const uint8_t*, const uint8_t*, float*, cudaStream_t);
+    void (*launch_soft)(const Params&, const uint8_t*, const uint8_t*, double*, float*, cudaStream_t);
 };
 
 template <int NC, int NT, int NO>
@@ -66,9 +66,10 @@ static void launch_fov_shape(const Params& p, const int32_t* env, const int32_t*
     fov_range_kernel<NC, NO><<<(unsigned)((n + 127) / 128), 128, 0, stream>>>(p, env, camera, angle, out, n);
 }
 template <int NC, int NT, int NO>
-static void launch_soft_shape(const Params& p, const uint8_t* mask_ct, const uint8_t* done, float* out, cudaStream_t stream) {
+static void launch_soft_shape(const Params& p, const uint8_t* mask_ct, const uint8_t* done, double* edges, float* out, cudaStream_t stream) {
     const long long warps = (long long)p.num_envs * (NC > 0 ? NC : 1);
-    soft_coverage_kernel<NC, NT, NO><<<(unsigned)((warps + 3) / 4), 128, 0, stream>>>(p, mask_ct, done, out);
+    soft_edges_kernel<NC, NO><<<(unsigned)((warps * 2 + 127) / 128), 128, 0, stream>>>(p, done, edges);
+    soft_coverage_kernel<NC, NT, NO><<<(unsigned)((warps + 3) / 4), 128, 0, stream>>>(p, mask_ct, done, edges, out);
 }
 template <int NC, int NT, int NO>
 static cudaError_t prepare_shape2() {
@@ -122,6 +123,7 @@ struct MateSim {
     Params* d_next = nullptr; // device copy of next_base (Params::next of the step launches)
     cudaStream_t side = nullptr;
     cudaEvent_t side_event = nullptr;
+    double* soft_edges = nullptr;   // scratch of mate_b200_soft_coverage, allocated on first use
     int refill_mode = 0;      // 0 = off, 1 = side stream every refill_period steps, 2 = same stream after every step (tests)
     int refill_period = 512;
     long long steps_since_refill = 0;
@@ -295,6 +297,7 @@ extern "C" int mate_b200_destroy(MateSim* sim) {
     }
     if (sim->side) { cudaStreamSynchronize(sim->side); cudaStreamDestroy(sim->side); }
     if (sim->side_event) cudaEventDestroy(sim->side_event);
+    cudaFree(sim->soft_edges);
     cudaFree(sim->next_block);
     cudaFree(sim->d_next);
     cudaFree(sim->state_block);
@@ -411,8 +414,10 @@ extern "C" int mate_b200_soft_coverage(MateSim* sim, const uint8_t* mask_ct, con
     if (!sim || !mask_ct || !soft_matrix) return fail(MATE_EINVAL, "null argument");
     if (sim->cfg.num_cameras == 0) return fail(MATE_EINVAL, "the configuration has no cameras");
     CUDA_TRY(cudaSetDevice(sim->device));
-    sim->kernel.launch_soft(sim->base, mask_ct, done, soft_matrix, (cudaStream_t)stream);
-    sim->launches += 1;
+    if (!sim->soft_edges)   // ranges at the two sector edges of every camera, filled by the pre-pass
+        CUDA_TRY(cudaMalloc(&sim->soft_edges, sizeof(double) * 2 * (size_t)sim->num_envs * sim->cfg.num_cameras));
+    sim->kernel.launch_soft(sim->base, mask_ct, done, sim->soft_edges, soft_matrix, (cudaStream_t)stream);
+    sim->launches += 2;
     cudaError_t err = cudaGetLastError();
     if (err != cudaSuccess) return fail(MATE_ECUDA, std::string("soft coverage launch: ") + cudaGetErrorString(err));
     return MATE_OK;

@@ -343,17 +343,53 @@ __global__ void aux_terms_kernel(const MateStepAux ax, const float* __restrict__
 // "Tangent rays").  Environments that were auto-reset in the last step get zeros (their state already belongs to
 // the next episode).
 // =============================================================================================
+// Pre-pass of the soft coverage: the ranges of the inner polyline at the two sector edges of every camera
+// (boundary_between uses sight_range_at for its first and last point, entities.py:507-511, 536-541), one THREAD per
+// (environment, camera, side).  Inside the warp-per-camera kernel below this scalar routine (~3000 dependent fp64
+// instructions) was executed by all 32 lanes for two values and set the kernel's time: 5.9 ms at 65 536 environments.
+template <int NC, int NO>
+__global__ void soft_edges_kernel(const Params p, const uint8_t* __restrict__ done, double* __restrict__ edges) {
+    constexpr int NCX = NC > 0 ? NC : 1;
+    const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;   // ((environment, camera), side)
+    if (q >= (long long)p.num_envs * NCX * 2) return;
+    const int side = (int)(q & 1);
+    const long long item = q >> 1;
+    const int e = (int)(item / NCX), c = (int)(item - (long long)e * NCX);
+    if (done != nullptr && done[e] != 0) { edges[q] = 0.0; return; }
+    const size_t bp = p.bpad;
+    const double cx = p.cam_x[(size_t)c * bp + e], cy = p.cam_y[(size_t)c * bp + e];
+    const double phi = p.cam_phi[(size_t)c * bp + e], theta = p.cam_theta[(size_t)c * bp + e];
+    const double left = normalize_angle(phi - theta * 0.5);
+    const double a = normalize_angle(side ? left + theta : left);
+    double rho = p.cam_rmax;
+    if (NO > 0) {
+        bool collapsed = false;   // the camera inside a disc of its set: every ray has norm 0 (entities.py:378-388)
+        for (int o = 0; o < NO; ++o) {
+            const double ox = p.obs_x[(size_t)o * bp + e] - cx, oy = p.obs_y[(size_t)o * bp + e] - cy, orad = p.obs_r[(size_t)o * bp + e];
+            const double od = sqrt(ox * ox + oy * oy);
+            collapsed = collapsed || (od < p.cam_rmax + orad && orad > od);
+        }
+        double sn, cs;
+        sincospi(a * (1.0 / 180.0), &sn, &cs);
+        rho = collapsed ? 0.0 : sight_range_at<NO>(ObsRef{p.obs_x + e, p.obs_y + e, p.obs_r + e, bp}, cx, cy, p.cam_rmax, a, cs, sn);
+    }
+    edges[q] = rho;
+}
+
 template <int NC, int NT, int NO>
 __global__ void soft_coverage_kernel(const Params p, const uint8_t* __restrict__ mask_ct, const uint8_t* __restrict__ done,
-                                     float* __restrict__ out) {
+                                     const double* __restrict__ edges, float* __restrict__ out) {
     constexpr int NCX = NC > 0 ? NC : 1, NOX = NO > 0 ? NO : 1;
     constexpr uint32_t FULL = 0xffffffffu;
     constexpr int WARPS = 4;   // launch: 128 threads per block
     // per warp: the discs of the camera's obstacle set {x, y, R, distance, bearing, half opening angle} relative to
     // the camera; read by all lanes at the same address (broadcast)
-    __shared__ double sdisc[WARPS][NOX][6];
+    // ... plus the end points of its two 21-point edge segments {near x, near y, far x, far y} x {left, right}
+    __shared__ double sdisc[WARPS][NOX][14];
+    __shared__ int soffs[WARPS][NOX + 1];   // prefix sums of the discs' sample counts (dense batching of (b))
     const int lane = threadIdx.x & 31;
-    double (*disc)[6] = sdisc[(threadIdx.x >> 5) & (WARPS - 1)];
+    double (*disc)[14] = sdisc[(threadIdx.x >> 5) & (WARPS - 1)];
+    int* offs = soffs[(threadIdx.x >> 5) & (WARPS - 1)];
     const long long item = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;   // (environment, camera)
     if (item >= (long long)p.num_envs * NCX) return;
     const int e = (int)(item / NCX), c = (int)(item - (long long)e * NCX);
@@ -374,8 +410,21 @@ __global__ void soft_coverage_kernel(const Params p, const uint8_t* __restrict__
         member = od < rmax + orad;
         inside_disc = member && orad > od;
         disc[lane][0] = ox; disc[lane][1] = oy; disc[lane][2] = orad; disc[lane][3] = od;
-        disc[lane][4] = atan2(oy, ox) * kRad2Deg;
-        disc[lane][5] = od > orad ? asin(orad / od) * kRad2Deg : 90.0;
+        const double ang = atan2(oy, ox) * kRad2Deg, half = od > orad ? asin(orad / od) * kRad2Deg : 90.0;
+        disc[lane][4] = ang;
+        disc[lane][5] = half;
+        if (member) {   // the two edge segments of entities.py:431-448: from near_rho on the tangent to rmax 0.01 degrees beside it
+            const double near_rho = fmin(rmax, sqrt(od * od + orad * orad));
+#pragma unroll
+            for (int side = 0; side < 2; ++side) {
+                const double edge = side ? ang + half : ang - half, far_angle = side ? ang + half + 0.01 : ang - half - 0.01;
+                double ns, nc_, fs, fc;
+                sincospi(normalize_angle(edge) * (1.0 / 180.0), &ns, &nc_);
+                sincospi(normalize_angle(far_angle) * (1.0 / 180.0), &fs, &fc);
+                disc[lane][6 + 4 * side] = near_rho * nc_; disc[lane][7 + 4 * side] = near_rho * ns;
+                disc[lane][8 + 4 * side] = rmax * fc; disc[lane][9 + 4 * side] = rmax * fs;
+            }
+        }
     }
     const uint32_t members = __ballot_sync(FULL, member);
     const bool collapsed = __any_sync(FULL, inside_disc);   // entities.py:378-388: every ray has norm 0
@@ -405,10 +454,9 @@ __global__ void soft_coverage_kernel(const Params p, const uint8_t* __restrict__
     // One sample ray (angle in degrees, normalised; norm): cut at the far side of the discs it crosses
     // (Obstacle.obstruct(outer=True)), then visit.  A ray can only cross a disc whose bearing is within the disc's
     // half opening angle of the ray: everything else is rejected on two shared-memory reads.
-    auto sample_if = [&](const bool live, const double a, const double norm) {
+    auto sample_dir = [&](const bool live, const double a, const double norm, double cs, double sn, const bool have_dir) {
         if (!live) return;
-        double sn, cs;
-        sincospi(a * (1.0 / 180.0), &sn, &cs);
+        if (!have_dir) sincospi(a * (1.0 / 180.0), &sn, &cs);
         double n = collapsed ? 0.0 : norm;
         uint32_t m = members;
         while (m != 0u) {
@@ -427,59 +475,72 @@ __global__ void soft_coverage_kernel(const Params p, const uint8_t* __restrict__
         }
         visit(n, cs, sn);
     };
-    // (a) the integer-degree grid (entities.py:339-342)
-    for (int k0 = 0; k0 < 360; k0 += 32) {
-        const int k = k0 + lane;
-        const double a = (double)(k < 360 ? k : 0) - 180.0;
-        sample_if(k < 360 && in_sector(a), a, rmax);
+    auto sample_if = [&](const bool live, const double a, const double norm) { sample_dir(live, a, norm, 0.0, 0.0, false); };
+    // (a) the integer-degree grid (entities.py:339-342): only the degrees inside the sector are enumerated (a
+    //     sector of theta degrees holds about theta of them: 1-6 passes of 32 instead of 12)
+    {
+        const int k_first = (int)floor(left) - 1;                 // a little more than the open interval (left, right); in_sector decides
+        const int count = (int)ceil(theta) + 3;
+        for (int j0 = 0; j0 < count; j0 += 32) {
+            const int j = j0 + lane;
+            int k = k_first + j;                                   // integer degree, may run past +180
+            if (k >= 180) k -= 360;
+            const double a = (double)k;
+            // every degree at most once: the window is shorter than 360 unless theta = 180 + slack, where j < 360 caps it
+            sample_if(j < count && j < 360 && in_sector(a), a, rmax);
+        }
     }
-    // (b) per obstacle of the set: lattice rays at max_rho and the two edge segments (entities.py:419-448)
+    // (b) per obstacle of the set: lattice rays at max_rho and the two edge segments (entities.py:419-448).  The
+    //     samples of ALL relevant discs are enumerated densely, 32 per pass (17-40 lattice rays + 42 edge points per
+    //     disc would otherwise leave most lanes of three passes per disc idle)
     if (!collapsed) {
-        uint32_t m = members;
-        while (m != 0u) {
-            const int o = __ffs(m) - 1;
-            m &= m - 1u;
+        if (lane == 0) {
+            int total = 0;
+            for (int o = 0; o < NO; ++o) {
+                offs[o] = total;
+                if (!((members >> o) & 1u)) continue;
+                const double ang = disc[o][4], half = disc[o][5];
+                // angular distance between the disc's bearing and the sector axis vs. the two half widths (+ slack)
+                if (fabs(normalize_angle(ang - phi)) > half + theta * 0.5 + 0.02) continue;
+                const int two_half = (int)(2.0 * half);
+                total += (two_half > 16 ? two_half : 16) + 1 + 42;
+            }
+            offs[NO] = total;
+        }
+        __syncwarp();
+        const int total = offs[NO];
+        for (int s0 = 0; s0 < total; s0 += 32) {
+            const int sidx = s0 + lane;
+            const bool live = sidx < total;
+            int o = 0;
+            if (live) { while (o + 1 < NO && offs[o + 1] <= sidx) ++o; }   // offs is non-decreasing; discs without samples have an empty range
+            const int j = sidx - offs[o];
             const double R = disc[o][2], d = disc[o][3], ang = disc[o][4], half = disc[o][5];
             const double aL = ang - half, aR = ang + half;
-            {   // angular distance between the disc's bearing and the sector axis vs. the two half widths (+ slack)
-                const double off = fabs(normalize_angle(ang - phi));
-                if (off > half + theta * 0.5 + 0.02) continue;
-            }
-            const double max_rho = fmin(rmax, d + R);
             const int two_half = (int)(2.0 * half);
             const int nlat = two_half > 16 ? two_half : 16;
-            const double step = (aR - aL) / (double)nlat;   // np.linspace
-            for (int j0 = 0; j0 <= nlat; j0 += 32) {
-                const int j = j0 + lane;
+            if (j <= nlat) {        // lattice ray
+                const double step = (aR - aL) / (double)nlat;   // np.linspace
                 const double a = normalize_angle(j >= nlat ? aR : ((double)j * step + aL));
-                sample_if(j <= nlat && in_sector(a), a, max_rho);
-            }
-            const double near_rho = fmin(rmax, sqrt(d * d + R * R));
-            for (int j0 = 0; j0 < 42; j0 += 32) {
-                const int j = j0 + lane;
-                const bool is_right = j >= 21;
-                const int k = is_right ? j - 21 : j;
-                const double edge = is_right ? aR : aL, far_angle = is_right ? aR + 0.01 : aL - 0.01;
-                double ns, nc_, fs, fc;
-                sincospi(normalize_angle(edge) * (1.0 / 180.0), &ns, &nc_);
-                sincospi(normalize_angle(far_angle) * (1.0 / 180.0), &fs, &fc);
+                sample_if(live && in_sector(a), a, fmin(rmax, d + R));
+            } else {                // point k of an edge segment
+                const int q = j - nlat - 1;
+                const int side = q >= 21 ? 1 : 0, k = side ? q - 21 : q;
                 const double t = k >= 20 ? 1.0 : (double)k * 0.05;
-                const double vx = (1.0 - t) * (near_rho * nc_) + t * (rmax * fc), vy = (1.0 - t) * (near_rho * ns) + t * (rmax * fs);
+                const double vx = (1.0 - t) * disc[o][6 + 4 * side] + t * disc[o][8 + 4 * side];
+                const double vy = (1.0 - t) * disc[o][7 + 4 * side] + t * disc[o][9 + 4 * side];
                 const double a = atan2(vy, vx) * kRad2Deg;
-                sample_if(j < 42 && in_sector(a), a, sqrt(vx * vx + vy * vy));
+                const double norm = sqrt(vx * vx + vy * vy);
+                // the ray's direction is the point's own direction (the reference goes through (cos, sin)(atan2): 1 ulp)
+                sample_dir(live && in_sector(a), a, norm, vx / norm, vy / norm, true);
             }
         }
     }
     // (c) the two sector edges: end point from the INNER polyline (boundary_between uses sight_range_at), then 16
     //     points from the camera to it (auxiliary_camera_rewards.py:203-214)
     {
-        const double a_mine = normalize_angle(lane < 16 ? left : right);
         double sn, cs;
-        sincospi(a_mine * (1.0 / 180.0), &sn, &cs);
-        double rho_mine = rmax;
-        if (collapsed) rho_mine = 0.0;
-        else if (NO > 0) rho_mine = sight_range_at<NO>(ObsRef{p.obs_x + e, p.obs_y + e, p.obs_r + e, bp}, cx, cy, rmax, a_mine, cs, sn);
-        const double rho_l = __shfl_sync(FULL, rho_mine, 0), rho_r = __shfl_sync(FULL, rho_mine, 16);
+        const double rho_l = edges[item * 2], rho_r = edges[item * 2 + 1];   // soft_edges_kernel
         for (int q0 = 0; q0 < 34; q0 += 32) {
             const int q = q0 + lane;
             if (q < 34) {
