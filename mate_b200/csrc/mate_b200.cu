@@ -34,7 +34,7 @@ static int fail(int code, const std::string& msg) {
 // All 17 presets of the reference (mate/assets/MATE-*.yaml).
 #if defined(MATE_DEV_SHAPE_OTHERS)   // development builds: the other BASELINE shapes
 #define MATE_SHAPES(X) X(4, 2, 9) X(4, 8, 0) X(8, 8, 9) X(0, 8, 32)
-#elif defined(MATE_DEV_SHAPE)   // development builds: a single specialisation (scratch/build_variant.sh)
+#elif defined(MATE_DEV_SHAPE)   // development builds: a single specialisation (profiles/tools/build_variant.sh)
 #define MATE_SHAPES(X) X(4, 8, 9)
 #else
 #define MATE_SHAPES(X)                                                                        \
@@ -858,7 +858,7 @@ extern "C" int mate_b200_episode_stats(MateSim* sim, float* out16, int32_t reset
     return MATE_OK;
 }
 
-#ifdef MATE_DEV_TIMELINE   // development builds only (scratch/timeline.py): per-tile phase time stamps of the last step launch
+#ifdef MATE_DEV_TIMELINE   // development builds only (profiles/tools/timeline.py): per-tile phase time stamps of the last step launch
 extern "C" int mate_b200_debug_timeline(unsigned long long* out, int32_t count) {
     CUDA_TRY(cudaDeviceSynchronize());
     CUDA_TRY(cudaMemcpyFromSymbol(out, mate::g_timeline, sizeof(unsigned long long) * (size_t)count));

@@ -54,7 +54,7 @@
 
 namespace mate {
 
-#ifdef MATE_DEV_TIMELINE   // development builds only: per-tile phase time stamps (scratch/timeline.py)
+#ifdef MATE_DEV_TIMELINE   // development builds only: per-tile phase time stamps (profiles/tools/timeline.py)
 __device__ unsigned long long g_timeline[4096 * 8];
 __device__ __forceinline__ void tl_mark(const int env0, const int k) {
     if ((threadIdx.x & 31) == 0 && (env0 >> 5) < 4096) {
