@@ -103,27 +103,43 @@ __global__ void greedy_target_kernel(const Params p, const int nt, double* __res
 
 // =============================================================================================
 // GreedyCameraAgent (mate/agents/greedy.py:14-232) for the camera team of every environment, driven like
-// MultiTarget drives its opponents (observe -> communicate -> act).  One thread = one environment.  Per camera the
-// memory holds what the reference agent keeps between steps: the remembered public state of every target, the
-// time-to-forget counters, never_loaded, the previous action, the communication delays per teammate, the set of
-// known teammates and whether the agent's own state is still to be sent (first step after reset).  The
-// peer-to-peer messages of one step (teammate state, tracked target states filtered by the recipient's range) live
-// in two small per-thread tables between the send and the receive phase.
+// MultiTarget drives its opponents (observe -> communicate -> act).  One THREAD = one camera agent; the agents of an
+// environment are neighbouring lanes of a warp (Nc divides 32 for every preset).  Per camera the memory holds what the
+// reference agent keeps between steps: the remembered public state of every target, the time-to-forget counters,
+// never_loaded, the previous action, the communication delays per teammate, the set of known teammates and whether the
+// agent's own state is still to be sent (first step after reset).  (Round 1: one thread per environment walked its
+// 4 cameras one after the other.  Staging a warp's 32 agent memories in shared memory was measured too: 58 KB per
+// block leave 12 warps per SM for a kernel whose time is the latency of fp64 chains, 0.26 ms.)  The peer-to-peer messages of a step (teammate
+// state, tracked target states filtered by the recipient's range; environment.py:1249-1269 routes them through the
+// message queues) are two registers of the sender, read by the recipients with warp shuffles between the send and
+// the receive phase.
 // Layout per camera (doubles): [4 Nt] memory (x, y, sight range, is_loaded) | [Nt] time2forget | [Nt] never_loaded |
 // [2] previous action | [Nc] communication delay | neighbours (bit set) | has_state_message.
 // =============================================================================================
 __host__ __device__ inline int camera_agent_memory(int nc, int nt) { return 6 * nt + nc + 4; }
 
-__global__ void greedy_camera_kernel(const Params p, const int nc, const int nt, double* __restrict__ memory,
-                                     const uint8_t* __restrict__ tracked, const uint8_t* __restrict__ reset_mask,
-                                     const unsigned long long seed, const unsigned long long serial,
-                                     const MateCameraAgentReplay replay, float* __restrict__ cam_act) {
+constexpr int kCameraAgentThreads = 128;
+
+__global__ void __launch_bounds__(kCameraAgentThreads)
+greedy_camera_kernel(const Params p, const int nc, const int nt, double* __restrict__ memory,
+                     const uint8_t* __restrict__ tracked, const uint8_t* __restrict__ reset_mask,
+                     const unsigned long long seed, const unsigned long long serial,
+                     const MateCameraAgentReplay replay, float* __restrict__ cam_act) {
     constexpr int MAXN = 8;
+    constexpr uint32_t FULL = 0xffffffffu;
     constexpr double kMemoryPeriod = 25.0, kRangeFactor = 1.1;   // greedy.py:22, 32
-    const int e = blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= p.num_envs) return;
-    const size_t bp = p.bpad;
     const int M = camera_agent_memory(nc, nt);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const long long total = (long long)p.num_envs * nc;
+    const long long first = ((long long)blockIdx.x * kCameraAgentThreads + warp * 32);   // first agent of this warp
+    const long long agent = first + lane;
+    const bool live = agent < total;
+    const uint32_t active = __ballot_sync(FULL, live);          // whole environments: B * Nc agents, Nc divides 32
+    if (!live) return;
+    const long long ag = agent;
+    const int e = (int)(ag / nc), c = (int)(ag - (long long)e * nc);
+    const int lane0 = lane - c;                                  // lane of camera 0 of this environment
+    const size_t bp = p.bpad;
     const bool reset = reset_mask != nullptr && reset_mask[e] != 0;
     const RngKey key{seed, (uint32_t)(p.env_index_base + e), 0x4341474Eu /* 'CAGN' */};
     const uint32_t draw = (uint32_t)serial * 64u;
@@ -135,13 +151,13 @@ __global__ void greedy_camera_kernel(const Params p, const int nc, const int nt,
         const uint32_t tp = p.tgt_pack[(size_t)t * bp + e];
         loaded |= (uint32_t)(tp_goal(tp) >= 0 && tp_weight(tp) > 0) << t;
     }
-    double cx[MAXN], cy[MAXN];
-    for (int c = 0; c < nc; ++c) { cx[c] = p.cam_x[(size_t)c * bp + e]; cy[c] = p.cam_y[(size_t)c * bp + e]; }
-    uint8_t msg_state[MAXN], msg_targets[MAXN][MAXN];   // msg_state[sender] bit recipient, msg_targets[sender][recipient]
-    // observe -> process_messages (greedy.py:104-115); send_responses (greedy.py:156-194)
-    for (int c = 0; c < nc; ++c) {
-        double* m = memory + ((size_t)e * nc + c) * M;
-        double* mem = m, *t2f = m + 4 * nt, *never = m + 5 * nt, *prev = m + 6 * nt, *delay = m + 6 * nt + 2;
+    const double my_x = p.cam_x[(size_t)c * bp + e], my_y = p.cam_y[(size_t)c * bp + e];
+    double* const m = memory + (size_t)ag * M;
+    double* const mem = m, *t2f = m + 4 * nt, *never = m + 5 * nt, *prev = m + 6 * nt, *delay = m + 6 * nt + 2;
+    // ---- observe -> process_messages (greedy.py:104-115); send_responses (greedy.py:156-194)
+    uint32_t msg_state = 0;                 // bit k: my state goes to camera k
+    unsigned long long msg_targets = 0ull;  // byte k: the tracked targets I report to camera k
+    {
         uint32_t seen = 0;
         for (int t = 0; t < nt; ++t) seen |= (uint32_t)(tracked[((size_t)e * nc + c) * nt + t] != 0) << t;
         if (reset) {   // reset(observation), greedy.py:44-66: untracked targets read as zeros in the observation
@@ -167,42 +183,37 @@ __global__ void greedy_camera_kernel(const Params p, const int nc, const int nt,
         }
         const uint32_t neighbours = (uint32_t)m[6 * nt + 2 + nc];
         const bool has_state = m[6 * nt + 3 + nc] != 0.0;
-        msg_state[c] = 0;
-        for (int k = 0; k < nc; ++k) {
-            msg_targets[c][k] = 0;
-            delay[k] = fmax(delay[k] - 1.0, 0.0);
-        }
-        if (has_state || seen != 0u) {
-            for (int k = 0; k < nc; ++k) {
-                if (k == c || delay[k] > 0.0) continue;
-                uint32_t targets = 0;
-                if (seen != 0u && ((neighbours >> k) & 1u)) {   // the recipient's range (all cameras share max_sight_range)
-                    for (int t = 0; t < nt; ++t) {
-                        const double dx = tx[t] - cx[k], dy = ty[t] - cy[k];
-                        if (((seen >> t) & 1u) && sqrt(dx * dx + dy * dy) < threshold) targets |= 1u << t;
-                    }
-                }
-                if (has_state || targets != 0u) {
-                    msg_state[c] |= (uint8_t)(has_state ? (1u << k) : 0u);
-                    msg_targets[c][k] = (uint8_t)targets;
-                    int d;   // np_random.randint(memory_period // 4, 2 * memory_period)
-                    if (replay.delay) d = replay.delay[((size_t)e * nc + c) * nc + k];
-                    else d = 6 + (int)rng_below(key, STREAM_AGENT_DELAY, draw + (uint32_t)(c * MAXN + k), 44u);
-                    delay[k] = (double)d;
+        for (int k = 0; k < nc; ++k) delay[k] = fmax(delay[k] - 1.0, 0.0);
+        for (int k = 0; k < nc; ++k) {      // every lane takes part in the shuffles; the recipient's location comes from its lane
+            const double kx = __shfl_sync(active, my_x, lane0 + k), ky = __shfl_sync(active, my_y, lane0 + k);
+            if (!(has_state || seen != 0u) || k == c || delay[k] > 0.0) continue;
+            uint32_t targets = 0;
+            if (seen != 0u && ((neighbours >> k) & 1u)) {   // the recipient's range (all cameras share max_sight_range)
+                for (int t = 0; t < nt; ++t) {
+                    const double dx = tx[t] - kx, dy = ty[t] - ky;
+                    if (((seen >> t) & 1u) && sqrt(dx * dx + dy * dy) < threshold) targets |= 1u << t;
                 }
             }
-            m[6 * nt + 3 + nc] = 0.0;
+            if (has_state || targets != 0u) {
+                msg_state |= has_state ? (1u << k) : 0u;
+                msg_targets |= (unsigned long long)targets << (8 * k);
+                int d;   // np_random.randint(memory_period // 4, 2 * memory_period)
+                if (replay.delay) d = replay.delay[((size_t)e * nc + c) * nc + k];
+                else d = 6 + (int)rng_below(key, STREAM_AGENT_DELAY, draw + (uint32_t)(c * MAXN + k), 44u);
+                delay[k] = (double)d;
+            }
         }
+        if (has_state || seen != 0u) m[6 * nt + 3 + nc] = 0.0;
     }
-    // receive_responses (greedy.py:196-232) + act (greedy.py:68-102)
-    for (int c = 0; c < nc; ++c) {
-        double* m = memory + ((size_t)e * nc + c) * M;
-        double* mem = m, *t2f = m + 4 * nt, *never = m + 5 * nt, *prev = m + 6 * nt;
+    // ---- receive_responses (greedy.py:196-232) + act (greedy.py:68-102)
+    {
         uint32_t neighbours = (uint32_t)m[6 * nt + 2 + nc];
         for (int s = 0; s < nc; ++s) {
+            const uint32_t s_state = __shfl_sync(active, msg_state, lane0 + s);
+            const unsigned long long s_targets = __shfl_sync(active, msg_targets, lane0 + s);
             if (s == c) continue;
-            if ((msg_state[s] >> c) & 1u) neighbours |= 1u << s;   // greedy.py:219 adds the sender unconditionally
-            const uint32_t targets = msg_targets[s][c];
+            if ((s_state >> c) & 1u) neighbours |= 1u << s;   // greedy.py:219 adds the sender unconditionally
+            const uint32_t targets = (uint32_t)(s_targets >> (8 * c)) & 0xFFu;
             for (int t = 0; t < nt; ++t) {
                 if (!((targets >> t) & 1u)) continue;
                 mem[4 * t] = tx[t]; mem[4 * t + 1] = ty[t]; mem[4 * t + 2] = p.tgt_sight_range; mem[4 * t + 3] = (double)((loaded >> t) & 1u);
@@ -216,7 +227,7 @@ __global__ void greedy_camera_kernel(const Params p, const int nc, const int nt,
         double best = 0.0;
         for (int t = 0; t < nt; ++t) {
             if (!(t2f[t] > 0.0)) continue;
-            const double dx = mem[4 * t] - cx[c], dy = mem[4 * t + 1] - cy[c];
+            const double dx = mem[4 * t] - my_x, dy = mem[4 * t + 1] - my_y;
             const double dist = sqrt(dx * dx + dy * dy);
             if (!(dist < threshold)) continue;
             if (nearest < 0 || dist < best) { nearest = t; best = dist; }
@@ -224,7 +235,7 @@ __global__ void greedy_camera_kernel(const Params p, const int nc, const int nt,
         double a0, a1;
         if (nearest >= 0) {   // act_from_target_states (greedy.py:117-154)
             const double phi = p.cam_phi[(size_t)c * bp + e], theta = p.cam_theta[(size_t)c * bp + e];
-            const double dx = mem[4 * nearest] - cx[c], dy = mem[4 * nearest + 1] - cy[c];
+            const double dx = mem[4 * nearest] - my_x, dy = mem[4 * nearest + 1] - my_y;
             const double orientation = atan2(dy, dx) * kRad2Deg;
             double view;
             double sn, cs;

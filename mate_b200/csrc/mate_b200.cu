@@ -465,9 +465,12 @@ extern "C" int mate_b200_greedy_camera_actions(MateSim* sim, double* memory, con
     CUDA_TRY(cudaSetDevice(sim->device));
     MateCameraAgentReplay r{};
     if (replay) r = *replay;
-    const int threads = 64;
-    greedy_camera_kernel<<<(sim->num_envs + threads - 1) / threads, threads, 0, (cudaStream_t)stream>>>(
-        sim->base, sim->cfg.num_cameras, sim->cfg.num_targets, memory, tracked, reset_mask, seed, serial, r, cam_act);
+    // one thread per camera agent; a warp's 32 agent memories are staged in shared memory
+    const int nc = sim->cfg.num_cameras, nt = sim->cfg.num_targets;
+    if (32 % nc != 0) return fail(MATE_EINVAL, "the batched GreedyCameraAgent needs a number of cameras that divides 32");
+    const long long agents = (long long)sim->num_envs * nc;
+    greedy_camera_kernel<<<(unsigned)((agents + kCameraAgentThreads - 1) / kCameraAgentThreads), kCameraAgentThreads, 0, (cudaStream_t)stream>>>(
+        sim->base, nc, nt, memory, tracked, reset_mask, seed, serial, r, cam_act);
     sim->launches += 1;
     cudaError_t err = cudaGetLastError();
     if (err != cudaSuccess) return fail(MATE_ECUDA, std::string("greedy camera launch: ") + cudaGetErrorString(err));

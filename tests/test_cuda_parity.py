@@ -225,6 +225,33 @@ def test_step_host_matches_device_step():
         assert torch.equal(rew.cpu(), out[2]) and torch.equal(done.cpu(), out[3])
 
 
+def test_step_host_adopts_prepared_resets(monkeypatch):
+    """The host-buffer path launches the step in chunks; its auto-resets adopt the prepared next episodes like the
+    device path (round 1 dropped them for every chunk and never refilled) and give the same results."""
+    from mate_b200.config import flatten_config, read_config
+
+    cfg = flatten_config(read_config('MATE-4v8-9.yaml', max_episode_steps=4))
+    B = 4096
+    monkeypatch.setenv('MATE_B200_REFILL', 'sync')
+    a, b = _sim(cfg, B), _sim(cfg, B)
+    a.reset(seed=5)
+    b.reset(seed=5)
+    rng = np.random.RandomState(1)
+    out = (torch.zeros((B, 4, a.dc)).pin_memory(), torch.zeros((B, 8, a.dt)).pin_memory(),
+           torch.zeros((B, 2)).pin_memory(), torch.zeros(B, dtype=torch.uint8).pin_memory())
+    for k in range(12):
+        cam_act = torch.from_numpy((rng.uniform(-1, 1, (B, 4, 2)) * [5.0, 2.5]).astype(np.float32)).pin_memory()
+        tgt_act = torch.from_numpy((rng.uniform(-1, 1, (B, 8, 2)) * 20.0).astype(np.float32)).pin_memory()
+        (cam, tgt), rew, done = a.step(cam_act.cuda(), tgt_act.cuda(), auto_reset=True)
+        b.step_host(cam_act, tgt_act, out, auto_reset=True)
+        torch.cuda.synchronize()
+        assert torch.equal(cam.cpu(), out[0]) and torch.equal(tgt.cpu(), out[1]), k
+        assert torch.equal(rew.cpu(), out[2]) and torch.equal(done.cpu(), out[3]), k
+    stats_a, stats_b = _np(a.episode_stats()), _np(b.episode_stats())
+    assert stats_b[0] == stats_a[0] >= 2 * B
+    assert stats_b[6] == stats_b[0] and stats_b[7] == 0, stats_b[:8]   # every reset of the host path adopted a prepared episode
+
+
 @pytest.mark.parametrize('preset,overrides', [('MATE-4v8-9.yaml', {'max_episode_steps': 9}),
                                               ('MATE-Navigation.yaml', {'max_episode_steps': 7}),
                                               ('MATE-2v4-9.yaml', {'max_episode_steps': 1})])
