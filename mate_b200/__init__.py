@@ -15,6 +15,7 @@ environment does (there is no CPU fallback).
 from mate_b200 import config, constants
 from mate_b200.config import PRESETS, flatten_config, preset, read_config
 from mate_b200.constants import *  # noqa: F401,F403
+from mate_b200.messages import Message, Team  # noqa: F401
 
 __version__ = '0.1.0'
 

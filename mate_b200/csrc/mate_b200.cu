@@ -126,6 +126,7 @@ struct MateSim {
     double* soft_edges = nullptr;   // scratch of mate_b200_soft_coverage, allocated on first use
     int refill_mode = 0;      // 0 = off, 1 = side stream every refill_period steps, 2 = same stream after every step (tests)
     int refill_period = 512;
+    int tile_envs = 32;       // environments per warp tile (Params::tile_envs), chosen from the batch size at creation
     long long steps_since_refill = 0;
     // host-path (step_host) resources
     static constexpr int kHostStreams = 4;
@@ -206,6 +207,12 @@ extern "C" int mate_b200_create(const MateConfig* cfg, int32_t num_envs, int32_t
     p.cargo = (uint4*)(b + o_cargo); p.env_a = (uint4*)(b + o_env_a); p.env_b = (int4*)(b + o_env_b);
     p.cc_clear = (unsigned long long*)(b + o_cc);
     p.stats = (float*)(b + o_stats);
+
+    // Warp tiles: 32 environments per warp when the batch fills the machine with those (148 SMs x ~14 resident warps);
+    // smaller batches are cut into tiles of 16 or 8 so that the latency-bound launch still has warps to overlap.
+    sim->tile_envs = num_envs >= 49152 ? 32 : (num_envs >= 24576 ? 16 : 8);
+    if (const char* v = getenv("MATE_B200_TILE")) { const int t = atoi(v); if (t == 8 || t == 16 || t == 32) sim->tile_envs = t; }
+    p.tile_envs = sim->tile_envs;
 
     // prepared resets: a second state block of the same layout + first-view masks + the ready tags
     sim->refill_mode = 1;
@@ -509,7 +516,8 @@ static int launch_range(MateSim* sim, Params p, int begin, int count, cudaStream
     p.next_offset = begin;   // `next` addresses whole-batch arrays
     p.env_index_base += begin;
     p.num_envs = count;
-    const int grid = (count + sim->kernel.envs_per_cta - 1) / sim->kernel.envs_per_cta;
+    const int per_cta = sim->kernel.envs_per_cta / 32 * sim->tile_envs;
+    const int grid = (count + per_cta - 1) / per_cta;
     sim->kernel.launch(p, grid, stream);
     sim->launches += 1;
     cudaError_t err = cudaGetLastError();
@@ -559,7 +567,8 @@ static int launch_prepare(MateSim* sim, cudaStream_t stream) {
     n.mode = MODE_PREPARE; n.flags = 0; n.seed = sim->seed;
     n.cam_act = n.tgt_act = nullptr; n.cam_obs = n.tgt_obs = n.rewards = nullptr; n.done = nullptr; n.env_mask = nullptr;
     fill_aux(n, nullptr, nullptr);
-    const int grid = (sim->num_envs + sim->kernel.envs_per_cta - 1) / sim->kernel.envs_per_cta;
+    const int per_cta = sim->kernel.envs_per_cta / 32 * sim->tile_envs;
+    const int grid = (sim->num_envs + per_cta - 1) / per_cta;
     sim->kernel.launch(n, grid, target);
     sim->launches += 1;
     sim->steps_since_refill = 0;

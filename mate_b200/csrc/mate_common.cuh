@@ -84,6 +84,7 @@ struct Params {
     const uint8_t* replay_transmit; const int8_t* replay_choice;
     // observation wrappers applied to the rows before they leave the SM (mate_b200_set_observation_ops)
     ObsOps obs_ops; const float* cam_affine; const float* tgt_affine; FoldOps fold;
+    int tile_envs;     // environments per warp tile of the step kernel: 32, 16 or 8 (MateSim::tile_envs)
     int warp_stride;   // bytes between the shared-memory blocks of two warps of a CTA (Shape2::WARP_BYTES, + scratch with obs_ops)
     // --- scalars ---
     int num_envs; int bpad; int mode; uint32_t flags;

@@ -1040,11 +1040,16 @@ mate_step_kernel2(const __grid_constant__ Params p) {
     float* myval = val + lane * S::VSTRIDE;
     float* mycam = myval + S::V_C;
 
-    const int env0 = (blockIdx.x * S::WARPS + warp) * 32;     // first env of this warp
+    // A warp tile is p.tile_envs (32, 16 or 8) consecutive environments: small batches are cut into more, smaller tiles so
+    // that the machine still holds ~14 warps per SM (the launch is latency bound); the lanes beyond the tile idle along.
+    const int tile_envs = p.tile_envs;
+    const int env0 = (blockIdx.x * S::WARPS + warp) * tile_envs;   // first env of this warp
     if (env0 >= p.num_envs) return;                            // warps never synchronise with each other
     const int e = env0 + lane;
-    const bool env_ok = e < p.num_envs;
-    const int er = env_ok ? e : p.num_envs - 1;                // tail lanes mirror the last env (reads only)
+    const bool env_ok = lane < tile_envs && e < p.num_envs;
+    // lanes without an environment mirror a live one (reads only; same lines, same branches as their twin); they feed no queue
+    const int twin = env0 + (lane & (tile_envs - 1));
+    const int er = env_ok ? e : (twin < p.num_envs ? twin : p.num_envs - 1);
     const size_t bp = p.bpad;
     const int mode = p.mode;
 
@@ -1143,6 +1148,7 @@ mate_step_kernel2(const __grid_constant__ Params p) {
                 }
             }
         }
+        if (!env_ok) slow = 0u;
         if (MATE2_PF_OBS == 1 && NO > 0 && slow != 0) prefetch_discs64<NO>(p, er);
         double ntx_ = p.tgt_x[er], nty_ = p.tgt_y[er];
         uint32_t npk_ = p.tgt_pack[er];
@@ -1404,6 +1410,7 @@ mate_step_kernel2(const __grid_constant__ Params p) {
         // memory and are evaluated 32 at a time, one pair per lane; pairs the conservative occlusion
         // classification cannot decide go through a second queue to the exact polyline.
         if (NC > 0) {
+            if (!env_ok) pend = 0ull;
             int count = 0, count2 = 0;   // warp-uniform
             for (;;) {
                 const bool more = __any_sync(FULL, pend != 0ull);
@@ -1668,7 +1675,7 @@ mate_step_kernel2(const __grid_constant__ Params p) {
         }
         if (last_pass || !__any_sync(FULL, auto_reset_needed)) break;
     }
-    const int nvalid = min(32, p.num_envs - env0);
+    const int nvalid = min(tile_envs, p.num_envs - env0);
     if (mode == MODE_STEP && lane == 0) atomicAdd(&p.stats[5], (float)nvalid);
 
     // ------------------------------------------------------------------ write state back

@@ -21,7 +21,9 @@ All simulation happens in ``libmate_b200.so`` (hand-written sm_100a CUDA); this 
 moves pointers.  There is no CPU fallback.
 """
 
-from typing import Any, Dict, Optional, Tuple, Union
+import copy
+from collections import defaultdict, deque
+from typing import Any, Dict, Iterable, List, Optional, Tuple, Union
 
 import numpy as np
 import torch
@@ -30,9 +32,10 @@ from mate_b200 import constants as consts
 from mate_b200 import spaces
 from mate_b200.config import DEFAULT_CONFIG_FILE, flatten_config, read_config
 from mate_b200.entities import CameraView, ObstacleView, TargetView
+from mate_b200.messages import Message, Team
 from mate_b200.sim import BatchedSim
 
-__all__ = ['MultiAgentTracking', 'EnvMeta', 'read_config', 'DEFAULT_CONFIG_FILE']
+__all__ = ['MultiAgentTracking', 'EnvMeta', 'Message', 'Team', 'read_config', 'DEFAULT_CONFIG_FILE']
 
 
 class EnvMeta(type):
@@ -116,6 +119,18 @@ class MultiAgentTracking(metaclass=EnvMeta):  # pylint: disable=too-many-instanc
         self.cameras_ordered, self.targets_ordered, self.obstacles_ordered = self.cameras, self.targets, self.obstacles
         self.preserved_data = np.concatenate([[nc, nt, no, 0.0], consts.WAREHOUSES.ravel(), [consts.WAREHOUSE_RADIUS]]).astype(np.float64)
         self.viewer = None
+        self.render_callbacks = {}
+        # intra-team messages (mate/environment.py:540-562): host objects of the reference-compatible mode
+        self.camera_message_buffer, self.target_message_buffer = defaultdict(list), defaultdict(list)
+        self.message_buffers = (self.camera_message_buffer, self.target_message_buffer)
+        self.camera_message_queue, self.target_message_queue = defaultdict(deque), defaultdict(deque)
+        self.message_queues = (self.camera_message_queue, self.target_message_queue)
+        self.camera_communication_edges = np.zeros((nc, nc), dtype=np.int64)
+        self.target_communication_edges = np.zeros((nt, nt), dtype=np.int64)
+        self.camera_total_communication_edges = self.camera_communication_edges.copy()
+        self.target_total_communication_edges = self.target_communication_edges.copy()
+        self.communication_edges = (self.camera_communication_edges, self.target_communication_edges)
+        self.total_communication_edges = (self.camera_total_communication_edges, self.target_total_communication_edges)
 
     # ------------------------------------------------------------------ configuration properties
     @property
@@ -183,6 +198,9 @@ class MultiAgentTracking(metaclass=EnvMeta):  # pylint: disable=too-many-instanc
         self.sim.observe(aux=True)   # refresh the mask attributes for the new episode
         self._needs_reset = False
         self._state_serial += 1
+        for edges in self.communication_edges + self.total_communication_edges:   # environment.py:823-830
+            edges.fill(0)
+        self._clear_messages()
         return self._format_obs(cam_obs, tgt_obs)
 
     def _check_actions(self, action):
@@ -233,13 +251,87 @@ class MultiAgentTracking(metaclass=EnvMeta):  # pylint: disable=too-many-instanc
             'num_delivered_cargoes': int(self._aux['num_delivered'][0].item()),
         }
         norm = self.max_target_team_episode_reward
-        camera_infos = [dict(raw_reward=rew[0], normalized_raw_reward=rew[0] / norm, messages=[],
-                             out_communication_edges=0, in_communication_edges=0, **common)
-                        for _ in range(self.num_cameras)]
-        target_infos = [dict(raw_reward=rew[1], normalized_raw_reward=rew[1] / norm, messages=[],
-                             out_communication_edges=0, in_communication_edges=0, **common)
-                        for _ in range(self.num_targets)]
+        # the messages sent since the previous step reach their recipients through the infos (environment.py:641-669)
+        cam_edges, tgt_edges = self.communication_edges
+        camera_infos = [dict(raw_reward=rew[0], normalized_raw_reward=rew[0] / norm, messages=self.camera_message_buffer[c],
+                             out_communication_edges=cam_edges[c, :].sum(), in_communication_edges=cam_edges[:, c].sum(), **common)
+                        for c in range(self.num_cameras)]
+        target_infos = [dict(raw_reward=rew[1], normalized_raw_reward=rew[1] / norm, messages=self.target_message_buffer[t],
+                             out_communication_edges=tgt_edges[t, :].sum(), in_communication_edges=tgt_edges[:, t].sum(), **common)
+                        for t in range(self.num_targets)]
+        for total, edges in zip(self.total_communication_edges, self.communication_edges):
+            total += edges
+            edges.fill(0)
+        self._clear_messages()
         return self._format_obs(cam_obs, tgt_obs), (rew[0], rew[1]), done_flag, (camera_infos, target_infos)
+
+    # ------------------------------------------------------------------ intra-team messages (reference-compatible mode)
+    def _clear_messages(self):
+        for table in self.message_buffers + self.message_queues:
+            table.clear()
+
+    def _messages_supported(self):
+        if self.batched:
+            raise NotImplementedError(
+                'Message objects are a host API of the single-environment mode (num_envs=None); the batched greedy '
+                'teams exchange their messages inside their CUDA kernels (mate_b200.MultiCamera / MultiTarget)')
+
+    def send_messages(self, messages) -> None:
+        """Buffer messages from an agent to teammates; they are delivered by ``receive_messages`` and through the
+        ``'messages'`` entry of the next step's infos (mate/environment.py:836-854).  Accepts the reference's
+        ``mate.utils.Message`` objects as well as ``mate_b200.Message``."""
+        self._messages_supported()
+        if hasattr(messages, 'sender') and hasattr(messages, 'content'):
+            messages = (messages,)
+        messages = list(messages)
+        assert len({consts._team_index(m.team) for m in messages}) <= 1, (   # pylint: disable=protected-access
+            f'All messages must be from the same team. Got messages = {messages}.')
+        for message in self.route_messages(messages):
+            team = consts._team_index(message.team)   # pylint: disable=protected-access
+            self.message_queues[team][message.recipient].append(message)
+            self.message_buffers[team][message.recipient].append(message)
+            self.communication_edges[team][message.sender, message.recipient] += 1
+
+    def receive_messages(self, agent_id=None, agent=None):
+        """Messages waiting for one agent (``agent_id = (team, index)`` or an agent object with ``TEAM`` and
+        ``index``) or, without arguments, for all agents of both teams (mate/environment.py:856-892)."""
+        self._messages_supported()
+        if agent_id is None and agent is None:
+            messages = ([list(self.camera_message_queue[c]) for c in range(self.num_cameras)],
+                        [list(self.target_message_queue[t]) for t in range(self.num_targets)])
+            self.camera_message_queue.clear()
+            self.target_message_queue.clear()
+            return messages
+        if agent is None and hasattr(agent_id, 'TEAM') and hasattr(agent_id, 'index'):
+            agent_id, agent = None, agent_id
+        if agent is not None:
+            assert agent_id is None, ('You should specify either `agent_id` or `agent`, not both.'
+                                      f'Got (agent_id, agent) = {(agent_id, agent)}.')
+            team, index = agent.TEAM, agent.index
+        else:
+            team, index = agent_id
+        queue = self.message_queues[consts._team_index(team)]   # pylint: disable=protected-access
+        messages = list(queue[index])
+        del queue[index]
+        return messages
+
+    def route_messages(self, messages):
+        """Broadcast messages (``recipient is None``) become one peer-to-peer copy per teammate, the sender included
+        (mate/environment.py:1249-1269)."""
+        routed = []
+        for message in messages:
+            if message.recipient is None:
+                num_teammates = (self.num_cameras, self.num_targets)[consts._team_index(message.team)]   # pylint: disable=protected-access
+                for recipient in range(num_teammates):
+                    routed.append(type(message)(sender=message.sender, recipient=recipient, content=copy.deepcopy(message.content),
+                                                team=message.team, broadcasting=True))
+            else:
+                routed.append(message)
+        return routed
+
+    def add_render_callback(self, name: str, callback) -> None:
+        """Kept for wrappers that register one (mate/environment.py:1181-1186); never called: there is no renderer."""
+        self.render_callbacks[name] = callback
 
     def joint_observation(self):
         """Joint observations of both teams for the current state (environment.py:908-983)."""

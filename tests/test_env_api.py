@@ -121,3 +121,30 @@ def test_wrappers_survive_load_config():
         assert torch.equal(out_a[0], out_b[0]) and torch.equal(out_a[1], out_b[1])
     env.close()
     fresh.close()
+
+
+def test_message_api_in_single_env_mode():
+    """send_messages / receive_messages / route_messages and the 'messages' entry of the step infos
+    (mate/environment.py:641-669, 836-892, 1249-1269); the reference-side comparison is tests/test_reference_wrappers.py."""
+    import mate_b200 as mate
+
+    env = mate.make('MATE-4v8-9-v0')
+    env.reset(seed=1)
+    env.send_messages(mate.Message(sender=2, recipient=None, content={'k': 1}, team=mate.Team.TARGET))
+    env.send_messages([mate.Message(sender=0, recipient=3, content='x', team=mate.Team.CAMERA)])
+    assert [m.recipient for m in env.receive_messages(agent_id=(mate.Team.CAMERA, 3))] == [3]
+    assert env.receive_messages(agent_id=(mate.Team.CAMERA, 3)) == []
+    assert env.target_communication_edges[2].tolist() == [1] * 8
+    _, _, _, (cam_infos, tgt_infos) = env.step((np.zeros((4, 2)), np.zeros((8, 2))))
+    assert [len(info['messages']) for info in cam_infos] == [0, 0, 0, 1]
+    assert all(len(info['messages']) == 1 and info['messages'][0].broadcasting and info['messages'][0]['k'] == 1 for info in tgt_infos)
+    assert tgt_infos[2]['out_communication_edges'] == 8 and tgt_infos[5]['in_communication_edges'] == 1
+    assert env.receive_messages() == ([[], [], [], []], [[] for _ in range(8)])
+    assert env.target_total_communication_edges.sum() == 8 and env.target_communication_edges.sum() == 0
+    _, _, _, (cam_infos, _) = env.step((np.zeros((4, 2)), np.zeros((8, 2))))
+    assert cam_infos[3]['messages'] == []
+    env.close()
+    batched = mate.make('MATE-4v8-9-v0', num_envs=64)
+    with pytest.raises(NotImplementedError):
+        batched.send_messages(mate.Message(0, 1, {}, mate.Team.CAMERA))
+    batched.close()

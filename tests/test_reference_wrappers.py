@@ -285,3 +285,96 @@ def test_readme_wrapper_stack_steps_on_the_b200_environment(mate, monkeypatch, f
             assert bool(info['is_tracked']) == bool(g['a_out_tgt_is_tracked'][i][t])
             assert bool(info['is_colliding']) == bool(g['a_out_tgt_is_colliding'][i][t])
             assert info['state'].shape == base.state_space.shape
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# intra-team messages (mate/environment.py:836-892, 1249-1269): the same traffic through the reference environment
+# and through the B200 environment class, with the reference's own agents and communication wrappers on top
+# ---------------------------------------------------------------------------------------------------------------------
+class ObservationsOnlySim(RecordedSim):
+    """Serves the recorded observations of sample `index` as the outcome of every step (``wrappers_*.npz`` holds states
+    and observations, no step outcomes): enough for everything that happens ABOVE the simulator."""
+
+    def step(self, cam_act, tgt_act, auto_reset=True, replay=None, aux=False):
+        self.actions.append((None if cam_act is None else cam_act.numpy().copy(), tgt_act.numpy().copy()))
+        return self.observe(), torch.zeros((1, 2)), torch.zeros(1, dtype=torch.uint8)
+
+
+def _message_view(messages):
+    return [(m.sender, m.recipient, m.team.value, bool(m.broadcasting), repr(m.content)) for m in messages]
+
+
+def test_message_api_matches_the_reference_environment(mate, monkeypatch):
+    g = np.load(os.path.join(GOLDEN, 'wrappers_4v8-9.npz'))
+    reference_env = mate.MultiAgentTracking(config=str(g['config_name']))   # the unmodified reference class (CPU)
+    reference_env.seed(0)
+    reference_env.reset()
+    drop_in = _drop_in(mate, monkeypatch, ObservationsOnlySim, (g, 'w_'))
+    env = drop_in(config=str(g['config_name']))
+    env.reset()
+    Message, Team = mate.utils.Message, mate.utils.Team
+    rng = np.random.RandomState(3)
+    for _ in range(4):
+        for e in (reference_env, env):
+            state = rng.get_state()
+            for _ in range(6):
+                team = Team.CAMERA if rng.rand() < 0.5 else Team.TARGET
+                n = e.num_cameras if team is Team.CAMERA else e.num_targets
+                sender = int(rng.randint(n))
+                recipient = None if rng.rand() < 0.3 else int(rng.randint(n))
+                e.send_messages(Message(sender=sender, recipient=recipient, content={'k': int(rng.randint(100))}, team=team))
+            e.send_messages([Message(sender=0, recipient=1, content='a', team=Team.TARGET),
+                             Message(sender=1, recipient=None, content='b', team=Team.TARGET)])
+            if e is reference_env:
+                rng.set_state(state)
+        # one agent picks its messages up early; the infos of the next step still carry everything that was sent
+        assert _message_view(env.receive_messages(agent_id=(Team.TARGET, 1))) == \
+            _message_view(reference_env.receive_messages(agent_id=(Team.TARGET, 1)))
+        assert env.receive_messages(agent_id=(Team.TARGET, 1)) == []
+        for a, b in zip(env.communication_edges, reference_env.communication_edges):
+            assert (a == b).all()
+        action = (np.zeros((env.num_cameras, 2)), np.zeros((env.num_targets, 2)))
+        _, _, _, (cam_infos, tgt_infos) = env.step(action)
+        _, _, _, (ref_cam_infos, ref_tgt_infos) = reference_env.step(action)
+        for mine, theirs in zip(cam_infos + tgt_infos, ref_cam_infos + ref_tgt_infos):
+            assert _message_view(mine['messages']) == _message_view(theirs['messages'])
+            assert mine['out_communication_edges'] == theirs['out_communication_edges']
+            assert mine['in_communication_edges'] == theirs['in_communication_edges']
+        for a, b in zip(env.total_communication_edges, (reference_env.camera_total_communication_edges,
+                                                        reference_env.target_total_communication_edges)):
+            assert (a == b).all()
+        assert env.receive_messages() == ([[] for _ in range(env.num_cameras)], [[] for _ in range(env.num_targets)])
+    with pytest.raises(AssertionError):
+        env.send_messages([Message(0, 1, 'x', Team.CAMERA), Message(0, 1, 'y', Team.TARGET)])
+
+
+def test_reference_agents_and_communication_wrappers_on_the_b200_environment(mate, monkeypatch):
+    """The reference's single-team wrapper drives the reference's own greedy camera agents (observe -> send -> receive ->
+    act through the environment's message queues) on the B200 environment class, below the reference's communication
+    wrappers."""
+    g = np.load(os.path.join(GOLDEN, 'wrappers_4v8-9.npz'))
+    drop_in = _drop_in(mate, monkeypatch, ObservationsOnlySim, (g, 'w_'))
+    base = drop_in(config=str(g['config_name']))
+    env = mate.RestrictedCommunicationRange(base, range_limit=1500.0)
+    env = mate.RandomMessageDropout(env, dropout_rate=0.25)
+    # (ExtraCommunicationDelays is left out: its heap compares Message objects on ties, which the reference's own
+    #  dataclass does not support -- it fails on the reference environment in the same way)
+    env = mate.MultiTarget(env, camera_agent=mate.GreedyCameraAgent(seed=0))
+    assert isinstance(env, mate.MultiAgentTracking)
+    base.sim.load(0)
+    tgt_obs = env.reset()
+    assert tgt_obs.shape == (base.num_targets, base.target_observation_dim)
+    for i in range(1, 12):
+        base.sim.load(i)
+        tgt_obs, tgt_reward, done, tgt_infos = env.step(np.zeros((base.num_targets, 2)))
+        assert tgt_obs.shape == (base.num_targets, base.target_observation_dim) and len(tgt_infos) == base.num_targets
+        cam_act = base.sim.actions[-1][0][0]
+        assert cam_act.shape == (base.num_cameras, 2) and np.isfinite(cam_act).all()
+        assert (np.abs(cam_act) <= np.array([base.camera_rotation_step, base.camera_zooming_step]) + 1e-6).all()
+    # the greedy cameras tell their teammates where they are (first step) and which targets they track, through the
+    # environment's message queues and the communication wrappers
+    assert int(base.camera_total_communication_edges.sum()) > 0
+    plain = mate.NoCommunication(drop_in(config=str(g['config_name'])), team='both')
+    plain.reset()
+    plain.send_messages(mate.utils.Message(sender=0, recipient=None, content={}, team=mate.utils.Team.TARGET))
+    assert plain.receive_messages() == ([[] for _ in range(base.num_cameras)], [[] for _ in range(base.num_targets)])
