@@ -208,9 +208,11 @@ extern "C" int mate_b200_create(const MateConfig* cfg, int32_t num_envs, int32_t
     p.cc_clear = (unsigned long long*)(b + o_cc);
     p.stats = (float*)(b + o_stats);
 
-    // Warp tiles: 32 environments per warp when the batch fills the machine with those (148 SMs x ~14 resident warps);
-    // smaller batches are cut into tiles of 16 or 8 so that the latency-bound launch still has warps to overlap.
-    sim->tile_envs = num_envs >= 49152 ? 32 : (num_envs >= 24576 ? 16 : 8);
+    // Warp tiles: 32 environments per warp for the batches that give every SM several of those; smaller batches are cut
+    // into tiles of 16 or 8 so that the latency-bound launch still has warps to overlap (measured, MATE-4v8-9: 16 384
+    // envs 0.0697 / 0.0622 / 0.0685 ms with 32 / 16 / 8, 4096 envs 0.0610 / 0.0468 / 0.0417; from 32 768 envs on 32 wins:
+    // MATE-8v8-9 x 32 768 0.129 / 0.178 / 0.218 -- idle lanes still cost issue slots).
+    sim->tile_envs = num_envs >= 24576 ? 32 : (num_envs >= 8192 ? 16 : 8);
     if (const char* v = getenv("MATE_B200_TILE")) { const int t = atoi(v); if (t == 8 || t == 16 || t == 32) sim->tile_envs = t; }
     p.tile_envs = sim->tile_envs;
 

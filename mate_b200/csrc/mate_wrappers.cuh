@@ -376,20 +376,44 @@ __global__ void soft_edges_kernel(const Params p, const uint8_t* __restrict__ do
     edges[q] = rho;
 }
 
+// Far side of disc (rx, ry, R, d) on the ray of bearing `a` (degrees), exactly as the reference evaluates it
+// (Obstacle.obstruct(outer=True), entities.py:158-184) in fp64; < 0: the ray is not cut.  Only reached by the rays the
+// fp32 evaluation below finds within 1e-4 R of tangency.
+__device__ __noinline__ double soft_cut_exact(double rx, double ry, double R, double d, double a) {
+    double sn, cs;
+    sincospi(a * (1.0 / 180.0), &sn, &cs);
+    const double proj = rx * cs + ry * sn;
+    if (proj < 0.0) return -1.0;
+    const double cosv = fmin(1.0, proj / d);
+    const double perp = d * sqrt(fmax(1.0 - cosv * cosv, 0.0));
+    if (!(R > perp * (1.0 + 1e-9))) return -1.0;
+    return fmax(0.0, d * cosv + sqrt(fmax(R * R - perp * perp, 0.0)));
+}
+
+// Round 2: every sample is classified in fp64 (its bearing, the sector test: a handful of adds and compares) but
+// EVALUATED in fp32.  A cut is computed from the ray's bearing RELATIVE to the disc (beta = a - bearing of the disc, an
+// exact fp64 difference of a few degrees: perp = d sin(beta), proj = d cos(beta)), which keeps the relative precision
+// of fp32 where the absolute formulation (ray direction against a centre 1000 units away) loses the near-tangent
+// chords; rays within 1e-4 R of tangency take the fp64 expression of the reference.  Only the discs whose angular
+// extent meets the sector can cut a sample inside the sector: the cut loop walks that compact list (1-3 discs instead
+// of the 9 of the obstacle set), behind an fp32 bearing test.  The three kinds of samples (grid rays, per-disc lattice
+// rays / edge points, sector-edge points) share one dense index space: 32 per pass whatever their kind.
 template <int NC, int NT, int NO>
-__global__ void soft_coverage_kernel(const Params p, const uint8_t* __restrict__ mask_ct, const uint8_t* __restrict__ done,
-                                     const double* __restrict__ edges, float* __restrict__ out) {
+__global__ void __launch_bounds__(128, 8)
+soft_coverage_kernel(const Params p, const uint8_t* __restrict__ mask_ct, const uint8_t* __restrict__ done,
+                     const double* __restrict__ edges, float* __restrict__ out) {
     constexpr int NCX = NC > 0 ? NC : 1, NOX = NO > 0 ? NO : 1;
     constexpr uint32_t FULL = 0xffffffffu;
     constexpr int WARPS = 4;   // launch: 128 threads per block
-    // per warp: the discs of the camera's obstacle set {x, y, R, distance, bearing, half opening angle} relative to
-    // the camera; read by all lanes at the same address (broadcast)
-    // ... plus the end points of its two 21-point edge segments {near x, near y, far x, far y} x {left, right}
-    __shared__ double sdisc[WARPS][NOX][14];
-    __shared__ int soffs[WARPS][NOX + 1];   // prefix sums of the discs' sample counts (dense batching of (b))
-    const int lane = threadIdx.x & 31;
-    double (*disc)[14] = sdisc[(threadIdx.x >> 5) & (WARPS - 1)];
-    int* offs = soffs[(threadIdx.x >> 5) & (WARPS - 1)];
+    // per warp: the RELEVANT discs of the camera's obstacle set (those whose angular extent meets the sector), compacted,
+    // relative to the camera; read by all lanes (mostly broadcast)
+    __shared__ double sdisc64[WARPS][NOX][6];    // x, y, R, distance, bearing (deg), half opening angle (deg)
+    __shared__ float sdisc32[WARPS][NOX][13];    // distance, R, half opening angle, near_rho, {near x, near y, far x, far y} x {left, right}, bearing
+    __shared__ int soffs[WARPS][NOX + 1];        // prefix sums of their sample counts
+    const int lane = threadIdx.x & 31, wslot = (threadIdx.x >> 5) & (WARPS - 1);
+    double (*disc)[6] = sdisc64[wslot];
+    float (*fdisc)[13] = sdisc32[wslot];
+    int* offs = soffs[wslot];
     const long long item = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;   // (environment, camera)
     if (item >= (long long)p.num_envs * NCX) return;
     const int e = (int)(item / NCX), c = (int)(item - (long long)e * NCX);
@@ -402,154 +426,173 @@ __global__ void soft_coverage_kernel(const Params p, const uint8_t* __restrict__
     const double cx = p.cam_x[(size_t)c * bp + e], cy = p.cam_y[(size_t)c * bp + e];
     const double phi = p.cam_phi[(size_t)c * bp + e], theta = p.cam_theta[(size_t)c * bp + e];
     const double rmax = p.cam_rmax;
-    // the camera's obstacle set (entities.py:363-368), one disc per lane
-    bool member = false, inside_disc = false;
-    if (lane < NO) {
-        const double ox = p.obs_x[(size_t)lane * bp + e] - cx, oy = p.obs_y[(size_t)lane * bp + e] - cy, orad = p.obs_r[(size_t)lane * bp + e];
-        const double od = sqrt(ox * ox + oy * oy);
-        member = od < rmax + orad;
-        inside_disc = member && orad > od;
-        disc[lane][0] = ox; disc[lane][1] = oy; disc[lane][2] = orad; disc[lane][3] = od;
-        const double ang = atan2(oy, ox) * kRad2Deg, half = od > orad ? asin(orad / od) * kRad2Deg : 90.0;
-        disc[lane][4] = ang;
-        disc[lane][5] = half;
-        if (member) {   // the two edge segments of entities.py:431-448: from near_rho on the tangent to rmax 0.01 degrees beside it
-            const double near_rho = fmin(rmax, sqrt(od * od + orad * orad));
-#pragma unroll
-            for (int side = 0; side < 2; ++side) {
-                const double edge = side ? ang + half : ang - half, far_angle = side ? ang + half + 0.01 : ang - half - 0.01;
-                double ns, nc_, fs, fc;
-                sincospi(normalize_angle(edge) * (1.0 / 180.0), &ns, &nc_);
-                sincospi(normalize_angle(far_angle) * (1.0 / 180.0), &fs, &fc);
-                disc[lane][6 + 4 * side] = near_rho * nc_; disc[lane][7 + 4 * side] = near_rho * ns;
-                disc[lane][8 + 4 * side] = rmax * fc; disc[lane][9 + 4 * side] = rmax * fs;
-            }
-        }
-    }
-    const uint32_t members = __ballot_sync(FULL, member);
-    const bool collapsed = __any_sync(FULL, inside_disc);   // entities.py:378-388: every ray has norm 0
-    __syncwarp();
+    const float rmax32 = (float)rmax;
     // sector (boundary_between, entities.py:484-511)
     const double left = normalize_angle(phi - theta * 0.5), right = left + theta;
     const bool wraps = right > 180.0;
     auto in_sector = [&](const double a) {
         return wraps ? (a > left || a < right - 360.0 || a == -180.0) : (a > left && a < right);
     };
-    // the boundary points are computed in fp64; the distances of the targets to them (relative to the camera, at
-    // most ~4000 units) in fp32: the score is a float32 anyway and loses < 1e-6 of dist_max here
+    // the camera's obstacle set (entities.py:363-368), one disc per lane; its samples: lattice rays at max_rho and the
+    // two 21-point edge segments (entities.py:419-448), only for the discs that reach into the sector
+    bool member = false, inside_disc = false;
+    int my_count = 0;
+    double ox = 0.0, oy = 0.0, orad = 0.0, od = 0.0, ang = 0.0, half = 0.0;
+    if (lane < NO) {
+        ox = p.obs_x[(size_t)lane * bp + e] - cx; oy = p.obs_y[(size_t)lane * bp + e] - cy; orad = p.obs_r[(size_t)lane * bp + e];
+        od = sqrt(ox * ox + oy * oy);
+        member = od < rmax + orad;
+        inside_disc = member && orad > od;
+        // cheap rejection before the fp64 atan2 / asin: a disc farther than 90 + theta / 2 degrees from the sector axis (+ its
+        // own half opening angle, at most 90 where the camera is outside) cannot meet the sector when its centre lies behind
+        if (member && !inside_disc) {
+            ang = atan2(oy, ox) * kRad2Deg; half = asin(orad / od) * kRad2Deg;
+            // angular distance between the disc's bearing and the sector axis vs. the two half widths (+ slack)
+            if (!(fabs(normalize_angle(ang - phi)) > half + theta * 0.5 + 0.02)) {
+                const int two_half = (int)(2.0 * half);
+                my_count = (two_half > 16 ? two_half : 16) + 1 + 42;
+            }
+        }
+    }
+    const bool collapsed = __any_sync(FULL, inside_disc);   // entities.py:378-388: every ray has norm 0
+    if (collapsed) my_count = 0;
+    const uint32_t relevant = __ballot_sync(FULL, my_count > 0);
+    const int nrel = __popc(relevant);
+    int incl = my_count;    // inclusive scan over the lanes
+#pragma unroll
+    for (int sh = 1; sh < 32; sh <<= 1) {
+        const int up = __shfl_up_sync(FULL, incl, sh);
+        if (lane >= sh) incl += up;
+    }
+    if (my_count > 0) {
+        const int r = __popc(relevant & ((1u << lane) - 1u));
+        offs[r] = incl - my_count;
+        disc[r][0] = ox; disc[r][1] = oy; disc[r][2] = orad; disc[r][3] = od; disc[r][4] = ang; disc[r][5] = half;
+        float* fd = fdisc[r];
+        fd[0] = (float)od; fd[1] = (float)orad; fd[2] = (float)half; fd[12] = (float)ang;
+        // the two edge segments: from near_rho on the tangent to rmax 0.01 degrees beside it
+        const float near_rho = (float)fmin(rmax, sqrt(od * od + orad * orad));
+        fd[3] = near_rho;
+#pragma unroll
+        for (int side = 0; side < 2; ++side) {
+            const double edge = side ? ang + half : ang - half, far_angle = side ? ang + half + 0.01 : ang - half - 0.01;
+            float ns, nc_, fs, fc;
+            sincospif((float)(normalize_angle(edge) * (1.0 / 180.0)), &ns, &nc_);
+            sincospif((float)(normalize_angle(far_angle) * (1.0 / 180.0)), &fs, &fc);
+            fd[4 + 4 * side] = near_rho * nc_; fd[5 + 4 * side] = near_rho * ns;
+            fd[6 + 4 * side] = rmax32 * fc; fd[7 + 4 * side] = rmax32 * fs;
+        }
+    }
+    const int total_disc = __shfl_sync(FULL, incl, 31);
+    __syncwarp();
+    // the boundary points and the distances of the targets to them (relative to the camera, at most ~4000 units) in
+    // fp32: the score is a float32 and loses < 1e-5 of dist_max here
     float tx[NT], ty[NT], best[NT];
 #pragma unroll
     for (int t = 0; t < NT; ++t) {
         tx[t] = (float)(p.tgt_x[(size_t)t * bp + e] - cx); ty[t] = (float)(p.tgt_y[(size_t)t * bp + e] - cy);
         best[t] = 3.0e38f;
     }
-    auto visit = [&](const double rho, const double cs, const double sn) {
-        const float px = (float)(rho * cs), py = (float)(rho * sn);
+    const float rho_l = (float)edges[item * 2], rho_r = (float)edges[item * 2 + 1];   // soft_edges_kernel
+    // (a) the integer-degree grid (entities.py:339-342): only the degrees inside the sector are enumerated
+    const int k_first = (int)floor(left) - 1;                 // a little more than the open interval (left, right); in_sector decides
+    int count_grid = (int)ceil(theta) + 3;
+    if (count_grid > 360) count_grid = 360;                   // every degree at most once
+    // (c) the two sector edges: 16 points from the camera to the end point + the end point, per side
+    const int total = count_grid + total_disc + 34;
+    constexpr float kTan = 1.7453292431e-4f;   // tan(0.01 deg): the 0.01 degrees between the two ends of an edge segment
+    for (int s0 = 0; s0 < total; s0 += 32) {
+        const int s = s0 + lane;
+        bool live = s < total;
+        double a = 0.0;            // bearing of the sample, degrees in [-180, 180)
+        float n = 0.f, cs = 1.f, sn = 0.f;
+        int skip = -1;             // the disc a tangent ray / an edge point belongs to: it does not cut its own samples
+        bool cut = true;
+        if (s < count_grid) {
+            int k = k_first + s;                                   // integer degree, may run past +180
+            if (k >= 180) k -= 360;
+            a = (double)k;
+            live = live && in_sector(a);
+            sincospif((float)k * (1.0f / 180.0f), &sn, &cs);
+            n = rmax32;
+        } else if (s < count_grid + total_disc) {
+            const int sidx = s - count_grid;
+            int o = 0;
+            while (o + 1 < nrel && offs[o + 1] <= sidx) ++o;
+            const int j = sidx - offs[o];
+            const double ang_o = disc[o][4], half_o = disc[o][5];
+            const double aL = ang_o - half_o, aR = ang_o + half_o;
+            const int two_half = (int)(2.0 * half_o);
+            const int nlat = two_half > 16 ? two_half : 16;
+            const float* fd = fdisc[o];
+            if (j <= nlat) {        // lattice ray
+                const double step = (aR - aL) / (double)nlat;   // np.linspace
+                a = normalize_angle(j >= nlat ? aR : ((double)j * step + aL));
+                sincospif((float)(a * (1.0 / 180.0)), &sn, &cs);
+                n = fminf(rmax32, fd[0] + fd[1]);
+                if (j == 0 || j == nlat) skip = o;               // exactly tangent to its own disc
+            } else {                // point k of an edge segment
+                const int q = j - nlat - 1;
+                const int side = q >= 21 ? 1 : 0, k = side ? q - 21 : q;
+                const float t = k >= 20 ? 1.0f : (float)k * 0.05f;
+                const float vx = (1.0f - t) * fd[4 + 4 * side] + t * fd[6 + 4 * side];
+                const float vy = (1.0f - t) * fd[5 + 4 * side] + t * fd[7 + 4 * side];
+                const float inv = rsqrtf(vx * vx + vy * vy);
+                n = 1.0f / inv;
+                cs = vx * inv; sn = vy * inv;
+                // bearing of the point: the tangent's bearing plus the (tiny) angle between the segment's near end and the
+                // point, t rmax sin(0.01 deg) / ((1 - t) near_rho + t rmax cos(0.01 deg)) radians to 1e-8 relative
+                const float delta = __fdividef(t * rmax32 * kTan, (1.0f - t) * fd[3] + t * rmax32) * (float)kRad2Deg;
+                a = normalize_angle(side ? aR + (double)delta : aL - (double)delta);
+                skip = o;
+            }
+            live = live && in_sector(a);
+        } else {
+            const int q = s - count_grid - total_disc;
+            const bool is_right = q >= 17;
+            const int k = is_right ? q - 17 : q;          // k = 16: the end point itself
+            const float rho = is_right ? rho_r : rho_l;
+            sincospif((float)((is_right ? right : left) * (1.0 / 180.0)), &sn, &cs);
+            n = k >= 16 ? rho : (float)k * (rho * 0.0625f);
+            cut = false;
+        }
+        if (!live) continue;
+        if (collapsed && cut) n = 0.f;
+        // cut at the far side of the discs the ray crosses (Obstacle.obstruct(outer=True))
+        if (cut && n > 0.f) {
+            const float a32 = (float)a;
+#pragma unroll 1
+            for (int o = 0; o < nrel; ++o) {
+                const float* fd = fdisc[o];
+                float coarse = fabsf(a32 - fd[12]);
+                coarse = coarse > 180.f ? 360.f - coarse : coarse;
+                if (coarse > fd[2] + 2e-3f || o == skip) continue;      // the ray passes beside the disc
+                const float d = fd[0], R = fd[1];
+                if (d >= n + R) continue;
+                double beta = fabs(a - disc[o][4]);
+                beta = beta > 180.0 ? 360.0 - beta : beta;
+                float sb, cb;
+                sincospif((float)beta * (1.0f / 180.0f), &sb, &cb);
+                const float perp = d * sb, proj = d * cb;
+                if (proj < 0.f) continue;
+                const float margin = R - perp;
+                float far_side;
+                if (fabsf(margin) < 1e-4f * R) {
+                    const double f64 = soft_cut_exact(disc[o][0], disc[o][1], disc[o][2], disc[o][3], a);
+                    if (f64 < 0.0) continue;
+                    far_side = (float)f64;
+                } else {
+                    if (!(margin > 0.f)) continue;
+                    far_side = proj + sqrtf(margin * (R + perp));
+                }
+                n = fminf(n, far_side);
+            }
+        }
+        const float px = n * cs, py = n * sn;
 #pragma unroll
         for (int t = 0; t < NT; ++t) {
             const float dx = tx[t] - px, dy = ty[t] - py;
             best[t] = fminf(best[t], dx * dx + dy * dy);
-        }
-    };
-    // One sample ray (angle in degrees, normalised; norm): cut at the far side of the discs it crosses
-    // (Obstacle.obstruct(outer=True)), then visit.  A ray can only cross a disc whose bearing is within the disc's
-    // half opening angle of the ray: everything else is rejected on two shared-memory reads.
-    auto sample_dir = [&](const bool live, const double a, const double norm, double cs, double sn, const bool have_dir) {
-        if (!live) return;
-        if (!have_dir) sincospi(a * (1.0 / 180.0), &sn, &cs);
-        double n = collapsed ? 0.0 : norm;
-        uint32_t m = members;
-        while (m != 0u) {
-            const int o = __ffs(m) - 1;
-            m &= m - 1u;
-            if (fabs(normalize_angle(a - disc[o][4])) > disc[o][5] + 1e-4) continue;
-            const double rx = disc[o][0], ry = disc[o][1], R = disc[o][2], d = disc[o][3];
-            if (!(n > 0.0) || d >= n + R) continue;
-            const double proj = rx * cs + ry * sn;
-            if (proj < 0.0) continue;
-            const double cosv = fmin(1.0, proj / d);
-            const double perp = d * sqrt(fmax(1.0 - cosv * cosv, 0.0));
-            if (!(R > perp * (1.0 + 1e-9))) continue;
-            const double far_side = fmax(0.0, d * cosv + sqrt(fmax(R * R - perp * perp, 0.0)));
-            if (far_side < n) n = far_side;
-        }
-        visit(n, cs, sn);
-    };
-    auto sample_if = [&](const bool live, const double a, const double norm) { sample_dir(live, a, norm, 0.0, 0.0, false); };
-    // (a) the integer-degree grid (entities.py:339-342): only the degrees inside the sector are enumerated (a
-    //     sector of theta degrees holds about theta of them: 1-6 passes of 32 instead of 12)
-    {
-        const int k_first = (int)floor(left) - 1;                 // a little more than the open interval (left, right); in_sector decides
-        const int count = (int)ceil(theta) + 3;
-        for (int j0 = 0; j0 < count; j0 += 32) {
-            const int j = j0 + lane;
-            int k = k_first + j;                                   // integer degree, may run past +180
-            if (k >= 180) k -= 360;
-            const double a = (double)k;
-            // every degree at most once: the window is shorter than 360 unless theta = 180 + slack, where j < 360 caps it
-            sample_if(j < count && j < 360 && in_sector(a), a, rmax);
-        }
-    }
-    // (b) per obstacle of the set: lattice rays at max_rho and the two edge segments (entities.py:419-448).  The
-    //     samples of ALL relevant discs are enumerated densely, 32 per pass (17-40 lattice rays + 42 edge points per
-    //     disc would otherwise leave most lanes of three passes per disc idle)
-    if (!collapsed) {
-        if (lane == 0) {
-            int total = 0;
-            for (int o = 0; o < NO; ++o) {
-                offs[o] = total;
-                if (!((members >> o) & 1u)) continue;
-                const double ang = disc[o][4], half = disc[o][5];
-                // angular distance between the disc's bearing and the sector axis vs. the two half widths (+ slack)
-                if (fabs(normalize_angle(ang - phi)) > half + theta * 0.5 + 0.02) continue;
-                const int two_half = (int)(2.0 * half);
-                total += (two_half > 16 ? two_half : 16) + 1 + 42;
-            }
-            offs[NO] = total;
-        }
-        __syncwarp();
-        const int total = offs[NO];
-        for (int s0 = 0; s0 < total; s0 += 32) {
-            const int sidx = s0 + lane;
-            const bool live = sidx < total;
-            int o = 0;
-            if (live) { while (o + 1 < NO && offs[o + 1] <= sidx) ++o; }   // offs is non-decreasing; discs without samples have an empty range
-            const int j = sidx - offs[o];
-            const double R = disc[o][2], d = disc[o][3], ang = disc[o][4], half = disc[o][5];
-            const double aL = ang - half, aR = ang + half;
-            const int two_half = (int)(2.0 * half);
-            const int nlat = two_half > 16 ? two_half : 16;
-            if (j <= nlat) {        // lattice ray
-                const double step = (aR - aL) / (double)nlat;   // np.linspace
-                const double a = normalize_angle(j >= nlat ? aR : ((double)j * step + aL));
-                sample_if(live && in_sector(a), a, fmin(rmax, d + R));
-            } else {                // point k of an edge segment
-                const int q = j - nlat - 1;
-                const int side = q >= 21 ? 1 : 0, k = side ? q - 21 : q;
-                const double t = k >= 20 ? 1.0 : (double)k * 0.05;
-                const double vx = (1.0 - t) * disc[o][6 + 4 * side] + t * disc[o][8 + 4 * side];
-                const double vy = (1.0 - t) * disc[o][7 + 4 * side] + t * disc[o][9 + 4 * side];
-                const double a = atan2(vy, vx) * kRad2Deg;
-                const double norm = sqrt(vx * vx + vy * vy);
-                // the ray's direction is the point's own direction (the reference goes through (cos, sin)(atan2): 1 ulp)
-                sample_dir(live && in_sector(a), a, norm, vx / norm, vy / norm, true);
-            }
-        }
-    }
-    // (c) the two sector edges: end point from the INNER polyline (boundary_between uses sight_range_at), then 16
-    //     points from the camera to it (auxiliary_camera_rewards.py:203-214)
-    {
-        double sn, cs;
-        const double rho_l = edges[item * 2], rho_r = edges[item * 2 + 1];   // soft_edges_kernel
-        for (int q0 = 0; q0 < 34; q0 += 32) {
-            const int q = q0 + lane;
-            if (q < 34) {
-                const bool is_right = q >= 17;
-                const int k = is_right ? q - 17 : q;          // k = 16: the end point itself
-                const double rho = is_right ? rho_r : rho_l;
-                sincospi((is_right ? right : left) * (1.0 / 180.0), &sn, &cs);
-                visit(k >= 16 ? rho : (double)k * (rho / 16.0), cs, sn);
-            }
         }
     }
 #pragma unroll
@@ -557,17 +600,18 @@ __global__ void soft_coverage_kernel(const Params p, const uint8_t* __restrict__
 #pragma unroll
         for (int sh = 16; sh >= 1; sh >>= 1) best[t] = fminf(best[t], __shfl_xor_sync(FULL, best[t], sh));
     }
-    const double sight_range = sqrt(p.cam_area_product / theta);
-    double sn_h, cs_h;
-    sincospi(theta * (0.5 / 180.0), &sn_h, &cs_h);
-    const double dist_max = theta < 180.0 ? sight_range / (1.0 + 1.0 / sn_h) : sight_range * 0.5;
-    if (lane == 0) {
+    // one target per lane: the signed distance in units of the radius of the sector's inscribed circle
+    if (lane < NT) {
+        const double sight_range = sqrt(p.cam_area_product / theta);
+        double sn_h, cs_h;
+        sincospi(theta * (0.5 / 180.0), &sn_h, &cs_h);
+        const double dist_max = theta < 180.0 ? sight_range / (1.0 + 1.0 / sn_h) : sight_range * 0.5;
+        float mine = best[0];
 #pragma unroll
-        for (int t = 0; t < NT; ++t) {
-            const double dist = (double)sqrtf(best[t]);
-            const bool tracked = mask_ct[((size_t)e * NCX + c) * NT + t] != 0;
-            row[t] = (float)((tracked ? dist : -dist) / dist_max);
-        }
+        for (int t = 1; t < NT; ++t) mine = lane == t ? best[t] : mine;
+        const double dist = (double)sqrtf(mine);
+        const bool tracked = mask_ct[((size_t)e * NCX + c) * NT + lane] != 0;
+        row[lane] = (float)((tracked ? dist : -dist) / dist_max);
     }
 }
 

@@ -223,7 +223,7 @@ def test_soft_coverage_matches_the_restatement(name):
 
     g = gu.load(name)
     nc, nt, _ = (int(x) for x in g['cfg_counts'])
-    limit = 96
+    limit = 256
     want, _ = _soft_reference(g, limit)
     n = len(want)
     env = mate_b200.make('MultiAgentTracking-v0', config=str(g['config_name']), num_envs=n, wrappers=[

@@ -337,3 +337,40 @@ def test_invalid_shape_and_alignment_errors():
     cfg['target']['location_random_range'] = cfg['target']['location_random_range'][:3]
     with pytest.raises(ValueError):
         _sim(flatten_config(cfg), 8)
+
+
+@pytest.mark.parametrize('preset,overrides', [('MATE-4v8-9.yaml', {'max_episode_steps': 6}), ('MATE-Navigation.yaml', {'max_episode_steps': 5}),
+                                              ('MATE-8v8-9.yaml', {'max_episode_steps': 6})])
+def test_results_do_not_depend_on_the_warp_tile_size(preset, overrides, monkeypatch):
+    """The step kernel cuts the batch into warp tiles of 32, 16 or 8 environments (chosen from the batch size,
+    MATE_B200_TILE overrides it); draws are keyed on the global environment index, so every tile size gives the same
+    bits -- including ragged last tiles, in-place resets and adopted prepared episodes."""
+    from mate_b200.config import flatten_config, read_config
+
+    cfg = flatten_config(read_config(preset, **overrides))
+    nc, nt = cfg['num_cameras'], cfg['num_targets']
+    B = 1003
+    monkeypatch.setenv('MATE_B200_REFILL', '3')
+    sims = []
+    for tile in (32, 16, 8):
+        monkeypatch.setenv('MATE_B200_TILE', str(tile))
+        sims.append(_sim(cfg, B))
+    first = [s.reset(seed=11) for s in sims]
+    for other in first[1:]:
+        assert torch.equal(first[0][1], other[1]) and (nc == 0 or torch.equal(first[0][0], other[0]))
+    rng = np.random.RandomState(2)
+    for k in range(20):
+        cam_act = torch.from_numpy((rng.uniform(-1, 1, (B, nc, 2)) * [5.0, 2.5]).astype(np.float32)).cuda() if nc else None
+        tgt_act = torch.from_numpy((rng.uniform(-1, 1, (B, nt, 2)) * 20.0).astype(np.float32)).cuda()
+        outs = []
+        for s in sims:
+            (cam, tgt), rew, done = s.step(cam_act, tgt_act, auto_reset=True)
+            outs.append((cam.clone() if nc else None, tgt.clone(), rew.clone(), done.clone()))
+        for other in outs[1:]:
+            assert torch.equal(outs[0][1], other[1]) and torch.equal(outs[0][2], other[2]) and torch.equal(outs[0][3], other[3]), k
+            assert nc == 0 or torch.equal(outs[0][0], other[0]), k
+    states = [s.get_state() for s in sims]
+    for other in states[1:]:
+        for key, value in states[0].items():
+            assert np.array_equal(value, other[key]), key
+    assert _np(sims[0].episode_stats())[0] >= 2 * B
