@@ -679,15 +679,19 @@ __device__ __noinline__ void pack_observations(const Params& p, const int env0, 
     // and the constant entries of the private state -- unless observation wrappers are folded in, which rewrite
     // them in place for every environment
     const bool has_ops = FOLD && !fast && p.obs_ops.n > 0;   // a stack outside the canonical form: generic shared-memory path
+    if (FOLD && f_resc) __syncwarp();   // aff_own is read below
+    // (with RescaledObservation folded in, the constants are staged already rescaled; RelativeCoordinates rewrites the
+    //  eight warehouse coordinates of a row for every environment, everything else here stays)
     auto stage_constants = [&]() {
         if (lane < R) {
             const int row = lane;
             float* q = stage + row_base(row);
-            q[0] = (float)NC; q[1] = (float)NT; q[2] = (float)NO; q[3] = (float)(row < NC ? row : row - NC);
-            q[4] = 925.f; q[5] = 925.f; q[6] = -925.f; q[7] = 925.f; q[8] = -925.f; q[9] = -925.f; q[10] = 925.f; q[11] = -925.f;
-            q[12] = 75.f;
-            if (row < NC) { q[C_SELF + 2] = f_crad; q[C_SELF + 6] = f_rmax; q[C_SELF + 7] = f_rot; q[C_SELF + 8] = f_zoom; }
-            else q[T_SELF + 2] = f_sr;
+            auto put = [&](const int col, const float x, const int aff) { q[col] = (FOLD && f_resc) ? fmaf(x, aff_own[aff].x, aff_own[aff].y) : x; };
+            put(0, (float)NC, 0); put(1, (float)NT, 1); put(2, (float)NO, 2); put(3, (float)(row < NC ? row : row - NC), 3);
+            put(4, 925.f, 4); put(5, 925.f, 5); put(6, -925.f, 6); put(7, 925.f, 7); put(8, -925.f, 8); put(9, -925.f, 9); put(10, 925.f, 10); put(11, -925.f, 11);
+            put(12, 75.f, 12);
+            if (row < NC) { put(C_SELF + 2, f_crad, 27 + 2); put(C_SELF + 6, f_rmax, 27 + 6); put(C_SELF + 7, f_rot, 27 + 7); put(C_SELF + 8, f_zoom, 27 + 8); }
+            else put(T_SELF + 2, f_sr, 13 + 2);
         }
     };
     stage_constants();
@@ -904,41 +908,33 @@ __device__ __noinline__ void pack_observations(const Params& p, const int env0, 
                 }
             }
         }
-        if (FOLD && fast) {
-            // with wrappers folded in, a row's preserved block and private state are written per environment:
-            // RelativeCoordinates moves the warehouse locations, RescaledObservation touches every column
-            auto own_row = [&](float* q, const int ko, const float* self, auto nself_c, const float2* aff_self) {
-                constexpr int nself = decltype(nself_c)::value;
-                float pres[13] = {(float)NC, (float)NT, (float)NO, 0.f, 925.f, 925.f, -925.f, 925.f, -925.f, -925.f, 925.f, -925.f, 75.f};
-                pres[3] = self[nself];   // the row's index in its team (passed behind the private state)
-                if (f_rel) {
+        {
+            // own rows, the entries that change: lane t < NT writes target row t, lane NT + k (k < NC) the row of camera
+            // c_idx (NC consecutive lanes hold NC different cameras) -- one instruction stream for both kinds of rows.
+            // With wrappers folded in: RescaledObservation is one FMA per entry, RelativeCoordinates moves the eight
+            // warehouse coordinates of the row (the agent's own location stays absolute, mate/constants.py:372-427)
+            const bool is_t = lane < NT, is_c = NC > 0 && lane >= NT && lane < NT + NC;
+            float* const q = is_t ? self_t : self_c;
+            const int aff0 = is_t ? 13 : 27;
+            auto put = [&](const int j, const float x) { q[j] = (FOLD && f_resc) ? fmaf(x, aff_own[aff0 + j].x, aff_own[aff0 + j].y) : x; };
+            if (is_t || is_c) {
+                put(0, is_t ? t0 : c0); put(1, is_t ? t1 : c1); put(3, is_t ? t3 : c3); put(4, is_t ? s_step : c4); put(5, is_t ? s_cap : c5);
+                if (FOLD && f_rel) {
+                    const int ko = is_t ? lane : NT + NO + c_idx;
+                    float* const pr = q - 13;      // the row's preserved block (C_SELF == T_SELF == 13)
+                    const double ox = fpos[2 * ko], oy = fpos[2 * ko + 1];
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) pres[4 + j] = (float)((double)pres[4 + j] - fpos[2 * ko + (j & 1)]);
+                    for (int j = 0; j < 8; ++j) {
+                        const float wh = (j == 0 || j == 1 || j == 3 || j == 6) ? 925.f : -925.f;   // (+,+) (-,+) (-,-) (+,-)
+                        const float x = (float)((double)wh - ((j & 1) ? oy : ox));
+                        pr[4 + j] = f_resc ? fmaf(x, aff_own[4 + j].x, aff_own[4 + j].y) : x;
+                    }
                 }
-#pragma unroll
-                for (int j = 0; j < 13; ++j) q[j] = f_resc ? fmaf(pres[j], aff_own[j].x, aff_own[j].y) : pres[j];
-#pragma unroll
-                for (int j = 0; j < nself; ++j) q[13 + j] = f_resc ? fmaf(self[j], aff_self[j].x, aff_self[j].y) : self[j];
-            };
-            if (lane < NT) {
-                const float self[15] = {t0, t1, f_sr, t3, s_step, s_cap, sg[0], sg[1], sg[2], sg[3], se[0], se[1], se[2], se[3], (float)lane};
-                own_row(stage + S::STAGE_CAM + lane * DT, lane, self, std::integral_constant<int, 14>{}, aff_own + 13);
             }
-            if (NC > 0 && lane < NC) {
-                const float self[10] = {c0, c1, f_crad, c3, c4, c5, f_rmax, f_rot, f_zoom, (float)lane};
-                own_row(stage + lane * DC, NT + NO + lane, self, std::integral_constant<int, 9>{}, aff_own + 27);
-            }
-        } else {
-        if (lane < NT) {
-            float* q = self_t;
-            q[0] = t0; q[1] = t1; q[3] = t3; q[4] = s_step; q[5] = s_cap;
+            if (is_t) {
 #pragma unroll
-            for (int w = 0; w < NW; ++w) { q[6 + w] = sg[w]; q[10 + w] = se[w]; }
-        }
-        if (NC > 0 && lane < NC) {
-            float* q = self_c;
-            q[0] = c0; q[1] = c1; q[3] = c3; q[4] = c4; q[5] = c5;
-        }
+                for (int w = 0; w < NW; ++w) { put(6 + w, sg[w]); put(10 + w, se[w]); }
+            }
         }
         // ---- registered observation wrappers (EnhancedObservation, SharedFieldOfView, RelativeCoordinates,
         //      RescaledObservation): applied to the staged rows, no extra pass over the observation tensors
