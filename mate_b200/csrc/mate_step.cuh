@@ -83,7 +83,10 @@ struct Shape2 {
     static constexpr int CV = 5;
     static constexpr int V_T = 0, V_C = 3 * NT, VN = 3 * NT + CV * NC;
     static constexpr int VSTRIDE = VN | 1;
-    static constexpr int STAGE_CAM = ((CAM_ROW + 3) / 4) * 4;
+    // Camera rows whose length is a multiple of 32 floats (MATE-4v2-9: 96) would all start at the same shared-memory bank
+    // and every scatter store of the packer would be a 4-way conflict: such rows are staged 4 floats apart (plain packer)
+    static constexpr int CAM_SKEW = (NC > 1 && DC % 32 == 0) ? 4 : 0;
+    static constexpr int STAGE_CAM = ((NC * (DC + CAM_SKEW) + 3) / 4) * 4;
     static constexpr int STAGE_FLOATS = STAGE_CAM + ((TGT_ROW + 3) / 4) * 4;
     static constexpr bool BULK = (CAM_ROW % 4 == 0) && (TGT_ROW % 4 == 0);   // 16-byte aligned blocks per env
     static constexpr int E = NT + NO + NC;                     // entity slots (lanes of the scatter)
@@ -642,7 +645,8 @@ __device__ __noinline__ void pack_observations(const Params& p, const int env0, 
     const int t_idx = lane % NT, t_sub = lane / NT;
     const int o_idx = lane % NOX, o_sub = lane / NOX;
     const int c_idx = lane % NCX, c_sub = lane / NCX;
-    auto row_base = [&](const int row) { return row < NC ? row * DC : S::STAGE_CAM + (row - NC) * DT; };
+    constexpr int DCS = DC + (FOLD ? 0 : S::CAM_SKEW);   // stride of the staged camera rows (the wrappers' code expects dense rows)
+    auto row_base = [&](const int row) { return row < NC ? row * DCS : S::STAGE_CAM + (row - NC) * DT; };
     float* q_ptr[NRND];   // this lane's slot in the staged block, per round
     int m_idx[NRND];      // and the mask word that decides it
     uint32_t on_bits = 0; // bit rd: the lane has a pair in round rd
@@ -696,7 +700,7 @@ __device__ __noinline__ void pack_observations(const Params& p, const int env0, 
     };
     stage_constants();
     float* const self_t = stage + S::STAGE_CAM + t_idx * DT + T_SELF;   // used by lanes 0..NT-1
-    float* const self_c = stage + c_idx * DC + C_SELF;                   // used by lanes 0..NC-1
+    float* const self_c = stage + c_idx * DCS + C_SELF;                  // used by the NC lanes from NT on
     // obstacle entries are fetched two environments ahead (an L2 round trip is longer than one iteration)
     const float4* ob_ptr = obs_f4 + (size_t)o_idx * bp + env0;
     float4 ob_next = make_float4(0.f, 0.f, 0.f, 0.f), ob_next2 = ob_next;
@@ -894,7 +898,25 @@ __device__ __noinline__ void pack_observations(const Params& p, const int env0, 
                 for (int rd = 0; rd < RND_O; ++rd) {
                     if ((on_bits >> (RND_T + rd)) & 1u) {
                         float* q = q_ptr[RND_T + rd];
-                        q[0] = vo[rd][0]; q[1] = vo[rd][1]; q[2] = vo[rd][2]; q[3] = vo[rd][3];
+                        if (RPR_O == 1) {
+                            // One observer row per round (more than 16 obstacles: Navigation's 32): the 32 lanes write 512
+                            // contiguous bytes and every lane's 16-byte slot has the same alignment, known at compile time.
+                            // Scalar stores with a stride of 16 bytes are 4-way bank conflicts (4 x 4 wavefronts per round);
+                            // the widest aligned stores need 4 (16-byte), 8 (two 8-byte) or 12 wavefronts.
+                            const int al = ((rd < NC ? rd * DC + C_OBS : S::STAGE_CAM + (rd - NC) * DT + T_OBS)) & 3;
+                            if (al == 0) {
+                                *reinterpret_cast<float4*>(q) = make_float4(vo[rd][0], vo[rd][1], vo[rd][2], vo[rd][3]);
+                            } else if (al == 2) {
+                                *reinterpret_cast<float2*>(q) = make_float2(vo[rd][0], vo[rd][1]);
+                                *reinterpret_cast<float2*>(q + 2) = make_float2(vo[rd][2], vo[rd][3]);
+                            } else {
+                                q[0] = vo[rd][0];
+                                *reinterpret_cast<float2*>(q + 1) = make_float2(vo[rd][1], vo[rd][2]);
+                                q[3] = vo[rd][3];
+                            }
+                        } else {
+                            q[0] = vo[rd][0]; q[1] = vo[rd][1]; q[2] = vo[rd][2]; q[3] = vo[rd][3];
+                        }
                     }
                 }
             }
@@ -944,6 +966,7 @@ __device__ __noinline__ void pack_observations(const Params& p, const int env0, 
             __syncwarp();
         }
         // ---- staged rows -> HBM
+        static_assert(!(S::BULK && S::CAM_SKEW != 0), "the 16-byte copy of the whole block expects dense camera rows");
         if (S::BULK && MATE2_COPYOUT == 1) {
             // plain 16-byte copies: every warp store covers 512 contiguous bytes; unlike the bulk copy there
             // is nothing to wait for before the block is reused (MATE2_COPYOUT)
@@ -979,13 +1002,34 @@ __device__ __noinline__ void pack_observations(const Params& p, const int env0, 
                 asm volatile("cp.async.bulk.commit_group;" ::: "memory");
             }
         } else {
+            // an environment's rows of one team are not a multiple of 16 bytes (MATE-4v2-9: 2 x 101 floats): each team's part
+            // leaves with the widest store its size allows (the caller's buffers are 16-byte aligned, so part i starts at
+            // a multiple of gcd(16, part bytes))
             __syncwarp();
-            if (NC > 0) {
-                float* dst = cam_obs0 + (size_t)i * S::CAM_ROW;
-                for (int k = lane; k < S::CAM_ROW; k += 32) dst[k] = stage[k];
-            }
-            float* dst = tgt_obs0 + (size_t)i * S::TGT_ROW;
-            for (int k = lane; k < S::TGT_ROW; k += 32) dst[k] = stage[S::STAGE_CAM + k];
+            auto copy_part = [&](float* dst, const float* src, auto nfloats_c, auto row4_c, auto skew4_c) {
+                constexpr int n = decltype(nfloats_c)::value;
+                constexpr int row4 = decltype(row4_c)::value, skew4 = decltype(skew4_c)::value;   // staged rows `skew4` chunks apart
+                if constexpr (n % 4 == 0) {
+#pragma unroll
+                    for (int it = 0; it < (n / 4 + 31) / 32; ++it) {
+                        const int k = it * 32 + lane;
+                        if (k < n / 4) __stcs(reinterpret_cast<float4*>(dst) + k, reinterpret_cast<const float4*>(src)[skew4 ? k + (k / row4) * skew4 : k]);
+                    }
+                } else if constexpr (n % 2 == 0) {
+#pragma unroll
+                    for (int it = 0; it < (n / 2 + 31) / 32; ++it) {
+                        const int k = it * 32 + lane;
+                        if (k < n / 2) __stcs(reinterpret_cast<float2*>(dst) + k, reinterpret_cast<const float2*>(src)[k]);
+                    }
+                } else {
+                    for (int k = lane; k < n; k += 32) dst[k] = src[k];
+                }
+            };
+            static_assert(S::CAM_SKEW == 0 || DC % 4 == 0, "skewed camera rows are copied in 16-byte chunks");
+            if (NC > 0) copy_part(cam_obs0 + (size_t)i * S::CAM_ROW, stage, std::integral_constant<int, S::CAM_ROW>{},
+                                  std::integral_constant<int, (DC / 4 > 0 ? DC / 4 : 1)>{}, std::integral_constant<int, (DCS - DC) / 4>{});
+            copy_part(tgt_obs0 + (size_t)i * S::TGT_ROW, stage + S::STAGE_CAM, std::integral_constant<int, S::TGT_ROW>{},
+                      std::integral_constant<int, 1>{}, std::integral_constant<int, 0>{});
             __syncwarp();
         }
     }
