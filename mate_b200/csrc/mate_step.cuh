@@ -90,6 +90,36 @@ struct Shape2 {
     static constexpr int STAGE_FLOATS = STAGE_CAM + ((TGT_ROW + 3) / 4) * 4;
     static constexpr bool BULK = (CAM_ROW % 4 == 0) && (TGT_ROW % 4 == 0);   // 16-byte aligned blocks per env
     static constexpr int E = NT + NO + NC;                     // entity slots (lanes of the scatter)
+    // Obstacle slots of the packer: a slot is 4 floats, a row's slots are contiguous, and scalar stores of lanes 16 bytes
+    // apart are 4-way bank conflicts.  Observer rows are therefore grouped by the ALIGNMENT of their obstacle block
+    // (16 bytes / 8 bytes / odd) into rounds of 32 / NO rows, and a round stores with the widest aligned type
+    // (1, 2 or 3 instructions instead of 4) -- unless the grouping needs more than one round more than plain row order.
+    struct ORounds { int n; int grouped; int row[40][4]; int cls[40]; };   // cls: 0 = 16-byte aligned, 2 = 8-byte, 1 = odd, -1 = mixed (scalar stores)
+    __host__ __device__ static constexpr int o_offset(int row) { return row < NC ? row * (DC + CAM_SKEW) + 22 + 5 * NT : STAGE_CAM + (row - NC) * DT + 27 + 7 * NC; }
+    __host__ __device__ static constexpr ORounds make_orounds() {
+        ORounds r{};
+        const int rpr = NO > 0 ? 32 / NO : 1, plain = (R + rpr - 1) / rpr;
+        for (int i = 0; i < 40; ++i) { r.cls[i] = -1; for (int j = 0; j < 4; ++j) r.row[i][j] = -1; }
+        if (NO == 0) { r.n = 0; return r; }
+        const int order[3] = {0, 2, 1};
+        int n = 0;
+        for (int k = 0; k < 3; ++k) {
+            int fill = 0;
+            for (int row = 0; row < R; ++row) {
+                const int al = o_offset(row) & 3, cls = al == 0 ? 0 : (al == 2 ? 2 : 1);
+                if (cls != order[k]) continue;
+                if (fill == 0) r.cls[n] = cls;
+                r.row[n][fill++] = row;
+                if (fill == rpr) { fill = 0; ++n; }
+            }
+            if (fill > 0) ++n;
+        }
+        if (n <= plain + 1) { r.n = n; r.grouped = 1; return r; }
+        for (int i = 0; i < 40; ++i) { r.cls[i] = -1; for (int j = 0; j < 4; ++j) r.row[i][j] = -1; }
+        for (int row = 0; row < R; ++row) r.row[row / rpr][row % rpr] = row;
+        r.n = plain;
+        return r;
+    }
     static constexpr int WARPS = MATE2_WARPS;
     static constexpr int ENVS_PER_CTA = WARPS * 32;
     static constexpr int QCAP = 64;
@@ -634,7 +664,8 @@ __device__ __noinline__ void pack_observations(const Params& p, const int env0, 
     constexpr int T_SELF = 13, T_CAM = 27, T_OBS = 27 + 7 * NC, T_TGT = 27 + 7 * NC + 4 * NO;
     constexpr int NOX = NO > 0 ? NO : 1;
     constexpr int RPR_T = 32 / NT, RPR_O = 32 / NOX, RPR_C = 32 / NCX;          // observer rows per round
-    constexpr int RND_T = (R + RPR_T - 1) / RPR_T, RND_O = (R + RPR_O - 1) / RPR_O, RND_C = (R + RPR_C - 1) / RPR_C;
+    constexpr typename S::ORounds ORND = S::make_orounds();
+    constexpr int RND_T = (R + RPR_T - 1) / RPR_T, RND_O = NO > 0 ? ORND.n : 1, RND_C = (R + RPR_C - 1) / RPR_C;
     const float f_sr = (float)p.tgt_sight_range, f_crad = (float)p.cam_radius;
     const float f_rmax = (float)p.cam_rmax, f_rot = (float)p.cam_rot_step, f_zoom = (float)p.cam_zoom_step;
     const float f_step1 = (float)p.tgt_step_size, f_step2 = (float)(p.tgt_step_size / 2.0);
@@ -661,8 +692,14 @@ __device__ __noinline__ void pack_observations(const Params& p, const int env0, 
     if (NO > 0) {
 #pragma unroll
         for (int rd = 0; rd < RND_O; ++rd) {
-            const int row = rd * RPR_O + o_sub;
-            const bool on = o_sub < RPR_O && row < R;
+            int row = rd * RPR_O + o_sub;
+            bool on = o_sub < RPR_O && row < R;
+            if (ORND.grouped) {
+                row = -1;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) row = (j < RPR_O && o_sub == j) ? ORND.row[rd][j] : row;
+                on = row >= 0;
+            }
             q_ptr[RND_T + rd] = stage + (on ? row_base(row) + (row < NC ? C_OBS : T_OBS) + 4 * o_idx : 0);
             m_idx[RND_T + rd] = on ? row * MW + (MW - 1) : 0;
             on_bits |= (uint32_t)on << (RND_T + rd);
@@ -898,12 +935,9 @@ __device__ __noinline__ void pack_observations(const Params& p, const int env0, 
                 for (int rd = 0; rd < RND_O; ++rd) {
                     if ((on_bits >> (RND_T + rd)) & 1u) {
                         float* q = q_ptr[RND_T + rd];
-                        if (RPR_O == 1) {
-                            // One observer row per round (more than 16 obstacles: Navigation's 32): the 32 lanes write 512
-                            // contiguous bytes and every lane's 16-byte slot has the same alignment, known at compile time.
-                            // Scalar stores with a stride of 16 bytes are 4-way bank conflicts (4 x 4 wavefronts per round);
-                            // the widest aligned stores need 4 (16-byte), 8 (two 8-byte) or 12 wavefronts.
-                            const int al = ((rd < NC ? rd * DC + C_OBS : S::STAGE_CAM + (rd - NC) * DT + T_OBS)) & 3;
+                        if (ORND.cls[rd] >= 0) {
+                            // every lane's 16-byte slot of this round has the same alignment, known at compile time
+                            const int al = ORND.cls[rd];
                             if (al == 0) {
                                 *reinterpret_cast<float4*>(q) = make_float4(vo[rd][0], vo[rd][1], vo[rd][2], vo[rd][3]);
                             } else if (al == 2) {
