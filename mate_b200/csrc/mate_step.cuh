@@ -33,6 +33,9 @@
 #include "mate_common.cuh"
 #include "mate_wrappers.cuh"
 
+#ifndef MATE2_ROLL_C
+#define MATE2_ROLL_C 5        // from this many cameras on, the loop over the observing camera of Camera.perceive stays rolled (instruction cache)
+#endif
 #ifndef MATE2_WARPS
 #define MATE2_WARPS 2          // warps per CTA (warps are independent; this only sets the CTA granularity)
 #endif
@@ -1440,25 +1443,32 @@ mate_step_kernel2(const __grid_constant__ Params p) {
                 ccw = build_cc_cache<NC, NO>(p, er);
                 if (env_ok) p.cc_clear[e] = ccw;
             }
-#pragma unroll
+            // With 8 cameras the fully unrolled loop nest (8 x 16 inlined range + sector tests, 50 KB of code) does not fit the
+            // 32 KB instruction cache and a fifth of the warps' stalls are instruction fetches: the loop over the observing
+            // camera stays rolled there (its own entries come from shared memory, its camera -> camera bits go through `cc_bits`)
+            constexpr bool ROLL_C = NC >= MATE2_ROLL_C;
+            unsigned long long cc_bits = 0ull;
+#pragma unroll (ROLL_C ? 1 : (NC > 0 ? NC : 1))
             for (int c = 0; c < NC; ++c) {
                 const float* cv = mycam + CV * c;
                 const float cs = cv[3], sn = cv[4], rs2 = cs * cs + sn * sn;   // heading scaled by Rs
                 const float ch = cospif(cv[2] * (1.0f / 360.0f)), ch2 = ch * ch;
+                const float mx = ROLL_C ? cv[0] : fcx[ROLL_C ? 0 : c], my = ROLL_C ? cv[1] : fcy[ROLL_C ? 0 : c];
                 uint32_t reach_t = 0, band_t = 0, reach_c = 0, band_c = 0;
 #pragma unroll
                 for (int t = 0; t < NT; ++t) {
-                    const int reach = fov_reach32(fcx[c], fcy[c], rs2, cs, sn, ch2, ftx[t], fty[t]);
+                    const int reach = fov_reach32(mx, my, rs2, cs, sn, ch2, ftx[t], fty[t]);
                     reach_t |= (uint32_t)(reach == 1) << t;
                     band_t |= (uint32_t)(reach == 2) << t;
                 }
 #pragma unroll
                 for (int j = 0; j < NC; ++j) {
-                    if (j == c) continue;
-                    const int reach = fov_reach32(fcx[c], fcy[c], rs2, cs, sn, ch2, fcx[j], fcy[j]);
+                    if (!ROLL_C && j == c) continue;
+                    const int reach = fov_reach32(mx, my, rs2, cs, sn, ch2, fcx[j], fcy[j]);
                     reach_c |= (uint32_t)(reach == 1) << j;
                     band_c |= (uint32_t)(reach == 2) << j;
                 }
+                if (ROLL_C) { reach_c &= ~(1u << c); band_c &= ~(1u << c); }   // the camera itself (the diagonal is set elsewhere)
                 if (band_t) reach_t |= resolve_fov_band(p, er, c, band_t, 0);
                 if (band_c) reach_c |= resolve_fov_band(p, er, c, band_c, 1);
                 pend |= (unsigned long long)reach_t << (c * NT);
@@ -1466,7 +1476,12 @@ mate_step_kernel2(const __grid_constant__ Params p) {
                 uint32_t clear_c = 0;
 #pragma unroll
                 for (int j = 0; j < NC; ++j) clear_c |= (uint32_t)((ccw >> (8 * j + c)) & 1ull) << j;
-                crow[c] |= reach_c & clear_c;   // bit_cam(j) == 1 << j
+                if (ROLL_C) cc_bits |= (unsigned long long)(reach_c & clear_c) << (8 * c);
+                else crow[ROLL_C ? 0 : c] |= reach_c & clear_c;   // bit_cam(j) == 1 << j
+            }
+            if (ROLL_C) {
+#pragma unroll
+                for (int c = 0; c < NC; ++c) crow[c] |= (uint32_t)(cc_bits >> (8 * c)) & 0xFFu;
             }
             if (view_active) {
 #pragma unroll
