@@ -264,7 +264,7 @@ int mate_b200_soft_coverage(MateSim* sim, const uint8_t* mask_ct, const uint8_t*
 /* Batched opponents for the single-team wrappers: GreedyTargetAgent
  * (mate/agents/greedy.py:235-365) for every target of every environment, driven like MultiCamera drives its
  * opponents (mate/wrappers/single_team.py:79-92, 261-279: observe -> communicate -> act).
- *   memory     dev double [B, Nt, MATE_AGENT_MEMORY], owned by the caller, carried from step to step: goal (-1 = none),
+ *   memory     dev double [MATE_AGENT_MEMORY, Nt, B] (field-major), owned by the caller, carried from step to step: goal (-1 = none),
  *              remembered non-empty warehouses (bit set), previous location x, y, previous noise x, y;
  *   reset_mask dev uint8 [B], nullable: environments whose agents are reset on the current state first
  *              (GreedyTargetAgent.reset: after env.reset and after an auto-reset);
@@ -283,9 +283,9 @@ int mate_b200_greedy_target_actions(MateSim* sim, double* memory, const uint8_t*
                                     void* stream);
 
 /* GreedyCameraAgent (mate/agents/greedy.py:14-232) for every camera of every environment, driven like MultiTarget
- * drives its opponents.  memory: dev double [B, Nc, 6 Nt + Nc + 4] owned by the caller (per camera: remembered target
- * states [Nt][4], time2forget [Nt], never_loaded [Nt], previous action [2], communication delay [Nc], known teammates
- * (bit set), own-state message pending); tracked: dev uint8 [B, Nc, Nt], the target flags of the cameras' CURRENT
+ * drives its opponents.  memory: dev double [6 Nt + Nc + 4, B, Nc] owned by the caller, FIELD-MAJOR (per camera the
+ * fields are: remembered target states [Nt][4], time2forget [Nt], never_loaded [Nt], previous action [2], communication
+ * delay [Nc], known teammates (bit set), own-state message pending); tracked: dev uint8 [B, Nc, Nt], the target flags of the cameras' CURRENT
  * observations; cam_act: dev float [B, Nc, 2].  Other arguments as for mate_b200_greedy_target_actions. */
 typedef struct MateCameraAgentReplay {
     const int8_t* binomial;   /* [B, Nc] outcome of binomial(1, 0.1), greedy.py:96 (-1 = not drawn)          */

@@ -51,7 +51,9 @@ class GreedyTargetAgent(TargetAgentBase):
     def bind(self, sim):
         """Allocate the team memory for a simulator (``mate_b200.sim.BatchedSim``)."""
         self._sim = sim
-        self.memory = torch.zeros((sim.B, sim.nt, _abi.AGENT_MEMORY), dtype=torch.float64, device=sim.device)
+        # stored field-major [6, Nt, B] (coalesced in the kernel, one thread per environment); `memory` is its [B, Nt, 6] view
+        self._memory = torch.zeros((_abi.AGENT_MEMORY, sim.nt, sim.B), dtype=torch.float64, device=sim.device)
+        self.memory = self._memory.permute(2, 1, 0)
         self.actions = torch.zeros((sim.B, sim.nt, 2), dtype=torch.float32, device=sim.device)
         self._serial = 0
 
@@ -75,7 +77,7 @@ class GreedyTargetAgent(TargetAgentBase):
                     setattr(rs, name, ctypes.cast(ctypes.c_void_p(t.data_ptr()), ctype))
         with torch.cuda.device(sim.device):
             _check(sim.lib, sim.lib.mate_b200_greedy_target_actions(
-                sim.handle, _dptr(self.memory), _dptr(reset_mask), self.noise_scale, self._seed % (2 ** 64), self._serial,
+                sim.handle, _dptr(self._memory), _dptr(reset_mask), self.noise_scale, self._seed % (2 ** 64), self._serial,
                 ctypes.byref(rs) if rs is not None else None, _dptr(self.actions), sim._stream()))  # pylint: disable=protected-access
         del keep
         self._serial += 1
@@ -113,7 +115,9 @@ class GreedyCameraAgent(CameraAgentBase):
     def bind(self, sim):
         self._sim = sim
         width = 6 * sim.nt + sim.nc + 4
-        self.memory = torch.zeros((sim.B, sim.nc, width), dtype=torch.float64, device=sim.device)
+        # stored field-major [M, B, Nc] (the kernel's accesses are coalesced); `memory` is the [B, Nc, M] view of it
+        self._memory = torch.zeros((width, sim.B, sim.nc), dtype=torch.float64, device=sim.device)
+        self.memory = self._memory.permute(1, 2, 0)
         self.actions = torch.zeros((sim.B, sim.nc, 2), dtype=torch.float32, device=sim.device)
         self._serial = 0
 
@@ -138,7 +142,7 @@ class GreedyCameraAgent(CameraAgentBase):
                     setattr(rs, name, ctypes.cast(ctypes.c_void_p(t.data_ptr()), ctype))
         with torch.cuda.device(sim.device):
             _check(sim.lib, sim.lib.mate_b200_greedy_camera_actions(
-                sim.handle, _dptr(self.memory), _dptr(tracked), _dptr(reset_mask), self._seed % (2 ** 64), self._serial,
+                sim.handle, _dptr(self._memory), _dptr(tracked), _dptr(reset_mask), self._seed % (2 ** 64), self._serial,
                 ctypes.byref(rs) if rs is not None else None, _dptr(self.actions), sim._stream()))  # pylint: disable=protected-access
         del keep
         self._serial += 1

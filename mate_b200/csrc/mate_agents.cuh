@@ -13,7 +13,15 @@
 namespace mate {
 
 constexpr uint32_t STREAM_AGENT_BINOMIAL = 16, STREAM_AGENT_SAMPLE = 17, STREAM_AGENT_CHOICE = 18, STREAM_AGENT_RESET = 19, STREAM_AGENT_DELAY = 20;
-constexpr int kAgentMemory = 6;   // per target: goal, non-empty warehouse set, previous x, y, previous noise x, y
+constexpr int kAgentMemory = 6;   // per target: goal, non-empty warehouse set, previous x, y, previous noise x, y; stored FIELD-MAJOR [6][Nt][B]
+
+// one agent's view of a field-major table: entry k of the agent is `stride` doubles after entry k - 1
+struct Field {
+    double* base;
+    size_t stride;
+    __device__ __forceinline__ double& operator[](int k) const { return base[(size_t)k * stride]; }
+    __device__ __forceinline__ Field from(int k) const { return Field{base + (size_t)k * stride, stride}; }
+};
 
 __global__ void greedy_target_kernel(const Params p, const int nt, double* __restrict__ memory, const uint8_t* __restrict__ reset_mask,
                                      const double noise_scale, const unsigned long long seed, const unsigned long long serial,
@@ -29,7 +37,7 @@ __global__ void greedy_target_kernel(const Params p, const int nt, double* __res
     // observe -> process_messages (greedy.py:330-336), and the sets that are broadcast
     uint32_t sent_and = 15u;
     for (int t = 0; t < nt; ++t) {
-        double* m = memory + ((size_t)e * nt + t) * kAgentMemory;
+        const Field m{memory + (size_t)t * p.num_envs + e, (size_t)nt * p.num_envs};
         const uint32_t tp = p.tgt_pack[(size_t)t * bp + e];
         if (reset) {   // reset(observation), greedy.py:265-277
             const double x = p.tgt_x[(size_t)t * bp + e], y = p.tgt_y[(size_t)t * bp + e];
@@ -53,7 +61,7 @@ __global__ void greedy_target_kernel(const Params p, const int nt, double* __res
     }
     // receive_responses (greedy.py:355-365) + act (greedy.py:289-328)
     for (int t = 0; t < nt; ++t) {
-        double* m = memory + ((size_t)e * nt + t) * kAgentMemory;
+        const Field m{memory + (size_t)t * p.num_envs + e, (size_t)nt * p.num_envs};
         const uint32_t tp = p.tgt_pack[(size_t)t * bp + e];
         const double x = p.tgt_x[(size_t)t * bp + e], y = p.tgt_y[(size_t)t * bp + e];
         const double step_size = p.tgt_step_size / (double)tp_capacity(tp);
@@ -113,10 +121,12 @@ __global__ void greedy_target_kernel(const Params p, const int nt, double* __res
 // state, tracked target states filtered by the recipient's range; environment.py:1249-1269 routes them through the
 // message queues) are two registers of the sender, read by the recipients with warp shuffles between the send and
 // the receive phase.
-// Layout per camera (doubles): [4 Nt] memory (x, y, sight range, is_loaded) | [Nt] time2forget | [Nt] never_loaded |
-// [2] previous action | [Nc] communication delay | neighbours (bit set) | has_state_message.
+// Fields per camera (doubles): [4 Nt] memory (x, y, sight range, is_loaded) | [Nt] time2forget | [Nt] never_loaded |
+// [2] previous action | [Nc] communication delay | neighbours (bit set) | has_state_message; stored FIELD-MAJOR,
+// [M][B * Nc] (round 1 and the first half of round 2: one record per agent, every access of a warp 32 sectors wide).
 // =============================================================================================
 __host__ __device__ inline int camera_agent_memory(int nc, int nt) { return 6 * nt + nc + 4; }
+
 
 constexpr int kCameraAgentThreads = 128;
 
@@ -152,8 +162,10 @@ greedy_camera_kernel(const Params p, const int nc, const int nt, double* __restr
         loaded |= (uint32_t)(tp_goal(tp) >= 0 && tp_weight(tp) > 0) << t;
     }
     const double my_x = p.cam_x[(size_t)c * bp + e], my_y = p.cam_y[(size_t)c * bp + e];
-    double* const m = memory + (size_t)ag * M;
-    double* const mem = m, *t2f = m + 4 * nt, *never = m + 5 * nt, *prev = m + 6 * nt, *delay = m + 6 * nt + 2;
+    // the memory is stored field-major, [M][B * Nc]: the agents of a warp read and write neighbouring doubles
+    (void)M;
+    const Field m{memory + ag, (size_t)total};
+    const Field mem = m, t2f = m.from(4 * nt), never = m.from(5 * nt), prev = m.from(6 * nt), delay = m.from(6 * nt + 2);
     // ---- observe -> process_messages (greedy.py:104-115); send_responses (greedy.py:156-194)
     uint32_t msg_state = 0;                 // bit k: my state goes to camera k
     unsigned long long msg_targets = 0ull;  // byte k: the tracked targets I report to camera k
@@ -244,10 +256,12 @@ greedy_camera_kernel(const Params p, const int nc, const int nt, double* __restr
             else if (best <= sqrt(p.cam_area_product / 180.0) * 0.5) view = 180.0;
             else {
                 double b = 180.0;
-                for (int it = 0; it < 20; ++it) {
+                for (int it = 0; it < 20; ++it) {   // the reference's 20 fixed-point steps; a step that reproduces its input ends them all
                     sincospi(fmin(b * 0.5, 90.0) * (1.0 / 180.0), &sn, &cs);
                     const double sight = best * (1.0 + sn);
-                    b = p.cam_area_product / (sight * sight);
+                    const double b_next = p.cam_area_product / (sight * sight);
+                    if (b_next == b) break;
+                    b = b_next;
                 }
                 view = fmin(fmax(b, p.cam_min_view), 180.0);
             }

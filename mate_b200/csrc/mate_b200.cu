@@ -439,8 +439,11 @@ extern "C" int mate_b200_auxiliary_terms(MateSim* sim, const MateStepAux* aux, c
         (sim->cfg.num_cameras > 0 && (!aux->mask_ct || !aux->mask_tc)))
         return fail(MATE_EINVAL, "auxiliary_terms needs mask_ct, mask_tc, coverage, target_dones, is_colliding, warehouse_dist, tgt_goal, tgt_empty_bits");
     CUDA_TRY(cudaSetDevice(sim->device));
+    if (((uintptr_t)cam_terms & 15) || ((uintptr_t)tgt_terms & 15) || ((uintptr_t)aux->warehouse_dist & 15))
+        return fail(MATE_EINVAL, "term tensors and warehouse_dist must be 16-byte aligned");
     const int threads = 128;
-    aux_terms_kernel<<<(sim->num_envs + threads - 1) / threads, threads, 0, (cudaStream_t)stream>>>(
+    const long long agents = (long long)sim->num_envs * (sim->cfg.num_cameras + sim->cfg.num_targets);
+    aux_terms_kernel<<<(unsigned)((agents + threads - 1) / threads), threads, 0, (cudaStream_t)stream>>>(
         *aux, rewards, soft_matrix, cam_terms, tgt_terms, sim->num_envs, sim->cfg.num_cameras, sim->cfg.num_targets);
     sim->launches += 1;
     cudaError_t err = cudaGetLastError();

@@ -268,64 +268,68 @@ __global__ void decode_actions_kernel(const int64_t* __restrict__ index, const f
 
 // Per-agent terms of AuxiliaryCameraRewards / AuxiliaryTargetRewards / MoreTrainingInformation
 // (mate/wrappers/auxiliary_camera_rewards.py:140-149, auxiliary_target_rewards.py:135-177,
-// more_training_information.py:61-82) from the auxiliary outputs of the last step.  One thread per
-// environment: the inputs are ~150 bytes per environment, the outputs 4 (8 Nc + 16 Nt) bytes.
+// more_training_information.py:61-82) from the auxiliary outputs of the last step.  One thread per AGENT (first all
+// cameras, then all targets, so that a warp holds one kind): an agent's 8 / 16 output floats leave as two / four
+// 16-byte stores, neighbouring threads read neighbouring mask rows.  (Round 1: one thread per environment wrote its
+// 160 floats with scalar stores 640 bytes apart.)
 __global__ void aux_terms_kernel(const MateStepAux ax, const float* __restrict__ rewards, const float* __restrict__ soft,
                                  float* __restrict__ cam_terms, float* __restrict__ tgt_terms, int num_envs, int nc, int nt) {
-    const int e = blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= num_envs) return;
-    const float cov = ax.coverage[(size_t)e * 3], cov_real = ax.coverage[(size_t)e * 3 + 1], transport = ax.coverage[(size_t)e * 3 + 2];
-    const float cam_reward = rewards[(size_t)e * 2], tgt_reward = rewards[(size_t)e * 2 + 1];
-    uint32_t tracked = 0;   // bit t: some camera sees target t
-    for (int c = 0; c < nc; ++c) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long num_cam = (long long)num_envs * nc, num_tgt = (long long)num_envs * nt;
+    if (i >= num_cam + num_tgt) return;
+    if (i < num_cam) {
+        const int e = (int)(i / nc), c = (int)(i - (long long)e * nc);
         int num_tracked = 0, sensed = 0;
         float soft_sum = 0.f, soft_max = -3.0e38f;   // auxiliary_camera_rewards.py:130-138
         for (int t = 0; t < nt; ++t) {
-            const int seen = ax.mask_ct[((size_t)e * nc + c) * nt + t] != 0;
+            const int seen = ax.mask_ct[(size_t)i * nt + t] != 0;
             num_tracked += seen;
-            tracked |= (uint32_t)seen << t;
             sensed |= ax.mask_tc[((size_t)e * nt + t) * nc + c] != 0;
             if (soft) {
-                const float v = soft[((size_t)e * nc + c) * nt + t];
+                const float v = soft[(size_t)i * nt + t];
                 soft_sum += seen ? v : 0.f;
                 soft_max = fmaxf(soft_max, v);
             }
         }
-        float* q = cam_terms + ((size_t)e * nc + c) * MATE_CAM_TERMS;
-        q[0] = cam_reward; q[1] = cov; q[2] = cov_real; q[3] = transport;
-        q[4] = soft ? (num_tracked > 0 ? soft_sum : tanhf(soft_max)) : 0.f;
-        q[5] = (float)num_tracked; q[6] = 1.f; q[7] = (float)sensed;
+        float4* q = reinterpret_cast<float4*>(cam_terms + (size_t)i * MATE_CAM_TERMS);
+        q[0] = make_float4(rewards[(size_t)e * 2], ax.coverage[(size_t)e * 3], ax.coverage[(size_t)e * 3 + 1], ax.coverage[(size_t)e * 3 + 2]);
+        q[1] = make_float4(soft ? (num_tracked > 0 ? soft_sum : tanhf(soft_max)) : 0.f, (float)num_tracked, 1.f, (float)sensed);
+        return;
     }
-    for (int t = 0; t < nt; ++t) {
-        const size_t i = (size_t)e * nt + t;
-        const int goal = ax.tgt_goal[i], empty = ax.tgt_empty_bits[i];
-        float wd[NW];
-        float nearest_open = (float)kTerrain;   // TERRAIN_WIDTH / 2 when every warehouse is known to be empty
-        bool any_open = false;
-        for (int w = 0; w < NW; ++w) {
-            wd[w] = fmaxf(ax.warehouse_dist[i * NW + w] - (float)kWarehouseRadius, 0.f);
-            if (!((empty >> w) & 1)) { nearest_open = any_open ? fminf(nearest_open, wd[w]) : wd[w]; any_open = true; }
+    const long long k = i - num_cam;          // (environment, target)
+    const int e = (int)(k / nt), t = (int)(k - (long long)e * nt);
+    bool tracked = false;                     // some camera sees target t
+    float soft_sum = 0.f, soft_max = -3.0e38f;
+    for (int c = 0; c < nc; ++c) {
+        const size_t j = ((size_t)e * nc + c) * nt + t;
+        const bool seen = ax.mask_ct[j] != 0;
+        tracked = tracked || seen;
+        if (soft) {
+            const float v = soft[j];
+            soft_sum += seen ? v : 0.f;
+            soft_max = fmaxf(soft_max, v);
         }
-        const float goal_distance = goal >= 0 ? wd[goal] : nearest_open;               // auxiliary_target_rewards.py:143-149
-        const float info_goal_distance = goal >= 0 ? wd[goal] : (float)kTerrain;       // more_training_information.py:72
-        float* q = tgt_terms + i * MATE_TGT_TERMS;
-        q[0] = tgt_reward; q[1] = cov; q[2] = cov_real; q[3] = transport;
-        q[4] = goal_distance / (float)(2.0 * kTerrain);
-        float soft_t = 0.f;                           // auxiliary_target_rewards.py:151-162
-        if (soft && nc > 0) {
-            float soft_sum = 0.f, soft_max = -3.0e38f;
-            for (int c = 0; c < nc; ++c) {
-                const float v = soft[((size_t)e * nc + c) * nt + t];
-                soft_sum += ax.mask_ct[((size_t)e * nc + c) * nt + t] != 0 ? v : 0.f;
-                soft_max = fmaxf(soft_max, v);
-            }
-            soft_t = ((tracked >> t) & 1u) ? soft_sum : tanhf(soft_max);
-        }
-        q[5] = (float)(ax.target_dones[i] != 0); q[6] = soft_t; q[7] = (float)((tracked >> t) & 1u);
-        q[8] = (float)(ax.is_colliding[i] != 0); q[9] = 1.f;
-        q[10] = (float)goal; q[11] = info_goal_distance;
-        for (int w = 0; w < NW; ++w) q[12 + w] = wd[w];
     }
+    const int goal = ax.tgt_goal[k], empty = ax.tgt_empty_bits[k];
+    const float4 dist = reinterpret_cast<const float4*>(ax.warehouse_dist)[k];
+    float wd[NW] = {fmaxf(dist.x - (float)kWarehouseRadius, 0.f), fmaxf(dist.y - (float)kWarehouseRadius, 0.f),
+                    fmaxf(dist.z - (float)kWarehouseRadius, 0.f), fmaxf(dist.w - (float)kWarehouseRadius, 0.f)};
+    float nearest_open = (float)kTerrain;     // TERRAIN_WIDTH / 2 when every warehouse is known to be empty
+    bool any_open = false;
+    float at_goal = 0.f;
+#pragma unroll
+    for (int w = 0; w < NW; ++w) {
+        if (!((empty >> w) & 1)) { nearest_open = any_open ? fminf(nearest_open, wd[w]) : wd[w]; any_open = true; }
+        at_goal = goal == w ? wd[w] : at_goal;
+    }
+    const float goal_distance = goal >= 0 ? at_goal : nearest_open;               // auxiliary_target_rewards.py:143-149
+    const float info_goal_distance = goal >= 0 ? at_goal : (float)kTerrain;       // more_training_information.py:72
+    const float soft_t = (soft && nc > 0) ? (tracked ? soft_sum : tanhf(soft_max)) : 0.f;   // auxiliary_target_rewards.py:151-162
+    float4* q = reinterpret_cast<float4*>(tgt_terms + (size_t)k * MATE_TGT_TERMS);
+    q[0] = make_float4(rewards[(size_t)e * 2 + 1], ax.coverage[(size_t)e * 3], ax.coverage[(size_t)e * 3 + 1], ax.coverage[(size_t)e * 3 + 2]);
+    q[1] = make_float4(goal_distance / (float)(2.0 * kTerrain), (float)(ax.target_dones[k] != 0), soft_t, (float)tracked);
+    q[2] = make_float4((float)(ax.is_colliding[k] != 0), 1.f, (float)goal, info_goal_distance);
+    q[3] = make_float4(wd[0], wd[1], wd[2], wd[3]);
 }
 
 // =============================================================================================
