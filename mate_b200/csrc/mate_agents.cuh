@@ -153,7 +153,7 @@ greedy_camera_kernel(const Params p, const int nc, const int nt, double* __restr
     const bool reset = reset_mask != nullptr && reset_mask[e] != 0;
     const RngKey key{seed, (uint32_t)(p.env_index_base + e), 0x4341474Eu /* 'CAGN' */};
     const uint32_t draw = (uint32_t)serial * 64u;
-    const double threshold = kRangeFactor * p.cam_rmax;
+    const double threshold = kRangeFactor * p.cam_rmax, thr2 = threshold * threshold;
     double tx[MAXN], ty[MAXN];
     uint32_t loaded = 0;
     for (int t = 0; t < nt; ++t) {
@@ -201,9 +201,10 @@ greedy_camera_kernel(const Params p, const int nc, const int nt, double* __restr
             if (!(has_state || seen != 0u) || k == c || delay[k] > 0.0) continue;
             uint32_t targets = 0;
             if (seen != 0u && ((neighbours >> k) & 1u)) {   // the recipient's range (all cameras share max_sight_range)
-                for (int t = 0; t < nt; ++t) {
-                    const double dx = tx[t] - kx, dy = ty[t] - ky;
-                    if (((seen >> t) & 1u) && sqrt(dx * dx + dy * dy) < threshold) targets |= 1u << t;
+                for (int t = 0; t < nt; ++t) {   // norm < threshold, decided on squares; the square root only inside a 1e-12 band
+                    const double dx = tx[t] - kx, dy = ty[t] - ky, d2 = dx * dx + dy * dy;
+                    if (!((seen >> t) & 1u) || d2 > thr2 * (1.0 + 1e-12)) continue;
+                    if (d2 < thr2 * (1.0 - 1e-12) || sqrt(d2) < threshold) targets |= 1u << t;
                 }
             }
             if (has_state || targets != 0u) {
