@@ -7,13 +7,16 @@
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
+#include <chrono>
 #include <cstring>
+#include <memory>
 #include <string>
 #include <vector>
 
 #include "mate_step.cuh"
 #include "mate_wrappers.cuh"
 #include "mate_agents.cuh"
+#include "mate_hostpath.cuh"
 
 using namespace mate;
 
@@ -135,6 +138,18 @@ struct MateSim {
     float *h_cam_act = nullptr, *h_tgt_act = nullptr, *h_cam_obs = nullptr, *h_tgt_obs = nullptr, *h_rewards = nullptr;
     uint8_t* h_done = nullptr;
     bool host_ready = false;
+    // compacted device -> host leg (mate_hostpath.cuh): region 0 = camera rows, 1 = target rows
+    static constexpr int kMaxHostChunks = 64;
+    int compact_mode = 0;                     // 1: rows cross the link compacted and are expanded by host threads
+    uint4* d_compact[2] = {nullptr, nullptr}; // compact streams (a launch chunk's stream starts where its dense rows start)
+    CompactEntry* d_table[2] = {nullptr, nullptr};
+    unsigned int* d_count = nullptr;          // [kMaxHostChunks][2] chunks kept
+    uint4* p_compact[2] = {nullptr, nullptr}; // pinned host copies of the above
+    CompactEntry* p_table[2] = {nullptr, nullptr};
+    unsigned int* p_count = nullptr;
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t e_counts[kMaxHostChunks] = {}, e_stream[kMaxHostChunks] = {};
+    std::unique_ptr<ExpandPool> pool;
 };
 
 extern "C" const char* mate_b200_last_error(void) { return g_error.c_str(); }
@@ -303,6 +318,13 @@ extern "C" int mate_b200_destroy(MateSim* sim) {
         for (int i = 0; i < MateSim::kHostStreams; ++i) { cudaStreamDestroy(sim->hstreams[i]); cudaEventDestroy(sim->hevents[i]); }
         cudaFree(sim->h_cam_act); cudaFree(sim->h_tgt_act); cudaFree(sim->h_cam_obs); cudaFree(sim->h_tgt_obs);
         cudaFree(sim->h_rewards); cudaFree(sim->h_done);
+        sim->pool.reset();
+        for (int r = 0; r < 2; ++r) { cudaFree(sim->d_compact[r]); cudaFree(sim->d_table[r]); cudaFreeHost(sim->p_compact[r]); cudaFreeHost(sim->p_table[r]); }
+        cudaFree(sim->d_count); cudaFreeHost(sim->p_count);
+        if (sim->copy_stream) {
+            cudaStreamDestroy(sim->copy_stream);
+            for (int i = 0; i < MateSim::kMaxHostChunks; ++i) { cudaEventDestroy(sim->e_counts[i]); cudaEventDestroy(sim->e_stream[i]); }
+        }
     }
     if (sim->side) { cudaStreamSynchronize(sim->side); cudaStreamDestroy(sim->side); }
     if (sim->side_event) cudaEventDestroy(sim->side_event);
@@ -669,6 +691,35 @@ static int ensure_host_path(MateSim* sim) {
     CUDA_TRY(cudaMalloc(&sim->h_tgt_obs, sizeof(float) * B * nt * sim->kernel.dt));
     CUDA_TRY(cudaMalloc(&sim->h_rewards, sizeof(float) * B * 2));
     CUDA_TRY(cudaMalloc(&sim->h_done, B));
+    // compacted device -> host leg: opt-in with MATE_B200_HOST_COMPACT=1 (measured 0 - 10 % faster than the dense copy with
+    // 15 host threads, slower with fewer: profiles/r2v_hostpath.md); needs row blocks that are multiples of 16 bytes
+    sim->compact_mode = 0;
+    if (const char* v = getenv("MATE_B200_HOST_COMPACT")) sim->compact_mode = v[0] == '1' ? 1 : 0;
+    if (sim->compact_mode) {
+        const size_t region_bytes[2] = {sizeof(float) * B * nc * sim->kernel.dc, sizeof(float) * B * nt * sim->kernel.dt};
+        for (int r = 0; r < 2; ++r) {
+            if (region_bytes[r] == 0) continue;
+            const size_t chunks = region_bytes[r] / 16 + 8, blocks = chunks / kCompactBlock + MateSim::kMaxHostChunks + 1;
+            CUDA_TRY(cudaMalloc(&sim->d_compact[r], chunks * 16));
+            CUDA_TRY(cudaMalloc(&sim->d_table[r], blocks * sizeof(CompactEntry)));
+            CUDA_TRY(cudaMallocHost(&sim->p_compact[r], chunks * 16));
+            CUDA_TRY(cudaMallocHost(&sim->p_table[r], blocks * sizeof(CompactEntry)));
+        }
+        CUDA_TRY(cudaMalloc(&sim->d_count, sizeof(unsigned int) * MateSim::kMaxHostChunks * 2));
+        CUDA_TRY(cudaMallocHost(&sim->p_count, sizeof(unsigned int) * MateSim::kMaxHostChunks * 2));
+        CUDA_TRY(cudaStreamCreateWithFlags(&sim->copy_stream, cudaStreamNonBlocking));
+        for (int i = 0; i < MateSim::kMaxHostChunks; ++i) {
+            CUDA_TRY(cudaEventCreateWithFlags(&sim->e_counts[i], cudaEventDisableTiming));
+            CUDA_TRY(cudaEventCreateWithFlags(&sim->e_stream[i], cudaEventDisableTiming));
+        }
+        // expansion threads: all host threads but the caller's; processes that share the host (one per GPU) share them
+        int threads = (int)std::thread::hardware_concurrency();
+        int sharers = 1;
+        if (const char* v = getenv("LOCAL_WORLD_SIZE")) sharers = std::max(1, atoi(v));
+        threads = std::max(1, threads / sharers - 1);
+        if (const char* v = getenv("MATE_B200_HOST_THREADS")) threads = std::max(1, atoi(v));
+        sim->pool.reset(new ExpandPool(std::min(threads, 64), sim->device));
+    }
     sim->host_ready = true;
     return MATE_OK;
 }
@@ -695,6 +746,92 @@ extern "C" int mate_b200_step_host(MateSim* sim, const float* cam_act, const flo
     // callers that use non-blocking streams of their own synchronise them before this call (include/mate_b200.h)
     CUDA_TRY(cudaEventRecord(sim->hevents[0], nullptr));
     for (int i = 0; i < MateSim::kHostStreams; ++i) CUDA_TRY(cudaStreamWaitEvent(sim->hstreams[i], sim->hevents[0], 0));
+    // ---- compacted device -> host leg (mate_hostpath.cuh): every launch chunk's rows are compacted on the device, the
+    //      compact streams cross the link one after the other, host threads expand them into the caller's buffers
+    const int num_chunks = (B + chunk - 1) / chunk;
+    const bool compact = sim->compact_mode && num_chunks <= MateSim::kMaxHostChunks && B % 4 == 0 &&
+                         !((uintptr_t)cam_obs & 3) && !((uintptr_t)tgt_obs & 3);
+    if (compact) {
+        static const bool trace = getenv("MATE_B200_HOST_TRACE") != nullptr;
+        const auto t_start = std::chrono::steady_clock::now();
+        auto since = [&]() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_start).count(); };
+        double t_enq = 0, t_counts = 0, t_last_stream = 0;
+        const size_t per_env[2] = {(size_t)nc * dc * 4, (size_t)nt * dt * 4};   // bytes of rows per environment and region
+        float* const host_rows[2] = {cam_obs, tgt_obs};
+        float* const dev_rows[2] = {sim->h_cam_obs, sim->h_tgt_obs};
+        std::vector<long long> table_base(2 * (num_chunks + 1), 0);
+        CUDA_TRY(cudaMemsetAsync(sim->d_count, 0, sizeof(unsigned int) * MateSim::kMaxHostChunks * 2, sim->hstreams[0]));
+        CUDA_TRY(cudaEventRecord(sim->hevents[1], sim->hstreams[0]));
+        for (int i = 1; i < MateSim::kHostStreams; ++i) CUDA_TRY(cudaStreamWaitEvent(sim->hstreams[i], sim->hevents[1], 0));
+        int kc = 0;
+        for (int begin = 0; begin < B; begin += chunk, ++kc) {
+            const int count = std::min(chunk, B - begin);
+            cudaStream_t s = sim->hstreams[kc % MateSim::kHostStreams];
+            if (nc) CUDA_TRY(cudaMemcpyAsync(sim->h_cam_act + (size_t)begin * nc * 2, cam_act + (size_t)begin * nc * 2, sizeof(float) * count * nc * 2, cudaMemcpyHostToDevice, s));
+            CUDA_TRY(cudaMemcpyAsync(sim->h_tgt_act + (size_t)begin * nt * 2, tgt_act + (size_t)begin * nt * 2, sizeof(float) * count * nt * 2, cudaMemcpyHostToDevice, s));
+            if (int rc = launch_range(sim, p, begin, count, s)) return rc;
+            for (int r = 0; r < 2; ++r) {
+                table_base[2 * (kc + 1) + r] = table_base[2 * kc + r];
+                if (per_env[r] == 0) continue;
+                const size_t first = (size_t)begin * per_env[r] / 16;            // B % 4 == 0 and chunk % 4 == 0: whole chunks
+                const long long nchunks = (long long)((size_t)count * per_env[r] / 16);
+                const long long nblocks = (nchunks + kCompactBlock - 1) / kCompactBlock;
+                CompactEntry* table = sim->d_table[r] + table_base[2 * kc + r];
+                table_base[2 * (kc + 1) + r] += nblocks;
+                compact_chunks_kernel<<<1184, 128, 0, s>>>(reinterpret_cast<const uint4*>(dev_rows[r]) + first, nchunks,
+                                                           sim->d_compact[r] + first, table, sim->d_count + 2 * kc + r);
+                CUDA_TRY(cudaMemcpyAsync(sim->p_table[r] + table_base[2 * kc + r], table, sizeof(CompactEntry) * nblocks, cudaMemcpyDeviceToHost, s));
+            }
+            sim->launches += (nc ? 2 : 1);
+            CUDA_TRY(cudaMemcpyAsync(sim->p_count + 2 * kc, sim->d_count + 2 * kc, sizeof(unsigned int) * 2, cudaMemcpyDeviceToHost, s));
+            CUDA_TRY(cudaMemcpyAsync(rewards + (size_t)begin * 2, sim->h_rewards + (size_t)begin * 2, sizeof(float) * count * 2, cudaMemcpyDeviceToHost, s));
+            CUDA_TRY(cudaMemcpyAsync(done + begin, sim->h_done + begin, count, cudaMemcpyDeviceToHost, s));
+            CUDA_TRY(cudaEventRecord(sim->e_counts[kc], s));
+        }
+        t_enq = since();
+        // the sizes are known once a chunk's kernels have run: its compact streams go on the copy stream in chunk order
+        const int pieces = std::max(1, sim->pool->size());
+        kc = 0;
+        for (int begin = 0; begin < B; begin += chunk, ++kc) {
+            CUDA_TRY(cudaEventSynchronize(sim->e_counts[kc]));
+            for (int r = 0; r < 2; ++r) {
+                if (per_env[r] == 0 || sim->p_count[2 * kc + r] == 0) continue;
+                const size_t first = (size_t)begin * per_env[r] / 16;
+                CUDA_TRY(cudaMemcpyAsync(sim->p_compact[r] + first, sim->d_compact[r] + first, (size_t)sim->p_count[2 * kc + r] * 16,
+                                         cudaMemcpyDeviceToHost, sim->copy_stream));
+            }
+            CUDA_TRY(cudaEventRecord(sim->e_stream[kc], sim->copy_stream));
+            // expansion: the pool's threads wait for the chunk's stream themselves, so the caller's thread goes on to the next sizes
+            const int count = std::min(chunk, B - begin);
+            for (int r = 0; r < 2; ++r) {
+                if (per_env[r] == 0) continue;
+                const size_t first = (size_t)begin * per_env[r] / 16;
+                const long long nchunks = (long long)((size_t)count * per_env[r] / 16);
+                const long long nblocks = (nchunks + kCompactBlock - 1) / kCompactBlock;
+                const long long per_piece = (nblocks + pieces - 1) / pieces;
+                __m128i* dst = reinterpret_cast<__m128i*>(host_rows[r]) + first;
+                const bool aligned = (((uintptr_t)dst) & 15) == 0;
+                for (long long b0 = 0; b0 < nblocks; b0 += per_piece)
+                    sim->pool->submit(ExpandPool::Work{sim->p_table[r] + table_base[2 * kc + r], reinterpret_cast<const __m128i*>(sim->p_compact[r] + first),
+                                                       dst, nchunks, b0, std::min(nblocks, b0 + per_piece), aligned, sim->e_stream[kc]});
+            }
+        }
+        t_counts = since();
+        CUDA_TRY(cudaStreamSynchronize(sim->copy_stream));
+        t_last_stream = since();
+        sim->pool->wait();
+        for (int i = 0; i < MateSim::kHostStreams; ++i) CUDA_TRY(cudaStreamSynchronize(sim->hstreams[i]));
+        if (trace) {
+            unsigned long long kept = 0;
+            for (int i = 0; i < 2 * num_chunks; ++i) kept += sim->p_count[i];
+            fprintf(stderr, "step_host compact: enqueued %.2f ms, sizes known + copies enqueued %.2f, last stream arrived %.2f, expanded %.2f; kept %.1f MB of %.1f MB, %d threads\n",
+                    t_enq, t_counts, t_last_stream, since(), kept * 16 / 1e6, (per_env[0] + per_env[1]) * (double)B / 1e6, sim->pool->size());
+        }
+        if ((flags & MATE_STEP_AUTO_RESET) && sim->refill_mode &&
+            (sim->refill_mode == 2 || ++sim->steps_since_refill >= sim->refill_period))
+            return launch_prepare(sim, nullptr);
+        return MATE_OK;
+    }
     int k = 0;
     for (int begin = 0; begin < B; begin += chunk, ++k) {
         const int count = std::min(chunk, B - begin);

@@ -1,0 +1,175 @@
+// mate_hostpath.cuh -- the device -> host leg of mate_b200_step_host.
+//
+// The observation rows of a step are 6.2 KB per environment (MATE-4v8-9) and 55 % of their 16-byte chunks are zero
+// (entities the observer does not see).  The plain path copies them densely and is bound by the PCIe link (407 MB per
+// step of 65 536 environments at 57 GB/s = 7.1 ms).  Here the rows are COMPACTED on the device (zero chunks dropped, one
+// bit per chunk), the compact stream crosses the link, and a pool of host threads EXPANDS it into the caller's buffers
+// with streaming stores while the next pieces are still in flight.  Lossless: the caller sees exactly the bytes of the
+// dense copy (tests/test_cuda_parity.py::test_step_host_*).  What bounds it then is the host's memory system (measured on
+// the B200 box's 16 host threads, scratch/host_expand_probe.cu: 80 GB/s of expanded rows while the DMA runs at 40 GB/s).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <emmintrin.h>
+
+#include <condition_variable>
+#include <cstdint>
+#include <deque>
+#include <mutex>
+#include <thread>
+#include <vector>
+
+namespace mate {
+
+constexpr int kCompactBlock = 256;                   // 16-byte chunks per block: one table entry
+constexpr int kCompactWords = kCompactBlock / 32;    // bitmap words per block
+struct CompactEntry {
+    uint32_t offset;                                 // position of the block's first kept chunk in the compact stream
+    uint32_t words[kCompactWords];                   // bit k of word w: chunk 32 w + k of the block is not all-zero
+};
+
+// One warp per block of 256 chunks: the block's chunks stay in registers between the vote and the packed store; the
+// position in the compact stream comes from one atomicAdd per block (the order of the blocks in the stream is
+// arbitrary, the table records it).
+__global__ void compact_chunks_kernel(const uint4* __restrict__ src, const long long nchunks, uint4* __restrict__ dst,
+                                      CompactEntry* __restrict__ table, unsigned int* __restrict__ counter) {
+    const int lane = threadIdx.x & 31;
+    const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+    const long long nblocks = (nchunks + kCompactBlock - 1) / kCompactBlock;
+    for (long long b = warp; b < nblocks; b += nwarps) {
+        uint4 v[kCompactWords];
+        uint32_t words[kCompactWords];
+        int total = 0;
+#pragma unroll
+        for (int it = 0; it < kCompactWords; ++it) {
+            const long long k = b * kCompactBlock + it * 32 + lane;
+            v[it] = k < nchunks ? src[k] : make_uint4(0u, 0u, 0u, 0u);
+            words[it] = __ballot_sync(0xffffffffu, (v[it].x | v[it].y | v[it].z | v[it].w) != 0u);
+            total += __popc(words[it]);
+        }
+        uint32_t base = 0;
+        if (lane == 0) base = atomicAdd(counter, (unsigned int)total);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        uint32_t run = base;
+#pragma unroll
+        for (int it = 0; it < kCompactWords; ++it) {
+            if ((words[it] >> lane) & 1u) dst[run + __popc(words[it] & ((1u << lane) - 1u))] = v[it];
+            run += __popc(words[it]);
+            if (lane == it) table[b].words[it] = words[it];
+        }
+        if (lane == 0) table[b].offset = base;
+    }
+}
+
+// Expand blocks [b0, b1) of a region: dst = the caller's dense rows (16-byte chunks), src = the compact stream.
+// The next compact chunk is always loaded and kept only if the bit is set (no branch per chunk); the stream buffer is
+// one chunk longer than its content.
+inline void expand_blocks(const CompactEntry* table, const __m128i* stream, __m128i* dst, long long nchunks, long long b0,
+                          long long b1, bool aligned) {
+    const __m128i zero = _mm_setzero_si128();
+    for (long long b = b0; b < b1; ++b) {
+        const CompactEntry& entry = table[b];
+        const __m128i* s = stream + entry.offset;
+        __m128i* d = dst + b * kCompactBlock;
+        const long long left = nchunks - b * kCompactBlock;
+        for (int w = 0; w < kCompactWords; ++w) {
+            const long long rem = left - 32 * w;
+            if (rem <= 0) break;
+            const int n = rem < 32 ? (int)rem : 32;
+            const uint32_t m = entry.words[w];
+            __m128i* dw = d + 32 * w;
+            if (aligned) {
+                if (m == 0u) {
+                    for (int k = 0; k < n; ++k) _mm_stream_si128(dw + k, zero);
+                } else {
+                    for (int k = 0; k < n; ++k) {
+                        const uint32_t bit = (m >> k) & 1u;
+                        const __m128i x = _mm_and_si128(_mm_loadu_si128(s), _mm_set1_epi32(-(int)bit));
+                        s += bit;
+                        _mm_stream_si128(dw + k, x);
+                    }
+                }
+            } else {
+                for (int k = 0; k < n; ++k) {
+                    const uint32_t bit = (m >> k) & 1u;
+                    const __m128i x = _mm_and_si128(_mm_loadu_si128(s), _mm_set1_epi32(-(int)bit));
+                    s += bit;
+                    _mm_storeu_si128(dw + k, x);
+                }
+            }
+        }
+    }
+    _mm_sfence();
+}
+
+// A fixed pool of host threads that expand pieces of the compact stream.
+class ExpandPool {
+public:
+    struct Work {
+        const CompactEntry* table;
+        const __m128i* stream;
+        __m128i* dst;
+        long long nchunks, b0, b1;
+        bool aligned;
+        cudaEvent_t ready;                           // the piece's part of the stream has arrived once this event is done
+    };
+    ExpandPool(int threads, int device) : device_(device) {
+        for (int i = 0; i < threads; ++i) pool_.emplace_back([this] { run(); });
+    }
+    ~ExpandPool() {
+        {
+            std::lock_guard<std::mutex> lock(mu_);
+            quit_ = true;
+        }
+        cv_work_.notify_all();
+        for (auto& t : pool_) t.join();
+    }
+    void submit(const Work& w) {
+        {
+            std::lock_guard<std::mutex> lock(mu_);
+            queue_.push_back(w);
+            ++pending_;
+        }
+        cv_work_.notify_one();
+    }
+    void wait() {
+        std::unique_lock<std::mutex> lock(mu_);
+        cv_done_.wait(lock, [this] { return pending_ == 0; });
+    }
+    int size() const { return (int)pool_.size(); }
+    int pending() {
+        std::lock_guard<std::mutex> lock(mu_);
+        return pending_;
+    }
+
+private:
+    void run() {
+        cudaSetDevice(device_);
+        for (;;) {
+            Work w;
+            {
+                std::unique_lock<std::mutex> lock(mu_);
+                cv_work_.wait(lock, [this] { return quit_ || !queue_.empty(); });
+                if (queue_.empty()) return;
+                w = queue_.front();
+                queue_.pop_front();
+            }
+            if (w.ready) cudaEventSynchronize(w.ready);
+            expand_blocks(w.table, w.stream, w.dst, w.nchunks, w.b0, w.b1, w.aligned);
+            {
+                std::lock_guard<std::mutex> lock(mu_);
+                if (--pending_ == 0) cv_done_.notify_all();
+            }
+        }
+    }
+    const int device_;
+    std::vector<std::thread> pool_;
+    std::mutex mu_;
+    std::condition_variable cv_work_, cv_done_;
+    std::deque<Work> queue_;
+    int pending_ = 0;
+    bool quit_ = false;
+};
+
+}  // namespace mate

@@ -204,9 +204,13 @@ def test_cuda_vs_oracle(preset, B, steps, overrides):
     np.testing.assert_allclose(stats[:6], rstats[:6], rtol=1e-4, atol=1e-3)
 
 
-def test_step_host_matches_device_step():
+@pytest.mark.parametrize('compact', ['0', '1'])
+def test_step_host_matches_device_step(compact, monkeypatch):
+    """Both device -> host legs of mate_b200_step_host (dense copy; compacted rows expanded by host threads,
+    mate_hostpath.cuh) hand the caller exactly the bytes of the device-resident step."""
     from mate_b200.config import flatten_config, read_config
 
+    monkeypatch.setenv('MATE_B200_HOST_COMPACT', compact)
     cfg = flatten_config(read_config('MATE-4v8-9.yaml'))
     B = 1024
     a, b = _sim(cfg, B), _sim(cfg, B)
