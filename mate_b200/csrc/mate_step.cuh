@@ -747,19 +747,30 @@ __device__ __noinline__ void pack_observations(const Params& p, const int env0, 
     if (NO > 0) { ob_next = ob_ptr[0]; if (nvalid > 1) ob_next2 = ob_ptr[1]; }
     // RelativeCoordinates: the fp64 locations of the next environment's entities are fetched one environment ahead
     constexpr int FJ = (EALL + 31) / 32;
-    double fx_next[FJ], fy_next[FJ];
-    auto load_locations = [&](const int env) {
+    double fx_next[FJ] = {}, fy_next[FJ] = {};
+    // this lane's entities (targets, obstacles, cameras in that order): the addresses of their coordinates in the tile's first
+    // environment are worked out once, an environment's fetch is then two loads per entity
+    const double* loc_x[FJ];
+    const double* loc_y[FJ];
 #pragma unroll
-        for (int j = 0; j < FJ; ++j) {
-            const int k = lane + 32 * j;
-            double x = 0.0, y = 0.0;
-            if (k < NT) { x = p.tgt_x[(size_t)k * bp + env]; y = p.tgt_y[(size_t)k * bp + env]; }
-            else if (k < NT + NO) { x = p.obs_x[(size_t)(k - NT) * bp + env]; y = p.obs_y[(size_t)(k - NT) * bp + env]; }
-            else if (k < EALL) { x = p.cam_x[(size_t)(k - NT - NO) * bp + env]; y = p.cam_y[(size_t)(k - NT - NO) * bp + env]; }
-            fx_next[j] = x; fy_next[j] = y;
-        }
+    for (int j = 0; j < FJ; ++j) {
+        const int k = lane + 32 * j;
+        const double *bx = p.tgt_x, *by = p.tgt_y;
+        int idx = k < NT ? k : 0;
+        if (NO > 0 && k >= NT && k < NT + NO) { bx = p.obs_x; by = p.obs_y; idx = k - NT; }
+        if (NC > 0 && k >= NT + NO && k < EALL) { bx = p.cam_x; by = p.cam_y; idx = k - NT - NO; }
+        loc_x[j] = bx + (size_t)idx * bp + env0; loc_y[j] = by + (size_t)idx * bp + env0;
+    }
+    auto load_locations = [&](const int i_env) {
+#pragma unroll
+        for (int j = 0; j < FJ; ++j)
+            if (lane + 32 * j < EALL) { fx_next[j] = loc_x[j][i_env]; fy_next[j] = loc_y[j][i_env]; }
     };
-    if (FOLD && f_rel) load_locations(env0);
+    if (FOLD && f_rel) load_locations(0);
+    // the mask wrappers in their order, four bits each (read once: the parameter block is only reachable through generic loads)
+    uint32_t mask_ops = 0;
+    const int n_mask = FOLD ? p.fold.n_mask : 0;
+    if (FOLD && f_mask) { for (int k = 0; k < n_mask; ++k) mask_ops |= (uint32_t)p.fold.mask_op[k] << (4 * k); }
     __syncwarp();
 #pragma unroll 1
     for (int i = 0; i < nvalid; ++i) {
@@ -777,7 +788,7 @@ __device__ __noinline__ void pack_observations(const Params& p, const int env0, 
                     const int k = lane + 32 * j;
                     if (k < EALL) { fpos[2 * k] = fx_next[j]; fpos[2 * k + 1] = fy_next[j]; }
                 }
-                if (i + 1 < nvalid) load_locations(env + 1);   // in flight while this environment is packed
+                if (i + 1 < nvalid) load_locations(i + 1);   // in flight while this environment is packed
             }
             if (f_mask) {
                 // lane r < R owns observer row r: its mask words go through the mask wrappers in their order;
@@ -789,8 +800,8 @@ __device__ __noinline__ void pack_observations(const Params& p, const int env0, 
                 uint32_t w0 = lane < R ? m[lane * MW] : 0u, w1 = (MW == 2 && lane < R) ? m[lane * MW + 1] : 0u;
                 int emp = lane < NT ? tp_empty(__float_as_uint(v[S::V_T + 3 * lane + 2])) : 0;
                 const bool cam_lane = lane < NC, tgt_lane = lane >= NC && lane < R;
-                for (int k = 0; k < p.fold.n_mask; ++k) {   // warp-uniform
-                    const int op = p.fold.mask_op[k];
+                for (int k = 0; k < n_mask; ++k) {   // warp-uniform
+                    const int op = (int)((mask_ops >> (4 * k)) & 15u);
                     if (op == MATE_OBS_ENHANCED_CAMERA) { if (cam_lane) { w0 = CAMS | TGTS | OBS0; w1 = OBS1; } }
                     else if (op == MATE_OBS_ENHANCED_TARGET) {
                         if (tgt_lane) { w0 = CAMS | TGTS | OBS0; w1 = OBS1; }
@@ -853,15 +864,27 @@ __device__ __noinline__ void pack_observations(const Params& p, const int env0, 
                     for (int j = 0; j < 5; ++j) a[j] = f_resc ? aff_own[36 + j] : make_float2(1.f, 0.f);
                     double ex = 0.0, ey = 0.0;
                     if (f_rel) { ex = fpos[2 * t_idx]; ey = fpos[2 * t_idx + 1]; }
+                    // the lane keeps its entity for all rounds: the entries are rescaled once per environment, a round selects
+                    // between them and the image of zero (only relative locations depend on the observer)
+                    const float e_in[5] = {t0, t1, f_sr, t3, 1.f};
+                    float sv[5];
+#pragma unroll
+                    for (int j = 0; j < 5; ++j) sv[j] = f_resc ? fmaf(e_in[j], a[j].x, a[j].y) : e_in[j];
 #pragma unroll
                     for (int rd = 0; rd < RND_T; ++rd) {
                         const bool hit = (mw[rd] & t_bit) != 0u;
-                        float x[5] = {hit ? t0 : 0.f, hit ? t1 : 0.f, hit ? f_sr : 0.f, hit ? t3 : 0.f, hit ? 1.f : 0.f};
-                        if (f_rel && hit) { const int ko = observer(m_idx[rd]); x[0] = (float)(ex - fpos[2 * ko]); x[1] = (float)(ey - fpos[2 * ko + 1]); }
+                        float x[5];
+#pragma unroll
+                        for (int j = 0; j < 5; ++j) x[j] = hit ? sv[j] : a[j].y;
+                        if (f_rel && hit) {
+                            const int ko = observer(m_idx[rd]);
+                            const float rx = (float)(ex - fpos[2 * ko]), ry = (float)(ey - fpos[2 * ko + 1]);
+                            x[0] = f_resc ? fmaf(rx, a[0].x, a[0].y) : rx; x[1] = f_resc ? fmaf(ry, a[1].x, a[1].y) : ry;
+                        }
                         if ((on_bits >> rd) & 1u) {
                             float* q = q_ptr[rd];
 #pragma unroll
-                            for (int j = 0; j < 5; ++j) q[j] = f_resc ? fmaf(x[j], a[j].x, a[j].y) : x[j];
+                            for (int j = 0; j < 5; ++j) q[j] = x[j];
                         }
                     }
                 }
@@ -871,15 +894,25 @@ __device__ __noinline__ void pack_observations(const Params& p, const int env0, 
                     for (int j = 0; j < 4; ++j) a[j] = f_resc ? aff_own[41 + j] : make_float2(1.f, 0.f);
                     double ex = 0.0, ey = 0.0;
                     if (f_rel) { ex = fpos[2 * (NT + o_idx)]; ey = fpos[2 * (NT + o_idx) + 1]; }
+                    const float e_in[4] = {ob.x, ob.y, ob.z, 1.f};
+                    float sv[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) sv[j] = f_resc ? fmaf(e_in[j], a[j].x, a[j].y) : e_in[j];
 #pragma unroll
                     for (int rd = 0; rd < RND_O; ++rd) {
                         const bool hit = (mw[RND_T + rd] & o_bit) != 0u;
-                        float x[4] = {hit ? ob.x : 0.f, hit ? ob.y : 0.f, hit ? ob.z : 0.f, hit ? 1.f : 0.f};
-                        if (f_rel && hit) { const int ko = observer(m_idx[RND_T + rd]); x[0] = (float)(ex - fpos[2 * ko]); x[1] = (float)(ey - fpos[2 * ko + 1]); }
+                        float x[4];
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) x[j] = hit ? sv[j] : a[j].y;
+                        if (f_rel && hit) {
+                            const int ko = observer(m_idx[RND_T + rd]);
+                            const float rx = (float)(ex - fpos[2 * ko]), ry = (float)(ey - fpos[2 * ko + 1]);
+                            x[0] = f_resc ? fmaf(rx, a[0].x, a[0].y) : rx; x[1] = f_resc ? fmaf(ry, a[1].x, a[1].y) : ry;
+                        }
                         if ((on_bits >> (RND_T + rd)) & 1u) {
                             float* q = q_ptr[RND_T + rd];
 #pragma unroll
-                            for (int j = 0; j < 4; ++j) q[j] = f_resc ? fmaf(x[j], a[j].x, a[j].y) : x[j];
+                            for (int j = 0; j < 4; ++j) q[j] = x[j];
                         }
                     }
                 }
@@ -889,15 +922,25 @@ __device__ __noinline__ void pack_observations(const Params& p, const int env0, 
                     for (int j = 0; j < 7; ++j) a[j] = f_resc ? aff_own[45 + j] : make_float2(1.f, 0.f);
                     double ex = 0.0, ey = 0.0;
                     if (f_rel) { ex = fpos[2 * (NT + NO + c_idx)]; ey = fpos[2 * (NT + NO + c_idx) + 1]; }
+                    const float e_in[7] = {c0, c1, f_crad, c3, c4, c5, 1.f};
+                    float sv[7];
+#pragma unroll
+                    for (int j = 0; j < 7; ++j) sv[j] = f_resc ? fmaf(e_in[j], a[j].x, a[j].y) : e_in[j];
 #pragma unroll
                     for (int rd = 0; rd < RND_C; ++rd) {
                         const bool hit = (mw[NRND - RND_C + rd] & c_bit) != 0u;
-                        float x[7] = {hit ? c0 : 0.f, hit ? c1 : 0.f, hit ? f_crad : 0.f, hit ? c3 : 0.f, hit ? c4 : 0.f, hit ? c5 : 0.f, hit ? 1.f : 0.f};
-                        if (f_rel && hit) { const int ko = observer(m_idx[NRND - RND_C + rd]); x[0] = (float)(ex - fpos[2 * ko]); x[1] = (float)(ey - fpos[2 * ko + 1]); }
+                        float x[7];
+#pragma unroll
+                        for (int j = 0; j < 7; ++j) x[j] = hit ? sv[j] : a[j].y;
+                        if (f_rel && hit) {
+                            const int ko = observer(m_idx[NRND - RND_C + rd]);
+                            const float rx = (float)(ex - fpos[2 * ko]), ry = (float)(ey - fpos[2 * ko + 1]);
+                            x[0] = f_resc ? fmaf(rx, a[0].x, a[0].y) : rx; x[1] = f_resc ? fmaf(ry, a[1].x, a[1].y) : ry;
+                        }
                         if ((on_bits >> (NRND - RND_C + rd)) & 1u) {
                             float* q = q_ptr[NRND - RND_C + rd];
 #pragma unroll
-                            for (int j = 0; j < 7; ++j) q[j] = f_resc ? fmaf(x[j], a[j].x, a[j].y) : x[j];
+                            for (int j = 0; j < 7; ++j) q[j] = x[j];
                         }
                     }
                 }
