@@ -10,6 +10,7 @@
 #include <chrono>
 #include <cstring>
 #include <memory>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -56,12 +57,75 @@ struct KernelInfo {
     void (*launch_soft)(const Params&, const uint8_t*, const uint8_t*, double*, float*, cudaStream_t);
 };
 
+// ---- L2 persistence for the fp32 obstacle entries -------------------------------------------------
+// The simulation phase of a step reads obs_f4 and the packer reads it again 60 us later, while the observation rows
+// stream through the L2.  When the rows of one launch are several times the L2 (MATE-4v8-9 x 65 536: 407 MB against
+// 126 MB) the entries are evicted in between and the re-reads go to HBM in the middle of the write phase.  Such a
+// simulator sets aside a part of the L2 for persisting lines while it lives (12 MB by default, MATE_B200_L2_KEEP=<MB>,
+// 0 = off) and its step launches carry a persisting access window over the array.  Measured (profiles/r2v_summary.md):
+// 10 - 16 MB set aside -1.5 to -2.2 % ms/step, 24 MB +4 %, 32 MB +22 % (the write stream needs the rest of the L2);
+// no gain for the smaller workloads and a loss when the array does not fit the set-aside (MATE-Navigation), so only
+// simulators that meet both conditions take part.  The device limit is reference-counted and restored afterwards.
+struct L2Keep {
+    std::mutex mu;
+    int users[64] = {};
+    size_t previous[64] = {};
+};
+static L2Keep g_l2;
+static size_t l2_keep_wanted() {
+    size_t mb = 12;
+    if (const char* v = getenv("MATE_B200_L2_KEEP")) mb = (size_t)std::max(0, atoi(v));
+    return mb << 20;
+}
+// returns the window a simulator of this size gets (0 = none) and takes a reference on the device's set-aside
+static size_t l2_keep_acquire(int dev, size_t array_bytes, size_t row_bytes_per_launch) {
+    const size_t want = l2_keep_wanted();
+    if (want == 0 || array_bytes == 0 || array_bytes > want || dev < 0 || dev >= 64) return 0;
+    int l2 = 0, max_persist = 0, max_window = 0;
+    cudaDeviceGetAttribute(&l2, cudaDevAttrL2CacheSize, dev);
+    cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, dev);
+    cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, dev);
+    if (l2 <= 0 || row_bytes_per_launch < 3 * (size_t)l2) return 0;     // the rows do not flush the L2 between the two reads
+    if ((size_t)std::max(max_persist, 0) < want || (size_t)std::max(max_window, 0) < array_bytes) return 0;
+    std::lock_guard<std::mutex> lock(g_l2.mu);
+    if (g_l2.users[dev] == 0) {
+        size_t current = 0;
+        cudaDeviceGetLimit(&current, cudaLimitPersistingL2CacheSize);
+        g_l2.previous[dev] = current;
+        if (current < want && cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want) != cudaSuccess) { cudaGetLastError(); return 0; }
+    }
+    ++g_l2.users[dev];
+    return array_bytes;
+}
+static void l2_keep_release(int dev) {
+    std::lock_guard<std::mutex> lock(g_l2.mu);
+    if (dev < 0 || dev >= 64 || g_l2.users[dev] == 0) return;
+    if (--g_l2.users[dev] == 0) {
+        cudaCtxResetPersistingL2Cache();
+        if (g_l2.previous[dev] < l2_keep_wanted()) cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, g_l2.previous[dev]);
+        cudaGetLastError();
+    }
+}
+
 template <int NC, int NT, int NO>
 static void launch_shape2(const Params& p, int grid, cudaStream_t stream) {
     using S = Shape2<NC, NT, NO>;
     Params q = p;
     q.warp_stride = S::WARP_BYTES + (p.obs_ops.n > 0 ? S::OPS_BYTES : 0);   // scratch of the folded observation wrappers
-    mate_step_kernel2<NC, NT, NO><<<grid, S::WARPS * 32, S::WARPS * q.warp_stride, stream>>>(q);
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(S::WARPS * 32);
+    cfg.dynamicSmemBytes = (size_t)S::WARPS * q.warp_stride; cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    if (NO > 0 && q.l2_window_bytes > 0) {
+        attr[0].id = cudaLaunchAttributeAccessPolicyWindow;
+        attr[0].val.accessPolicyWindow.base_ptr = q.obs_f4;
+        attr[0].val.accessPolicyWindow.num_bytes = (size_t)q.l2_window_bytes;
+        attr[0].val.accessPolicyWindow.hitRatio = 1.0f;
+        attr[0].val.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+        attr[0].val.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+    }
+    cudaLaunchKernelEx(&cfg, mate_step_kernel2<NC, NT, NO>, q);
 }
 template <int NC, int NT, int NO>
 static void launch_fov_shape(const Params& p, const int32_t* env, const int32_t* camera, const double* angle, double* out,
@@ -138,6 +202,7 @@ struct MateSim {
     float *h_cam_act = nullptr, *h_tgt_act = nullptr, *h_cam_obs = nullptr, *h_tgt_obs = nullptr, *h_rewards = nullptr;
     uint8_t* h_done = nullptr;
     bool host_ready = false;
+    size_t l2_window = 0;                     // bytes of obs_f4 the step launches keep in the L2 (0: none), see l2_keep_acquire
     // compacted device -> host leg (mate_hostpath.cuh): region 0 = camera rows, 1 = target rows
     static constexpr int kMaxHostChunks = 64;
     int compact_mode = 0;                     // 1: rows cross the link compacted and are expanded by host threads
@@ -276,6 +341,9 @@ extern "C" int mate_b200_create(const MateConfig* cfg, int32_t num_envs, int32_t
     p.cam_ranges = sim->d_ranges; p.tgt_ranges = sim->d_ranges + 4 * nc; p.obs_ranges = sim->d_ranges + 4 * (nc + nt);
 
     p.num_envs = num_envs; p.bpad = bpad; p.env_index_base = env_index_base; p.seed = 0;
+    sim->l2_window = l2_keep_acquire(device, no > 0 ? ((size_t)(no - 1) * bpad + (size_t)num_envs) * sizeof(float4) : 0,
+                                     (size_t)num_envs * ((size_t)nc * sim->kernel.dc + (size_t)nt * sim->kernel.dt) * sizeof(float));
+    p.l2_window_bytes = sim->l2_window;
     p.max_episode_steps = cfg->max_episode_steps; p.num_cargoes_per_target = cfg->num_cargoes_per_target;
     p.num_high_capacity = cfg->num_high_capacity_targets; p.start_with_cargoes = cfg->targets_start_with_cargoes != 0;
     p.shuffle = cfg->shuffle_entities != 0; p.reward_sparse = cfg->reward_sparse != 0;
@@ -333,6 +401,7 @@ extern "C" int mate_b200_destroy(MateSim* sim) {
     cudaFree(sim->d_next);
     cudaFree(sim->state_block);
     cudaFree(sim->d_ranges);
+    if (sim->l2_window) l2_keep_release(sim->device);
     delete sim;
     return MATE_OK;
 }

@@ -86,6 +86,7 @@ struct Params {
     ObsOps obs_ops; const float* cam_affine; const float* tgt_affine; FoldOps fold;
     int tile_envs;     // environments per warp tile of the step kernel: 32, 16 or 8 (MateSim::tile_envs)
     int warp_stride;   // bytes between the shared-memory blocks of two warps of a CTA (Shape2::WARP_BYTES, + scratch with obs_ops)
+    unsigned long long l2_window_bytes;   // host side only: bytes of obs_f4 the launch asks the L2 to keep (0 = no window), mate_b200.cu
     // --- scalars ---
     int num_envs; int bpad; int mode; uint32_t flags;
     int next_offset;   // a launch over [begin, begin + num_envs) of the batch: env e of the launch is env e + next_offset of the arrays `next` addresses
