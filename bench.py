@@ -166,7 +166,7 @@ def make_actions(cfg, B, device, ring, seed):
     return cams, tgts
 
 
-def cpu_arm(cfg, envs, seconds, threads, seed=0):
+def cpu_arm(cfg, envs, seconds, threads, seed=0, settle=0):
     """Time the CPU oracle (float64 C port of the reference step) on `envs` environments with
     `threads` host threads for about `seconds` seconds.  Returns (env-steps/s, steps, sample)."""
     import numpy as np
@@ -183,6 +183,8 @@ def cpu_arm(cfg, envs, seconds, threads, seed=0):
     tgts = [rng.uniform(-1, 1, (envs, nt, 2)) * cfg['target_step_size'] for _ in range(ring)]
     aux = ref.alloc_aux()
     aux = {k: (v if k in ('coverage', 'num_delivered') else None) for k, v in aux.items()}
+    for k in range(settle):   # the same initial condition as the GPU arm: the running distribution, not the reset state
+        ref.step(cams[k % ring], tgts[k % ring], seed=seed, auto_reset=True, aux=aux)
     ref.step(cams[0], tgts[0], seed=seed, auto_reset=True, aux=aux)   # warm-up / calibration
     t0 = time.perf_counter()
     ref.step(cams[1], tgts[1], seed=seed, auto_reset=True, aux=aux)
@@ -216,7 +218,7 @@ def run_reference(args, cfg, workload):
     cams = [rng.uniform(-1, 1, (envs, nc, 2)) * [cfg['camera_rotation_step'], cfg['camera_zooming_step']] for _ in range(ring)]
     tgts = [rng.uniform(-1, 1, (envs, nt, 2)) * cfg['target_step_size'] for _ in range(ring)]
     aux = {k: (v if k in ('coverage', 'num_delivered') else None) for k, v in ref.alloc_aux().items()}
-    for k in range(args.warmup):
+    for k in range(args.settle + args.warmup):
         ref.step(cams[k % ring], tgts[k % ring], seed=0, auto_reset=True, aux=aux)
     t0 = time.perf_counter()
     for k in range(args.steps):
@@ -229,7 +231,8 @@ def run_reference(args, cfg, workload):
         'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * elapsed / args.steps,
         'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
         'config': {'workload': workload, 'envs_per_gpu': envs, 'actions': 'uniform random joint actions (ring of 4 pre-generated batches)', 'auto_reset': True,
-                   'episode_clocks': 'staggered uniformly over one episode: %.1f resets per step' % (envs / (cfg['max_episode_steps'] + 1.0))},
+                   'episode_clocks': 'staggered uniformly over one episode: %.1f resets per step' % (envs / (cfg['max_episode_steps'] + 1.0)),
+                   'initial_state': '%d untimed steps after the reset, before the W warm-up steps (positions drawn from the running distribution, not from reset)' % args.settle},
         'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': threads, 'kind': 'port', 'sample': sample},
         'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'agent_steps_per_s': value * (nc + nt),
@@ -252,8 +255,9 @@ def kernel_sources_sha16():
 OTHER_CONFIGS = [('MATE-4v2-9.yaml', 65536), ('MATE-4v8-0.yaml', 65536), ('MATE-Navigation.yaml', 65536), ('MATE-8v8-9.yaml', 32768)]
 
 
-def time_workload(config_name, B, steps, warmup, rank, world, local_rank, stagger=True, sample_clocks=False):
-    """W untimed + K timed steps of one workload on this rank's GPU; CUDA events, max over ranks.
+def time_workload(config_name, B, steps, warmup, rank, world, local_rank, stagger=True, sample_clocks=False, settle=0):
+    """`settle` steps that move the batch from its reset state to the running distribution, then W untimed + K timed
+    steps of one workload on this rank's GPU; CUDA events, max over ranks.
     Returns (record, sim, cfg, (cams, tgts))."""
     import numpy as np
     import torch
@@ -287,8 +291,13 @@ def time_workload(config_name, B, steps, warmup, rank, world, local_rank, stagge
             dist.barrier()
         torch.cuda.synchronize(device)
 
-    for k in range(warmup):
+    # Initial condition: after reset every target stands at its start and every camera looks where the reset put it; with
+    # staggered clocks that never happens again once the batch runs (the first ~60 steps see 51 % non-zero target entries,
+    # the running state 29 %, profiles/r2h_summary.md).  `settle` untimed steps draw the state from the running distribution.
+    for k in range(settle):
         sim.step(cams[k % ring], tgts[k % ring], auto_reset=True, aux=True)
+    for k in range(warmup):
+        sim.step(cams[(settle + k) % ring], tgts[(settle + k) % ring], auto_reset=True, aux=True)
     barrier()
     launches0 = sim.launch_count
     start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -342,6 +351,7 @@ def main():
     parser.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
     parser.add_argument('--no-e2e', action='store_true', help='skip the host-buffer e2e leg')
     parser.add_argument('--no-configs', action='store_true', help='skip the other BASELINE workloads')
+    parser.add_argument('--settle', type=int, default=64, help='untimed steps after the reset, before the warm-up: the state is drawn from the running distribution')
     parser.add_argument('--no-stagger', action='store_true', help='do not stagger the episode clocks (no resets in the timed region)')
     args = parser.parse_args()
     if args.cpu_envs <= 0:
@@ -375,7 +385,7 @@ def main():
         torch.cuda.synchronize(device)
 
     head, sim, cfg, (cams, tgts) = time_workload(args.config, B, args.steps, warmup, rank, world, local_rank,
-                                                 stagger=not args.no_stagger, sample_clocks=True)
+                                                 stagger=not args.no_stagger, sample_clocks=True, settle=args.settle)
     elapsed_ms, launches = head['elapsed_ms'], head['gpu_launches']
     value = head['env_steps_per_s']
 
@@ -421,7 +431,7 @@ def main():
         for name, envs in OTHER_CONFIGS:
             if name == args.config and envs == B:
                 continue
-            rec, osim, _, _ = time_workload(name, envs, args.other_steps, warmup, rank, world, local_rank, stagger=not args.no_stagger)
+            rec, osim, _, _ = time_workload(name, envs, args.other_steps, warmup, rank, world, local_rank, stagger=not args.no_stagger, settle=args.settle)
             osim.close()
             del osim
             torch.cuda.empty_cache()
@@ -445,6 +455,7 @@ def main():
             'episode_clocks': 'all zero' if args.no_stagger else 'staggered uniformly over one episode: %.1f resets per step' % (B / (cfg['max_episode_steps'] + 1.0)),
             'l2': 'per-step working set (observations %.0f MB + state) exceeds the 126 MB L2' % (B * 4 * (nc * head_dims(cfg)[0] + nt * head_dims(cfg)[1]) / 1e6),
             'timing': 'CUDA events around the K step launches, enqueued behind a 1 ms device-side delay (no launch gap inside the region)',
+            'initial_state': '%d untimed steps after the reset, before the W warm-up steps (positions drawn from the running distribution, not from reset)' % args.settle,
         },
         'agent_steps_per_s': value * (nc + nt),
         'gpu_launches': launches,
@@ -465,7 +476,7 @@ def main():
         line['e2e'] = e2e
     if not args.no_cpu and world == 1:   # the CPU baseline is reported at N = 1 only
         threads = os.cpu_count() or 1
-        cpu_value, cpu_steps, cpu_elapsed = cpu_arm(cfg, args.cpu_envs, args.cpu_seconds, threads)
+        cpu_value, cpu_steps, cpu_elapsed = cpu_arm(cfg, args.cpu_envs, args.cpu_seconds, threads, settle=args.settle)
         line['cpu_baseline'] = {
             'value': cpu_value, 'unit': UNIT, 'cores': threads, 'kind': 'port',
             'sample': f'{args.cpu_envs} envs x {cpu_steps} steps ({cpu_elapsed:.1f} s) of the same workload, '

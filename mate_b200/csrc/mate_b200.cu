@@ -116,7 +116,7 @@ static void launch_shape2(const Params& p, int grid, cudaStream_t stream) {
     cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(S::WARPS * 32);
     cfg.dynamicSmemBytes = (size_t)S::WARPS * q.warp_stride; cfg.stream = stream;
     cudaLaunchAttribute attr[1];
-    if (NO > 0 && q.l2_window_bytes > 0) {
+    if (NO > 0 && q.l2_window_bytes > 0 && q.mode == MODE_STEP) {   // resets and prepared episodes are written once: nothing to keep
         attr[0].id = cudaLaunchAttributeAccessPolicyWindow;
         attr[0].val.accessPolicyWindow.base_ptr = q.obs_f4;
         attr[0].val.accessPolicyWindow.num_bytes = (size_t)q.l2_window_bytes;
@@ -660,7 +660,7 @@ static int launch_prepare(MateSim* sim, cudaStream_t stream) {
         target = sim->side;
     }
     Params n = sim->next_base;
-    n.mode = MODE_PREPARE; n.flags = 0; n.seed = sim->seed;
+    n.mode = MODE_PREPARE; n.flags = 0; n.seed = sim->seed; n.l2_window_bytes = 0;
     n.cam_act = n.tgt_act = nullptr; n.cam_obs = n.tgt_obs = n.rewards = nullptr; n.done = nullptr; n.env_mask = nullptr;
     fill_aux(n, nullptr, nullptr);
     const int per_cta = sim->kernel.envs_per_cta / 32 * sim->tile_envs;
