@@ -418,7 +418,7 @@ def main():
             'h2d_bytes_per_step': B * (nc + nt) * 2 * 4,
             'd2h_bytes_per_step': B * (4 * (nc * sim.dc + nt * sim.dt) + 8 + 1),
             'steps': args.e2e_steps,
-            'note': 'mate_b200_step_host: pinned host actions in, observations/rewards/done out, chunked over 4 streams',
+            'note': 'mate_b200_step_host: pinned host actions in, observations/rewards/done out (dense rows in host memory), chunked over 4 streams; device -> host leg chosen by the library from the host threads it has: dense copy, or all-zero 16-byte chunks dropped on the device and the dense rows rebuilt by host threads (MATE_B200_HOST_COMPACT)',
         }
         del out, host_cam_act, host_tgt_act
     sim.close()

@@ -10,6 +10,7 @@
 #include <chrono>
 #include <cstring>
 #include <memory>
+#include <sched.h>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -760,34 +761,44 @@ static int ensure_host_path(MateSim* sim) {
     CUDA_TRY(cudaMalloc(&sim->h_tgt_obs, sizeof(float) * B * nt * sim->kernel.dt));
     CUDA_TRY(cudaMalloc(&sim->h_rewards, sizeof(float) * B * 2));
     CUDA_TRY(cudaMalloc(&sim->h_done, B));
-    // compacted device -> host leg: opt-in with MATE_B200_HOST_COMPACT=1 (measured 0 - 10 % faster than the dense copy with
-    // 15 host threads, slower with fewer: profiles/r2v_hostpath.md); needs row blocks that are multiples of 16 bytes
-    sim->compact_mode = 0;
+    // Compacted device -> host leg (mate_hostpath.cuh): what bounds it is the number of host threads that rebuild the dense
+    // rows (measured with 15: 9.3 - 9.6e6 env-steps/s against 8.6 - 8.7e6 for the dense copy, with 10: 8.3e6, with 6: 6.4e6,
+    // profiles/r2v_hostpath.md), so it is used when this process has at least 14 of them to itself -- all host threads the
+    // process may run on but the caller's, divided among the processes that share the host (one per GPU) -- and the rows
+    // are whole 16-byte chunks.  MATE_B200_HOST_COMPACT=0 / 1 forces the choice, MATE_B200_HOST_THREADS the pool size.
+    int threads = (int)std::thread::hardware_concurrency();
+    {
+        cpu_set_t set;
+        if (sched_getaffinity(0, sizeof(set), &set) == 0 && CPU_COUNT(&set) > 0) threads = std::min(threads > 0 ? threads : CPU_COUNT(&set), CPU_COUNT(&set));
+    }
+    int sharers = 1;
+    if (const char* v = getenv("LOCAL_WORLD_SIZE")) sharers = std::max(1, atoi(v));
+    threads = std::max(1, threads / sharers - 1);
+    if (const char* v = getenv("MATE_B200_HOST_THREADS")) threads = std::max(1, atoi(v));
+    threads = std::min(threads, 64);
+    sim->compact_mode = threads >= 14 ? 1 : 0;
     if (const char* v = getenv("MATE_B200_HOST_COMPACT")) sim->compact_mode = v[0] == '1' ? 1 : 0;
+    if ((sizeof(float) * nc * sim->kernel.dc) % 16 || (sizeof(float) * nt * sim->kernel.dt) % 16) sim->compact_mode = 0;
     if (sim->compact_mode) {
         const size_t region_bytes[2] = {sizeof(float) * B * nc * sim->kernel.dc, sizeof(float) * B * nt * sim->kernel.dt};
-        for (int r = 0; r < 2; ++r) {
+        bool ok = true;
+        for (int r = 0; r < 2 && ok; ++r) {
             if (region_bytes[r] == 0) continue;
             const size_t chunks = region_bytes[r] / 16 + 8, blocks = chunks / kCompactBlock + MateSim::kMaxHostChunks + 1;
-            CUDA_TRY(cudaMalloc(&sim->d_compact[r], chunks * 16));
-            CUDA_TRY(cudaMalloc(&sim->d_table[r], blocks * sizeof(CompactEntry)));
-            CUDA_TRY(cudaMallocHost(&sim->p_compact[r], chunks * 16));
-            CUDA_TRY(cudaMallocHost(&sim->p_table[r], blocks * sizeof(CompactEntry)));
+            ok = cudaMalloc(&sim->d_compact[r], chunks * 16) == cudaSuccess && cudaMalloc(&sim->d_table[r], blocks * sizeof(CompactEntry)) == cudaSuccess &&
+                 cudaMallocHost(&sim->p_compact[r], chunks * 16) == cudaSuccess && cudaMallocHost(&sim->p_table[r], blocks * sizeof(CompactEntry)) == cudaSuccess;
         }
-        CUDA_TRY(cudaMalloc(&sim->d_count, sizeof(unsigned int) * MateSim::kMaxHostChunks * 2));
-        CUDA_TRY(cudaMallocHost(&sim->p_count, sizeof(unsigned int) * MateSim::kMaxHostChunks * 2));
-        CUDA_TRY(cudaStreamCreateWithFlags(&sim->copy_stream, cudaStreamNonBlocking));
-        for (int i = 0; i < MateSim::kMaxHostChunks; ++i) {
-            CUDA_TRY(cudaEventCreateWithFlags(&sim->e_counts[i], cudaEventDisableTiming));
-            CUDA_TRY(cudaEventCreateWithFlags(&sim->e_stream[i], cudaEventDisableTiming));
+        ok = ok && cudaMalloc(&sim->d_count, sizeof(unsigned int) * MateSim::kMaxHostChunks * 2) == cudaSuccess &&
+             cudaMallocHost(&sim->p_count, sizeof(unsigned int) * MateSim::kMaxHostChunks * 2) == cudaSuccess &&
+             cudaStreamCreateWithFlags(&sim->copy_stream, cudaStreamNonBlocking) == cudaSuccess;
+        for (int i = 0; i < MateSim::kMaxHostChunks && ok; ++i)
+            ok = cudaEventCreateWithFlags(&sim->e_counts[i], cudaEventDisableTiming) == cudaSuccess &&
+                 cudaEventCreateWithFlags(&sim->e_stream[i], cudaEventDisableTiming) == cudaSuccess;
+        if (ok) sim->pool.reset(new ExpandPool(threads, sim->device));
+        else {   // not enough pinned host memory or device memory for the second copy of the rows: the dense leg needs neither
+            cudaGetLastError();
+            sim->compact_mode = 0;
         }
-        // expansion threads: all host threads but the caller's; processes that share the host (one per GPU) share them
-        int threads = (int)std::thread::hardware_concurrency();
-        int sharers = 1;
-        if (const char* v = getenv("LOCAL_WORLD_SIZE")) sharers = std::max(1, atoi(v));
-        threads = std::max(1, threads / sharers - 1);
-        if (const char* v = getenv("MATE_B200_HOST_THREADS")) threads = std::max(1, atoi(v));
-        sim->pool.reset(new ExpandPool(std::min(threads, 64), sim->device));
     }
     sim->host_ready = true;
     return MATE_OK;
