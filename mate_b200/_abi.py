@@ -19,6 +19,7 @@ c_uint8_p = ctypes.POINTER(ctypes.c_uint8)
 c_int8_p = ctypes.POINTER(ctypes.c_int8)
 
 MATE_STEP_AUTO_RESET = 1
+MATE_STEP_HOST_ROWS_KEPT = 2
 
 
 class MateConfig(ctypes.Structure):

@@ -211,7 +211,11 @@ struct MateSim {
     CompactEntry* d_table[2] = {nullptr, nullptr};
     unsigned int* d_count = nullptr;          // [kMaxHostChunks][2] chunks kept
     uint4* p_compact[2] = {nullptr, nullptr}; // pinned host copies of the above
-    CompactEntry* p_table[2] = {nullptr, nullptr};
+    CompactEntry* p_table[2] = {nullptr, nullptr};   // two tables per region: this step's and the previous one's
+    size_t table_blocks[2] = {0, 0};
+    int table_parity = 0;
+    const float* kept_rows[2] = {nullptr, nullptr};  // the caller's buffers the previous table describes (MATE_STEP_HOST_ROWS_KEPT)
+    bool kept_valid = false;
     unsigned int* p_count = nullptr;
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t e_counts[kMaxHostChunks] = {}, e_stream[kMaxHostChunks] = {};
@@ -786,7 +790,8 @@ static int ensure_host_path(MateSim* sim) {
             if (region_bytes[r] == 0) continue;
             const size_t chunks = region_bytes[r] / 16 + 8, blocks = chunks / kCompactBlock + MateSim::kMaxHostChunks + 1;
             ok = cudaMalloc(&sim->d_compact[r], chunks * 16) == cudaSuccess && cudaMalloc(&sim->d_table[r], blocks * sizeof(CompactEntry)) == cudaSuccess &&
-                 cudaMallocHost(&sim->p_compact[r], chunks * 16) == cudaSuccess && cudaMallocHost(&sim->p_table[r], blocks * sizeof(CompactEntry)) == cudaSuccess;
+                 cudaMallocHost(&sim->p_compact[r], chunks * 16) == cudaSuccess && cudaMallocHost(&sim->p_table[r], 2 * blocks * sizeof(CompactEntry)) == cudaSuccess;
+            sim->table_blocks[r] = blocks;
         }
         ok = ok && cudaMalloc(&sim->d_count, sizeof(unsigned int) * MateSim::kMaxHostChunks * 2) == cudaSuccess &&
              cudaMallocHost(&sim->p_count, sizeof(unsigned int) * MateSim::kMaxHostChunks * 2) == cudaSuccess &&
@@ -840,6 +845,16 @@ extern "C" int mate_b200_step_host(MateSim* sim, const float* cam_act, const flo
         float* const host_rows[2] = {cam_obs, tgt_obs};
         float* const dev_rows[2] = {sim->h_cam_obs, sim->h_tgt_obs};
         std::vector<long long> table_base(2 * (num_chunks + 1), 0);
+        // MATE_STEP_HOST_ROWS_KEPT: the caller's row buffers still hold what the previous call wrote (same buffers, not
+        // modified since).  The previous step's bitmaps then tell which 64-byte groups were zero and are zero again: the
+        // expansion skips them.
+        const bool use_kept = (flags & MATE_STEP_HOST_ROWS_KEPT) && sim->kept_valid && sim->kept_rows[0] == cam_obs && sim->kept_rows[1] == tgt_obs;
+        sim->kept_valid = false;
+        const int par = sim->table_parity;
+        CompactEntry* const cur_table[2] = {sim->p_table[0] ? sim->p_table[0] + (size_t)par * sim->table_blocks[0] : nullptr,
+                                            sim->p_table[1] ? sim->p_table[1] + (size_t)par * sim->table_blocks[1] : nullptr};
+        const CompactEntry* const old_table[2] = {use_kept && sim->p_table[0] ? sim->p_table[0] + (size_t)(1 - par) * sim->table_blocks[0] : nullptr,
+                                                  use_kept && sim->p_table[1] ? sim->p_table[1] + (size_t)(1 - par) * sim->table_blocks[1] : nullptr};
         CUDA_TRY(cudaMemsetAsync(sim->d_count, 0, sizeof(unsigned int) * MateSim::kMaxHostChunks * 2, sim->hstreams[0]));
         CUDA_TRY(cudaEventRecord(sim->hevents[1], sim->hstreams[0]));
         for (int i = 1; i < MateSim::kHostStreams; ++i) CUDA_TRY(cudaStreamWaitEvent(sim->hstreams[i], sim->hevents[1], 0));
@@ -860,7 +875,7 @@ extern "C" int mate_b200_step_host(MateSim* sim, const float* cam_act, const flo
                 table_base[2 * (kc + 1) + r] += nblocks;
                 compact_chunks_kernel<<<1184, 128, 0, s>>>(reinterpret_cast<const uint4*>(dev_rows[r]) + first, nchunks,
                                                            sim->d_compact[r] + first, table, sim->d_count + 2 * kc + r);
-                CUDA_TRY(cudaMemcpyAsync(sim->p_table[r] + table_base[2 * kc + r], table, sizeof(CompactEntry) * nblocks, cudaMemcpyDeviceToHost, s));
+                CUDA_TRY(cudaMemcpyAsync(cur_table[r] + table_base[2 * kc + r], table, sizeof(CompactEntry) * nblocks, cudaMemcpyDeviceToHost, s));
             }
             sim->launches += (nc ? 2 : 1);
             CUDA_TRY(cudaMemcpyAsync(sim->p_count + 2 * kc, sim->d_count + 2 * kc, sizeof(unsigned int) * 2, cudaMemcpyDeviceToHost, s));
@@ -892,7 +907,7 @@ extern "C" int mate_b200_step_host(MateSim* sim, const float* cam_act, const flo
                 __m128i* dst = reinterpret_cast<__m128i*>(host_rows[r]) + first;
                 const bool aligned = (((uintptr_t)dst) & 15) == 0;
                 for (long long b0 = 0; b0 < nblocks; b0 += per_piece)
-                    sim->pool->submit(ExpandPool::Work{sim->p_table[r] + table_base[2 * kc + r], reinterpret_cast<const __m128i*>(sim->p_compact[r] + first),
+                    sim->pool->submit(ExpandPool::Work{cur_table[r] + table_base[2 * kc + r], old_table[r] ? old_table[r] + table_base[2 * kc + r] : nullptr, reinterpret_cast<const __m128i*>(sim->p_compact[r] + first),
                                                        dst, nchunks, b0, std::min(nblocks, b0 + per_piece), aligned, sim->e_stream[kc]});
             }
         }
@@ -901,17 +916,20 @@ extern "C" int mate_b200_step_host(MateSim* sim, const float* cam_act, const flo
         t_last_stream = since();
         sim->pool->wait();
         for (int i = 0; i < MateSim::kHostStreams; ++i) CUDA_TRY(cudaStreamSynchronize(sim->hstreams[i]));
+        // this step's tables now describe the caller's buffers
+        sim->kept_rows[0] = cam_obs; sim->kept_rows[1] = tgt_obs; sim->kept_valid = true; sim->table_parity = 1 - par;
         if (trace) {
             unsigned long long kept = 0;
             for (int i = 0; i < 2 * num_chunks; ++i) kept += sim->p_count[i];
-            fprintf(stderr, "step_host compact: enqueued %.2f ms, sizes known + copies enqueued %.2f, last stream arrived %.2f, expanded %.2f; kept %.1f MB of %.1f MB, %d threads\n",
-                    t_enq, t_counts, t_last_stream, since(), kept * 16 / 1e6, (per_env[0] + per_env[1]) * (double)B / 1e6, sim->pool->size());
+            fprintf(stderr, "step_host compact: enqueued %.2f ms, sizes known + copies enqueued %.2f, last stream arrived %.2f, expanded %.2f; kept %.1f MB of %.1f MB, %d threads, rows kept %d\n",
+                    t_enq, t_counts, t_last_stream, since(), kept * 16 / 1e6, (per_env[0] + per_env[1]) * (double)B / 1e6, sim->pool->size(), (int)use_kept);
         }
         if ((flags & MATE_STEP_AUTO_RESET) && sim->refill_mode &&
             (sim->refill_mode == 2 || ++sim->steps_since_refill >= sim->refill_period))
             return launch_prepare(sim, nullptr);
         return MATE_OK;
     }
+    sim->kept_valid = false;   // the dense leg keeps no bitmaps
     int k = 0;
     for (int begin = 0; begin < B; begin += chunk, ++k) {
         const int count = std::min(chunk, B - begin);

@@ -64,9 +64,10 @@ __global__ void compact_chunks_kernel(const uint4* __restrict__ src, const long 
 
 // Expand blocks [b0, b1) of a region: dst = the caller's dense rows (16-byte chunks), src = the compact stream.
 // The next compact chunk is always loaded and kept only if the bit is set (no branch per chunk); the stream buffer is
-// one chunk longer than its content.
-inline void expand_blocks(const CompactEntry* table, const __m128i* stream, __m128i* dst, long long nchunks, long long b0,
-                          long long b1, bool aligned) {
+// one chunk longer than its content.  With `prev` (the table of the previous step into the same, unmodified buffers) a
+// group of four chunks (64 bytes) that was all-zero and is all-zero again is not written at all.
+inline void expand_blocks(const CompactEntry* table, const CompactEntry* prev, const __m128i* stream, __m128i* dst, long long nchunks,
+                          long long b0, long long b1, bool aligned) {
     const __m128i zero = _mm_setzero_si128();
     for (long long b = b0; b < b1; ++b) {
         const CompactEntry& entry = table[b];
@@ -78,16 +79,22 @@ inline void expand_blocks(const CompactEntry* table, const __m128i* stream, __m1
             if (rem <= 0) break;
             const int n = rem < 32 ? (int)rem : 32;
             const uint32_t m = entry.words[w];
+            const uint32_t live = prev ? (m | prev[b].words[w]) : 0xffffffffu;   // chunks that hold or held something
+            if (live == 0u) continue;
             __m128i* dw = d + 32 * w;
             if (aligned) {
-                if (m == 0u) {
+                if (m == 0u && live == 0xffffffffu) {
                     for (int k = 0; k < n; ++k) _mm_stream_si128(dw + k, zero);
                 } else {
-                    for (int k = 0; k < n; ++k) {
-                        const uint32_t bit = (m >> k) & 1u;
-                        const __m128i x = _mm_and_si128(_mm_loadu_si128(s), _mm_set1_epi32(-(int)bit));
-                        s += bit;
-                        _mm_stream_si128(dw + k, x);
+                    for (int k0 = 0; k0 < n; k0 += 4) {
+                        if (((live >> k0) & 0xFu) == 0u) continue;              // was zero, is zero
+                        const int k1 = k0 + 4 < n ? k0 + 4 : n;
+                        for (int k = k0; k < k1; ++k) {
+                            const uint32_t bit = (m >> k) & 1u;
+                            const __m128i x = _mm_and_si128(_mm_loadu_si128(s), _mm_set1_epi32(-(int)bit));
+                            s += bit;
+                            _mm_stream_si128(dw + k, x);
+                        }
                     }
                 }
             } else {
@@ -95,7 +102,7 @@ inline void expand_blocks(const CompactEntry* table, const __m128i* stream, __m1
                     const uint32_t bit = (m >> k) & 1u;
                     const __m128i x = _mm_and_si128(_mm_loadu_si128(s), _mm_set1_epi32(-(int)bit));
                     s += bit;
-                    _mm_storeu_si128(dw + k, x);
+                    if ((live >> k) & 1u) _mm_storeu_si128(dw + k, x);
                 }
             }
         }
@@ -108,6 +115,7 @@ class ExpandPool {
 public:
     struct Work {
         const CompactEntry* table;
+        const CompactEntry* prev;                    // the previous step's table of the same blocks, or nullptr
         const __m128i* stream;
         __m128i* dst;
         long long nchunks, b0, b1;
@@ -156,7 +164,7 @@ private:
                 queue_.pop_front();
             }
             if (w.ready) cudaEventSynchronize(w.ready);
-            expand_blocks(w.table, w.stream, w.dst, w.nchunks, w.b0, w.b1, w.aligned);
+            expand_blocks(w.table, w.prev, w.stream, w.dst, w.nchunks, w.b0, w.b1, w.aligned);
             {
                 std::lock_guard<std::mutex> lock(mu_);
                 if (--pending_ == 0) cv_done_.notify_all();

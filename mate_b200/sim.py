@@ -272,14 +272,16 @@ class BatchedSim:
                 _dptr(cam_terms) if self.nc else None, _dptr(tgt_terms), self._stream()))
         return cam_terms, tgt_terms
 
-    def step_host(self, cam_act, tgt_act, out, auto_reset=True):
+    def step_host(self, cam_act, tgt_act, out, auto_reset=True, rows_kept=False):
         """Host-buffer step: `cam_act`/`tgt_act` and the tensors in `out` (cam_obs, tgt_obs,
-        rewards, done) are CPU tensors (pinned for full PCIe speed)."""
+        rewards, done) are CPU tensors (pinned for full PCIe speed).  `rows_kept=True` promises that
+        `out` is the tuple of the previous `step_host` call and has not been written to since
+        (MATE_STEP_HOST_ROWS_KEPT, include/mate_b200.h): parts of the rows that stay zero are then not rewritten."""
         cam_obs, tgt_obs, rewards, done = out
+        flags = (_abi.MATE_STEP_AUTO_RESET if auto_reset else 0) | (_abi.MATE_STEP_HOST_ROWS_KEPT if rows_kept else 0)
         _check(self.lib, self.lib.mate_b200_step_host(
             self.handle, _dptr(cam_act) if self.nc else None, _dptr(tgt_act),
-            _dptr(cam_obs) if self.nc else None, _dptr(tgt_obs), _dptr(rewards), _dptr(done),
-            _abi.MATE_STEP_AUTO_RESET if auto_reset else 0))
+            _dptr(cam_obs) if self.nc else None, _dptr(tgt_obs), _dptr(rewards), _dptr(done), flags))
         return out
 
     def get_state(self):

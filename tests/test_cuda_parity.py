@@ -204,6 +204,45 @@ def test_cuda_vs_oracle(preset, B, steps, overrides):
     np.testing.assert_allclose(stats[:6], rstats[:6], rtol=1e-4, atol=1e-3)
 
 
+def test_step_host_rows_kept(monkeypatch):
+    """MATE_STEP_HOST_ROWS_KEPT: with the caller's buffers reused and untouched between calls the compacted leg skips what
+    was zero and is zero again; the buffers still equal the rows of the device-resident step, entries that turn zero
+    included (auto-resets every 4 steps change many of them).  A call without the flag rewrites everything: garbage the
+    caller left in the buffers is gone afterwards, and so is the history when the buffers change."""
+    from mate_b200.config import flatten_config, read_config
+
+    monkeypatch.setenv('MATE_B200_HOST_COMPACT', '1')
+    monkeypatch.setenv('MATE_B200_REFILL', 'sync')
+    cfg = flatten_config(read_config('MATE-4v8-9.yaml', max_episode_steps=4))
+    B = 2048
+    a, b = _sim(cfg, B), _sim(cfg, B)
+    a.reset(seed=9)
+    b.reset(seed=9)
+    rng = np.random.RandomState(3)
+
+    def buffers():
+        return (torch.zeros((B, 4, a.dc)).pin_memory(), torch.zeros((B, 8, a.dt)).pin_memory(),
+                torch.zeros((B, 2)).pin_memory(), torch.zeros(B, dtype=torch.uint8).pin_memory())
+
+    out, other = buffers(), buffers()
+    for k in range(14):
+        cam_act = torch.from_numpy((rng.uniform(-1, 1, (B, 4, 2)) * [5.0, 2.5]).astype(np.float32)).pin_memory()
+        tgt_act = torch.from_numpy((rng.uniform(-1, 1, (B, 8, 2)) * 20.0).astype(np.float32)).pin_memory()
+        (cam, tgt), rew, done = a.step(cam_act.cuda(), tgt_act.cuda(), auto_reset=True)
+        if k == 6:     # the caller scribbles over the buffers and says so by not passing the flag
+            out[0].fill_(7.0); out[1].fill_(-3.0)
+            b.step_host(cam_act, tgt_act, out, auto_reset=True, rows_kept=False)
+        elif k == 10:  # other buffers (all 5.0): the flag is passed wrongly, the library notices the new addresses
+            other[0].fill_(5.0); other[1].fill_(5.0)
+            out, other = other, out
+            b.step_host(cam_act, tgt_act, out, auto_reset=True, rows_kept=True)
+        else:
+            b.step_host(cam_act, tgt_act, out, auto_reset=True, rows_kept=True)
+        torch.cuda.synchronize()
+        assert torch.equal(cam.cpu(), out[0]) and torch.equal(tgt.cpu(), out[1]), k
+        assert torch.equal(rew.cpu(), out[2]) and torch.equal(done.cpu(), out[3]), k
+
+
 @pytest.mark.parametrize('compact', ['0', '1'])
 def test_step_host_matches_device_step(compact, monkeypatch):
     """Both device -> host legs of mate_b200_step_host (dense copy; compacted rows expanded by host threads,
