@@ -419,7 +419,7 @@ def main():
             'h2d_bytes_per_step': B * (nc + nt) * 2 * 4,
             'd2h_bytes_per_step': B * (4 * (nc * sim.dc + nt * sim.dt) + 8 + 1),
             'steps': args.e2e_steps,
-            'note': 'mate_b200_step_host: pinned host actions in, observations/rewards/done out (dense rows in host memory), chunked over 4 streams; device -> host leg chosen by the library from the host threads it has: dense copy, or all-zero 16-byte chunks dropped on the device and the dense rows rebuilt by host threads (MATE_B200_HOST_COMPACT); the output buffers are reused and untouched between steps, which the call is told (MATE_STEP_HOST_ROWS_KEPT: what was zero and is zero again is not rewritten)',
+            'note': 'mate_b200_step_host: pinned host actions in, observations/rewards/done out (dense rows in host memory), chunked over 4 streams; device -> host leg chosen by the library from the host threads it has: dense copy, or all-zero 16-byte chunks dropped on the device and the dense rows rebuilt by host threads (MATE_B200_HOST_COMPACT); the output buffers are reused and untouched between steps, which the call is told (MATE_STEP_HOST_ROWS_KEPT: only the 64-byte groups that differ from the previous step cross the link and are rewritten)',
         }
         del out, host_cam_act, host_tgt_act
     sim.close()

@@ -130,9 +130,10 @@ typedef struct MateSim MateSim;
 /* Flags for mate_b200_step. */
 #define MATE_STEP_AUTO_RESET 1u /* reset finished episodes inside the call; returned obs are the new episode's */
 /* mate_b200_step_host only: the caller passes the same cam_obs / tgt_obs buffers as in its previous mate_b200_step_host
- * call on this handle and has not written to them since.  The library may then leave parts of the rows that were zero
- * and are zero again untouched (fewer host-memory writes); the buffers hold the complete rows of this step either way.
- * Without the flag every byte of the rows is written. */
+ * call on this handle and has not written to them since.  The library then sends and rewrites only the 64-byte groups of
+ * the rows that differ from the previous call's rows (which it keeps on the device); the buffers hold the complete rows of
+ * this step either way.  Without the flag, or with other buffers than the previous call's, every byte of the rows is
+ * written. */
 #define MATE_STEP_HOST_ROWS_KEPT 2u
 
 const char* mate_b200_last_error(void);

@@ -211,14 +211,17 @@ struct MateSim {
     CompactEntry* d_table[2] = {nullptr, nullptr};
     unsigned int* d_count = nullptr;          // [kMaxHostChunks][2] chunks kept
     uint4* p_compact[2] = {nullptr, nullptr}; // pinned host copies of the above
-    CompactEntry* p_table[2] = {nullptr, nullptr};   // two tables per region: this step's and the previous one's
-    size_t table_blocks[2] = {0, 0};
-    int table_parity = 0;
-    const float* kept_rows[2] = {nullptr, nullptr};  // the caller's buffers the previous table describes (MATE_STEP_HOST_ROWS_KEPT)
+    CompactEntry* p_table[2] = {nullptr, nullptr};
+    // MATE_STEP_HOST_ROWS_KEPT: the rows of the previous call stay on the device (second pair of row buffers, used in turn);
+    // only the 64-byte groups that differ from them cross the link and are rewritten in the caller's buffers
+    float* h_rows2[2] = {nullptr, nullptr};
+    int row_parity = 0;
+    const float* kept_rows[2] = {nullptr, nullptr};  // the caller's buffers that hold the previous call's rows
     bool kept_valid = false;
     unsigned int* p_count = nullptr;
     cudaStream_t copy_stream = nullptr;
-    cudaEvent_t e_counts[kMaxHostChunks] = {}, e_stream[kMaxHostChunks] = {};
+    cudaEvent_t e_counts[kMaxHostChunks] = {}, e_stream[kMaxHostChunks] = {}, e_tables[kMaxHostChunks] = {};
+    unsigned int* p_count_dev = nullptr;      // device address of the pinned p_count (the sizes are stored there by a kernel, not copied)
     std::unique_ptr<ExpandPool> pool;
 };
 
@@ -392,11 +395,11 @@ extern "C" int mate_b200_destroy(MateSim* sim) {
         cudaFree(sim->h_cam_act); cudaFree(sim->h_tgt_act); cudaFree(sim->h_cam_obs); cudaFree(sim->h_tgt_obs);
         cudaFree(sim->h_rewards); cudaFree(sim->h_done);
         sim->pool.reset();
-        for (int r = 0; r < 2; ++r) { cudaFree(sim->d_compact[r]); cudaFree(sim->d_table[r]); cudaFreeHost(sim->p_compact[r]); cudaFreeHost(sim->p_table[r]); }
+        for (int r = 0; r < 2; ++r) { cudaFree(sim->d_compact[r]); cudaFree(sim->d_table[r]); cudaFreeHost(sim->p_compact[r]); cudaFreeHost(sim->p_table[r]); cudaFree(sim->h_rows2[r]); }
         cudaFree(sim->d_count); cudaFreeHost(sim->p_count);
         if (sim->copy_stream) {
             cudaStreamDestroy(sim->copy_stream);
-            for (int i = 0; i < MateSim::kMaxHostChunks; ++i) { cudaEventDestroy(sim->e_counts[i]); cudaEventDestroy(sim->e_stream[i]); }
+            for (int i = 0; i < MateSim::kMaxHostChunks; ++i) { cudaEventDestroy(sim->e_counts[i]); cudaEventDestroy(sim->e_stream[i]); cudaEventDestroy(sim->e_tables[i]); }
         }
     }
     if (sim->side) { cudaStreamSynchronize(sim->side); cudaStreamDestroy(sim->side); }
@@ -790,19 +793,22 @@ static int ensure_host_path(MateSim* sim) {
             if (region_bytes[r] == 0) continue;
             const size_t chunks = region_bytes[r] / 16 + 8, blocks = chunks / kCompactBlock + MateSim::kMaxHostChunks + 1;
             ok = cudaMalloc(&sim->d_compact[r], chunks * 16) == cudaSuccess && cudaMalloc(&sim->d_table[r], blocks * sizeof(CompactEntry)) == cudaSuccess &&
-                 cudaMallocHost(&sim->p_compact[r], chunks * 16) == cudaSuccess && cudaMallocHost(&sim->p_table[r], 2 * blocks * sizeof(CompactEntry)) == cudaSuccess;
-            sim->table_blocks[r] = blocks;
+                 cudaMallocHost(&sim->p_compact[r], chunks * 16) == cudaSuccess && cudaMallocHost(&sim->p_table[r], blocks * sizeof(CompactEntry)) == cudaSuccess &&
+                 cudaMalloc(&sim->h_rows2[r], region_bytes[r] + 16) == cudaSuccess;
         }
         ok = ok && cudaMalloc(&sim->d_count, sizeof(unsigned int) * MateSim::kMaxHostChunks * 2) == cudaSuccess &&
              cudaMallocHost(&sim->p_count, sizeof(unsigned int) * MateSim::kMaxHostChunks * 2) == cudaSuccess &&
+             cudaHostGetDevicePointer(reinterpret_cast<void**>(&sim->p_count_dev), sim->p_count, 0) == cudaSuccess &&
              cudaStreamCreateWithFlags(&sim->copy_stream, cudaStreamNonBlocking) == cudaSuccess;
         for (int i = 0; i < MateSim::kMaxHostChunks && ok; ++i)
-            ok = cudaEventCreateWithFlags(&sim->e_counts[i], cudaEventDisableTiming) == cudaSuccess &&
+            ok = cudaEventCreateWithFlags(&sim->e_tables[i], cudaEventDisableTiming) == cudaSuccess &&
+                 cudaEventCreateWithFlags(&sim->e_counts[i], cudaEventDisableTiming) == cudaSuccess &&
                  cudaEventCreateWithFlags(&sim->e_stream[i], cudaEventDisableTiming) == cudaSuccess;
         if (ok) sim->pool.reset(new ExpandPool(threads, sim->device));
         else {   // not enough pinned host memory or device memory for the second copy of the rows: the dense leg needs neither
             cudaGetLastError();
             sim->compact_mode = 0;
+            for (int r = 0; r < 2; ++r) { cudaFree(sim->h_rows2[r]); sim->h_rows2[r] = nullptr; }
         }
     }
     sim->host_ready = true;
@@ -824,7 +830,11 @@ extern "C" int mate_b200_step_host(MateSim* sim, const float* cam_act, const flo
     chunk = (int)align_up((size_t)std::max(chunk, 1), (size_t)tile);
     Params p = sim->base;
     p.mode = MODE_STEP; p.flags = flags; p.seed = sim->seed;
-    p.cam_act = sim->h_cam_act; p.tgt_act = sim->h_tgt_act; p.cam_obs = sim->h_cam_obs; p.tgt_obs = sim->h_tgt_obs;
+    // the rows of this call and of the previous one take turns in two pairs of device buffers (compacted leg only)
+    const bool two_buffers = sim->compact_mode && sim->h_rows2[1] != nullptr && (nc == 0 || sim->h_rows2[0] != nullptr);
+    float* const rows_now[2] = {two_buffers && sim->row_parity ? sim->h_rows2[0] : sim->h_cam_obs, two_buffers && sim->row_parity ? sim->h_rows2[1] : sim->h_tgt_obs};
+    float* const rows_before[2] = {two_buffers && !sim->row_parity ? sim->h_rows2[0] : sim->h_cam_obs, two_buffers && !sim->row_parity ? sim->h_rows2[1] : sim->h_tgt_obs};
+    p.cam_act = sim->h_cam_act; p.tgt_act = sim->h_tgt_act; p.cam_obs = rows_now[0]; p.tgt_obs = rows_now[1];
     p.rewards = sim->h_rewards; p.done = sim->h_done;
     fill_aux(p, nullptr, nullptr);
     // work queued earlier on the legacy default stream (torch's default) or on blocking streams is finished first;
@@ -843,18 +853,13 @@ extern "C" int mate_b200_step_host(MateSim* sim, const float* cam_act, const flo
         double t_enq = 0, t_counts = 0, t_last_stream = 0;
         const size_t per_env[2] = {(size_t)nc * dc * 4, (size_t)nt * dt * 4};   // bytes of rows per environment and region
         float* const host_rows[2] = {cam_obs, tgt_obs};
-        float* const dev_rows[2] = {sim->h_cam_obs, sim->h_tgt_obs};
+        float* const dev_rows[2] = {rows_now[0], rows_now[1]};
         std::vector<long long> table_base(2 * (num_chunks + 1), 0);
-        // MATE_STEP_HOST_ROWS_KEPT: the caller's row buffers still hold what the previous call wrote (same buffers, not
-        // modified since).  The previous step's bitmaps then tell which 64-byte groups were zero and are zero again: the
-        // expansion skips them.
-        const bool use_kept = (flags & MATE_STEP_HOST_ROWS_KEPT) && sim->kept_valid && sim->kept_rows[0] == cam_obs && sim->kept_rows[1] == tgt_obs;
+        // MATE_STEP_HOST_ROWS_KEPT: the caller's row buffers still hold the rows of the previous call (same buffers, not
+        // modified since) and the device still holds them too: only the 64-byte groups that differ cross the link and are
+        // rewritten.  Otherwise the all-zero chunks are dropped and every byte of the caller's buffers is written.
+        const bool delta = two_buffers && (flags & MATE_STEP_HOST_ROWS_KEPT) && sim->kept_valid && sim->kept_rows[0] == cam_obs && sim->kept_rows[1] == tgt_obs;
         sim->kept_valid = false;
-        const int par = sim->table_parity;
-        CompactEntry* const cur_table[2] = {sim->p_table[0] ? sim->p_table[0] + (size_t)par * sim->table_blocks[0] : nullptr,
-                                            sim->p_table[1] ? sim->p_table[1] + (size_t)par * sim->table_blocks[1] : nullptr};
-        const CompactEntry* const old_table[2] = {use_kept && sim->p_table[0] ? sim->p_table[0] + (size_t)(1 - par) * sim->table_blocks[0] : nullptr,
-                                                  use_kept && sim->p_table[1] ? sim->p_table[1] + (size_t)(1 - par) * sim->table_blocks[1] : nullptr};
         CUDA_TRY(cudaMemsetAsync(sim->d_count, 0, sizeof(unsigned int) * MateSim::kMaxHostChunks * 2, sim->hstreams[0]));
         CUDA_TRY(cudaEventRecord(sim->hevents[1], sim->hstreams[0]));
         for (int i = 1; i < MateSim::kHostStreams; ++i) CUDA_TRY(cudaStreamWaitEvent(sim->hstreams[i], sim->hevents[1], 0));
@@ -873,15 +878,24 @@ extern "C" int mate_b200_step_host(MateSim* sim, const float* cam_act, const flo
                 const long long nblocks = (nchunks + kCompactBlock - 1) / kCompactBlock;
                 CompactEntry* table = sim->d_table[r] + table_base[2 * kc + r];
                 table_base[2 * (kc + 1) + r] += nblocks;
-                compact_chunks_kernel<<<1184, 128, 0, s>>>(reinterpret_cast<const uint4*>(dev_rows[r]) + first, nchunks,
-                                                           sim->d_compact[r] + first, table, sim->d_count + 2 * kc + r);
-                CUDA_TRY(cudaMemcpyAsync(cur_table[r] + table_base[2 * kc + r], table, sizeof(CompactEntry) * nblocks, cudaMemcpyDeviceToHost, s));
+                if (delta) compact_changes_kernel<<<1184, 128, 0, s>>>(reinterpret_cast<const uint4*>(dev_rows[r]) + first, reinterpret_cast<const uint4*>(rows_before[r]) + first,
+                                                                       nchunks, sim->d_compact[r] + first, table, sim->d_count + 2 * kc + r);
+                else compact_chunks_kernel<<<1184, 128, 0, s>>>(reinterpret_cast<const uint4*>(dev_rows[r]) + first, nchunks,
+                                                                sim->d_compact[r] + first, table, sim->d_count + 2 * kc + r);
             }
             sim->launches += (nc ? 2 : 1);
-            CUDA_TRY(cudaMemcpyAsync(sim->p_count + 2 * kc, sim->d_count + 2 * kc, sizeof(unsigned int) * 2, cudaMemcpyDeviceToHost, s));
+            // The sizes of the chunk's compact streams go to the host by a store into pinned memory, not by a copy: a copy
+            // would queue behind the compact streams of earlier chunks on the copy engine, and the next stream could only be
+            // enqueued after the previous one had crossed the link (a bubble per chunk).
+            publish_counts_kernel<<<1, 32, 0, s>>>(sim->d_count + 2 * kc, sim->p_count_dev + 2 * kc);
+            CUDA_TRY(cudaEventRecord(sim->e_counts[kc], s));
+            for (int r = 0; r < 2; ++r) {
+                const long long nblocks = table_base[2 * (kc + 1) + r] - table_base[2 * kc + r];
+                if (nblocks > 0) CUDA_TRY(cudaMemcpyAsync(sim->p_table[r] + table_base[2 * kc + r], sim->d_table[r] + table_base[2 * kc + r], sizeof(CompactEntry) * nblocks, cudaMemcpyDeviceToHost, s));
+            }
             CUDA_TRY(cudaMemcpyAsync(rewards + (size_t)begin * 2, sim->h_rewards + (size_t)begin * 2, sizeof(float) * count * 2, cudaMemcpyDeviceToHost, s));
             CUDA_TRY(cudaMemcpyAsync(done + begin, sim->h_done + begin, count, cudaMemcpyDeviceToHost, s));
-            CUDA_TRY(cudaEventRecord(sim->e_counts[kc], s));
+            CUDA_TRY(cudaEventRecord(sim->e_tables[kc], s));
         }
         t_enq = since();
         // the sizes are known once a chunk's kernels have run: its compact streams go on the copy stream in chunk order
@@ -889,6 +903,7 @@ extern "C" int mate_b200_step_host(MateSim* sim, const float* cam_act, const flo
         kc = 0;
         for (int begin = 0; begin < B; begin += chunk, ++kc) {
             CUDA_TRY(cudaEventSynchronize(sim->e_counts[kc]));
+            CUDA_TRY(cudaStreamWaitEvent(sim->copy_stream, sim->e_tables[kc], 0));   // a chunk's stream event then covers its tables too
             for (int r = 0; r < 2; ++r) {
                 if (per_env[r] == 0 || sim->p_count[2 * kc + r] == 0) continue;
                 const size_t first = (size_t)begin * per_env[r] / 16;
@@ -907,7 +922,7 @@ extern "C" int mate_b200_step_host(MateSim* sim, const float* cam_act, const flo
                 __m128i* dst = reinterpret_cast<__m128i*>(host_rows[r]) + first;
                 const bool aligned = (((uintptr_t)dst) & 15) == 0;
                 for (long long b0 = 0; b0 < nblocks; b0 += per_piece)
-                    sim->pool->submit(ExpandPool::Work{cur_table[r] + table_base[2 * kc + r], old_table[r] ? old_table[r] + table_base[2 * kc + r] : nullptr, reinterpret_cast<const __m128i*>(sim->p_compact[r] + first),
+                    sim->pool->submit(ExpandPool::Work{sim->p_table[r] + table_base[2 * kc + r], delta, reinterpret_cast<const __m128i*>(sim->p_compact[r] + first),
                                                        dst, nchunks, b0, std::min(nblocks, b0 + per_piece), aligned, sim->e_stream[kc]});
             }
         }
@@ -916,20 +931,21 @@ extern "C" int mate_b200_step_host(MateSim* sim, const float* cam_act, const flo
         t_last_stream = since();
         sim->pool->wait();
         for (int i = 0; i < MateSim::kHostStreams; ++i) CUDA_TRY(cudaStreamSynchronize(sim->hstreams[i]));
-        // this step's tables now describe the caller's buffers
-        sim->kept_rows[0] = cam_obs; sim->kept_rows[1] = tgt_obs; sim->kept_valid = true; sim->table_parity = 1 - par;
+        // the caller's buffers and the device now hold this call's rows
+        sim->kept_rows[0] = cam_obs; sim->kept_rows[1] = tgt_obs; sim->kept_valid = true;
+        if (two_buffers) sim->row_parity ^= 1;
         if (trace) {
             unsigned long long kept = 0;
             for (int i = 0; i < 2 * num_chunks; ++i) kept += sim->p_count[i];
-            fprintf(stderr, "step_host compact: enqueued %.2f ms, sizes known + copies enqueued %.2f, last stream arrived %.2f, expanded %.2f; kept %.1f MB of %.1f MB, %d threads, rows kept %d\n",
-                    t_enq, t_counts, t_last_stream, since(), kept * 16 / 1e6, (per_env[0] + per_env[1]) * (double)B / 1e6, sim->pool->size(), (int)use_kept);
+            fprintf(stderr, "step_host compact: enqueued %.2f ms, sizes known + copies enqueued %.2f, last stream arrived %.2f, expanded %.2f; kept %.1f MB of %.1f MB, %d threads, changes only %d\n",
+                    t_enq, t_counts, t_last_stream, since(), kept * 16 / 1e6, (per_env[0] + per_env[1]) * (double)B / 1e6, sim->pool->size(), (int)delta);
         }
         if ((flags & MATE_STEP_AUTO_RESET) && sim->refill_mode &&
             (sim->refill_mode == 2 || ++sim->steps_since_refill >= sim->refill_period))
             return launch_prepare(sim, nullptr);
         return MATE_OK;
     }
-    sim->kept_valid = false;   // the dense leg keeps no bitmaps
+    sim->kept_valid = false;   // (the dense leg runs when the compacted one cannot; the next compacted call writes everything)
     int k = 0;
     for (int begin = 0; begin < B; begin += chunk, ++k) {
         const int count = std::min(chunk, B - begin);
@@ -937,8 +953,8 @@ extern "C" int mate_b200_step_host(MateSim* sim, const float* cam_act, const flo
         if (nc) CUDA_TRY(cudaMemcpyAsync(sim->h_cam_act + (size_t)begin * nc * 2, cam_act + (size_t)begin * nc * 2, sizeof(float) * count * nc * 2, cudaMemcpyHostToDevice, s));
         CUDA_TRY(cudaMemcpyAsync(sim->h_tgt_act + (size_t)begin * nt * 2, tgt_act + (size_t)begin * nt * 2, sizeof(float) * count * nt * 2, cudaMemcpyHostToDevice, s));
         if (int rc = launch_range(sim, p, begin, count, s)) return rc;
-        if (nc) CUDA_TRY(cudaMemcpyAsync(cam_obs + (size_t)begin * nc * dc, sim->h_cam_obs + (size_t)begin * nc * dc, sizeof(float) * count * nc * dc, cudaMemcpyDeviceToHost, s));
-        CUDA_TRY(cudaMemcpyAsync(tgt_obs + (size_t)begin * nt * dt, sim->h_tgt_obs + (size_t)begin * nt * dt, sizeof(float) * count * nt * dt, cudaMemcpyDeviceToHost, s));
+        if (nc) CUDA_TRY(cudaMemcpyAsync(cam_obs + (size_t)begin * nc * dc, rows_now[0] + (size_t)begin * nc * dc, sizeof(float) * count * nc * dc, cudaMemcpyDeviceToHost, s));
+        CUDA_TRY(cudaMemcpyAsync(tgt_obs + (size_t)begin * nt * dt, rows_now[1] + (size_t)begin * nt * dt, sizeof(float) * count * nt * dt, cudaMemcpyDeviceToHost, s));
         CUDA_TRY(cudaMemcpyAsync(rewards + (size_t)begin * 2, sim->h_rewards + (size_t)begin * 2, sizeof(float) * count * 2, cudaMemcpyDeviceToHost, s));
         CUDA_TRY(cudaMemcpyAsync(done + begin, sim->h_done + begin, count, cudaMemcpyDeviceToHost, s));
     }

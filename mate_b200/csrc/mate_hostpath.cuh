@@ -62,11 +62,56 @@ __global__ void compact_chunks_kernel(const uint4* __restrict__ src, const long 
     }
 }
 
+// The same for the rows of a call against the rows of the previous call (both on the device): a 64-byte GROUP of four
+// chunks is kept when any of its bytes differs, so that the host rewrites whole cache lines and nothing else.
+__global__ void compact_changes_kernel(const uint4* __restrict__ src, const uint4* __restrict__ before, const long long nchunks,
+                                       uint4* __restrict__ dst, CompactEntry* __restrict__ table, unsigned int* __restrict__ counter) {
+    const int lane = threadIdx.x & 31;
+    const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+    const long long nblocks = (nchunks + kCompactBlock - 1) / kCompactBlock;
+    for (long long b = warp; b < nblocks; b += nwarps) {
+        uint4 v[kCompactWords];
+        uint32_t words[kCompactWords];
+        int total = 0;
+#pragma unroll
+        for (int it = 0; it < kCompactWords; ++it) {
+            const long long k = b * kCompactBlock + it * 32 + lane;
+            uint4 q = make_uint4(0u, 0u, 0u, 0u);
+            v[it] = q;
+            if (k < nchunks) { v[it] = src[k]; q = before[k]; }
+            uint32_t w = __ballot_sync(0xffffffffu, ((v[it].x ^ q.x) | (v[it].y ^ q.y) | (v[it].z ^ q.z) | (v[it].w ^ q.w)) != 0u);
+            w |= w >> 1; w |= w >> 2;                       // bit 4 g: any chunk of group g differs
+            words[it] = (w & 0x11111111u) * 0xFu;           // all four chunks of such a group
+            total += __popc(words[it]);
+        }
+        uint32_t base = 0;
+        if (lane == 0) base = atomicAdd(counter, (unsigned int)total);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        uint32_t run = base;
+#pragma unroll
+        for (int it = 0; it < kCompactWords; ++it) {
+            if ((words[it] >> lane) & 1u) dst[run + __popc(words[it] & ((1u << lane) - 1u))] = v[it];
+            run += __popc(words[it]);
+            if (lane == it) table[b].words[it] = words[it];
+        }
+        if (lane == 0) table[b].offset = base;
+    }
+}
+
+// the two stream sizes of a launch chunk, stored straight into pinned host memory
+__global__ void publish_counts_kernel(const unsigned int* __restrict__ counts, unsigned int* __restrict__ host_counts) {
+    if (threadIdx.x < 2) {
+        host_counts[threadIdx.x] = counts[threadIdx.x];
+        __threadfence_system();
+    }
+}
+
 // Expand blocks [b0, b1) of a region: dst = the caller's dense rows (16-byte chunks), src = the compact stream.
 // The next compact chunk is always loaded and kept only if the bit is set (no branch per chunk); the stream buffer is
-// one chunk longer than its content.  With `prev` (the table of the previous step into the same, unmodified buffers) a
-// group of four chunks (64 bytes) that was all-zero and is all-zero again is not written at all.
-inline void expand_blocks(const CompactEntry* table, const CompactEntry* prev, const __m128i* stream, __m128i* dst, long long nchunks,
+// one chunk longer than its content.  With `only_marked` (compact_changes_kernel: whole 64-byte groups that differ from
+// what the buffers hold) the unmarked chunks are left alone instead of being zeroed.
+inline void expand_blocks(const CompactEntry* table, const bool only_marked, const __m128i* stream, __m128i* dst, long long nchunks,
                           long long b0, long long b1, bool aligned) {
     const __m128i zero = _mm_setzero_si128();
     for (long long b = b0; b < b1; ++b) {
@@ -79,7 +124,7 @@ inline void expand_blocks(const CompactEntry* table, const CompactEntry* prev, c
             if (rem <= 0) break;
             const int n = rem < 32 ? (int)rem : 32;
             const uint32_t m = entry.words[w];
-            const uint32_t live = prev ? (m | prev[b].words[w]) : 0xffffffffu;   // chunks that hold or held something
+            const uint32_t live = only_marked ? m : 0xffffffffu;   // chunks to write
             if (live == 0u) continue;
             __m128i* dw = d + 32 * w;
             if (aligned) {
@@ -87,7 +132,7 @@ inline void expand_blocks(const CompactEntry* table, const CompactEntry* prev, c
                     for (int k = 0; k < n; ++k) _mm_stream_si128(dw + k, zero);
                 } else {
                     for (int k0 = 0; k0 < n; k0 += 4) {
-                        if (((live >> k0) & 0xFu) == 0u) continue;              // was zero, is zero
+                        if (((live >> k0) & 0xFu) == 0u) continue;              // the buffer holds these 64 bytes already
                         const int k1 = k0 + 4 < n ? k0 + 4 : n;
                         for (int k = k0; k < k1; ++k) {
                             const uint32_t bit = (m >> k) & 1u;
@@ -115,7 +160,7 @@ class ExpandPool {
 public:
     struct Work {
         const CompactEntry* table;
-        const CompactEntry* prev;                    // the previous step's table of the same blocks, or nullptr
+        bool only_marked;                            // the table marks what differs from the buffers' content
         const __m128i* stream;
         __m128i* dst;
         long long nchunks, b0, b1;
@@ -164,7 +209,7 @@ private:
                 queue_.pop_front();
             }
             if (w.ready) cudaEventSynchronize(w.ready);
-            expand_blocks(w.table, w.prev, w.stream, w.dst, w.nchunks, w.b0, w.b1, w.aligned);
+            expand_blocks(w.table, w.only_marked, w.stream, w.dst, w.nchunks, w.b0, w.b1, w.aligned);
             {
                 std::lock_guard<std::mutex> lock(mu_);
                 if (--pending_ == 0) cv_done_.notify_all();

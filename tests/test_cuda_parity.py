@@ -205,10 +205,10 @@ def test_cuda_vs_oracle(preset, B, steps, overrides):
 
 
 def test_step_host_rows_kept(monkeypatch):
-    """MATE_STEP_HOST_ROWS_KEPT: with the caller's buffers reused and untouched between calls the compacted leg skips what
-    was zero and is zero again; the buffers still equal the rows of the device-resident step, entries that turn zero
-    included (auto-resets every 4 steps change many of them).  A call without the flag rewrites everything: garbage the
-    caller left in the buffers is gone afterwards, and so is the history when the buffers change."""
+    """MATE_STEP_HOST_ROWS_KEPT: with the caller's buffers reused and untouched between calls only the 64-byte groups
+    that differ from the previous call's rows cross the link and are rewritten; the buffers still equal the rows of the
+    device-resident step (auto-resets every 4 steps change many entries at once).  A call without the flag rewrites
+    everything: garbage the caller left in the buffers is gone afterwards; so does a call with other buffers."""
     from mate_b200.config import flatten_config, read_config
 
     monkeypatch.setenv('MATE_B200_HOST_COMPACT', '1')
