@@ -403,12 +403,13 @@ def main():
         out = (torch.zeros((B, nc, sim.dc)).pin_memory(), torch.zeros((B, nt, sim.dt)).pin_memory(),
                torch.zeros((B, 2)).pin_memory(), torch.zeros(B, dtype=torch.uint8).pin_memory())
         # `out` is reused and never written by the host between the calls: MATE_STEP_HOST_ROWS_KEPT
+        kept = os.environ.get('MATE_B200_BENCH_ROWS_KEPT', '1') != '0'   # 0: measure the leg that rewrites every byte
         for k in range(3):
-            sim.step_host(host_cam_act[k % 2], host_tgt_act[k % 2], out, auto_reset=True, rows_kept=True)
+            sim.step_host(host_cam_act[k % 2], host_tgt_act[k % 2], out, auto_reset=True, rows_kept=kept)
         barrier()
         t0 = time.perf_counter()
         for k in range(args.e2e_steps):
-            sim.step_host(host_cam_act[k % 2], host_tgt_act[k % 2], out, auto_reset=True, rows_kept=True)
+            sim.step_host(host_cam_act[k % 2], host_tgt_act[k % 2], out, auto_reset=True, rows_kept=kept)
         e2e_s = time.perf_counter() - t0
         if world > 1:
             t = torch.tensor([e2e_s], device=device, dtype=torch.float64)

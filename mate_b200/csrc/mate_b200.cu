@@ -783,8 +783,10 @@ static int ensure_host_path(MateSim* sim) {
     threads = std::max(1, threads / sharers - 1);
     if (const char* v = getenv("MATE_B200_HOST_THREADS")) threads = std::max(1, atoi(v));
     threads = std::min(threads, 64);
-    sim->compact_mode = threads >= 14 ? 1 : 0;
-    if (const char* v = getenv("MATE_B200_HOST_COMPACT")) sim->compact_mode = v[0] == '1' ? 1 : 0;
+    // 1: every call takes the compacted leg (rebuilding all rows needs >= 14 threads to beat the dense copy); 2: only the calls
+    // that patch changes into kept rows do (5 threads are enough for those: 1.02e7 against 8.5e6), the others copy densely
+    sim->compact_mode = threads >= 14 ? 1 : (threads >= 5 ? 2 : 0);
+    if (const char* v = getenv("MATE_B200_HOST_COMPACT")) sim->compact_mode = v[0] == '1' ? 1 : (v[0] == '2' ? 2 : 0);
     if ((sizeof(float) * nc * sim->kernel.dc) % 16 || (sizeof(float) * nt * sim->kernel.dt) % 16) sim->compact_mode = 0;
     if (sim->compact_mode) {
         const size_t region_bytes[2] = {sizeof(float) * B * nc * sim->kernel.dc, sizeof(float) * B * nt * sim->kernel.dt};
@@ -844,8 +846,13 @@ extern "C" int mate_b200_step_host(MateSim* sim, const float* cam_act, const flo
     // ---- compacted device -> host leg (mate_hostpath.cuh): every launch chunk's rows are compacted on the device, the
     //      compact streams cross the link one after the other, host threads expand them into the caller's buffers
     const int num_chunks = (B + chunk - 1) / chunk;
-    const bool compact = sim->compact_mode && num_chunks <= MateSim::kMaxHostChunks && B % 4 == 0 &&
+    // MATE_STEP_HOST_ROWS_KEPT: the caller's row buffers still hold the rows of the previous call (same buffers, not
+    // modified since) and the device still holds them too: only the 64-byte groups that differ cross the link and are
+    // rewritten.  Otherwise the all-zero chunks are dropped and every byte of the caller's buffers is written.
+    const bool delta = two_buffers && (flags & MATE_STEP_HOST_ROWS_KEPT) && sim->kept_valid && sim->kept_rows[0] == cam_obs && sim->kept_rows[1] == tgt_obs;
+    const bool compact = (sim->compact_mode == 1 || (sim->compact_mode == 2 && delta)) && num_chunks <= MateSim::kMaxHostChunks && B % 4 == 0 &&
                          !((uintptr_t)cam_obs & 3) && !((uintptr_t)tgt_obs & 3);
+    sim->kept_valid = false;
     if (compact) {
         static const bool trace = getenv("MATE_B200_HOST_TRACE") != nullptr;
         const auto t_start = std::chrono::steady_clock::now();
@@ -855,11 +862,6 @@ extern "C" int mate_b200_step_host(MateSim* sim, const float* cam_act, const flo
         float* const host_rows[2] = {cam_obs, tgt_obs};
         float* const dev_rows[2] = {rows_now[0], rows_now[1]};
         std::vector<long long> table_base(2 * (num_chunks + 1), 0);
-        // MATE_STEP_HOST_ROWS_KEPT: the caller's row buffers still hold the rows of the previous call (same buffers, not
-        // modified since) and the device still holds them too: only the 64-byte groups that differ cross the link and are
-        // rewritten.  Otherwise the all-zero chunks are dropped and every byte of the caller's buffers is written.
-        const bool delta = two_buffers && (flags & MATE_STEP_HOST_ROWS_KEPT) && sim->kept_valid && sim->kept_rows[0] == cam_obs && sim->kept_rows[1] == tgt_obs;
-        sim->kept_valid = false;
         CUDA_TRY(cudaMemsetAsync(sim->d_count, 0, sizeof(unsigned int) * MateSim::kMaxHostChunks * 2, sim->hstreams[0]));
         CUDA_TRY(cudaEventRecord(sim->hevents[1], sim->hstreams[0]));
         for (int i = 1; i < MateSim::kHostStreams; ++i) CUDA_TRY(cudaStreamWaitEvent(sim->hstreams[i], sim->hevents[1], 0));
@@ -945,7 +947,6 @@ extern "C" int mate_b200_step_host(MateSim* sim, const float* cam_act, const flo
             return launch_prepare(sim, nullptr);
         return MATE_OK;
     }
-    sim->kept_valid = false;   // (the dense leg runs when the compacted one cannot; the next compacted call writes everything)
     int k = 0;
     for (int begin = 0; begin < B; begin += chunk, ++k) {
         const int count = std::min(chunk, B - begin);
@@ -959,6 +960,9 @@ extern "C" int mate_b200_step_host(MateSim* sim, const float* cam_act, const flo
         CUDA_TRY(cudaMemcpyAsync(done + begin, sim->h_done + begin, count, cudaMemcpyDeviceToHost, s));
     }
     for (int i = 0; i < MateSim::kHostStreams; ++i) CUDA_TRY(cudaStreamSynchronize(sim->hstreams[i]));
+    if (two_buffers) {   // the caller's buffers and the device hold this call's rows: the next call may send changes only
+        sim->kept_rows[0] = cam_obs; sim->kept_rows[1] = tgt_obs; sim->kept_valid = true; sim->row_parity ^= 1;
+    }
     // the prepared episodes are refilled on the side stream like on the device path
     if ((flags & MATE_STEP_AUTO_RESET) && sim->refill_mode &&
         (sim->refill_mode == 2 || ++sim->steps_since_refill >= sim->refill_period))

@@ -108,12 +108,15 @@ __global__ void publish_counts_kernel(const unsigned int* __restrict__ counts, u
 }
 
 // Expand blocks [b0, b1) of a region: dst = the caller's dense rows (16-byte chunks), src = the compact stream.
-// The next compact chunk is always loaded and kept only if the bit is set (no branch per chunk); the stream buffer is
-// one chunk longer than its content.  With `only_marked` (compact_changes_kernel: whole 64-byte groups that differ from
-// what the buffers hold) the unmarked chunks are left alone instead of being zeroed.
-inline void expand_blocks(const CompactEntry* table, const bool only_marked, const __m128i* stream, __m128i* dst, long long nchunks,
-                          long long b0, long long b1, bool aligned) {
+// A group of four chunks that is all-zero or all-kept is written without looking at its chunks; in a mixed group the next
+// compact chunk is always loaded and kept only if its bit is set (the stream buffer is some chunks longer than its content).
+// With `only_marked` (compact_changes_kernel: whole 64-byte groups that differ from what the buffers hold) the unmarked
+// groups are left alone instead of being zeroed.
+template <bool ALIGNED>
+inline void expand_blocks_impl(const CompactEntry* table, const bool only_marked, const __m128i* stream, __m128i* dst, long long nchunks,
+                               long long b0, long long b1) {
     const __m128i zero = _mm_setzero_si128();
+    auto put = [](__m128i* q, const __m128i x) { if (ALIGNED) _mm_stream_si128(q, x); else _mm_storeu_si128(q, x); };
     for (long long b = b0; b < b1; ++b) {
         const CompactEntry& entry = table[b];
         const __m128i* s = stream + entry.offset;
@@ -124,35 +127,45 @@ inline void expand_blocks(const CompactEntry* table, const bool only_marked, con
             if (rem <= 0) break;
             const int n = rem < 32 ? (int)rem : 32;
             const uint32_t m = entry.words[w];
-            const uint32_t live = only_marked ? m : 0xffffffffu;   // chunks to write
-            if (live == 0u) continue;
             __m128i* dw = d + 32 * w;
-            if (aligned) {
-                if (m == 0u && live == 0xffffffffu) {
-                    for (int k = 0; k < n; ++k) _mm_stream_si128(dw + k, zero);
-                } else {
-                    for (int k0 = 0; k0 < n; k0 += 4) {
-                        if (((live >> k0) & 0xFu) == 0u) continue;              // the buffer holds these 64 bytes already
-                        const int k1 = k0 + 4 < n ? k0 + 4 : n;
-                        for (int k = k0; k < k1; ++k) {
-                            const uint32_t bit = (m >> k) & 1u;
-                            const __m128i x = _mm_and_si128(_mm_loadu_si128(s), _mm_set1_epi32(-(int)bit));
-                            s += bit;
-                            _mm_stream_si128(dw + k, x);
-                        }
-                    }
+            if (only_marked) {
+                // whole groups of four chunks (the region is a whole number of groups): one pass over the marked groups
+                uint32_t g = m & 0x11111111u;
+                while (g) {
+                    const int k0 = __builtin_ctz(g);
+                    g &= g - 1u;
+                    const __m128i x0 = _mm_loadu_si128(s), x1 = _mm_loadu_si128(s + 1), x2 = _mm_loadu_si128(s + 2), x3 = _mm_loadu_si128(s + 3);
+                    s += 4;
+                    put(dw + k0, x0); put(dw + k0 + 1, x1); put(dw + k0 + 2, x2); put(dw + k0 + 3, x3);
                 }
-            } else {
-                for (int k = 0; k < n; ++k) {
-                    const uint32_t bit = (m >> k) & 1u;
-                    const __m128i x = _mm_and_si128(_mm_loadu_si128(s), _mm_set1_epi32(-(int)bit));
-                    s += bit;
-                    if ((live >> k) & 1u) _mm_storeu_si128(dw + k, x);
+                continue;
+            }
+            for (int k0 = 0; k0 < n; k0 += 4) {
+                const uint32_t nib = (m >> k0) & 0xFu;
+                const int k1 = k0 + 4 < n ? k0 + 4 : n;
+                if (nib == 0u) {
+                    for (int k = k0; k < k1; ++k) put(dw + k, zero);
+                } else if (nib == 0xFu && k1 == k0 + 4) {
+                    const __m128i x0 = _mm_loadu_si128(s), x1 = _mm_loadu_si128(s + 1), x2 = _mm_loadu_si128(s + 2), x3 = _mm_loadu_si128(s + 3);
+                    s += 4;
+                    put(dw + k0, x0); put(dw + k0 + 1, x1); put(dw + k0 + 2, x2); put(dw + k0 + 3, x3);
+                } else {
+                    for (int k = k0; k < k1; ++k) {   // the next compact chunk is loaded in any case and kept only if the bit is set
+                        const uint32_t bit = (m >> k) & 1u;
+                        const __m128i x = _mm_and_si128(_mm_loadu_si128(s), _mm_set1_epi32(-(int)bit));
+                        s += bit;
+                        put(dw + k, x);
+                    }
                 }
             }
         }
     }
     _mm_sfence();
+}
+inline void expand_blocks(const CompactEntry* table, const bool only_marked, const __m128i* stream, __m128i* dst, long long nchunks,
+                          long long b0, long long b1, bool aligned) {
+    if (aligned) expand_blocks_impl<true>(table, only_marked, stream, dst, nchunks, b0, b1);
+    else expand_blocks_impl<false>(table, only_marked, stream, dst, nchunks, b0, b1);
 }
 
 // A fixed pool of host threads that expand pieces of the compact stream.

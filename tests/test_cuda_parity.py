@@ -204,14 +204,15 @@ def test_cuda_vs_oracle(preset, B, steps, overrides):
     np.testing.assert_allclose(stats[:6], rstats[:6], rtol=1e-4, atol=1e-3)
 
 
-def test_step_host_rows_kept(monkeypatch):
+@pytest.mark.parametrize('mode', ['1', '2'])   # 2: only the calls that patch changes take the compacted leg, the others copy densely
+def test_step_host_rows_kept(mode, monkeypatch):
     """MATE_STEP_HOST_ROWS_KEPT: with the caller's buffers reused and untouched between calls only the 64-byte groups
     that differ from the previous call's rows cross the link and are rewritten; the buffers still equal the rows of the
     device-resident step (auto-resets every 4 steps change many entries at once).  A call without the flag rewrites
     everything: garbage the caller left in the buffers is gone afterwards; so does a call with other buffers."""
     from mate_b200.config import flatten_config, read_config
 
-    monkeypatch.setenv('MATE_B200_HOST_COMPACT', '1')
+    monkeypatch.setenv('MATE_B200_HOST_COMPACT', mode)
     monkeypatch.setenv('MATE_B200_REFILL', 'sync')
     cfg = flatten_config(read_config('MATE-4v8-9.yaml', max_episode_steps=4))
     B = 2048
