@@ -311,6 +311,12 @@ int mate_b200_decode_actions(const int64_t* index, const float* table, int32_t t
 /* Number of kernels this handle has launched since creation (bench bookkeeping). */
 int64_t mate_b200_launch_count(const MateSim* sim);
 
+/* What the last mate_b200_step_host call on this handle did on its device -> host leg (bench bookkeeping): *leg = 0 the rows
+ * were copied densely, 1 their non-zero 16-byte chunks crossed the link and the rows were rebuilt in the caller's buffers,
+ * 2 only the 64-byte groups that differ from the previous call's rows crossed and were patched in (MATE_STEP_HOST_ROWS_KEPT);
+ * *row_bytes_on_link = bytes of observation rows (and their bitmaps) that crossed the link in that call. */
+int mate_b200_host_leg_info(const MateSim* sim, int32_t* leg, uint64_t* row_bytes_on_link);
+
 #ifdef __cplusplus
 }
 #endif

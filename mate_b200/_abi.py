@@ -185,6 +185,8 @@ def load_library():
     lib.mate_b200_episode_stats.argtypes = [void_p, void_p, ctypes.c_int32, void_p]
     lib.mate_b200_launch_count.argtypes = [void_p]
     lib.mate_b200_launch_count.restype = ctypes.c_int64
+    lib.mate_b200_host_leg_info.argtypes = [void_p, ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_uint64)]
+    lib.mate_b200_host_leg_info.restype = ctypes.c_int
     lib.mate_b200_transform_observations.argtypes = [void_p, void_p, void_p, c_int32_p, ctypes.c_int32, void_p, void_p, void_p]
     lib.mate_b200_set_observation_ops.argtypes = [void_p, c_int32_p, ctypes.c_int32, void_p, void_p]
     lib.mate_b200_decode_actions.argtypes = [void_p, void_p, ctypes.c_int32, void_p, ctypes.c_int64, void_p]
@@ -206,7 +208,7 @@ EXPORTED_SYMBOLS = [
     'mate_b200_last_error', 'mate_b200_abi_version', 'mate_b200_create', 'mate_b200_destroy',
     'mate_b200_obs_dims', 'mate_b200_reset', 'mate_b200_seed', 'mate_b200_step', 'mate_b200_observe',
     'mate_b200_step_host', 'mate_b200_get_state', 'mate_b200_set_state',
-    'mate_b200_episode_stats', 'mate_b200_launch_count', 'mate_b200_transform_observations', 'mate_b200_set_observation_ops',
+    'mate_b200_episode_stats', 'mate_b200_launch_count', 'mate_b200_host_leg_info', 'mate_b200_transform_observations', 'mate_b200_set_observation_ops',
     'mate_b200_decode_actions', 'mate_b200_auxiliary_terms', 'mate_b200_fov_range', 'mate_b200_soft_coverage', 'mate_b200_greedy_target_actions', 'mate_b200_greedy_camera_actions',
 ]
 

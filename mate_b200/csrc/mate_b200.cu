@@ -218,6 +218,8 @@ struct MateSim {
     int row_parity = 0;
     const float* kept_rows[2] = {nullptr, nullptr};  // the caller's buffers that hold the previous call's rows
     bool kept_valid = false;
+    int last_leg = 0;                                // device -> host leg of the last step_host call (mate_b200_host_leg_info)
+    unsigned long long last_link_bytes = 0;
     unsigned int* p_count = nullptr;
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t e_counts[kMaxHostChunks] = {}, e_stream[kMaxHostChunks] = {}, e_tables[kMaxHostChunks] = {};
@@ -435,6 +437,12 @@ extern "C" int mate_b200_fov_range(MateSim* sim, const int32_t* env, const int32
 }
 
 extern "C" int64_t mate_b200_launch_count(const MateSim* sim) { return sim ? sim->launches : 0; }
+extern "C" int mate_b200_host_leg_info(const MateSim* sim, int32_t* leg, uint64_t* row_bytes_on_link) {
+    if (!sim) return fail(MATE_EINVAL, "null handle");
+    if (leg) *leg = sim->last_leg;
+    if (row_bytes_on_link) *row_bytes_on_link = sim->last_link_bytes;
+    return MATE_OK;
+}
 
 extern "C" int mate_b200_transform_observations(MateSim* sim, float* cam_obs, float* tgt_obs, const int32_t* ops,
                                                 int32_t num_ops, const float* cam_affine, const float* tgt_affine,
@@ -933,6 +941,12 @@ extern "C" int mate_b200_step_host(MateSim* sim, const float* cam_act, const flo
         t_last_stream = since();
         sim->pool->wait();
         for (int i = 0; i < MateSim::kHostStreams; ++i) CUDA_TRY(cudaStreamSynchronize(sim->hstreams[i]));
+        {
+            unsigned long long link = 0;
+            for (int i = 0; i < 2 * num_chunks; ++i) link += (unsigned long long)sim->p_count[i] * 16ull;
+            link += (unsigned long long)(table_base[2 * num_chunks] + table_base[2 * num_chunks + 1]) * sizeof(CompactEntry);
+            sim->last_leg = delta ? 2 : 1; sim->last_link_bytes = link;
+        }
         // the caller's buffers and the device now hold this call's rows
         sim->kept_rows[0] = cam_obs; sim->kept_rows[1] = tgt_obs; sim->kept_valid = true;
         if (two_buffers) sim->row_parity ^= 1;
@@ -960,6 +974,7 @@ extern "C" int mate_b200_step_host(MateSim* sim, const float* cam_act, const flo
         CUDA_TRY(cudaMemcpyAsync(done + begin, sim->h_done + begin, count, cudaMemcpyDeviceToHost, s));
     }
     for (int i = 0; i < MateSim::kHostStreams; ++i) CUDA_TRY(cudaStreamSynchronize(sim->hstreams[i]));
+    sim->last_leg = 0; sim->last_link_bytes = (unsigned long long)B * ((size_t)nc * dc + (size_t)nt * dt) * sizeof(float);
     if (two_buffers) {   // the caller's buffers and the device hold this call's rows: the next call may send changes only
         sim->kept_rows[0] = cam_obs; sim->kept_rows[1] = tgt_obs; sim->kept_valid = true; sim->row_parity ^= 1;
     }

@@ -301,6 +301,13 @@ class BatchedSim:
                                                               self._stream()))
         return self._stats
 
+    def host_leg_info(self):
+        """(leg, row bytes on the link) of the last `step_host` call: 0 dense copy, 1 rows rebuilt from their non-zero
+        chunks, 2 changes patched into kept rows (mate_b200_host_leg_info)."""
+        leg, link = ctypes.c_int32(0), ctypes.c_uint64(0)
+        _check(self.lib, self.lib.mate_b200_host_leg_info(self.handle, ctypes.byref(leg), ctypes.byref(link)))
+        return int(leg.value), int(link.value)
+
     @property
     def launch_count(self):
         return int(self.lib.mate_b200_launch_count(self.handle))
