@@ -1,12 +1,18 @@
 // mate_hostpath.cuh -- the device -> host leg of mate_b200_step_host.
 //
-// The observation rows of a step are 6.2 KB per environment (MATE-4v8-9) and 55 % of their 16-byte chunks are zero
-// (entities the observer does not see).  The plain path copies them densely and is bound by the PCIe link (407 MB per
-// step of 65 536 environments at 57 GB/s = 7.1 ms).  Here the rows are COMPACTED on the device (zero chunks dropped, one
-// bit per chunk), the compact stream crosses the link, and a pool of host threads EXPANDS it into the caller's buffers
-// with streaming stores while the next pieces are still in flight.  Lossless: the caller sees exactly the bytes of the
-// dense copy (tests/test_cuda_parity.py::test_step_host_*).  What bounds it then is the host's memory system (measured on
-// the B200 box's 16 host threads, scratch/host_expand_probe.cu: 80 GB/s of expanded rows while the DMA runs at 40 GB/s).
+// The observation rows of a step are 6.2 KB per environment (MATE-4v8-9); the plain leg copies them densely and is bound
+// by the PCIe link (407 MB per step of 65 536 environments at 57 GB/s = 7.1 ms).  Two lossless alternatives, both built
+// from the same pieces -- a kernel that keeps some of the rows' 16-byte chunks and records which (one bit per chunk, one
+// table entry per 256 chunks), the kept chunks crossing the link as one stream per launch chunk, and a pool of host
+// threads that put them where they belong in the caller's buffers while later streams are still in flight:
+//   * compact_chunks_kernel keeps the chunks that are not all-zero (55 % are: entities the observer does not see); the
+//     host threads rebuild every byte of the rows (zeros included);
+//   * compact_changes_kernel, when the caller's buffers still hold the previous call's rows (MATE_STEP_HOST_ROWS_KEPT) and
+//     the device does too, keeps the 64-byte groups that differ from them (45 % under random actions); the host threads
+//     rewrite exactly those cache lines.
+// The caller sees the bytes of the dense copy either way (tests/test_cuda_parity.py::test_step_host_*).  What bounds the
+// leg then is the host's memory system and the number of host threads (profiles/r2v_hostpath.md; first probe:
+// profiles/tools/host_expand_probe.cu).
 #pragma once
 
 #include <cuda_runtime.h>
