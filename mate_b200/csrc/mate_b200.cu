@@ -792,8 +792,10 @@ static int ensure_host_path(MateSim* sim) {
     if (const char* v = getenv("MATE_B200_HOST_THREADS")) threads = std::max(1, atoi(v));
     threads = std::min(threads, 64);
     // 1: every call takes the compacted leg (rebuilding all rows needs >= 14 threads to beat the dense copy); 2: only the calls
-    // that patch changes into kept rows do (5 threads are enough for those: 1.02e7 against 8.5e6), the others copy densely
-    sim->compact_mode = threads >= 14 ? 1 : (threads >= 5 ? 2 : 0);
+    // that patch changes into kept rows do (5 threads are enough for those: 1.02e7 against 8.5e6; 3 when four or more
+    // processes share the host, whose memory system then bounds the dense copies: 8 x B200 1.74e7 against 1.49e7), the others
+    // copy densely
+    sim->compact_mode = threads >= 14 ? 1 : ((threads >= 5 || (threads >= 3 && sharers >= 4)) ? 2 : 0);
     if (const char* v = getenv("MATE_B200_HOST_COMPACT")) sim->compact_mode = v[0] == '1' ? 1 : (v[0] == '2' ? 2 : 0);
     if ((sizeof(float) * nc * sim->kernel.dc) % 16 || (sizeof(float) * nt * sim->kernel.dt) % 16) sim->compact_mode = 0;
     if (sim->compact_mode) {
