@@ -244,6 +244,41 @@ def test_step_host_rows_kept(mode, monkeypatch):
         assert torch.equal(rew.cpu(), out[2]) and torch.equal(done.cpu(), out[3]), k
 
 
+@pytest.mark.parametrize('mode', ['0', '1', '2'])
+@pytest.mark.parametrize('preset', ['MATE-Navigation.yaml', 'MATE-8v8-9.yaml', 'MATE-4v2-9.yaml', 'MATE-4v8-0.yaml'])
+def test_step_host_other_shapes(preset, mode, monkeypatch):
+    """Every device -> host leg of mate_b200_step_host on the other BASELINE shapes (no cameras; 8 cameras; rows that are
+    not whole 16-byte chunks and therefore always copied densely; no obstacles): the caller's buffers equal the rows of
+    the device-resident step, with and without MATE_STEP_HOST_ROWS_KEPT."""
+    from mate_b200.config import flatten_config, read_config
+
+    monkeypatch.setenv('MATE_B200_HOST_COMPACT', mode)
+    monkeypatch.setenv('MATE_B200_REFILL', 'sync')
+    cfg = flatten_config(read_config(preset, max_episode_steps=5))
+    nc, nt = cfg['num_cameras'], cfg['num_targets']
+    B = 1536
+    a, b = _sim(cfg, B), _sim(cfg, B)
+    a.reset(seed=3)
+    b.reset(seed=3)
+    out = (torch.zeros((B, max(nc, 1), a.dc)).pin_memory(), torch.zeros((B, nt, a.dt)).pin_memory(),
+           torch.zeros((B, 2)).pin_memory(), torch.zeros(B, dtype=torch.uint8).pin_memory())
+    rng = np.random.RandomState(0)
+    legs = set()
+    for k in range(8):
+        cam_act = torch.from_numpy((rng.uniform(-1, 1, (B, max(nc, 1), 2)) * [5.0, 2.5]).astype(np.float32)).pin_memory()
+        tgt_act = torch.from_numpy((rng.uniform(-1, 1, (B, nt, 2)) * 20.0).astype(np.float32)).pin_memory()
+        (cam, tgt), rew, done = a.step(cam_act.cuda(), tgt_act.cuda(), auto_reset=True)
+        b.step_host(cam_act, tgt_act, out, auto_reset=True, rows_kept=(k != 3))
+        torch.cuda.synchronize()
+        legs.add(b.host_leg_info()[0])
+        if nc:
+            assert torch.equal(cam.cpu(), out[0]), k
+        assert torch.equal(tgt.cpu(), out[1]) and torch.equal(rew.cpu(), out[2]) and torch.equal(done.cpu(), out[3]), k
+    whole_chunks = (4 * nc * a.dc) % 16 == 0 and (4 * nt * a.dt) % 16 == 0
+    expected = {'0': {0}, '1': {1, 2}, '2': {0, 2}}[mode] if whole_chunks else {0}
+    assert legs == expected, legs
+
+
 @pytest.mark.parametrize('compact', ['0', '1'])
 def test_step_host_matches_device_step(compact, monkeypatch):
     """Both device -> host legs of mate_b200_step_host (dense copy; compacted rows expanded by host threads,
