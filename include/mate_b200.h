@@ -187,7 +187,12 @@ int mate_b200_observe(MateSim* sim, float* cam_obs, float* tgt_obs,
  * already queued on the legacy default stream (and on blocking streams, e.g. torch's default
  * stream); a caller that queued reset / step / set_state work on a NON-BLOCKING stream of its
  * own synchronises that stream before this call.  Auto-resets adopt the prepared next
- * episodes exactly like mate_b200_step (the refill runs on the side stream). */
+ * episodes exactly like mate_b200_step (the refill runs on the side stream).
+ * The observation rows reach cam_obs / tgt_obs as a dense copy or, depending on the host threads the process has
+ * (INTEGRATION.md), compacted: non-zero 16-byte chunks only, or -- with MATE_STEP_HOST_ROWS_KEPT -- only the 64-byte
+ * groups that differ from the previous call's rows; host threads of the library put them in place before the call
+ * returns.  The buffers hold the same bytes in every case.  Row buffers must be 4-byte aligned (16-byte aligned for full
+ * speed). */
 int mate_b200_step_host(MateSim* sim, const float* cam_act, const float* tgt_act,
                         float* cam_obs, float* tgt_obs, float* rewards, uint8_t* done,
                         uint32_t flags);
